@@ -1,0 +1,120 @@
+/* spvipes_b200 — C ABI of the B200-native spVIPES training hot path.
+ *
+ * The reference (nrclaudio/spVIPES) is pure Python/PyTorch and has no FFI of its own; these entry points are what a
+ * binding for its per-minibatch path (spVIPESmodule inference -> generative -> loss, forward and backward) binds instead
+ * of the ATen library calls listed in SURVEY.md section 2.2.  Each function cites the reference code it replaces.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless said otherwise; matrices are row-major with an explicit leading
+ * dimension in elements; `stream` is a cudaStream_t passed as void*; functions only enqueue work (no allocation, no
+ * synchronisation, CUDA-graph capturable) and return SPV_OK (0) or a negative error code.  `rows` arguments are optional
+ * row-gather indices into a device-resident count matrix (the minibatch), NULL meaning rows 0..B-1.
+ */
+#ifndef SPVIPES_B200_H
+#define SPVIPES_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPV_ABI_VERSION 1
+
+/* error codes */
+#define SPV_OK 0
+#define SPV_ERR_ARG -1
+#define SPV_ERR_LAUNCH -2
+#define SPV_ERR_ARCH -3
+
+/* operand source kinds (srcA / srcB / src arguments) */
+#define SPV_SRC_F32_ 0       /* float values                                                       */
+#define SPV_SRC_U16_LOG1P_ 1 /* uint16 counts, consumed as log(1 + x)  (module/spVIPESmodule.py:432-433) */
+#define SPV_SRC_F32_LOG1P_ 2 /* float counts,  consumed as log(1 + x)                                */
+
+/* PoE modes (module/spVIPESmodule.py:484-509) and partner codes */
+#define SPV_POE_LABEL_ 0
+#define SPV_POE_PAIRED_ 1
+#define SPV_POE_CLUSTER_ 2
+
+int spv_abi_version(void);
+/* 0 if device `dev` is sm_100 (B200), SPV_ERR_ARCH otherwise, SPV_ERR_LAUNCH if no CUDA device. Host-side query. */
+int spv_arch_check(int dev);
+
+/* C[b] (+)= act(op(A[b]) op(B[b]) + bias[b]) in fp32, batched over `batch` (element strides sA/sB/sC/sBias), optional
+ * split-K (`ws` holds batch*splits*M*N floats).  transA: A stored [K][M]; transB: B stored [N][K] (y = x W^T).
+ * Replaces nn.Linear forward/backward GEMMs: nn/networks.py:119-125 (Encoder), :314-325 (decoder, scvi FCLayers). */
+int spv_gemm(int srcA, int transA, int srcB, int transB, const void* A, long long lda, const int* rowsA, const void* B,
+             long long ldb, const int* rowsB, float* C, long long ldc, int M, int N, int K, int batch, long long sA,
+             long long sB, long long sC, const float* bias, long long sBias, int relu, int accumulate, int splits, float* ws,
+             void* stream);
+
+/* lib[b] = log(sum_g log1p(x[b,g]))   module/spVIPESmodule.py:433-435 */
+int spv_library_size(int src, const void* X, long long ldx, const int* rows, int B, int G, float* lib, void* stream);
+
+/* h *= mask (explicit multipliers) or a Philox keep-mask scaled by 1/(1-p)   nn/networks.py:121 */
+int spv_dropout(float* h, long long ld, int B, int C, const float* mask, long long ldm, float p, unsigned long long seed,
+                unsigned int stream_id, const int* step, void* stream);
+/* dy <- y > 0 ? dy * (mask ? mask : scale) : 0   (ReLU + dropout backward) */
+int spv_relu_bwd(float* dy, long long lddy, const float* y, long long ldy, int B, int C, const float* mask, long long ldm,
+                 float scale, void* stream);
+
+/* BatchNorm1d over the minibatch (training: batch statistics + running-stat update; eval: running statistics).
+ * nn/networks.py:74-83 (eps 1e-5, momentum 0.1) and scvi FCLayers (eps 1e-3, momentum 0.01). */
+int spv_bn_fwd(const float* x, long long ldx, float* y, long long ldy, int B, int C, const float* gamma, const float* beta,
+               float eps, float momentum, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+               int training, int relu, void* stream);
+int spv_bn_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* y_relu, long long ldy, float* dx,
+               long long lddx, int B, int C, const float* gamma, const float* save_mean, const float* save_invstd,
+               float* dgamma, float* dbeta, void* stream);
+int spv_colsum(const float* x, long long ldx, int B, int C, float* out, void* stream);
+
+/* label-rank pairing, bit-exact integer contract   module/spVIPESmodule.py:599-659, 685-701, 297-326 */
+int spv_pair_label(const int* la, const int* lb, int Ba, int Bb, int* pa, int* pb, void* stream);
+/* sub = T[idx0][:, idx1]   :474-482 ;  row/col argmax (ties -> first)   :526-527 */
+int spv_plan_gather(const float* T, long long ldT, const int* idx0, const int* idx1, int B0, int B1, float* sub, void* stream);
+int spv_plan_argmax(const float* sub, int B0, int B1, int* row_arg, int* col_arg, void* stream);
+/* masked row-normalised sub-plans of the cluster mode   :207-219 */
+int spv_plan_cluster_norm(const float* sub, int B0, int B1, const int* l0, const int* l1, float* P1, float* P2, void* stream);
+
+/* PoE merge + reparameterised sampling + KL terms, both groups in one launch.
+ * ptrs per group (SPV_POE_FWD_NPTR): own_loc, own_lv, oth_loc, oth_lv, stats, partner, eps_p, eps_q, zpriv, poe_loc,
+ * poe_lv, poe_scale, zpoe, klp, klq, zz ;  lds per group: ld_own, ld_oth, ld_stats, ld_zz.
+ * module/spVIPESmodule.py:282-379, 511-581, 583-718, 841-868; nn/networks.py:125-127. */
+#define SPV_POE_FWD_NPTR 16
+int spv_poe_fwd(int mode, int S, int P, int B0, int B1, const void* const* ptrs0, const long long* lds0,
+                const void* const* ptrs1, const long long* lds1, unsigned long long seed, const int* step, void* stream);
+/* ptrs per group (SPV_POE_BWD_NPTR): own_loc, own_lv, oth_loc, oth_lv, stats, partner, eps_p, eps_q, dzz, dstats, g_own,
+ * g_contrib, out ;  lds per group: ld_own, ld_oth, ld_stats, ld_dzz, ld_dstats, ld_out */
+#define SPV_POE_BWD_NPTR 13
+int spv_poe_bwd(int mode, int S, int P, int B0, int B1, const void* const* ptrs0, const long long* lds0,
+                const void* const* ptrs1, const long long* lds1, unsigned long long seed, const int* step,
+                const float* kl_weight, float inv_batch, void* stream);
+/* out[0] = loss (:886-893), out[1..4] = mean KL private0, poe0, private1, poe1 (:870-875), out[5..6] = mean rec0, rec1 */
+int spv_loss(const float* rec0, const float* rec1, const float* klp0, const float* klq0, const float* klp1, const float* klq1,
+             int B, const float* kl_weight, float* out, void* stream);
+
+/* decoder: closed-form per-gene BatchNorm fold + NB constants.
+ * ptrs (18): Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, cov_part, wfold, genec,
+ * zmean, zcov.   nn/networks.py:314-320, scvi FCLayers; module/spVIPESmodule.py:758 */
+#define SPV_DEC_GENEC_ROWS 12
+int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, int S, int training, float eps, float momentum,
+                 void* stream);
+/* fused decoder + NB-mixture likelihood sweeps.  ptrs (SPV_DEC_NPTR): X, rows, amix, wfold, wm, bm, genec, lib, part_stats,
+ * rowc, pi, part_nb, dyp, dys, dpi, colpart, rec.   nn/networks.py:314-325; module/spVIPESmodule.py:759, 817-824 */
+#define SPV_DEC_NPTR 17
+int spv_dec_nb_fwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P, int S,
+                   void* stream);
+int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P, int S,
+                   float scale, float* colsum, void* stream);
+/* ptrs (18): Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm, wv, wmx */
+int spv_dec_gene_bwd(const void* const* ptrs, int B, int G, int P, int S, void* stream);
+int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* v1, const float* M,
+                        const float* zz, long long ld_zz, const float* zmean, float* dzz, int B, int P, int S, void* stream);
+
+/* Adam with the scvi TrainingPlan defaults restated by the caller (training_mixin.py:93-111); *step is a device counter */
+int spv_adam_tick(int* step, void* stream);
+int spv_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
+             float grad_scale, const int* step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPVIPES_B200_H */

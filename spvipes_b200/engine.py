@@ -1,0 +1,532 @@
+"""Host-side orchestration of one spVIPES training step on a B200: flat parameter layout, workspaces and the
+sequence of C-ABI kernel launches for inference -> generative -> loss, their backward and Adam.
+
+Mirrors reference module/spVIPESmodule.py:425-472 (inference), :720-771 (generative), :809-899 (loss) and
+nn/networks.py (Encoder, LinearDecoderSPVIPE); the optimiser restates scvi TrainingPlan's defaults
+(model/base/training_mixin.py:93-111: Adam lr 1e-3, eps 0.01, weight_decay 1e-6).
+
+torch is used for device memory and streams only; every arithmetic step is a launch into libspvipes_b200.so.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+HD = 256  # decoder hidden width is fixed (reference nn/networks.py:194, quirk Q8)
+ENC_BN_EPS, ENC_BN_MOM = 1e-5, 0.1
+DEC_BN_EPS, DEC_BN_MOM = 1e-3, 0.01
+
+
+# ------------------------------------------------------------------------------------------------
+# flat parameter layout (names follow the reference state_dict so checkpoints load 1:1)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Dims:
+    genes: Tuple[int, int]
+    n_hidden: int = 128
+    n_shared: int = 25
+    n_private: int = 10
+
+    @property
+    def KZ(self):
+        return self.n_shared + self.n_private
+
+    @property
+    def KMIX(self):
+        return HD + self.KZ
+
+    @property
+    def NST(self):
+        return 2 * self.n_shared + 2 * self.n_private
+
+
+def _group_param_entries(g: int, G: int, d: Dims):
+    """[(fused name, shape, [(state_dict name, row slice / index)])] in flat order for group g."""
+    H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
+    ep, es, dec = f"encoder_{g}_private", f"encoder_{g}_shared", f"decoder_{g}"
+    fl = "fc_layers.Layer 0"
+    return [
+        ("W1", (2 * H, G), [(f"{ep}.fc1.weight", (0, H)), (f"{es}.fc1.weight", (H, 2 * H))]),
+        ("b1", (2 * H,), [(f"{ep}.fc1.bias", (0, H)), (f"{es}.fc1.bias", (H, 2 * H))]),
+        ("W2", (2 * H, H), [(f"{ep}.fc2.weight", (0, H)), (f"{es}.fc2.weight", (H, 2 * H))]),
+        ("b2", (2 * H,), [(f"{ep}.fc2.bias", (0, H)), (f"{es}.fc2.bias", (H, 2 * H))]),
+        ("Whp", (2 * P, H), [(f"{ep}.mu_encoder.0.weight", (0, P)), (f"{ep}.lvar_encoder.0.weight", (P, 2 * P))]),
+        ("Whs", (2 * S, H), [(f"{es}.mu_encoder.0.weight", (0, S)), (f"{es}.lvar_encoder.0.weight", (S, 2 * S))]),
+        ("bhd", (NST,), [(f"{ep}.mu_encoder.0.bias", (0, P)), (f"{ep}.lvar_encoder.0.bias", (P, 2 * P)),
+                         (f"{es}.mu_encoder.0.bias", (2 * P, 2 * P + S)), (f"{es}.lvar_encoder.0.bias", (2 * P + S, NST))]),
+        ("ghd", (NST,), [(f"{ep}.mu_encoder.1.weight", (0, P)), (f"{ep}.lvar_encoder.1.weight", (P, 2 * P)),
+                         (f"{es}.mu_encoder.1.weight", (2 * P, 2 * P + S)), (f"{es}.lvar_encoder.1.weight", (2 * P + S, NST))]),
+        ("bthd", (NST,), [(f"{ep}.mu_encoder.1.bias", (0, P)), (f"{ep}.lvar_encoder.1.bias", (P, 2 * P)),
+                          (f"{es}.mu_encoder.1.bias", (2 * P, 2 * P + S)), (f"{es}.lvar_encoder.1.bias", (2 * P + S, NST))]),
+        ("Wp", (G, P), [(f"{dec}.factor_regressor_private.{fl}.0.weight", None)]),
+        ("gp", (G,), [(f"{dec}.factor_regressor_private.{fl}.1.weight", None)]),
+        ("bp", (G,), [(f"{dec}.factor_regressor_private.{fl}.1.bias", None)]),
+        ("Ws", (G, S), [(f"{dec}.factor_regressor_shared.{fl}.0.weight", None)]),
+        ("gs", (G,), [(f"{dec}.factor_regressor_shared.{fl}.1.weight", None)]),
+        ("bs", (G,), [(f"{dec}.factor_regressor_shared.{fl}.1.bias", None)]),
+        ("Wh", (HD, KZ), [(f"{dec}.sigmoid_decoder.{fl}.0.weight", None)]),
+        ("bh", (HD,), [(f"{dec}.sigmoid_decoder.{fl}.0.bias", None)]),
+        ("gh", (HD,), [(f"{dec}.sigmoid_decoder.{fl}.1.weight", None)]),
+        ("bth", (HD,), [(f"{dec}.sigmoid_decoder.{fl}.1.bias", None)]),
+        ("Wm", (G, KMIX), [(f"{dec}.mixture.{fl}.0.weight", None)]),
+        ("bm", (G,), [(f"{dec}.mixture.{fl}.0.bias", None)]),
+        ("px_r", (G,), [(f"px_r.{g}", None)]),
+    ]
+
+
+def _group_buffer_entries(g: int, G: int, d: Dims):
+    S, P, NST = d.n_shared, d.n_private, d.NST
+    ep, es, dec = f"encoder_{g}_private", f"encoder_{g}_shared", f"decoder_{g}"
+    fl = "fc_layers.Layer 0"
+    out = []
+    for kind in ("running_mean", "running_var"):
+        tag = "rm" if kind == "running_mean" else "rv"
+        out += [
+            (f"{tag}_hd", (NST,), [(f"{ep}.mu_encoder.1.{kind}", (0, P)), (f"{ep}.lvar_encoder.1.{kind}", (P, 2 * P)),
+                                   (f"{es}.mu_encoder.1.{kind}", (2 * P, 2 * P + S)), (f"{es}.lvar_encoder.1.{kind}", (2 * P + S, NST))]),
+            (f"{tag}_p", (G,), [(f"{dec}.factor_regressor_private.{fl}.1.{kind}", None)]),
+            (f"{tag}_s", (G,), [(f"{dec}.factor_regressor_shared.{fl}.1.{kind}", None)]),
+            (f"{tag}_h", (HD,), [(f"{dec}.sigmoid_decoder.{fl}.1.{kind}", None)]),
+        ]
+    return out
+
+
+class FlatStore:
+    """one flat fp32 tensor + named views (fused blocks per group, and reference state_dict names)"""
+
+    def __init__(self, entries_per_group, device):
+        self.offsets: List[Dict[str, Tuple[int, Tuple[int, ...]]]] = []
+        self.sd_index: "OrderedDict[str, Tuple[int, str, Optional[Tuple[int, int]]]]" = OrderedDict()
+        off = 0
+        for g, entries in enumerate(entries_per_group):
+            table = {}
+            for name, shape, subs in entries:
+                n = int(math.prod(shape))
+                table[name] = (off, shape)
+                for sd_name, sl in subs:
+                    self.sd_index[sd_name] = (g, name, sl)
+                off += (n + 3) // 4 * 4  # keep every block 16-byte aligned
+            self.offsets.append(table)
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+
+    def block(self, g: int, name: str, flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+        off, shape = self.offsets[g][name]
+        base = self.flat if flat is None else flat
+        return base[off:off + int(math.prod(shape))].view(shape)
+
+    def view(self, sd_name: str, flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+        g, name, sl = self.sd_index[sd_name]
+        blk = self.block(g, name, flat)
+        return blk if sl is None else blk[sl[0]:sl[1]]
+
+    def names(self):
+        return list(self.sd_index.keys())
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class GroupBatch:
+    """one group's minibatch: a device-resident count matrix plus optional row-gather indices"""
+    X: torch.Tensor                       # [N, ld] uint16 or float32 counts (device); columns col0 .. col0+G are this group's genes
+    rows: Optional[torch.Tensor] = None   # int32 [B] row indices into X, or None for X[:B]
+    col0: int = 0
+    labels: Optional[torch.Tensor] = None  # int32 [B] cell-type labels (label mode) or cluster labels (cluster mode)
+    idx: Optional[torch.Tensor] = None     # int32 [B] within-group indices into the transport plan
+    B: Optional[int] = None
+
+    def batch_size(self):
+        if self.B is not None:
+            return self.B
+        return int(self.rows.shape[0]) if self.rows is not None else int(self.X.shape[0])
+
+
+@dataclass
+class Noise:
+    """explicit reparameterisation noise / dropout multipliers (parity tests); None -> in-kernel Philox"""
+    eps_private: Optional[Sequence[torch.Tensor]] = None   # per group [B, P]
+    eps_poe: Optional[Sequence[torch.Tensor]] = None       # per group [B, S]
+    drop: Optional[Sequence[torch.Tensor]] = None          # per group [B, 2H] multipliers (private | shared)
+
+
+class _GroupWS:
+    def __init__(self, B, G, d: Dims, dev, with_grad: bool):
+        H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        self.B, self.G = B, G
+        self.nTG, self.nTB = (G + 63) // 64, (B + 63) // 64
+        self.lib = f(B)
+        self.h1, self.h2 = f(B, 2 * H), f(B, 2 * H)
+        self.r, self.stats = f(B, NST), f(B, NST)
+        self.bn_hd_mean, self.bn_hd_istd = f(NST), f(NST)
+        self.zpriv, self.zpoe = f(B, P), f(B, S)
+        self.poe_loc, self.poe_lv, self.poe_scale = f(B, S), f(B, S), f(B, S)
+        self.klp, self.klq, self.rec = f(B), f(B), f(B)
+        self.partner = torch.empty(B, dtype=torch.int32, device=dev)
+        self.amix = f(B, KMIX)
+        self.zsum, self.zmean, self.zcov = f(KZ), f(KZ), f(KZ, KZ)
+        self.cov_part = f(self.nTB, KZ * KZ)
+        self.wfold, self.genec = f(G, KZ), f(L.GENEC_ROWS, G)
+        self.ah = f(B, HD)
+        self.bn_h_mean, self.bn_h_istd = f(HD), f(HD)
+        self.part_stats, self.part_nb = f(self.nTG, B, 4), f(self.nTG, B, 3)
+        self.rowc = f(B, 4)
+        self.pi = f(B, G)
+        self.expert = f(B, 2 * S)  # cluster mode: plan-weighted expert statistics
+        # split-K workspace: the largest user is fc1 forward (B x 2H) and d Amix (B x KMIX)
+        self.splits_fc1 = max(1, min(16, G // 512))
+        self.splits_g = max(1, min(16, G // 512))
+        self.ws = f(max(self.splits_fc1 * B * 2 * H, self.splits_g * B * KMIX, self.splits_g * KZ * KZ, 1))
+        if with_grad:
+            self.dyp, self.dys, self.dpi = f(B, G), f(B, G), f(B, G)
+            self.colpart, self.colsum = f(self.nTB, 4, G), f(4, G)
+            self.Qp, self.Qs = f(G, P), f(G, S)
+            self.damix, self.dzraw, self.dzz = f(B, KMIX), f(B, KZ), f(B, KZ)
+            self.wv, self.wmx = f(G, KZ), f(G, KZ)
+            self.v1 = f(KZ)
+            self.Mmat = torch.zeros(KZ, KZ, dtype=torch.float32, device=dev)
+            self.dah = f(B, HD)
+            self.dstats, self.dr = f(B, NST), f(B, NST)
+            self.g_own, self.g_contrib, self.dexpert = f(B, 2 * S), f(B, 2 * S), f(B, 2 * S)
+            self.dh2, self.dh1 = f(B, 2 * H), f(B, 2 * H)
+
+
+class StepEngine:
+    """fwd / bwd / Adam of the spVIPES step for two groups on one GPU."""
+
+    def __init__(self, genes: Tuple[int, int], n_hidden=128, n_shared=25, n_private=10, dropout_rate=0.1, mode="label",
+                 device="cuda", seed: int = 0, plan: Optional[torch.Tensor] = None):
+        self.lib = L.load()
+        self.d = Dims(tuple(int(x) for x in genes), int(n_hidden), int(n_shared), int(n_private))
+        if self.d.n_private > self.d.n_shared:
+            raise ValueError("n_dimensions_private > n_dimensions_shared is not supported by the reference's latent slicing")
+        self.mode = mode
+        self.mode_id = L.POE_MODES[mode]
+        self.dropout_rate = float(dropout_rate)
+        self.device = torch.device(device)
+        self.seed = int(seed)
+        self.params = FlatStore([_group_param_entries(g, G, self.d) for g, G in enumerate(self.d.genes)], self.device)
+        self.buffers = FlatStore([_group_buffer_entries(g, G, self.d) for g, G in enumerate(self.d.genes)], self.device)
+        for n in self.buffers.names():
+            if n.endswith("running_var"):
+                self.buffers.view(n).fill_(1.0)
+        self.grads = torch.zeros_like(self.params.flat)
+        self.adam_m: Optional[torch.Tensor] = None
+        self.adam_v: Optional[torch.Tensor] = None
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.kl_weight = torch.ones(1, dtype=torch.float32, device=self.device)
+        self.loss_out = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self.plan = plan
+        self._ws: Dict[Tuple[int, int, bool], List[_GroupWS]] = {}
+        self._ctx = None
+
+    # -------------------------------------------------------------------------------- helpers
+    def P(self, g, name):
+        return self.params.block(g, name)
+
+    def Gd(self, g, name):
+        return self.params.block(g, name, self.grads)
+
+    def Bf(self, g, name):
+        return self.buffers.block(g, name)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _gemm(self, A, B, C, M, N, K, *, lda, ldb, ldc, ta=0, tb=0, srcA=L.SRC_F32, srcB=L.SRC_F32, rowsA=None, rowsB=None,
+              batch=1, sA=0, sB=0, sC=0, bias=None, sBias=0, relu=0, acc=0, splits=1, ws=None):
+        L.check(self.lib.spv_gemm(srcA, ta, srcB, tb, A, lda, L.ptr(rowsA), B, ldb, L.ptr(rowsB), C, ldc, M, N, K, batch,
+                                  sA, sB, sC, bias, sBias, relu, acc, splits, L.ptr(ws), self._stream()), "spv_gemm")
+
+    def workspace(self, B0, B1, with_grad=True):
+        key = (B0, B1, with_grad)
+        if key not in self._ws:
+            self._ws[key] = [_GroupWS(B, G, self.d, self.device, with_grad) for B, G in zip((B0, B1), self.d.genes)]
+        return self._ws[key]
+
+    @staticmethod
+    def _src_of(X):
+        if X.dtype == torch.uint16:
+            return L.SRC_U16_LOG1P, 2
+        if X.dtype == torch.float32:
+            return L.SRC_F32_LOG1P, 4
+        raise TypeError(f"counts must be uint16 or float32, got {X.dtype}")
+
+    # -------------------------------------------------------------------------------- forward
+    def forward(self, batches: Sequence[GroupBatch], training: bool = True, noise: Optional[Noise] = None,
+                with_grad: Optional[bool] = None, decode: bool = True):
+        """inference -> generative -> loss.  Returns the workspaces (device tensors) holding every output."""
+        d, st, lib = self.d, self._stream(), self.lib
+        H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
+        with_grad = training if with_grad is None else with_grad
+        Bs = [b.batch_size() for b in batches]
+        ws = self.workspace(Bs[0], Bs[1], with_grad)
+        noise = noise or Noise()
+        tr = 1 if training else 0
+        srcs = []
+        # ---------------- encoders (reference nn/networks.py:119-125, module :428-448)
+        for g, (bt, w) in enumerate(zip(batches, ws)):
+            G, B = d.genes[g], Bs[g]
+            src, esz = self._src_of(bt.X)
+            ldx = bt.X.stride(0)
+            xptr = bt.X.data_ptr() + bt.col0 * esz
+            srcs.append((src, xptr, ldx))
+            L.check(lib.spv_library_size(src, xptr, ldx, L.ptr(bt.rows), B, G, L.ptr(w.lib), st), "spv_library_size")
+            self._gemm(xptr, L.ptr(self.P(g, "W1")), L.ptr(w.h1), B, 2 * H, G, lda=ldx, ldb=G, ldc=2 * H, tb=1, srcA=src,
+                       rowsA=bt.rows, bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.splits_fc1, ws=w.ws)
+            self._gemm(L.ptr(w.h1), L.ptr(self.P(g, "W2")), L.ptr(w.h2), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, tb=1, batch=2,
+                       sA=H, sB=H * H, sC=H, bias=L.ptr(self.P(g, "b2")), sBias=H, relu=1)
+            if training:
+                mask = noise.drop[g] if noise.drop is not None else None
+                if mask is not None or self.dropout_rate > 0:
+                    L.check(lib.spv_dropout(L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, self.dropout_rate, self.seed,
+                                            8 + g, L.ptr(self.step_dev), st), "spv_dropout")
+            bhd = self.P(g, "bhd")
+            self._gemm(L.ptr(w.h2), L.ptr(self.P(g, "Whp")), L.ptr(w.r), B, 2 * P, H, lda=2 * H, ldb=H, ldc=NST, tb=1,
+                       bias=L.ptr(bhd))
+            self._gemm(w.h2.data_ptr() + 4 * H, L.ptr(self.P(g, "Whs")), w.r.data_ptr() + 4 * 2 * P, B, 2 * S, H, lda=2 * H,
+                       ldb=H, ldc=NST, tb=1, bias=bhd.data_ptr() + 4 * 2 * P)
+            L.check(lib.spv_bn_fwd(L.ptr(w.r), NST, L.ptr(w.stats), NST, B, NST, L.ptr(self.P(g, "ghd")),
+                                   L.ptr(self.P(g, "bthd")), ENC_BN_EPS, ENC_BN_MOM, L.ptr(self.Bf(g, "rm_hd")),
+                                   L.ptr(self.Bf(g, "rv_hd")), L.ptr(w.bn_hd_mean), L.ptr(w.bn_hd_istd), tr, 0, st), "spv_bn_fwd")
+        # ---------------- pairing (integer work) and PoE (reference :484-718)
+        aux = self._pairing(batches, ws, Bs)
+        self._poe_fwd(ws, Bs, noise, aux)
+        ctx = {"batches": batches, "ws": ws, "Bs": Bs, "noise": noise, "srcs": srcs, "aux": aux, "training": training}
+        self._ctx = ctx
+        if not decode:
+            return ws
+        # ---------------- decoders + NB likelihood (reference nn/networks.py:314-325, module :751-759, :817-824)
+        for g, (bt, w) in enumerate(zip(batches, ws)):
+            G, B = d.genes[g], Bs[g]
+            src, xptr, ldx = srcs[g]
+            zzp = w.amix.data_ptr() + 4 * HD
+            L.check(lib.spv_colsum(zzp, KMIX, B, KZ, L.ptr(w.zsum), st), "spv_colsum")
+            fold = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), self.P(g, "gp"), self.P(g, "bp"), self.P(g, "gs"),
+                                self.P(g, "bs"), self.P(g, "px_r"), self.Bf(g, "rm_p"), self.Bf(g, "rv_p"),
+                                self.Bf(g, "rm_s"), self.Bf(g, "rv_s"), zzp, w.zsum, w.cov_part, w.wfold, w.genec, w.zmean,
+                                w.zcov])
+            L.check(lib.spv_dec_fold(fold, KMIX, B, G, P, S, tr, DEC_BN_EPS, DEC_BN_MOM, st), "spv_dec_fold")
+            self._gemm(zzp, L.ptr(self.P(g, "Wh")), L.ptr(w.ah), B, HD, KZ, lda=KMIX, ldb=KZ, ldc=HD, tb=1,
+                       bias=L.ptr(self.P(g, "bh")))
+            L.check(lib.spv_bn_fwd(L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, B, HD, L.ptr(self.P(g, "gh")), L.ptr(self.P(g, "bth")),
+                                   DEC_BN_EPS, DEC_BN_MOM, L.ptr(self.Bf(g, "rm_h")), L.ptr(self.Bf(g, "rv_h")),
+                                   L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), tr, 1, st), "spv_bn_fwd")
+            L.check(lib.spv_dec_nb_fwd(src, self._dec_ptrs(g, w, xptr, bt.rows, with_grad), ldx, KMIX, B, G, HD, P, S, st),
+                    "spv_dec_nb_fwd")
+        if Bs[0] != Bs[1]:
+            raise ValueError("the loss needs equally sized minibatches in both groups (reference :886-893)")
+        L.check(lib.spv_loss(L.ptr(ws[0].rec), L.ptr(ws[1].rec), L.ptr(ws[0].klp), L.ptr(ws[0].klq), L.ptr(ws[1].klp),
+                             L.ptr(ws[1].klq), Bs[0], L.ptr(self.kl_weight), L.ptr(self.loss_out), st), "spv_loss")
+        return ws
+
+    def _dec_ptrs(self, g, w, xptr, rows, with_grad):
+        wg = with_grad
+        return L.ptr_array([xptr, rows, w.amix, w.wfold, self.P(g, "Wm"), self.P(g, "bm"), w.genec, w.lib, w.part_stats,
+                            w.rowc, w.pi, w.part_nb, w.dyp if wg else None, w.dys if wg else None, w.dpi if wg else None,
+                            w.colpart if wg else None, w.rec])
+
+    def _pairing(self, batches, ws, Bs):
+        lib, st, d = self.lib, self._stream(), self.d
+        aux = {}
+        if self.mode == "label":
+            if batches[0].labels is None or batches[1].labels is None:
+                raise ValueError("Labels are required when using label-based POE.")  # reference :401-402
+            L.check(lib.spv_pair_label(L.ptr(batches[0].labels), L.ptr(batches[1].labels), Bs[0], Bs[1], L.ptr(ws[0].partner),
+                                       L.ptr(ws[1].partner), st), "spv_pair_label")
+            return aux
+        if self.plan is None:
+            raise ValueError("a transport plan is required for the OT PoE modes")
+        if Bs[0] != Bs[1]:
+            raise ValueError("OT PoE needs equally sized minibatches (reference :521-523)")
+        key = ("sub", Bs[0], Bs[1])
+        if key not in self._ws:
+            self._ws[key] = {"sub": torch.empty(Bs[0], Bs[1], dtype=torch.float32, device=self.device),
+                             "P1": torch.empty(Bs[0], Bs[1], dtype=torch.float32, device=self.device),
+                             "P2": torch.empty(Bs[1], Bs[0], dtype=torch.float32, device=self.device)}
+        aux = self._ws[key]
+        L.check(lib.spv_plan_gather(L.ptr(self.plan), self.plan.stride(0), L.ptr(batches[0].idx), L.ptr(batches[1].idx),
+                                    Bs[0], Bs[1], L.ptr(aux["sub"]), st), "spv_plan_gather")
+        if self.mode == "paired":
+            L.check(lib.spv_plan_argmax(L.ptr(aux["sub"]), Bs[0], Bs[1], L.ptr(ws[0].partner), L.ptr(ws[1].partner), st),
+                    "spv_plan_argmax")
+            return aux
+        # cluster mode (reference :184-280)
+        if batches[0].labels is None or batches[1].labels is None:
+            raise ValueError("processed_transport_labels are required when using transport plan.")  # reference :394-397
+        L.check(lib.spv_pair_label(L.ptr(batches[0].labels), L.ptr(batches[1].labels), Bs[0], Bs[1], L.ptr(ws[0].partner),
+                                   L.ptr(ws[1].partner), st), "spv_pair_label")
+        L.check(lib.spv_plan_cluster_norm(L.ptr(aux["sub"]), Bs[0], Bs[1], L.ptr(batches[0].labels), L.ptr(batches[1].labels),
+                                          L.ptr(aux["P1"]), L.ptr(aux["P2"]), st), "spv_plan_cluster_norm")
+        S, P, NST = d.n_shared, d.n_private, d.NST
+        # expert A = P1 @ stats_0[:, shared], expert B = P2 @ stats_1[:, shared]  (cross-indexing quirk Q5, :222, :228)
+        self._gemm(L.ptr(aux["P1"]), ws[0].stats.data_ptr() + 4 * 2 * P, L.ptr(ws[0].expert), Bs[0], 2 * S, Bs[1], lda=Bs[1],
+                   ldb=NST, ldc=2 * S)
+        self._gemm(L.ptr(aux["P2"]), ws[1].stats.data_ptr() + 4 * 2 * P, L.ptr(ws[1].expert), Bs[1], 2 * S, Bs[0], lda=Bs[0],
+                   ldb=NST, ldc=2 * S)
+        return aux
+
+    def _poe_sides(self, ws):
+        d = self.d
+        S, P, NST = d.n_shared, d.n_private, d.NST
+        if self.mode == "cluster":
+            own = [(w.expert.data_ptr(), w.expert.data_ptr() + 4 * S, 2 * S) for w in ws]
+        else:
+            own = [(w.stats.data_ptr() + 4 * 2 * P, w.stats.data_ptr() + 4 * (2 * P + S), NST) for w in ws]
+        return own
+
+    def _poe_fwd(self, ws, Bs, noise, aux):
+        d = self.d
+        S, P, NST, KMIX = d.n_shared, d.n_private, d.NST, d.KMIX
+        own = self._poe_sides(ws)
+        arrs = []
+        for g in (0, 1):
+            o, t, w = own[g], own[1 - g], ws[g]
+            ep = noise.eps_private[g] if noise.eps_private is not None else None
+            eq = noise.eps_poe[g] if noise.eps_poe is not None else None
+            ptrs = L.ptr_array([o[0], o[1], t[0], t[1], w.stats, w.partner, ep, eq, w.zpriv, w.poe_loc, w.poe_lv, w.poe_scale,
+                                w.zpoe, w.klp, w.klq, w.amix.data_ptr() + 4 * HD])
+            lds = L.ll_array([o[2], t[2], NST, KMIX])
+            arrs.append((ptrs, lds))
+        L.check(self.lib.spv_poe_fwd(self.mode_id, S, P, Bs[0], Bs[1], arrs[0][0], arrs[0][1], arrs[1][0], arrs[1][1], self.seed,
+                                     L.ptr(self.step_dev), self._stream()), "spv_poe_fwd")
+
+    # -------------------------------------------------------------------------------- backward
+    def backward(self, grad_scale: float = 1.0):
+        """gradients of loss * grad_scale w.r.t. every parameter, written into self.grads."""
+        ctx = self._ctx
+        if ctx is None or not ctx["training"]:
+            raise RuntimeError("backward needs a preceding training-mode forward")
+        d, st, lib = self.d, self._stream(), self.lib
+        H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
+        batches, ws, Bs, noise, srcs, aux = ctx["batches"], ctx["ws"], ctx["Bs"], ctx["noise"], ctx["srcs"], ctx["aux"]
+        # ---------------- decoders
+        for g, (bt, w) in enumerate(zip(batches, ws)):
+            G, B = d.genes[g], Bs[g]
+            src, xptr, ldx = srcs[g]
+            zzp = w.amix.data_ptr() + 4 * HD
+            L.check(lib.spv_dec_nb_bwd(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, KMIX, B, G, HD, P, S,
+                                       -float(grad_scale) / B, L.ptr(w.colsum), st), "spv_dec_nb_bwd")
+            # d Wm = dpi^T [hm | zz];   Q = dy^T z
+            self._gemm(L.ptr(w.dpi), L.ptr(w.amix), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=G, ldb=KMIX, ldc=KMIX, ta=1)
+            self._gemm(L.ptr(w.dyp), zzp, L.ptr(w.Qp), G, P, B, lda=G, ldb=KMIX, ldc=P, ta=1)
+            self._gemm(L.ptr(w.dys), zzp + 4 * P, L.ptr(w.Qs), G, S, B, lda=G, ldb=KMIX, ldc=S, ta=1)
+            # d [hm | zz] = dpi Wm ;  dz (softmax branches) = dy W'
+            self._gemm(L.ptr(w.dpi), L.ptr(self.P(g, "Wm")), L.ptr(w.damix), B, KMIX, G, lda=G, ldb=KMIX, ldc=KMIX,
+                       splits=w.splits_g, ws=w.ws)
+            self._gemm(L.ptr(w.dyp), L.ptr(w.wfold), L.ptr(w.dzraw), B, P, G, lda=G, ldb=KZ, ldc=KZ, splits=w.splits_g, ws=w.ws)
+            self._gemm(L.ptr(w.dys), w.wfold.data_ptr() + 4 * P, w.dzraw.data_ptr() + 4 * P, B, S, G, lda=G, ldb=KZ, ldc=KZ,
+                       splits=w.splits_g, ws=w.ws)
+            gb = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), w.Qp, w.Qs, w.genec, w.colsum, w.zmean, w.zcov,
+                              self.Gd(g, "Wp"), self.Gd(g, "Ws"), self.Gd(g, "gp"), self.Gd(g, "bp"), self.Gd(g, "gs"),
+                              self.Gd(g, "bs"), self.Gd(g, "px_r"), self.Gd(g, "bm"), w.wv, w.wmx])
+            L.check(lib.spv_dec_gene_bwd(gb, B, G, P, S, st), "spv_dec_gene_bwd")
+            L.check(lib.spv_colsum(L.ptr(w.wv), KZ, G, KZ, L.ptr(w.v1), st), "spv_colsum")
+            self._gemm(L.ptr(w.wmx), L.ptr(self.P(g, "Wp")), L.ptr(w.Mmat), P, P, G, lda=KZ, ldb=P, ldc=KZ, ta=1,
+                       splits=w.splits_g, ws=w.ws)
+            self._gemm(w.wmx.data_ptr() + 4 * P, L.ptr(self.P(g, "Ws")), w.Mmat.data_ptr() + 4 * (P * KZ + P), S, S, G, lda=KZ,
+                       ldb=S, ldc=KZ, ta=1, splits=w.splits_g, ws=w.ws)
+            L.check(lib.spv_dec_dzz_combine(w.damix.data_ptr() + 4 * HD, KMIX, L.ptr(w.dzraw), L.ptr(w.v1), L.ptr(w.Mmat), zzp,
+                                            KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S, st), "spv_dec_dzz_combine")
+            # hidden layer of the mixing net: ReLU + BatchNorm backward, then its Linear
+            L.check(lib.spv_bn_bwd(L.ptr(w.damix), KMIX, L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, L.ptr(w.dah), HD, B, HD,
+                                   L.ptr(self.P(g, "gh")), L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), L.ptr(self.Gd(g, "gh")),
+                                   L.ptr(self.Gd(g, "bth")), st), "spv_bn_bwd")
+            self._gemm(L.ptr(w.dah), zzp, L.ptr(self.Gd(g, "Wh")), HD, KZ, B, lda=HD, ldb=KMIX, ldc=KZ, ta=1)
+            L.check(lib.spv_colsum(L.ptr(w.dah), HD, B, HD, L.ptr(self.Gd(g, "bh")), st), "spv_colsum")
+            self._gemm(L.ptr(w.dah), L.ptr(self.P(g, "Wh")), L.ptr(w.dzz), B, KZ, HD, lda=HD, ldb=KZ, ldc=KZ, acc=1)
+        # ---------------- PoE
+        own = self._poe_sides(ws)
+        arrs = []
+        for g in (0, 1):
+            o, t, w = own[g], own[1 - g], ws[g]
+            ep = noise.eps_private[g] if noise.eps_private is not None else None
+            eq = noise.eps_poe[g] if noise.eps_poe is not None else None
+            if self.mode == "cluster":
+                out, ld_out = w.dexpert.data_ptr(), 2 * S
+            else:
+                out, ld_out = w.dstats.data_ptr() + 4 * 2 * P, NST
+            ptrs = L.ptr_array([o[0], o[1], t[0], t[1], w.stats, w.partner, ep, eq, w.dzz, w.dstats, w.g_own, w.g_contrib, out])
+            lds = L.ll_array([o[2], t[2], NST, KZ, NST, ld_out])
+            arrs.append((ptrs, lds))
+        L.check(lib.spv_poe_bwd(self.mode_id, S, P, Bs[0], Bs[1], arrs[0][0], arrs[0][1], arrs[1][0], arrs[1][1], self.seed,
+                                L.ptr(self.step_dev), L.ptr(self.kl_weight), float(grad_scale) / Bs[0], st), "spv_poe_bwd")
+        if self.mode == "cluster":
+            # d stats_0[:, shared] += P1^T d expertA ;  d stats_1[:, shared] += P2^T d expertB   (quirk Q5)
+            self._gemm(L.ptr(aux["P1"]), L.ptr(ws[0].dexpert), ws[0].dstats.data_ptr() + 4 * 2 * P, Bs[1], 2 * S, Bs[0],
+                       lda=Bs[1], ldb=2 * S, ldc=NST, ta=1, acc=1)
+            self._gemm(L.ptr(aux["P2"]), L.ptr(ws[1].dexpert), ws[1].dstats.data_ptr() + 4 * 2 * P, Bs[0], 2 * S, Bs[1],
+                       lda=Bs[0], ldb=2 * S, ldc=NST, ta=1, acc=1)
+        # ---------------- encoders
+        for g, (bt, w) in enumerate(zip(batches, ws)):
+            G, B = d.genes[g], Bs[g]
+            src, xptr, ldx = srcs[g]
+            L.check(lib.spv_bn_bwd(L.ptr(w.dstats), NST, L.ptr(w.r), NST, None, 0, L.ptr(w.dr), NST, B, NST,
+                                   L.ptr(self.P(g, "ghd")), L.ptr(w.bn_hd_mean), L.ptr(w.bn_hd_istd), L.ptr(self.Gd(g, "ghd")),
+                                   L.ptr(self.Gd(g, "bthd")), st), "spv_bn_bwd")
+            L.check(lib.spv_colsum(L.ptr(w.dr), NST, B, NST, L.ptr(self.Gd(g, "bhd")), st), "spv_colsum")
+            drs = w.dr.data_ptr() + 4 * 2 * P
+            self._gemm(L.ptr(w.dr), L.ptr(w.h2), L.ptr(self.Gd(g, "Whp")), 2 * P, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1)
+            self._gemm(drs, w.h2.data_ptr() + 4 * H, L.ptr(self.Gd(g, "Whs")), 2 * S, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1)
+            self._gemm(L.ptr(w.dr), L.ptr(self.P(g, "Whp")), L.ptr(w.dh2), B, H, 2 * P, lda=NST, ldb=H, ldc=2 * H)
+            self._gemm(drs, L.ptr(self.P(g, "Whs")), w.dh2.data_ptr() + 4 * H, B, H, 2 * S, lda=NST, ldb=H, ldc=2 * H)
+            mask = noise.drop[g] if noise.drop is not None else None
+            scale = 1.0 / (1.0 - self.dropout_rate) if self.dropout_rate > 0 else 1.0
+            L.check(lib.spv_relu_bwd(L.ptr(w.dh2), 2 * H, L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, scale, st),
+                    "spv_relu_bwd")
+            self._gemm(L.ptr(w.dh2), L.ptr(w.h1), L.ptr(self.Gd(g, "W2")), H, H, B, lda=2 * H, ldb=2 * H, ldc=H, ta=1, batch=2,
+                       sA=H, sB=H, sC=H * H)
+            L.check(lib.spv_colsum(L.ptr(w.dh2), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b2")), st), "spv_colsum")
+            self._gemm(L.ptr(w.dh2), L.ptr(self.P(g, "W2")), L.ptr(w.dh1), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, batch=2, sA=H,
+                       sB=H * H, sC=H)
+            L.check(lib.spv_relu_bwd(L.ptr(w.dh1), 2 * H, L.ptr(w.h1), 2 * H, B, 2 * H, None, 0, 1.0, st), "spv_relu_bwd")
+            self._gemm(L.ptr(w.dh1), xptr, L.ptr(self.Gd(g, "W1")), 2 * H, G, B, lda=2 * H, ldb=ldx, ldc=G, ta=1, srcB=src,
+                       rowsB=bt.rows)
+            L.check(lib.spv_colsum(L.ptr(w.dh1), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b1")), st), "spv_colsum")
+
+    # -------------------------------------------------------------------------------- optimiser
+    def adam_step(self, lr=1e-3, betas=(0.9, 0.999), eps=0.01, weight_decay=1e-6, grad_scale=1.0):
+        if self.adam_m is None:
+            self.adam_m = torch.zeros_like(self.params.flat)
+            self.adam_v = torch.zeros_like(self.params.flat)
+        st = self._stream()
+        L.check(self.lib.spv_adam_tick(L.ptr(self.step_dev), st), "spv_adam_tick")
+        L.check(self.lib.spv_adam(L.ptr(self.params.flat), L.ptr(self.grads), L.ptr(self.adam_m), L.ptr(self.adam_v),
+                                  self.params.numel, lr, betas[0], betas[1], eps, weight_decay, grad_scale,
+                                  L.ptr(self.step_dev), st), "spv_adam")
+
+    # -------------------------------------------------------------------------------- state
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        """copy a reference-format state_dict (torch CPU/GPU tensors) into the flat stores"""
+        missing = []
+        for store in (self.params, self.buffers):
+            for n in store.names():
+                if n not in sd:
+                    missing.append(n)
+                    continue
+                store.view(n).copy_(sd[n].to(self.device, torch.float32).reshape(store.view(n).shape))
+        if missing:
+            raise KeyError(f"state_dict is missing {missing[:4]}... ({len(missing)} keys)")
+
+    def state_dict(self) -> "OrderedDict[str, torch.Tensor]":
+        out = OrderedDict()
+        for store in (self.params, self.buffers):
+            for n in store.names():
+                out[n] = store.view(n)
+        return out
+
+    def grad_dict(self) -> "OrderedDict[str, torch.Tensor]":
+        return OrderedDict((n, self.params.view(n, self.grads)) for n in self.params.names())
+
+    def set_kl_weight(self, w: float):
+        self.kl_weight.fill_(float(w))
+
+    def loss_terms(self):
+        """(loss, kl_private0, kl_poe0, kl_private1, kl_poe1 means, rec0 mean, rec1 mean) as a device tensor"""
+        return self.loss_out[:7]

@@ -1,0 +1,45 @@
+"""helpers for the -m gpu tests: drive spvipes_b200.engine.StepEngine from a golden fixture / synthetic case."""
+import numpy as np
+import torch
+
+
+def engine_from_golden(gd, device="cuda"):
+    from spvipes_b200.engine import GroupBatch, Noise, StepEngine
+
+    plan = gd.plan.to(device) if gd.mode != "label" else None
+    eng = StepEngine((gd.G0, gd.G1), gd.H, gd.S, gd.P, gd.dropout, gd.mode, device, plan=plan)
+    eng.load_state_dict(gd.sd)
+    eng.set_kl_weight(gd.kl_weight)
+    batches = []
+    for g in (0, 1):
+        X = torch.from_numpy(gd.x[g].numpy().astype(np.uint16)).to(device)
+        labels = torch.from_numpy(gd.labels[g].astype(np.int32)).to(device) if gd.mode in ("label", "cluster") else None
+        idx = torch.from_numpy(gd.idx[g].astype(np.int32)).to(device)
+        batches.append(GroupBatch(X=X, labels=labels, idx=idx))
+    dm = gd.drop_masks()
+    drop = None
+    if dm is not None:
+        drop = [torch.cat([dm[(g, "private")], dm[(g, "shared")]], dim=1).contiguous().to(device) for g in (0, 1)]
+    noise = Noise(eps_private=[e.to(device) for e in gd.eps_private], eps_poe=[e.to(device) for e in gd.eps_poe], drop=drop)
+    return eng, batches, noise
+
+
+def engine_outputs(eng, ws):
+    """same keys as oracle.restatement.step's output"""
+    d = eng.d
+    P, S = d.n_private, d.n_shared
+    out = {"loss": eng.loss_out[0].cpu()}
+    for k in ("library", "private_loc", "private_logvar", "private_log_z", "shared_loc", "shared_logvar", "poe_loc",
+              "poe_logvar", "poe_scale", "poe_log_z", "rec", "kl_private", "kl_poe", "partners"):
+        out[k] = []
+    for w in ws:
+        st = w.stats.cpu()
+        out["library"].append(w.lib.cpu().unsqueeze(1))
+        out["private_loc"].append(st[:, :P]); out["private_logvar"].append(st[:, P:2 * P])
+        out["shared_loc"].append(st[:, 2 * P:2 * P + S]); out["shared_logvar"].append(st[:, 2 * P + S:])
+        out["private_log_z"].append(w.zpriv.cpu()); out["poe_loc"].append(w.poe_loc.cpu())
+        out["poe_logvar"].append(w.poe_lv.cpu()); out["poe_scale"].append(w.poe_scale.cpu())
+        out["poe_log_z"].append(w.zpoe.cpu()); out["rec"].append(w.rec.cpu())
+        out["kl_private"].append(w.klp.cpu()); out["kl_poe"].append(w.klq.cpu())
+        out["partners"].append(w.partner.cpu().numpy().astype(np.int64))
+    return out
