@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the spVIPES per-minibatch training hot path on B200 (BASELINE.json metric: training cells/sec, fwd+bwd
+ELBO + optimiser; NB-loglik kernel HBM GB/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port)
+
+A "step" is one minibatch (B cells per group, 2 groups) through inference -> generative -> loss -> backward -> Adam.
+Workload (N = 1): BASELINE.json configs[1] — label-based PoE, 2 groups x 50k cells, 5k HVGs, n_hidden 128, batch 512.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (mode, cells per group, genes per group, n_hidden, batch per group, n_labels)
+    "C1": ("label", 5_000, 2_000, 128, 512, 10),
+    "C2": ("label", 50_000, 5_000, 128, 512, 10),
+    "C5": ("label", 1_000_000, 20_000, 128, 2048, 10),
+}
+S_DIM, P_DIM = 25, 10
+METRIC = "training cells/sec (fwd+bwd ELBO + Adam)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_cells_per_sec(workload, steps, warmup, seed=0):
+    """oracle/restatement.py (validated against the unmodified reference, tests/test_oracle.py) + autograd backward + Adam
+    (scvi TrainingPlan defaults) with every host thread; bounded sample: `steps` minibatches of the workload's shape."""
+    from oracle import restatement as rs
+    from spvipes_b200 import synth
+    from spvipes_b200.engine import StepEngine
+    from spvipes_b200.trainer import init_params
+
+    mode, n_cells, genes, H, B, n_labels = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_sample = B * (steps + warmup)
+    data = synth.make_counts((n_sample, n_sample), (genes, genes), n_labels, device="cpu", seed=1234)
+    eng = StepEngine((genes, genes), H, S_DIM, P_DIM, 0.1, mode, device="cpu")
+    init_params(eng, seed)
+    sd = {k: v.clone() for k, v in eng.state_dict().items()}
+    names = rs.param_names(sd)
+    for k in names:
+        sd[k].requires_grad_(True)
+    opt = torch.optim.Adam([sd[k] for k in names], lr=1e-3, eps=0.01, weight_decay=1e-6)
+    gen = torch.Generator().manual_seed(1)
+    t0 = None
+    for s in range(steps + warmup):
+        if s == warmup:
+            t0 = time.perf_counter()
+        sl = slice(s * B, (s + 1) * B)
+        x = [data.X[g][sl].to(torch.float32) for g in (0, 1)]
+        labels = [data.labels[g][sl].numpy() for g in (0, 1)]
+        eps_p = [torch.randn(B, P_DIM, generator=gen) for _ in (0, 1)]
+        eps_q = [torch.randn(B, S_DIM, generator=gen) for _ in (0, 1)]
+        dm = {(g, k): (torch.rand(B, H, generator=gen) < 0.9).float() / 0.9 for g in (0, 1) for k in ("private", "shared")}
+        out = rs.step(sd, x, mode=mode, n_shared=S_DIM, n_private=P_DIM, eps_private=eps_p, eps_poe=eps_q, labels=labels,
+                      drop_masks=dm, kl_weight=min(1.0, s / 400.0))
+        opt.zero_grad(set_to_none=True)
+        out["loss"].backward()
+        opt.step()
+        for k, v in out["new_stats"].items():
+            sd[k] = v
+    dt = time.perf_counter() - t0
+    return 2 * B * steps / dt, dt / steps * 1e3, cores, f"{steps} minibatches of {workload} shape (2x{B} cells, {genes} genes/group), oracle port, torch CPU"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workload = args.workload
+    steps = min(args.steps, 20)
+    v, ms, cores, sample = cpu_reference_cells_per_sec(workload, steps, min(args.warmup, 2))
+    mode, n_cells, genes, H, B, n_labels = WORKLOADS[workload]
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "cells/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(workload, args.gpus),
+            "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(workload, n_gpus):
+    mode, n_cells, genes, H, B, n_labels = WORKLOADS[workload]
+    return {"workload": f"{workload}: {mode}-based PoE, 2 groups x {n_cells} cells, {genes} genes/group, n_hidden {H}, "
+                        f"shared {S_DIM} / private {P_DIM}, batch {B}/group/GPU, {n_labels} labels",
+            "cells_per_step_per_gpu": 2 * B, "parallelism": f"dp{n_gpus}",
+            "l2": "inputs larger than L2: every step gathers a fresh random minibatch from the device-resident count "
+                  "matrices and streams all weights/Adam state"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    from spvipes_b200 import _lib as L
+    from spvipes_b200 import synth
+    from spvipes_b200.engine import GroupBatch, StepEngine
+    from spvipes_b200.trainer import TrainLoop, init_params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    workload = args.workload
+    mode, n_cells, genes, H, B, n_labels = WORKLOADS[workload]
+    if world > 1 and workload == "C5":
+        n_cells = n_cells // world  # rank-local shard of the 2 x 1M cells (weak scaling: batch per GPU fixed)
+    lib = L.load()
+    L.check(lib.spv_arch_check(local_rank), "spv_arch_check (this library is sm_100a only)")
+    data = synth.make_counts((n_cells, n_cells), (genes, genes), n_labels, device=dev, seed=1234 + 17 * rank)
+    eng = StepEngine((genes, genes), H, S_DIM, P_DIM, 0.1, mode, device=dev, seed=rank)
+    init_params(eng, 0)
+    loop = TrainLoop(eng)
+    if world > 1:
+        from spvipes_b200.parallel import GradSync
+        loop.grad_sync = GradSync(eng, dist)
+    K, W = args.steps, args.warmup
+    total = K + W
+    gen = torch.Generator(device=dev).manual_seed(5 + rank)
+    rows = [torch.stack([torch.randperm(n_cells, generator=gen, device=dev)[:B] for _ in range(total)]).to(torch.int32)
+            for _ in (0, 1)]
+
+    def batches_for(s):
+        return [GroupBatch(X=data.X[g], rows=rows[g][s], labels=data.labels[g], labels_per_cell=True) for g in (0, 1)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    loop.set_epoch(1)
+    for s in range(W):
+        loop.step(batches_for(s))
+    barrier()
+    clk = ClockSampler(local_rank)
+    if rank == 0:
+        clk.start()
+    n0 = lib.spv_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nb_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * K)]
+    eng.nb_events = iter(nb_ev)
+    ev0.record()
+    for s in range(W, total):
+        loop.step(batches_for(s))
+    ev1.record()
+    barrier()
+    eng.nb_events = None
+    launches = lib.spv_launch_count() - n0
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = clk.stop() if rank == 0 else None
+    loss = float(eng.loss_out[0].item())
+    value = world * 2 * B * K / (ms * 1e-3)
+
+    # ---- NB-loglik kernel roofline (forward sweep of the fused decoder + NB kernel), timed live with CUDA events
+    nb_ms = float(np.mean([a.elapsed_time(b) for a, b in nb_ev]))
+    KM = 256 + S_DIM + P_DIM
+    alg_bytes = B * genes * 2 + genes * KM * 4 + 6 * genes * 4 + B * (KM + 1) * 4 + B * 4 + B * genes * 4
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (nb_ms * 1e-3) / 1e9
+    roofline = {"kernel": "dec_tile_kernel<PASS_NB> (fused decoder GEMM + NB-mixture log-likelihood, forward)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": nb_ms}
+
+    # ---- end-to-end through the public step API with HOST (pinned) minibatches
+    e2e = measure_e2e(loop, data, rows, B, genes, K, W, dev, dist, world)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, cms, cores, sample = cpu_reference_cells_per_sec(workload, args.cpu_steps, 1)
+            cpu = {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": cms}
+        line = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(workload, world), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "final_loss": loss}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def measure_e2e(loop, data, rows, B, genes, K, W, dev, dist, world):
+    """same metric through the public step call with host buffers: per step the two groups' count minibatches and labels are
+    copied from pinned host memory (double-buffered on a copy stream) and the loss terms are read back."""
+    from spvipes_b200.engine import GroupBatch
+    total = K + W
+    host_x = [[data.X[g][rows[g][s].long()].cpu().pin_memory() for s in range(total)] for g in (0, 1)]
+    host_l = [[data.labels[g][rows[g][s].long()].cpu().pin_memory() for s in range(total)] for g in (0, 1)]
+    dev_x = [[torch.empty(B, genes, dtype=torch.uint16, device=dev) for _ in (0, 1)] for _ in (0, 1)]  # [buf][group]
+    dev_l = [[torch.empty(B, dtype=torch.int32, device=dev) for _ in (0, 1)] for _ in (0, 1)]
+    out_host = torch.empty(8, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in (0, 1)]
+    freed = [torch.cuda.Event() for _ in (0, 1)]
+    main = torch.cuda.current_stream(dev)
+
+    def upload(s):
+        b = s % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[b])
+            for g in (0, 1):
+                dev_x[b][g].copy_(host_x[g][s], non_blocking=True)
+                dev_l[b][g].copy_(host_l[g][s], non_blocking=True)
+            ready[b].record(copy_stream)
+
+    for b in (0, 1):
+        freed[b].record(main)
+    h2d = sum(host_x[g][0].numel() * 2 + host_l[g][0].numel() * 4 for g in (0, 1))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    upload(0)
+    for s in range(total):
+        if s == W:
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            ev0.record(main)
+            upload(s)  # the first timed step's copy happens inside the timed region
+        b = s % 2
+        if s + 1 < total and s + 1 != W:
+            upload(s + 1)
+        main.wait_event(ready[b])
+        loop.step([GroupBatch(X=dev_x[b][g], labels=dev_l[b][g]) for g in (0, 1)])
+        freed[b].record(main)
+        out_host.copy_(loop.engine.loss_out, non_blocking=True)
+    ev1.record(main)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": world * 2 * B * K / (ms * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": 32, "ms_per_step": ms / K, "api": "spvipes_b200.trainer.TrainLoop.step (host uint16 minibatches)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--cpu-steps", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "C2"
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

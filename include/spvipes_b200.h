@@ -35,6 +35,8 @@ extern "C" {
 #define SPV_POE_CLUSTER_ 2
 
 int spv_abi_version(void);
+/* kernels launched (or captured) by this library so far in this process; host-side counter */
+long long spv_launch_count(void);
 /* 0 if device `dev` is sm_100 (B200), SPV_ERR_ARCH otherwise, SPV_ERR_LAUNCH if no CUDA device. Host-side query. */
 int spv_arch_check(int dev);
 
@@ -66,8 +68,10 @@ int spv_bn_bwd(const float* dy, long long lddy, const float* x, long long ldx, c
                float* dgamma, float* dbeta, void* stream);
 int spv_colsum(const float* x, long long ldx, int B, int C, float* out, void* stream);
 
-/* label-rank pairing, bit-exact integer contract   module/spVIPESmodule.py:599-659, 685-701, 297-326 */
-int spv_pair_label(const int* la, const int* lb, int Ba, int Bb, int* pa, int* pb, void* stream);
+/* label-rank pairing, bit-exact integer contract   module/spVIPESmodule.py:599-659, 685-701, 297-326.
+ * rows_a / rows_b (optional): the minibatch's labels are la[rows_a[i]] / lb[rows_b[i]] (gather from per-cell arrays). */
+int spv_pair_label(const int* la, const int* lb, const int* rows_a, const int* rows_b, int Ba, int Bb, int* pa, int* pb,
+                   void* stream);
 /* sub = T[idx0][:, idx1]   :474-482 ;  row/col argmax (ties -> first)   :526-527 */
 int spv_plan_gather(const float* T, long long ldT, const int* idx0, const int* idx1, int B0, int B1, float* sub, void* stream);
 int spv_plan_argmax(const float* sub, int B0, int B1, int* row_arg, int* col_arg, void* stream);
@@ -100,8 +104,9 @@ int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, 
 /* fused decoder + NB-mixture likelihood sweeps.  ptrs (SPV_DEC_NPTR): X, rows, amix, wfold, wm, bm, genec, lib, part_stats,
  * rowc, pi, part_nb, dyp, dys, dpi, colpart, rec.   nn/networks.py:314-325; module/spVIPESmodule.py:759, 817-824 */
 #define SPV_DEC_NPTR 17
+/* phases: bit 0 = gene-axis softmax normaliser sweep, bit 1 = mixture GEMM + NB log-likelihood sweep (3 = both) */
 int spv_dec_nb_fwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P, int S,
-                   void* stream);
+                   int phases, void* stream);
 int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P, int S,
                    float scale, float* colsum, void* stream);
 /* ptrs (18): Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm, wv, wmx */

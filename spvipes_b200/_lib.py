@@ -21,6 +21,7 @@ p, i, ll, f, u64, u32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulongl
 # name -> argtypes (must mirror include/spvipes_b200.h)
 _SIGS = {
     "spv_abi_version": [],
+    "spv_launch_count": [],
     "spv_arch_check": [i],
     "spv_gemm": [i, i, i, i, p, ll, p, p, ll, p, p, ll, i, i, i, i, ll, ll, ll, p, ll, i, i, i, p, p],
     "spv_library_size": [i, p, ll, p, i, i, p, p],
@@ -29,7 +30,7 @@ _SIGS = {
     "spv_bn_fwd": [p, ll, p, ll, i, i, p, p, f, f, p, p, p, p, i, i, p],
     "spv_bn_bwd": [p, ll, p, ll, p, ll, p, ll, i, i, p, p, p, p, p, p],
     "spv_colsum": [p, ll, i, i, p, p],
-    "spv_pair_label": [p, p, i, i, p, p, p],
+    "spv_pair_label": [p, p, p, p, i, i, p, p, p],
     "spv_plan_gather": [p, ll, p, p, i, i, p, p],
     "spv_plan_argmax": [p, i, i, p, p, p],
     "spv_plan_cluster_norm": [p, i, i, p, p, p, p, p],
@@ -37,7 +38,7 @@ _SIGS = {
     "spv_poe_bwd": [i, i, i, i, i, p, p, p, p, u64, p, p, f, p],
     "spv_loss": [p, p, p, p, p, p, i, p, p, p],
     "spv_dec_fold": [p, ll, i, i, i, i, i, f, f, p],
-    "spv_dec_nb_fwd": [i, p, ll, ll, i, i, i, i, i, p],
+    "spv_dec_nb_fwd": [i, p, ll, ll, i, i, i, i, i, i, p],
     "spv_dec_nb_bwd": [i, p, ll, ll, i, i, i, i, i, f, p, p],
     "spv_dec_gene_bwd": [p, i, i, i, i, p],
     "spv_dec_dzz_combine": [p, ll, p, p, p, p, ll, p, p, i, i, i, p],
@@ -63,7 +64,7 @@ def load():
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = args
-        fn.restype = C.c_int
+        fn.restype = C.c_longlong if name == "spv_launch_count" else C.c_int
     _lib = lib
     return lib
 

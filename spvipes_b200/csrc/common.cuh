@@ -9,8 +9,11 @@
 #define SPV_ERR_LAUNCH -2
 #define SPV_ERR_ARCH -3
 
+// every kernel launch site goes through this: counts the launch (spv_launch_count) and checks the launch status
+extern unsigned long long g_spv_launches;
 #define SPV_CHECK_LAUNCH()                              \
     do {                                                \
+        ++g_spv_launches;                               \
         cudaError_t e__ = cudaGetLastError();           \
         if (e__ != cudaSuccess) return SPV_ERR_LAUNCH;  \
     } while (0)

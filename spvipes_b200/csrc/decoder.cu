@@ -413,8 +413,8 @@ static void fill_decp(DecP& p, const void* const* ptrs, long long ldx, long long
 // ptrs (SPV_DEC_NPTR = 17): X, rows, amix, wfold, wm, bm, genec, lib, part_stats, rowc, pi, part_nb, dyp, dys, dpi,
 // colpart, rec.   Forward: rec[b], rowc and pi are produced.
 extern "C" int spv_dec_nb_fwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P,
-                              int S, void* stream) {
-    if (!ptrs || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
+                              int S, int phases, void* stream) {
+    if (!ptrs || (phases & 3) == 0 || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
     const int need[] = {0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 16};
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
@@ -423,17 +423,21 @@ extern "C" int spv_dec_nb_fwd(int src, const void* const* ptrs, long long ldx, l
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     dim3 grid((G + GT_BN - 1) / GT_BN, (B + GT_BM - 1) / GT_BM);
     const int nTG = grid.x;
-    if (src == SPV_SRC_U16_LOG1P) dec_tile_kernel<PASS_STATS, SPV_SRC_U16_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
-    else if (src == SPV_SRC_F32_LOG1P) dec_tile_kernel<PASS_STATS, SPV_SRC_F32_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
-    else return SPV_ERR_ARG;
-    SPV_CHECK_LAUNCH();
-    rowstat_kernel<<<(B + 127) / 128, 128, 0, st>>>(p.part_stats, nTG, B, p.lib, p.rowc);
-    SPV_CHECK_LAUNCH();
-    if (src == SPV_SRC_U16_LOG1P) dec_tile_kernel<PASS_NB, SPV_SRC_U16_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
-    else dec_tile_kernel<PASS_NB, SPV_SRC_F32_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
-    SPV_CHECK_LAUNCH();
-    rownb_kernel<<<(B + 127) / 128, 128, 0, st>>>(p.part_nb, nTG, B, p.rowc, (float*)ptrs[16]);
-    SPV_CHECK_LAUNCH();
+    if (src != SPV_SRC_U16_LOG1P && src != SPV_SRC_F32_LOG1P) return SPV_ERR_ARG;
+    if (phases & 1) {  // gene-axis softmax normalisers
+        if (src == SPV_SRC_U16_LOG1P) dec_tile_kernel<PASS_STATS, SPV_SRC_U16_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
+        else dec_tile_kernel<PASS_STATS, SPV_SRC_F32_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
+        SPV_CHECK_LAUNCH();
+        rowstat_kernel<<<(B + 127) / 128, 128, 0, st>>>(p.part_stats, nTG, B, p.lib, p.rowc);
+        SPV_CHECK_LAUNCH();
+    }
+    if (phases & 2) {  // mixture GEMM + NB log-likelihood
+        if (src == SPV_SRC_U16_LOG1P) dec_tile_kernel<PASS_NB, SPV_SRC_U16_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
+        else dec_tile_kernel<PASS_NB, SPV_SRC_F32_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
+        SPV_CHECK_LAUNCH();
+        rownb_kernel<<<(B + 127) / 128, 128, 0, st>>>(p.part_nb, nTG, B, p.rowc, (float*)ptrs[16]);
+        SPV_CHECK_LAUNCH();
+    }
     return SPV_OK;
 }
 

@@ -11,13 +11,13 @@
 // order) is paired with the rank-r label-L row of group b; PAD if b has the label but fewer
 // rows, ABSENT if b's minibatch lacks the label (reference :599-659, :685-701, _poe2 :297-326)
 // ---------------------------------------------------------------------------------------
-__global__ void pair_label_kernel(const int* __restrict__ la, const int* __restrict__ lb, int Ba, int Bb,
-                                  int* __restrict__ pa, int* __restrict__ pb) {
+__global__ void pair_label_kernel(const int* __restrict__ la, const int* __restrict__ lb, const int* __restrict__ rows_a,
+                                  const int* __restrict__ rows_b, int Ba, int Bb, int* __restrict__ pa, int* __restrict__ pb) {
     extern __shared__ int sl[];
     int* sa = sl;
     int* sb = sl + Ba;
-    for (int i = threadIdx.x; i < Ba; i += blockDim.x) sa[i] = la[i];
-    for (int i = threadIdx.x; i < Bb; i += blockDim.x) sb[i] = lb[i];
+    for (int i = threadIdx.x; i < Ba; i += blockDim.x) sa[i] = la[rows_a ? rows_a[i] : i];
+    for (int i = threadIdx.x; i < Bb; i += blockDim.x) sb[i] = lb[rows_b ? rows_b[i] : i];
     __syncthreads();
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= Ba + Bb) return;
@@ -40,13 +40,14 @@ __global__ void pair_label_kernel(const int* __restrict__ la, const int* __restr
     (side_a ? pa : pb)[i] = found;
 }
 
-extern "C" int spv_pair_label(const int* la, const int* lb, int Ba, int Bb, int* pa, int* pb, void* stream) {
+extern "C" int spv_pair_label(const int* la, const int* lb, const int* rows_a, const int* rows_b, int Ba, int Bb, int* pa,
+                              int* pb, void* stream) {
     if (!la || !lb || !pa || !pb || Ba <= 0 || Bb <= 0) return SPV_ERR_ARG;
     size_t smem = (size_t)(Ba + Bb) * sizeof(int);
     if (smem > 200 * 1024) return SPV_ERR_ARG;
     if (smem > 48 * 1024) cudaFuncSetAttribute(pair_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int blocks = (Ba + Bb + 255) / 256;
-    pair_label_kernel<<<blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(la, lb, Ba, Bb, pa, pb);
+    pair_label_kernel<<<blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(la, lb, rows_a, rows_b, Ba, Bb, pa, pb);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

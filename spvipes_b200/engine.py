@@ -140,6 +140,7 @@ class GroupBatch:
     labels: Optional[torch.Tensor] = None  # int32 [B] cell-type labels (label mode) or cluster labels (cluster mode)
     idx: Optional[torch.Tensor] = None     # int32 [B] within-group indices into the transport plan
     B: Optional[int] = None
+    labels_per_cell: bool = False          # labels (and idx) are indexed by X's row, i.e. gathered with `rows`
 
     def batch_size(self):
         if self.B is not None:
@@ -225,6 +226,7 @@ class StepEngine:
         self.plan = plan
         self._ws: Dict[Tuple[int, int, bool], List[_GroupWS]] = {}
         self._ctx = None
+        self.nb_events = None  # bench hook: iterator of (start, end) CUDA events bracketing the NB-loglik sweep
 
     # -------------------------------------------------------------------------------- helpers
     def P(self, g, name):
@@ -318,8 +320,14 @@ class StepEngine:
             L.check(lib.spv_bn_fwd(L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, B, HD, L.ptr(self.P(g, "gh")), L.ptr(self.P(g, "bth")),
                                    DEC_BN_EPS, DEC_BN_MOM, L.ptr(self.Bf(g, "rm_h")), L.ptr(self.Bf(g, "rv_h")),
                                    L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), tr, 1, st), "spv_bn_fwd")
-            L.check(lib.spv_dec_nb_fwd(src, self._dec_ptrs(g, w, xptr, bt.rows, with_grad), ldx, KMIX, B, G, HD, P, S, st),
-                    "spv_dec_nb_fwd")
+            dptrs = self._dec_ptrs(g, w, xptr, bt.rows, with_grad)
+            L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 1, st), "spv_dec_nb_fwd")
+            evs = next(self.nb_events) if self.nb_events is not None else None
+            if evs is not None:
+                evs[0].record()
+            L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 2, st), "spv_dec_nb_fwd")
+            if evs is not None:
+                evs[1].record()
         if Bs[0] != Bs[1]:
             raise ValueError("the loss needs equally sized minibatches in both groups (reference :886-893)")
         L.check(lib.spv_loss(L.ptr(ws[0].rec), L.ptr(ws[1].rec), L.ptr(ws[0].klp), L.ptr(ws[0].klq), L.ptr(ws[1].klp),
@@ -338,8 +346,7 @@ class StepEngine:
         if self.mode == "label":
             if batches[0].labels is None or batches[1].labels is None:
                 raise ValueError("Labels are required when using label-based POE.")  # reference :401-402
-            L.check(lib.spv_pair_label(L.ptr(batches[0].labels), L.ptr(batches[1].labels), Bs[0], Bs[1], L.ptr(ws[0].partner),
-                                       L.ptr(ws[1].partner), st), "spv_pair_label")
+            self._pair_label(batches, ws, Bs)
             return aux
         if self.plan is None:
             raise ValueError("a transport plan is required for the OT PoE modes")
@@ -360,8 +367,7 @@ class StepEngine:
         # cluster mode (reference :184-280)
         if batches[0].labels is None or batches[1].labels is None:
             raise ValueError("processed_transport_labels are required when using transport plan.")  # reference :394-397
-        L.check(lib.spv_pair_label(L.ptr(batches[0].labels), L.ptr(batches[1].labels), Bs[0], Bs[1], L.ptr(ws[0].partner),
-                                   L.ptr(ws[1].partner), st), "spv_pair_label")
+        self._pair_label(batches, ws, Bs)
         L.check(lib.spv_plan_cluster_norm(L.ptr(aux["sub"]), Bs[0], Bs[1], L.ptr(batches[0].labels), L.ptr(batches[1].labels),
                                           L.ptr(aux["P1"]), L.ptr(aux["P2"]), st), "spv_plan_cluster_norm")
         S, P, NST = d.n_shared, d.n_private, d.NST
@@ -371,6 +377,12 @@ class StepEngine:
         self._gemm(L.ptr(aux["P2"]), ws[1].stats.data_ptr() + 4 * 2 * P, L.ptr(ws[1].expert), Bs[1], 2 * S, Bs[0], lda=Bs[0],
                    ldb=NST, ldc=2 * S)
         return aux
+
+    def _pair_label(self, batches, ws, Bs):
+        """labels are either per-minibatch [B] arrays, or per-cell arrays gathered with the batch's row indices"""
+        lr = [bt.rows if (bt.labels_per_cell and bt.rows is not None) else None for bt in batches]
+        L.check(self.lib.spv_pair_label(L.ptr(batches[0].labels), L.ptr(batches[1].labels), L.ptr(lr[0]), L.ptr(lr[1]), Bs[0],
+                                        Bs[1], L.ptr(ws[0].partner), L.ptr(ws[1].partner), self._stream()), "spv_pair_label")
 
     def _poe_sides(self, ws):
         d = self.d

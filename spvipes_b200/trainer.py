@@ -1,0 +1,124 @@
+"""Training loop around StepEngine: minibatch index schedule with the reference's semantics, device-resident or
+host-fed minibatches, KL warm-up and the optimiser step.
+
+Index semantics restated from the reference (bit-exact contract):
+  * split: np.random.RandomState(seed).permutation per group, in group order; val first, then train
+    (data/_multi_datasplitter.py:65-85; n_train = ceil(train_size * n), scvi validate_data_split)
+  * per epoch and group: a BatchSampler(RandomSampler) over the train subset, batch_size B, drop_last=True
+    (dataloaders/_ann_dataloader.py:85-92); RandomSampler draws its seed from the global torch CPU RNG and then
+    torch.randperm(n, generator=...)
+  * the group with fewer batches is replayed with itertools.cycle, i.e. its FIRST pass is cached and repeated
+    (dataloaders/_concat_dataloader.py:108-110)
+  * kl_weight = min(1, epoch / n_epochs_kl_warmup) (scvi TrainingPlan, model/base/training_mixin.py:93-101)
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .engine import GroupBatch, Noise, StepEngine
+
+
+def validate_data_split(n: int, train_size: float, validation_size: Optional[float] = None) -> Tuple[int, int]:
+    """scvi.dataloaders._data_splitting.validate_data_split (0.20.0)"""
+    n_train = math.ceil(train_size * n)
+    n_val = n - n_train if validation_size is None else math.floor(n * validation_size)
+    return n_train, n_val
+
+
+def split_indices(group_indices_list: Sequence[np.ndarray], train_size=0.9, validation_size=None, seed=0):
+    """reference data/_multi_datasplitter.py:65-79 -> (train, val, test) index lists per group"""
+    rs = np.random.RandomState(seed=seed)
+    train, val, test = [], [], []
+    for gi in group_indices_list:
+        gi = np.asarray(gi)
+        n_train, n_val = validate_data_split(len(gi), train_size, validation_size)
+        perm = rs.permutation(gi)
+        val.append(perm[:n_val])
+        train.append(perm[n_val:n_val + n_train])
+        test.append(perm[n_val + n_train:])
+    return train, val, test
+
+
+def _random_sampler_perm(n: int) -> torch.Tensor:
+    """torch.utils.data.RandomSampler.__iter__ (replacement=False, generator=None): seed from the global CPU RNG"""
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    gen = torch.Generator()
+    gen.manual_seed(seed)
+    return torch.randperm(n, generator=gen)
+
+
+def epoch_batches(train_idx: Sequence[np.ndarray], batch_size: int, shuffle=True, drop_last=True) -> List[List[np.ndarray]]:
+    """one epoch of ConcatDataLoader: list over steps of [rows_group0, rows_group1] (global row ids).
+    The global torch CPU RNG is consumed exactly as the reference's samplers consume it: the largest loader's sampler is
+    started first?  No: zip() calls iter() on each loader in list order, but a BatchSampler only draws its permutation
+    when the first batch is requested, which zip does in list order at step 0."""
+    per_group = []
+    for idx in train_idx:
+        n = len(idx)
+        order = _random_sampler_perm(n).numpy() if shuffle else np.arange(n)
+        nb = n // batch_size if drop_last else math.ceil(n / batch_size)
+        per_group.append([np.asarray(idx)[order[k * batch_size:(k + 1) * batch_size]] for k in range(nb)])
+    lens = [len(p) for p in per_group]
+    largest = int(np.argmax(lens))
+    steps = lens[largest]
+    out = []
+    for s in range(steps):
+        out.append([per_group[g][s] if g == largest else per_group[g][s % lens[g]] for g in range(len(per_group))])
+    return out
+
+
+class TrainLoop:
+    """fwd + bwd + Adam per minibatch on one GPU (one process per GPU; see parallel.py for the data-parallel wrapper)."""
+
+    def __init__(self, engine: StepEngine, lr=1e-3, eps=0.01, weight_decay=1e-6, n_epochs_kl_warmup=400):
+        self.engine = engine
+        self.lr, self.eps, self.weight_decay = lr, eps, weight_decay
+        self.n_epochs_kl_warmup = n_epochs_kl_warmup
+        self.epoch = 0
+        self.grad_sync = None  # optional callable(engine) run between backward and the optimiser step (data parallel)
+
+    def set_epoch(self, epoch: int):
+        self.epoch = epoch
+        w = 1.0 if not self.n_epochs_kl_warmup else min(1.0, epoch / self.n_epochs_kl_warmup)
+        self.engine.set_kl_weight(w)
+
+    def step(self, batches: Sequence[GroupBatch], noise: Optional[Noise] = None):
+        e = self.engine
+        e.forward(batches, training=True, noise=noise)
+        e.backward()
+        gs = self.grad_sync(e) if self.grad_sync is not None else 1.0
+        e.adam_step(lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=gs)
+        return e.loss_terms()
+
+
+def init_params(engine: StepEngine, seed: int = 0):
+    """reference default initialisation, restated: nn.Linear -> U(+-1/sqrt(fan_in)) for weight and bias
+    (kaiming_uniform(a=sqrt(5))), BatchNorm weight 1 / bias 0, px_r ~ N(0, 1) (module/spVIPESmodule.py:115-117)."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name in engine.params.names():
+        v = engine.params.view(name)
+        shape = tuple(v.shape)
+        if name.startswith("px_r"):
+            t = torch.randn(shape, generator=gen)
+        elif ".1.weight" in name:  # BatchNorm affine
+            t = torch.ones(shape)
+        elif ".1.bias" in name:
+            t = torch.zeros(shape)
+        elif name.endswith("weight"):
+            bound = 1.0 / math.sqrt(shape[1])
+            t = (torch.rand(shape, generator=gen) * 2 - 1) * bound
+        else:  # Linear bias: fan_in of the matching weight
+            wname = name[:-4] + "weight"
+            fan_in = engine.params.view(wname).shape[1]
+            t = (torch.rand(shape, generator=gen) * 2 - 1) / math.sqrt(fan_in)
+        sd[name] = t
+    for name in engine.buffers.names():
+        v = engine.buffers.view(name)
+        sd[name] = torch.ones(v.shape) if name.endswith("running_var") else torch.zeros(v.shape)
+    engine.load_state_dict(sd)
+    return sd

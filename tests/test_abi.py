@@ -17,7 +17,7 @@ def lib_path():
 def _declared():
     src = open(os.path.join(ROOT, "include", "spvipes_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\bint\s+(spv_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(?:int|long long)\s+(spv_\w+)\s*\(", src)))
 
 
 def test_header_symbols_exported(lib_path):
@@ -34,7 +34,7 @@ def test_binding_table_matches_header(lib_path):
     src = open(os.path.join(ROOT, "include", "spvipes_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     for name, args in _lib._SIGS.items():
-        m = re.search(r"\bint\s+" + name + r"\s*\((.*?)\)\s*;", src, flags=re.S)
+        m = re.search(r"\b(?:int|long long)\s+" + name + r"\s*\((.*?)\)\s*;", src, flags=re.S)
         assert m, name
         decl = m.group(1).strip()
         n = 0 if decl in ("", "void") else len(decl.split(","))
