@@ -195,23 +195,39 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     loop.set_epoch(1)
+    use_graph = not args.no_graph
+    rows_cur = [torch.empty(B, dtype=torch.int32, device=dev) for _ in (0, 1)]
+    static_batches = [GroupBatch(X=data.X[g], rows=rows_cur[g], labels=data.labels[g], labels_per_cell=True) for g in (0, 1)]
+    per_step_launches = None
+    if use_graph:
+        for g in (0, 1):
+            rows_cur[g].copy_(rows[g][0])
+        c0 = lib.spv_launch_count()
+        graph = loop.capture(static_batches)
+        per_step_launches = (lib.spv_launch_count() - c0) // 3  # 2 warm-up steps + 1 captured step
+
+    def run_step(s):
+        if use_graph:
+            for g in (0, 1):
+                rows_cur[g].copy_(rows[g][s], non_blocking=True)
+            graph.replay()
+        else:
+            loop.step(batches_for(s))
+
     for s in range(W):
-        loop.step(batches_for(s))
+        run_step(s)
     barrier()
     clk = ClockSampler(local_rank)
     if rank == 0:
         clk.start()
     n0 = lib.spv_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nb_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * K)]
-    eng.nb_events = iter(nb_ev)
     ev0.record()
     for s in range(W, total):
-        loop.step(batches_for(s))
+        run_step(s)
     ev1.record()
     barrier()
-    eng.nb_events = None
-    launches = lib.spv_launch_count() - n0
+    launches = per_step_launches * K if use_graph else lib.spv_launch_count() - n0
     ms = ev0.elapsed_time(ev1)
     if dist is not None:
         t = torch.tensor([ms], device=dev)
@@ -221,6 +237,14 @@ def run_ours(args):
     loss = float(eng.loss_out[0].item())
     value = world * 2 * B * K / (ms * 1e-3)
 
+    # ---- the NB-loglik kernel alone, timed with CUDA events on the launching stream: K eager forward passes over fresh
+    #      minibatches (the graph replays above cannot carry timing events); every launch of the sweep is bracketed.
+    nb_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * K)]
+    eng.nb_events = iter(nb_ev)
+    for s in range(W, total):
+        eng.forward(batches_for(s), training=True)
+    torch.cuda.synchronize()
+    eng.nb_events = None
     # ---- NB-loglik kernel roofline (forward sweep of the fused decoder + NB kernel), timed live with CUDA events
     nb_ms = float(np.mean([a.elapsed_time(b) for a, b in nb_ev]))
     KM = 256 + S_DIM + P_DIM
@@ -232,7 +256,7 @@ def run_ours(args):
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": nb_ms}
 
     # ---- end-to-end through the public step API with HOST (pinned) minibatches
-    e2e = measure_e2e(loop, data, rows, B, genes, K, W, dev, dist, world)
+    e2e = None if args.no_e2e else measure_e2e(loop, data, rows, B, genes, K, W, dev, dist, world, use_graph)
 
     if rank == 0:
         cpu = None
@@ -248,12 +272,13 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def measure_e2e(loop, data, rows, B, genes, K, W, dev, dist, world):
+def measure_e2e(loop, data, rows, B, genes, K, W, dev, dist, world, use_graph=True):
     """same metric through the public step call with host buffers: per step the two groups' count minibatches and labels are
     copied from pinned host memory (double-buffered on a copy stream) and the loss terms are read back."""
     from spvipes_b200.engine import GroupBatch
     total = K + W
-    host_x = [[data.X[g][rows[g][s].long()].cpu().pin_memory() for s in range(total)] for g in (0, 1)]
+    host_x = [[data.X[g].view(torch.int16)[rows[g][s].long()].view(torch.uint16).cpu().pin_memory() for s in range(total)]
+              for g in (0, 1)]
     host_l = [[data.labels[g][rows[g][s].long()].cpu().pin_memory() for s in range(total)] for g in (0, 1)]
     dev_x = [[torch.empty(B, genes, dtype=torch.uint16, device=dev) for _ in (0, 1)] for _ in (0, 1)]  # [buf][group]
     dev_l = [[torch.empty(B, dtype=torch.int32, device=dev) for _ in (0, 1)] for _ in (0, 1)]
@@ -262,6 +287,13 @@ def measure_e2e(loop, data, rows, B, genes, K, W, dev, dist, world):
     ready = [torch.cuda.Event() for _ in (0, 1)]
     freed = [torch.cuda.Event() for _ in (0, 1)]
     main = torch.cuda.current_stream(dev)
+    bufs = [[GroupBatch(X=dev_x[b][g], labels=dev_l[b][g]) for g in (0, 1)] for b in (0, 1)]
+    graphs = None
+    if use_graph:
+        for b in (0, 1):
+            for g in (0, 1):
+                dev_x[b][g].copy_(host_x[g][0]); dev_l[b][g].copy_(host_l[g][0])
+        graphs = [loop.capture(bufs[b]) for b in (0, 1)]
 
     def upload(s):
         b = s % 2
@@ -291,7 +323,10 @@ def measure_e2e(loop, data, rows, B, genes, K, W, dev, dist, world):
         if s + 1 < total and s + 1 != W:
             upload(s + 1)
         main.wait_event(ready[b])
-        loop.step([GroupBatch(X=dev_x[b][g], labels=dev_l[b][g]) for g in (0, 1)])
+        if graphs is not None:
+            graphs[b].replay()
+        else:
+            loop.step(bufs[b])
         freed[b].record(main)
         out_host.copy_(loop.engine.loss_out, non_blocking=True)
     ev1.record(main)
@@ -304,7 +339,8 @@ def measure_e2e(loop, data, rows, B, genes, K, W, dev, dist, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     return {"value": world * 2 * B * K / (ms * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": 32, "ms_per_step": ms / K, "api": "spvipes_b200.trainer.TrainLoop.step (host uint16 minibatches)"}
+            "d2h_bytes_per_step": 32, "ms_per_step": ms / K,
+            "api": "spvipes_b200.trainer.TrainLoop (host uint16 minibatches in pinned memory, loss terms read back)"}
 
 
 def main():
@@ -316,6 +352,8 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-fed measurement")
     args = ap.parse_args()
     if args.workload is None:
         args.workload = "C2"

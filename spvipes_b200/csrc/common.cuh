@@ -65,6 +65,20 @@ __device__ __forceinline__ float load_src(const void* p, long i) {
     return c == 0.0f ? 0.0f : logf(1.0f + c);  // torch.log(1 + x), reference :433
 }
 
+// raw load / transform split, so that a batch of loads can be issued before any transform code runs
+template <int SRC>
+__device__ __forceinline__ unsigned int load_raw(const void* p, long i) {
+    if (SRC == SPV_SRC_U16_LOG1P) return (unsigned int)__ldg(reinterpret_cast<const unsigned short*>(p) + i);
+    return __ldg(reinterpret_cast<const unsigned int*>(p) + i);
+}
+template <int SRC>
+__device__ __forceinline__ float xform_raw(unsigned int r) {
+    if (SRC == SPV_SRC_F32) return __uint_as_float(r);
+    if (SRC == SPV_SRC_U16_LOG1P) return r == 0u ? 0.0f : log1pf((float)r);
+    float c = __uint_as_float(r);
+    return c == 0.0f ? 0.0f : logf(1.0f + c);
+}
+
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 counter RNG (for in-kernel reparameterisation noise and dropout keep masks)
 // ---------------------------------------------------------------------------------------

@@ -94,6 +94,35 @@ class TrainLoop:
         e.adam_step(lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=gs)
         return e.loss_terms()
 
+    def capture(self, batches: Sequence[GroupBatch], noise: Optional[Noise] = None) -> "torch.cuda.CUDAGraph":
+        """record one step (every kernel launch of forward, backward, gradient sync and Adam) into a CUDA graph.
+        `batches` must reference STATIC device buffers (count matrix, row-index buffer, labels): the caller refreshes their
+        contents before each replay.  Steps are launch-latency bound at the BASELINE shapes (~100 kernels of 2-100 us),
+        so replaying a graph instead of issuing the launches from Python is what keeps the GPU busy.
+        Engine state (parameters, Adam moments, BatchNorm running statistics, step counter) is restored after the
+        warm-up launches that precede the capture, so capturing does not advance training."""
+        e = self.engine
+        keep = [e.params.flat.clone(), e.buffers.flat.clone(), e.step_dev.clone(),
+                None if e.adam_m is None else e.adam_m.clone(), None if e.adam_v is None else e.adam_v.clone()]
+        cur = torch.cuda.current_stream(e.device)
+        side = torch.cuda.Stream(device=e.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.step(batches, noise)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(e.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step(batches, noise)
+        torch.cuda.synchronize(e.device)
+        e.params.flat.copy_(keep[0]); e.buffers.flat.copy_(keep[1]); e.step_dev.copy_(keep[2])
+        if keep[3] is None:
+            e.adam_m.zero_(); e.adam_v.zero_()
+        else:
+            e.adam_m.copy_(keep[3]); e.adam_v.copy_(keep[4])
+        return graph
+
 
 def init_params(engine: StepEngine, seed: int = 0):
     """reference default initialisation, restated: nn.Linear -> U(+-1/sqrt(fan_in)) for weight and bias
