@@ -48,6 +48,17 @@ int spv_gemm(int srcA, int transA, int srcB, int transB, const void* A, long lon
              long long sB, long long sC, const float* bias, long long sBias, int relu, int accumulate, int splits, float* ws,
              void* stream);
 
+/* bf16 tensor-core GEMM (tcgen05.mma, TMEM accumulator, TMA-fed): C[M,N] (+)= act(A B^T + bias), fp32 output.
+ * a_mn = 0: A stored [M][K], 1: A stored [K][M];  b_mn = 0: B stored [N][K], 1: B stored [K][N]; lda / ldb in bf16
+ * elements, multiples of 8, bases 16-byte aligned.  Same call sites as spv_gemm, for the "bf16 tensor-core path". */
+int spv_tc_gemm(int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb, float* C, long long ldc, int M,
+                int N, int K, const float* bias, int relu, int accumulate, int splits, float* ws, void* stream);
+/* bf16 staging of GEMM operands: dst[r, :C] = bf16(src[r, :C]), zero padded up to ld_dst */
+int spv_to_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, int R, int C, void* stream);
+/* T[b, :G] = bf16(log1p(X[rows[b], :G]))   module/spVIPESmodule.py:428-433 */
+int spv_counts_to_bf16(int src, const void* X, long long ldx, const int* rows, void* dst, long long ld_dst, int B, int G,
+                       void* stream);
+
 /* lib[b] = log(sum_g log1p(x[b,g]))   module/spVIPESmodule.py:433-435 */
 int spv_library_size(int src, const void* X, long long ldx, const int* rows, int B, int G, float* lib, void* stream);
 

@@ -1,0 +1,340 @@
+// bf16 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma with the
+// fp32 accumulator in TMEM -> tcgen05.ld epilogue.  One 128 x BN output tile per CTA, warp-specialised:
+//   warp 0: TMA producer (one elected lane)      warp 1: TMEM allocator + MMA issuer (one elected lane)
+//   warps 2-5: epilogue (TMEM -> registers -> global), warp w owns TMEM lanes 32 * (w % 4) ..
+// Both operands may be K-major ([rows][K]) or MN-major ([K][rows]), so weight / activation gradients
+// (dW = dY^T X, dX = dY W) run without materialising transposes.
+// This is the "bf16 tensor-core path" of BASELINE.json's north_star (parity gate 1e-2); the fp32 SIMT path of
+// gemm_simt.cu is the 1e-4 mode.  Replaces the cuBLAS GEMMs behind nn.Linear in reference nn/networks.py:119, 323-325.
+#include "tc_common.cuh"
+#include "../../include/spvipes_b200.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int STAGES = 4;
+constexpr int THREADS = 192;
+
+struct TcParams {
+    float* C;
+    const float* bias;
+    float* ws;
+    long ldc;
+    int M, N, K, relu, accumulate, splits, kb_per_split;
+};
+
+template <int BN>
+struct Smem {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                             const __grid_constant__ CUtensorMap mapB, TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    using S = Smem<BN>;
+    const uint32_t raw = tc::smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    uint8_t* tiles = smem_raw + pad;  // 1024-byte aligned (SWIZZLE_128B atoms)
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * S::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int split = blockIdx.z;
+    const int num_kb_total = (p.K + BK - 1) / BK;
+    const int kb_begin = split * p.kb_per_split;
+    const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+    const int num_kb = max(kb_end - kb_begin, 0);
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&mapA);
+        tc::tma_prefetch_desc(&mapB);
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full[s], 1);
+            tc::mbar_init(&empty[s], 1);
+        }
+        tc::mbar_init(tmem_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (tc::elect_one()) {
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                tc::mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* a_dst = tiles + s * S::STAGE_BYTES;
+                uint8_t* b_dst = a_dst + S::A_BYTES;
+                tc::mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                const int k0 = (kb_begin + i) * BK;
+                if (!A_MN) {
+                    tc::tma_load_2d(&mapA, &full[s], a_dst, k0, m0);  // box {64 k, 128 rows}
+                } else {
+#pragma unroll
+                    for (int h = 0; h < BM / 64; ++h) tc::tma_load_2d(&mapA, &full[s], a_dst + h * 8192, m0 + 64 * h, k0);
+                }
+                if (!B_MN) {
+                    tc::tma_load_2d(&mapB, &full[s], b_dst, k0, n0);  // box {64 k, BN rows}
+                } else {
+#pragma unroll
+                    for (int h = 0; h < BN / 64; ++h) tc::tma_load_2d(&mapB, &full[s], b_dst + h * 8192, n0 + 64 * h, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, A_MN, B_MN);
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                tc::mbar_wait(&full[s], ph);
+                tc::fence_after_sync();
+                const uint32_t a_base = tc::smem_u32(tiles + s * S::STAGE_BYTES);
+                const uint32_t b_base = a_base + S::A_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; ++kk) {
+                    // K-major: 16 k = 32 bytes along the swizzled 128-byte row; SBO = 1024 (8-row groups)
+                    // MN-major: 16 k = 16 rows of 128 bytes = 2048 bytes; LBO = 8192 (next 64-wide block), SBO = 1024
+                    const uint64_t da = A_MN ? tc::smem_desc(a_base + kk * 2048, 8192, 1024) : tc::smem_desc(a_base + kk * 32, 16, 1024);
+                    const uint64_t db = B_MN ? tc::smem_desc(b_base + kk * 2048, 8192, 1024) : tc::smem_desc(b_base + kk * 32, 16, 1024);
+                    tc::umma_bf16(tmem_base, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                }
+                tc::umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+            }
+            tc::umma_commit(tmem_full);  // accumulator complete
+        }
+    } else {
+        // ================= epilogue (warps 2..5) =================
+        const int lane_base = (warp & 3) * 32;
+        const int m = m0 + lane_base + lane;
+        if (num_kb > 0) {
+            tc::mbar_wait(tmem_full, 0);
+            tc::fence_after_sync();
+        }
+        float* out;
+        long ld;
+        if (p.splits > 1) {
+            out = p.ws + (size_t)split * p.M * p.N;
+            ld = p.N;
+        } else {
+            out = p.C;
+            ld = p.ldc;
+        }
+        const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            if (num_kb > 0) {
+                tc::tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, r);
+                tc::tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            if (m >= p.M) continue;
+            const int nb = n0 + c0;
+            if (nb >= p.N) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.splits == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (p.bias && nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
+                    if (p.relu) v[j] = fmaxf(v[j], 0.0f);
+                }
+            }
+            float* dst = out + (size_t)m * ld + nb;
+            const bool acc = p.accumulate && p.splits == 1;
+            if (vec && nb + 32 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    if (acc) {
+                        float4 c = *reinterpret_cast<const float4*>(dst + j);
+                        o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+                    }
+                    *reinterpret_cast<float4*>(dst + j) = o;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (nb + j < p.N) dst[j] = acc ? dst[j] + v[j] : v[j];
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc(tmem_base, BN);
+    }
+}
+
+__global__ void tc_splitk_reduce_kernel(TcParams p) {
+    long total = (long)p.M * p.N;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int n = (int)(i % p.N);
+        long m = i / p.N;
+        float v = 0.0f;
+        for (int s = 0; s < p.splits; ++s) v += p.ws[(size_t)s * total + i];
+        if (p.bias) v += p.bias[n];
+        if (p.relu) v = fmaxf(v, 0.0f);
+        float* c = p.C + m * p.ldc + n;
+        *c = p.accumulate ? (*c + v) : v;
+    }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || !ptr) return nullptr;
+    fn = reinterpret_cast<EncodeFn>(ptr);
+    return fn;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+    using S = Smem<BN>;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
+            return SPV_ERR_LAUNCH;
+        configured = true;
+    }
+    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
+    tc_gemm_kernel<BN, A_MN, B_MN><<<grid, THREADS, S::TOTAL, st>>>(ma, mb, p);
+    SPV_CHECK_LAUNCH();
+    if (p.splits > 1) {
+        long total = (long)p.M * p.N;
+        int blocks = (int)min((long)148 * 8, (total + 255) / 256);
+        tc_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p);
+        SPV_CHECK_LAUNCH();
+    }
+    return SPV_OK;
+}
+
+template <int BN>
+int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch<BN, false, false>(ma, mb, p, st);
+    if (!a_mn && b_mn) return launch<BN, false, true>(ma, mb, p, st);
+    if (a_mn && !b_mn) return launch<BN, true, false>(ma, mb, p, st);
+    return launch<BN, true, true>(ma, mb, p, st);
+}
+
+}  // namespace
+
+int spv_make_tensor_map_bf16(CUtensorMap* map, const void* base, unsigned long long inner, unsigned long long outer,
+                             unsigned long long ld_elems, unsigned box_inner, unsigned box_outer) {
+    EncodeFn enc = get_encode();
+    if (!enc) return SPV_ERR_LAUNCH;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld_elems & 7) || box_inner * 2 > 128 || box_outer > 256) return SPV_ERR_ARG;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SPV_OK : SPV_ERR_ARG;
+}
+
+// C[M, N] (+)= act(A B^T + bias), bf16 operands, fp32 accumulate / output.
+//   a_mn == 0: A stored [M][K] (lda elements per row);  a_mn == 1: A stored [K][M]
+//   b_mn == 0: B stored [N][K];                          b_mn == 1: B stored [K][N]
+extern "C" int spv_tc_gemm(int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb, float* C,
+                           long long ldc, int M, int N, int K, const float* bias, int relu, int accumulate, int splits,
+                           float* ws, void* stream) {
+    if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return SPV_ERR_ARG;
+    if (splits < 1) splits = 1;
+    const int num_kb = (K + BK - 1) / BK;
+    if (splits > num_kb) splits = num_kb;
+    int kb_per = (num_kb + splits - 1) / splits;
+    splits = (num_kb + kb_per - 1) / kb_per;
+    if (splits > 1 && !ws) return SPV_ERR_ARG;
+    const int BN = N <= 64 ? 64 : 128;
+    CUtensorMap ma, mb;
+    int rc;
+    if (!a_mn) rc = spv_make_tensor_map_bf16(&ma, A, (unsigned long long)K, (unsigned long long)M, (unsigned long long)lda, 64, BM);
+    else rc = spv_make_tensor_map_bf16(&ma, A, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, 64, 64);
+    if (rc != SPV_OK) return rc;
+    if (!b_mn) rc = spv_make_tensor_map_bf16(&mb, B, (unsigned long long)K, (unsigned long long)N, (unsigned long long)ldb, 64, BN);
+    else rc = spv_make_tensor_map_bf16(&mb, B, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldb, 64, 64);
+    if (rc != SPV_OK) return rc;
+    TcParams p;
+    p.C = C; p.bias = bias; p.ws = ws; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu; p.accumulate = accumulate;
+    p.splits = splits; p.kb_per_split = kb_per;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (BN == 64) return dispatch_major<64>(a_mn, b_mn, ma, mb, p, st);
+    return dispatch_major<128>(a_mn, b_mn, ma, mb, p, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// bf16 operand staging for the tensor-core path
+// ---------------------------------------------------------------------------------------
+// dst[r, c] = bf16(src[r, c]) for c < C, 0 for C <= c < ld_dst  (ld_dst = C rounded up to a multiple of 8)
+__global__ void to_bf16_kernel(const float* __restrict__ src, long ld_src, __nv_bfloat16* __restrict__ dst, long ld_dst, int R, int C) {
+    long total = (long)R * ld_dst;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % ld_dst);
+        long r = i / ld_dst;
+        dst[i] = __float2bfloat16(c < C ? src[r * ld_src + c] : 0.0f);
+    }
+}
+
+extern "C" int spv_to_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, int R, int C, void* stream) {
+    if (!src || !dst || R <= 0 || C <= 0 || ld_dst < C) return SPV_ERR_ARG;
+    long total = (long)R * ld_dst;
+    int blocks = (int)min((long)148 * 16, (total + 255) / 256);
+    to_bf16_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, R, C);
+    SPV_CHECK_LAUNCH();
+    return SPV_OK;
+}
+
+// T[b, g] = bf16(log1p(X[rows[b], g]))   (the encoder's input, reference module/spVIPESmodule.py:428-433), zero padded to ld_dst
+template <int SRC>
+__global__ void counts_to_bf16_kernel(const void* __restrict__ X, long ldx, const int* __restrict__ rows, __nv_bfloat16* __restrict__ dst,
+                                      long ld_dst, int B, int G) {
+    long total = (long)B * ld_dst;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int g = (int)(i % ld_dst);
+        long b = i / ld_dst;
+        float v = 0.0f;
+        if (g < G) v = load_src<SRC>(X, (rows ? (long)rows[b] : b) * ldx + g);
+        dst[i] = __float2bfloat16(v);
+    }
+}
+
+extern "C" int spv_counts_to_bf16(int src, const void* X, long long ldx, const int* rows, void* dst, long long ld_dst, int B, int G,
+                                  void* stream) {
+    if (!X || !dst || B <= 0 || G <= 0 || ld_dst < G) return SPV_ERR_ARG;
+    long total = (long)B * ld_dst;
+    int blocks = (int)min((long)148 * 16, (total + 255) / 256);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
+    if (src == SPV_SRC_U16_LOG1P) counts_to_bf16_kernel<SPV_SRC_U16_LOG1P><<<blocks, 256, 0, st>>>(X, ldx, rows, d, ld_dst, B, G);
+    else if (src == SPV_SRC_F32_LOG1P) counts_to_bf16_kernel<SPV_SRC_F32_LOG1P><<<blocks, 256, 0, st>>>(X, ldx, rows, d, ld_dst, B, G);
+    else return SPV_ERR_ARG;
+    SPV_CHECK_LAUNCH();
+    return SPV_OK;
+}
