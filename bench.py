@@ -174,7 +174,7 @@ def run_ours(args):
     lib = L.load()
     L.check(lib.spv_arch_check(local_rank), "spv_arch_check (this library is sm_100a only)")
     data = synth.make_counts((n_cells, n_cells), (genes, genes), n_labels, device=dev, seed=1234 + 17 * rank)
-    eng = StepEngine((genes, genes), H, S_DIM, P_DIM, 0.1, mode, device=dev, seed=rank)
+    eng = StepEngine((genes, genes), H, S_DIM, P_DIM, 0.1, mode, device=dev, seed=rank, precision=args.precision)
     init_params(eng, 0)
     loop = TrainLoop(eng)
     if world > 1:
@@ -264,7 +264,8 @@ def run_ours(args):
             v, cms, cores, sample = cpu_reference_cells_per_sec(workload, args.cpu_steps, 1)
             cpu = {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample, "ms_per_step": cms}
         line = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16 tensor-core GEMMs, f32 accumulate / elementwise / Adam" if args.precision == "bf16" else "f32",
                 "data": "synthetic", "config": workload_config(workload, world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "final_loss": loss}
         print(json.dumps(line), flush=True)
@@ -353,6 +354,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying a CUDA graph")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16: tcgen05 tensor-core path for the large GEMMs (parity gate 1e-2); fp32: SIMT path (1e-4)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-fed measurement")
     args = ap.parse_args()
     if args.workload is None:

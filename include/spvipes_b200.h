@@ -115,11 +115,12 @@ int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, 
 /* fused decoder + NB-mixture likelihood sweeps.  ptrs (SPV_DEC_NPTR): X, rows, amix, wfold, wm, bm, genec, lib, part_stats,
  * rowc, pi, part_nb, dyp, dys, dpi, colpart, rec.   nn/networks.py:314-325; module/spVIPESmodule.py:759, 817-824 */
 #define SPV_DEC_NPTR 17
-/* phases: bit 0 = gene-axis softmax normaliser sweep, bit 1 = mixture GEMM + NB log-likelihood sweep (3 = both) */
+/* phases: bit 0 = gene-axis softmax normaliser sweep, bit 1 = mixture GEMM + NB log-likelihood sweep (3 = both),
+ * bit 2 = the mixture logits are already in `pi` (written by spv_tc_gemm), skip the in-kernel fp32 GEMM */
 int spv_dec_nb_fwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P, int S,
                    int phases, void* stream);
 int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P, int S,
-                   float scale, float* colsum, void* stream);
+                   float scale, float* colsum, void* dpi_bf16, long long ld_dpi_bf16, void* stream);
 /* ptrs (18): Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm, wv, wmx */
 int spv_dec_gene_bwd(const void* const* ptrs, int B, int G, int P, int S, void* stream);
 int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* v1, const float* M,

@@ -7,6 +7,7 @@
 // No [B, G] softmax / rate tensor is materialised: the per-gene BatchNorm statistics of z W^T are obtained in closed
 // form from mean(z) and Cov(z) (spv_dec_fold), the gene-axis softmax normaliser by a first tile sweep
 // (pass STATS), the likelihood and the row sums the backward needs by a second sweep (pass NB).
+#include <cuda_bf16.h>
 #include "gemm_simt.cuh"
 #include "../../include/spvipes_b200.h"
 
@@ -223,6 +224,8 @@ struct DecP {
     float* colpart;                                      // [nTB, 4, G]
     int B, G, HD, P, S;
     float scale;
+    int pi_ready;                                        // PASS_NB: pi already holds the mixture logits (tensor-core GEMM)
+    __nv_bfloat16* dpi_bf16; long ld_dpi_bf16;           // PASS_BWD: write d pi as bf16 (operand of the tensor-core GEMMs)
 };
 
 enum { PASS_STATS = 0, PASS_NB = 1, PASS_BWD = 2 };
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(GT_THREADS) dec_tile_kernel(DecP p) {
     const float* azz = p.amix + p.HD;
     tile_mainloop<SPV_SRC_F32, false, SPV_SRC_F32, true>(lp, azz, p.ld_amix, nullptr, p.wfold, KZ, nullptr, B, G, 0, p.P, m0, n0, sm);
     tile_mainloop<SPV_SRC_F32, false, SPV_SRC_F32, true>(ls, azz + p.P, p.ld_amix, nullptr, p.wfold + p.P, KZ, nullptr, B, G, 0, p.S, m0, n0, sm);
-    if (PASS == PASS_NB)
+    if (PASS == PASS_NB && !p.pi_ready)
         tile_mainloop<SPV_SRC_F32, false, SPV_SRC_F32, true>(pi, p.amix, p.ld_amix, nullptr, p.wm, KMIX, nullptr, B, G, 0, KMIX, m0, n0, sm);
 
     // per-gene constants of this thread's 4 genes
@@ -316,10 +319,10 @@ __global__ void __launch_bounds__(GT_THREADS) dec_tile_kernel(DecP p) {
                 int n = n0 + tx * 4 + j;
                 if (mok && nok[j]) {
                     float t = load_src<SRC>(p.X, xr + n);
-                    float piv = pi[i][j] + bm[j];
+                    float piv = p.pi_ready ? p.pi[(long)m * G + n] : pi[i][j] + bm[j];
                     NbFwd o = nb_forward(t, lp[i][j] + cp[j], ls[i][j] + cs[j], piv, th[j], lte[j], lgx[j], Rp, Rs);
                     sll += o.ll; sep += o.ep; ses += o.es;
-                    p.pi[(long)m * G + n] = piv;
+                    if (!p.pi_ready) p.pi[(long)m * G + n] = piv;
                 }
             }
             sll = half_warp_sum(sll);
@@ -342,7 +345,8 @@ __global__ void __launch_bounds__(GT_THREADS) dec_tile_kernel(DecP p) {
                                           inv_elib, p.scale);
                     p.dyp[(long)m * G + n] = o.dyp;
                     p.dys[(long)m * G + n] = o.dys;
-                    p.dpi[(long)m * G + n] = o.dpi;
+                    if (p.dpi_bf16) p.dpi_bf16[(long)m * p.ld_dpi_bf16 + n] = __float2bfloat16(o.dpi);
+                    else p.dpi[(long)m * G + n] = o.dpi;
                     csum[0][j] += o.dyp; csum[1][j] += o.dys; csum[2][j] += o.dpi; csum[3][j] += o.dth;
                 }
             }
@@ -408,6 +412,7 @@ static void fill_decp(DecP& p, const void* const* ptrs, long long ldx, long long
     p.part_stats = (float*)ptrs[8]; p.rowc = (float*)ptrs[9]; p.pi = (float*)ptrs[10]; p.part_nb = (float*)ptrs[11];
     p.dyp = (float*)ptrs[12]; p.dys = (float*)ptrs[13]; p.dpi = (float*)ptrs[14]; p.colpart = (float*)ptrs[15];
     p.ldx = ldx; p.ld_amix = ld_amix; p.B = B; p.G = G; p.HD = HD; p.P = P; p.S = S; p.scale = scale;
+    p.pi_ready = 0; p.dpi_bf16 = nullptr; p.ld_dpi_bf16 = 0;
 }
 
 // ptrs (SPV_DEC_NPTR = 17): X, rows, amix, wfold, wm, bm, genec, lib, part_stats, rowc, pi, part_nb, dyp, dys, dpi,
@@ -420,6 +425,7 @@ extern "C" int spv_dec_nb_fwd(int src, const void* const* ptrs, long long ldx, l
         if (!ptrs[i]) return SPV_ERR_ARG;
     DecP p;
     fill_decp(p, ptrs, ldx, ld_amix, B, G, HD, P, S, 0.0f);
+    p.pi_ready = (phases & 4) ? 1 : 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     dim3 grid((G + GT_BN - 1) / GT_BN, (B + GT_BM - 1) / GT_BM);
     const int nTG = grid.x;
@@ -452,13 +458,16 @@ __global__ void colpart_reduce_kernel(const float* __restrict__ colpart, int nTB
 // Backward sweep: writes dyp, dys, dpi [B, G] (gradients w.r.t. the two BatchNorm outputs and the mixture logits)
 // and colsum [4, G] = column sums of dyp, dys, dpi and d loss / d theta.   scale = -grad_scale / B.
 extern "C" int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P,
-                              int S, float scale, float* colsum, void* stream) {
+                              int S, float scale, float* colsum, void* dpi_bf16, long long ld_dpi_bf16, void* stream) {
     if (!ptrs || !colsum || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
-    const int need[] = {0, 2, 3, 6, 7, 9, 10, 12, 13, 14, 15};
+    const int need[] = {0, 2, 3, 6, 7, 9, 10, 12, 13, 15};
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
+    if (!ptrs[14] && !dpi_bf16) return SPV_ERR_ARG;
     DecP p;
     fill_decp(p, ptrs, ldx, ld_amix, B, G, HD, P, S, scale);
+    p.dpi_bf16 = reinterpret_cast<__nv_bfloat16*>(dpi_bf16);
+    p.ld_dpi_bf16 = ld_dpi_bf16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     dim3 grid((G + GT_BN - 1) / GT_BN, (B + GT_BM - 1) / GT_BM);
     if (src == SPV_SRC_U16_LOG1P) dec_tile_kernel<PASS_BWD, SPV_SRC_U16_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);

@@ -157,7 +157,7 @@ class Noise:
 
 
 class _GroupWS:
-    def __init__(self, B, G, d: Dims, dev, with_grad: bool):
+    def __init__(self, B, G, d: Dims, dev, with_grad: bool, bf16: bool = False):
         H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         self.B, self.G = B, G
@@ -182,8 +182,23 @@ class _GroupWS:
         self.expert = f(B, 2 * S)  # cluster mode: plan-weighted expert statistics
         # split-K workspace: the largest user is fc1 forward (B x 2H) and d Amix (B x KMIX)
         self.splits_fc1 = max(1, min(16, G // 512))
-        self.splits_g = max(1, min(16, G // 512))
-        self.ws = f(max(self.splits_fc1 * B * 2 * H, self.splits_g * B * KMIX, self.splits_g * KZ * KZ, 1))
+        self.splits_g = max(1, min(32, G // 256))       # reductions over the gene axis with a small output
+        self.splits_b = max(1, min(8, B // 64))         # reductions over the minibatch with a small output
+        big = max(2 * H, KMIX)
+        self.ws = f(max(32 * B * big, self.splits_b * G * KZ, 2 * self.splits_b * big * big, 1))
+        r8 = lambda x: (x + 7) // 8 * 8
+        self.Gp, self.KMp = r8(G), r8(KMIX)
+        if bf16:
+            h = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
+            self.Tb, self.W1b = h(B, self.Gp), h(2 * H, self.Gp)
+            self.Wmb, self.amixb = h(G, self.KMp), h(B, self.KMp)
+            if with_grad:
+                self.dpib, self.dh1b = h(B, self.Gp), h(B, 2 * H)
+            # split-K factors of the tensor-core GEMMs (128-wide tiles): fill the 148 SMs
+            tiles = ((B + 127) // 128) * ((2 * H + 127) // 128)
+            self.tc_splits_fc1 = max(1, min(148 // tiles, (G + 63) // 64 // 2))
+            tiles = ((B + 127) // 128) * ((KMIX + 127) // 128)
+            self.tc_splits_damix = max(1, min(148 // tiles, (G + 63) // 64 // 2))
         if with_grad:
             self.dyp, self.dys, self.dpi = f(B, G), f(B, G), f(B, G)
             self.colpart, self.colsum = f(self.nTB, 4, G), f(4, G)
@@ -202,7 +217,14 @@ class StepEngine:
     """fwd / bwd / Adam of the spVIPES step for two groups on one GPU."""
 
     def __init__(self, genes: Tuple[int, int], n_hidden=128, n_shared=25, n_private=10, dropout_rate=0.1, mode="label",
-                 device="cuda", seed: int = 0, plan: Optional[torch.Tensor] = None):
+                 device="cuda", seed: int = 0, plan: Optional[torch.Tensor] = None, precision: str = "fp32"):
+        """precision: "fp32" = fp32 SIMT GEMMs everywhere (parity gate 1e-4); "bf16" = the large contractions (encoder fc1
+        forward / weight gradient, decoder mixture GEMM forward / weight gradient / input gradient) run on the tcgen05
+        tensor-core path with bf16 operands and fp32 accumulation (parity gate 1e-2, BASELINE.json north_star)."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        self.bf16 = precision == "bf16"
         self.lib = L.load()
         self.d = Dims(tuple(int(x) for x in genes), int(n_hidden), int(n_shared), int(n_private))
         if self.d.n_private > self.d.n_shared:
@@ -246,10 +268,14 @@ class StepEngine:
         L.check(self.lib.spv_gemm(srcA, ta, srcB, tb, A, lda, L.ptr(rowsA), B, ldb, L.ptr(rowsB), C, ldc, M, N, K, batch,
                                   sA, sB, sC, bias, sBias, relu, acc, splits, L.ptr(ws), self._stream()), "spv_gemm")
 
+    def _tc_gemm(self, A, B, C, M, N, K, *, lda, ldb, ldc, a_mn=0, b_mn=0, bias=None, relu=0, acc=0, splits=1, ws=None):
+        L.check(self.lib.spv_tc_gemm(a_mn, b_mn, A, lda, B, ldb, C, ldc, M, N, K, bias, relu, acc, splits, L.ptr(ws),
+                                     self._stream()), "spv_tc_gemm")
+
     def workspace(self, B0, B1, with_grad=True):
         key = (B0, B1, with_grad)
         if key not in self._ws:
-            self._ws[key] = [_GroupWS(B, G, self.d, self.device, with_grad) for B, G in zip((B0, B1), self.d.genes)]
+            self._ws[key] = [_GroupWS(B, G, self.d, self.device, with_grad, self.bf16) for B, G in zip((B0, B1), self.d.genes)]
         return self._ws[key]
 
     @staticmethod
@@ -280,8 +306,14 @@ class StepEngine:
             xptr = bt.X.data_ptr() + bt.col0 * esz
             srcs.append((src, xptr, ldx))
             L.check(lib.spv_library_size(src, xptr, ldx, L.ptr(bt.rows), B, G, L.ptr(w.lib), st), "spv_library_size")
-            self._gemm(xptr, L.ptr(self.P(g, "W1")), L.ptr(w.h1), B, 2 * H, G, lda=ldx, ldb=G, ldc=2 * H, tb=1, srcA=src,
-                       rowsA=bt.rows, bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.splits_fc1, ws=w.ws)
+            if self.bf16:
+                L.check(lib.spv_counts_to_bf16(src, xptr, ldx, L.ptr(bt.rows), L.ptr(w.Tb), w.Gp, B, G, st), "spv_counts_to_bf16")
+                L.check(lib.spv_to_bf16(L.ptr(self.P(g, "W1")), G, L.ptr(w.W1b), w.Gp, 2 * H, G, st), "spv_to_bf16")
+                self._tc_gemm(L.ptr(w.Tb), L.ptr(w.W1b), L.ptr(w.h1), B, 2 * H, G, lda=w.Gp, ldb=w.Gp, ldc=2 * H,
+                              bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.tc_splits_fc1, ws=w.ws)
+            else:
+                self._gemm(xptr, L.ptr(self.P(g, "W1")), L.ptr(w.h1), B, 2 * H, G, lda=ldx, ldb=G, ldc=2 * H, tb=1, srcA=src,
+                           rowsA=bt.rows, bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.splits_fc1, ws=w.ws)
             self._gemm(L.ptr(w.h1), L.ptr(self.P(g, "W2")), L.ptr(w.h2), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, tb=1, batch=2,
                        sA=H, sB=H * H, sC=H, bias=L.ptr(self.P(g, "b2")), sBias=H, relu=1)
             if training:
@@ -325,7 +357,12 @@ class StepEngine:
             evs = next(self.nb_events) if self.nb_events is not None else None
             if evs is not None:
                 evs[0].record()
-            L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 2, st), "spv_dec_nb_fwd")
+            if self.bf16:  # mixture logits on the tensor cores, consumed by the NB sweep
+                L.check(lib.spv_to_bf16(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX, st), "spv_to_bf16")
+                L.check(lib.spv_to_bf16(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX, st), "spv_to_bf16")
+                self._tc_gemm(L.ptr(w.amixb), L.ptr(w.Wmb), L.ptr(w.pi), B, G, KMIX, lda=w.KMp, ldb=w.KMp, ldc=G,
+                              bias=L.ptr(self.P(g, "bm")))
+            L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 2 | (4 if self.bf16 else 0), st), "spv_dec_nb_fwd")
             if evs is not None:
                 evs[1].record()
         if Bs[0] != Bs[1]:
@@ -424,14 +461,21 @@ class StepEngine:
             src, xptr, ldx = srcs[g]
             zzp = w.amix.data_ptr() + 4 * HD
             L.check(lib.spv_dec_nb_bwd(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, KMIX, B, G, HD, P, S,
-                                       -float(grad_scale) / B, L.ptr(w.colsum), st), "spv_dec_nb_bwd")
-            # d Wm = dpi^T [hm | zz];   Q = dy^T z
-            self._gemm(L.ptr(w.dpi), L.ptr(w.amix), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=G, ldb=KMIX, ldc=KMIX, ta=1)
-            self._gemm(L.ptr(w.dyp), zzp, L.ptr(w.Qp), G, P, B, lda=G, ldb=KMIX, ldc=P, ta=1)
-            self._gemm(L.ptr(w.dys), zzp + 4 * P, L.ptr(w.Qs), G, S, B, lda=G, ldb=KMIX, ldc=S, ta=1)
-            # d [hm | zz] = dpi Wm ;  dz (softmax branches) = dy W'
-            self._gemm(L.ptr(w.dpi), L.ptr(self.P(g, "Wm")), L.ptr(w.damix), B, KMIX, G, lda=G, ldb=KMIX, ldc=KMIX,
-                       splits=w.splits_g, ws=w.ws)
+                                       -float(grad_scale) / B, L.ptr(w.colsum), L.ptr(w.dpib) if self.bf16 else None,
+                                       w.Gp if self.bf16 else 0, st), "spv_dec_nb_bwd")
+            # d Wm = dpi^T [hm | zz];   d [hm | zz] = dpi Wm
+            if self.bf16:
+                self._tc_gemm(L.ptr(w.dpib), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=w.Gp, ldb=w.KMp, ldc=KMIX,
+                              a_mn=1, b_mn=1)
+                self._tc_gemm(L.ptr(w.dpib), L.ptr(w.Wmb), L.ptr(w.damix), B, KMIX, G, lda=w.Gp, ldb=w.KMp, ldc=KMIX, b_mn=1,
+                              splits=w.tc_splits_damix, ws=w.ws)
+            else:
+                self._gemm(L.ptr(w.dpi), L.ptr(w.amix), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=G, ldb=KMIX, ldc=KMIX, ta=1)
+                self._gemm(L.ptr(w.dpi), L.ptr(self.P(g, "Wm")), L.ptr(w.damix), B, KMIX, G, lda=G, ldb=KMIX, ldc=KMIX,
+                           splits=w.splits_g, ws=w.ws)
+            # Q = dy^T z ;  dz (softmax branches) = dy W'
+            self._gemm(L.ptr(w.dyp), zzp, L.ptr(w.Qp), G, P, B, lda=G, ldb=KMIX, ldc=P, ta=1, splits=w.splits_b, ws=w.ws)
+            self._gemm(L.ptr(w.dys), zzp + 4 * P, L.ptr(w.Qs), G, S, B, lda=G, ldb=KMIX, ldc=S, ta=1, splits=w.splits_b, ws=w.ws)
             self._gemm(L.ptr(w.dyp), L.ptr(w.wfold), L.ptr(w.dzraw), B, P, G, lda=G, ldb=KZ, ldc=KZ, splits=w.splits_g, ws=w.ws)
             self._gemm(L.ptr(w.dys), w.wfold.data_ptr() + 4 * P, w.dzraw.data_ptr() + 4 * P, B, S, G, lda=G, ldb=KZ, ldc=KZ,
                        splits=w.splits_g, ws=w.ws)
@@ -450,7 +494,8 @@ class StepEngine:
             L.check(lib.spv_bn_bwd(L.ptr(w.damix), KMIX, L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, L.ptr(w.dah), HD, B, HD,
                                    L.ptr(self.P(g, "gh")), L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), L.ptr(self.Gd(g, "gh")),
                                    L.ptr(self.Gd(g, "bth")), st), "spv_bn_bwd")
-            self._gemm(L.ptr(w.dah), zzp, L.ptr(self.Gd(g, "Wh")), HD, KZ, B, lda=HD, ldb=KMIX, ldc=KZ, ta=1)
+            self._gemm(L.ptr(w.dah), zzp, L.ptr(self.Gd(g, "Wh")), HD, KZ, B, lda=HD, ldb=KMIX, ldc=KZ, ta=1, splits=w.splits_b,
+                       ws=w.ws)
             L.check(lib.spv_colsum(L.ptr(w.dah), HD, B, HD, L.ptr(self.Gd(g, "bh")), st), "spv_colsum")
             self._gemm(L.ptr(w.dah), L.ptr(self.P(g, "Wh")), L.ptr(w.dzz), B, KZ, HD, lda=HD, ldb=KZ, ldc=KZ, acc=1)
         # ---------------- PoE
@@ -484,8 +529,10 @@ class StepEngine:
                                    L.ptr(self.Gd(g, "bthd")), st), "spv_bn_bwd")
             L.check(lib.spv_colsum(L.ptr(w.dr), NST, B, NST, L.ptr(self.Gd(g, "bhd")), st), "spv_colsum")
             drs = w.dr.data_ptr() + 4 * 2 * P
-            self._gemm(L.ptr(w.dr), L.ptr(w.h2), L.ptr(self.Gd(g, "Whp")), 2 * P, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1)
-            self._gemm(drs, w.h2.data_ptr() + 4 * H, L.ptr(self.Gd(g, "Whs")), 2 * S, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1)
+            self._gemm(L.ptr(w.dr), L.ptr(w.h2), L.ptr(self.Gd(g, "Whp")), 2 * P, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1,
+                       splits=w.splits_b, ws=w.ws)
+            self._gemm(drs, w.h2.data_ptr() + 4 * H, L.ptr(self.Gd(g, "Whs")), 2 * S, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1,
+                       splits=w.splits_b, ws=w.ws)
             self._gemm(L.ptr(w.dr), L.ptr(self.P(g, "Whp")), L.ptr(w.dh2), B, H, 2 * P, lda=NST, ldb=H, ldc=2 * H)
             self._gemm(drs, L.ptr(self.P(g, "Whs")), w.dh2.data_ptr() + 4 * H, B, H, 2 * S, lda=NST, ldb=H, ldc=2 * H)
             mask = noise.drop[g] if noise.drop is not None else None
@@ -493,13 +540,18 @@ class StepEngine:
             L.check(lib.spv_relu_bwd(L.ptr(w.dh2), 2 * H, L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, scale, st),
                     "spv_relu_bwd")
             self._gemm(L.ptr(w.dh2), L.ptr(w.h1), L.ptr(self.Gd(g, "W2")), H, H, B, lda=2 * H, ldb=2 * H, ldc=H, ta=1, batch=2,
-                       sA=H, sB=H, sC=H * H)
+                       sA=H, sB=H, sC=H * H, splits=w.splits_b, ws=w.ws)
             L.check(lib.spv_colsum(L.ptr(w.dh2), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b2")), st), "spv_colsum")
             self._gemm(L.ptr(w.dh2), L.ptr(self.P(g, "W2")), L.ptr(w.dh1), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, batch=2, sA=H,
                        sB=H * H, sC=H)
             L.check(lib.spv_relu_bwd(L.ptr(w.dh1), 2 * H, L.ptr(w.h1), 2 * H, B, 2 * H, None, 0, 1.0, st), "spv_relu_bwd")
-            self._gemm(L.ptr(w.dh1), xptr, L.ptr(self.Gd(g, "W1")), 2 * H, G, B, lda=2 * H, ldb=ldx, ldc=G, ta=1, srcB=src,
-                       rowsB=bt.rows)
+            if self.bf16:
+                L.check(lib.spv_to_bf16(L.ptr(w.dh1), 2 * H, L.ptr(w.dh1b), 2 * H, B, 2 * H, st), "spv_to_bf16")
+                self._tc_gemm(L.ptr(w.dh1b), L.ptr(w.Tb), L.ptr(self.Gd(g, "W1")), 2 * H, G, B, lda=2 * H, ldb=w.Gp, ldc=G,
+                              a_mn=1, b_mn=1)
+            else:
+                self._gemm(L.ptr(w.dh1), xptr, L.ptr(self.Gd(g, "W1")), 2 * H, G, B, lda=2 * H, ldb=ldx, ldc=G, ta=1, srcB=src,
+                           rowsB=bt.rows)
             L.check(lib.spv_colsum(L.ptr(w.dh1), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b1")), st), "spv_colsum")
 
     # -------------------------------------------------------------------------------- optimiser

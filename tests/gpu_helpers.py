@@ -3,11 +3,11 @@ import numpy as np
 import torch
 
 
-def engine_from_golden(gd, device="cuda"):
+def engine_from_golden(gd, device="cuda", precision="fp32"):
     from spvipes_b200.engine import GroupBatch, Noise, StepEngine
 
     plan = gd.plan.to(device) if gd.mode != "label" else None
-    eng = StepEngine((gd.G0, gd.G1), gd.H, gd.S, gd.P, gd.dropout, gd.mode, device, plan=plan)
+    eng = StepEngine((gd.G0, gd.G1), gd.H, gd.S, gd.P, gd.dropout, gd.mode, device, plan=plan, precision=precision)
     eng.load_state_dict(gd.sd)
     eng.set_kl_weight(gd.kl_weight)
     batches = []
