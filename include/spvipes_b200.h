@@ -121,6 +121,12 @@ int spv_dec_nb_fwd(int src, const void* const* ptrs, long long ldx, long long ld
                    int phases, void* stream);
 int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P, int S,
                    float scale, float* colsum, void* dpi_bf16, long long ld_dpi_bf16, void* stream);
+/* tensor-core version of phase 2 of spv_dec_nb_fwd: mixture GEMM on tcgen05 (bf16 operands via TMA, fp32 accumulator in
+ * TMEM) with the NB-mixture log-likelihood fused into the TMEM epilogue.  amix_bf16 [B, ld_amixb], wm_bf16 [G, ld_wmb]:
+ * bf16 copies of [hm | zz] and the mixture weight.  store_pi: also write the mixture logits to ptrs[10] (fp32 [B, G]). */
+int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, long long ld_amix, const void* amix_bf16,
+                      long long ld_amixb, const void* wm_bf16, long long ld_wmb, int B, int G, int HD, int P, int S, int store_pi,
+                      void* stream);
 /* ptrs (18): Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm, wv, wmx */
 int spv_dec_gene_bwd(const void* const* ptrs, int B, int G, int P, int S, void* stream);
 int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* v1, const float* M,

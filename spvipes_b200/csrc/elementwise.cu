@@ -11,21 +11,23 @@
 template <int SRC>
 __global__ void library_kernel(const void* __restrict__ X, long ldx, const int* __restrict__ rows, int B, int G,
                                float* __restrict__ lib) {
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= B) return;
-    long r = rows ? (long)rows[warp] : (long)warp;
+    // one CTA (128 threads) per row
+    __shared__ float red[4];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long r = rows ? (long)rows[b] : (long)b;
     float s = 0.0f;
-    for (int g = lane; g < G; g += 32) s += load_src<SRC>(X, r * ldx + g);
+    for (int g = threadIdx.x; g < G; g += blockDim.x) s += load_src<SRC>(X, r * ldx + g);
     s = warp_sum(s);
-    if (lane == 0) lib[warp] = logf(s);
+    if (lane == 0) red[w] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) lib[b] = logf(red[0] + red[1] + red[2] + red[3]);
 }
 
 extern "C" int spv_library_size(int src, const void* X, long long ldx, const int* rows, int B, int G, float* lib, void* stream) {
     if (!X || !lib || B <= 0 || G <= 0) return SPV_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    int blocks = (B * 32 + 255) / 256;
-    if (src == SPV_SRC_U16_LOG1P) library_kernel<SPV_SRC_U16_LOG1P><<<blocks, 256, 0, st>>>(X, ldx, rows, B, G, lib);
-    else if (src == SPV_SRC_F32_LOG1P) library_kernel<SPV_SRC_F32_LOG1P><<<blocks, 256, 0, st>>>(X, ldx, rows, B, G, lib);
+    if (src == SPV_SRC_U16_LOG1P) library_kernel<SPV_SRC_U16_LOG1P><<<B, 128, 0, st>>>(X, ldx, rows, B, G, lib);
+    else if (src == SPV_SRC_F32_LOG1P) library_kernel<SPV_SRC_F32_LOG1P><<<B, 128, 0, st>>>(X, ldx, rows, B, G, lib);
     else return SPV_ERR_ARG;
     SPV_CHECK_LAUNCH();
     return SPV_OK;

@@ -1,0 +1,53 @@
+// Element math of the NB-mixture likelihood for the tensor-core path (fast SFU intrinsics: ex2.approx / lg2.approx /
+// rcp.approx; parity gate of this path is 1e-2 relative on the loss terms, BASELINE.json north_star).
+// scvi-tools 0.20.0 log_mixture_nb, shared-theta branch, eps = 1e-8; reference call sites module/spVIPESmodule.py:759, 823-824.
+#pragma once
+#include "common.cuh"
+
+// lgamma(x) for x > 0: shift by 8 (lgamma(x) = lgamma(x + 8) - log(x (x+1) ... (x+7))) then Stirling at y = x + 8 >= 8
+// (truncation error < 1/(1260 y^5) < 3e-8).  Branch-free: 2 lg2 + 1 rcp on the SFU, the rest FMA.
+__device__ __forceinline__ float lgamma_pos_fast(float x) {
+    float p = x * (x + 1.0f);
+    p *= (x + 2.0f) * (x + 3.0f);
+    p *= (x + 4.0f) * (x + 5.0f);
+    p *= (x + 6.0f) * (x + 7.0f);
+    float y = x + 8.0f;
+    float iy = __frcp_rn(y);
+    float s = iy * (0.083333333f - iy * iy * 0.0027777778f);
+    return (y - 0.5f) * __logf(y) - y + 0.91893853f + s - __logf(p);
+}
+
+struct NbOut { float ll, ep, es; };
+
+// t = log1p(count); lp / ls = BatchNorm'd softmax logits of the private / shared branch; Rp / Rs = lib - logsumexp_g(logits);
+// th = exp(px_r), lte = log(th + eps), lgt = lgamma(th).   Returns log-likelihood and d ll / d rho * rho for both branches.
+__device__ __forceinline__ NbOut nb_forward_fast(float t, float lp, float ls, float pi, float th, float lte, float lgt, float Rp,
+                                                 float Rs) {
+    float rp = __expf(lp + Rp), rs = __expf(ls + Rs);
+    float d1 = th + rp + NB_EPS, d2 = th + rs + NB_EPS;
+    float l1 = __logf(d1), l2 = __logf(d2);
+    float a = th * (lte - l1), b = th * (lte - l2);
+    float gp = 0.0f, gs = 0.0f;
+    if (t != 0.0f) {
+        float lg = lgamma_pos_fast(t + th) - lgt - lgamma_pos_fast(t + 1.0f);
+        a += t * (__logf(rp + NB_EPS) - l1) + lg;
+        b += t * (__logf(rs + NB_EPS) - l2) + lg;
+        gp = __fdividef(t, rp + NB_EPS);
+        gs = __fdividef(t, rs + NB_EPS);
+    }
+    b -= pi;
+    // logsumexp(a, b) = max + log(1 + exp(-|a - b|));  softplus(-pi) = max(-pi, 0) + log(1 + exp(-|pi|))
+    float df = a - b;
+    float e = __expf(-fabsf(df));
+    float lse = fmaxf(a, b) + __logf(1.0f + e);
+    float sp = fmaxf(-pi, 0.0f) + __logf(1.0f + __expf(-fabsf(pi)));
+    NbOut o;
+    o.ll = lse - sp;
+    float wmin = __fdividef(e, 1.0f + e);  // weight of the smaller of (a, b)
+    float wa = df >= 0.0f ? 1.0f - wmin : wmin;
+    float wb = 1.0f - wa;
+    float q1 = __fdividef(th + t, d1), q2 = __fdividef(th + t, d2);
+    o.ep = wa * (gp - q1) * rp;
+    o.es = wb * (gs - q2) * rs;
+    return o;
+}

@@ -19,25 +19,33 @@ __global__ void pair_label_kernel(const int* __restrict__ la, const int* __restr
     for (int i = threadIdx.x; i < Ba; i += blockDim.x) sa[i] = la[rows_a ? rows_a[i] : i];
     for (int i = threadIdx.x; i < Bb; i += blockDim.x) sb[i] = lb[rows_b ? rows_b[i] : i];
     __syncthreads();
-    int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= Ba + Bb) return;
-    const bool side_a = gid < Ba;
-    const int i = side_a ? gid : gid - Ba;
+    // one warp per row: 32 labels are compared per step with a ballot
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= Ba + Bb) return;
+    const bool side_a = row < Ba;
+    const int i = side_a ? row : row - Ba;
     const int* own = side_a ? sa : sb;
     const int* oth = side_a ? sb : sa;
     const int n_oth = side_a ? Bb : Ba;
     const int l = own[i];
-    int rank = 0;
-    for (int k = 0; k < i; ++k) rank += (own[k] == l);
-    int found = SPV_PARTNER_ABSENT, seen = 0;
-    for (int j = 0; j < n_oth; ++j) {
-        if (oth[j] == l) {
-            if (seen == rank) { found = j; break; }
-            ++seen;
-            found = SPV_PARTNER_PAD;
-        }
+    int rank = 0;  // number of earlier rows of this group with the same label
+    for (int k0 = 0; k0 < i; k0 += 32) {
+        int k = k0 + lane;
+        rank += __popc(__ballot_sync(0xffffffffu, k < i && own[k] == l));
     }
-    (side_a ? pa : pb)[i] = found;
+    int found = SPV_PARTNER_ABSENT, seen = 0;
+    for (int j0 = 0; j0 < n_oth; j0 += 32) {
+        int j = j0 + lane;
+        unsigned m = __ballot_sync(0xffffffffu, j < n_oth && oth[j] == l);
+        int c = __popc(m);
+        if (c) found = SPV_PARTNER_PAD;
+        if (seen + c > rank) {  // the (rank - seen)-th set bit of m is the partner
+            found = j0 + __fns(m, 0, rank - seen + 1);
+            break;
+        }
+        seen += c;
+    }
+    if (lane == 0) (side_a ? pa : pb)[i] = found;
 }
 
 extern "C" int spv_pair_label(const int* la, const int* lb, const int* rows_a, const int* rows_b, int Ba, int Bb, int* pa,
@@ -46,7 +54,7 @@ extern "C" int spv_pair_label(const int* la, const int* lb, const int* rows_a, c
     size_t smem = (size_t)(Ba + Bb) * sizeof(int);
     if (smem > 200 * 1024) return SPV_ERR_ARG;
     if (smem > 48 * 1024) cudaFuncSetAttribute(pair_label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int blocks = (Ba + Bb + 255) / 256;
+    int blocks = (Ba + Bb + 7) / 8;  // 8 warps per CTA, one warp per row
     pair_label_kernel<<<blocks, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(la, lb, rows_a, rows_b, Ba, Bb, pa, pb);
     SPV_CHECK_LAUNCH();
     return SPV_OK;

@@ -225,6 +225,8 @@ class StepEngine:
             raise ValueError("precision must be 'fp32' or 'bf16'")
         self.precision = precision
         self.bf16 = precision == "bf16"
+        # fused tcgen05 mixture-GEMM + NB-likelihood kernel (bf16 mode); needs latent widths <= 32
+        self.fused_nb = self.bf16 and int(n_shared) <= 32 and int(n_private) <= 32
         self.lib = L.load()
         self.d = Dims(tuple(int(x) for x in genes), int(n_hidden), int(n_shared), int(n_private))
         if self.d.n_private > self.d.n_shared:
@@ -360,9 +362,15 @@ class StepEngine:
             if self.bf16:  # mixture logits on the tensor cores, consumed by the NB sweep
                 L.check(lib.spv_to_bf16(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX, st), "spv_to_bf16")
                 L.check(lib.spv_to_bf16(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX, st), "spv_to_bf16")
-                self._tc_gemm(L.ptr(w.amixb), L.ptr(w.Wmb), L.ptr(w.pi), B, G, KMIX, lda=w.KMp, ldb=w.KMp, ldc=G,
-                              bias=L.ptr(self.P(g, "bm")))
-            L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 2 | (4 if self.bf16 else 0), st), "spv_dec_nb_fwd")
+                if self.fused_nb:
+                    L.check(lib.spv_dec_nb_fwd_tc(src, dptrs, ldx, KMIX, L.ptr(w.amixb), w.KMp, L.ptr(w.Wmb), w.KMp, B, G, HD, P, S,
+                                                  1 if with_grad else 0, st), "spv_dec_nb_fwd_tc")
+                else:  # unfused: tensor-core GEMM writes pi, the SIMT sweep consumes it
+                    self._tc_gemm(L.ptr(w.amixb), L.ptr(w.Wmb), L.ptr(w.pi), B, G, KMIX, lda=w.KMp, ldb=w.KMp, ldc=G,
+                                  bias=L.ptr(self.P(g, "bm")))
+                    L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 2 | 4, st), "spv_dec_nb_fwd")
+            else:
+                L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 2, st), "spv_dec_nb_fwd")
             if evs is not None:
                 evs[1].record()
         if Bs[0] != Bs[1]:
