@@ -45,7 +45,7 @@ _SIGS = {
     "spv_dec_nb_bwd": [i, p, ll, ll, i, i, i, i, i, f, p, p, ll, p],
     "spv_dec_nb_fwd_tc": [i, p, ll, ll, p, ll, p, ll, i, i, i, i, i, i, p],
     "spv_dec_gene_bwd": [p, i, i, i, i, p],
-    "spv_dec_dzz_combine": [p, ll, p, p, p, p, ll, p, p, i, i, i, p],
+    "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, p],
     "spv_adam_tick": [p, p],
     "spv_adam": [p, p, p, p, ll, f, f, f, f, f, f, p, p],
 }

@@ -11,139 +11,7 @@
 #include "gemm_simt.cuh"
 #include "../../include/spvipes_b200.h"
 
-// genec rows (SoA, stride G)
-enum { GC_CP = 0, GC_CS, GC_AP, GC_AS, GC_ISTD_P, GC_ISTD_S, GC_MEAN_P, GC_MEAN_S, GC_THETA, GC_LTE, GC_LGT, GC_DGT, GC_N };
-
-// ---------------------------------------------------------------------------------------
-// partial (un-normalised, centred) second moments of zz over a chunk of 64 rows
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) zcov_kernel(const float* __restrict__ zz, long ld, int B, int KZ,
-                                                   const float* __restrict__ zsum, float* __restrict__ cov_part) {
-    extern __shared__ float tile[];  // [64][KZ + 1]
-    const int r0 = blockIdx.x * 64;
-    const int ldt = KZ + 1;
-    const float invB = 1.0f / (float)B;
-    for (int i = threadIdx.x; i < 64 * KZ; i += blockDim.x) {
-        int r = i / KZ, k = i % KZ;
-        float v = 0.0f;
-        if (r0 + r < B) v = zz[(long)(r0 + r) * ld + k] - zsum[k] * invB;
-        tile[r * ldt + k] = v;
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < KZ * KZ; idx += blockDim.x) {
-        int i = idx / KZ, j = idx % KZ;
-        float s = 0.0f;
-#pragma unroll 8
-        for (int r = 0; r < 64; ++r) s = fmaf(tile[r * ldt + i], tile[r * ldt + j], s);
-        cov_part[(long)blockIdx.x * KZ * KZ + idx] = s;
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// per gene: closed-form BatchNorm statistics of u = z W^T, folded affine, running-stat update,
-// and the constants of the NB term
-// ---------------------------------------------------------------------------------------
-struct FoldP {
-    const float *Wp, *Ws, *gp, *bp, *gs, *bs, *px_r;
-    float *rm_p, *rv_p, *rm_s, *rv_s;
-    const float *zsum, *cov_part;
-    float *wfold, *genec, *zmean, *zcov;
-    int G, P, S, B, ncov, training;
-    float eps, momentum;
-};
-
-__global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
-    extern __shared__ float sh[];  // mean[KZ] | cov[KZ*KZ]
-    const int KZ = p.P + p.S;
-    float* smean = sh;
-    float* scov = sh + KZ;
-    const float invB = 1.0f / (float)p.B;
-    for (int k = threadIdx.x; k < KZ; k += blockDim.x) smean[k] = p.zsum[k] * invB;
-    for (int i = threadIdx.x; i < KZ * KZ; i += blockDim.x) {
-        float s = 0.0f;
-        for (int c = 0; c < p.ncov; ++c) s += p.cov_part[(long)c * KZ * KZ + i];
-        scov[i] = s * invB;
-    }
-    __syncthreads();
-    if (blockIdx.x == 0) {
-        for (int k = threadIdx.x; k < KZ; k += blockDim.x) p.zmean[k] = smean[k];
-        for (int i = threadIdx.x; i < KZ * KZ; i += blockDim.x) p.zcov[i] = scov[i];
-    }
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= p.G) return;
-    const int G = p.G;
-#pragma unroll
-    for (int br = 0; br < 2; ++br) {
-        const int K = br == 0 ? p.P : p.S;
-        const int off = br == 0 ? 0 : p.P;
-        const float* W = (br == 0 ? p.Wp : p.Ws) + (long)g * K;
-        float* rm = br == 0 ? p.rm_p : p.rm_s;
-        float* rv = br == 0 ? p.rv_p : p.rv_s;
-        float mean, var;
-        if (p.training) {
-            mean = 0.0f;
-            var = 0.0f;
-            for (int k = 0; k < K; ++k) {
-                float wk = W[k];
-                mean = fmaf(smean[off + k], wk, mean);
-                float t = 0.0f;
-                for (int l = 0; l < K; ++l) t = fmaf(scov[(off + k) * KZ + off + l], W[l], t);
-                var = fmaf(wk, t, var);
-            }
-            var = fmaxf(var, 0.0f);
-            float unb = var * ((float)p.B / (float)max(p.B - 1, 1));
-            rm[g] = (1.0f - p.momentum) * rm[g] + p.momentum * mean;
-            rv[g] = (1.0f - p.momentum) * rv[g] + p.momentum * unb;
-        } else {
-            mean = rm[g];
-            var = rv[g];
-        }
-        float invstd = 1.0f / sqrtf(var + p.eps);
-        float a = (br == 0 ? p.gp : p.gs)[g] * invstd;
-        float c = (br == 0 ? p.bp : p.bs)[g] - mean * a;
-        for (int k = 0; k < K; ++k) p.wfold[(long)g * KZ + off + k] = a * W[k];
-        p.genec[(br == 0 ? GC_CP : GC_CS) * (long)G + g] = c;
-        p.genec[(br == 0 ? GC_AP : GC_AS) * (long)G + g] = a;
-        p.genec[(br == 0 ? GC_ISTD_P : GC_ISTD_S) * (long)G + g] = invstd;
-        p.genec[(br == 0 ? GC_MEAN_P : GC_MEAN_S) * (long)G + g] = mean;
-    }
-    float th = expf(p.px_r[g]);  // reference module/spVIPESmodule.py:758
-    p.genec[GC_THETA * (long)G + g] = th;
-    p.genec[GC_LTE * (long)G + g] = logf(th + NB_EPS);
-    p.genec[GC_LGT * (long)G + g] = lgammaf(th);
-    p.genec[GC_DGT * (long)G + g] = digammaf_pos(th);
-}
-
-// ptrs: Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, cov_part, wfold, genec, zmean, zcov
-extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, int S, int training, float eps,
-                            float momentum, void* stream) {
-    if (!ptrs || B <= 0 || G <= 0 || P <= 0 || S <= 0 || P + S > 96) return SPV_ERR_ARG;
-    for (int i = 0; i < 18; ++i)
-        if (!ptrs[i]) return SPV_ERR_ARG;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int KZ = P + S;
-    const float* zz = (const float*)ptrs[11];
-    const float* zsum = (const float*)ptrs[12];
-    float* cov_part = (float*)ptrs[13];
-    const int ncov = (B + 63) / 64;
-    if (training) {
-        size_t sm1 = (size_t)64 * (KZ + 1) * sizeof(float);
-        zcov_kernel<<<ncov, 256, sm1, st>>>(zz, ld_zz, B, KZ, zsum, cov_part);
-        SPV_CHECK_LAUNCH();
-    }
-    FoldP p;
-    p.Wp = (const float*)ptrs[0]; p.Ws = (const float*)ptrs[1]; p.gp = (const float*)ptrs[2]; p.bp = (const float*)ptrs[3];
-    p.gs = (const float*)ptrs[4]; p.bs = (const float*)ptrs[5]; p.px_r = (const float*)ptrs[6];
-    p.rm_p = (float*)ptrs[7]; p.rv_p = (float*)ptrs[8]; p.rm_s = (float*)ptrs[9]; p.rv_s = (float*)ptrs[10];
-    p.zsum = zsum; p.cov_part = cov_part; p.wfold = (float*)ptrs[14]; p.genec = (float*)ptrs[15];
-    p.zmean = (float*)ptrs[16]; p.zcov = (float*)ptrs[17];
-    p.G = G; p.P = P; p.S = S; p.B = B; p.ncov = training ? ncov : 0; p.training = training; p.eps = eps; p.momentum = momentum;
-    size_t sm2 = (size_t)(KZ + KZ * KZ) * sizeof(float);
-    if (sm2 > 48 * 1024) cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-    fold_kernel<<<(G + 255) / 256, 256, sm2, st>>>(p);
-    SPV_CHECK_LAUNCH();
-    return SPV_OK;
-}
+#include "decoder_common.cuh"
 
 // ---------------------------------------------------------------------------------------
 // the NB-mixture element (scvi log_mixture_nb, shared theta).  t = log1p(count) (quirk Q3).
@@ -373,36 +241,46 @@ __global__ void __launch_bounds__(GT_THREADS) dec_tile_kernel(DecP p) {
 // combine the per-gene-tile softmax partials: Rp = lib - logsumexp_g(y_p), Rs likewise
 __global__ void rowstat_kernel(const float* __restrict__ part, int nTG, int B, const float* __restrict__ lib,
                                float* __restrict__ rowc) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per row, lanes over the gene tiles
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= B) return;
     float Mp = -INFINITY, Ms = -INFINITY;
-    for (int t = 0; t < nTG; ++t) {
+    for (int t = lane; t < nTG; t += 32) {
         const float* o = part + ((long)t * B + b) * 4;
         Mp = fmaxf(Mp, o[0]);
         Ms = fmaxf(Ms, o[2]);
     }
+    Mp = warp_max(Mp);
+    Ms = warp_max(Ms);
     float Sp = 0.0f, Ss = 0.0f;
-    for (int t = 0; t < nTG; ++t) {
+    for (int t = lane; t < nTG; t += 32) {
         const float* o = part + ((long)t * B + b) * 4;
         Sp += o[1] * expf(o[0] - Mp);
         Ss += o[3] * expf(o[2] - Ms);
     }
-    float l = lib[b];
-    rowc[(long)b * 4 + 0] = l - (Mp + logf(Sp));
-    rowc[(long)b * 4 + 1] = l - (Ms + logf(Ss));
+    Sp = warp_sum(Sp);
+    Ss = warp_sum(Ss);
+    if (lane == 0) {
+        float l = lib[b];
+        rowc[(long)b * 4 + 0] = l - (Mp + logf(Sp));
+        rowc[(long)b * 4 + 1] = l - (Ms + logf(Ss));
+    }
 }
 
 __global__ void rownb_kernel(const float* __restrict__ part, int nTG, int B, float* __restrict__ rowc, float* __restrict__ rec) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= B) return;
     float ll = 0.0f, dp = 0.0f, ds = 0.0f;
-    for (int t = 0; t < nTG; ++t) {
+    for (int t = lane; t < nTG; t += 32) {
         const float* o = part + ((long)t * B + b) * 3;
         ll += o[0]; dp += o[1]; ds += o[2];
     }
-    rec[b] = -ll;  // reference :823-824
-    rowc[(long)b * 4 + 2] = dp;
-    rowc[(long)b * 4 + 3] = ds;
+    ll = warp_sum(ll); dp = warp_sum(dp); ds = warp_sum(ds);
+    if (lane == 0) {
+        rec[b] = -ll;  // reference :823-824
+        rowc[(long)b * 4 + 2] = dp;
+        rowc[(long)b * 4 + 3] = ds;
+    }
 }
 
 static void fill_decp(DecP& p, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P, int S,
@@ -434,14 +312,14 @@ extern "C" int spv_dec_nb_fwd(int src, const void* const* ptrs, long long ldx, l
         if (src == SPV_SRC_U16_LOG1P) dec_tile_kernel<PASS_STATS, SPV_SRC_U16_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
         else dec_tile_kernel<PASS_STATS, SPV_SRC_F32_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
         SPV_CHECK_LAUNCH();
-        rowstat_kernel<<<(B + 127) / 128, 128, 0, st>>>(p.part_stats, nTG, B, p.lib, p.rowc);
+        rowstat_kernel<<<(B + 7) / 8, 256, 0, st>>>(p.part_stats, nTG, B, p.lib, p.rowc);
         SPV_CHECK_LAUNCH();
     }
     if (phases & 2) {  // mixture GEMM + NB log-likelihood
         if (src == SPV_SRC_U16_LOG1P) dec_tile_kernel<PASS_NB, SPV_SRC_U16_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
         else dec_tile_kernel<PASS_NB, SPV_SRC_F32_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
         SPV_CHECK_LAUNCH();
-        rownb_kernel<<<(B + 127) / 128, 128, 0, st>>>(p.part_nb, nTG, B, p.rowc, (float*)ptrs[16]);
+        rownb_kernel<<<(B + 7) / 8, 256, 0, st>>>(p.part_nb, nTG, B, p.rowc, (float*)ptrs[16]);
         SPV_CHECK_LAUNCH();
     }
     return SPV_OK;
@@ -475,108 +353,6 @@ extern "C" int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, l
     else return SPV_ERR_ARG;
     SPV_CHECK_LAUNCH();
     colpart_reduce_kernel<<<(4 * G + 255) / 256, 256, 0, st>>>(p.colpart, grid.y, G, colsum);
-    SPV_CHECK_LAUNCH();
-    return SPV_OK;
-}
-
-// ---------------------------------------------------------------------------------------
-// per-gene backward of the two folded BatchNorm+Linear branches (closed form):
-//   Q = dy^T z (from spv_gemm), sdy = colsum(dy):  S2 = (Q.W - sdy mean_u) invstd = dgamma,  dbeta = sdy,
-//   dW = a (Q - sdy zbar - S2 invstd Cov W);  rows of the correction operands for d z:
-//   wv[g, :] = a sdy / B * W[g, :],   wmx[g, :] = a S2 / B * invstd * W[g, :]
-// also d px_r = theta * colsum(dtheta), d bm = colsum(dpi).
-// ---------------------------------------------------------------------------------------
-struct GeneBwdP {
-    const float *Wp, *Ws, *Qp, *Qs, *genec, *colsum, *zmean, *zcov;
-    float *dWp, *dWs, *dgp, *dbp, *dgs, *dbs, *dpx_r, *dbm, *wv, *wmx;
-    int G, P, S, B;
-};
-
-__global__ void __launch_bounds__(256) gene_bwd_kernel(GeneBwdP p) {
-    extern __shared__ float sh[];
-    const int KZ = p.P + p.S;
-    float* smean = sh;
-    float* scov = sh + KZ;
-    for (int k = threadIdx.x; k < KZ; k += blockDim.x) smean[k] = p.zmean[k];
-    for (int i = threadIdx.x; i < KZ * KZ; i += blockDim.x) scov[i] = p.zcov[i];
-    __syncthreads();
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= p.G) return;
-    const long G = p.G;
-    const float invB = 1.0f / (float)p.B;
-#pragma unroll
-    for (int br = 0; br < 2; ++br) {
-        const int K = br == 0 ? p.P : p.S;
-        const int off = br == 0 ? 0 : p.P;
-        const float* W = (br == 0 ? p.Wp : p.Ws) + (long)g * K;
-        const float* Q = (br == 0 ? p.Qp : p.Qs) + (long)g * K;
-        float* dW = (br == 0 ? p.dWp : p.dWs) + (long)g * K;
-        const float a = p.genec[(br == 0 ? GC_AP : GC_AS) * G + g];
-        const float invstd = p.genec[(br == 0 ? GC_ISTD_P : GC_ISTD_S) * G + g];
-        const float mean_u = p.genec[(br == 0 ? GC_MEAN_P : GC_MEAN_S) * G + g];
-        const float sdy = p.colsum[(long)br * G + g];
-        float qw = 0.0f;
-        for (int k = 0; k < K; ++k) qw = fmaf(Q[k], W[k], qw);
-        const float S2 = (qw - sdy * mean_u) * invstd;
-        (br == 0 ? p.dgp : p.dgs)[g] = S2;
-        (br == 0 ? p.dbp : p.dbs)[g] = sdy;
-        const float cv = a * sdy * invB, cm = a * S2 * invB * invstd;
-        for (int k = 0; k < K; ++k) {
-            float cw = 0.0f;
-            for (int l = 0; l < K; ++l) cw = fmaf(scov[(off + k) * KZ + off + l], W[l], cw);
-            dW[k] = a * (Q[k] - sdy * smean[off + k] - S2 * invstd * cw);
-            p.wv[(long)g * KZ + off + k] = cv * W[k];
-            p.wmx[(long)g * KZ + off + k] = cm * W[k];
-        }
-    }
-    p.dpx_r[g] = p.genec[GC_THETA * G + g] * p.colsum[3 * G + g];
-    p.dbm[g] = p.colsum[2 * G + g];
-}
-
-// ptrs: Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm, wv, wmx
-extern "C" int spv_dec_gene_bwd(const void* const* ptrs, int B, int G, int P, int S, void* stream) {
-    if (!ptrs || B <= 0 || G <= 0 || P <= 0 || S <= 0 || P + S > 96) return SPV_ERR_ARG;
-    for (int i = 0; i < 18; ++i)
-        if (!ptrs[i]) return SPV_ERR_ARG;
-    GeneBwdP p;
-    p.Wp = (const float*)ptrs[0]; p.Ws = (const float*)ptrs[1]; p.Qp = (const float*)ptrs[2]; p.Qs = (const float*)ptrs[3];
-    p.genec = (const float*)ptrs[4]; p.colsum = (const float*)ptrs[5]; p.zmean = (const float*)ptrs[6];
-    p.zcov = (const float*)ptrs[7]; p.dWp = (float*)ptrs[8]; p.dWs = (float*)ptrs[9]; p.dgp = (float*)ptrs[10];
-    p.dbp = (float*)ptrs[11]; p.dgs = (float*)ptrs[12]; p.dbs = (float*)ptrs[13]; p.dpx_r = (float*)ptrs[14];
-    p.dbm = (float*)ptrs[15]; p.wv = (float*)ptrs[16]; p.wmx = (float*)ptrs[17];
-    p.G = G; p.P = P; p.S = S; p.B = B;
-    const int KZ = P + S;
-    size_t smem = (size_t)(KZ + KZ * KZ) * sizeof(float);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(gene_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gene_bwd_kernel<<<(G + 255) / 256, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-    SPV_CHECK_LAUNCH();
-    return SPV_OK;
-}
-
-// dzz[b, c] = dmix[b, c] + dzraw[b, c] - v1[c] - sum_l M[c, l] (zz[b, l] - zbar[l])   (l within c's branch block)
-//   dmix: the zz columns of d Amix (mixture GEMM);  dzraw = dy W' (both softmax branches);
-//   v1 = colsum over genes of wv;  M = wmx^T W (block diagonal: [P, P] and [S, S], stored in a [KZ, KZ] matrix)
-__global__ void dzz_combine_kernel(const float* __restrict__ dmix, long ld_dmix, const float* __restrict__ dzraw,
-                                   const float* __restrict__ v1, const float* __restrict__ M, const float* __restrict__ zz,
-                                   long ld_zz, const float* __restrict__ zmean, float* __restrict__ dzz, int B, int P, int S) {
-    const int KZ = P + S;
-    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (i >= (long)B * KZ) return;
-    int c = (int)(i % KZ);
-    long b = i / KZ;
-    int lo = c < P ? 0 : P, hi = c < P ? P : KZ;
-    float corr = 0.0f;
-    for (int l = lo; l < hi; ++l) corr = fmaf(M[c * KZ + l], zz[b * ld_zz + l] - zmean[l], corr);
-    dzz[b * KZ + c] = dmix[b * ld_dmix + c] + dzraw[b * KZ + c] - v1[c] - corr;
-}
-
-extern "C" int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* v1, const float* M,
-                                   const float* zz, long long ld_zz, const float* zmean, float* dzz, int B, int P, int S,
-                                   void* stream) {
-    if (!dmix || !dzraw || !v1 || !M || !zz || !zmean || !dzz || B <= 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
-    long total = (long)B * (P + S);
-    dzz_combine_kernel<<<(int)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dmix, ld_dmix, dzraw, v1, M, zz, ld_zz, zmean, dzz, B, P, S);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

@@ -1,0 +1,17 @@
+// per-gene constant table shared by the decoder kernels: genec[GC_N][G] (SoA, stride G)
+#pragma once
+enum {
+    GC_CP = 0,   // folded BatchNorm shift of the private branch: beta - mean * a
+    GC_CS,       // ... shared branch
+    GC_AP,       // folded scale gamma / sqrt(var + eps), private
+    GC_AS,       // ... shared
+    GC_ISTD_P,   // 1 / sqrt(var + eps)
+    GC_ISTD_S,
+    GC_MEAN_P,   // batch (or running) mean of z W^T
+    GC_MEAN_S,
+    GC_THETA,    // exp(px_r)
+    GC_LTE,      // log(theta + eps)
+    GC_LGT,      // lgamma(theta)
+    GC_DGT,      // digamma(theta)
+    GC_N
+};

@@ -204,9 +204,7 @@ class _GroupWS:
             self.colpart, self.colsum = f(self.nTB, 4, G), f(4, G)
             self.Qp, self.Qs = f(G, P), f(G, S)
             self.damix, self.dzraw, self.dzz = f(B, KMIX), f(B, KZ), f(B, KZ)
-            self.wv, self.wmx = f(G, KZ), f(G, KZ)
-            self.v1 = f(KZ)
-            self.Mmat = torch.zeros(KZ, KZ, dtype=torch.float32, device=dev)
+            self.vpart, self.mpart = f(self.nTG, KZ), f(self.nTG, KZ * KZ)  # per 64-gene CTA partials (spv_dec_gene_bwd)
             self.dah = f(B, HD)
             self.dstats, self.dr = f(B, NST), f(B, NST)
             self.g_own, self.g_contrib, self.dexpert = f(B, 2 * S), f(B, 2 * S), f(B, 2 * S)
@@ -489,15 +487,10 @@ class StepEngine:
                        splits=w.splits_g, ws=w.ws)
             gb = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), w.Qp, w.Qs, w.genec, w.colsum, w.zmean, w.zcov,
                               self.Gd(g, "Wp"), self.Gd(g, "Ws"), self.Gd(g, "gp"), self.Gd(g, "bp"), self.Gd(g, "gs"),
-                              self.Gd(g, "bs"), self.Gd(g, "px_r"), self.Gd(g, "bm"), w.wv, w.wmx])
+                              self.Gd(g, "bs"), self.Gd(g, "px_r"), self.Gd(g, "bm"), w.vpart, w.mpart])
             L.check(lib.spv_dec_gene_bwd(gb, B, G, P, S, st), "spv_dec_gene_bwd")
-            L.check(lib.spv_colsum(L.ptr(w.wv), KZ, G, KZ, L.ptr(w.v1), st), "spv_colsum")
-            self._gemm(L.ptr(w.wmx), L.ptr(self.P(g, "Wp")), L.ptr(w.Mmat), P, P, G, lda=KZ, ldb=P, ldc=KZ, ta=1,
-                       splits=w.splits_g, ws=w.ws)
-            self._gemm(w.wmx.data_ptr() + 4 * P, L.ptr(self.P(g, "Ws")), w.Mmat.data_ptr() + 4 * (P * KZ + P), S, S, G, lda=KZ,
-                       ldb=S, ldc=KZ, ta=1, splits=w.splits_g, ws=w.ws)
-            L.check(lib.spv_dec_dzz_combine(w.damix.data_ptr() + 4 * HD, KMIX, L.ptr(w.dzraw), L.ptr(w.v1), L.ptr(w.Mmat), zzp,
-                                            KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S, st), "spv_dec_dzz_combine")
+            L.check(lib.spv_dec_dzz_combine(w.damix.data_ptr() + 4 * HD, KMIX, L.ptr(w.dzraw), L.ptr(w.vpart), L.ptr(w.mpart),
+                                            w.nTG, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S, st), "spv_dec_dzz_combine")
             # hidden layer of the mixing net: ReLU + BatchNorm backward, then its Linear
             L.check(lib.spv_bn_bwd(L.ptr(w.damix), KMIX, L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, L.ptr(w.dah), HD, B, HD,
                                    L.ptr(self.P(g, "gh")), L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), L.ptr(self.Gd(g, "gh")),
