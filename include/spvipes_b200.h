@@ -110,8 +110,10 @@ int spv_loss(const float* rec0, const float* rec1, const float* klp0, const floa
  * ptrs (18): Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, cov_part, wfold, genec,
  * zmean, zcov.   nn/networks.py:314-320, scvi FCLayers; module/spVIPESmodule.py:758 */
 #define SPV_DEC_GENEC_ROWS 12
+/* wfold_bf16 (optional, [G, 128] bf16): the folded weights laid out against the 64-wide k-block that holds the latent
+ * columns of the mixture operand (private block in columns 0-63, shared block in 64-127), operand of spv_dec_nb_fwd_tc */
 int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, int S, int training, float eps, float momentum,
-                 void* stream);
+                 void* wfold_bf16, void* stream);
 /* fused decoder + NB-mixture likelihood sweeps.  ptrs (SPV_DEC_NPTR): X, rows, amix, wfold, wm, bm, genec, lib, part_stats,
  * rowc, pi, part_nb, dyp, dys, dpi, colpart, rec.   nn/networks.py:314-325; module/spVIPESmodule.py:759, 817-824 */
 #define SPV_DEC_NPTR 17
@@ -121,12 +123,13 @@ int spv_dec_nb_fwd(int src, const void* const* ptrs, long long ldx, long long ld
                    int phases, void* stream);
 int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P, int S,
                    float scale, float* colsum, void* dpi_bf16, long long ld_dpi_bf16, void* stream);
-/* tensor-core version of phase 2 of spv_dec_nb_fwd: mixture GEMM on tcgen05 (bf16 operands via TMA, fp32 accumulator in
- * TMEM) with the NB-mixture log-likelihood fused into the TMEM epilogue.  amix_bf16 [B, ld_amixb], wm_bf16 [G, ld_wmb]:
- * bf16 copies of [hm | zz] and the mixture weight.  store_pi: also write the mixture logits to ptrs[10] (fp32 [B, G]). */
-int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, long long ld_amix, const void* amix_bf16,
-                      long long ld_amixb, const void* wm_bf16, long long ld_wmb, int B, int G, int HD, int P, int S, int store_pi,
-                      void* stream);
+/* tensor-core version of phase 2 of spv_dec_nb_fwd: the mixture GEMM and the two softmax-branch logit GEMMs on tcgen05
+ * (bf16 operands via TMA, fp32 accumulators in TMEM) with the NB-mixture log-likelihood fused into the TMEM epilogue.
+ * amix_bf16 [B, ld_amixb] = [hm | zz], wm_bf16 [G, ld_wmb] = mixture weight, wfold_bf16 [G, 128] from spv_dec_fold.
+ * part_nb (ptrs[11]) needs 2 * ceil(G/64) * B * 3 floats.  store_pi: also write the mixture logits to ptrs[10] (fp32). */
+int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
+                      const void* wm_bf16, long long ld_wmb, const void* wfold_bf16, int B, int G, int HD, int P, int S,
+                      int store_pi, void* stream);
 /* ptrs (18): Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm,
  * vpart [ceil(G/64), P+S], mpart [ceil(G/64), (P+S)^2]   (backward of nn/networks.py:314-320 through the folded BatchNorm) */
 int spv_dec_gene_bwd(const void* const* ptrs, int B, int G, int P, int S, void* stream);

@@ -5,6 +5,7 @@
 // W[g]^T Cov(z) W[g]: no [B, G] pass is needed, only the [KZ, KZ] covariance of the latent minibatch.
 //
 // Work split: one warp per gene (lanes over the latent dimension), 64 genes per CTA.
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "decoder_common.cuh"
 #include "../../include/spvipes_b200.h"
@@ -41,6 +42,7 @@ struct FoldP {
     float *rm_p, *rv_p, *rm_s, *rv_s;
     const float *zsum, *cov_part;
     float *wfold, *genec, *zmean, *zcov;
+    __nv_bfloat16* wfold_bf16;  // optional [G, 128]: folded weights laid out against the latent k-block of the mixture operand
     int G, P, S, B, ncov, training;
     float eps, momentum;
 };
@@ -99,6 +101,9 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
             float a = (br == 0 ? p.gp : p.gs)[g] * invstd;
             float c = (br == 0 ? p.bp : p.bs)[g] - mean * a;
             for (int k = lane; k < K; k += 32) p.wfold[(long)g * KZ + off + k] = a * W[k];
+            if (p.wfold_bf16)  // columns br*64 + j, j = position of the latent inside its 64-wide k-block, zero elsewhere
+                for (int j = lane; j < 64; j += 32)
+                    p.wfold_bf16[(long)g * 128 + br * 64 + j] = __float2bfloat16((j >= off && j < off + K) ? a * W[j - off] : 0.0f);
             if (lane == 0) {
                 p.genec[(br == 0 ? GC_CP : GC_CS) * G + g] = c;
                 p.genec[(br == 0 ? GC_AP : GC_AS) * G + g] = a;
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
 
 // ptrs: Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, cov_part, wfold, genec, zmean, zcov
 extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, int S, int training, float eps,
-                            float momentum, void* stream) {
+                            float momentum, void* wfold_bf16, void* stream) {
     if (!ptrs || B <= 0 || G <= 0 || P <= 0 || S <= 0 || P + S > 96) return SPV_ERR_ARG;
     for (int i = 0; i < 18; ++i)
         if (!ptrs[i]) return SPV_ERR_ARG;
@@ -139,6 +144,7 @@ extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int
     p.rm_p = (float*)ptrs[7]; p.rv_p = (float*)ptrs[8]; p.rm_s = (float*)ptrs[9]; p.rv_s = (float*)ptrs[10];
     p.zsum = zsum; p.cov_part = cov_part; p.wfold = (float*)ptrs[14]; p.genec = (float*)ptrs[15];
     p.zmean = (float*)ptrs[16]; p.zcov = (float*)ptrs[17];
+    p.wfold_bf16 = reinterpret_cast<__nv_bfloat16*>(wfold_bf16);
     p.G = G; p.P = P; p.S = S; p.B = B; p.ncov = training ? ncov : 0; p.training = training; p.eps = eps; p.momentum = momentum;
     size_t sm2 = (size_t)(KZ + KZ * KZ) * sizeof(float);
     if (sm2 > 48 * 1024) cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);

@@ -1,62 +1,59 @@
-// Fused decoder mixture GEMM + NB-mixture log-likelihood, tensor-core path (the north-star kernel).
+// Fused decoder GEMMs + NB-mixture log-likelihood, tensor-core path (the north-star kernel).
 //
-//   pi[b, g]  = [hm | z_private_arg | z_shared_arg][b, :] . Wm[g, :] + bm[g]     tcgen05.mma, bf16 operands via TMA, fp32 in TMEM
-//   lp, ls    = folded BatchNorm'd softmax logits (K = P / S, fp32 FMA in the epilogue from z and the folded weights)
-//   rec_b     = - sum_g log_mixture_nb(log1p(x[b, g]); exp(lib) softmax(lp), exp(lib) softmax(ls), theta, pi)
+//   pi[b, g] = [hm | z_private_arg | z_shared_arg][b, :] . Wm[g, :] + bm[g]                 K = 256 + P + S
+//   lp[b, g] = z_private_arg[b, :] . W'p[g, :] + cp[g],   ls[b, g] = z_shared_arg[b, :] . W's[g, :] + cs[g]
+//                                      (W', c: BatchNorm folded into the factor regressors by spv_dec_fold)
+//   rec_b    = - sum_g log_mixture_nb(log1p(x[b, g]); exp(lib) softmax(lp), exp(lib) softmax(ls), theta, pi)
 //
-// One 128 (cells) x 128 (genes) tile per CTA, two CTAs per SM.  warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer,
-// warps 2..5: epilogue (thread = cell row; warp w owns TMEM lanes 32 * (w % 4) ..).
-// The epilogue stages the tile's per-gene constants in shared memory while the MMAs run; once the accumulator is complete
-// the (now free) operand stages are reused for the tile's raw counts (coalesced row-gather, uint16), and the accumulator is
-// streamed out of TMEM 32 columns at a time.  Nothing of size [B, G] is written unless store_pi is set.
+// All three contractions run on tcgen05.mma (bf16 operands via TMA, fp32 accumulators in TMEM: columns 0-63 pi, 64-127 lp,
+// 128-191 ls).  The latent columns of the A operand all sit in k-block HD/64, so lp and ls each cost one extra MMA group on
+// that block against a zero-padded [genes, 64] copy of the folded weights.
+// One 128 (cells) x 64 (genes) tile per CTA, two CTAs per SM.  warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer,
+// warps 2..9: epilogue (thread = cell row; two warps per TMEM lane quarter, 32 gene columns each).  Once the accumulators
+// are complete the operand stages are reused for the tile's raw counts (coalesced row gather, uint16); the accumulators
+// are streamed out of TMEM four columns at a time.  Nothing of size [B, G] is written unless store_pi is set.
 // Reference: nn/networks.py:314-325, module/spVIPESmodule.py:751-759, 817-824; scvi log_mixture_nb.
 #include "tc_common.cuh"
 #include "nb_math.cuh"
+#include "decoder_common.cuh"
 #include "../../include/spvipes_b200.h"
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 2;
-constexpr int EPI_WARPS = 4, EPI_THREADS = 32 * EPI_WARPS;
+constexpr int BM = 128, BN = 64, BK = 64, STAGES = 2;
+constexpr int EPI_WARPS = 8, EPI_THREADS = 32 * EPI_WARPS;
 constexpr int THREADS = 64 + EPI_THREADS;
-constexpr int MAX_LAT = 32;  // max private / shared latent width (each padded to a multiple of 4)
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int CNT_PITCH_W = BN / 2 + 1;  // uint16 count tile, 65 32-bit words per row: conflict-free for thread = row reads
-
-enum { GC_CP = 0, GC_CS, GC_AP, GC_AS, GC_ISTD_P, GC_ISTD_S, GC_MEAN_P, GC_MEAN_S, GC_THETA, GC_LTE, GC_LGT, GC_DGT };
-
-struct NbTcParams {
-    const void* X; long ldx; const int* rows;
-    const float* amix; long ld_amix;   // fp32 [B, HD + P + S] (z columns are read in fp32)
-    const float* wfold;                // [G, P + S]
-    const float* bm;                   // [G]
-    const float* genec;                // [12, G]
-    const float* rowc;                 // [B, 4]: Rp, Rs
-    float* pi;                         // [B, G] or null
-    float* part_nb;                    // [nTG, B, 3]
-    int B, G, HD, P, S, K;
-};
+constexpr int TMEM_COLS = 256;           // 3 x 64 used
+constexpr int CNT_PITCH_W = BN / 2 + 1;  // uint16 count tile: 33 32-bit words per row, conflict-free for thread = row reads
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 6 * BN * 4 + 256;
 
 static_assert(BM * CNT_PITCH_W * 4 <= STAGES * STAGE_BYTES, "count tile must fit in the operand stages");
 
-__host__ __device__ inline int smem_bytes(int P, int S) {
-    int kzs = ((P + 3) / 4 + (S + 3) / 4) * 4;
-    return STAGES * STAGE_BYTES + 1024 + BN * kzs * 4 + 6 * BN * 4 + 256;
-}
+struct NbTcParams {
+    const void* X; long ldx; const int* rows;
+    const float* bm;                   // [G]
+    const float* genec;                // [GC_N, G]
+    const float* rowc;                 // [B, 4]: Rp, Rs
+    float* pi;                         // [B, G] or null
+    float* part_nb;                    // [nTG, B, 3]
+    int B, G, K, kb_z;                 // kb_z: k-block holding the latent columns
+};
 
 template <int SRC>
 __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                               const __grid_constant__ CUtensorMap mapB, NbTcParams p) {
+                                                               const __grid_constant__ CUtensorMap mapB,
+                                                               const __grid_constant__ CUtensorMap mapZ, NbTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = tc::smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
     uint8_t* tiles = smem_raw + pad;
-    const int nP4 = (p.P + 3) / 4, nS4 = (p.S + 3) / 4, KZS = (nP4 + nS4) * 4;
-    float* s_wfold = reinterpret_cast<float*>(tiles + STAGES * STAGE_BYTES);  // [BN][KZS]: private (padded) | shared (padded)
-    float* s_gc = s_wfold + BN * KZS;                                          // [6][BN]: cp, cs, theta, lte, lgt, bm
+    uint8_t* z_tiles = tiles + STAGES * STAGE_BYTES;                    // folded private | shared weights, [BN][64] bf16 each
+    float* s_gc = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);      // [6][BN]: cp, cs, theta, lte, lgt, bm
     uint64_t* full = reinterpret_cast<uint64_t*>(s_gc + 6 * BN);
     uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
+    uint64_t* z_full = empty + STAGES;
+    uint64_t* tmem_full = z_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(tiles);  // aliases the operand stages once the MMAs are done
 
@@ -67,14 +64,16 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&mapA);
         tc::tma_prefetch_desc(&mapB);
+        tc::tma_prefetch_desc(&mapZ);
         for (int s = 0; s < STAGES; ++s) {
             tc::mbar_init(&full[s], 1);
             tc::mbar_init(&empty[s], 1);
         }
+        tc::mbar_init(z_full, 1);
         tc::mbar_init(tmem_full, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, BN);
+    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -82,6 +81,9 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
 
     if (warp == 0) {
         if (tc::elect_one()) {
+            tc::mbar_expect_tx(z_full, 2 * B_BYTES);
+            tc::tma_load_2d(&mapZ, z_full, z_tiles, 0, n0);             // private block, columns 0..63
+            tc::tma_load_2d(&mapZ, z_full, z_tiles + B_BYTES, 64, n0);  // shared block, columns 64..127
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
@@ -106,22 +108,27 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
                 for (int kk = 0; kk < BK / 16; ++kk)
                     tc::umma_bf16(tmem_base, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(b_base + kk * 32, 16, 1024),
                                   idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                if (i == p.kb_z) {  // the two softmax-branch logits: same A block against the folded weights
+                    tc::mbar_wait(z_full, 0);
+                    tc::fence_after_sync();
+                    const uint32_t zp_base = tc::smem_u32(z_tiles), zs_base = zp_base + B_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        tc::umma_bf16(tmem_base + BN, tc::smem_desc(a_base + kk * 32, 16, 1024),
+                                      tc::smem_desc(zp_base + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
+                        tc::umma_bf16(tmem_base + 2 * BN, tc::smem_desc(a_base + kk * 32, 16, 1024),
+                                      tc::smem_desc(zs_base + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
+                    }
+                }
                 tc::umma_commit(&empty[s]);
             }
             tc::umma_commit(tmem_full);
         }
     } else {
-        // ================= epilogue: 4 warps =================
-        const int et = threadIdx.x - 64;  // 0..127
+        // ================= epilogue: 8 warps =================
+        const int et = threadIdx.x - 64;  // 0..255
         const long G = p.G;
-        const int KZ = p.P + p.S;
-        // stage the tile's per-gene constants (overlaps the TMA / MMA phase)
-        for (int i = et; i < BN * KZS; i += EPI_THREADS) {
-            int g = i / KZS, k = i - g * KZS;
-            int src_k = k < nP4 * 4 ? (k < p.P ? k : -1) : (k - nP4 * 4 < p.S ? p.P + (k - nP4 * 4) : -1);
-            s_wfold[i] = (src_k >= 0 && n0 + g < p.G) ? __ldg(p.wfold + (long)(n0 + g) * KZ + src_k) : 0.0f;
-        }
-        for (int i = et; i < BN; i += EPI_THREADS) {
+        for (int i = et; i < BN; i += EPI_THREADS) {  // per-gene constants of the tile (overlaps the TMA / MMA phase)
             int g = n0 + i;
             bool ok = g < p.G;
             s_gc[0 * BN + i] = ok ? __ldg(p.genec + GC_CP * G + g) : 0.0f;
@@ -131,107 +138,83 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
             s_gc[4 * BN + i] = ok ? __ldg(p.genec + GC_LGT * G + g) : 0.0f;
             s_gc[5 * BN + i] = ok ? __ldg(p.bm + g) : 0.0f;
         }
-        const int q = warp & 3;             // TMEM lane quarter this warp may access
-        const int rloc = q * 32 + lane;     // row within the tile
+        const int e = warp - 2;
+        const int q = warp & 3;          // TMEM lane quarter this warp may access
+        const int half = e >> 2;         // which 32 gene columns of the tile
+        const int rloc = q * 32 + lane;  // row within the tile
         const int m = m0 + rloc;
         const bool mok = m < p.B;
         const int mm = mok ? m : 0;
-        float zp[MAX_LAT], zs[MAX_LAT];
-#pragma unroll
-        for (int k = 0; k < MAX_LAT; ++k) {
-            zp[k] = (k < p.P) ? __ldg(p.amix + (long)mm * p.ld_amix + p.HD + k) : 0.0f;
-            zs[k] = (k < p.S) ? __ldg(p.amix + (long)mm * p.ld_amix + p.HD + p.P + k) : 0.0f;
-        }
         const float Rp = __ldg(p.rowc + (long)mm * 4 + 0), Rs = __ldg(p.rowc + (long)mm * 4 + 1);
         const long xrow = (p.rows ? (long)__ldg(p.rows + mm) : (long)mm) * p.ldx;
-        tc::mbar_wait(tmem_full, 0);  // accumulator complete; the operand stages are free from here on
+        tc::mbar_wait(tmem_full, 0);  // accumulators complete; the operand stages are free from here on
         tc::fence_after_sync();
         if (SRC == SPV_SRC_U16_LOG1P) {
-            // coalesced row-gather of the tile's counts: warp e loads rows e, e + 4, ...; lane l takes genes 4l .. 4l+3
+            // coalesced row gather of the tile's counts: warp e loads rows e, e + 8, ...; lane l takes genes 2l, 2l + 1
             const unsigned short* X16 = reinterpret_cast<const unsigned short*>(p.X);
-            const int e = warp - 2;
             for (int r = e; r < BM; r += EPI_WARPS) {
                 const int gm = m0 + r;
-                uint32_t w0 = 0, w1 = 0;
+                uint32_t w0 = 0;
                 if (gm < p.B) {
                     const long xr = (p.rows ? (long)__ldg(p.rows + gm) : (long)gm) * p.ldx;
-                    const int g = n0 + 4 * lane;
+                    const int g = n0 + 2 * lane;
                     const unsigned short* src = X16 + xr + g;
-                    if (g + 3 < p.G && ((reinterpret_cast<uintptr_t>(src) & 7) == 0)) {
-                        uint2 v = __ldg(reinterpret_cast<const uint2*>(src));
-                        w0 = v.x; w1 = v.y;
+                    if (g + 1 < p.G && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+                        w0 = __ldg(reinterpret_cast<const uint32_t*>(src));
                     } else {
-                        unsigned short c[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) c[j] = (g + j < p.G) ? __ldg(src + j) : (unsigned short)0;
-                        w0 = (uint32_t)c[0] | ((uint32_t)c[1] << 16);
-                        w1 = (uint32_t)c[2] | ((uint32_t)c[3] << 16);
+                        uint32_t c0 = g < p.G ? __ldg(src) : 0u, c1 = g + 1 < p.G ? __ldg(src + 1) : 0u;
+                        w0 = c0 | (c1 << 16);
                     }
                 }
-                s_cnt[r * CNT_PITCH_W + 2 * lane] = w0;
-                s_cnt[r * CNT_PITCH_W + 2 * lane + 1] = w1;
+                s_cnt[r * CNT_PITCH_W + lane] = w0;
             }
         }
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");  // constants + counts staged (epilogue warps only)
         float sll = 0.0f, sep = 0.0f, ses = 0.0f;
         const bool vec_pi = p.pi && ((G & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.pi) & 15) == 0);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc) {
-            const int c0 = cc * 32;
-#pragma unroll 1
-            for (int j4 = 0; j4 < 32; j4 += 4) {
-                uint32_t r[4];
-                tc::tmem_ld4(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + j4), r);
-                tc::tmem_ld_wait();
-                if (!mok) continue;
-                float pv[4];
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+            const int c0 = half * 32 + j4;
+            uint32_t rpi[4], rlp[4], rls[4];
+            tc::tmem_ld4(lane_addr + (uint32_t)c0, rpi);
+            tc::tmem_ld4(lane_addr + (uint32_t)(BN + c0), rlp);
+            tc::tmem_ld4(lane_addr + (uint32_t)(2 * BN + c0), rls);
+            tc::tmem_ld_wait();
+            if (!mok) continue;
+            float pv[4];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int j = j4 + jj, gl = c0 + j, g = n0 + gl;
-                    pv[jj] = 0.0f;
-                    if (g < p.G) {
-                        const float4* wf = reinterpret_cast<const float4*>(s_wfold + gl * KZS);
-                        float lp = s_gc[0 * BN + gl], ls = s_gc[1 * BN + gl];
-#pragma unroll
-                        for (int c = 0; c < MAX_LAT / 4; ++c)
-                            if (c < nP4) {
-                                float4 w = wf[c];
-                                lp = fmaf(zp[4 * c], w.x, lp); lp = fmaf(zp[4 * c + 1], w.y, lp);
-                                lp = fmaf(zp[4 * c + 2], w.z, lp); lp = fmaf(zp[4 * c + 3], w.w, lp);
-                            }
-#pragma unroll
-                        for (int c = 0; c < MAX_LAT / 4; ++c)
-                            if (c < nS4) {
-                                float4 w = wf[nP4 + c];
-                                ls = fmaf(zs[4 * c], w.x, ls); ls = fmaf(zs[4 * c + 1], w.y, ls);
-                                ls = fmaf(zs[4 * c + 2], w.z, ls); ls = fmaf(zs[4 * c + 3], w.w, ls);
-                            }
-                        const float piv = __uint_as_float(r[jj]) + s_gc[5 * BN + gl];
-                        float t;
-                        if (SRC == SPV_SRC_U16_LOG1P) {
-                            uint32_t w = s_cnt[rloc * CNT_PITCH_W + (gl >> 1)];
-                            uint32_t c = (gl & 1) ? (w >> 16) : (w & 0xffffu);
-                            t = c == 0u ? 0.0f : __logf(1.0f + (float)c);
-                        } else {
-                            t = load_src<SRC>(p.X, xrow + g);
-                        }
-                        NbOut o = nb_forward_fast(t, lp, ls, piv, s_gc[2 * BN + gl], s_gc[3 * BN + gl], s_gc[4 * BN + gl], Rp, Rs);
-                        sll += o.ll; sep += o.ep; ses += o.es;
-                        pv[jj] = piv;
+            for (int jj = 0; jj < 4; ++jj) {
+                const int gl = c0 + jj, g = n0 + gl;
+                pv[jj] = 0.0f;
+                if (g < p.G) {
+                    const float lp = __uint_as_float(rlp[jj]) + s_gc[0 * BN + gl];
+                    const float ls = __uint_as_float(rls[jj]) + s_gc[1 * BN + gl];
+                    const float piv = __uint_as_float(rpi[jj]) + s_gc[5 * BN + gl];
+                    float t;
+                    if (SRC == SPV_SRC_U16_LOG1P) {
+                        uint32_t w = s_cnt[rloc * CNT_PITCH_W + (gl >> 1)];
+                        uint32_t c = (gl & 1) ? (w >> 16) : (w & 0xffffu);
+                        t = c == 0u ? 0.0f : __logf(1.0f + (float)c);
+                    } else {
+                        t = load_src<SRC>(p.X, xrow + g);
                     }
+                    NbOut o = nb_forward_fast(t, lp, ls, piv, s_gc[2 * BN + gl], s_gc[3 * BN + gl], s_gc[4 * BN + gl], Rp, Rs);
+                    sll += o.ll; sep += o.ep; ses += o.es;
+                    pv[jj] = piv;
                 }
-                if (p.pi) {
-                    const int g = n0 + c0 + j4;
-                    float* dst = p.pi + (long)m * G + g;
-                    if (vec_pi && g + 3 < p.G) *reinterpret_cast<float4*>(dst) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-                    else
-                        for (int jj = 0; jj < 4; ++jj)
-                            if (g + jj < p.G) dst[jj] = pv[jj];
-                }
+            }
+            if (p.pi) {
+                const int g = n0 + c0;
+                float* dst = p.pi + (long)m * G + g;
+                if (vec_pi && g + 3 < p.G) *reinterpret_cast<float4*>(dst) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                else
+                    for (int jj = 0; jj < 4; ++jj)
+                        if (g + jj < p.G) dst[jj] = pv[jj];
             }
         }
         if (mok) {
-            float* o = p.part_nb + ((long)blockIdx.x * p.B + m) * 3;
+            float* o = p.part_nb + ((long)(blockIdx.x * 2 + half) * p.B + m) * 3;
             o[0] = sll; o[1] = sep; o[2] = ses;
         }
     }
@@ -239,7 +222,7 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
     __syncthreads();
     if (warp == 1) {
         tc::fence_after_sync();
-        tc::tmem_dealloc(tmem_base, BN);
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -261,44 +244,45 @@ __global__ void rownb_tc_kernel(const float* __restrict__ part, int nPart, int B
 
 }  // namespace
 
-// ptrs: the SPV_DEC_NPTR list of spv_dec_nb_fwd (X, rows, amix, wfold, wm [unused], bm, genec, lib, part_stats, rowc, pi,
-// part_nb [>= ceil(G/128) * B * 3 floats], ..., rec).  rowc[:, 0:2] must hold the softmax normalisers (phase 1 of
-// spv_dec_nb_fwd).  amix_bf16 [B, ld_amixb], wm_bf16 [G, ld_wmb]: bf16 copies of the mixture operands (K = HD + P + S).
-extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, long long ld_amix, const void* amix_bf16,
-                                 long long ld_amixb, const void* wm_bf16, long long ld_wmb, int B, int G, int HD, int P, int S,
-                                 int store_pi, void* stream) {
-    if (!ptrs || !amix_bf16 || !wm_bf16 || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0 || P > MAX_LAT || S > MAX_LAT)
-        return SPV_ERR_ARG;
-    const int need[] = {0, 2, 3, 5, 6, 9, 11, 16};
+// ptrs: the SPV_DEC_NPTR list of spv_dec_nb_fwd (X, rows, amix [unused], wfold [unused], wm [unused], bm, genec, lib,
+// part_stats, rowc, pi, part_nb [>= 2 * ceil(G/64) * B * 3 floats], ..., rec).  rowc[:, 0:2] must hold the softmax
+// normalisers (phase 1 of spv_dec_nb_fwd).  bf16 operands: amix_bf16 [B, ld_amixb] = [hm | zz], wm_bf16 [G, ld_wmb] = mixture
+// weight, wfold_bf16 [G, 128] = folded factor-regressor weights laid out against the latent k-block (written by spv_dec_fold).
+extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
+                                 const void* wm_bf16, long long ld_wmb, const void* wfold_bf16, int B, int G, int HD, int P,
+                                 int S, int store_pi, void* stream) {
+    if (!ptrs || !amix_bf16 || !wm_bf16 || !wfold_bf16 || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
+    if ((HD % BK) != 0 || P + S > BK) return SPV_ERR_ARG;  // the latent columns must sit in one k-block
+    const int need[] = {0, 5, 6, 9, 11, 16};
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
     if (store_pi && !ptrs[10]) return SPV_ERR_ARG;
     const int K = HD + P + S;
-    CUtensorMap ma, mb;
+    CUtensorMap ma, mb, mz;
     int rc = spv_make_tensor_map_bf16(&ma, amix_bf16, (unsigned long long)K, (unsigned long long)B, (unsigned long long)ld_amixb, 64, BM);
     if (rc != SPV_OK) return rc;
     rc = spv_make_tensor_map_bf16(&mb, wm_bf16, (unsigned long long)K, (unsigned long long)G, (unsigned long long)ld_wmb, 64, BN);
     if (rc != SPV_OK) return rc;
+    rc = spv_make_tensor_map_bf16(&mz, wfold_bf16, 128ull, (unsigned long long)G, 128ull, 64, BN);
+    if (rc != SPV_OK) return rc;
     NbTcParams p;
-    p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.amix = (const float*)ptrs[2]; p.ld_amix = ld_amix;
-    p.wfold = (const float*)ptrs[3]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6]; p.rowc = (const float*)ptrs[9];
-    p.pi = store_pi ? (float*)ptrs[10] : nullptr; p.part_nb = (float*)ptrs[11];
-    p.B = B; p.G = G; p.HD = HD; p.P = P; p.S = S; p.K = K;
+    p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
+    p.rowc = (const float*)ptrs[9]; p.pi = store_pi ? (float*)ptrs[10] : nullptr; p.part_nb = (float*)ptrs[11];
+    p.B = B; p.G = G; p.K = K; p.kb_z = HD / BK;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int smem = smem_bytes(P, S);
-    static int configured = 0;
-    if (configured < smem) {
-        if (cudaFuncSetAttribute(nb_tc_fwd_kernel<SPV_SRC_U16_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-            cudaFuncSetAttribute(nb_tc_fwd_kernel<SPV_SRC_F32_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(nb_tc_fwd_kernel<SPV_SRC_U16_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(nb_tc_fwd_kernel<SPV_SRC_F32_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
             return SPV_ERR_LAUNCH;
-        configured = smem;
+        configured = true;
     }
     dim3 grid((G + BN - 1) / BN, (B + BM - 1) / BM);
-    if (src == SPV_SRC_U16_LOG1P) nb_tc_fwd_kernel<SPV_SRC_U16_LOG1P><<<grid, THREADS, smem, st>>>(ma, mb, p);
-    else if (src == SPV_SRC_F32_LOG1P) nb_tc_fwd_kernel<SPV_SRC_F32_LOG1P><<<grid, THREADS, smem, st>>>(ma, mb, p);
+    if (src == SPV_SRC_U16_LOG1P) nb_tc_fwd_kernel<SPV_SRC_U16_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, p);
+    else if (src == SPV_SRC_F32_LOG1P) nb_tc_fwd_kernel<SPV_SRC_F32_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, p);
     else return SPV_ERR_ARG;
     SPV_CHECK_LAUNCH();
-    rownb_tc_kernel<<<(B + 7) / 8, 256, 0, st>>>(p.part_nb, (int)grid.x, B, (float*)ptrs[9], (float*)ptrs[16]);
+    rownb_tc_kernel<<<(B + 7) / 8, 256, 0, st>>>(p.part_nb, 2 * (int)grid.x, B, (float*)ptrs[9], (float*)ptrs[16]);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

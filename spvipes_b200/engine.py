@@ -176,7 +176,7 @@ class _GroupWS:
         self.wfold, self.genec = f(G, KZ), f(L.GENEC_ROWS, G)
         self.ah = f(B, HD)
         self.bn_h_mean, self.bn_h_istd = f(HD), f(HD)
-        self.part_stats, self.part_nb = f(self.nTG, B, 4), f(self.nTG, B, 3)
+        self.part_stats, self.part_nb = f(self.nTG, B, 4), f(2 * self.nTG, B, 3)
         self.rowc = f(B, 4)
         self.pi = f(B, G)
         self.expert = f(B, 2 * S)  # cluster mode: plan-weighted expert statistics
@@ -191,7 +191,7 @@ class _GroupWS:
         if bf16:
             h = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
             self.Tb, self.W1b = h(B, self.Gp), h(2 * H, self.Gp)
-            self.Wmb, self.amixb = h(G, self.KMp), h(B, self.KMp)
+            self.Wmb, self.amixb, self.wfoldb = h(G, self.KMp), h(B, self.KMp), h(G, 128)
             if with_grad:
                 self.dpib, self.dh1b = h(B, self.Gp), h(B, 2 * H)
             # split-K factors of the tensor-core GEMMs (128-wide tiles): fill the 148 SMs
@@ -223,8 +223,8 @@ class StepEngine:
             raise ValueError("precision must be 'fp32' or 'bf16'")
         self.precision = precision
         self.bf16 = precision == "bf16"
-        # fused tcgen05 mixture-GEMM + NB-likelihood kernel (bf16 mode); needs latent widths <= 32
-        self.fused_nb = self.bf16 and int(n_shared) <= 32 and int(n_private) <= 32
+        # fused tcgen05 decoder-GEMMs + NB-likelihood kernel (bf16 mode); the latent columns must fit one 64-wide k-block
+        self.fused_nb = self.bf16 and int(n_shared) + int(n_private) <= 64
         self.lib = L.load()
         self.d = Dims(tuple(int(x) for x in genes), int(n_hidden), int(n_shared), int(n_private))
         if self.d.n_private > self.d.n_shared:
@@ -248,6 +248,8 @@ class StepEngine:
         self.plan = plan
         self._ws: Dict[Tuple[int, int, bool], List[_GroupWS]] = {}
         self._ctx = None
+        self._side = None
+        self.parallel_groups = True
         self.nb_events = None  # bench hook: iterator of (start, end) CUDA events bracketing the NB-loglik sweep
 
     # -------------------------------------------------------------------------------- helpers
@@ -271,6 +273,31 @@ class StepEngine:
     def _tc_gemm(self, A, B, C, M, N, K, *, lda, ldb, ldc, a_mn=0, b_mn=0, bias=None, relu=0, acc=0, splits=1, ws=None):
         L.check(self.lib.spv_tc_gemm(a_mn, b_mn, A, lda, B, ldb, C, ldc, M, N, K, bias, relu, acc, splits, L.ptr(ws),
                                      self._stream()), "spv_tc_gemm")
+
+    def _fork_groups(self):
+        """iterate over the two groups, issuing each group's launches on its own stream (forked from the current stream and
+        joined back after the loop).  The two groups' encoder / decoder chains are independent and most of their kernels
+        fill only part of the 148 SMs, so they overlap; inside a CUDA graph the fork/join becomes two parallel branches."""
+        if not self.parallel_groups or self.device.type != "cuda":
+            for g in (0, 1):
+                yield g
+            return
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in (0, 1)]
+        cur = torch.cuda.current_stream(self.device)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        joins = []
+        for g in (0, 1):
+            s = self._side[g]
+            s.wait_event(fork)
+            with torch.cuda.stream(s):
+                yield g
+            ev = torch.cuda.Event()
+            ev.record(s)
+            joins.append(ev)
+        for ev in joins:
+            cur.wait_event(ev)
 
     def workspace(self, B0, B1, with_grad=True):
         key = (B0, B1, with_grad)
@@ -299,7 +326,8 @@ class StepEngine:
         tr = 1 if training else 0
         srcs = []
         # ---------------- encoders (reference nn/networks.py:119-125, module :428-448)
-        for g, (bt, w) in enumerate(zip(batches, ws)):
+        for g in self._fork_groups():
+            bt, w, st = batches[g], ws[g], self._stream()
             G, B = d.genes[g], Bs[g]
             src, esz = self._src_of(bt.X)
             ldx = bt.X.stride(0)
@@ -337,7 +365,8 @@ class StepEngine:
         if not decode:
             return ws
         # ---------------- decoders + NB likelihood (reference nn/networks.py:314-325, module :751-759, :817-824)
-        for g, (bt, w) in enumerate(zip(batches, ws)):
+        for g in self._fork_groups():
+            bt, w, st = batches[g], ws[g], self._stream()
             G, B = d.genes[g], Bs[g]
             src, xptr, ldx = srcs[g]
             zzp = w.amix.data_ptr() + 4 * HD
@@ -346,7 +375,8 @@ class StepEngine:
                                 self.P(g, "bs"), self.P(g, "px_r"), self.Bf(g, "rm_p"), self.Bf(g, "rv_p"),
                                 self.Bf(g, "rm_s"), self.Bf(g, "rv_s"), zzp, w.zsum, w.cov_part, w.wfold, w.genec, w.zmean,
                                 w.zcov])
-            L.check(lib.spv_dec_fold(fold, KMIX, B, G, P, S, tr, DEC_BN_EPS, DEC_BN_MOM, st), "spv_dec_fold")
+            L.check(lib.spv_dec_fold(fold, KMIX, B, G, P, S, tr, DEC_BN_EPS, DEC_BN_MOM, L.ptr(w.wfoldb) if self.fused_nb else None, st),
+                    "spv_dec_fold")
             self._gemm(zzp, L.ptr(self.P(g, "Wh")), L.ptr(w.ah), B, HD, KZ, lda=KMIX, ldb=KZ, ldc=HD, tb=1,
                        bias=L.ptr(self.P(g, "bh")))
             L.check(lib.spv_bn_fwd(L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, B, HD, L.ptr(self.P(g, "gh")), L.ptr(self.P(g, "bth")),
@@ -361,8 +391,8 @@ class StepEngine:
                 L.check(lib.spv_to_bf16(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX, st), "spv_to_bf16")
                 L.check(lib.spv_to_bf16(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX, st), "spv_to_bf16")
                 if self.fused_nb:
-                    L.check(lib.spv_dec_nb_fwd_tc(src, dptrs, ldx, KMIX, L.ptr(w.amixb), w.KMp, L.ptr(w.Wmb), w.KMp, B, G, HD, P, S,
-                                                  1 if with_grad else 0, st), "spv_dec_nb_fwd_tc")
+                    L.check(lib.spv_dec_nb_fwd_tc(src, dptrs, ldx, L.ptr(w.amixb), w.KMp, L.ptr(w.Wmb), w.KMp, L.ptr(w.wfoldb), B, G,
+                                                  HD, P, S, 1 if with_grad else 0, st), "spv_dec_nb_fwd_tc")
                 else:  # unfused: tensor-core GEMM writes pi, the SIMT sweep consumes it
                     self._tc_gemm(L.ptr(w.amixb), L.ptr(w.Wmb), L.ptr(w.pi), B, G, KMIX, lda=w.KMp, ldb=w.KMp, ldc=G,
                                   bias=L.ptr(self.P(g, "bm")))
@@ -462,7 +492,8 @@ class StepEngine:
         H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
         batches, ws, Bs, noise, srcs, aux = ctx["batches"], ctx["ws"], ctx["Bs"], ctx["noise"], ctx["srcs"], ctx["aux"]
         # ---------------- decoders
-        for g, (bt, w) in enumerate(zip(batches, ws)):
+        for g in self._fork_groups():
+            bt, w, st = batches[g], ws[g], self._stream()
             G, B = d.genes[g], Bs[g]
             src, xptr, ldx = srcs[g]
             zzp = w.amix.data_ptr() + 4 * HD
@@ -522,7 +553,8 @@ class StepEngine:
             self._gemm(L.ptr(aux["P2"]), L.ptr(ws[1].dexpert), ws[1].dstats.data_ptr() + 4 * 2 * P, Bs[0], 2 * S, Bs[1],
                        lda=Bs[0], ldb=2 * S, ldc=NST, ta=1, acc=1)
         # ---------------- encoders
-        for g, (bt, w) in enumerate(zip(batches, ws)):
+        for g in self._fork_groups():
+            bt, w, st = batches[g], ws[g], self._stream()
             G, B = d.genes[g], Bs[g]
             src, xptr, ldx = srcs[g]
             L.check(lib.spv_bn_bwd(L.ptr(w.dstats), NST, L.ptr(w.r), NST, None, 0, L.ptr(w.dr), NST, B, NST,
