@@ -130,6 +130,13 @@ int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld
 int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
                       const void* wm_bf16, long long ld_wmb, const void* wfold_bf16, int B, int G, int HD, int P, int S,
                       int store_pi, void* stream);
+int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, float* rowc, float* rec, void* stream);
+/* tensor-core backward sweep: recomputes the three logit tiles on tcgen05 and writes dpi (bf16 [B, ld_dpi]), dyp / dys
+ * (ptrs[12], ptrs[13], fp32 [B, G]) and colsum [4, G] (column sums of dyp, dys, dpi, d loss / d theta);
+ * ptrs[15] = colpart workspace [ceil(B/128), 4, G].  scale = - grad_scale / B. */
+int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
+                      const void* wm_bf16, long long ld_wmb, const void* wfold_bf16, void* dpi_bf16, long long ld_dpi, int B,
+                      int G, int HD, int P, int S, float scale, float* colsum, void* stream);
 /* ptrs (18): Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm,
  * vpart [ceil(G/64), P+S], mpart [ceil(G/64), (P+S)^2]   (backward of nn/networks.py:314-320 through the folded BatchNorm) */
 int spv_dec_gene_bwd(const void* const* ptrs, int B, int G, int P, int S, void* stream);

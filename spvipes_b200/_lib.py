@@ -44,6 +44,8 @@ _SIGS = {
     "spv_dec_nb_fwd": [i, p, ll, ll, i, i, i, i, i, i, p],
     "spv_dec_nb_bwd": [i, p, ll, ll, i, i, i, i, i, f, p, p, ll, p],
     "spv_dec_nb_fwd_tc": [i, p, ll, p, ll, p, ll, p, i, i, i, i, i, i, p],
+    "spv_dec_nb_rowreduce": [p, i, i, p, p, p],
+    "spv_dec_nb_bwd_tc": [i, p, ll, p, ll, p, ll, p, p, ll, i, i, i, i, i, f, p, p],
     "spv_dec_gene_bwd": [p, i, i, i, i, p],
     "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, p],
     "spv_adam_tick": [p, p],

@@ -17,6 +17,54 @@ __device__ __forceinline__ float lgamma_pos_fast(float x) {
     return (y - 0.5f) * __logf(y) - y + 0.91893853f + s - __logf(p);
 }
 
+// digamma(x) for x > 0: psi(x) = psi(x + 6) - sum_{i<6} 1/(x+i), the sum as P'(x)/P(x) of P = prod (x+i) (one division),
+// then the asymptotic series at y = x + 6 (truncation error < 1/(240 y^8)).
+__device__ __forceinline__ float digamma_pos_fast(float x) {
+    float pr = x, dp = 1.0f;
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+        float xi = x + (float)i;
+        dp = fmaf(dp, xi, pr);
+        pr *= xi;
+    }
+    float y = x + 6.0f;
+    float iy = __frcp_rn(y), iy2 = iy * iy;
+    float s = iy2 * (0.083333333f - iy2 * (0.0083333333f - iy2 * 0.003968254f));
+    return __logf(y) - 0.5f * iy - s - __fdividef(dp, pr);
+}
+
+struct NbGrad { float dyp, dys, dpi, dth; };
+
+// gradients of loss w.r.t. the two softmax logits, the mixture logit and theta for one (cell, gene) element.
+// Dp / Ds: this cell's row sums of d ll / d rho * rho (from the forward), inv_elib = exp(-lib), scale = d loss / d ll.
+__device__ __forceinline__ NbGrad nb_backward_fast(float t, float lp, float ls, float pi, float th, float lte, float dgt, float Rp,
+                                                   float Rs, float Dp, float Ds, float inv_elib, float scale) {
+    float rp = __expf(lp + Rp), rs = __expf(ls + Rs);
+    float d1 = th + rp + NB_EPS, d2 = th + rs + NB_EPS;
+    float l1 = __logf(d1), l2 = __logf(d2);
+    float diff = th * (l2 - l1) + pi;  // log_nb_p - (log_nb_s - pi); the lgamma terms cancel
+    float gp = 0.0f, gs = 0.0f, dg = 0.0f;
+    if (t != 0.0f) {
+        diff += t * (__logf(rp + NB_EPS) - l1 - __logf(rs + NB_EPS) + l2);
+        gp = __fdividef(t, rp + NB_EPS);
+        gs = __fdividef(t, rs + NB_EPS);
+        dg = digamma_pos_fast(t + th) - dgt;
+    }
+    float e = __expf(-fabsf(diff));
+    float wmin = __fdividef(e, 1.0f + e);
+    float wa = diff >= 0.0f ? 1.0f - wmin : wmin, wb = 1.0f - wa;
+    float q1 = __fdividef(th + t, d1), q2 = __fdividef(th + t, d2);
+    float ep = wa * (gp - q1) * rp, es = wb * (gs - q2) * rs;
+    float epi = __expf(-fabsf(pi));
+    float sneg = __fdividef(pi >= 0.0f ? epi : 1.0f, 1.0f + epi);  // sigmoid(-pi)
+    NbGrad o;
+    o.dyp = scale * (ep - rp * inv_elib * Dp);
+    o.dys = scale * (es - rs * inv_elib * Ds);
+    o.dpi = scale * (sneg - wb);
+    o.dth = scale * (wa * (lte - l1 - q1) + wb * (lte - l2 - q2) + __fdividef(th, th + NB_EPS) + dg);
+    return o;
+}
+
 struct NbOut { float ll, ep, es; };
 
 // t = log1p(count); lp / ls = BatchNorm'd softmax logits of the private / shared branch; Rp / Rs = lib - logsumexp_g(logits);

@@ -1,18 +1,10 @@
-// Fused decoder GEMMs + NB-mixture log-likelihood, tensor-core path (the north-star kernel).
-//
-//   pi[b, g] = [hm | z_private_arg | z_shared_arg][b, :] . Wm[g, :] + bm[g]                 K = 256 + P + S
-//   lp[b, g] = z_private_arg[b, :] . W'p[g, :] + cp[g],   ls[b, g] = z_shared_arg[b, :] . W's[g, :] + cs[g]
-//                                      (W', c: BatchNorm folded into the factor regressors by spv_dec_fold)
-//   rec_b    = - sum_g log_mixture_nb(log1p(x[b, g]); exp(lib) softmax(lp), exp(lib) softmax(ls), theta, pi)
-//
-// All three contractions run on tcgen05.mma (bf16 operands via TMA, fp32 accumulators in TMEM: columns 0-63 pi, 64-127 lp,
-// 128-191 ls).  The latent columns of the A operand all sit in k-block HD/64, so lp and ls each cost one extra MMA group on
-// that block against a zero-padded [genes, 64] copy of the folded weights.
-// One 128 (cells) x 64 (genes) tile per CTA, two CTAs per SM.  warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer,
-// warps 2..9: epilogue (thread = cell row; two warps per TMEM lane quarter, 32 gene columns each).  Once the accumulators
-// are complete the operand stages are reused for the tile's raw counts (coalesced row gather, uint16); the accumulators
-// are streamed out of TMEM four columns at a time.  Nothing of size [B, G] is written unless store_pi is set.
-// Reference: nn/networks.py:314-325, module/spVIPESmodule.py:751-759, 817-824; scvi log_mixture_nb.
+// Backward sweep of the fused decoder + NB-mixture likelihood on the tensor-core path.
+// Same tiling and pipeline as nb_tc.cu: the three logit tiles (pi, lp, ls) are RECOMPUTED on tcgen05 from the bf16 operands
+// (nothing [B, G]-sized was saved by the forward); the epilogue turns them into
+//   dpi [B, G] bf16  (operand of the weight / input gradient GEMMs of the mixture layer),
+//   dyp, dys [B, G] f32 (gradients w.r.t. the two folded BatchNorm outputs = softmax logits),
+//   colpart [nTB, 4, G]: per-128-row-tile column sums of dyp, dys, dpi and d loss / d theta.
+// Reference: autograd of nn/networks.py:314-325 + scvi log_mixture_nb (module/spVIPESmodule.py:823-824).
 #include "tc_common.cuh"
 #include "nb_math.cuh"
 #include "decoder_common.cuh"
@@ -24,38 +16,42 @@ constexpr int BM = 128, BN = 64, BK = 64, STAGES = 2;
 constexpr int EPI_WARPS = 8, EPI_THREADS = 32 * EPI_WARPS;
 constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TMEM_COLS = 256;           // 3 x 64 used
-constexpr int CNT_PITCH_W = BN / 2 + 1;  // uint16 count tile: 33 32-bit words per row, conflict-free for thread = row reads
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 6 * BN * 4 + 256;
+constexpr int TMEM_COLS = 256;
+constexpr int CNT_PITCH_W = BN / 2 + 1;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 6 * BN * 4 + 4 * 4 * BN * 4 + 256;
 
 static_assert(BM * CNT_PITCH_W * 4 <= STAGES * STAGE_BYTES, "count tile must fit in the operand stages");
 
-struct NbTcParams {
+struct NbTcBwdParams {
     const void* X; long ldx; const int* rows;
-    const float* bm;                   // [G]
-    const float* genec;                // [GC_N, G]
-    const float* rowc;                 // [B, 4]: Rp, Rs
-    float* pi;                         // [B, G] or null
-    float* part_nb;                    // [nTG, B, 3]
-    int B, G, K, kb_z;                 // kb_z: k-block holding the latent columns
+    const float* bm;
+    const float* genec;
+    const float* rowc;   // [B, 4]: Rp, Rs, Dp, Ds
+    const float* lib;    // [B]
+    __nv_bfloat16* dpi; long ld_dpi;
+    float* dyp; float* dys;   // [B, G]
+    float* colpart;           // [nTB, 4, G]
+    int B, G, K, kb_z;
+    float scale;
 };
 
 template <int SRC>
-__global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                const __grid_constant__ CUtensorMap mapB,
-                                                               const __grid_constant__ CUtensorMap mapZ, NbTcParams p) {
+                                                               const __grid_constant__ CUtensorMap mapZ, NbTcBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = tc::smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
     uint8_t* tiles = smem_raw + pad;
-    uint8_t* z_tiles = tiles + STAGES * STAGE_BYTES;                    // folded private | shared weights, [BN][64] bf16 each
-    float* s_gc = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);      // [6][BN]: cp, cs, theta, lte, lgt, bm
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_gc + 6 * BN);
+    uint8_t* z_tiles = tiles + STAGES * STAGE_BYTES;
+    float* s_gc = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);  // [6][BN]: cp, cs, theta, lte, dgt, bm
+    float* s_col = s_gc + 6 * BN;                                    // [4 quantities][4 quarters][BN]
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_col + 16 * BN);
     uint64_t* empty = full + STAGES;
     uint64_t* z_full = empty + STAGES;
     uint64_t* tmem_full = z_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(tiles);  // aliases the operand stages once the MMAs are done
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(tiles);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
@@ -82,8 +78,8 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
     if (warp == 0) {
         if (tc::elect_one()) {
             tc::mbar_expect_tx(z_full, 2 * B_BYTES);
-            tc::tma_load_2d(&mapZ, z_full, z_tiles, 0, n0);             // private block, columns 0..63
-            tc::tma_load_2d(&mapZ, z_full, z_tiles + B_BYTES, 64, n0);  // shared block, columns 64..127
+            tc::tma_load_2d(&mapZ, z_full, z_tiles, 0, n0);
+            tc::tma_load_2d(&mapZ, z_full, z_tiles + B_BYTES, 64, n0);
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
@@ -108,7 +104,7 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
                 for (int kk = 0; kk < BK / 16; ++kk)
                     tc::umma_bf16(tmem_base, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(b_base + kk * 32, 16, 1024),
                                   idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                if (i == p.kb_z) {  // the two softmax-branch logits: same A block against the folded weights
+                if (i == p.kb_z) {
                     tc::mbar_wait(z_full, 0);
                     tc::fence_after_sync();
                     const uint32_t zp_base = tc::smem_u32(z_tiles), zs_base = zp_base + B_BYTES;
@@ -126,31 +122,32 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
         }
     } else {
         // ================= epilogue: 8 warps =================
-        const int et = threadIdx.x - 64;  // 0..255
+        const int et = threadIdx.x - 64;
         const long G = p.G;
-        for (int i = et; i < BN; i += EPI_THREADS) {  // per-gene constants of the tile (overlaps the TMA / MMA phase)
+        for (int i = et; i < BN; i += EPI_THREADS) {
             int g = n0 + i;
             bool ok = g < p.G;
             s_gc[0 * BN + i] = ok ? __ldg(p.genec + GC_CP * G + g) : 0.0f;
             s_gc[1 * BN + i] = ok ? __ldg(p.genec + GC_CS * G + g) : 0.0f;
             s_gc[2 * BN + i] = ok ? __ldg(p.genec + GC_THETA * G + g) : 1.0f;
             s_gc[3 * BN + i] = ok ? __ldg(p.genec + GC_LTE * G + g) : 0.0f;
-            s_gc[4 * BN + i] = ok ? __ldg(p.genec + GC_LGT * G + g) : 0.0f;
+            s_gc[4 * BN + i] = ok ? __ldg(p.genec + GC_DGT * G + g) : 0.0f;
             s_gc[5 * BN + i] = ok ? __ldg(p.bm + g) : 0.0f;
         }
         const int e = warp - 2;
-        const int q = warp & 3;          // TMEM lane quarter this warp may access
-        const int half = e >> 2;         // which 32 gene columns of the tile
-        const int rloc = q * 32 + lane;  // row within the tile
+        const int q = warp & 3;
+        const int half = e >> 2;
+        const int rloc = q * 32 + lane;
         const int m = m0 + rloc;
         const bool mok = m < p.B;
         const int mm = mok ? m : 0;
         const float Rp = __ldg(p.rowc + (long)mm * 4 + 0), Rs = __ldg(p.rowc + (long)mm * 4 + 1);
+        const float Dp = __ldg(p.rowc + (long)mm * 4 + 2), Ds = __ldg(p.rowc + (long)mm * 4 + 3);
+        const float inv_elib = __expf(-__ldg(p.lib + mm));
         const long xrow = (p.rows ? (long)__ldg(p.rows + mm) : (long)mm) * p.ldx;
-        tc::mbar_wait(tmem_full, 0);  // accumulators complete; the operand stages are free from here on
+        tc::mbar_wait(tmem_full, 0);
         tc::fence_after_sync();
         if (SRC == SPV_SRC_U16_LOG1P) {
-            // coalesced row gather of the tile's counts: warp e loads rows e, e + 8, ...; lane l takes genes 2l, 2l + 1
             const unsigned short* X16 = reinterpret_cast<const unsigned short*>(p.X);
             for (int r = e; r < BM; r += EPI_WARPS) {
                 const int gm = m0 + r;
@@ -169,9 +166,9 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
                 s_cnt[r * CNT_PITCH_W + lane] = w0;
             }
         }
-        asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");  // constants + counts staged (epilogue warps only)
-        float sll = 0.0f, sep = 0.0f, ses = 0.0f;
-        const bool vec_pi = p.pi && ((G & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.pi) & 15) == 0);
+        asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
+        const bool vec4 = ((G & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dyp) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.dys) & 15) == 0);
+        const bool vec_b = ((p.ld_dpi & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dpi) & 7) == 0);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
         for (int j4 = 0; j4 < 32; j4 += 4) {
@@ -181,13 +178,12 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
             tc::tmem_ld4(lane_addr + (uint32_t)(BN + c0), rlp);
             tc::tmem_ld4(lane_addr + (uint32_t)(2 * BN + c0), rls);
             tc::tmem_ld_wait();
-            if (!mok) continue;
-            float pv[4];
+            float vyp[4], vys[4], vpi[4], vth[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const int gl = c0 + jj, g = n0 + gl;
-                pv[jj] = 0.0f;
-                if (g < p.G) {
+                vyp[jj] = vys[jj] = vpi[jj] = vth[jj] = 0.0f;
+                if (mok && g < p.G) {
                     const float lp = __uint_as_float(rlp[jj]) + s_gc[0 * BN + gl];
                     const float ls = __uint_as_float(rls[jj]) + s_gc[1 * BN + gl];
                     const float piv = __uint_as_float(rpi[jj]) + s_gc[5 * BN + gl];
@@ -199,23 +195,52 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
                     } else {
                         t = load_src<SRC>(p.X, xrow + g);
                     }
-                    NbOut o = nb_forward_fast(t, lp, ls, piv, s_gc[2 * BN + gl], s_gc[3 * BN + gl], s_gc[4 * BN + gl], Rp, Rs);
-                    sll += o.ll; sep += o.ep; ses += o.es;
-                    pv[jj] = piv;
+                    NbGrad o = nb_backward_fast(t, lp, ls, piv, s_gc[2 * BN + gl], s_gc[3 * BN + gl], s_gc[4 * BN + gl], Rp, Rs,
+                                                Dp, Ds, inv_elib, p.scale);
+                    vyp[jj] = o.dyp; vys[jj] = o.dys; vpi[jj] = o.dpi; vth[jj] = o.dth;
                 }
             }
-            if (p.pi) {
+            if (mok) {
                 const int g = n0 + c0;
-                float* dst = p.pi + (long)m * G + g;
-                if (vec_pi && g + 3 < p.G) *reinterpret_cast<float4*>(dst) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-                else
+                float* d1 = p.dyp + (long)m * G + g;
+                float* d2 = p.dys + (long)m * G + g;
+                __nv_bfloat16* d3 = p.dpi + (long)m * p.ld_dpi + g;
+                if (vec4 && g + 3 < p.G) {
+                    *reinterpret_cast<float4*>(d1) = make_float4(vyp[0], vyp[1], vyp[2], vyp[3]);
+                    *reinterpret_cast<float4*>(d2) = make_float4(vys[0], vys[1], vys[2], vys[3]);
+                } else {
                     for (int jj = 0; jj < 4; ++jj)
-                        if (g + jj < p.G) dst[jj] = pv[jj];
+                        if (g + jj < p.G) { d1[jj] = vyp[jj]; d2[jj] = vys[jj]; }
+                }
+                if (vec_b && g + 3 < p.G) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(vpi[0], vpi[1]), hi = __floats2bfloat162_rn(vpi[2], vpi[3]);
+                    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                    *reinterpret_cast<uint2*>(d3) = pk;
+                } else {
+                    for (int jj = 0; jj < 4; ++jj)
+                        if (g + jj < p.G) d3[jj] = __float2bfloat16(vpi[jj]);
+                }
+            }
+            // column sums over this warp's 32 rows (lanes), then lane 0 parks them for the cross-quarter sum
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                float a = warp_sum(vyp[jj]), b = warp_sum(vys[jj]), c = warp_sum(vpi[jj]), d = warp_sum(vth[jj]);
+                if (lane == 0) {
+                    const int gl = c0 + jj;
+                    s_col[(0 * 4 + q) * BN + gl] = a;
+                    s_col[(1 * 4 + q) * BN + gl] = b;
+                    s_col[(2 * 4 + q) * BN + gl] = c;
+                    s_col[(3 * 4 + q) * BN + gl] = d;
+                }
             }
         }
-        if (mok) {
-            float* o = p.part_nb + ((long)(blockIdx.x * 2 + half) * p.B + m) * 3;
-            o[0] = sll; o[1] = sep; o[2] = ses;
+        asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
+        for (int i = et; i < 4 * BN; i += EPI_THREADS) {
+            const int qty = i / BN, gl = i - qty * BN, g = n0 + gl;
+            if (g < p.G) {
+                const float* s = s_col + (qty * 4) * BN + gl;
+                p.colpart[((long)blockIdx.y * 4 + qty) * G + g] = s[0] + s[BN] + s[2 * BN] + s[3 * BN];
+            }
         }
     }
     tc::fence_before_sync();
@@ -226,37 +251,26 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
     }
 }
 
-__global__ void rownb_tc_kernel(const float* __restrict__ part, int nPart, int B, float* __restrict__ rowc, float* __restrict__ rec) {
-    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (b >= B) return;
-    float ll = 0.0f, dp = 0.0f, ds = 0.0f;
-    for (int t = lane; t < nPart; t += 32) {
-        const float* o = part + ((long)t * B + b) * 3;
-        ll += o[0]; dp += o[1]; ds += o[2];
-    }
-    ll = warp_sum(ll); dp = warp_sum(dp); ds = warp_sum(ds);
-    if (lane == 0) {
-        rec[b] = -ll;
-        rowc[(long)b * 4 + 2] = dp;
-        rowc[(long)b * 4 + 3] = ds;
-    }
+__global__ void colpart_reduce_tc_kernel(const float* __restrict__ colpart, int nTB, int G, float* __restrict__ colsum) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= 4L * G) return;
+    float s = 0.0f;
+    for (int t = 0; t < nTB; ++t) s += colpart[(long)t * 4 * G + i];
+    colsum[i] = s;
 }
 
 }  // namespace
 
-// ptrs: the SPV_DEC_NPTR list of spv_dec_nb_fwd (X, rows, amix [unused], wfold [unused], wm [unused], bm, genec, lib,
-// part_stats, rowc, pi, part_nb [>= 2 * ceil(G/64) * B * 3 floats], ..., rec).  rowc[:, 0:2] must hold the softmax
-// normalisers (phase 1 of spv_dec_nb_fwd).  bf16 operands: amix_bf16 [B, ld_amixb] = [hm | zz], wm_bf16 [G, ld_wmb] = mixture
-// weight, wfold_bf16 [G, 128] = folded factor-regressor weights laid out against the latent k-block (written by spv_dec_fold).
-extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
-                                 const void* wm_bf16, long long ld_wmb, const void* wfold_bf16, int B, int G, int HD, int P,
-                                 int S, int store_pi, void* stream) {
-    if (!ptrs || !amix_bf16 || !wm_bf16 || !wfold_bf16 || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
-    if ((HD % BK) != 0 || P + S > BK) return SPV_ERR_ARG;  // the latent columns must sit in one k-block
-    const int need[] = {0, 5, 6, 9, 11, 16};
+// ptrs: the SPV_DEC_NPTR list (X, rows, -, -, -, bm, genec, lib, -, rowc, -, -, dyp, dys, -, colpart [ceil(B/128), 4, G], -).
+// dpi_bf16 [B, ld_dpi] receives d loss / d pi.  colsum [4, G] = column sums of dyp, dys, dpi, d loss / d theta.
+extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
+                                 const void* wm_bf16, long long ld_wmb, const void* wfold_bf16, void* dpi_bf16, long long ld_dpi,
+                                 int B, int G, int HD, int P, int S, float scale, float* colsum, void* stream) {
+    if (!ptrs || !amix_bf16 || !wm_bf16 || !wfold_bf16 || !dpi_bf16 || !colsum || B <= 0 || G <= 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
+    if ((HD % BK) != 0 || P + S > BK) return SPV_ERR_ARG;
+    const int need[] = {0, 5, 6, 7, 9, 12, 13, 15};
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
-    if (store_pi && !ptrs[10]) return SPV_ERR_ARG;
     const int K = HD + P + S;
     CUtensorMap ma, mb, mz;
     int rc = spv_make_tensor_map_bf16(&ma, amix_bf16, (unsigned long long)K, (unsigned long long)B, (unsigned long long)ld_amixb, 64, BM);
@@ -265,30 +279,25 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
     if (rc != SPV_OK) return rc;
     rc = spv_make_tensor_map_bf16(&mz, wfold_bf16, 128ull, (unsigned long long)G, 128ull, 64, BN);
     if (rc != SPV_OK) return rc;
-    NbTcParams p;
+    NbTcBwdParams p;
     p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
-    p.rowc = (const float*)ptrs[9]; p.pi = store_pi ? (float*)ptrs[10] : nullptr; p.part_nb = (float*)ptrs[11];
-    p.B = B; p.G = G; p.K = K; p.kb_z = HD / BK;
+    p.lib = (const float*)ptrs[7]; p.rowc = (const float*)ptrs[9]; p.dyp = (float*)ptrs[12]; p.dys = (float*)ptrs[13];
+    p.colpart = (float*)ptrs[15]; p.dpi = reinterpret_cast<__nv_bfloat16*>(dpi_bf16); p.ld_dpi = ld_dpi;
+    p.B = B; p.G = G; p.K = K; p.kb_z = HD / BK; p.scale = scale;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(nb_tc_fwd_kernel<SPV_SRC_U16_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(nb_tc_fwd_kernel<SPV_SRC_F32_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(nb_tc_bwd_kernel<SPV_SRC_U16_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(nb_tc_bwd_kernel<SPV_SRC_F32_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
             return SPV_ERR_LAUNCH;
         configured = true;
     }
     dim3 grid((G + BN - 1) / BN, (B + BM - 1) / BM);
-    if (src == SPV_SRC_U16_LOG1P) nb_tc_fwd_kernel<SPV_SRC_U16_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, p);
-    else if (src == SPV_SRC_F32_LOG1P) nb_tc_fwd_kernel<SPV_SRC_F32_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, p);
+    if (src == SPV_SRC_U16_LOG1P) nb_tc_bwd_kernel<SPV_SRC_U16_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, p);
+    else if (src == SPV_SRC_F32_LOG1P) nb_tc_bwd_kernel<SPV_SRC_F32_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, p);
     else return SPV_ERR_ARG;
     SPV_CHECK_LAUNCH();
-    return SPV_OK;
-}
-
-// rec[b] = - sum over the 2 * ceil(G/64) per-tile partials of spv_dec_nb_fwd_tc; also the softmax-backward row sums rowc[:, 2:4]
-extern "C" int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, float* rowc, float* rec, void* stream) {
-    if (!part_nb || !rowc || !rec || G <= 0 || B <= 0) return SPV_ERR_ARG;
-    rownb_tc_kernel<<<(B + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part_nb, 2 * ((G + BN - 1) / BN), B, rowc, rec);
+    colpart_reduce_tc_kernel<<<(4 * G + 255) / 256, 256, 0, st>>>(p.colpart, (int)grid.y, G, colsum);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

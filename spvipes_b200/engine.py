@@ -385,14 +385,19 @@ class StepEngine:
             dptrs = self._dec_ptrs(g, w, xptr, bt.rows, with_grad)
             L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 1, st), "spv_dec_nb_fwd")
             evs = next(self.nb_events) if self.nb_events is not None else None
-            if evs is not None:
-                evs[0].record()
             if self.bf16:  # mixture logits on the tensor cores, consumed by the NB sweep
                 L.check(lib.spv_to_bf16(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX, st), "spv_to_bf16")
                 L.check(lib.spv_to_bf16(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX, st), "spv_to_bf16")
+            if evs is not None:
+                evs[0].record()
+            if self.bf16:
                 if self.fused_nb:
                     L.check(lib.spv_dec_nb_fwd_tc(src, dptrs, ldx, L.ptr(w.amixb), w.KMp, L.ptr(w.Wmb), w.KMp, L.ptr(w.wfoldb), B, G,
-                                                  HD, P, S, 1 if with_grad else 0, st), "spv_dec_nb_fwd_tc")
+                                                  HD, P, S, 0, st), "spv_dec_nb_fwd_tc")  # backward recomputes pi
+                    if evs is not None:
+                        evs[1].record()
+                        evs = None
+                    L.check(lib.spv_dec_nb_rowreduce(L.ptr(w.part_nb), G, B, L.ptr(w.rowc), L.ptr(w.rec), st), "spv_dec_nb_rowreduce")
                 else:  # unfused: tensor-core GEMM writes pi, the SIMT sweep consumes it
                     self._tc_gemm(L.ptr(w.amixb), L.ptr(w.Wmb), L.ptr(w.pi), B, G, KMIX, lda=w.KMp, ldb=w.KMp, ldc=G,
                                   bias=L.ptr(self.P(g, "bm")))
@@ -497,9 +502,14 @@ class StepEngine:
             G, B = d.genes[g], Bs[g]
             src, xptr, ldx = srcs[g]
             zzp = w.amix.data_ptr() + 4 * HD
-            L.check(lib.spv_dec_nb_bwd(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, KMIX, B, G, HD, P, S,
-                                       -float(grad_scale) / B, L.ptr(w.colsum), L.ptr(w.dpib) if self.bf16 else None,
-                                       w.Gp if self.bf16 else 0, st), "spv_dec_nb_bwd")
+            if self.fused_nb:  # logits recomputed on the tensor cores, gradients in the TMEM epilogue
+                L.check(lib.spv_dec_nb_bwd_tc(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, L.ptr(w.amixb), w.KMp,
+                                              L.ptr(w.Wmb), w.KMp, L.ptr(w.wfoldb), L.ptr(w.dpib), w.Gp, B, G, HD, P, S,
+                                              -float(grad_scale) / B, L.ptr(w.colsum), st), "spv_dec_nb_bwd_tc")
+            else:
+                L.check(lib.spv_dec_nb_bwd(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, KMIX, B, G, HD, P, S,
+                                           -float(grad_scale) / B, L.ptr(w.colsum), L.ptr(w.dpib) if self.bf16 else None,
+                                           w.Gp if self.bf16 else 0, st), "spv_dec_nb_bwd")
             # d Wm = dpi^T [hm | zz];   d [hm | zz] = dpi Wm
             if self.bf16:
                 self._tc_gemm(L.ptr(w.dpib), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=w.Gp, ldb=w.KMp, ldc=KMIX,
