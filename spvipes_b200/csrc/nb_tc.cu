@@ -147,27 +147,37 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
         const int mm = mok ? m : 0;
         const float Rp = __ldg(p.rowc + (long)mm * 4 + 0), Rs = __ldg(p.rowc + (long)mm * 4 + 1);
         const long xrow = (p.rows ? (long)__ldg(p.rows + mm) : (long)mm) * p.ldx;
+        // coalesced row gather of the tile's counts into registers (overlaps the MMA phase): warp e takes rows e, e + 8, ...;
+        // lane l takes genes 2l, 2l + 1
+        uint32_t cw[BM / EPI_WARPS];
+        if (SRC == SPV_SRC_U16_LOG1P) {
+            const unsigned short* X16 = reinterpret_cast<const unsigned short*>(p.X);
+            long xr[BM / EPI_WARPS];
+#pragma unroll
+            for (int i = 0; i < BM / EPI_WARPS; ++i) {
+                const int gm = m0 + e + EPI_WARPS * i;
+                xr[i] = gm < p.B ? (p.rows ? (long)__ldg(p.rows + gm) : (long)gm) * p.ldx : -1;
+            }
+            const int g = n0 + 2 * lane;
+#pragma unroll
+            for (int i = 0; i < BM / EPI_WARPS; ++i) {
+                cw[i] = 0u;
+                if (xr[i] >= 0) {
+                    const unsigned short* src = X16 + xr[i] + g;
+                    if (g + 1 < p.G && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+                        cw[i] = __ldg(reinterpret_cast<const uint32_t*>(src));
+                    } else {
+                        uint32_t c0 = g < p.G ? __ldg(src) : 0u, c1 = g + 1 < p.G ? __ldg(src + 1) : 0u;
+                        cw[i] = c0 | (c1 << 16);
+                    }
+                }
+            }
+        }
         tc::mbar_wait(tmem_full, 0);  // accumulators complete; the operand stages are free from here on
         tc::fence_after_sync();
         if (SRC == SPV_SRC_U16_LOG1P) {
-            // coalesced row gather of the tile's counts: warp e loads rows e, e + 8, ...; lane l takes genes 2l, 2l + 1
-            const unsigned short* X16 = reinterpret_cast<const unsigned short*>(p.X);
-            for (int r = e; r < BM; r += EPI_WARPS) {
-                const int gm = m0 + r;
-                uint32_t w0 = 0;
-                if (gm < p.B) {
-                    const long xr = (p.rows ? (long)__ldg(p.rows + gm) : (long)gm) * p.ldx;
-                    const int g = n0 + 2 * lane;
-                    const unsigned short* src = X16 + xr + g;
-                    if (g + 1 < p.G && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
-                        w0 = __ldg(reinterpret_cast<const uint32_t*>(src));
-                    } else {
-                        uint32_t c0 = g < p.G ? __ldg(src) : 0u, c1 = g + 1 < p.G ? __ldg(src + 1) : 0u;
-                        w0 = c0 | (c1 << 16);
-                    }
-                }
-                s_cnt[r * CNT_PITCH_W + lane] = w0;
-            }
+#pragma unroll
+            for (int i = 0; i < BM / EPI_WARPS; ++i) s_cnt[(e + EPI_WARPS * i) * CNT_PITCH_W + lane] = cw[i];
         }
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");  // constants + counts staged (epilogue warps only)
         float sll = 0.0f, sep = 0.0f, ses = 0.0f;
@@ -195,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
                     if (SRC == SPV_SRC_U16_LOG1P) {
                         uint32_t w = s_cnt[rloc * CNT_PITCH_W + (gl >> 1)];
                         uint32_t c = (gl & 1) ? (w >> 16) : (w & 0xffffu);
-                        t = c == 0u ? 0.0f : __logf(1.0f + (float)c);
+                        t = c == 0u ? 0.0f : fast_log(1.0f + (float)c);
                     } else {
                         t = load_src<SRC>(p.X, xrow + g);
                     }
