@@ -110,10 +110,10 @@ int spv_loss(const float* rec0, const float* rec1, const float* klp0, const floa
  * ptrs (18): Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, cov_part, wfold, genec,
  * zmean, zcov.   nn/networks.py:314-320, scvi FCLayers; module/spVIPESmodule.py:758 */
 #define SPV_DEC_GENEC_ROWS 12
-/* wfold_bf16 (optional, [G, 128] bf16): the folded weights laid out against the 64-wide k-block that holds the latent
- * columns of the mixture operand (private block in columns 0-63, shared block in 64-127), operand of spv_dec_nb_fwd_tc */
+/* wz_bf16 (optional): rows [Gp, 3 Gp) of the stacked bf16 tensor-core operand [3 Gp, ld_wz] (rows [0, G): mixture weight,
+ * [Gp, Gp + G): folded private weights in the latent columns HD .., [2 Gp, 2 Gp + G): folded shared weights) */
 int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, int S, int training, float eps, float momentum,
-                 void* wfold_bf16, void* stream);
+                 void* wz_bf16, long long ld_wz, int Gp, int HD, void* stream);
 /* fused decoder + NB-mixture likelihood sweeps.  ptrs (SPV_DEC_NPTR): X, rows, amix, wfold, wm, bm, genec, lib, part_stats,
  * rowc, pi, part_nb, dyp, dys, dpi, colpart, rec.   nn/networks.py:314-325; module/spVIPESmodule.py:759, 817-824 */
 #define SPV_DEC_NPTR 17
@@ -125,21 +125,21 @@ int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld
                    float scale, float* colsum, void* dpi_bf16, long long ld_dpi_bf16, void* stream);
 /* tensor-core version of phase 2 of spv_dec_nb_fwd: the mixture GEMM and the two softmax-branch logit GEMMs on tcgen05
  * (bf16 operands via TMA, fp32 accumulators in TMEM) with the NB-mixture log-likelihood fused into the TMEM epilogue.
- * amix_bf16 [B, ld_amixb] = [hm | zz], wm_bf16 [G, ld_wmb] = mixture weight, wfold_bf16 [G, 128] from spv_dec_fold.
+ * amix_bf16 [B, ld_amixb] = [hm | zz]; wstack_bf16 [3 Gp, ld_w] = mixture weight + folded branch weights (spv_dec_fold).
  * part_nb (ptrs[11]) needs 2 * ceil(G/64) * B * 3 floats.  store_pi: also write the mixture logits to ptrs[10] (fp32). */
 int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
-                      const void* wm_bf16, long long ld_wmb, const void* wfold_bf16, int B, int G, int HD, int P, int S,
-                      int store_pi, void* stream);
+                      const void* wstack_bf16, long long ld_w, int Gp, int B, int G, int HD, int P, int S, int store_pi,
+                      void* stream);
 int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, float* rowc, float* rec, void* stream);
-/* tensor-core backward sweep: recomputes the three logit tiles on tcgen05 and writes dpi (bf16 [B, ld_dpi]), dyp / dys
- * (ptrs[12], ptrs[13], fp32 [B, G]) and colsum [4, G] (column sums of dyp, dys, dpi, d loss / d theta);
+/* tensor-core backward sweep: recomputes the three logit tiles on tcgen05 and writes D3 = [dpi | dyp | dys] (bf16
+ * [B, 3 Gp], operand of the gradient GEMMs) and colsum [4, G] (column sums of dyp, dys, dpi, d loss / d theta);
  * ptrs[15] = colpart workspace [ceil(B/128), 4, G].  scale = - grad_scale / B. */
 int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
-                      const void* wm_bf16, long long ld_wmb, const void* wfold_bf16, void* dpi_bf16, long long ld_dpi, int B,
-                      int G, int HD, int P, int S, float scale, float* colsum, void* stream);
+                      const void* wstack_bf16, long long ld_w, int Gp, void* d3_bf16, int B, int G, int HD, int P, int S,
+                      float scale, float* colsum, void* stream);
 /* ptrs (18): Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm,
  * vpart [ceil(G/64), P+S], mpart [ceil(G/64), (P+S)^2]   (backward of nn/networks.py:314-320 through the folded BatchNorm) */
-int spv_dec_gene_bwd(const void* const* ptrs, int B, int G, int P, int S, void* stream);
+int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, int G, int P, int S, void* stream);
 /* d zz = d(mixture) + d(softmax branches) - BatchNorm coupling terms, the latter summed from the `nparts` per-CTA
  * partials (vpart [nparts, P+S], mpart [nparts, (P+S)^2]) that spv_dec_gene_bwd writes (its last two ptrs) */
 int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* vpart, const float* mpart,

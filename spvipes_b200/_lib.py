@@ -40,13 +40,13 @@ _SIGS = {
     "spv_poe_fwd": [i, i, i, i, i, p, p, p, p, u64, p, p],
     "spv_poe_bwd": [i, i, i, i, i, p, p, p, p, u64, p, p, f, p],
     "spv_loss": [p, p, p, p, p, p, i, p, p, p],
-    "spv_dec_fold": [p, ll, i, i, i, i, i, f, f, p, p],
+    "spv_dec_fold": [p, ll, i, i, i, i, i, f, f, p, ll, i, i, p],
     "spv_dec_nb_fwd": [i, p, ll, ll, i, i, i, i, i, i, p],
     "spv_dec_nb_bwd": [i, p, ll, ll, i, i, i, i, i, f, p, p, ll, p],
-    "spv_dec_nb_fwd_tc": [i, p, ll, p, ll, p, ll, p, i, i, i, i, i, i, p],
+    "spv_dec_nb_fwd_tc": [i, p, ll, p, ll, p, ll, i, i, i, i, i, i, i, p],
     "spv_dec_nb_rowreduce": [p, i, i, p, p, p],
-    "spv_dec_nb_bwd_tc": [i, p, ll, p, ll, p, ll, p, p, ll, i, i, i, i, i, f, p, p],
-    "spv_dec_gene_bwd": [p, i, i, i, i, p],
+    "spv_dec_nb_bwd_tc": [i, p, ll, p, ll, p, ll, i, p, i, i, i, i, i, f, p, p],
+    "spv_dec_gene_bwd": [p, ll, i, i, i, i, p],
     "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, p],
     "spv_adam_tick": [p, p],
     "spv_adam": [p, p, p, p, ll, f, f, f, f, f, f, p, p],

@@ -10,13 +10,16 @@
 #include "decoder_common.cuh"
 #include "../../include/spvipes_b200.h"
 
-#define GENES_PER_CTA 64
+#define GENES_PER_CTA 64        // gene_bwd: 64 genes share one set of per-CTA partial sums
+#define FOLD_GENES_PER_CTA 8    // fold: one gene per warp
+#define GENE_BWD_THREADS 1024
 
 // ---------------------------------------------------------------------------------------
 // partial (un-normalised, centred) second moments of zz over a chunk of 64 rows
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) zcov_kernel(const float* __restrict__ zz, long ld, int B, int KZ,
-                                                   const float* __restrict__ zsum, float* __restrict__ cov_part) {
+                                                   const float* __restrict__ zsum, float* cov_part,
+                                                   float* __restrict__ zmean_out, float* __restrict__ zcov_out) {
     extern __shared__ float tile[];  // [64][KZ + 1]
     const int r0 = blockIdx.x * 64;
     const int ldt = KZ + 1;
@@ -35,6 +38,25 @@ __global__ void __launch_bounds__(256) zcov_kernel(const float* __restrict__ zz,
         for (int r = 0; r < 64; ++r) s = fmaf(tile[r * ldt + i], tile[r * ldt + j], s);
         cov_part[(long)blockIdx.x * KZ * KZ + idx] = s;
     }
+    // the last CTA to finish sums the partials in chunk order (deterministic) into the final mean / covariance
+    __shared__ int is_last;
+    int* counter = reinterpret_cast<int*>(cov_part + (long)gridDim.x * KZ * KZ);  // one spare slot, zero between launches
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int ticket = atomicAdd(counter, 1);
+        is_last = ticket == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int k = threadIdx.x; k < KZ; k += blockDim.x) zmean_out[k] = zsum[k] * invB;
+    for (int idx = threadIdx.x; idx < KZ * KZ; idx += blockDim.x) {
+        float s = 0.0f;
+        for (int c = 0; c < (int)gridDim.x; ++c) s += __ldcg(cov_part + (long)c * KZ * KZ + idx);
+        zcov_out[idx] = s * invB;
+    }
+    if (threadIdx.x == 0) *counter = 0;
 }
 
 struct FoldP {
@@ -42,7 +64,11 @@ struct FoldP {
     float *rm_p, *rv_p, *rm_s, *rv_s;
     const float *zsum, *cov_part;
     float *wfold, *genec, *zmean, *zcov;
-    __nv_bfloat16* wfold_bf16;  // optional [G, 128]: folded weights laid out against the latent k-block of the mixture operand
+    // optional: rows [Gp, 3 Gp) of the stacked bf16 operand [3 Gp, ld_wz] (private block then shared block); the folded weights
+    // go into the latent columns HD .. HD + P + S of their block, every other entry of those rows stays zero
+    __nv_bfloat16* wfold_bf16;
+    long ld_wz;
+    int Gp, HD;
     int G, P, S, B, ncov, training;
     float eps, momentum;
 };
@@ -52,23 +78,16 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
     const int KZ = p.P + p.S;
     float* smean = sh;
     float* scov = sh + KZ;
-    const float invB = 1.0f / (float)p.B;
-    for (int k = threadIdx.x; k < KZ; k += blockDim.x) smean[k] = p.zsum[k] * invB;
-    for (int i = threadIdx.x; i < KZ * KZ; i += blockDim.x) {
-        float s = 0.0f;
-        for (int c = 0; c < p.ncov; ++c) s += p.cov_part[(long)c * KZ * KZ + i];
-        scov[i] = s * invB;
+    if (p.training) {  // final mean / covariance of the latent minibatch (zcov_kernel)
+        for (int k = threadIdx.x; k < KZ; k += blockDim.x) smean[k] = p.zmean[k];
+        for (int i = threadIdx.x; i < KZ * KZ; i += blockDim.x) scov[i] = p.zcov[i];
     }
     __syncthreads();
-    if (blockIdx.x == 0) {
-        for (int k = threadIdx.x; k < KZ; k += blockDim.x) p.zmean[k] = smean[k];
-        for (int i = threadIdx.x; i < KZ * KZ; i += blockDim.x) p.zcov[i] = scov[i];
-    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long G = p.G;
-    for (int gi = warp; gi < GENES_PER_CTA; gi += 8) {
-        const int g = blockIdx.x * GENES_PER_CTA + gi;
-        if (g >= p.G) break;
+    {  // one gene per warp: every gene's chain of dependent loads runs concurrently
+        const int g = blockIdx.x * FOLD_GENES_PER_CTA + warp;
+        if (g >= p.G) return;
 #pragma unroll
         for (int br = 0; br < 2; ++br) {
             const int K = br == 0 ? p.P : p.S;
@@ -101,9 +120,9 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
             float a = (br == 0 ? p.gp : p.gs)[g] * invstd;
             float c = (br == 0 ? p.bp : p.bs)[g] - mean * a;
             for (int k = lane; k < K; k += 32) p.wfold[(long)g * KZ + off + k] = a * W[k];
-            if (p.wfold_bf16)  // columns br*64 + j, j = position of the latent inside its 64-wide k-block, zero elsewhere
-                for (int j = lane; j < 64; j += 32)
-                    p.wfold_bf16[(long)g * 128 + br * 64 + j] = __float2bfloat16((j >= off && j < off + K) ? a * W[j - off] : 0.0f);
+            if (p.wfold_bf16)  // bf16 copy inside the stacked tensor-core operand: block br, row g, latent columns HD + off ..
+                for (int k = lane; k < K; k += 32)
+                    p.wfold_bf16[((long)br * p.Gp + g) * p.ld_wz + p.HD + off + k] = __float2bfloat16(a * W[k]);
             if (lane == 0) {
                 p.genec[(br == 0 ? GC_CP : GC_CS) * G + g] = c;
                 p.genec[(br == 0 ? GC_AP : GC_AS) * G + g] = a;
@@ -123,7 +142,7 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
 
 // ptrs: Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, cov_part, wfold, genec, zmean, zcov
 extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, int S, int training, float eps,
-                            float momentum, void* wfold_bf16, void* stream) {
+                            float momentum, void* wz_bf16, long long ld_wz, int Gp, int HD, void* stream) {
     if (!ptrs || B <= 0 || G <= 0 || P <= 0 || S <= 0 || P + S > 96) return SPV_ERR_ARG;
     for (int i = 0; i < 18; ++i)
         if (!ptrs[i]) return SPV_ERR_ARG;
@@ -135,7 +154,7 @@ extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int
     const int ncov = (B + 63) / 64;
     if (training) {
         size_t sm1 = (size_t)64 * (KZ + 1) * sizeof(float);
-        zcov_kernel<<<ncov, 256, sm1, st>>>(zz, ld_zz, B, KZ, zsum, cov_part);
+        zcov_kernel<<<ncov, 256, sm1, st>>>(zz, ld_zz, B, KZ, zsum, cov_part, (float*)ptrs[16], (float*)ptrs[17]);
         SPV_CHECK_LAUNCH();
     }
     FoldP p;
@@ -144,11 +163,12 @@ extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int
     p.rm_p = (float*)ptrs[7]; p.rv_p = (float*)ptrs[8]; p.rm_s = (float*)ptrs[9]; p.rv_s = (float*)ptrs[10];
     p.zsum = zsum; p.cov_part = cov_part; p.wfold = (float*)ptrs[14]; p.genec = (float*)ptrs[15];
     p.zmean = (float*)ptrs[16]; p.zcov = (float*)ptrs[17];
-    p.wfold_bf16 = reinterpret_cast<__nv_bfloat16*>(wfold_bf16);
+    p.wfold_bf16 = reinterpret_cast<__nv_bfloat16*>(wz_bf16);
+    p.ld_wz = ld_wz; p.Gp = Gp; p.HD = HD;
     p.G = G; p.P = P; p.S = S; p.B = B; p.ncov = training ? ncov : 0; p.training = training; p.eps = eps; p.momentum = momentum;
     size_t sm2 = (size_t)(KZ + KZ * KZ) * sizeof(float);
     if (sm2 > 48 * 1024) cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-    fold_kernel<<<(G + GENES_PER_CTA - 1) / GENES_PER_CTA, 256, sm2, st>>>(p);
+    fold_kernel<<<(G + FOLD_GENES_PER_CTA - 1) / FOLD_GENES_PER_CTA, 32 * FOLD_GENES_PER_CTA, sm2, st>>>(p);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }
@@ -166,9 +186,10 @@ struct GeneBwdP {
     const float *Wp, *Ws, *Qp, *Qs, *genec, *colsum, *zmean, *zcov;
     float *dWp, *dWs, *dgp, *dbp, *dgs, *dbs, *dpx_r, *dbm, *vpart, *mpart;
     int G, P, S, B;
+    long ldq;  // row pitch of Qp / Qs (0: packed, P resp. S)
 };
 
-__global__ void __launch_bounds__(256) gene_bwd_kernel(GeneBwdP p) {
+__global__ void __launch_bounds__(GENE_BWD_THREADS) gene_bwd_kernel(GeneBwdP p) {
     extern __shared__ float sh[];
     const int KZ = p.P + p.S;
     float* smean = sh;                         // [KZ]
@@ -190,7 +211,7 @@ __global__ void __launch_bounds__(256) gene_bwd_kernel(GeneBwdP p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long G = p.G;
     const float invB = 1.0f / (float)p.B;
-    for (int gl = warp; gl < GENES_PER_CTA; gl += 8) {
+    for (int gl = warp; gl < GENES_PER_CTA; gl += (int)(blockDim.x >> 5)) {
         const int g = g0 + gl;
         if (g >= p.G) break;
 #pragma unroll
@@ -198,7 +219,7 @@ __global__ void __launch_bounds__(256) gene_bwd_kernel(GeneBwdP p) {
             const int K = br == 0 ? p.P : p.S;
             const int off = br == 0 ? 0 : p.P;
             const float* W = sW + gl * KZ + off;
-            const float* Q = (br == 0 ? p.Qp : p.Qs) + (long)g * K;
+            const float* Q = (br == 0 ? p.Qp : p.Qs) + (long)g * (p.ldq > 0 ? p.ldq : K);
             float* dW = (br == 0 ? p.dWp : p.dWs) + (long)g * K;
             const float a = p.genec[(br == 0 ? GC_AP : GC_AS) * G + g];
             const float invstd = p.genec[(br == 0 ? GC_ISTD_P : GC_ISTD_S) * G + g];
@@ -247,7 +268,7 @@ __global__ void __launch_bounds__(256) gene_bwd_kernel(GeneBwdP p) {
 
 // ptrs: Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm,
 //       vpart [ceil(G/64), KZ], mpart [ceil(G/64), KZ*KZ]
-extern "C" int spv_dec_gene_bwd(const void* const* ptrs, int B, int G, int P, int S, void* stream) {
+extern "C" int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, int G, int P, int S, void* stream) {
     if (!ptrs || B <= 0 || G <= 0 || P <= 0 || S <= 0 || P + S > 96) return SPV_ERR_ARG;
     for (int i = 0; i < 18; ++i)
         if (!ptrs[i]) return SPV_ERR_ARG;
@@ -257,11 +278,11 @@ extern "C" int spv_dec_gene_bwd(const void* const* ptrs, int B, int G, int P, in
     p.zcov = (const float*)ptrs[7]; p.dWp = (float*)ptrs[8]; p.dWs = (float*)ptrs[9]; p.dgp = (float*)ptrs[10];
     p.dbp = (float*)ptrs[11]; p.dgs = (float*)ptrs[12]; p.dbs = (float*)ptrs[13]; p.dpx_r = (float*)ptrs[14];
     p.dbm = (float*)ptrs[15]; p.vpart = (float*)ptrs[16]; p.mpart = (float*)ptrs[17];
-    p.G = G; p.P = P; p.S = S; p.B = B;
+    p.G = G; p.P = P; p.S = S; p.B = B; p.ldq = ldq;
     const int KZ = P + S;
     size_t smem = (size_t)(KZ + KZ * KZ + GENES_PER_CTA * KZ + 4 * GENES_PER_CTA) * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(gene_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gene_bwd_kernel<<<(G + GENES_PER_CTA - 1) / GENES_PER_CTA, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    gene_bwd_kernel<<<(G + GENES_PER_CTA - 1) / GENES_PER_CTA, GENE_BWD_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }
@@ -299,13 +320,13 @@ __global__ void __launch_bounds__(1024) dzz_combine_kernel(const float* __restri
     int lo = c < P ? 0 : P, hi = c < P ? P : KZ;
     float corr = 0.0f;
     for (int l = lo; l < hi; ++l) corr = fmaf(sM[c * KZ + l], zz[b * ld_zz + l] - zmean[l], corr);
-    dzz[b * KZ + c] = dmix[b * ld_dmix + c] + dzraw[b * KZ + c] - sv[c] - corr;
+    dzz[b * KZ + c] = dmix[b * ld_dmix + c] + (dzraw ? dzraw[b * KZ + c] : 0.0f) - sv[c] - corr;
 }
 
 extern "C" int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* vpart, const float* mpart,
                                    int nparts, const float* zz, long long ld_zz, const float* zmean, float* dzz, int B, int P,
                                    int S, void* stream) {
-    if (!dmix || !dzraw || !vpart || !mpart || !zz || !zmean || !dzz || B <= 0 || P <= 0 || S <= 0 || nparts <= 0) return SPV_ERR_ARG;
+    if (!dmix || !vpart || !mpart || !zz || !zmean || !dzz || B <= 0 || P <= 0 || S <= 0 || nparts <= 0) return SPV_ERR_ARG;
     const int KZ = P + S;
     long total = (long)B * KZ;
     size_t smem = (size_t)(KZ + KZ * KZ) * sizeof(float);

@@ -38,6 +38,7 @@ struct NbTcParams {
     float* pi;                         // [B, G] or null
     float* part_nb;                    // [nTG, B, 3]
     int B, G, K, kb_z;                 // kb_z: k-block holding the latent columns
+    int Gp;                            // row offset of the shared block inside the folded-weight operand
 };
 
 template <int SRC>
@@ -82,8 +83,8 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
     if (warp == 0) {
         if (tc::elect_one()) {
             tc::mbar_expect_tx(z_full, 2 * B_BYTES);
-            tc::tma_load_2d(&mapZ, z_full, z_tiles, 0, n0);             // private block, columns 0..63
-            tc::tma_load_2d(&mapZ, z_full, z_tiles + B_BYTES, 64, n0);  // shared block, columns 64..127
+            tc::tma_load_2d(&mapZ, z_full, z_tiles, p.kb_z * BK, n0);                   // folded private weights (rows 0..G)
+            tc::tma_load_2d(&mapZ, z_full, z_tiles + B_BYTES, p.kb_z * BK, p.Gp + n0);  // folded shared weights (rows Gp..)
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
@@ -256,12 +257,16 @@ __global__ void rownb_tc_kernel(const float* __restrict__ part, int nPart, int B
 
 // ptrs: the SPV_DEC_NPTR list of spv_dec_nb_fwd (X, rows, amix [unused], wfold [unused], wm [unused], bm, genec, lib,
 // part_stats, rowc, pi, part_nb [>= 2 * ceil(G/64) * B * 3 floats], ..., rec).  rowc[:, 0:2] must hold the softmax
-// normalisers (phase 1 of spv_dec_nb_fwd).  bf16 operands: amix_bf16 [B, ld_amixb] = [hm | zz], wm_bf16 [G, ld_wmb] = mixture
-// weight, wfold_bf16 [G, 128] = folded factor-regressor weights laid out against the latent k-block (written by spv_dec_fold).
+// normalisers (phase 1 of spv_dec_nb_fwd).  bf16 operands: amix_bf16 [B, ld_amixb] = [hm | zz]; wstack_bf16 [3 * Gp, ld_w]:
+// rows [0, G) the mixture weight, rows [Gp, Gp + G) / [2 Gp, 2 Gp + G) the folded private / shared factor-regressor weights
+// placed in the latent columns (written by spv_dec_fold), zero elsewhere.  Gp = G rounded up to a multiple of 8.
 extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
-                                 const void* wm_bf16, long long ld_wmb, const void* wfold_bf16, int B, int G, int HD, int P,
-                                 int S, int store_pi, void* stream) {
-    if (!ptrs || !amix_bf16 || !wm_bf16 || !wfold_bf16 || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
+                                 const void* wstack_bf16, long long ld_w, int Gp, int B, int G, int HD, int P, int S,
+                                 int store_pi, void* stream) {
+    if (!ptrs || !amix_bf16 || !wstack_bf16 || Gp < G || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
+    const void* wm_bf16 = wstack_bf16;
+    const long long ld_wmb = ld_w;
+    const void* wz_bf16 = reinterpret_cast<const __nv_bfloat16*>(wstack_bf16) + (size_t)Gp * ld_w;
     if ((HD % BK) != 0 || P + S > BK) return SPV_ERR_ARG;  // the latent columns must sit in one k-block
     const int need[] = {0, 5, 6, 9, 11, 16};
     for (int i : need)
@@ -273,9 +278,10 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
     if (rc != SPV_OK) return rc;
     rc = spv_make_tensor_map_bf16(&mb, wm_bf16, (unsigned long long)K, (unsigned long long)G, (unsigned long long)ld_wmb, 64, BN);
     if (rc != SPV_OK) return rc;
-    rc = spv_make_tensor_map_bf16(&mz, wfold_bf16, 128ull, (unsigned long long)G, 128ull, 64, BN);
+    rc = spv_make_tensor_map_bf16(&mz, wz_bf16, (unsigned long long)K, (unsigned long long)(2 * Gp), (unsigned long long)ld_w, 64, BN);
     if (rc != SPV_OK) return rc;
     NbTcParams p;
+    p.Gp = Gp;
     p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
     p.rowc = (const float*)ptrs[9]; p.pi = store_pi ? (float*)ptrs[10] : nullptr; p.part_nb = (float*)ptrs[11];
     p.B = B; p.G = G; p.K = K; p.kb_z = HD / BK;

@@ -28,10 +28,9 @@ struct NbTcBwdParams {
     const float* genec;
     const float* rowc;   // [B, 4]: Rp, Rs, Dp, Ds
     const float* lib;    // [B]
-    __nv_bfloat16* dpi; long ld_dpi;
-    float* dyp; float* dys;   // [B, G]
-    float* colpart;           // [nTB, 4, G]
-    int B, G, K, kb_z;
+    __nv_bfloat16* dpi; long ld_dpi;   // D3 [B, 3 * Gp] = [dpi | dyp | dys]
+    float* colpart;                    // [nTB, 4, G]
+    int B, G, K, kb_z, Gp;
     float scale;
 };
 
@@ -78,8 +77,8 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
     if (warp == 0) {
         if (tc::elect_one()) {
             tc::mbar_expect_tx(z_full, 2 * B_BYTES);
-            tc::tma_load_2d(&mapZ, z_full, z_tiles, 0, n0);
-            tc::tma_load_2d(&mapZ, z_full, z_tiles + B_BYTES, 64, n0);
+            tc::tma_load_2d(&mapZ, z_full, z_tiles, p.kb_z * BK, n0);
+            tc::tma_load_2d(&mapZ, z_full, z_tiles + B_BYTES, p.kb_z * BK, p.Gp + n0);
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
@@ -178,8 +177,7 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
             for (int i = 0; i < BM / EPI_WARPS; ++i) s_cnt[(e + EPI_WARPS * i) * CNT_PITCH_W + lane] = cw[i];
         }
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
-        const bool vec4 = ((G & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dyp) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.dys) & 15) == 0);
-        const bool vec_b = ((p.ld_dpi & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dpi) & 7) == 0);
+        const bool vec_b = ((p.ld_dpi & 3) == 0) && ((p.Gp & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dpi) & 7) == 0);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
         for (int j4 = 0; j4 < 32; j4 += 4) {
@@ -213,23 +211,20 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
             }
             if (mok) {
                 const int g = n0 + c0;
-                float* d1 = p.dyp + (long)m * G + g;
-                float* d2 = p.dys + (long)m * G + g;
+                // D3[b, :] = [dpi (Gp) | dyp (Gp) | dys (Gp)] in bf16: one operand for the three gradient GEMMs
                 __nv_bfloat16* d3 = p.dpi + (long)m * p.ld_dpi + g;
-                if (vec4 && g + 3 < p.G) {
-                    *reinterpret_cast<float4*>(d1) = make_float4(vyp[0], vyp[1], vyp[2], vyp[3]);
-                    *reinterpret_cast<float4*>(d2) = make_float4(vys[0], vys[1], vys[2], vys[3]);
-                } else {
-                    for (int jj = 0; jj < 4; ++jj)
-                        if (g + jj < p.G) { d1[jj] = vyp[jj]; d2[jj] = vys[jj]; }
-                }
-                if (vec_b && g + 3 < p.G) {
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(vpi[0], vpi[1]), hi = __floats2bfloat162_rn(vpi[2], vpi[3]);
-                    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-                    *reinterpret_cast<uint2*>(d3) = pk;
-                } else {
-                    for (int jj = 0; jj < 4; ++jj)
-                        if (g + jj < p.G) d3[jj] = __float2bfloat16(vpi[jj]);
+                const float* vals[3] = {vpi, vyp, vys};
+#pragma unroll
+                for (int blk = 0; blk < 3; ++blk) {
+                    __nv_bfloat16* dst = d3 + (long)blk * p.Gp;
+                    const float* v = vals[blk];
+                    if (vec_b && g + 3 < p.G) {
+                        __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+                        *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                    } else {
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (g + jj < p.G) dst[jj] = __float2bfloat16(v[jj]);
+                    }
                 }
             }
             // column sums over this warp's 32 rows (lanes), then lane 0 parks them for the cross-quarter sum
@@ -272,29 +267,31 @@ __global__ void colpart_reduce_tc_kernel(const float* __restrict__ colpart, int 
 
 }  // namespace
 
-// ptrs: the SPV_DEC_NPTR list (X, rows, -, -, -, bm, genec, lib, -, rowc, -, -, dyp, dys, -, colpart [ceil(B/128), 4, G], -).
-// dpi_bf16 [B, ld_dpi] receives d loss / d pi.  colsum [4, G] = column sums of dyp, dys, dpi, d loss / d theta.
+// ptrs: the SPV_DEC_NPTR list (X, rows, -, -, -, bm, genec, lib, -, rowc, -, -, -, -, -, colpart [ceil(B/128), 4, G], -).
+// d3_bf16 [B, 3 * Gp] receives [d loss / d pi | d loss / d y_private | d loss / d y_shared] (bf16, the A operand of the
+// gradient GEMMs).  wstack_bf16 [3 * Gp, ld_w]: see spv_dec_nb_fwd_tc.  colsum [4, G] = column sums of dyp, dys, dpi, dtheta.
 extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
-                                 const void* wm_bf16, long long ld_wmb, const void* wfold_bf16, void* dpi_bf16, long long ld_dpi,
-                                 int B, int G, int HD, int P, int S, float scale, float* colsum, void* stream) {
-    if (!ptrs || !amix_bf16 || !wm_bf16 || !wfold_bf16 || !dpi_bf16 || !colsum || B <= 0 || G <= 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
+                                 const void* wstack_bf16, long long ld_w, int Gp, void* d3_bf16, int B, int G, int HD, int P,
+                                 int S, float scale, float* colsum, void* stream) {
+    if (!ptrs || !amix_bf16 || !wstack_bf16 || !d3_bf16 || !colsum || Gp < G || B <= 0 || G <= 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
     if ((HD % BK) != 0 || P + S > BK) return SPV_ERR_ARG;
-    const int need[] = {0, 5, 6, 7, 9, 12, 13, 15};
+    const int need[] = {0, 5, 6, 7, 9, 15};
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
     const int K = HD + P + S;
+    const void* wz_bf16 = reinterpret_cast<const __nv_bfloat16*>(wstack_bf16) + (size_t)Gp * ld_w;
     CUtensorMap ma, mb, mz;
     int rc = spv_make_tensor_map_bf16(&ma, amix_bf16, (unsigned long long)K, (unsigned long long)B, (unsigned long long)ld_amixb, 64, BM);
     if (rc != SPV_OK) return rc;
-    rc = spv_make_tensor_map_bf16(&mb, wm_bf16, (unsigned long long)K, (unsigned long long)G, (unsigned long long)ld_wmb, 64, BN);
+    rc = spv_make_tensor_map_bf16(&mb, wstack_bf16, (unsigned long long)K, (unsigned long long)G, (unsigned long long)ld_w, 64, BN);
     if (rc != SPV_OK) return rc;
-    rc = spv_make_tensor_map_bf16(&mz, wfold_bf16, 128ull, (unsigned long long)G, 128ull, 64, BN);
+    rc = spv_make_tensor_map_bf16(&mz, wz_bf16, (unsigned long long)K, (unsigned long long)(2 * Gp), (unsigned long long)ld_w, 64, BN);
     if (rc != SPV_OK) return rc;
     NbTcBwdParams p;
     p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
-    p.lib = (const float*)ptrs[7]; p.rowc = (const float*)ptrs[9]; p.dyp = (float*)ptrs[12]; p.dys = (float*)ptrs[13];
-    p.colpart = (float*)ptrs[15]; p.dpi = reinterpret_cast<__nv_bfloat16*>(dpi_bf16); p.ld_dpi = ld_dpi;
-    p.B = B; p.G = G; p.K = K; p.kb_z = HD / BK; p.scale = scale;
+    p.lib = (const float*)ptrs[7]; p.rowc = (const float*)ptrs[9];
+    p.colpart = (float*)ptrs[15]; p.dpi = reinterpret_cast<__nv_bfloat16*>(d3_bf16); p.ld_dpi = 3L * Gp;
+    p.B = B; p.G = G; p.K = K; p.kb_z = HD / BK; p.Gp = Gp; p.scale = scale;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     static bool configured = false;
     if (!configured) {

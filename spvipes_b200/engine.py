@@ -172,7 +172,8 @@ class _GroupWS:
         self.partner = torch.empty(B, dtype=torch.int32, device=dev)
         self.amix = f(B, KMIX)
         self.zsum, self.zmean, self.zcov = f(KZ), f(KZ), f(KZ, KZ)
-        self.cov_part = f(self.nTB, KZ * KZ)
+        # per-64-row partial second moments + one spare slot holding the "last CTA" ticket counter (must start at zero)
+        self.cov_part = torch.zeros(self.nTB + 1, KZ * KZ, dtype=torch.float32, device=dev)
         self.wfold, self.genec = f(G, KZ), f(L.GENEC_ROWS, G)
         self.ah = f(B, HD)
         self.bn_h_mean, self.bn_h_istd = f(HD), f(HD)
@@ -191,14 +192,20 @@ class _GroupWS:
         if bf16:
             h = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
             self.Tb, self.W1b = h(B, self.Gp), h(2 * H, self.Gp)
-            self.Wmb, self.amixb, self.wfoldb = h(G, self.KMp), h(B, self.KMp), h(G, 128)
+            # stacked tensor-core operand [3 Gp, KMp]: rows [0, G) mixture weight, [Gp, Gp+G) / [2Gp, 2Gp+G) the folded
+            # private / shared factor-regressor weights in the latent columns (zero elsewhere)
+            self.Wstack, self.amixb = h(3 * self.Gp, self.KMp), h(B, self.KMp)
+            self.Wmb = self.Wstack[:G]
             if with_grad:
-                self.dpib, self.dh1b = h(B, self.Gp), h(B, 2 * H)
+                self.D3, self.dh1b = h(B, 3 * self.Gp), h(B, 2 * H)  # D3 = [dpi | dyp | dys]
+                self.dpib = self.D3  # unfused path: only the first Gp columns are used (row pitch 3 Gp)
+                self.CQ = f(2 * self.Gp, KZ)
             # split-K factors of the tensor-core GEMMs (128-wide tiles): fill the 148 SMs
             tiles = ((B + 127) // 128) * ((2 * H + 127) // 128)
             self.tc_splits_fc1 = max(1, min(148 // tiles, (G + 63) // 64 // 2))
             tiles = ((B + 127) // 128) * ((KMIX + 127) // 128)
             self.tc_splits_damix = max(1, min(148 // tiles, (G + 63) // 64 // 2))
+            self.tc_splits_damix3 = max(1, min(148 // tiles, (3 * self.Gp + 63) // 64 // 2))
         if with_grad:
             self.dyp, self.dys, self.dpi = f(B, G), f(B, G), f(B, G)
             self.colpart, self.colsum = f(self.nTB, 4, G), f(4, G)
@@ -375,8 +382,9 @@ class StepEngine:
                                 self.P(g, "bs"), self.P(g, "px_r"), self.Bf(g, "rm_p"), self.Bf(g, "rv_p"),
                                 self.Bf(g, "rm_s"), self.Bf(g, "rv_s"), zzp, w.zsum, w.cov_part, w.wfold, w.genec, w.zmean,
                                 w.zcov])
-            L.check(lib.spv_dec_fold(fold, KMIX, B, G, P, S, tr, DEC_BN_EPS, DEC_BN_MOM, L.ptr(w.wfoldb) if self.fused_nb else None, st),
-                    "spv_dec_fold")
+            wz = w.Wstack.data_ptr() + 2 * w.Gp * w.KMp if self.fused_nb else None
+            L.check(lib.spv_dec_fold(fold, KMIX, B, G, P, S, tr, DEC_BN_EPS, DEC_BN_MOM, wz, w.KMp if self.fused_nb else 0,
+                                     w.Gp, HD, st), "spv_dec_fold")
             self._gemm(zzp, L.ptr(self.P(g, "Wh")), L.ptr(w.ah), B, HD, KZ, lda=KMIX, ldb=KZ, ldc=HD, tb=1,
                        bias=L.ptr(self.P(g, "bh")))
             L.check(lib.spv_bn_fwd(L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, B, HD, L.ptr(self.P(g, "gh")), L.ptr(self.P(g, "bth")),
@@ -392,7 +400,7 @@ class StepEngine:
                 evs[0].record()
             if self.bf16:
                 if self.fused_nb:
-                    L.check(lib.spv_dec_nb_fwd_tc(src, dptrs, ldx, L.ptr(w.amixb), w.KMp, L.ptr(w.Wmb), w.KMp, L.ptr(w.wfoldb), B, G,
+                    L.check(lib.spv_dec_nb_fwd_tc(src, dptrs, ldx, L.ptr(w.amixb), w.KMp, L.ptr(w.Wstack), w.KMp, w.Gp, B, G,
                                                   HD, P, S, 0, st), "spv_dec_nb_fwd_tc")  # backward recomputes pi
                     if evs is not None:
                         evs[1].record()
@@ -502,35 +510,48 @@ class StepEngine:
             G, B = d.genes[g], Bs[g]
             src, xptr, ldx = srcs[g]
             zzp = w.amix.data_ptr() + 4 * HD
-            if self.fused_nb:  # logits recomputed on the tensor cores, gradients in the TMEM epilogue
+            if self.fused_nb:
+                # logits recomputed on the tensor cores, gradients in the TMEM epilogue -> D3 = [dpi | dyp | dys] (bf16)
                 L.check(lib.spv_dec_nb_bwd_tc(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, L.ptr(w.amixb), w.KMp,
-                                              L.ptr(w.Wmb), w.KMp, L.ptr(w.wfoldb), L.ptr(w.dpib), w.Gp, B, G, HD, P, S,
+                                              L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.D3), B, G, HD, P, S,
                                               -float(grad_scale) / B, L.ptr(w.colsum), st), "spv_dec_nb_bwd_tc")
+                Gp3 = 3 * w.Gp
+                # d Wm = dpi^T [hm | zz]
+                self._tc_gemm(L.ptr(w.D3), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=Gp3, ldb=w.KMp, ldc=KMIX,
+                              a_mn=1, b_mn=1)
+                # [Qp | .] = dyp^T zz, [. | Qs] = dys^T zz in one GEMM over the stacked rows (rows g and Gp + g)
+                self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, w.amixb.data_ptr() + 2 * HD, L.ptr(w.CQ), 2 * w.Gp, KZ, B, lda=Gp3,
+                              ldb=w.KMp, ldc=KZ, a_mn=1, b_mn=1)
+                # d [hm | zz] = dpi Wm + dyp W'p + dys W's: one GEMM against the stacked weights
+                self._tc_gemm(L.ptr(w.D3), L.ptr(w.Wstack), L.ptr(w.damix), B, KMIX, Gp3, lda=Gp3, ldb=w.KMp, ldc=KMIX, b_mn=1,
+                              splits=w.tc_splits_damix3, ws=w.ws)
+                Qp, Qs, ldq, dzraw = w.CQ.data_ptr(), w.CQ.data_ptr() + 4 * (w.Gp * KZ + P), KZ, None
             else:
                 L.check(lib.spv_dec_nb_bwd(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, KMIX, B, G, HD, P, S,
                                            -float(grad_scale) / B, L.ptr(w.colsum), L.ptr(w.dpib) if self.bf16 else None,
-                                           w.Gp if self.bf16 else 0, st), "spv_dec_nb_bwd")
-            # d Wm = dpi^T [hm | zz];   d [hm | zz] = dpi Wm
-            if self.bf16:
-                self._tc_gemm(L.ptr(w.dpib), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=w.Gp, ldb=w.KMp, ldc=KMIX,
-                              a_mn=1, b_mn=1)
-                self._tc_gemm(L.ptr(w.dpib), L.ptr(w.Wmb), L.ptr(w.damix), B, KMIX, G, lda=w.Gp, ldb=w.KMp, ldc=KMIX, b_mn=1,
-                              splits=w.tc_splits_damix, ws=w.ws)
-            else:
-                self._gemm(L.ptr(w.dpi), L.ptr(w.amix), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=G, ldb=KMIX, ldc=KMIX, ta=1)
-                self._gemm(L.ptr(w.dpi), L.ptr(self.P(g, "Wm")), L.ptr(w.damix), B, KMIX, G, lda=G, ldb=KMIX, ldc=KMIX,
+                                           3 * w.Gp if self.bf16 else 0, st), "spv_dec_nb_bwd")
+                # d Wm = dpi^T [hm | zz];   d [hm | zz] = dpi Wm
+                if self.bf16:
+                    self._tc_gemm(L.ptr(w.dpib), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=3 * w.Gp, ldb=w.KMp,
+                                  ldc=KMIX, a_mn=1, b_mn=1)
+                    self._tc_gemm(L.ptr(w.dpib), L.ptr(w.Wmb), L.ptr(w.damix), B, KMIX, G, lda=3 * w.Gp, ldb=w.KMp, ldc=KMIX,
+                                  b_mn=1, splits=w.tc_splits_damix, ws=w.ws)
+                else:
+                    self._gemm(L.ptr(w.dpi), L.ptr(w.amix), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=G, ldb=KMIX, ldc=KMIX, ta=1)
+                    self._gemm(L.ptr(w.dpi), L.ptr(self.P(g, "Wm")), L.ptr(w.damix), B, KMIX, G, lda=G, ldb=KMIX, ldc=KMIX,
+                               splits=w.splits_g, ws=w.ws)
+                # Q = dy^T z ;  dz (softmax branches) = dy W'
+                self._gemm(L.ptr(w.dyp), zzp, L.ptr(w.Qp), G, P, B, lda=G, ldb=KMIX, ldc=P, ta=1, splits=w.splits_b, ws=w.ws)
+                self._gemm(L.ptr(w.dys), zzp + 4 * P, L.ptr(w.Qs), G, S, B, lda=G, ldb=KMIX, ldc=S, ta=1, splits=w.splits_b, ws=w.ws)
+                self._gemm(L.ptr(w.dyp), L.ptr(w.wfold), L.ptr(w.dzraw), B, P, G, lda=G, ldb=KZ, ldc=KZ, splits=w.splits_g, ws=w.ws)
+                self._gemm(L.ptr(w.dys), w.wfold.data_ptr() + 4 * P, w.dzraw.data_ptr() + 4 * P, B, S, G, lda=G, ldb=KZ, ldc=KZ,
                            splits=w.splits_g, ws=w.ws)
-            # Q = dy^T z ;  dz (softmax branches) = dy W'
-            self._gemm(L.ptr(w.dyp), zzp, L.ptr(w.Qp), G, P, B, lda=G, ldb=KMIX, ldc=P, ta=1, splits=w.splits_b, ws=w.ws)
-            self._gemm(L.ptr(w.dys), zzp + 4 * P, L.ptr(w.Qs), G, S, B, lda=G, ldb=KMIX, ldc=S, ta=1, splits=w.splits_b, ws=w.ws)
-            self._gemm(L.ptr(w.dyp), L.ptr(w.wfold), L.ptr(w.dzraw), B, P, G, lda=G, ldb=KZ, ldc=KZ, splits=w.splits_g, ws=w.ws)
-            self._gemm(L.ptr(w.dys), w.wfold.data_ptr() + 4 * P, w.dzraw.data_ptr() + 4 * P, B, S, G, lda=G, ldb=KZ, ldc=KZ,
-                       splits=w.splits_g, ws=w.ws)
-            gb = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), w.Qp, w.Qs, w.genec, w.colsum, w.zmean, w.zcov,
+                Qp, Qs, ldq, dzraw = L.ptr(w.Qp), L.ptr(w.Qs), 0, L.ptr(w.dzraw)
+            gb = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), Qp, Qs, w.genec, w.colsum, w.zmean, w.zcov,
                               self.Gd(g, "Wp"), self.Gd(g, "Ws"), self.Gd(g, "gp"), self.Gd(g, "bp"), self.Gd(g, "gs"),
                               self.Gd(g, "bs"), self.Gd(g, "px_r"), self.Gd(g, "bm"), w.vpart, w.mpart])
-            L.check(lib.spv_dec_gene_bwd(gb, B, G, P, S, st), "spv_dec_gene_bwd")
-            L.check(lib.spv_dec_dzz_combine(w.damix.data_ptr() + 4 * HD, KMIX, L.ptr(w.dzraw), L.ptr(w.vpart), L.ptr(w.mpart),
+            L.check(lib.spv_dec_gene_bwd(gb, ldq, B, G, P, S, st), "spv_dec_gene_bwd")
+            L.check(lib.spv_dec_dzz_combine(w.damix.data_ptr() + 4 * HD, KMIX, dzraw, L.ptr(w.vpart), L.ptr(w.mpart),
                                             w.nTG, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S, st), "spv_dec_dzz_combine")
             # hidden layer of the mixing net: ReLU + BatchNorm backward, then its Linear
             L.check(lib.spv_bn_bwd(L.ptr(w.damix), KMIX, L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, L.ptr(w.dah), HD, B, HD,
