@@ -53,10 +53,15 @@ def _random_sampler_perm(n: int) -> torch.Tensor:
 
 def epoch_batches(train_idx: Sequence[np.ndarray], batch_size: int, shuffle=True, drop_last=True) -> List[List[np.ndarray]]:
     """one epoch of ConcatDataLoader: list over steps of [rows_group0, rows_group1] (global row ids).
-    The global torch CPU RNG is consumed exactly as the reference's samplers consume it: the largest loader's sampler is
-    started first?  No: zip() calls iter() on each loader in list order, but a BatchSampler only draws its permutation
-    when the first batch is requested, which zip does in list order at step 0."""
+    The global torch CPU RNG is consumed exactly as the reference's loader stack consumes it
+    (dataloaders/_concat_dataloader.py:108-110 on top of torch.utils.data): creating each DataLoader iterator draws one
+    int64 (its base seed) — the cycled loaders when `cycle(dl)` is built, the largest when zip() starts — and only then, at
+    the first batch, each RandomSampler draws its own seed in list order and builds torch.randperm from it.
+    tests/test_index_semantics.py checks this against the real torch DataLoader / BatchSampler / RandomSampler classes."""
     per_group = []
+    if shuffle is not None:  # one base-seed draw per DataLoader iterator (shuffled or not)
+        for _ in train_idx:
+            torch.empty((), dtype=torch.int64).random_()
     for idx in train_idx:
         n = len(idx)
         order = _random_sampler_perm(n).numpy() if shuffle else np.arange(n)
