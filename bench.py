@@ -166,12 +166,18 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("SPV_ALL_ON_GPU0"):
+        local_rank = 0
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        backend = os.environ.get("SPV_DIST_BACKEND", "nccl")  # "gloo": debugging the multi-rank flow on a single GPU
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            dist.init_process_group(backend)
     workload = args.workload
     mode, n_cells, genes, H, B, n_labels = WORKLOADS[workload]
     if world > 1 and workload == "C5":

@@ -258,8 +258,8 @@ class spVIPES:
         its = [iter(c) if g == largest else cycle(c) for g, c in enumerate(chunks)]
         res = {"shared": [[], []], "private": [[], []], "idx": [[], []]}
         for st in zip(*its):
-            if len(st[0]) != len(st[1]):
-                m = min(len(st[0]), len(st[1]))  # ragged tail: the PoE pairs rows, keep the common length
+            if len(st[0]) != len(st[1]) and eng.mode != "label":
+                m = min(len(st[0]), len(st[1]))  # the OT modes need equally sized minibatches (reference :521-523)
                 st = [s[:m] for s in st]
             rows = [torch.from_numpy(self._local_rows(g, st[g]).astype(np.int32)).to(eng.device) for g in (0, 1)]
             batches = []

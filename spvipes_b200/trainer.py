@@ -117,9 +117,21 @@ class TrainLoop:
                 self.step(batches, noise)
         cur.wait_stream(side)
         torch.cuda.synchronize(e.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            self.step(batches, noise)
+        if self.grad_sync is None:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.step(batches, noise)
+        else:
+            # data parallel: forward + backward and the optimiser are two graphs, the gradient all-reduce is issued eagerly
+            # on the stream between the two replays (collectives are kept out of graph capture)
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                e.forward(batches, training=True, noise=noise)
+                e.backward()
+            scale = 1.0 / self.grad_sync.world
+            with torch.cuda.graph(g2):
+                e.adam_step(lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=scale)
+            graph = _SyncedGraphs(g1, g2, self.grad_sync, e)
         torch.cuda.synchronize(e.device)
         e.params.flat.copy_(keep[0]); e.buffers.flat.copy_(keep[1]); e.step_dev.copy_(keep[2])
         if keep[3] is None:
@@ -127,6 +139,18 @@ class TrainLoop:
         else:
             e.adam_m.copy_(keep[3]); e.adam_v.copy_(keep[4])
         return graph
+
+
+class _SyncedGraphs:
+    """replay(): forward+backward graph -> eager gradient all-reduce -> Adam graph"""
+
+    def __init__(self, g_fb, g_opt, grad_sync, engine):
+        self.g_fb, self.g_opt, self.grad_sync, self.engine = g_fb, g_opt, grad_sync, engine
+
+    def replay(self):
+        self.g_fb.replay()
+        self.grad_sync(self.engine)
+        self.g_opt.replay()
 
 
 def init_params(engine: StepEngine, seed: int = 0):
