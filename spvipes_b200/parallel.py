@@ -33,8 +33,10 @@ class GradSync:
     """sum the flat gradient buffer over ranks in `n_buckets` chunks; returns the 1/world factor that the fused Adam kernel
     folds into its gradient read (no separate scaling pass)."""
 
-    def __init__(self, engine, dist, n_buckets: int = 4):
+    def __init__(self, engine, dist, n_buckets: int = 0):
         self.dist = dist
+        if n_buckets <= 0:  # one bucket up to 64 MiB of gradients (latency bound on NVSwitch), then 32 MiB buckets
+            n_buckets = max(1, (engine.grads.numel() * 4 + (64 << 20) - 1) // (64 << 20) * 2 - 1)
         self.world = dist.get_world_size()
         self.buckets = [engine.grads[a:b] for a, b in reversed(bucket_bounds(engine.grads.numel(), n_buckets))]
 
