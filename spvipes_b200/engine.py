@@ -9,6 +9,7 @@ torch is used for device memory and streams only; every arithmetic step is a lau
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from collections import OrderedDict
 from dataclasses import dataclass, field
@@ -187,6 +188,7 @@ class _GroupWS:
         self.splits_b = max(1, min(8, B // 64))         # reductions over the minibatch with a small output
         big = max(2 * H, KMIX)
         self.ws = f(max(32 * B * big, self.splits_b * G * KZ, 2 * self.splits_b * big * big, 1))
+        self.ws2 = f(max(2 * self.splits_b * big * big, 1))  # split-K scratch of the auxiliary (weight-gradient) stream
         r8 = lambda x: (x + 7) // 8 * 8
         self.Gp, self.KMp = r8(G), r8(KMIX)
         if bf16:
@@ -256,6 +258,8 @@ class StepEngine:
         self._ws: Dict[Tuple[int, int, bool], List[_GroupWS]] = {}
         self._ctx = None
         self._side = None
+        self._aux = None
+        self._pending = {}
         self.parallel_groups = True
         self.nb_events = None  # bench hook: iterator of (start, end) CUDA events bracketing the NB-loglik sweep
 
@@ -306,6 +310,33 @@ class StepEngine:
         for ev in joins:
             cur.wait_event(ev)
 
+    @contextlib.contextmanager
+    def _branch(self, g, tag):
+        """run the enclosed launches on group g's auxiliary stream, forked from the current stream; `_join(g, tag)` makes
+        the current stream wait for them.  Used for work that is off the critical path of the step (weight-gradient GEMMs,
+        bias column sums, operand staging that does not depend on the minibatch)."""
+        if not self.parallel_groups or self.device.type != "cuda":
+            yield
+            return
+        if self._aux is None:
+            self._aux = [torch.cuda.Stream(device=self.device) for _ in (0, 1)]
+        cur = torch.cuda.current_stream(self.device)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        aux = self._aux[g]
+        aux.wait_event(fork)
+        with torch.cuda.stream(aux):
+            yield
+        done = torch.cuda.Event()
+        done.record(aux)
+        self._pending.setdefault((g, tag), []).append(done)
+
+    def _join(self, g, tag=None):
+        cur = torch.cuda.current_stream(self.device)
+        for key in [k for k in self._pending if k[0] == g and (tag is None or k[1] == tag)]:
+            for ev in self._pending.pop(key):
+                cur.wait_event(ev)
+
     def workspace(self, B0, B1, with_grad=True):
         key = (B0, B1, with_grad)
         if key not in self._ws:
@@ -340,10 +371,19 @@ class StepEngine:
             ldx = bt.X.stride(0)
             xptr = bt.X.data_ptr() + bt.col0 * esz
             srcs.append((src, xptr, ldx))
-            L.check(lib.spv_library_size(src, xptr, ldx, L.ptr(bt.rows), B, G, L.ptr(w.lib), st), "spv_library_size")
+            if self.bf16:  # bf16 copies of the two big weights do not depend on the minibatch: off the critical path
+                with self._branch(g, "w1"):
+                    L.check(lib.spv_to_bf16(L.ptr(self.P(g, "W1")), G, L.ptr(w.W1b), w.Gp, 2 * H, G, self._stream()), "spv_to_bf16")
+                if decode:
+                    with self._branch(g, "wm"):
+                        L.check(lib.spv_to_bf16(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX, self._stream()),
+                                "spv_to_bf16")
+            with self._branch(g, "lib"):
+                L.check(lib.spv_library_size(src, xptr, ldx, L.ptr(bt.rows), B, G, L.ptr(w.lib), self._stream()),
+                        "spv_library_size")
             if self.bf16:
                 L.check(lib.spv_counts_to_bf16(src, xptr, ldx, L.ptr(bt.rows), L.ptr(w.Tb), w.Gp, B, G, st), "spv_counts_to_bf16")
-                L.check(lib.spv_to_bf16(L.ptr(self.P(g, "W1")), G, L.ptr(w.W1b), w.Gp, 2 * H, G, st), "spv_to_bf16")
+                self._join(g, "w1")
                 self._tc_gemm(L.ptr(w.Tb), L.ptr(w.W1b), L.ptr(w.h1), B, 2 * H, G, lda=w.Gp, ldb=w.Gp, ldc=2 * H,
                               bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.tc_splits_fc1, ws=w.ws)
             else:
@@ -370,6 +410,8 @@ class StepEngine:
         ctx = {"batches": batches, "ws": ws, "Bs": Bs, "noise": noise, "srcs": srcs, "aux": aux, "training": training}
         self._ctx = ctx
         if not decode:
+            for g in (0, 1):
+                self._join(g)
             return ws
         # ---------------- decoders + NB likelihood (reference nn/networks.py:314-325, module :751-759, :817-824)
         for g in self._fork_groups():
@@ -391,11 +433,12 @@ class StepEngine:
                                    DEC_BN_EPS, DEC_BN_MOM, L.ptr(self.Bf(g, "rm_h")), L.ptr(self.Bf(g, "rv_h")),
                                    L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), tr, 1, st), "spv_bn_fwd")
             dptrs = self._dec_ptrs(g, w, xptr, bt.rows, with_grad)
+            self._join(g, "lib")
             L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 1, st), "spv_dec_nb_fwd")
             evs = next(self.nb_events) if self.nb_events is not None else None
             if self.bf16:  # mixture logits on the tensor cores, consumed by the NB sweep
                 L.check(lib.spv_to_bf16(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX, st), "spv_to_bf16")
-                L.check(lib.spv_to_bf16(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX, st), "spv_to_bf16")
+                self._join(g, "wm")
             if evs is not None:
                 evs[0].record()
             if self.bf16:
@@ -516,9 +559,9 @@ class StepEngine:
                                               L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.D3), B, G, HD, P, S,
                                               -float(grad_scale) / B, L.ptr(w.colsum), st), "spv_dec_nb_bwd_tc")
                 Gp3 = 3 * w.Gp
-                # d Wm = dpi^T [hm | zz]
-                self._tc_gemm(L.ptr(w.D3), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=Gp3, ldb=w.KMp, ldc=KMIX,
-                              a_mn=1, b_mn=1)
+                with self._branch(g, "wgrad"):  # d Wm = dpi^T [hm | zz]
+                    self._tc_gemm(L.ptr(w.D3), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=Gp3, ldb=w.KMp, ldc=KMIX,
+                                  a_mn=1, b_mn=1)
                 # [Qp | .] = dyp^T zz, [. | Qs] = dys^T zz in one GEMM over the stacked rows (rows g and Gp + g)
                 self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, w.amixb.data_ptr() + 2 * HD, L.ptr(w.CQ), 2 * w.Gp, KZ, B, lda=Gp3,
                               ldb=w.KMp, ldc=KZ, a_mn=1, b_mn=1)
@@ -557,9 +600,10 @@ class StepEngine:
             L.check(lib.spv_bn_bwd(L.ptr(w.damix), KMIX, L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, L.ptr(w.dah), HD, B, HD,
                                    L.ptr(self.P(g, "gh")), L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), L.ptr(self.Gd(g, "gh")),
                                    L.ptr(self.Gd(g, "bth")), st), "spv_bn_bwd")
-            self._gemm(L.ptr(w.dah), zzp, L.ptr(self.Gd(g, "Wh")), HD, KZ, B, lda=HD, ldb=KMIX, ldc=KZ, ta=1, splits=w.splits_b,
-                       ws=w.ws)
-            L.check(lib.spv_colsum(L.ptr(w.dah), HD, B, HD, L.ptr(self.Gd(g, "bh")), st), "spv_colsum")
+            with self._branch(g, "wgrad"):
+                self._gemm(L.ptr(w.dah), zzp, L.ptr(self.Gd(g, "Wh")), HD, KZ, B, lda=HD, ldb=KMIX, ldc=KZ, ta=1,
+                           splits=w.splits_b, ws=w.ws2)
+                L.check(lib.spv_colsum(L.ptr(w.dah), HD, B, HD, L.ptr(self.Gd(g, "bh")), self._stream()), "spv_colsum")
             self._gemm(L.ptr(w.dah), L.ptr(self.P(g, "Wh")), L.ptr(w.dzz), B, KZ, HD, lda=HD, ldb=KZ, ldc=KZ, acc=1)
         # ---------------- PoE
         own = self._poe_sides(ws)
@@ -591,21 +635,23 @@ class StepEngine:
             L.check(lib.spv_bn_bwd(L.ptr(w.dstats), NST, L.ptr(w.r), NST, None, 0, L.ptr(w.dr), NST, B, NST,
                                    L.ptr(self.P(g, "ghd")), L.ptr(w.bn_hd_mean), L.ptr(w.bn_hd_istd), L.ptr(self.Gd(g, "ghd")),
                                    L.ptr(self.Gd(g, "bthd")), st), "spv_bn_bwd")
-            L.check(lib.spv_colsum(L.ptr(w.dr), NST, B, NST, L.ptr(self.Gd(g, "bhd")), st), "spv_colsum")
             drs = w.dr.data_ptr() + 4 * 2 * P
-            self._gemm(L.ptr(w.dr), L.ptr(w.h2), L.ptr(self.Gd(g, "Whp")), 2 * P, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1,
-                       splits=w.splits_b, ws=w.ws)
-            self._gemm(drs, w.h2.data_ptr() + 4 * H, L.ptr(self.Gd(g, "Whs")), 2 * S, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1,
-                       splits=w.splits_b, ws=w.ws)
+            with self._branch(g, "wgrad"):
+                L.check(lib.spv_colsum(L.ptr(w.dr), NST, B, NST, L.ptr(self.Gd(g, "bhd")), self._stream()), "spv_colsum")
+                self._gemm(L.ptr(w.dr), L.ptr(w.h2), L.ptr(self.Gd(g, "Whp")), 2 * P, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1,
+                           splits=w.splits_b, ws=w.ws2)
+                self._gemm(drs, w.h2.data_ptr() + 4 * H, L.ptr(self.Gd(g, "Whs")), 2 * S, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1,
+                           splits=w.splits_b, ws=w.ws2)
             self._gemm(L.ptr(w.dr), L.ptr(self.P(g, "Whp")), L.ptr(w.dh2), B, H, 2 * P, lda=NST, ldb=H, ldc=2 * H)
             self._gemm(drs, L.ptr(self.P(g, "Whs")), w.dh2.data_ptr() + 4 * H, B, H, 2 * S, lda=NST, ldb=H, ldc=2 * H)
             mask = noise.drop[g] if noise.drop is not None else None
             scale = 1.0 / (1.0 - self.dropout_rate) if self.dropout_rate > 0 else 1.0
             L.check(lib.spv_relu_bwd(L.ptr(w.dh2), 2 * H, L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, scale, st),
                     "spv_relu_bwd")
-            self._gemm(L.ptr(w.dh2), L.ptr(w.h1), L.ptr(self.Gd(g, "W2")), H, H, B, lda=2 * H, ldb=2 * H, ldc=H, ta=1, batch=2,
-                       sA=H, sB=H, sC=H * H, splits=w.splits_b, ws=w.ws)
-            L.check(lib.spv_colsum(L.ptr(w.dh2), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b2")), st), "spv_colsum")
+            with self._branch(g, "wgrad"):
+                self._gemm(L.ptr(w.dh2), L.ptr(w.h1), L.ptr(self.Gd(g, "W2")), H, H, B, lda=2 * H, ldb=2 * H, ldc=H, ta=1,
+                           batch=2, sA=H, sB=H, sC=H * H, splits=w.splits_b, ws=w.ws2)
+                L.check(lib.spv_colsum(L.ptr(w.dh2), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b2")), self._stream()), "spv_colsum")
             self._gemm(L.ptr(w.dh2), L.ptr(self.P(g, "W2")), L.ptr(w.dh1), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, batch=2, sA=H,
                        sB=H * H, sC=H)
             L.check(lib.spv_relu_bwd(L.ptr(w.dh1), 2 * H, L.ptr(w.h1), 2 * H, B, 2 * H, None, 0, 1.0, st), "spv_relu_bwd")
@@ -616,7 +662,9 @@ class StepEngine:
             else:
                 self._gemm(L.ptr(w.dh1), xptr, L.ptr(self.Gd(g, "W1")), 2 * H, G, B, lda=2 * H, ldb=ldx, ldc=G, ta=1, srcB=src,
                            rowsB=bt.rows)
-            L.check(lib.spv_colsum(L.ptr(w.dh1), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b1")), st), "spv_colsum")
+            with self._branch(g, "wgrad"):
+                L.check(lib.spv_colsum(L.ptr(w.dh1), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b1")), self._stream()), "spv_colsum")
+            self._join(g)
 
     # -------------------------------------------------------------------------------- optimiser
     def adam_step(self, lr=1e-3, betas=(0.9, 0.999), eps=0.01, weight_decay=1e-6, grad_scale=1.0):
