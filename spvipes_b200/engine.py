@@ -460,7 +460,7 @@ class StepEngine:
         if Bs[0] != Bs[1]:
             raise ValueError("the loss needs equally sized minibatches in both groups (reference :886-893)")
         L.check(lib.spv_loss(L.ptr(ws[0].rec), L.ptr(ws[1].rec), L.ptr(ws[0].klp), L.ptr(ws[0].klq), L.ptr(ws[1].klp),
-                             L.ptr(ws[1].klq), Bs[0], L.ptr(self.kl_weight), L.ptr(self.loss_out), st), "spv_loss")
+                             L.ptr(ws[1].klq), Bs[0], L.ptr(self.kl_weight), L.ptr(self.loss_out), self._stream()), "spv_loss")
         return ws
 
     def _dec_ptrs(self, g, w, xptr, rows, with_grad):
@@ -620,7 +620,8 @@ class StepEngine:
             lds = L.ll_array([o[2], t[2], NST, KZ, NST, ld_out])
             arrs.append((ptrs, lds))
         L.check(lib.spv_poe_bwd(self.mode_id, S, P, Bs[0], Bs[1], arrs[0][0], arrs[0][1], arrs[1][0], arrs[1][1], self.seed,
-                                L.ptr(self.step_dev), L.ptr(self.kl_weight), float(grad_scale) / Bs[0], st), "spv_poe_bwd")
+                                L.ptr(self.step_dev), L.ptr(self.kl_weight), float(grad_scale) / Bs[0], self._stream()),
+                "spv_poe_bwd")
         if self.mode == "cluster":
             # d stats_0[:, shared] += P1^T d expertA ;  d stats_1[:, shared] += P2^T d expertB   (quirk Q5)
             self._gemm(L.ptr(aux["P1"]), L.ptr(ws[0].dexpert), ws[0].dstats.data_ptr() + 4 * 2 * P, Bs[1], 2 * S, Bs[0],
