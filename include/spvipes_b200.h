@@ -140,11 +140,12 @@ int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const voi
 /* ptrs (18): Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm,
  * vpart [ceil(G/64), P+S], mpart [ceil(G/64), (P+S)^2]   (backward of nn/networks.py:314-320 through the folded BatchNorm) */
 int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, int G, int P, int S, void* stream);
-/* d zz = d(mixture) + d(softmax branches) - BatchNorm coupling terms, the latter summed from the `nparts` per-CTA
+/* d zz = d(mixture) + d(softmax branches) + dah Wh (hidden layer of the mixing net, optional: dah [B, HDh], Wh [HDh, P+S])
+ * - BatchNorm coupling terms, the latter summed from the `nparts` per-CTA
  * partials (vpart [nparts, P+S], mpart [nparts, (P+S)^2]) that spv_dec_gene_bwd writes (its last two ptrs) */
 int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* vpart, const float* mpart,
-                        int nparts, const float* zz, long long ld_zz, const float* zmean, float* dzz, int B, int P, int S,
-                        void* stream);
+                        int nparts, const float* zz, long long ld_zz, const float* zmean, const float* dah, const float* Wh,
+                        int HDh, float* dzz, int B, int P, int S, void* stream);
 
 /* Adam with the scvi TrainingPlan defaults restated by the caller (training_mixin.py:93-111); *step is a device counter */
 int spv_adam_tick(int* step, void* stream);

@@ -293,6 +293,7 @@ extern "C" int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, i
 __global__ void __launch_bounds__(1024) dzz_combine_kernel(const float* __restrict__ dmix, long ld_dmix, const float* __restrict__ dzraw,
                                                            const float* __restrict__ vpart, const float* __restrict__ mpart, int nparts,
                                                            const float* __restrict__ zz, long ld_zz, const float* __restrict__ zmean,
+                                                           const float* __restrict__ dah, const float* __restrict__ Wh, int HDh,
                                                            float* __restrict__ dzz, int B, int P, int S) {
     extern __shared__ float sh[];
     const int KZ = P + S;
@@ -300,6 +301,7 @@ __global__ void __launch_bounds__(1024) dzz_combine_kernel(const float* __restri
     float* sM = sh + KZ;       // [KZ * KZ] (block entries only)
     for (int c = threadIdx.x; c < KZ; c += blockDim.x) {
         float s = 0.0f;
+#pragma unroll 8
         for (int t = 0; t < nparts; ++t) s += vpart[(long)t * KZ + c];
         sv[c] = s;
     }
@@ -309,6 +311,7 @@ __global__ void __launch_bounds__(1024) dzz_combine_kernel(const float* __restri
         if (idx < nPP) { k = idx / P; l = idx - k * P; }
         else { int j = idx - nPP; k = P + j / S; l = P + j % S; }
         float s = 0.0f;
+#pragma unroll 8
         for (int t = 0; t < nparts; ++t) s += mpart[(long)t * KZ * KZ + k * KZ + l];
         sM[k * KZ + l] = s;
     }
@@ -320,19 +323,23 @@ __global__ void __launch_bounds__(1024) dzz_combine_kernel(const float* __restri
     int lo = c < P ? 0 : P, hi = c < P ? P : KZ;
     float corr = 0.0f;
     for (int l = lo; l < hi; ++l) corr = fmaf(sM[c * KZ + l], zz[b * ld_zz + l] - zmean[l], corr);
-    dzz[b * KZ + c] = dmix[b * ld_dmix + c] + (dzraw ? dzraw[b * KZ + c] : 0.0f) - sv[c] - corr;
+    float hid = 0.0f;  // gradient through the hidden layer of the mixing net: dah Wh  (nn/networks.py:322-323)
+    if (dah)
+#pragma unroll 8
+        for (int k = 0; k < HDh; ++k) hid = fmaf(dah[b * HDh + k], __ldg(Wh + (long)k * KZ + c), hid);
+    dzz[b * KZ + c] = dmix[b * ld_dmix + c] + (dzraw ? dzraw[b * KZ + c] : 0.0f) - sv[c] - corr + hid;
 }
 
 extern "C" int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* vpart, const float* mpart,
-                                   int nparts, const float* zz, long long ld_zz, const float* zmean, float* dzz, int B, int P,
-                                   int S, void* stream) {
+                                   int nparts, const float* zz, long long ld_zz, const float* zmean, const float* dah,
+                                   const float* Wh, int HDh, float* dzz, int B, int P, int S, void* stream) {
     if (!dmix || !vpart || !mpart || !zz || !zmean || !dzz || B <= 0 || P <= 0 || S <= 0 || nparts <= 0) return SPV_ERR_ARG;
     const int KZ = P + S;
     long total = (long)B * KZ;
     size_t smem = (size_t)(KZ + KZ * KZ) * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(dzz_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dzz_combine_kernel<<<(int)((total + 1023) / 1024), 1024, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dmix, ld_dmix, dzraw, vpart, mpart, nparts, zz, ld_zz, zmean, dzz, B, P, S);
+        dmix, ld_dmix, dzraw, vpart, mpart, nparts, zz, ld_zz, zmean, dah, Wh, HDh, dzz, B, P, S);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

@@ -88,13 +88,14 @@ extern "C" int spv_relu_bwd(float* dy, long long lddy, const float* y, long long
 }
 
 // ---------------------------------------------------------------------------------------
-// BatchNorm1d over the minibatch.  32 columns per CTA, 8 row lanes.
+// BatchNorm1d over the minibatch.  8 columns (one 32-byte sector per row) x 64 row lanes per CTA: the column count is
+// small (70 .. 256), so narrow CTAs are what spreads the rows of one column block over enough SMs.
 // ---------------------------------------------------------------------------------------
-#define BN_TX 32
-#define BN_TY 8
+#define BN_TX 8    // columns per CTA: one 32-byte sector per row
+#define BN_TY 64   // row lanes
 
 __device__ __forceinline__ float col_reduce(float v, float (*red)[BN_TX]) {
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tx = threadIdx.x % BN_TX, ty = threadIdx.x / BN_TX;
     __syncthreads();
     red[ty][tx] = v;
     __syncthreads();
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(BN_TX* BN_TY) bn_fwd_kernel(const float* __res
                                                                float* __restrict__ save_mean, float* __restrict__ save_invstd,
                                                                int training, int relu) {
     __shared__ float red[BN_TY][BN_TX];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tx = threadIdx.x % BN_TX, ty = threadIdx.x / BN_TX;
     const int c = blockIdx.x * BN_TX + tx;
     const bool ok = c < C;
     float mean, var;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(BN_TX* BN_TY) bn_bwd_kernel(const float* __res
                                                                const float* __restrict__ save_invstd, float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta) {
     __shared__ float red[BN_TY][BN_TX];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tx = threadIdx.x % BN_TX, ty = threadIdx.x / BN_TX;
     const int c = blockIdx.x * BN_TX + tx;
     const bool ok = c < C;
     float mean = ok ? save_mean[c] : 0.0f, invstd = ok ? save_invstd[c] : 0.0f;
@@ -204,7 +205,7 @@ extern "C" int spv_bn_bwd(const float* dy, long long lddy, const float* x, long 
 
 __global__ void __launch_bounds__(BN_TX* BN_TY) colsum_kernel(const float* __restrict__ x, long ldx, int B, int C, float* __restrict__ out) {
     __shared__ float red[BN_TY][BN_TX];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tx = threadIdx.x % BN_TX, ty = threadIdx.x / BN_TX;
     const int c = blockIdx.x * BN_TX + tx;
     float s = 0.0f;
     if (c < C) for (int b = ty; b < B; b += BN_TY) s += x[(long)b * ldx + c];

@@ -134,9 +134,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             out = p.C;
             ld = p.ldc;
         }
-        const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        // All TMA loads have landed and all MMAs have read them once tmem_full fires, so the operand stages are free:
+        // each warp transposes its 32 x 32 chunk through a private pitch-33 staging block so that global stores are
+        // one full 128-byte row segment per instruction whatever ldc is (ldc = 291 for the mixing-net gradients).
+        float* stage = reinterpret_cast<float*>(tiles) + (warp - 2) * (32 * 33);
+        const bool acc = p.accumulate && p.splits == 1;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
+            const int nb = n0 + c0;
+            if (nb >= p.N || m0 + lane_base >= p.M) break;  // warp-uniform
             uint32_t r[32];
             if (num_kb > 0) {
                 tc::tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, r);
@@ -145,36 +151,24 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
             }
-            if (m >= p.M) continue;
-            const int nb = n0 + c0;
-            if (nb >= p.N) continue;
-            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (p.splits == 1) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (p.bias && nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
-                    if (p.relu) v[j] = fmaxf(v[j], 0.0f);
+            for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
+            __syncwarp();
+            const int n = nb + lane;
+            const bool n_ok = n < p.N;
+            const float bv = (p.splits == 1 && p.bias && n_ok) ? __ldg(p.bias + n) : 0.0f;
+            const int rows = min(32, p.M - (m0 + lane_base));
+            float* dst = out + (size_t)(m0 + lane_base) * ld + n;
+            if (n_ok) {
+#pragma unroll 8
+                for (int rr = 0; rr < rows; ++rr) {
+                    float v = stage[rr * 33 + lane] + bv;
+                    if (p.relu && p.splits == 1) v = fmaxf(v, 0.0f);
+                    if (acc) v += dst[(size_t)rr * ld];
+                    dst[(size_t)rr * ld] = v;
                 }
             }
-            float* dst = out + (size_t)m * ld + nb;
-            const bool acc = p.accumulate && p.splits == 1;
-            if (vec && nb + 32 <= p.N) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    if (acc) {
-                        float4 c = *reinterpret_cast<const float4*>(dst + j);
-                        o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
-                    }
-                    *reinterpret_cast<float4*>(dst + j) = o;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (nb + j < p.N) dst[j] = acc ? dst[j] + v[j] : v[j];
-            }
+            __syncwarp();
         }
     }
     tc::fence_before_sync();

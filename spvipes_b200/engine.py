@@ -590,13 +590,8 @@ class StepEngine:
                 self._gemm(L.ptr(w.dys), w.wfold.data_ptr() + 4 * P, w.dzraw.data_ptr() + 4 * P, B, S, G, lda=G, ldb=KZ, ldc=KZ,
                            splits=w.splits_g, ws=w.ws)
                 Qp, Qs, ldq, dzraw = L.ptr(w.Qp), L.ptr(w.Qs), 0, L.ptr(w.dzraw)
-            gb = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), Qp, Qs, w.genec, w.colsum, w.zmean, w.zcov,
-                              self.Gd(g, "Wp"), self.Gd(g, "Ws"), self.Gd(g, "gp"), self.Gd(g, "bp"), self.Gd(g, "gs"),
-                              self.Gd(g, "bs"), self.Gd(g, "px_r"), self.Gd(g, "bm"), w.vpart, w.mpart])
-            L.check(lib.spv_dec_gene_bwd(gb, ldq, B, G, P, S, st), "spv_dec_gene_bwd")
-            L.check(lib.spv_dec_dzz_combine(w.damix.data_ptr() + 4 * HD, KMIX, dzraw, L.ptr(w.vpart), L.ptr(w.mpart),
-                                            w.nTG, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S, st), "spv_dec_dzz_combine")
-            # hidden layer of the mixing net: ReLU + BatchNorm backward, then its Linear
+            # hidden layer of the mixing net: ReLU + BatchNorm backward (needs only d [hm | zz]), its Linear's weight
+            # gradient goes to the auxiliary stream, its input gradient is folded into the d zz combine below
             L.check(lib.spv_bn_bwd(L.ptr(w.damix), KMIX, L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, L.ptr(w.dah), HD, B, HD,
                                    L.ptr(self.P(g, "gh")), L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), L.ptr(self.Gd(g, "gh")),
                                    L.ptr(self.Gd(g, "bth")), st), "spv_bn_bwd")
@@ -604,7 +599,13 @@ class StepEngine:
                 self._gemm(L.ptr(w.dah), zzp, L.ptr(self.Gd(g, "Wh")), HD, KZ, B, lda=HD, ldb=KMIX, ldc=KZ, ta=1,
                            splits=w.splits_b, ws=w.ws2)
                 L.check(lib.spv_colsum(L.ptr(w.dah), HD, B, HD, L.ptr(self.Gd(g, "bh")), self._stream()), "spv_colsum")
-            self._gemm(L.ptr(w.dah), L.ptr(self.P(g, "Wh")), L.ptr(w.dzz), B, KZ, HD, lda=HD, ldb=KZ, ldc=KZ, acc=1)
+            gb = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), Qp, Qs, w.genec, w.colsum, w.zmean, w.zcov,
+                              self.Gd(g, "Wp"), self.Gd(g, "Ws"), self.Gd(g, "gp"), self.Gd(g, "bp"), self.Gd(g, "gs"),
+                              self.Gd(g, "bs"), self.Gd(g, "px_r"), self.Gd(g, "bm"), w.vpart, w.mpart])
+            L.check(lib.spv_dec_gene_bwd(gb, ldq, B, G, P, S, st), "spv_dec_gene_bwd")
+            L.check(lib.spv_dec_dzz_combine(w.damix.data_ptr() + 4 * HD, KMIX, dzraw, L.ptr(w.vpart), L.ptr(w.mpart),
+                                            w.nTG, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dah), L.ptr(self.P(g, "Wh")), HD,
+                                            L.ptr(w.dzz), B, P, S, st), "spv_dec_dzz_combine")
         # ---------------- PoE
         own = self._poe_sides(ws)
         arrs = []
