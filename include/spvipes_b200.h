@@ -55,9 +55,10 @@ int spv_tc_gemm(int a_mn, int b_mn, const void* A, long long lda, const void* B,
                 int N, int K, const float* bias, int relu, int accumulate, int splits, float* ws, void* stream);
 /* bf16 staging of GEMM operands: dst[r, :C] = bf16(src[r, :C]), zero padded up to ld_dst */
 int spv_to_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, int R, int C, void* stream);
-/* T[b, :G] = bf16(log1p(X[rows[b], :G]))   module/spVIPESmodule.py:428-433 */
+/* T[b, :G] = bf16(log1p(X[rows[b], :G])), zero padded to ld_dst (a multiple of 8)   module/spVIPESmodule.py:428-433;
+ * lib (optional, [B]): library size log(sum_g log1p(x[b,g])) from the same pass   module/spVIPESmodule.py:433-435 */
 int spv_counts_to_bf16(int src, const void* X, long long ldx, const int* rows, void* dst, long long ld_dst, int B, int G,
-                       void* stream);
+                       float* lib, void* stream);
 
 /* lib[b] = log(sum_g log1p(x[b,g]))   module/spVIPESmodule.py:433-435 */
 int spv_library_size(int src, const void* X, long long ldx, const int* rows, int B, int G, float* lib, void* stream);
@@ -140,17 +141,23 @@ int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const voi
 /* ptrs (18): Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm,
  * vpart [ceil(G/64), P+S], mpart [ceil(G/64), (P+S)^2]   (backward of nn/networks.py:314-320 through the folded BatchNorm) */
 int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, int G, int P, int S, void* stream);
-/* d zz = d(mixture) + d(softmax branches) + dah Wh (hidden layer of the mixing net, optional: dah [B, HDh], Wh [HDh, P+S])
- * - BatchNorm coupling terms, the latter summed from the `nparts` per-CTA
+/* d zz = dmix (latent columns of d [hm | zz]) + dzraw (optional further addends [B, P+S]: softmax-branch and hidden-layer
+ * input gradients when they are not in dmix) - BatchNorm coupling terms, the latter summed from the `nparts` per-CTA
  * partials (vpart [nparts, P+S], mpart [nparts, (P+S)^2]) that spv_dec_gene_bwd writes (its last two ptrs) */
 int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* vpart, const float* mpart,
-                        int nparts, const float* zz, long long ld_zz, const float* zmean, const float* dah, const float* Wh,
-                        int HDh, float* dzz, int B, int P, int S, void* stream);
+                        int nparts, const float* zz, long long ld_zz, const float* zmean, float* dzz, int B, int P, int S,
+                        void* stream);
 
-/* Adam with the scvi TrainingPlan defaults restated by the caller (training_mixin.py:93-111); *step is a device counter */
+/* Adam with the scvi TrainingPlan defaults restated by the caller (training_mixin.py:93-111); *step is a device counter of
+ * completed optimiser steps.  ticket == NULL: *step already holds this step's 1-based index (spv_adam_tick first);
+ * ticket != NULL (zeroed device int): the launch uses *step + 1 and its last CTA stores it back.
+ * nseg (<= 8) staging segments, host arrays: the parameter block [seg_begin, seg_begin + seg_rows * seg_cols) viewed as
+ * [seg_rows, seg_cols] is also written, updated, as bf16 into seg_dst (row pitch seg_ld): the tensor-core operand copies of
+ * the large weights, so that the next step does not start with conversion kernels.  p, g, m, v 16-byte aligned. */
 int spv_adam_tick(int* step, void* stream);
 int spv_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
-             float grad_scale, const int* step, void* stream);
+             float grad_scale, int* step, int* ticket, int nseg, const long long* seg_begin, const int* seg_rows,
+             const int* seg_cols, void* const* seg_dst, const long long* seg_ld, void* stream);
 
 #ifdef __cplusplus
 }

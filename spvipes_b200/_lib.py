@@ -26,7 +26,7 @@ _SIGS = {
     "spv_gemm": [i, i, i, i, p, ll, p, p, ll, p, p, ll, i, i, i, i, ll, ll, ll, p, ll, i, i, i, p, p],
     "spv_tc_gemm": [i, i, p, ll, p, ll, p, ll, i, i, i, p, i, i, i, p, p],
     "spv_to_bf16": [p, ll, p, ll, i, i, p],
-    "spv_counts_to_bf16": [i, p, ll, p, p, ll, i, i, p],
+    "spv_counts_to_bf16": [i, p, ll, p, p, ll, i, i, p, p],
     "spv_library_size": [i, p, ll, p, i, i, p, p],
     "spv_dropout": [p, ll, i, i, p, ll, f, u64, u32, p, p],
     "spv_relu_bwd": [p, ll, p, ll, i, i, p, ll, f, p],
@@ -47,9 +47,9 @@ _SIGS = {
     "spv_dec_nb_rowreduce": [p, i, i, p, p, p],
     "spv_dec_nb_bwd_tc": [i, p, ll, p, ll, p, ll, i, p, i, i, i, i, i, f, p, p],
     "spv_dec_gene_bwd": [p, ll, i, i, i, i, p],
-    "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, p, i, p, i, i, i, p],
+    "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, p],
     "spv_adam_tick": [p, p],
-    "spv_adam": [p, p, p, p, ll, f, f, f, f, f, f, p, p],
+    "spv_adam": [p, p, p, p, ll, f, f, f, f, f, f, p, p, i, p, p, p, p, p, p],
 }
 
 _lib = None
@@ -99,6 +99,13 @@ def ptr_array(items):
             arr[k] = it
         else:
             arr[k] = it.data_ptr()
+    return arr
+
+
+def int_array(items):
+    arr = (C.c_int * len(items))()
+    for k, it in enumerate(items):
+        arr[k] = int(it)
     return arr
 
 

@@ -288,58 +288,59 @@ extern "C" int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, i
 }
 
 // dzz[b, c] = dmix[b, c] + dzraw[b, c] - v1[c] - sum_l M[c, l] (zz[b, l] - zbar[l])   (l within c's branch block)
-//   dmix: the zz columns of d Amix (mixture GEMM);  dzraw = dy W' (both softmax branches);
-//   v1 / M: sums over the `nparts` per-CTA partials written by spv_dec_gene_bwd (fixed order: deterministic)
-__global__ void __launch_bounds__(1024) dzz_combine_kernel(const float* __restrict__ dmix, long ld_dmix, const float* __restrict__ dzraw,
-                                                           const float* __restrict__ vpart, const float* __restrict__ mpart, int nparts,
-                                                           const float* __restrict__ zz, long ld_zz, const float* __restrict__ zmean,
-                                                           const float* __restrict__ dah, const float* __restrict__ Wh, int HDh,
-                                                           float* __restrict__ dzz, int B, int P, int S) {
-    extern __shared__ float sh[];
+//   dmix: the zz columns of d Amix (mixture GEMM);  dzraw: further addends (dy W' of the softmax branches when they are
+//   not part of dmix already, and dah Wh of the mixing net's hidden layer), may be null;
+//   v1 / M: sums over the `nparts` per-CTA partials written by spv_dec_gene_bwd (fixed order: deterministic).
+// One latent column per CTA (blockIdx.x) and 256 rows (blockIdx.y): the CTA only needs row c of M, i.e. at most
+// max(P, S) + 1 sums over the partials, taken by 8 part lanes x 32 entries and combined in lane order.
+#define DZC_THREADS 256
+__global__ void __launch_bounds__(DZC_THREADS) dzz_combine_kernel(const float* __restrict__ dmix, long ld_dmix,
+                                                                  const float* __restrict__ dzraw, const float* __restrict__ vpart,
+                                                                  const float* __restrict__ mpart, int nparts,
+                                                                  const float* __restrict__ zz, long ld_zz,
+                                                                  const float* __restrict__ zmean, float* __restrict__ dzz, int B,
+                                                                  int P, int S) {
+    __shared__ float red[8][100];
+    __shared__ float srow[100];  // [0, n): M[c, lo + .],  [n]: v1[c]
     const int KZ = P + S;
-    float* sv = sh;            // [KZ]
-    float* sM = sh + KZ;       // [KZ * KZ] (block entries only)
-    for (int c = threadIdx.x; c < KZ; c += blockDim.x) {
+    const int c = blockIdx.x;
+    const int lo = c < P ? 0 : P, n = c < P ? P : S;
+    const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+    for (int e0 = 0; e0 <= n; e0 += 32) {
+        const int e = e0 + lane;
         float s = 0.0f;
-#pragma unroll 8
-        for (int t = 0; t < nparts; ++t) s += vpart[(long)t * KZ + c];
-        sv[c] = s;
-    }
-    const int nPP = P * P, nSS = S * S;
-    for (int idx = threadIdx.x; idx < nPP + nSS; idx += blockDim.x) {
-        int k, l;
-        if (idx < nPP) { k = idx / P; l = idx - k * P; }
-        else { int j = idx - nPP; k = P + j / S; l = P + j % S; }
-        float s = 0.0f;
-#pragma unroll 8
-        for (int t = 0; t < nparts; ++t) s += mpart[(long)t * KZ * KZ + k * KZ + l];
-        sM[k * KZ + l] = s;
+        if (e <= n) {
+            const float* src = e < n ? mpart + (long)c * KZ + lo + e : vpart + c;
+            const long pitch = e < n ? (long)KZ * KZ : KZ;
+#pragma unroll 4
+            for (int t = q; t < nparts; t += 8) s += src[(long)t * pitch];
+            red[q][e] = s;
+        }
     }
     __syncthreads();
-    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (i >= (long)B * KZ) return;
-    int c = (int)(i % KZ);
-    long b = i / KZ;
-    int lo = c < P ? 0 : P, hi = c < P ? P : KZ;
+    if (threadIdx.x <= n) {
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+        srow[threadIdx.x] = s;
+    }
+    __syncthreads();
+    const int b = blockIdx.y * DZC_THREADS + threadIdx.x;
+    if (b >= B) return;
+    const float* zrow = zz + (long)b * ld_zz + lo;
     float corr = 0.0f;
-    for (int l = lo; l < hi; ++l) corr = fmaf(sM[c * KZ + l], zz[b * ld_zz + l] - zmean[l], corr);
-    float hid = 0.0f;  // gradient through the hidden layer of the mixing net: dah Wh  (nn/networks.py:322-323)
-    if (dah)
-#pragma unroll 8
-        for (int k = 0; k < HDh; ++k) hid = fmaf(dah[b * HDh + k], __ldg(Wh + (long)k * KZ + c), hid);
-    dzz[b * KZ + c] = dmix[b * ld_dmix + c] + (dzraw ? dzraw[b * KZ + c] : 0.0f) - sv[c] - corr + hid;
+    for (int l = 0; l < n; ++l) corr = fmaf(srow[l], zrow[l] - zmean[lo + l], corr);
+    dzz[(long)b * KZ + c] = dmix[(long)b * ld_dmix + c] + (dzraw ? dzraw[(long)b * KZ + c] : 0.0f) - srow[n] - corr;
 }
 
 extern "C" int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* vpart, const float* mpart,
-                                   int nparts, const float* zz, long long ld_zz, const float* zmean, const float* dah,
-                                   const float* Wh, int HDh, float* dzz, int B, int P, int S, void* stream) {
-    if (!dmix || !vpart || !mpart || !zz || !zmean || !dzz || B <= 0 || P <= 0 || S <= 0 || nparts <= 0) return SPV_ERR_ARG;
-    const int KZ = P + S;
-    long total = (long)B * KZ;
-    size_t smem = (size_t)(KZ + KZ * KZ) * sizeof(float);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(dzz_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dzz_combine_kernel<<<(int)((total + 1023) / 1024), 1024, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dmix, ld_dmix, dzraw, vpart, mpart, nparts, zz, ld_zz, zmean, dah, Wh, HDh, dzz, B, P, S);
+                                   int nparts, const float* zz, long long ld_zz, const float* zmean, float* dzz, int B, int P,
+                                   int S, void* stream) {
+    if (!dmix || !vpart || !mpart || !zz || !zmean || !dzz || B <= 0 || P <= 0 || S <= 0 || nparts <= 0 || P > 96 || S > 96)
+        return SPV_ERR_ARG;
+    dim3 grid(P + S, (B + DZC_THREADS - 1) / DZC_THREADS);
+    dzz_combine_kernel<<<grid, DZC_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dmix, ld_dmix, dzraw, vpart, mpart, nparts,
+                                                                                         zz, ld_zz, zmean, dzz, B, P, S);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

@@ -2,6 +2,7 @@
 // library size, dropout, BatchNorm1d over the minibatch (forward + backward), column sums,
 // ReLU/dropout backward, Adam.  Reference: nn/networks.py:119-125 (Encoder.forward),
 // module/spVIPESmodule.py:435 (library), scvi FCLayers BatchNorm1d(momentum=0.01, eps=0.001).
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "../../include/spvipes_b200.h"
 
@@ -235,29 +236,118 @@ extern "C" int spv_adam_tick(int* step, void* stream) {
     return SPV_OK;
 }
 
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long n, float lr, float b1, float b2, float eps, float wd, float grad_scale,
-                            const int* __restrict__ step) {
-    const int t = *step;
+// Optional bf16 staging: up to ADAM_MAX_SEGS row-major [rows, cols] blocks of the flat parameter vector are also written,
+// freshly updated, as bf16 into the (padded, ld_dst >= cols) tensor-core operand buffers, so that the next step does not
+// start with conversion kernels.  The last CTA to finish advances *step (ticket counter, reset to zero).
+#define ADAM_MAX_SEGS 8
+struct AdamSegs {
+    long long begin[ADAM_MAX_SEGS], end[ADAM_MAX_SEGS], ld[ADAM_MAX_SEGS];
+    __nv_bfloat16* dst[ADAM_MAX_SEGS];
+    int cols[ADAM_MAX_SEGS];
+    float inv_cols[ADAM_MAX_SEGS];
+    int n;
+};
+
+__device__ __forceinline__ void adam_stage(const AdamSegs& sg, long long idx, float val) {
+#pragma unroll 1
+    for (int s = 0; s < sg.n; ++s) {
+        if (idx >= sg.begin[s] && idx < sg.end[s]) {
+            const int j = (int)(idx - sg.begin[s]);  // blocks are < 2^24 elements wide enough for the float estimate + fix-up
+            const int cols = sg.cols[s];
+            int r = __float2int_rd((float)j * sg.inv_cols[s]);
+            int c = j - r * cols;
+            if (c < 0) { --r; c += cols; }
+            else if (c >= cols) { ++r; c -= cols; }
+            sg.dst[s][(long long)r * sg.ld[s] + c] = __float2bfloat16(val);
+            return;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long n, float lr, float b1, float b2, float eps, float wd,
+                                                   float grad_scale, int* step, int* ticket, const __grid_constant__ AdamSegs sg) {
+    const int t = *step + (ticket ? 1 : 0);  // with a ticket counter this launch owns the increment of the step count
     const float bc1 = 1.0f - powf(b1, (float)t), bc2 = 1.0f - powf(b2, (float)t);
     const float step_size = lr / bc1, inv_sqrt_bc2 = 1.0f / sqrtf(bc2);
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long n4 = n >> 2;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 p4 = reinterpret_cast<float4*>(p)[i];
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+        float4 m4 = reinterpret_cast<float4*>(m)[i];
+        float4 v4 = reinterpret_cast<float4*>(v)[i];
+        float* pp = &p4.x;
+        const float* gg = &g4.x;
+        float* mm = &m4.x;
+        float* vv = &v4.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float gi = gg[k] * grad_scale + wd * pp[k];
+            mm[k] = b1 * mm[k] + (1.0f - b1) * gi;
+            vv[k] = b2 * vv[k] + (1.0f - b2) * gi * gi;
+            float denom = sqrtf(vv[k]) * inv_sqrt_bc2 + eps;
+            pp[k] = pp[k] - step_size * (mm[k] / denom);
+        }
+        reinterpret_cast<float4*>(m)[i] = m4;
+        reinterpret_cast<float4*>(v)[i] = v4;
+        reinterpret_cast<float4*>(p)[i] = p4;
+        if (sg.n > 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) adam_stage(sg, 4 * (long long)i + k, pp[k]);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {  // tail (the flat stores are padded to multiples of 4; kept for generality)
+        long i = (n4 << 2) + threadIdx.x;
         float pi = p[i];
         float gi = g[i] * grad_scale + wd * pi;
         float mi = b1 * m[i] + (1.0f - b1) * gi;
         float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
         m[i] = mi;
         v[i] = vi;
-        float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-        p[i] = pi - step_size * (mi / denom);
+        pi -= step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+        p[i] = pi;
+        if (sg.n > 0) adam_stage(sg, i, pi);
+    }
+    if (!ticket) return;
+    __syncthreads();  // every thread of this CTA has read *step
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+            *step = t;
+            *ticket = 0;
+        }
     }
 }
 
+// step: device counter of completed optimiser steps.  ticket == null: *step must already hold the 1-based index of this
+// step (spv_adam_tick before the call); ticket != null (a zeroed device int): the launch uses *step + 1 and stores it back.
+// Staging segments (nseg <= 8, host arrays): parameter block [seg_begin, seg_begin + seg_rows * seg_cols) viewed as
+// [seg_rows, seg_cols] is mirrored as bf16 into seg_dst with row pitch seg_ld.
 extern "C" int spv_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                        float wd, float grad_scale, const int* step, void* stream) {
-    if (!p || !g || !m || !v || !step || n <= 0) return SPV_ERR_ARG;
-    int blocks = (int)min((long long)148 * 16, (n + 255) / 256);
-    adam_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, b1, b2, eps, wd, grad_scale, step);
+                        float wd, float grad_scale, int* step, int* ticket, int nseg, const long long* seg_begin,
+                        const int* seg_rows, const int* seg_cols, void* const* seg_dst, const long long* seg_ld, void* stream) {
+    if (!p || !g || !m || !v || !step || n <= 0 || nseg < 0 || nseg > ADAM_MAX_SEGS) return SPV_ERR_ARG;
+    if (nseg > 0 && (!seg_begin || !seg_rows || !seg_cols || !seg_dst || !seg_ld)) return SPV_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+         reinterpret_cast<uintptr_t>(v)) & 15)
+        return SPV_ERR_ARG;
+    AdamSegs sg;
+    sg.n = nseg;
+    for (int s = 0; s < nseg; ++s) {
+        if (seg_rows[s] <= 0 || seg_cols[s] <= 0 || !seg_dst[s] || seg_ld[s] < seg_cols[s] ||
+            (long long)seg_rows[s] * seg_cols[s] >= (1ll << 24))
+            return SPV_ERR_ARG;
+        sg.begin[s] = seg_begin[s];
+        sg.end[s] = seg_begin[s] + (long long)seg_rows[s] * seg_cols[s];
+        sg.ld[s] = seg_ld[s];
+        sg.dst[s] = reinterpret_cast<__nv_bfloat16*>(seg_dst[s]);
+        sg.cols[s] = seg_cols[s];
+        sg.inv_cols[s] = 1.0f / (float)seg_cols[s];
+    }
+    int blocks = (int)min((long long)148 * 8, (n / 4 + 255) / 256);
+    if (blocks < 1) blocks = 1;
+    adam_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, b1, b2, eps, wd, grad_scale, step,
+                                                                            ticket, sg);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

@@ -305,29 +305,79 @@ extern "C" int spv_to_bf16(const float* src, long long ld_src, void* dst, long l
     return SPV_OK;
 }
 
-// T[b, g] = bf16(log1p(X[rows[b], g]))   (the encoder's input, reference module/spVIPESmodule.py:428-433), zero padded to ld_dst
+// T[b, g] = bf16(log1p(X[rows[b], g]))   (the encoder's input, reference module/spVIPESmodule.py:428-433), zero padded to ld_dst,
+// and optionally library[b] = log(sum_g log1p(x[b, g]))  (reference :433-435) from the same pass over the row.
+// One CTA per cell.  uint16 counts: 8 genes per 16-byte load when the row is 16-byte aligned, log1p of counts < 256 from a
+// shared-memory table filled with the same log1pf (bit-identical to computing it in place).
+#define ENC_IN_THREADS 256
 template <int SRC>
-__global__ void counts_to_bf16_kernel(const void* __restrict__ X, long ldx, const int* __restrict__ rows, __nv_bfloat16* __restrict__ dst,
-                                      long ld_dst, int B, int G) {
-    long total = (long)B * ld_dst;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        int g = (int)(i % ld_dst);
-        long b = i / ld_dst;
-        float v = 0.0f;
-        if (g < G) v = load_src<SRC>(X, (rows ? (long)rows[b] : b) * ldx + g);
-        dst[i] = __float2bfloat16(v);
+__global__ void __launch_bounds__(ENC_IN_THREADS) counts_to_bf16_kernel(const void* __restrict__ X, long ldx, const int* __restrict__ rows,
+                                                                        __nv_bfloat16* __restrict__ dst, long ld_dst, int B, int G,
+                                                                        float* __restrict__ lib) {
+    __shared__ float lut[256];
+    __shared__ float red[ENC_IN_THREADS / 32];
+    const int b = blockIdx.x;
+    const long r = rows ? (long)rows[b] : (long)b;
+    __nv_bfloat16* out = dst + (long)b * ld_dst;
+    float sum = 0.0f;
+    if (SRC == SPV_SRC_U16_LOG1P) {
+        lut[threadIdx.x] = threadIdx.x == 0 ? 0.0f : log1pf((float)threadIdx.x);
+        __syncthreads();
+        const unsigned short* row = reinterpret_cast<const unsigned short*>(X) + r * ldx;
+        const bool vec = (reinterpret_cast<uintptr_t>(row) & 15) == 0;  // dst rows are 16-byte aligned (ld_dst % 8 == 0)
+        const int nvec = vec ? G / 8 : 0;
+        for (int v = threadIdx.x; v < nvec; v += ENC_IN_THREADS) {
+            uint4 raw = __ldg(reinterpret_cast<const uint4*>(row) + v);
+            unsigned int w[4] = {raw.x, raw.y, raw.z, raw.w};
+            uint4 o;
+            unsigned int* ow = &o.x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                unsigned int c0 = w[j] & 0xffffu, c1 = w[j] >> 16;
+                float f0 = c0 < 256u ? lut[c0] : log1pf((float)c0);
+                float f1 = c1 < 256u ? lut[c1] : log1pf((float)c1);
+                sum += f0;
+                sum += f1;
+                __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+                ow[j] = *reinterpret_cast<unsigned int*>(&h);
+            }
+            *(reinterpret_cast<uint4*>(out) + v) = o;
+        }
+        for (int g = nvec * 8 + threadIdx.x; g < ld_dst; g += ENC_IN_THREADS) {
+            float f = 0.0f;
+            if (g < G) {
+                unsigned int c = row[g];
+                f = c < 256u ? lut[c] : log1pf((float)c);
+            }
+            sum += f;
+            out[g] = __float2bfloat16(f);
+        }
+    } else {
+        for (int g = threadIdx.x; g < ld_dst; g += ENC_IN_THREADS) {
+            float f = g < G ? load_src<SRC>(X, r * ldx + g) : 0.0f;
+            sum += f;
+            out[g] = __float2bfloat16(f);
+        }
+    }
+    if (!lib) return;
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < ENC_IN_THREADS / 32; ++i) s += red[i];
+        lib[b] = logf(s);
     }
 }
 
 extern "C" int spv_counts_to_bf16(int src, const void* X, long long ldx, const int* rows, void* dst, long long ld_dst, int B, int G,
-                                  void* stream) {
-    if (!X || !dst || B <= 0 || G <= 0 || ld_dst < G) return SPV_ERR_ARG;
-    long total = (long)B * ld_dst;
-    int blocks = (int)min((long)148 * 16, (total + 255) / 256);
+                                  float* lib, void* stream) {
+    if (!X || !dst || B <= 0 || G <= 0 || ld_dst < G || (ld_dst & 7)) return SPV_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
-    if (src == SPV_SRC_U16_LOG1P) counts_to_bf16_kernel<SPV_SRC_U16_LOG1P><<<blocks, 256, 0, st>>>(X, ldx, rows, d, ld_dst, B, G);
-    else if (src == SPV_SRC_F32_LOG1P) counts_to_bf16_kernel<SPV_SRC_F32_LOG1P><<<blocks, 256, 0, st>>>(X, ldx, rows, d, ld_dst, B, G);
+    if (src == SPV_SRC_U16_LOG1P) counts_to_bf16_kernel<SPV_SRC_U16_LOG1P><<<B, ENC_IN_THREADS, 0, st>>>(X, ldx, rows, d, ld_dst, B, G, lib);
+    else if (src == SPV_SRC_F32_LOG1P) counts_to_bf16_kernel<SPV_SRC_F32_LOG1P><<<B, ENC_IN_THREADS, 0, st>>>(X, ldx, rows, d, ld_dst, B, G, lib);
     else return SPV_ERR_ARG;
     SPV_CHECK_LAUNCH();
     return SPV_OK;

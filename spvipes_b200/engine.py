@@ -158,7 +158,7 @@ class Noise:
 
 
 class _GroupWS:
-    def __init__(self, B, G, d: Dims, dev, with_grad: bool, bf16: bool = False):
+    def __init__(self, B, G, d: Dims, dev, with_grad: bool, bf16: bool = False, wb=None):
         H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         self.B, self.G = B, G
@@ -193,10 +193,11 @@ class _GroupWS:
         self.Gp, self.KMp = r8(G), r8(KMIX)
         if bf16:
             h = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
-            self.Tb, self.W1b = h(B, self.Gp), h(2 * H, self.Gp)
-            # stacked tensor-core operand [3 Gp, KMp]: rows [0, G) mixture weight, [Gp, Gp+G) / [2Gp, 2Gp+G) the folded
-            # private / shared factor-regressor weights in the latent columns (zero elsewhere)
-            self.Wstack, self.amixb = h(3 * self.Gp, self.KMp), h(B, self.KMp)
+            self.Tb, self.amixb = h(B, self.Gp), h(B, self.KMp)
+            # bf16 weight operands are per engine (shared by every workspace): W1b [2H, Gp] and the stacked operand
+            # Wstack [3 Gp, KMp]: rows [0, G) mixture weight, [Gp, Gp+G) / [2Gp, 2Gp+G) the folded private / shared
+            # factor-regressor weights of the current minibatch in the latent columns (zero elsewhere)
+            self.W1b, self.Wstack = wb
             self.Wmb = self.Wstack[:G]
             if with_grad:
                 self.D3, self.dh1b = h(B, 3 * self.Gp), h(B, 2 * H)  # D3 = [dpi | dyp | dys]
@@ -261,6 +262,17 @@ class StepEngine:
         self._aux = None
         self._pending = {}
         self.parallel_groups = True
+        r8 = lambda x: (x + 7) // 8 * 8
+        self.wb = None
+        if self.bf16:
+            self.wb = [(torch.zeros(2 * self.d.n_hidden, r8(G), dtype=torch.bfloat16, device=self.device),
+                        torch.zeros(3 * r8(G), r8(self.d.KMIX), dtype=torch.bfloat16, device=self.device)) for G in self.d.genes]
+        # bf16 copies of W1 / Wm: refreshed by conversion kernels at the start of every forward, or (stage_in_adam, set by
+        # the owner of the optimiser step: TrainLoop) written by the Adam kernel itself; _staged_version detects parameter
+        # writes made through torch (load_state_dict, .copy_, a torch optimiser) since the last staging
+        self.stage_in_adam = False
+        self._staged_version = -1
+        self.adam_ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.nb_events = None  # bench hook: iterator of (start, end) CUDA events bracketing the NB-loglik sweep
 
     # -------------------------------------------------------------------------------- helpers
@@ -340,7 +352,8 @@ class StepEngine:
     def workspace(self, B0, B1, with_grad=True):
         key = (B0, B1, with_grad)
         if key not in self._ws:
-            self._ws[key] = [_GroupWS(B, G, self.d, self.device, with_grad, self.bf16) for B, G in zip((B0, B1), self.d.genes)]
+            self._ws[key] = [_GroupWS(B, G, self.d, self.device, with_grad, self.bf16, self.wb[g] if self.bf16 else None)
+                             for g, (B, G) in enumerate(zip((B0, B1), self.d.genes))]
         return self._ws[key]
 
     @staticmethod
@@ -363,6 +376,7 @@ class StepEngine:
         noise = noise or Noise()
         tr = 1 if training else 0
         srcs = []
+        convert = self.bf16 and not (self.stage_in_adam and self._staged_version == self.params.flat._version)
         # ---------------- encoders (reference nn/networks.py:119-125, module :428-448)
         for g in self._fork_groups():
             bt, w, st = batches[g], ws[g], self._stream()
@@ -371,22 +385,23 @@ class StepEngine:
             ldx = bt.X.stride(0)
             xptr = bt.X.data_ptr() + bt.col0 * esz
             srcs.append((src, xptr, ldx))
-            if self.bf16:  # bf16 copies of the two big weights do not depend on the minibatch: off the critical path
+            if convert:  # bf16 copies of the two big weights do not depend on the minibatch: off the critical path
                 with self._branch(g, "w1"):
                     L.check(lib.spv_to_bf16(L.ptr(self.P(g, "W1")), G, L.ptr(w.W1b), w.Gp, 2 * H, G, self._stream()), "spv_to_bf16")
-                if decode:
+                if decode or self.stage_in_adam:
                     with self._branch(g, "wm"):
                         L.check(lib.spv_to_bf16(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX, self._stream()),
                                 "spv_to_bf16")
-            with self._branch(g, "lib"):
-                L.check(lib.spv_library_size(src, xptr, ldx, L.ptr(bt.rows), B, G, L.ptr(w.lib), self._stream()),
-                        "spv_library_size")
-            if self.bf16:
-                L.check(lib.spv_counts_to_bf16(src, xptr, ldx, L.ptr(bt.rows), L.ptr(w.Tb), w.Gp, B, G, st), "spv_counts_to_bf16")
+            if self.bf16:  # encoder input and library size from one pass over the gathered rows
+                L.check(lib.spv_counts_to_bf16(src, xptr, ldx, L.ptr(bt.rows), L.ptr(w.Tb), w.Gp, B, G, L.ptr(w.lib), st),
+                        "spv_counts_to_bf16")
                 self._join(g, "w1")
                 self._tc_gemm(L.ptr(w.Tb), L.ptr(w.W1b), L.ptr(w.h1), B, 2 * H, G, lda=w.Gp, ldb=w.Gp, ldc=2 * H,
                               bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.tc_splits_fc1, ws=w.ws)
             else:
+                with self._branch(g, "lib"):
+                    L.check(lib.spv_library_size(src, xptr, ldx, L.ptr(bt.rows), B, G, L.ptr(w.lib), self._stream()),
+                            "spv_library_size")
                 self._gemm(xptr, L.ptr(self.P(g, "W1")), L.ptr(w.h1), B, 2 * H, G, lda=ldx, ldb=G, ldc=2 * H, tb=1, srcA=src,
                            rowsA=bt.rows, bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.splits_fc1, ws=w.ws)
             self._gemm(L.ptr(w.h1), L.ptr(self.P(g, "W2")), L.ptr(w.h2), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, tb=1, batch=2,
@@ -404,6 +419,8 @@ class StepEngine:
             L.check(lib.spv_bn_fwd(L.ptr(w.r), NST, L.ptr(w.stats), NST, B, NST, L.ptr(self.P(g, "ghd")),
                                    L.ptr(self.P(g, "bthd")), ENC_BN_EPS, ENC_BN_MOM, L.ptr(self.Bf(g, "rm_hd")),
                                    L.ptr(self.Bf(g, "rv_hd")), L.ptr(w.bn_hd_mean), L.ptr(w.bn_hd_istd), tr, 0, st), "spv_bn_fwd")
+        if convert and self.stage_in_adam:
+            self._staged_version = self.params.flat._version
         # ---------------- pairing (integer work) and PoE (reference :484-718)
         aux = self._pairing(batches, ws, Bs)
         self._poe_fwd(ws, Bs, noise, aux)
@@ -590,11 +607,17 @@ class StepEngine:
                 self._gemm(L.ptr(w.dys), w.wfold.data_ptr() + 4 * P, w.dzraw.data_ptr() + 4 * P, B, S, G, lda=G, ldb=KZ, ldc=KZ,
                            splits=w.splits_g, ws=w.ws)
                 Qp, Qs, ldq, dzraw = L.ptr(w.Qp), L.ptr(w.Qs), 0, L.ptr(w.dzraw)
-            # hidden layer of the mixing net: ReLU + BatchNorm backward (needs only d [hm | zz]), its Linear's weight
-            # gradient goes to the auxiliary stream, its input gradient is folded into the d zz combine below
+            # hidden layer of the mixing net: ReLU + BatchNorm backward (needs only d [hm | zz]); its Linear's input and
+            # weight gradients run on the auxiliary stream next to the per-gene BatchNorm backward
             L.check(lib.spv_bn_bwd(L.ptr(w.damix), KMIX, L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, L.ptr(w.dah), HD, B, HD,
                                    L.ptr(self.P(g, "gh")), L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), L.ptr(self.Gd(g, "gh")),
                                    L.ptr(self.Gd(g, "bth")), st), "spv_bn_bwd")
+            if dzraw is None:
+                dzraw = L.ptr(w.dzraw)
+                with self._branch(g, "hid"):
+                    self._gemm(L.ptr(w.dah), L.ptr(self.P(g, "Wh")), dzraw, B, KZ, HD, lda=HD, ldb=KZ, ldc=KZ)
+            else:
+                self._gemm(L.ptr(w.dah), L.ptr(self.P(g, "Wh")), dzraw, B, KZ, HD, lda=HD, ldb=KZ, ldc=KZ, acc=1)
             with self._branch(g, "wgrad"):
                 self._gemm(L.ptr(w.dah), zzp, L.ptr(self.Gd(g, "Wh")), HD, KZ, B, lda=HD, ldb=KMIX, ldc=KZ, ta=1,
                            splits=w.splits_b, ws=w.ws2)
@@ -603,9 +626,9 @@ class StepEngine:
                               self.Gd(g, "Wp"), self.Gd(g, "Ws"), self.Gd(g, "gp"), self.Gd(g, "bp"), self.Gd(g, "gs"),
                               self.Gd(g, "bs"), self.Gd(g, "px_r"), self.Gd(g, "bm"), w.vpart, w.mpart])
             L.check(lib.spv_dec_gene_bwd(gb, ldq, B, G, P, S, st), "spv_dec_gene_bwd")
+            self._join(g, "hid")
             L.check(lib.spv_dec_dzz_combine(w.damix.data_ptr() + 4 * HD, KMIX, dzraw, L.ptr(w.vpart), L.ptr(w.mpart),
-                                            w.nTG, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dah), L.ptr(self.P(g, "Wh")), HD,
-                                            L.ptr(w.dzz), B, P, S, st), "spv_dec_dzz_combine")
+                                            w.nTG, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S, st), "spv_dec_dzz_combine")
         # ---------------- PoE
         own = self._poe_sides(ws)
         arrs = []
@@ -674,10 +697,31 @@ class StepEngine:
             self.adam_m = torch.zeros_like(self.params.flat)
             self.adam_v = torch.zeros_like(self.params.flat)
         st = self._stream()
-        L.check(self.lib.spv_adam_tick(L.ptr(self.step_dev), st), "spv_adam_tick")
+        segs = self._stage_segments() if (self.bf16 and self.stage_in_adam) else []
         L.check(self.lib.spv_adam(L.ptr(self.params.flat), L.ptr(self.grads), L.ptr(self.adam_m), L.ptr(self.adam_v),
                                   self.params.numel, lr, betas[0], betas[1], eps, weight_decay, grad_scale,
-                                  L.ptr(self.step_dev), st), "spv_adam")
+                                  L.ptr(self.step_dev), L.ptr(self.adam_ticket), len(segs),
+                                  L.ll_array([s[0] for s in segs]), L.int_array([s[1] for s in segs]),
+                                  L.int_array([s[2] for s in segs]), L.ptr_array([s[3] for s in segs]),
+                                  L.ll_array([s[4] for s in segs]), st), "spv_adam")
+
+    def _stage_segments(self):
+        """(flat offset, rows, cols, bf16 destination, destination row pitch) of the weights the tensor-core path reads"""
+        out = []
+        for g, G in enumerate(self.d.genes):
+            W1b, Wstack = self.wb[g]
+            out.append((self.params.offsets[g]["W1"][0], 2 * self.d.n_hidden, G, W1b, W1b.stride(0)))
+            out.append((self.params.offsets[g]["Wm"][0], G, self.d.KMIX, Wstack, Wstack.stride(0)))
+        return out
+
+    def stage_weights(self):
+        """refresh the bf16 operand copies of W1 / Wm from the fp32 parameters (bf16 mode; a no-op otherwise)"""
+        if not self.bf16:
+            return
+        for off, rows, cols, dst, ld in self._stage_segments():
+            src = self.params.flat[off:off + rows * cols]
+            L.check(self.lib.spv_to_bf16(L.ptr(src), cols, L.ptr(dst), ld, rows, cols, self._stream()), "spv_to_bf16")
+        self._staged_version = self.params.flat._version
 
     # -------------------------------------------------------------------------------- state
     def load_state_dict(self, sd: Dict[str, torch.Tensor]):

@@ -85,6 +85,10 @@ class TrainLoop:
         self.n_epochs_kl_warmup = n_epochs_kl_warmup
         self.epoch = 0
         self.grad_sync = None  # optional callable(engine) run between backward and the optimiser step (data parallel)
+        # this loop owns the optimiser step: Adam also refreshes the bf16 tensor-core copies of the large weights
+        # (largest staged block must stay below 2^24 elements, the range of the kernel's index arithmetic)
+        if engine.bf16 and max(engine.d.genes) * max(engine.d.KMIX, 2 * engine.d.n_hidden) < (1 << 24):
+            engine.stage_in_adam = True
 
     def set_epoch(self, epoch: int):
         self.epoch = epoch
@@ -138,6 +142,7 @@ class TrainLoop:
             e.adam_m.zero_(); e.adam_v.zero_()
         else:
             e.adam_m.copy_(keep[3]); e.adam_v.copy_(keep[4])
+        e.stage_weights()  # the restore above went through torch: bring the bf16 operand copies back in line
         return graph
 
 
