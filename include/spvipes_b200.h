@@ -108,8 +108,10 @@ int spv_loss(const float* rec0, const float* rec1, const float* klp0, const floa
              int B, const float* kl_weight, float* out, void* stream);
 
 /* decoder: closed-form per-gene BatchNorm fold + NB constants.
- * ptrs (18): Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, cov_part, wfold, genec,
- * zmean, zcov.   nn/networks.py:314-320, scvi FCLayers; module/spVIPESmodule.py:758 */
+ * ptrs (18): Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, (unused), wfold, genec,
+ * zmean, zcov.  training != 0: zsum / zmean / zcov [P+S], [P+S], [P+S, P+S] are OUTPUTS (column sums, mean and biased
+ * covariance of the latent minibatch zz [B, P+S], one cluster launch).   nn/networks.py:314-320, scvi FCLayers;
+ * module/spVIPESmodule.py:758 */
 #define SPV_DEC_GENEC_ROWS 12
 /* wz_bf16 (optional): rows [Gp, 3 Gp) of the stacked bf16 tensor-core operand [3 Gp, ld_wz] (rows [0, G): mixture weight,
  * [Gp, Gp + G): folded private weights in the latent columns HD .., [2 Gp, 2 Gp + G): folded shared weights) */
@@ -139,7 +141,9 @@ int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const voi
                       const void* wstack_bf16, long long ld_w, int Gp, void* d3_bf16, int B, int G, int HD, int P, int S,
                       float scale, float* colsum, void* stream);
 /* ptrs (18): Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm,
- * vpart [ceil(G/64), P+S], mpart [ceil(G/64), (P+S)^2]   (backward of nn/networks.py:314-320 through the folded BatchNorm) */
+ * vpart [parts, P+S], mpart [parts, (P+S)^2] with parts = spv_dec_gene_bwd_parts(G)
+ * (backward of nn/networks.py:314-320 through the folded BatchNorm) */
+int spv_dec_gene_bwd_parts(int G);
 int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, int G, int P, int S, void* stream);
 /* d zz = dmix (latent columns of d [hm | zz]) + dzraw (optional further addends [B, P+S]: softmax-branch and hidden-layer
  * input gradients when they are not in dmix) - BatchNorm coupling terms, the latter summed from the `nparts` per-CTA

@@ -241,27 +241,42 @@ __global__ void __launch_bounds__(GT_THREADS) dec_tile_kernel(DecP p) {
 // combine the per-gene-tile softmax partials: Rp = lib - logsumexp_g(y_p), Rs likewise
 __global__ void rowstat_kernel(const float* __restrict__ part, int nTG, int B, const float* __restrict__ lib,
                                float* __restrict__ rowc) {
-    // one warp per row, lanes over the gene tiles
+    // one warp per row, lanes over the gene tiles; the row's partials are read once (16-byte loads, all in flight) and the
+    // library size is fetched up front: one memory round trip instead of three dependent ones
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= B) return;
+    const float l = __ldg(lib + b);
+    constexpr int R = 4;
+    const float4 none = make_float4(-INFINITY, 0.0f, -INFINITY, 0.0f);
+    float4 o[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int t = lane + 32 * r;
+        o[r] = t < nTG ? __ldg(reinterpret_cast<const float4*>(part) + (long)t * B + b) : none;
+    }
     float Mp = -INFINITY, Ms = -INFINITY;
-    for (int t = lane; t < nTG; t += 32) {
-        const float* o = part + ((long)t * B + b) * 4;
-        Mp = fmaxf(Mp, o[0]);
-        Ms = fmaxf(Ms, o[2]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) { Mp = fmaxf(Mp, o[r].x); Ms = fmaxf(Ms, o[r].z); }
+    for (int t = lane + 32 * R; t < nTG; t += 32) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(part) + (long)t * B + b);
+        Mp = fmaxf(Mp, v.x); Ms = fmaxf(Ms, v.z);
     }
     Mp = warp_max(Mp);
     Ms = warp_max(Ms);
     float Sp = 0.0f, Ss = 0.0f;
-    for (int t = lane; t < nTG; t += 32) {
-        const float* o = part + ((long)t * B + b) * 4;
-        Sp += o[1] * expf(o[0] - Mp);
-        Ss += o[3] * expf(o[2] - Ms);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        Sp += o[r].y * expf(o[r].x - Mp);
+        Ss += o[r].w * expf(o[r].z - Ms);
+    }
+    for (int t = lane + 32 * R; t < nTG; t += 32) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(part) + (long)t * B + b);
+        Sp += v.y * expf(v.x - Mp);
+        Ss += v.w * expf(v.z - Ms);
     }
     Sp = warp_sum(Sp);
     Ss = warp_sum(Ss);
     if (lane == 0) {
-        float l = lib[b];
         rowc[(long)b * 4 + 0] = l - (Mp + logf(Sp));
         rowc[(long)b * 4 + 1] = l - (Ms + logf(Ss));
     }
@@ -271,6 +286,7 @@ __global__ void rownb_kernel(const float* __restrict__ part, int nTG, int B, flo
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= B) return;
     float ll = 0.0f, dp = 0.0f, ds = 0.0f;
+#pragma unroll 4
     for (int t = lane; t < nTG; t += 32) {
         const float* o = part + ((long)t * B + b) * 3;
         ll += o[0]; dp += o[1]; ds += o[2];

@@ -5,142 +5,262 @@
 // W[g]^T Cov(z) W[g]: no [B, G] pass is needed, only the [KZ, KZ] covariance of the latent minibatch.
 //
 // Work split: one warp per gene (lanes over the latent dimension), 64 genes per CTA.
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 #include "decoder_common.cuh"
 #include "../../include/spvipes_b200.h"
 
-#define GENES_PER_CTA 64        // gene_bwd: 64 genes share one set of per-CTA partial sums
-#define FOLD_GENES_PER_CTA 8    // fold: one gene per warp
-#define GENE_BWD_THREADS 1024
+#define GENES_PER_CTA 32        // gene_bwd: 32 genes share one set of per-CTA partial sums (ncu r1: instruction bound, so
+                                // more, smaller CTAs; spv_dec_gene_bwd_parts reports the resulting number of partials)
+#define FOLD_GENES_PER_CTA 32   // fold: 8 warps x 4 genes for the quadratic forms, then one gene per lane for the NB constants
+#define GENE_BWD_THREADS 256
 
 // ---------------------------------------------------------------------------------------
-// partial (un-normalised, centred) second moments of zz over a chunk of 64 rows
+// mean and (biased) covariance of the latent minibatch zz [B, KZ] in ONE launch: a cluster of 8 CTAs, each owning a
+// contiguous slice of the rows.  Column sums are exchanged through distributed shared memory (every CTA adds the eight
+// partials in rank order, so all see the same mean), the centred second moments of the slice are accumulated in shared
+// memory, and CTA r adds the eight partials of every 8th covariance entry, again in rank order: deterministic, no
+// global-memory partials, no atomics, two cluster barriers instead of a second launch + "last CTA" pass.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) zcov_kernel(const float* __restrict__ zz, long ld, int B, int KZ,
-                                                   const float* __restrict__ zsum, float* cov_part,
-                                                   float* __restrict__ zmean_out, float* __restrict__ zcov_out) {
-    extern __shared__ float tile[];  // [64][KZ + 1]
-    const int r0 = blockIdx.x * 64;
+#define ZS_CTAS 8
+#define ZS_ROWS 64
+#define ZS_THREADS 256
+
+// rows [r0, r0 + nr) of zz into tile [ZS_ROWS][ldt] (zero rows beyond nr); all loads of a thread in flight before the stores
+__device__ __forceinline__ void zs_load_tile(float* tile, int ldt, const float* __restrict__ zz, long ld, int r0, int nr, int KZ) {
+    const int total = ZS_ROWS * KZ;
+    for (int base = 0; base < total; base += 12 * ZS_THREADS) {
+        float v[12];
+#pragma unroll
+        for (int u = 0; u < 12; ++u) {
+            const int i = base + u * ZS_THREADS + (int)threadIdx.x;
+            const int r = i / KZ, k = i - r * KZ;
+            v[u] = (i < total && r < nr) ? __ldg(zz + (long)(r0 + r) * ld + k) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 12; ++u) {
+            const int i = base + u * ZS_THREADS + (int)threadIdx.x;
+            const int r = i / KZ, k = i - r * KZ;
+            if (i < total) tile[r * ldt + k] = v[u];
+        }
+    }
+}
+
+__global__ void __cluster_dims__(ZS_CTAS, 1, 1) __launch_bounds__(ZS_THREADS)
+    zstats_kernel(const float* __restrict__ zz, long ld, int B, int KZ, float* __restrict__ zsum_out,
+                  float* __restrict__ zmean_out, float* __restrict__ zcov_out) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ float zs_sh[];
     const int ldt = KZ + 1;
+    float* tile = zs_sh;                    // [ZS_ROWS][KZ + 1]
+    float* csum = tile + ZS_ROWS * ldt;     // [KZ]   column sums of this CTA's rows
+    float* mean = csum + KZ;                // [KZ]
+    float* scratch = mean + KZ;             // [8][KZ]
+    float* cpart = scratch + 8 * KZ;        // [KZ * KZ] centred second moments of this CTA's rows
+    const int rank = (int)cluster.block_rank();
+    const int chunk = (B + ZS_CTAS - 1) / ZS_CTAS;
+    const int r_begin = min(B, rank * chunk), r_end = min(B, r_begin + chunk);
+    const bool single = chunk <= ZS_ROWS;  // the slice fits one tile: it is read from global memory once
     const float invB = 1.0f / (float)B;
-    for (int i = threadIdx.x; i < 64 * KZ; i += blockDim.x) {
-        int r = i / KZ, k = i % KZ;
-        float v = 0.0f;
-        if (r0 + r < B) v = zz[(long)(r0 + r) * ld + k] - zsum[k] * invB;
-        tile[r * ldt + k] = v;
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- column sums of the slice
+    for (int k = threadIdx.x; k < KZ; k += ZS_THREADS) csum[k] = 0.0f;
+    for (int i = threadIdx.x; i < KZ * KZ; i += ZS_THREADS) cpart[i] = 0.0f;
+    for (int r0 = r_begin; r0 < r_end || r0 == r_begin; r0 += ZS_ROWS) {
+        const int nr = max(0, min(ZS_ROWS, r_end - r0));
+        __syncthreads();
+        zs_load_tile(tile, ldt, zz, ld, r0, nr, KZ);
+        __syncthreads();
+        for (int k = lane; k < KZ; k += 32) {  // 8 row lanes per column, rows beyond nr are zero
+            float s = 0.0f;
+#pragma unroll
+            for (int r = 0; r < ZS_ROWS / 8; ++r) s += tile[(q + 8 * r) * ldt + k];
+            scratch[q * KZ + k] = s;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < KZ; k += ZS_THREADS) {
+            float s = csum[k];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += scratch[i * KZ + k];
+            csum[k] = s;
+        }
+        if (r0 + ZS_ROWS >= r_end) break;
     }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < KZ * KZ; idx += blockDim.x) {
-        int i = idx / KZ, j = idx % KZ;
+    cluster.sync();
+    for (int k = threadIdx.x; k < KZ; k += ZS_THREADS) {
         float s = 0.0f;
+#pragma unroll
+        for (int c = 0; c < ZS_CTAS; ++c) s += cluster.map_shared_rank(csum, c)[k];
+        mean[k] = s * invB;
+        if (rank == 0) {
+            zsum_out[k] = s;
+            zmean_out[k] = s * invB;
+        }
+    }
+    // ---- centred second moments of the slice
+    for (int r0 = r_begin; r0 < r_end; r0 += ZS_ROWS) {
+        const int nr = min(ZS_ROWS, r_end - r0);
+        __syncthreads();
+        if (!single) {
+            zs_load_tile(tile, ldt, zz, ld, r0, nr, KZ);
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < ZS_ROWS * KZ; i += ZS_THREADS) {
+            const int r = i / KZ, k = i - r * KZ;
+            if (r < nr) tile[r * ldt + k] -= mean[k];
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < KZ * KZ; idx += ZS_THREADS) {
+            const int i = idx / KZ, j = idx - i * KZ;
+            float s = 0.0f;
 #pragma unroll 8
-        for (int r = 0; r < 64; ++r) s = fmaf(tile[r * ldt + i], tile[r * ldt + j], s);
-        cov_part[(long)blockIdx.x * KZ * KZ + idx] = s;
+            for (int r = 0; r < ZS_ROWS; ++r) s = fmaf(tile[r * ldt + i], tile[r * ldt + j], s);
+            cpart[idx] += s;
+        }
     }
-    // the last CTA to finish sums the partials in chunk order (deterministic) into the final mean / covariance
-    __shared__ int is_last;
-    int* counter = reinterpret_cast<int*>(cov_part + (long)gridDim.x * KZ * KZ);  // one spare slot, zero between launches
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int ticket = atomicAdd(counter, 1);
-        is_last = ticket == (int)gridDim.x - 1;
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    for (int k = threadIdx.x; k < KZ; k += blockDim.x) zmean_out[k] = zsum[k] * invB;
-    for (int idx = threadIdx.x; idx < KZ * KZ; idx += blockDim.x) {
+    cluster.sync();
+    for (int idx = rank + ZS_CTAS * threadIdx.x; idx < KZ * KZ; idx += ZS_CTAS * ZS_THREADS) {
         float s = 0.0f;
-        for (int c = 0; c < (int)gridDim.x; ++c) s += __ldcg(cov_part + (long)c * KZ * KZ + idx);
+#pragma unroll
+        for (int c = 0; c < ZS_CTAS; ++c) s += cluster.map_shared_rank(cpart, c)[idx];
         zcov_out[idx] = s * invB;
     }
-    if (threadIdx.x == 0) *counter = 0;
+    cluster.sync();  // no CTA may exit while its shared memory is still being read by the others
 }
 
 struct FoldP {
-    const float *Wp, *Ws, *gp, *bp, *gs, *bs, *px_r;
+    const float *Wp, *Ws;
+    const float* vec[9];  // per-gene vectors: gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s
     float *rm_p, *rv_p, *rm_s, *rv_s;
-    const float *zsum, *cov_part;
-    float *wfold, *genec, *zmean, *zcov;
+    float *wfold, *genec;
+    const float *zmean, *zcov;
     // optional: rows [Gp, 3 Gp) of the stacked bf16 operand [3 Gp, ld_wz] (private block then shared block); the folded weights
     // go into the latent columns HD .. HD + P + S of their block, every other entry of those rows stays zero
     __nv_bfloat16* wfold_bf16;
     long ld_wz;
     int Gp, HD;
-    int G, P, S, B, ncov, training;
+    int G, P, S, B, training;
     float eps, momentum;
 };
 
+// 32 genes per CTA.  All inputs of the CTA arrive in one round of loads; the quadratic forms W C W^T run as one thread per
+// (gene, latent index) over T = W C, so every lane is busy (ncu r1: the one-gene-per-warp form used 10 resp. 25 of 32 lanes
+// and ~1000 instructions per gene, 5 M warp instructions per launch).
 __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
-    extern __shared__ float sh[];  // mean[KZ] | cov[KZ*KZ]
+    extern __shared__ float sh[];
     const int KZ = p.P + p.S;
-    float* smean = sh;
-    float* scov = sh + KZ;
-    if (p.training) {  // final mean / covariance of the latent minibatch (zcov_kernel)
-        for (int k = threadIdx.x; k < KZ; k += blockDim.x) smean[k] = p.zmean[k];
-        for (int i = threadIdx.x; i < KZ * KZ; i += blockDim.x) scov[i] = p.zcov[i];
+    const int g0 = blockIdx.x * FOLD_GENES_PER_CTA;
+    const int ng = min(FOLD_GENES_PER_CTA, p.G - g0);
+    float* scov = sh;                                   // [KZ][KZ]
+    float* smean = scov + KZ * KZ;                      // [KZ]
+    float* sWp = smean + KZ;                            // [32][P]
+    float* sWs = sWp + FOLD_GENES_PER_CTA * p.P;        // [32][S]
+    float* svec = sWs + FOLD_GENES_PER_CTA * p.S;       // [9][32]
+    float* sT = svec + 9 * FOLD_GENES_PER_CTA;          // [32][KZ]   T = W C (block diagonal)
+    float* sA = sT + FOLD_GENES_PER_CTA * KZ;           // [2][32]    folded scale a = gamma invstd
+    {
+        StageArr<5> c;
+        StageArr<1> m;
+        StageArr<2> wp;
+        StageArr<4> ws;
+        float sc[2];
+        c.load(p.training ? p.zcov : nullptr, KZ * KZ);
+        m.load(p.training ? p.zmean : nullptr, KZ);
+        wp.load(p.Wp + (long)g0 * p.P, ng * p.P);
+        ws.load(p.Ws + (long)g0 * p.S, ng * p.S);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = u * 256 + (int)threadIdx.x, arr = i >> 5, gl = i & 31;
+            sc[u] = (arr < 9 && gl < ng) ? __ldg(p.vec[arr] + g0 + gl) : 0.0f;
+        }
+        c.store(scov, KZ * KZ);
+        m.store(smean, KZ);
+        wp.store(sWp, ng * p.P);
+        ws.store(sWs, ng * p.S);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = u * 256 + (int)threadIdx.x;
+            if (i < 9 * 32) svec[i] = sc[u];
+        }
+        StageArr<5>::rest(scov, p.training ? p.zcov : nullptr, KZ * KZ);
+        StageArr<1>::rest(smean, p.training ? p.zmean : nullptr, KZ);
+        StageArr<2>::rest(sWp, p.Wp + (long)g0 * p.P, ng * p.P);
+        StageArr<4>::rest(sWs, p.Ws + (long)g0 * p.S, ng * p.S);
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long G = p.G;
-    {  // one gene per warp: every gene's chain of dependent loads runs concurrently
-        const int g = blockIdx.x * FOLD_GENES_PER_CTA + warp;
-        if (g >= p.G) return;
-#pragma unroll
-        for (int br = 0; br < 2; ++br) {
-            const int K = br == 0 ? p.P : p.S;
-            const int off = br == 0 ? 0 : p.P;
-            const float* W = (br == 0 ? p.Wp : p.Ws) + (long)g * K;
-            float* rm = br == 0 ? p.rm_p : p.rm_s;
-            float* rv = br == 0 ? p.rv_p : p.rv_s;
-            float mean, var;
-            if (p.training) {
-                float pm = 0.0f, pv = 0.0f;
-                for (int k = lane; k < K; k += 32) {
-                    float wk = W[k];
-                    pm = fmaf(smean[off + k], wk, pm);
-                    float t = 0.0f;
-                    for (int l = 0; l < K; ++l) t = fmaf(scov[(off + k) * KZ + off + l], __ldg(W + l), t);
-                    pv = fmaf(wk, t, pv);
-                }
-                mean = warp_sum(pm);
-                var = fmaxf(warp_sum(pv), 0.0f);
-                if (lane == 0) {
-                    float unb = var * ((float)p.B / (float)max(p.B - 1, 1));
-                    rm[g] = (1.0f - p.momentum) * rm[g] + p.momentum * mean;
-                    rv[g] = (1.0f - p.momentum) * rv[g] + p.momentum * unb;
-                }
-            } else {
-                mean = rm[g];
-                var = rv[g];
-            }
-            float invstd = 1.0f / sqrtf(var + p.eps);
-            float a = (br == 0 ? p.gp : p.gs)[g] * invstd;
-            float c = (br == 0 ? p.bp : p.bs)[g] - mean * a;
-            for (int k = lane; k < K; k += 32) p.wfold[(long)g * KZ + off + k] = a * W[k];
-            if (p.wfold_bf16)  // bf16 copy inside the stacked tensor-core operand: block br, row g, latent columns HD + off ..
-                for (int k = lane; k < K; k += 32)
-                    p.wfold_bf16[((long)br * p.Gp + g) * p.ld_wz + p.HD + off + k] = __float2bfloat16(a * W[k]);
-            if (lane == 0) {
-                p.genec[(br == 0 ? GC_CP : GC_CS) * G + g] = c;
-                p.genec[(br == 0 ? GC_AP : GC_AS) * G + g] = a;
-                p.genec[(br == 0 ? GC_ISTD_P : GC_ISTD_S) * G + g] = invstd;
-                p.genec[(br == 0 ? GC_MEAN_P : GC_MEAN_S) * G + g] = mean;
-            }
+    // T[gl][k] = sum_l C[k][l] W[gl][l]  (l within k's block)
+    if (p.training) {
+        for (int i = threadIdx.x; i < ng * KZ; i += 256) {
+            const int gl = i / KZ, k = i - gl * KZ;
+            const bool pr = k < p.P;
+            const int K = pr ? p.P : p.S, off = pr ? 0 : p.P;
+            const float* W = pr ? sWp + gl * p.P : sWs + gl * p.S;
+            const float* C = scov + k * KZ + off;
+            float t = 0.0f;
+#pragma unroll 5
+            for (int l = 0; l < K; ++l) t = fmaf(C[l], W[l], t);
+            sT[i] = t;
         }
-        if (lane == 0) {
-            float th = expf(p.px_r[g]);  // reference module/spVIPESmodule.py:758
+        __syncthreads();
+    }
+    // per (gene, branch): batch statistics of u = z W^T, running-statistics update, folded scale and shift
+    if (threadIdx.x < 2 * FOLD_GENES_PER_CTA) {
+        const int br = threadIdx.x >> 5, gl = threadIdx.x & 31;
+        if (gl < ng) {
+            const int g = g0 + gl;
+            const int K = br == 0 ? p.P : p.S, off = br == 0 ? 0 : p.P;
+            const float* W = br == 0 ? sWp + gl * p.P : sWs + gl * p.S;
+            const float gamma = svec[(br == 0 ? 0 : 2) * 32 + gl], beta = svec[(br == 0 ? 1 : 3) * 32 + gl];
+            float mean = svec[(br == 0 ? 5 : 7) * 32 + gl], var = svec[(br == 0 ? 6 : 8) * 32 + gl];  // running statistics
+            if (p.training) {
+                float bmean = 0.0f, bvar = 0.0f;
+                for (int k = 0; k < K; ++k) {
+                    bmean = fmaf(smean[off + k], W[k], bmean);
+                    bvar = fmaf(W[k], sT[gl * KZ + off + k], bvar);
+                }
+                bvar = fmaxf(bvar, 0.0f);
+                const float unb = bvar * ((float)p.B / (float)max(p.B - 1, 1));
+                (br == 0 ? p.rm_p : p.rm_s)[g] = (1.0f - p.momentum) * mean + p.momentum * bmean;
+                (br == 0 ? p.rv_p : p.rv_s)[g] = (1.0f - p.momentum) * var + p.momentum * unb;
+                mean = bmean;
+                var = bvar;
+            }
+            const float invstd = 1.0f / sqrtf(var + p.eps);
+            const float a = gamma * invstd;
+            sA[br * 32 + gl] = a;
+            p.genec[(br == 0 ? GC_CP : GC_CS) * G + g] = beta - mean * a;
+            p.genec[(br == 0 ? GC_AP : GC_AS) * G + g] = a;
+            p.genec[(br == 0 ? GC_ISTD_P : GC_ISTD_S) * G + g] = invstd;
+            p.genec[(br == 0 ? GC_MEAN_P : GC_MEAN_S) * G + g] = mean;
+        }
+    } else if (threadIdx.x < 3 * FOLD_GENES_PER_CTA) {
+        // NB constants of the inverse dispersion: one gene per lane
+        const int gl = threadIdx.x - 2 * FOLD_GENES_PER_CTA;
+        if (gl < ng) {
+            const int g = g0 + gl;
+            float th = expf(svec[4 * 32 + gl]);  // reference module/spVIPESmodule.py:758
             p.genec[GC_THETA * G + g] = th;
             p.genec[GC_LTE * G + g] = logf(th + NB_EPS);
             p.genec[GC_LGT * G + g] = lgammaf(th);
             p.genec[GC_DGT * G + g] = digammaf_pos(th);
         }
     }
+    __syncthreads();
+    // folded weights W' = a W: fp32 [G, KZ] and the bf16 copy inside the stacked tensor-core operand
+    for (int i = threadIdx.x; i < ng * KZ; i += 256) {
+        const int gl = i / KZ, k = i - gl * KZ;
+        const bool pr = k < p.P;
+        const float wf = sA[(pr ? 0 : 32) + gl] * (pr ? sWp[gl * p.P + k] : sWs[gl * p.S + (k - p.P)]);
+        const int g = g0 + gl;
+        p.wfold[(long)g * KZ + k] = wf;
+        if (p.wfold_bf16) p.wfold_bf16[((long)(pr ? 0 : 1) * p.Gp + g) * p.ld_wz + p.HD + k] = __float2bfloat16(wf);
+    }
 }
 
-// ptrs: Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, cov_part, wfold, genec, zmean, zcov
+// ptrs: Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, (unused), wfold, genec, zmean, zcov
 extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, int S, int training, float eps,
                             float momentum, void* wz_bf16, long long ld_wz, int Gp, int HD, void* stream) {
     if (!ptrs || B <= 0 || G <= 0 || P <= 0 || S <= 0 || P + S > 96) return SPV_ERR_ARG;
@@ -149,26 +269,25 @@ extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int KZ = P + S;
     const float* zz = (const float*)ptrs[11];
-    const float* zsum = (const float*)ptrs[12];
-    float* cov_part = (float*)ptrs[13];
-    const int ncov = (B + 63) / 64;
     if (training) {
-        size_t sm1 = (size_t)64 * (KZ + 1) * sizeof(float);
-        zcov_kernel<<<ncov, 256, sm1, st>>>(zz, ld_zz, B, KZ, zsum, cov_part, (float*)ptrs[16], (float*)ptrs[17]);
+        size_t sm1 = (size_t)(ZS_ROWS * (KZ + 1) + 10 * KZ + KZ * KZ) * sizeof(float);
+        if (sm1 > 48 * 1024) cudaFuncSetAttribute(zstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+        zstats_kernel<<<ZS_CTAS, ZS_THREADS, sm1, st>>>(zz, ld_zz, B, KZ, (float*)ptrs[12], (float*)ptrs[16], (float*)ptrs[17]);
         SPV_CHECK_LAUNCH();
     }
     FoldP p;
-    p.Wp = (const float*)ptrs[0]; p.Ws = (const float*)ptrs[1]; p.gp = (const float*)ptrs[2]; p.bp = (const float*)ptrs[3];
-    p.gs = (const float*)ptrs[4]; p.bs = (const float*)ptrs[5]; p.px_r = (const float*)ptrs[6];
+    p.Wp = (const float*)ptrs[0]; p.Ws = (const float*)ptrs[1];
+    for (int i = 0; i < 5; ++i) p.vec[i] = (const float*)ptrs[2 + i];
+    for (int i = 0; i < 4; ++i) p.vec[5 + i] = (const float*)ptrs[7 + i];
     p.rm_p = (float*)ptrs[7]; p.rv_p = (float*)ptrs[8]; p.rm_s = (float*)ptrs[9]; p.rv_s = (float*)ptrs[10];
-    p.zsum = zsum; p.cov_part = cov_part; p.wfold = (float*)ptrs[14]; p.genec = (float*)ptrs[15];
-    p.zmean = (float*)ptrs[16]; p.zcov = (float*)ptrs[17];
+    p.wfold = (float*)ptrs[14]; p.genec = (float*)ptrs[15];
+    p.zmean = (const float*)ptrs[16]; p.zcov = (const float*)ptrs[17];
     p.wfold_bf16 = reinterpret_cast<__nv_bfloat16*>(wz_bf16);
     p.ld_wz = ld_wz; p.Gp = Gp; p.HD = HD;
-    p.G = G; p.P = P; p.S = S; p.B = B; p.ncov = training ? ncov : 0; p.training = training; p.eps = eps; p.momentum = momentum;
-    size_t sm2 = (size_t)(KZ + KZ * KZ) * sizeof(float);
+    p.G = G; p.P = P; p.S = S; p.B = B; p.training = training; p.eps = eps; p.momentum = momentum;
+    size_t sm2 = (size_t)(KZ + KZ * KZ + FOLD_GENES_PER_CTA * (2 * KZ + 11)) * sizeof(float);
     if (sm2 > 48 * 1024) cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-    fold_kernel<<<(G + FOLD_GENES_PER_CTA - 1) / FOLD_GENES_PER_CTA, 32 * FOLD_GENES_PER_CTA, sm2, st>>>(p);
+    fold_kernel<<<(G + FOLD_GENES_PER_CTA - 1) / FOLD_GENES_PER_CTA, 256, sm2, st>>>(p);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }
@@ -183,104 +302,175 @@ extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int
 // also d px_r = theta * colsum(dtheta), d bm = colsum(dpi).
 // ---------------------------------------------------------------------------------------
 struct GeneBwdP {
-    const float *Wp, *Ws, *Qp, *Qs, *genec, *colsum, *zmean, *zcov;
+    const float *Wp, *Ws, *Qp, *Qs, *zmean, *zcov;
+    const float* vec[11];  // per-gene vectors: genec a_p, a_s, invstd_p, invstd_s, mean_p, mean_s, theta; colsum rows 0..3
     float *dWp, *dWs, *dgp, *dbp, *dgs, *dbs, *dpx_r, *dbm, *vpart, *mpart;
     int G, P, S, B;
     long ldq;  // row pitch of Qp / Qs (0: packed, P resp. S)
 };
 
+// 32 genes per CTA, 256 threads.  One round of loads brings in every input; T = W C runs as one thread per (gene, latent
+// index); the per-CTA partial of M is a rank-32 update computed on its upper triangle only.
 __global__ void __launch_bounds__(GENE_BWD_THREADS) gene_bwd_kernel(GeneBwdP p) {
     extern __shared__ float sh[];
     const int KZ = p.P + p.S;
-    float* smean = sh;                         // [KZ]
-    float* scov = smean + KZ;                  // [KZ * KZ]
-    float* sW = scov + KZ * KZ;                // [64][KZ]  (private | shared weights of this CTA's genes)
-    float* scv = sW + GENES_PER_CTA * KZ;      // [2][64]
-    float* scm = scv + 2 * GENES_PER_CTA;      // [2][64]
     const int g0 = blockIdx.x * GENES_PER_CTA;
-    for (int k = threadIdx.x; k < KZ; k += blockDim.x) smean[k] = p.zmean[k];
-    for (int i = threadIdx.x; i < KZ * KZ; i += blockDim.x) scov[i] = p.zcov[i];
-    for (int i = threadIdx.x; i < GENES_PER_CTA * KZ; i += blockDim.x) {
-        int gl = i / KZ, k = i - gl * KZ, g = g0 + gl;
-        float v = 0.0f;
-        if (g < p.G) v = k < p.P ? p.Wp[(long)g * p.P + k] : p.Ws[(long)g * p.S + (k - p.P)];
-        sW[i] = v;
-    }
-    for (int i = threadIdx.x; i < 2 * GENES_PER_CTA; i += blockDim.x) { scv[i] = 0.0f; scm[i] = 0.0f; }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ng = min(GENES_PER_CTA, p.G - g0);
     const long G = p.G;
-    const float invB = 1.0f / (float)p.B;
-    for (int gl = warp; gl < GENES_PER_CTA; gl += (int)(blockDim.x >> 5)) {
-        const int g = g0 + gl;
-        if (g >= p.G) break;
+    const int pitch_p = p.ldq > 0 ? (int)p.ldq : p.P, pitch_s = p.ldq > 0 ? (int)p.ldq : p.S;
+    const int nQp = (ng - 1) * pitch_p + p.P, nQs = (ng - 1) * pitch_s + p.S;
+    float* scov = sh;                                   // [KZ][KZ]
+    float* smean = scov + KZ * KZ;                      // [KZ]
+    float* sWp = smean + KZ;                            // [32][P]
+    float* sWs = sWp + GENES_PER_CTA * p.P;             // [32][S]
+    float* sQp = sWs + GENES_PER_CTA * p.S;             // [32][pitch_p]
+    float* sQs = sQp + GENES_PER_CTA * pitch_p;         // [32][pitch_s]
+    float* svec = sQs + GENES_PER_CTA * pitch_s;        // [11][32]
+    float* sT = svec + 11 * GENES_PER_CTA;              // [32][KZ]   T = W C (block diagonal)
+    float* sc1 = sT + GENES_PER_CTA * KZ;               // [2][32]    a S2 invstd          (scale of the T term of dW)
+    float* scv = sc1 + 2 * GENES_PER_CTA;               // [2][32]    a sdy / B            (weights of v1)
+    float* scm = scv + 2 * GENES_PER_CTA;               // [2][32]    a S2 invstd / B      (weights of M)
+    {
+        StageArr<5> c, qp, qs;
+        StageArr<1> m;
+        StageArr<2> wp;
+        StageArr<4> ws;
+        float sc[2];
+        c.load(p.zcov, KZ * KZ);
+        m.load(p.zmean, KZ);
+        wp.load(p.Wp + (long)g0 * p.P, ng * p.P);
+        ws.load(p.Ws + (long)g0 * p.S, ng * p.S);
+        qp.load(p.Qp + (long)g0 * pitch_p, nQp);
+        qs.load(p.Qs + (long)g0 * pitch_s, nQs);
 #pragma unroll
-        for (int br = 0; br < 2; ++br) {
-            const int K = br == 0 ? p.P : p.S;
-            const int off = br == 0 ? 0 : p.P;
-            const float* W = sW + gl * KZ + off;
-            const float* Q = (br == 0 ? p.Qp : p.Qs) + (long)g * (p.ldq > 0 ? p.ldq : K);
-            float* dW = (br == 0 ? p.dWp : p.dWs) + (long)g * K;
-            const float a = p.genec[(br == 0 ? GC_AP : GC_AS) * G + g];
-            const float invstd = p.genec[(br == 0 ? GC_ISTD_P : GC_ISTD_S) * G + g];
-            const float mean_u = p.genec[(br == 0 ? GC_MEAN_P : GC_MEAN_S) * G + g];
-            const float sdy = p.colsum[(long)br * G + g];
-            float qw = 0.0f;
-            for (int k = lane; k < K; k += 32) qw = fmaf(Q[k], W[k], qw);
-            qw = warp_sum(qw);
-            const float S2 = (qw - sdy * mean_u) * invstd;
-            if (lane == 0) {
-                (br == 0 ? p.dgp : p.dgs)[g] = S2;
-                (br == 0 ? p.dbp : p.dbs)[g] = sdy;
-                scv[br * GENES_PER_CTA + gl] = a * sdy * invB;
-                scm[br * GENES_PER_CTA + gl] = a * S2 * invB * invstd;
-            }
-            for (int k = lane; k < K; k += 32) {
-                float cw = 0.0f;
-                for (int l = 0; l < K; ++l) cw = fmaf(scov[(off + k) * KZ + off + l], W[l], cw);
-                dW[k] = a * (Q[k] - sdy * smean[off + k] - S2 * invstd * cw);
-            }
+        for (int u = 0; u < 2; ++u) {
+            const int i = u * GENE_BWD_THREADS + (int)threadIdx.x, arr = i >> 5, gl = i & 31;
+            sc[u] = (arr < 11 && gl < ng) ? __ldg(p.vec[arr] + g0 + gl) : 0.0f;
         }
-        if (lane == 0) {
-            p.dpx_r[g] = p.genec[GC_THETA * G + g] * p.colsum[3 * G + g];
-            p.dbm[g] = p.colsum[2 * G + g];
+        c.store(scov, KZ * KZ);
+        m.store(smean, KZ);
+        wp.store(sWp, ng * p.P);
+        ws.store(sWs, ng * p.S);
+        qp.store(sQp, nQp);
+        qs.store(sQs, nQs);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = u * GENE_BWD_THREADS + (int)threadIdx.x;
+            if (i < 11 * 32) svec[i] = sc[u];
+        }
+        StageArr<5>::rest(scov, p.zcov, KZ * KZ);
+        StageArr<1>::rest(smean, p.zmean, KZ);
+        StageArr<2>::rest(sWp, p.Wp + (long)g0 * p.P, ng * p.P);
+        StageArr<4>::rest(sWs, p.Ws + (long)g0 * p.S, ng * p.S);
+        StageArr<5>::rest(sQp, p.Qp + (long)g0 * pitch_p, nQp);
+        StageArr<5>::rest(sQs, p.Qs + (long)g0 * pitch_s, nQs);
+    }
+    __syncthreads();
+    // T[gl][k] = sum_l C[k][l] W[gl][l]  (l within k's block)
+    for (int i = threadIdx.x; i < ng * KZ; i += GENE_BWD_THREADS) {
+        const int gl = i / KZ, k = i - gl * KZ;
+        const bool pr = k < p.P;
+        const int K = pr ? p.P : p.S, off = pr ? 0 : p.P;
+        const float* W = pr ? sWp + gl * p.P : sWs + gl * p.S;
+        const float* C = scov + k * KZ + off;
+        float t = 0.0f;
+#pragma unroll 5
+        for (int l = 0; l < K; ++l) t = fmaf(C[l], W[l], t);
+        sT[i] = t;
+    }
+    // per (gene, branch): S2 = (Q . W - sdy mean_u) invstd = dgamma, dbeta = sdy
+    const float invB = 1.0f / (float)p.B;
+    if (threadIdx.x < 2 * GENES_PER_CTA) {
+        const int br = threadIdx.x >> 5, gl = threadIdx.x & 31;
+        if (gl < ng) {
+            const int g = g0 + gl;
+            const int K = br == 0 ? p.P : p.S;
+            const float* W = br == 0 ? sWp + gl * p.P : sWs + gl * p.S;
+            const float* Q = br == 0 ? sQp + gl * pitch_p : sQs + gl * pitch_s;
+            const float a = svec[(0 + br) * 32 + gl], invstd = svec[(2 + br) * 32 + gl], mean_u = svec[(4 + br) * 32 + gl];
+            const float sdy = svec[(7 + br) * 32 + gl];
+            float qw = 0.0f;
+            for (int k = 0; k < K; ++k) qw = fmaf(Q[k], W[k], qw);
+            const float S2 = (qw - sdy * mean_u) * invstd;
+            (br == 0 ? p.dgp : p.dgs)[g] = S2;
+            (br == 0 ? p.dbp : p.dbs)[g] = sdy;
+            sc1[br * 32 + gl] = a * S2 * invstd;
+            scv[br * 32 + gl] = a * sdy * invB;
+            scm[br * 32 + gl] = a * S2 * invB * invstd;
+        } else {
+            sc1[br * 32 + gl] = 0.0f; scv[br * 32 + gl] = 0.0f; scm[br * 32 + gl] = 0.0f;
+        }
+    } else if (threadIdx.x < 3 * GENES_PER_CTA) {
+        const int gl = threadIdx.x - 2 * GENES_PER_CTA;
+        if (gl < ng) {
+            p.dpx_r[g0 + gl] = svec[6 * 32 + gl] * svec[10 * 32 + gl];  // theta * colsum(d theta)
+            p.dbm[g0 + gl] = svec[9 * 32 + gl];                         // colsum(d pi)
         }
     }
     __syncthreads();
-    // per-CTA partials of v1 and M
-    for (int c = threadIdx.x; c < KZ; c += blockDim.x) {
-        const float* cv = scv + (c < p.P ? 0 : GENES_PER_CTA);
+    // dW[g, k] = a (Q[g, k] - sdy zbar[k]) - (a S2 invstd) T[g, k]
+    for (int i = threadIdx.x; i < ng * KZ; i += GENE_BWD_THREADS) {
+        const int gl = i / KZ, k = i - gl * KZ;
+        const bool pr = k < p.P;
+        const int br = pr ? 0 : 1, kr = pr ? k : k - p.P;
+        const float a = svec[br * 32 + gl], sdy = svec[(7 + br) * 32 + gl];
+        const float q = pr ? sQp[gl * pitch_p + kr] : sQs[gl * pitch_s + kr];
+        const float v = a * (q - sdy * smean[k]) - sc1[br * 32 + gl] * sT[i];
+        (pr ? p.dWp + (long)(g0 + gl) * p.P : p.dWs + (long)(g0 + gl) * p.S)[kr] = v;
+    }
+    // per-CTA partials: v1[c] = sum_g cv[g] W[g, c];  M[k, l] = sum_g cm[g] W[g, k] W[g, l] (symmetric: upper triangle, mirrored)
+    for (int c = threadIdx.x; c < KZ; c += GENE_BWD_THREADS) {
+        const bool pr = c < p.P;
+        const float* cv = scv + (pr ? 0 : 32);
+        const float* Wc = pr ? sWp + c : sWs + (c - p.P);
+        const int K = pr ? p.P : p.S;
         float s = 0.0f;
-        for (int gl = 0; gl < GENES_PER_CTA; ++gl) s = fmaf(cv[gl], sW[gl * KZ + c], s);
+        for (int gl = 0; gl < ng; ++gl) s = fmaf(cv[gl], Wc[gl * K], s);
         p.vpart[(long)blockIdx.x * KZ + c] = s;
     }
-    const int nPP = p.P * p.P, nSS = p.S * p.S;
-    for (int idx = threadIdx.x; idx < nPP + nSS; idx += blockDim.x) {
-        int k, l;
-        const float* cm;
-        if (idx < nPP) { k = idx / p.P; l = idx - k * p.P; cm = scm; }
-        else { int j = idx - nPP; k = p.P + j / p.S; l = p.P + j % p.S; cm = scm + GENES_PER_CTA; }
+    const int nP = p.P * (p.P + 1) / 2, nS = p.S * (p.S + 1) / 2;
+    for (int idx = threadIdx.x; idx < nP + nS; idx += GENE_BWD_THREADS) {
+        const bool pr = idx < nP;
+        const int K = pr ? p.P : p.S, o = pr ? 0 : p.P;
+        int j = pr ? idx : idx - nP;
+        // (k, l) with k <= l from the triangular index j = k K - k (k - 1) / 2 + (l - k)
+        int k = 0;
+        while (j >= K - k) { j -= K - k; ++k; }
+        const int l = k + j;
+        const float* cm = scm + (pr ? 0 : 32);
+        const float* Wb = pr ? sWp : sWs;
         float s = 0.0f;
-        for (int gl = 0; gl < GENES_PER_CTA; ++gl) s = fmaf(cm[gl] * sW[gl * KZ + k], sW[gl * KZ + l], s);
-        p.mpart[(long)blockIdx.x * KZ * KZ + k * KZ + l] = s;
+#pragma unroll 4
+        for (int gl = 0; gl < ng; ++gl) s = fmaf(cm[gl] * Wb[gl * K + k], Wb[gl * K + l], s);
+        float* M = p.mpart + (long)blockIdx.x * KZ * KZ;
+        M[(o + k) * KZ + o + l] = s;
+        M[(o + l) * KZ + o + k] = s;
     }
 }
 
+extern "C" int spv_dec_gene_bwd_parts(int G) { return G > 0 ? (G + GENES_PER_CTA - 1) / GENES_PER_CTA : 0; }
+
 // ptrs: Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm,
-//       vpart [ceil(G/64), KZ], mpart [ceil(G/64), KZ*KZ]
+//       vpart [parts, KZ], mpart [parts, KZ*KZ]   with parts = spv_dec_gene_bwd_parts(G)
 extern "C" int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, int G, int P, int S, void* stream) {
     if (!ptrs || B <= 0 || G <= 0 || P <= 0 || S <= 0 || P + S > 96) return SPV_ERR_ARG;
     for (int i = 0; i < 18; ++i)
         if (!ptrs[i]) return SPV_ERR_ARG;
     GeneBwdP p;
     p.Wp = (const float*)ptrs[0]; p.Ws = (const float*)ptrs[1]; p.Qp = (const float*)ptrs[2]; p.Qs = (const float*)ptrs[3];
-    p.genec = (const float*)ptrs[4]; p.colsum = (const float*)ptrs[5]; p.zmean = (const float*)ptrs[6];
+    const float* genec = (const float*)ptrs[4];
+    const float* colsum = (const float*)ptrs[5];
+    const int gc_rows[7] = {GC_AP, GC_AS, GC_ISTD_P, GC_ISTD_S, GC_MEAN_P, GC_MEAN_S, GC_THETA};
+    for (int i = 0; i < 7; ++i) p.vec[i] = genec + (long)gc_rows[i] * G;
+    for (int i = 0; i < 4; ++i) p.vec[7 + i] = colsum + (long)i * G;
+    p.zmean = (const float*)ptrs[6];
     p.zcov = (const float*)ptrs[7]; p.dWp = (float*)ptrs[8]; p.dWs = (float*)ptrs[9]; p.dgp = (float*)ptrs[10];
     p.dbp = (float*)ptrs[11]; p.dgs = (float*)ptrs[12]; p.dbs = (float*)ptrs[13]; p.dpx_r = (float*)ptrs[14];
     p.dbm = (float*)ptrs[15]; p.vpart = (float*)ptrs[16]; p.mpart = (float*)ptrs[17];
     p.G = G; p.P = P; p.S = S; p.B = B; p.ldq = ldq;
     const int KZ = P + S;
-    size_t smem = (size_t)(KZ + KZ * KZ + GENES_PER_CTA * KZ + 4 * GENES_PER_CTA) * sizeof(float);
+    const int pitch = ldq > 0 ? (int)ldq : (P > S ? P : S);
+    size_t smem = (size_t)(KZ + KZ * KZ + GENES_PER_CTA * (2 * KZ + 2 * pitch + 11 + 6)) * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(gene_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     gene_bwd_kernel<<<(G + GENES_PER_CTA - 1) / GENES_PER_CTA, GENE_BWD_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     SPV_CHECK_LAUNCH();

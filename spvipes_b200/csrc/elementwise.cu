@@ -106,6 +106,11 @@ __device__ __forceinline__ float col_reduce(float v, float (*red)[BN_TX]) {
     return s;
 }
 
+// CACHED (B <= BN_TY * BN_R): a thread's rows of the column stay in registers, so the column is read from global memory
+// once, with all loads in flight together, instead of once per pass (sum, centred squares, normalise): these kernels are
+// bound by the chain of dependent memory round trips, not by bandwidth.
+#define BN_R 16
+template <bool CACHED>
 __global__ void __launch_bounds__(BN_TX* BN_TY) bn_fwd_kernel(const float* __restrict__ x, long ldx, float* __restrict__ y,
                                                                long ldy, int B, int C, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float eps, float momentum,
@@ -116,22 +121,42 @@ __global__ void __launch_bounds__(BN_TX* BN_TY) bn_fwd_kernel(const float* __res
     const int tx = threadIdx.x % BN_TX, ty = threadIdx.x / BN_TX;
     const int c = blockIdx.x * BN_TX + tx;
     const bool ok = c < C;
-    float mean, var;
+    float xv[CACHED ? BN_R : 1];
+    if (CACHED) {
+#pragma unroll
+        for (int r = 0; r < BN_R; ++r) {
+            const int b = ty + r * BN_TY;
+            xv[r] = (ok && b < B) ? x[(long)b * ldx + c] : 0.0f;
+        }
+    }
+    const float g = ok ? gamma[c] : 0.0f, bt = ok ? beta[c] : 0.0f;
+    const float rmean = ok ? running_mean[c] : 0.0f, rvar = ok ? running_var[c] : 1.0f;
+    float mean = rmean, var = rvar;
     if (training) {
         float s = 0.0f;
-        if (ok) for (int b = ty; b < B; b += BN_TY) s += x[(long)b * ldx + c];
+        if (CACHED) {
+#pragma unroll
+            for (int r = 0; r < BN_R; ++r) s += xv[r];
+        } else if (ok) {
+            for (int b = ty; b < B; b += BN_TY) s += x[(long)b * ldx + c];
+        }
         mean = col_reduce(s, red) / (float)B;
         float q = 0.0f;
-        if (ok) for (int b = ty; b < B; b += BN_TY) { float d = x[(long)b * ldx + c] - mean; q += d * d; }
+        if (CACHED) {
+#pragma unroll
+            for (int r = 0; r < BN_R; ++r) {
+                const float d = xv[r] - mean;
+                if (ty + r * BN_TY < B) q += d * d;
+            }
+        } else if (ok) {
+            for (int b = ty; b < B; b += BN_TY) { float d = x[(long)b * ldx + c] - mean; q += d * d; }
+        }
         var = col_reduce(q, red) / (float)B;  // biased, used for normalisation
         if (ok && ty == 0) {
             float unb = var * ((float)B / (float)max(B - 1, 1));
-            running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean;
-            running_var[c] = (1.0f - momentum) * running_var[c] + momentum * unb;
+            running_mean[c] = (1.0f - momentum) * rmean + momentum * mean;
+            running_var[c] = (1.0f - momentum) * rvar + momentum * unb;
         }
-    } else {
-        mean = ok ? running_mean[c] : 0.0f;
-        var = ok ? running_var[c] : 1.0f;
     }
     if (!ok) return;
     float invstd = 1.0f / sqrtf(var + eps);
@@ -139,11 +164,20 @@ __global__ void __launch_bounds__(BN_TX* BN_TY) bn_fwd_kernel(const float* __res
         if (save_mean) save_mean[c] = mean;
         if (save_invstd) save_invstd[c] = invstd;
     }
-    float g = gamma[c], bt = beta[c];
-    for (int b = ty; b < B; b += BN_TY) {
-        float v = (x[(long)b * ldx + c] - mean) * invstd * g + bt;
-        if (relu) v = fmaxf(v, 0.0f);
-        y[(long)b * ldy + c] = v;
+    if (CACHED) {
+#pragma unroll
+        for (int r = 0; r < BN_R; ++r) {
+            const int b = ty + r * BN_TY;
+            float v = (xv[r] - mean) * invstd * g + bt;
+            if (relu) v = fmaxf(v, 0.0f);
+            if (b < B) y[(long)b * ldy + c] = v;
+        }
+    } else {
+        for (int b = ty; b < B; b += BN_TY) {
+            float v = (x[(long)b * ldx + c] - mean) * invstd * g + bt;
+            if (relu) v = fmaxf(v, 0.0f);
+            y[(long)b * ldy + c] = v;
+        }
     }
 }
 
@@ -151,13 +185,20 @@ extern "C" int spv_bn_fwd(const float* x, long long ldx, float* y, long long ldy
                           const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                           float* save_mean, float* save_invstd, int training, int relu, void* stream) {
     if (!x || !y || !gamma || !beta || !running_mean || !running_var || B <= 0 || C <= 0) return SPV_ERR_ARG;
-    bn_fwd_kernel<<<(C + BN_TX - 1) / BN_TX, BN_TX * BN_TY, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        x, ldx, y, ldy, B, C, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_invstd, training, relu);
+    const dim3 grid((C + BN_TX - 1) / BN_TX), block(BN_TX * BN_TY);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (B <= BN_TY * BN_R)
+        bn_fwd_kernel<true><<<grid, block, 0, st>>>(x, ldx, y, ldy, B, C, gamma, beta, eps, momentum, running_mean, running_var,
+                                                    save_mean, save_invstd, training, relu);
+    else
+        bn_fwd_kernel<false><<<grid, block, 0, st>>>(x, ldx, y, ldy, B, C, gamma, beta, eps, momentum, running_mean, running_var,
+                                                     save_mean, save_invstd, training, relu);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }
 
 // training-mode backward.  y_relu != null: the forward applied ReLU after the affine; dy is masked by y_relu > 0.
+template <bool CACHED>
 __global__ void __launch_bounds__(BN_TX* BN_TY) bn_bwd_kernel(const float* __restrict__ dy, long lddy, const float* __restrict__ x,
                                                                long ldx, const float* __restrict__ y_relu, long ldy,
                                                                float* __restrict__ dx, long lddx, int B, int C,
@@ -168,16 +209,40 @@ __global__ void __launch_bounds__(BN_TX* BN_TY) bn_bwd_kernel(const float* __res
     const int tx = threadIdx.x % BN_TX, ty = threadIdx.x / BN_TX;
     const int c = blockIdx.x * BN_TX + tx;
     const bool ok = c < C;
-    float mean = ok ? save_mean[c] : 0.0f, invstd = ok ? save_invstd[c] : 0.0f;
+    float dv[CACHED ? BN_R : 1], xh[CACHED ? BN_R : 1];
+    if (CACHED) {
+        float yr[BN_R];
+#pragma unroll
+        for (int r = 0; r < BN_R; ++r) {
+            const int b = ty + r * BN_TY;
+            const bool in = ok && b < B;
+            dv[r] = in ? dy[(long)b * lddy + c] : 0.0f;
+            xh[r] = in ? x[(long)b * ldx + c] : 0.0f;
+            yr[r] = (in && y_relu) ? y_relu[(long)b * ldy + c] : 1.0f;
+        }
+#pragma unroll
+        for (int r = 0; r < BN_R; ++r)
+            if (!(yr[r] > 0.0f)) dv[r] = 0.0f;
+    }
+    const float mean = ok ? save_mean[c] : 0.0f, invstd = ok ? save_invstd[c] : 0.0f;
+    const float gam = ok ? gamma[c] : 0.0f;
     float s1 = 0.0f, s2 = 0.0f;
-    if (ok)
+    if (CACHED) {
+#pragma unroll
+        for (int r = 0; r < BN_R; ++r) {
+            xh[r] = (ty + r * BN_TY < B) ? (xh[r] - mean) * invstd : 0.0f;
+            s1 += dv[r];
+            s2 += dv[r] * xh[r];
+        }
+    } else if (ok) {
         for (int b = ty; b < B; b += BN_TY) {
             float d = dy[(long)b * lddy + c];
             if (y_relu && !(y_relu[(long)b * ldy + c] > 0.0f)) d = 0.0f;
-            float xh = (x[(long)b * ldx + c] - mean) * invstd;
+            float xhat = (x[(long)b * ldx + c] - mean) * invstd;
             s1 += d;
-            s2 += d * xh;
+            s2 += d * xhat;
         }
+    }
     s1 = col_reduce(s1, red);
     s2 = col_reduce(s2, red);
     if (!ok) return;
@@ -185,12 +250,20 @@ __global__ void __launch_bounds__(BN_TX* BN_TY) bn_bwd_kernel(const float* __res
         dgamma[c] = s2;
         dbeta[c] = s1;
     }
-    float g = gamma[c] * invstd, m1 = s1 / (float)B, m2 = s2 / (float)B;
-    for (int b = ty; b < B; b += BN_TY) {
-        float d = dy[(long)b * lddy + c];
-        if (y_relu && !(y_relu[(long)b * ldy + c] > 0.0f)) d = 0.0f;
-        float xh = (x[(long)b * ldx + c] - mean) * invstd;
-        dx[(long)b * lddx + c] = g * (d - m1 - xh * m2);
+    float g = gam * invstd, m1 = s1 / (float)B, m2 = s2 / (float)B;
+    if (CACHED) {
+#pragma unroll
+        for (int r = 0; r < BN_R; ++r) {
+            const int b = ty + r * BN_TY;
+            if (b < B) dx[(long)b * lddx + c] = g * (dv[r] - m1 - xh[r] * m2);
+        }
+    } else {
+        for (int b = ty; b < B; b += BN_TY) {
+            float d = dy[(long)b * lddy + c];
+            if (y_relu && !(y_relu[(long)b * ldy + c] > 0.0f)) d = 0.0f;
+            float xhat = (x[(long)b * ldx + c] - mean) * invstd;
+            dx[(long)b * lddx + c] = g * (d - m1 - xhat * m2);
+        }
     }
 }
 
@@ -198,8 +271,14 @@ extern "C" int spv_bn_bwd(const float* dy, long long lddy, const float* x, long 
                           float* dx, long long lddx, int B, int C, const float* gamma, const float* save_mean,
                           const float* save_invstd, float* dgamma, float* dbeta, void* stream) {
     if (!dy || !x || !dx || !gamma || !save_mean || !save_invstd || !dgamma || !dbeta || B <= 0 || C <= 0) return SPV_ERR_ARG;
-    bn_bwd_kernel<<<(C + BN_TX - 1) / BN_TX, BN_TX * BN_TY, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dy, lddy, x, ldx, y_relu, ldy, dx, lddx, B, C, gamma, save_mean, save_invstd, dgamma, dbeta);
+    const dim3 grid((C + BN_TX - 1) / BN_TX), block(BN_TX * BN_TY);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (B <= BN_TY * BN_R)
+        bn_bwd_kernel<true><<<grid, block, 0, st>>>(dy, lddy, x, ldx, y_relu, ldy, dx, lddx, B, C, gamma, save_mean, save_invstd,
+                                                    dgamma, dbeta);
+    else
+        bn_bwd_kernel<false><<<grid, block, 0, st>>>(dy, lddy, x, ldx, y_relu, ldy, dx, lddx, B, C, gamma, save_mean, save_invstd,
+                                                     dgamma, dbeta);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }
@@ -209,7 +288,10 @@ __global__ void __launch_bounds__(BN_TX* BN_TY) colsum_kernel(const float* __res
     const int tx = threadIdx.x % BN_TX, ty = threadIdx.x / BN_TX;
     const int c = blockIdx.x * BN_TX + tx;
     float s = 0.0f;
-    if (c < C) for (int b = ty; b < B; b += BN_TY) s += x[(long)b * ldx + c];
+    if (c < C) {
+#pragma unroll 8
+        for (int b = ty; b < B; b += BN_TY) s += x[(long)b * ldx + c];
+    }
     s = col_reduce(s, red);
     if (c < C && ty == 0) out[c] = s;
 }

@@ -81,6 +81,153 @@ __global__ void splitk_reduce_kernel(GemmParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Whole-K variant for the small dense layers of the step (K <= 256: encoder fc2 and heads, the mixing net's hidden layer
+// and their input gradients).  These are 512-row problems of a few MFLOP, so what matters is (a) how many SMs share
+// the work and (b) how few dependent memory round trips a CTA makes: 8 x 64 output tiles (64 .. 256 CTAs), both operand
+// tiles brought into shared memory with all global loads of a thread in flight together (at most two rounds), 128 threads,
+// 1 x 4 outputs per thread.  fp32, A stored [M][K]; B stored [N][K] (TB) or [K][N].
+// (ncu, r1: the 32 x 64-tile / 256-thread first version spent 2550 instructions per warp on 16 SMs, 9-12 us per launch.)
+// ---------------------------------------------------------------------------------------
+#define SK_BM 8
+#define SK_BN 64
+#define SK_MAXK 256
+#define SK_THREADS 128
+#define SK_ROUND 16  // float4 loads in flight per thread and round
+
+// One round of staging of a [rows][cols4 * 4] float tile (zero filled outside rows_valid x cols_valid): U float4 per
+// thread starting at element `base`, loaded into registers by load() and written to shared memory by store(), so that the
+// caller can put the loads of several tiles in flight before the first store.
+template <int U>
+struct SkRound {
+    float4 v[U];
+    __device__ __forceinline__ void load(int base, const float* __restrict__ src, long ld, int rows, int rows_valid, int cols4,
+                                         int cols_valid) {
+        const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((ld & 3) == 0);
+        const int dq = SK_THREADS / cols4, dr = SK_THREADS - dq * cols4;  // (r, c4) advance per SK_THREADS elements
+        const int i0 = base + (int)threadIdx.x;
+        int rr = i0 / cols4, cc = i0 - rr * cols4;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = cc * 4;
+            const bool in = rr < rows_valid && rr < rows;
+            const float* g = src + (long)(in ? rr : 0) * ld + c;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec && c + 4 <= cols_valid) {
+                if (in) x = __ldg(reinterpret_cast<const float4*>(g));
+            } else {
+                if (in && c < cols_valid) x.x = __ldg(g);
+                if (in && c + 1 < cols_valid) x.y = __ldg(g + 1);
+                if (in && c + 2 < cols_valid) x.z = __ldg(g + 2);
+                if (in && c + 3 < cols_valid) x.w = __ldg(g + 3);
+            }
+            v[u] = x;
+            rr += dq; cc += dr;
+            if (cc >= cols4) { cc -= cols4; ++rr; }
+        }
+    }
+    __device__ __forceinline__ void store(int base, float* dst, int ldd, int rows, int cols4) const {
+        const int dq = SK_THREADS / cols4, dr = SK_THREADS - dq * cols4;
+        const int i0 = base + (int)threadIdx.x;
+        int r = i0 / cols4, c4 = i0 - r * cols4;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (r < rows) *reinterpret_cast<float4*>(dst + r * ldd + c4 * 4) = v[u];
+            r += dq; c4 += dr;
+            if (c4 >= cols4) { c4 -= cols4; ++r; }
+        }
+    }
+};
+
+template <bool TB>
+__global__ void __launch_bounds__(SK_THREADS) gemm_smallk_kernel(GemmParams p) {
+    extern __shared__ __align__(16) float sk_smem[];
+    const int K4 = (p.K + 3) / 4, Kp = K4 * 4;
+    const int lda_s = Kp + 4;                   // A tile [SK_BM][Kp + 4]
+    const int ldb_s = TB ? Kp + 4 : SK_BN + 4;  // B tile [SK_BN][Kp + 4] (TB) or [Kp][SK_BN + 4]
+    float* As = sk_smem;
+    float* Bs = sk_smem + SK_BM * lda_s;
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.y * SK_BM, n0 = blockIdx.x * SK_BN;
+    const int nvalid = min(SK_BN, p.N - n0);
+    const float* A = reinterpret_cast<const float*>(p.A) + (size_t)b * p.sA + (size_t)m0 * p.lda;
+    const float* B = reinterpret_cast<const float*>(p.B) + (size_t)b * p.sB;
+    {
+        // B tile: rows x cols4 float4;  A tile: SK_BM x K4 float4 (<= 4 per thread).  First round: A and B loads together.
+        const float* Bsrc = TB ? B + (size_t)n0 * p.ldb : B + n0;
+        const int b_rows = TB ? SK_BN : Kp, b_rows_valid = TB ? nvalid : p.K;
+        const int b_cols4 = TB ? K4 : SK_BN / 4, b_cols_valid = TB ? p.K : nvalid;
+        const int b_total = b_rows * b_cols4;
+        SkRound<SK_BM * SK_MAXK / 4 / SK_THREADS> ra;
+        SkRound<SK_ROUND> rb;
+        ra.load(0, A, p.lda, SK_BM, min(SK_BM, p.M - m0), K4, p.K);
+        rb.load(0, Bsrc, p.ldb, b_rows, b_rows_valid, b_cols4, b_cols_valid);
+        ra.store(0, As, lda_s, SK_BM, K4);
+        rb.store(0, Bs, ldb_s, b_rows, b_cols4);
+        for (int base = SK_ROUND * SK_THREADS; base < b_total; base += SK_ROUND * SK_THREADS) {
+            rb.load(base, Bsrc, p.ldb, b_rows, b_rows_valid, b_cols4, b_cols_valid);
+            rb.store(base, Bs, ldb_s, b_rows, b_cols4);
+        }
+    }
+    __syncthreads();
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;  // row ty; columns tx + 16 j (TB) or 4 tx + j
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* a0 = As + ty * lda_s;
+#pragma unroll 2
+    for (int k = 0; k < Kp; k += 4) {
+        const float4 x0 = *reinterpret_cast<const float4*>(a0 + k);
+        const float xa[4] = {x0.x, x0.y, x0.z, x0.w};
+        float wv[4][4];  // [kk][j]
+        if (TB) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 w4 = *reinterpret_cast<const float4*>(Bs + (tx + 16 * j) * ldb_s + k);
+                wv[0][j] = w4.x; wv[1][j] = w4.y; wv[2][j] = w4.z; wv[3][j] = w4.w;
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 w4 = *reinterpret_cast<const float4*>(Bs + (k + kk) * ldb_s + tx * 4);
+                wv[kk][0] = w4.x; wv[kk][1] = w4.y; wv[kk][2] = w4.z; wv[kk][3] = w4.w;
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fmaf(xa[kk], wv[kk][j], acc[j]);
+    }
+    float* C = p.C + (size_t)b * p.sC;
+    const float* bias = p.bias ? p.bias + (size_t)b * p.sBias : nullptr;
+    const int m = m0 + ty;
+    if (m >= p.M) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + (TB ? tx + 16 * j : tx * 4 + j);
+        if (n >= p.N) continue;
+        float v = acc[j];
+        if (bias) v += __ldg(bias + n);
+        if (p.relu) v = fmaxf(v, 0.0f);
+        float* c = C + (size_t)m * p.ldc + n;
+        *c = p.accumulate ? (*c + v) : v;
+    }
+}
+
+template <bool TB>
+static int launch_smallk(const GemmParams& p, cudaStream_t st) {
+    const int Kp = (p.K + 3) / 4 * 4;
+    const size_t smem = sizeof(float) * ((size_t)SK_BM * (Kp + 4) + (TB ? (size_t)SK_BN * (Kp + 4) : (size_t)Kp * (SK_BN + 4)));
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        if (cudaFuncSetAttribute(gemm_smallk_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return SPV_ERR_LAUNCH;
+        configured = smem;
+    }
+    dim3 grid((p.N + SK_BN - 1) / SK_BN, (p.M + SK_BM - 1) / SK_BM, p.batch);
+    gemm_smallk_kernel<TB><<<grid, SK_THREADS, smem, st>>>(p);
+    SPV_CHECK_LAUNCH();
+    return SPV_OK;
+}
+
 template <int SRC_A, bool TA, int SRC_B, bool TB>
 static int launch(const GemmParams& p, cudaStream_t st) {
     dim3 grid((p.N + GT_BN - 1) / GT_BN, (p.M + GT_BM - 1) / GT_BM, p.batch * p.splits);
@@ -113,6 +260,8 @@ extern "C" int spv_gemm(int srcA, int transA, int srcB, int transB, const void* 
     p.splits = splits; p.kchunk = kchunk;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool ta = transA != 0, tb = transB != 0;
+    if (srcA == SPV_SRC_F32 && srcB == SPV_SRC_F32 && !ta && !rowsA && !rowsB && splits == 1 && K > 0 && K <= SK_MAXK)
+        return tb ? launch_smallk<true>(p, st) : launch_smallk<false>(p, st);
     if (srcA == SPV_SRC_F32 && srcB == SPV_SRC_F32) {
         if (!ta && tb) return launch<SPV_SRC_F32, false, SPV_SRC_F32, true>(p, st);
         if (!ta && !tb) return launch<SPV_SRC_F32, false, SPV_SRC_F32, false>(p, st);

@@ -241,6 +241,7 @@ __global__ void rownb_tc_kernel(const float* __restrict__ part, int nPart, int B
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= B) return;
     float ll = 0.0f, dp = 0.0f, ds = 0.0f;
+#pragma unroll 8
     for (int t = lane; t < nPart; t += 32) {
         const float* o = part + ((long)t * B + b) * 3;
         ll += o[0]; dp += o[1]; ds += o[2];

@@ -214,7 +214,8 @@ class _GroupWS:
             self.colpart, self.colsum = f(self.nTB, 4, G), f(4, G)
             self.Qp, self.Qs = f(G, P), f(G, S)
             self.damix, self.dzraw, self.dzz = f(B, KMIX), f(B, KZ), f(B, KZ)
-            self.vpart, self.mpart = f(self.nTG, KZ), f(self.nTG, KZ * KZ)  # per 64-gene CTA partials (spv_dec_gene_bwd)
+            self.nGB = L.load().spv_dec_gene_bwd_parts(G)
+            self.vpart, self.mpart = f(self.nGB, KZ), f(self.nGB, KZ * KZ)  # per-CTA partials of spv_dec_gene_bwd
             self.dah = f(B, HD)
             self.dstats, self.dr = f(B, NST), f(B, NST)
             self.g_own, self.g_contrib, self.dexpert = f(B, 2 * S), f(B, 2 * S), f(B, 2 * S)
@@ -436,7 +437,6 @@ class StepEngine:
             G, B = d.genes[g], Bs[g]
             src, xptr, ldx = srcs[g]
             zzp = w.amix.data_ptr() + 4 * HD
-            L.check(lib.spv_colsum(zzp, KMIX, B, KZ, L.ptr(w.zsum), st), "spv_colsum")
             fold = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), self.P(g, "gp"), self.P(g, "bp"), self.P(g, "gs"),
                                 self.P(g, "bs"), self.P(g, "px_r"), self.Bf(g, "rm_p"), self.Bf(g, "rv_p"),
                                 self.Bf(g, "rm_s"), self.Bf(g, "rv_s"), zzp, w.zsum, w.cov_part, w.wfold, w.genec, w.zmean,
@@ -628,7 +628,7 @@ class StepEngine:
             L.check(lib.spv_dec_gene_bwd(gb, ldq, B, G, P, S, st), "spv_dec_gene_bwd")
             self._join(g, "hid")
             L.check(lib.spv_dec_dzz_combine(w.damix.data_ptr() + 4 * HD, KMIX, dzraw, L.ptr(w.vpart), L.ptr(w.mpart),
-                                            w.nTG, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S, st), "spv_dec_dzz_combine")
+                                            w.nGB, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S, st), "spv_dec_dzz_combine")
         # ---------------- PoE
         own = self._poe_sides(ws)
         arrs = []
