@@ -41,69 +41,130 @@ __device__ __forceinline__ float digamma_pos_fast(float x) {
     return fast_log(y) - 0.5f * iy - s - fast_div(dp, pr);
 }
 
+// ---- SFU economy ------------------------------------------------------------------------------------------------
+// MUFU (ex2 / lg2 / rcp) issues at 1/8 of the FP32 rate, and the r1 ncu captures show these kernels bound by issue slots
+// and the XU pipe, not by memory.  Three rewrites, all within the 1e-2 gate of this path (their error is ~1e-6):
+//  * k reciprocals from ONE rcp of the running product plus 3 (k - 1) multiplies;
+//  * log(rho + eps) without a logarithm: rho = exp(x) was just computed from x, so log(rho + eps) = x - log(1 - w) with
+//    w = eps / (rho + eps), a two-term series unless rho < ~1e-6 (then the plain lg2 form, a rarely taken branch);
+//  * nothing is gated on t != 0: every t-dependent term vanishes at t = 0 by itself, so the code is branch free.
+// t = log1p(count) and lgamma(t + 1) come from a per-CTA table over the integer count (uint16 sources).
+__device__ __forceinline__ void batch_rcp4(float a, float b, float c, float d, float& ia, float& ib, float& ic, float& id) {
+    const float ab = a * b, abc = ab * c;
+    float r = fast_rcp(abc * d);
+    id = r * abc; r *= d;
+    ic = r * ab;  r *= c;
+    ib = r * a;   ia = r * b;
+}
+__device__ __forceinline__ void batch_rcp2(float a, float b, float& ia, float& ib) {
+    const float r = fast_rcp(a * b);
+    ia = r * b; ib = r * a;
+}
+// log(rho + eps) given x = log(rho), ap = rho + eps and iap = 1 / ap
+__device__ __forceinline__ float log_rho_eps(float x, float ap, float iap) {
+    const float w = NB_EPS * iap;
+    float v = x + w * fmaf(0.5f, w, 1.0f);
+    if (w > 0.01f) v = fast_log(ap);
+    return v;
+}
+
 struct NbGrad { float dyp, dys, dpi, dth; };
 
-// gradients of loss w.r.t. the two softmax logits, the mixture logit and theta for one (cell, gene) element.
-// Dp / Ds: this cell's row sums of d ll / d rho * rho (from the forward), inv_elib = exp(-lib), scale = d loss / d ll.
-__device__ __forceinline__ NbGrad nb_backward_fast(float t, float lp, float ls, float pi, float th, float lte, float dgt, float Rp,
-                                                   float Rs, float Dp, float Ds, float inv_elib, float scale) {
-    float rp = fast_exp(lp + Rp), rs = fast_exp(ls + Rs);
-    float d1 = th + rp + NB_EPS, d2 = th + rs + NB_EPS;
-    float l1 = fast_log(d1), l2 = fast_log(d2);
-    float diff = th * (l2 - l1) + pi;  // log_nb_p - (log_nb_s - pi); the lgamma terms cancel
-    float gp = 0.0f, gs = 0.0f, dg = 0.0f;
-    if (t != 0.0f) {
-        diff += t * (fast_log(rp + NB_EPS) - l1 - fast_log(rs + NB_EPS) + l2);
-        gp = fast_div(t, rp + NB_EPS);
-        gs = fast_div(t, rs + NB_EPS);
-        dg = digamma_pos_fast(t + th) - dgt;
+// as nb_backward_fast; thr = theta / (theta + eps) (per-gene constant)
+__device__ __forceinline__ NbGrad nb_backward_fast2(float t, float lp, float ls, float pi, float th, float lte, float dgt,
+                                                    float thr, float Rp, float Rs, float Dp, float Ds, float inv_elib, float scale) {
+    const float xp = lp + Rp, xs = ls + Rs;
+    const float rp = fast_exp(xp), rs = fast_exp(xs);
+    const float ap = rp + NB_EPS, as = rs + NB_EPS;
+    const float d1 = th + ap, d2 = th + as;
+    float iap, ias, id1, id2;
+    batch_rcp4(ap, as, d1, d2, iap, ias, id1, id2);
+    const float l1 = fast_log(d1), l2 = fast_log(d2);
+    const float lrp = log_rho_eps(xp, ap, iap), lrs = log_rho_eps(xs, as, ias);
+    const float diff = th * (l2 - l1) + pi + t * (lrp - l1 - lrs + l2);  // log_nb_p - (log_nb_s - pi); the lgamma terms cancel
+    // digamma(t + theta) - digamma(theta): recurrence over 6 terms (P'/P) + asymptotic series at y = x + 6
+    const float x = t + th;
+    float pr = x, dp = 1.0f;
+#pragma unroll
+    for (int i = 1; i < 6; ++i) {
+        const float xi = x + (float)i;
+        dp = fmaf(dp, xi, pr);
+        pr *= xi;
     }
-    float e = fast_exp(-fabsf(diff));
-    float wmin = fast_div(e, 1.0f + e);
-    float wa = diff >= 0.0f ? 1.0f - wmin : wmin, wb = 1.0f - wa;
-    float q1 = fast_div(th + t, d1), q2 = fast_div(th + t, d2);
-    float ep = wa * (gp - q1) * rp, es = wb * (gs - q2) * rs;
-    float epi = fast_exp(-fabsf(pi));
-    float sneg = fast_div(pi >= 0.0f ? epi : 1.0f, 1.0f + epi);  // sigmoid(-pi)
+    const float y = x + 6.0f;
+    float iy, ipr;
+    batch_rcp2(y, pr, iy, ipr);
+    const float iy2 = iy * iy;
+    const float dg = fast_log(y) - 0.5f * iy - iy2 * (0.083333333f - iy2 * (0.0083333333f - iy2 * 0.003968254f)) - dp * ipr - dgt;
+    const float e = fast_exp(-fabsf(diff)), epi = fast_exp(-fabsf(pi));
+    float i1, i2;
+    batch_rcp2(1.0f + e, 1.0f + epi, i1, i2);
+    const float wmin = e * i1;
+    const float wa = diff >= 0.0f ? 1.0f - wmin : wmin, wb = 1.0f - wa;
+    const float tt = th + t;
+    const float q1 = tt * id1, q2 = tt * id2;
+    const float gp = t * iap, gs = t * ias;
+    const float ep = wa * (gp - q1) * rp, es = wb * (gs - q2) * rs;
+    const float sneg = (pi >= 0.0f ? epi : 1.0f) * i2;  // sigmoid(-pi)
     NbGrad o;
     o.dyp = scale * (ep - rp * inv_elib * Dp);
     o.dys = scale * (es - rs * inv_elib * Ds);
     o.dpi = scale * (sneg - wb);
-    o.dth = scale * (wa * (lte - l1 - q1) + wb * (lte - l2 - q2) + fast_div(th, th + NB_EPS) + dg);
+    o.dth = scale * (wa * (lte - l1 - q1) + wb * (lte - l2 - q2) + thr + dg);
     return o;
 }
 
 struct NbOut { float ll, ep, es; };
 
-// t = log1p(count); lp / ls = BatchNorm'd softmax logits of the private / shared branch; Rp / Rs = lib - logsumexp_g(logits);
-// th = exp(px_r), lte = log(th + eps), lgt = lgamma(th).   Returns log-likelihood and d ll / d rho * rho for both branches.
-__device__ __forceinline__ NbOut nb_forward_fast(float t, float lp, float ls, float pi, float th, float lte, float lgt, float Rp,
-                                                 float Rs) {
-    float rp = fast_exp(lp + Rp), rs = fast_exp(ls + Rs);
-    float d1 = th + rp + NB_EPS, d2 = th + rs + NB_EPS;
-    float l1 = fast_log(d1), l2 = fast_log(d2);
-    float a = th * (lte - l1), b = th * (lte - l2);
-    float gp = 0.0f, gs = 0.0f;
-    if (t != 0.0f) {
-        float lg = lgamma_pos_fast(t + th) - lgt - lgamma_pos_fast(t + 1.0f);
-        a += t * (fast_log(rp + NB_EPS) - l1) + lg;
-        b += t * (fast_log(rs + NB_EPS) - l2) + lg;
-        gp = fast_div(t, rp + NB_EPS);
-        gs = fast_div(t, rs + NB_EPS);
-    }
-    b -= pi;
-    // logsumexp(a, b) = max + log(1 + exp(-|a - b|));  softplus(-pi) = max(-pi, 0) + log(1 + exp(-|pi|))
-    float df = a - b;
-    float e = fast_exp(-fabsf(df));
-    float lse = fmaxf(a, b) + fast_log(1.0f + e);
-    float sp = fmaxf(-pi, 0.0f) + fast_log(1.0f + fast_exp(-fabsf(pi)));
+// as nb_forward_fast; lgt1 = lgamma(t + 1) is supplied by the caller (table over the integer count)
+__device__ __forceinline__ NbOut nb_forward_fast2(float t, float lgt1, float lp, float ls, float pi, float th, float lte,
+                                                  float lgt, float Rp, float Rs) {
+    const float xp = lp + Rp, xs = ls + Rs;
+    const float rp = fast_exp(xp), rs = fast_exp(xs);
+    const float ap = rp + NB_EPS, as = rs + NB_EPS;
+    const float d1 = th + ap, d2 = th + as;
+    float iap, ias, id1, id2;
+    batch_rcp4(ap, as, d1, d2, iap, ias, id1, id2);
+    const float l1 = fast_log(d1), l2 = fast_log(d2);
+    const float lrp = log_rho_eps(xp, ap, iap), lrs = log_rho_eps(xs, as, ias);
+    // lgamma(t + theta): shift by 8, Stirling at y = x + 8
+    const float x = t + th;
+    float pr = x * (x + 1.0f);
+    pr *= (x + 2.0f) * (x + 3.0f);
+    pr *= (x + 4.0f) * (x + 5.0f);
+    pr *= (x + 6.0f) * (x + 7.0f);
+    const float y = x + 8.0f;
+    const float iy = fast_rcp(y);
+    const float lgx = (y - 0.5f) * fast_log(y) - y + 0.91893853f + iy * (0.083333333f - iy * iy * 0.0027777778f) - fast_log(pr);
+    const float lg = lgx - lgt - lgt1;
+    const float a = th * (lte - l1) + t * (lrp - l1) + lg;
+    const float b = th * (lte - l2) + t * (lrs - l2) + lg - pi;
+    // logsumexp(a, b) - softplus(-pi) = max(a, b) - max(-pi, 0) + log((1 + exp(-|a - b|)) / (1 + exp(-|pi|)))
+    const float df = a - b;
+    const float e = fast_exp(-fabsf(df)), epi = fast_exp(-fabsf(pi));
+    const float o1 = 1.0f + e, o2 = 1.0f + epi;
+    float i1, i2;
+    batch_rcp2(o1, o2, i1, i2);
     NbOut o;
-    o.ll = lse - sp;
-    float wmin = fast_div(e, 1.0f + e);  // weight of the smaller of (a, b)
-    float wa = df >= 0.0f ? 1.0f - wmin : wmin;
-    float wb = 1.0f - wa;
-    float q1 = fast_div(th + t, d1), q2 = fast_div(th + t, d2);
-    o.ep = wa * (gp - q1) * rp;
-    o.es = wb * (gs - q2) * rs;
+    o.ll = fmaxf(a, b) - fmaxf(-pi, 0.0f) + fast_log(o1 * i2);
+    const float wmin = e * i1;  // weight of the smaller of (a, b)
+    const float wa = df >= 0.0f ? 1.0f - wmin : wmin;
+    const float wb = 1.0f - wa;
+    const float tt = th + t;
+    const float q1 = tt * id1, q2 = tt * id2;
+    o.ep = wa * (t * iap - q1) * rp;
+    o.es = wb * (t * ias - q2) * rs;
     return o;
+}
+
+// (t, lgamma(t + 1)) for a raw count: table lookup below 256, else computed (rare)
+__device__ __forceinline__ float2 nb_count_terms(uint32_t c, const float2* __restrict__ lut) {
+    if (c < 256u) return lut[c];
+    const float t = fast_log(1.0f + (float)c);
+    return make_float2(t, lgamma_pos_fast(t + 1.0f));
+}
+// fills lut[0..255] = (log1p(c), lgamma(log1p(c) + 1)); call with 256 consecutive thread indices i
+__device__ __forceinline__ void nb_fill_count_lut(float2* lut, int i) {
+    const float t = i == 0 ? 0.0f : log1pf((float)i);
+    lut[i] = make_float2(t, i == 0 ? 0.0f : lgammaf(t + 1.0f));
 }

@@ -26,7 +26,7 @@ constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int TMEM_COLS = 256;           // 3 x 64 used
 constexpr int CNT_PITCH_W = BN / 2 + 1;  // uint16 count tile: 33 32-bit words per row, conflict-free for thread = row reads
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 6 * BN * 4 + 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 6 * BN * 4 + 256 * 8 + 256;
 
 static_assert(BM * CNT_PITCH_W * 4 <= STAGES * STAGE_BYTES, "count tile must fit in the operand stages");
 
@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
     uint8_t* tiles = smem_raw + pad;
     uint8_t* z_tiles = tiles + STAGES * STAGE_BYTES;                    // folded private | shared weights, [BN][64] bf16 each
     float* s_gc = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);      // [6][BN]: cp, cs, theta, lte, lgt, bm
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_gc + 6 * BN);
+    float2* s_lut = reinterpret_cast<float2*>(s_gc + 6 * BN);         // [256]: (log1p(c), lgamma(log1p(c) + 1)) per raw count
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_lut + 256);
     uint64_t* empty = full + STAGES;
     uint64_t* z_full = empty + STAGES;
     uint64_t* tmem_full = z_full + 1;
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
         // ================= epilogue: 8 warps =================
         const int et = threadIdx.x - 64;  // 0..255
         const long G = p.G;
-        for (int i = et; i < BN; i += EPI_THREADS) {  // per-gene constants of the tile (overlaps the TMA / MMA phase)
+        if (SRC == SPV_SRC_U16_LOG1P) nb_fill_count_lut(s_lut, et);  // EPI_THREADS == 256; overlaps the TMA / MMA phase
+        for (int i = et; i < BN; i += EPI_THREADS) {  // per-gene constants of the tile
             int g = n0 + i;
             bool ok = g < p.G;
             s_gc[0 * BN + i] = ok ? __ldg(p.genec + GC_CP * G + g) : 0.0f;
@@ -202,15 +204,15 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
                     const float lp = __uint_as_float(rlp[jj]) + s_gc[0 * BN + gl];
                     const float ls = __uint_as_float(rls[jj]) + s_gc[1 * BN + gl];
                     const float piv = __uint_as_float(rpi[jj]) + s_gc[5 * BN + gl];
-                    float t;
+                    float2 tl;
                     if (SRC == SPV_SRC_U16_LOG1P) {
                         uint32_t w = s_cnt[rloc * CNT_PITCH_W + (gl >> 1)];
-                        uint32_t c = (gl & 1) ? (w >> 16) : (w & 0xffffu);
-                        t = c == 0u ? 0.0f : fast_log(1.0f + (float)c);
+                        tl = nb_count_terms((gl & 1) ? (w >> 16) : (w & 0xffffu), s_lut);
                     } else {
-                        t = load_src<SRC>(p.X, xrow + g);
+                        tl.x = load_src<SRC>(p.X, xrow + g);
+                        tl.y = lgamma_pos_fast(tl.x + 1.0f);
                     }
-                    NbOut o = nb_forward_fast(t, lp, ls, piv, s_gc[2 * BN + gl], s_gc[3 * BN + gl], s_gc[4 * BN + gl], Rp, Rs);
+                    NbOut o = nb_forward_fast2(tl.x, tl.y, lp, ls, piv, s_gc[2 * BN + gl], s_gc[3 * BN + gl], s_gc[4 * BN + gl], Rp, Rs);
                     sll += o.ll; sep += o.ep; ses += o.es;
                     pv[jj] = piv;
                 }

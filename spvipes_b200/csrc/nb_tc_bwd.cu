@@ -18,7 +18,7 @@ constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int TMEM_COLS = 256;
 constexpr int CNT_PITCH_W = BN / 2 + 1;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 6 * BN * 4 + 4 * 4 * BN * 4 + 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 7 * BN * 4 + 4 * 4 * BN * 4 + 256 * 4 + 256;
 
 static_assert(BM * CNT_PITCH_W * 4 <= STAGES * STAGE_BYTES, "count tile must fit in the operand stages");
 
@@ -43,9 +43,10 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
     uint8_t* tiles = smem_raw + pad;
     uint8_t* z_tiles = tiles + STAGES * STAGE_BYTES;
-    float* s_gc = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);  // [6][BN]: cp, cs, theta, lte, dgt, bm
-    float* s_col = s_gc + 6 * BN;                                    // [4 quantities][4 quarters][BN]
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_col + 16 * BN);
+    float* s_gc = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);  // [7][BN]: cp, cs, theta, lte, dgt, bm, theta / (theta + eps)
+    float* s_col = s_gc + 7 * BN;                                    // [4 quantities][4 quarters][BN]
+    float* s_lut = s_col + 16 * BN;                                  // [256]: log1p(c) per raw count
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_lut + 256);
     uint64_t* empty = full + STAGES;
     uint64_t* z_full = empty + STAGES;
     uint64_t* tmem_full = z_full + 1;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
         // ================= epilogue: 8 warps =================
         const int et = threadIdx.x - 64;
         const long G = p.G;
+        if (SRC == SPV_SRC_U16_LOG1P) s_lut[et] = et == 0 ? 0.0f : log1pf((float)et);  // EPI_THREADS == 256
         for (int i = et; i < BN; i += EPI_THREADS) {
             int g = n0 + i;
             bool ok = g < p.G;
@@ -132,6 +134,8 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
             s_gc[3 * BN + i] = ok ? __ldg(p.genec + GC_LTE * G + g) : 0.0f;
             s_gc[4 * BN + i] = ok ? __ldg(p.genec + GC_DGT * G + g) : 0.0f;
             s_gc[5 * BN + i] = ok ? __ldg(p.bm + g) : 0.0f;
+            const float th = s_gc[2 * BN + i];
+            s_gc[6 * BN + i] = th / (th + NB_EPS);
         }
         const int e = warp - 2;
         const int q = warp & 3;
@@ -200,12 +204,12 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
                     if (SRC == SPV_SRC_U16_LOG1P) {
                         uint32_t w = s_cnt[rloc * CNT_PITCH_W + (gl >> 1)];
                         uint32_t c = (gl & 1) ? (w >> 16) : (w & 0xffffu);
-                        t = c == 0u ? 0.0f : fast_log(1.0f + (float)c);
+                        t = c < 256u ? s_lut[c] : fast_log(1.0f + (float)c);
                     } else {
                         t = load_src<SRC>(p.X, xrow + g);
                     }
-                    NbGrad o = nb_backward_fast(t, lp, ls, piv, s_gc[2 * BN + gl], s_gc[3 * BN + gl], s_gc[4 * BN + gl], Rp, Rs,
-                                                Dp, Ds, inv_elib, p.scale);
+                    NbGrad o = nb_backward_fast2(t, lp, ls, piv, s_gc[2 * BN + gl], s_gc[3 * BN + gl], s_gc[4 * BN + gl],
+                                                 s_gc[6 * BN + gl], Rp, Rs, Dp, Ds, inv_elib, p.scale);
                     vyp[jj] = o.dyp; vys[jj] = o.dys; vpi[jj] = o.dpi; vth[jj] = o.dth;
                 }
             }
@@ -227,16 +231,36 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
                     }
                 }
             }
-            // column sums over this warp's 32 rows (lanes), then lane 0 parks them for the cross-quarter sum
+            // column sums over this warp's 32 rows (lanes): transpose-reduce of the 16 values (4 quantities x 4 columns).  Each
+            // butterfly step halves the values a lane carries, 15 shuffles in all instead of 16 x 5; lanes with bit 0 clear
+            // end up with the total of value index (lane >> 1) and park it for the cross-quarter sum.
+            {
+                float v16[16];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                float a = warp_sum(vyp[jj]), b = warp_sum(vys[jj]), c = warp_sum(vpi[jj]), d = warp_sum(vth[jj]);
-                if (lane == 0) {
-                    const int gl = c0 + jj;
-                    s_col[(0 * 4 + q) * BN + gl] = a;
-                    s_col[(1 * 4 + q) * BN + gl] = b;
-                    s_col[(2 * 4 + q) * BN + gl] = c;
-                    s_col[(3 * 4 + q) * BN + gl] = d;
+                for (int jj = 0; jj < 4; ++jj) { v16[jj] = vyp[jj]; v16[4 + jj] = vys[jj]; v16[8 + jj] = vpi[jj]; v16[12 + jj] = vth[jj]; }
+                float v8[8], v4[4], v2[2];
+                const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float send = b4 ? v16[i] : v16[i + 8], keep = b4 ? v16[i + 8] : v16[i];
+                    v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float send = b3 ? v8[i] : v8[i + 4], keep = b3 ? v8[i + 4] : v8[i];
+                    v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float send = b2 ? v4[i] : v4[i + 2], keep = b2 ? v4[i + 2] : v4[i];
+                    v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                const float send = b1 ? v2[0] : v2[1], keep = b1 ? v2[1] : v2[0];
+                float tot = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+                if ((lane & 1) == 0) {
+                    const int idx = lane >> 1;  // = 8 b4 + 4 b3 + 2 b2 + b1: quantity idx >> 2, column idx & 3
+                    s_col[((idx >> 2) * 4 + q) * BN + c0 + (idx & 3)] = tot;
                 }
             }
         }
