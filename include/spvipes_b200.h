@@ -112,7 +112,7 @@ int spv_loss(const float* rec0, const float* rec1, const float* klp0, const floa
  * zmean, zcov.  training != 0: zsum / zmean / zcov [P+S], [P+S], [P+S, P+S] are OUTPUTS (column sums, mean and biased
  * covariance of the latent minibatch zz [B, P+S], one cluster launch).   nn/networks.py:314-320, scvi FCLayers;
  * module/spVIPESmodule.py:758 */
-#define SPV_DEC_GENEC_ROWS 12
+#define SPV_DEC_GENEC_ROWS 17
 /* wz_bf16 (optional): rows [Gp, 3 Gp) of the stacked bf16 tensor-core operand [3 Gp, ld_wz] (rows [0, G): mixture weight,
  * [Gp, Gp + G): folded private weights in the latent columns HD .., [2 Gp, 2 Gp + G): folded shared weights) */
 int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, int S, int training, float eps, float momentum,
@@ -129,11 +129,15 @@ int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld
 /* tensor-core version of phase 2 of spv_dec_nb_fwd: the mixture GEMM and the two softmax-branch logit GEMMs on tcgen05
  * (bf16 operands via TMA, fp32 accumulators in TMEM) with the NB-mixture log-likelihood fused into the TMEM epilogue.
  * amix_bf16 [B, ld_amixb] = [hm | zz]; wstack_bf16 [3 Gp, ld_w] = mixture weight + folded branch weights (spv_dec_fold).
- * part_nb (ptrs[11]) needs 2 * ceil(G/64) * B * 3 floats.  store_pi: also write the mixture logits to ptrs[10] (fp32). */
+ * part_nb (ptrs[11]) needs spv_dec_nb_part_floats(B, G) floats.  store_pi: also write the mixture logits to ptrs[10] (fp32). */
 int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
                       const void* wstack_bf16, long long ld_w, int Gp, int B, int G, int HD, int P, int S, int store_pi,
                       void* stream);
-int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, float* rowc, float* rec, void* stream);
+/* floats spv_dec_nb_fwd_tc needs in part_nb (ptrs[11]) for a [B, G] problem */
+long long spv_dec_nb_part_floats(int B, int G);
+/* rec[b] (ptrs[16] of the forward) and the softmax-backward row sums rowc[:, 2:4] from the row partials part_nb that
+ * spv_dec_nb_fwd_tc wrote for the same B, G, HD */
+int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, int HD, float* rowc, float* rec, void* stream);
 /* tensor-core backward sweep: recomputes the three logit tiles on tcgen05 and writes D3 = [dpi | dyp | dys] (bf16
  * [B, 3 Gp], operand of the gradient GEMMs) and colsum [4, G] (column sums of dyp, dys, dpi, d loss / d theta);
  * ptrs[15] = colpart workspace [ceil(B/128), 4, G].  scale = - grad_scale / B. */

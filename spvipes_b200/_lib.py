@@ -14,7 +14,7 @@ SRC_F32, SRC_U16_LOG1P, SRC_F32_LOG1P = 0, 1, 2
 POE_LABEL, POE_PAIRED, POE_CLUSTER = 0, 1, 2
 PARTNER_PAD, PARTNER_ABSENT = -1, -2
 POE_MODES = {"label": POE_LABEL, "paired": POE_PAIRED, "cluster": POE_CLUSTER}
-GENEC_ROWS = 12
+GENEC_ROWS = 17
 
 p, i, ll, f, u64, u32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong, C.c_uint
 
@@ -44,10 +44,11 @@ _SIGS = {
     "spv_dec_nb_fwd": [i, p, ll, ll, i, i, i, i, i, i, p],
     "spv_dec_nb_bwd": [i, p, ll, ll, i, i, i, i, i, f, p, p, ll, p],
     "spv_dec_nb_fwd_tc": [i, p, ll, p, ll, p, ll, i, i, i, i, i, i, i, p],
-    "spv_dec_nb_rowreduce": [p, i, i, p, p, p],
+    "spv_dec_nb_rowreduce": [p, i, i, i, p, p, p],
     "spv_dec_nb_bwd_tc": [i, p, ll, p, ll, p, ll, i, p, i, i, i, i, i, f, p, p],
     "spv_dec_gene_bwd": [p, ll, i, i, i, i, p],
     "spv_dec_gene_bwd_parts": [i],
+    "spv_dec_nb_part_floats": [i, i],
     "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, p],
     "spv_adam_tick": [p, p],
     "spv_adam": [p, p, p, p, ll, f, f, f, f, f, f, p, p, i, p, p, p, p, p, p],
@@ -71,7 +72,7 @@ def load():
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = args
-        fn.restype = C.c_longlong if name == "spv_launch_count" else C.c_int
+        fn.restype = C.c_longlong if name in ("spv_launch_count", "spv_dec_nb_part_floats") else C.c_int
     _lib = lib
     return lib
 

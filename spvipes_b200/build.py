@@ -13,7 +13,7 @@ LIB = os.path.join(HERE, "libspvipes_b200.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr"]
+         "--expt-relaxed-constexpr"] + os.environ.get("SPV_NVCC_EXTRA", "").split()
 
 
 def _sources():

@@ -13,5 +13,11 @@ enum {
     GC_LTE,      // log(theta + eps)
     GC_LGT,      // lgamma(theta)
     GC_DGT,      // digamma(theta)
+    // ready-made constants of the base-2 element math of the tensor-core likelihood kernels (nb_math.cuh, v3)
+    GC_CPL,      // GC_CP * log2(e)
+    GC_CSL,      // GC_CS * log2(e)
+    GC_THE,      // theta + eps
+    GC_K0,       // theta log(theta + eps) - lgamma(theta) + 0.5 log(2 pi)          (forward)
+    GC_K1,       // log(theta + eps) + theta / (theta + eps) - digamma(theta)       (backward)
     GC_N
 };

@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
             const float a = gamma * invstd;
             sA[br * 32 + gl] = a;
             p.genec[(br == 0 ? GC_CP : GC_CS) * G + g] = beta - mean * a;
+            p.genec[(br == 0 ? GC_CPL : GC_CSL) * G + g] = (beta - mean * a) * 1.4426950408889634f;
             p.genec[(br == 0 ? GC_AP : GC_AS) * G + g] = a;
             p.genec[(br == 0 ? GC_ISTD_P : GC_ISTD_S) * G + g] = invstd;
             p.genec[(br == 0 ? GC_MEAN_P : GC_MEAN_S) * G + g] = mean;
@@ -242,10 +243,14 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
         if (gl < ng) {
             const int g = g0 + gl;
             float th = expf(svec[4 * 32 + gl]);  // reference module/spVIPESmodule.py:758
+            const float lte = logf(th + NB_EPS), lgt = lgammaf(th), dgt = digammaf_pos(th);
             p.genec[GC_THETA * G + g] = th;
-            p.genec[GC_LTE * G + g] = logf(th + NB_EPS);
-            p.genec[GC_LGT * G + g] = lgammaf(th);
-            p.genec[GC_DGT * G + g] = digammaf_pos(th);
+            p.genec[GC_LTE * G + g] = lte;
+            p.genec[GC_LGT * G + g] = lgt;
+            p.genec[GC_DGT * G + g] = dgt;
+            p.genec[GC_THE * G + g] = th + NB_EPS;
+            p.genec[GC_K0 * G + g] = fmaf(th, lte, 0.91893853f - lgt);
+            p.genec[GC_K1 * G + g] = lte + th / (th + NB_EPS) - dgt;
         }
     }
     __syncthreads();

@@ -14,6 +14,7 @@
 // are streamed out of TMEM four columns at a time.  Nothing of size [B, G] is written unless store_pi is set.
 // Reference: nn/networks.py:314-325, module/spVIPESmodule.py:751-759, 817-824; scvi log_mixture_nb.
 #include "tc_common.cuh"
+#include "nb_ptc.cuh"
 #include "nb_math.cuh"
 #include "decoder_common.cuh"
 #include "../../include/spvipes_b200.h"
@@ -21,10 +22,12 @@
 namespace {
 
 constexpr int BM = 128, BN = 64, BK = 64, STAGES = 2;
+constexpr int WCOLS = BN / 2;                 // gene columns per epilogue warp (two warps per TMEM lane quarter)
+constexpr int GATHER_ROWS = 64 / BN;          // rows of the count tile one warp gathers per load: 32 lanes cover BN / 2 words each
 constexpr int EPI_WARPS = 8, EPI_THREADS = 32 * EPI_WARPS;
 constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TMEM_COLS = 256;           // 3 x 64 used
+constexpr int TMEM_COLS = BN == 64 ? 256 : 128;           // 3 x 64 used
 constexpr int CNT_PITCH_W = BN / 2 + 1;  // uint16 count tile: 33 32-bit words per row, conflict-free for thread = row reads
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 6 * BN * 4 + 256 * 8 + 256;
 
@@ -40,6 +43,11 @@ struct NbTcParams {
     int B, G, K, kb_z;                 // kb_z: k-block holding the latent columns
     int Gp;                            // row offset of the shared block inside the folded-weight operand
 };
+
+// row of the count tile that lane `lane` of epilogue warp e loads in its i-th gather: a warp covers GATHER_ROWS rows per load
+__device__ __forceinline__ int cnt_row(int e, int lane, int i) {
+    return (e + EPI_WARPS * i) * GATHER_ROWS + lane / (BN / 2);
+}
 
 template <int SRC>
 __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA,
@@ -134,12 +142,12 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
         for (int i = et; i < BN; i += EPI_THREADS) {  // per-gene constants of the tile
             int g = n0 + i;
             bool ok = g < p.G;
-            s_gc[0 * BN + i] = ok ? __ldg(p.genec + GC_CP * G + g) : 0.0f;
-            s_gc[1 * BN + i] = ok ? __ldg(p.genec + GC_CS * G + g) : 0.0f;
-            s_gc[2 * BN + i] = ok ? __ldg(p.genec + GC_THETA * G + g) : 1.0f;
-            s_gc[3 * BN + i] = ok ? __ldg(p.genec + GC_LTE * G + g) : 0.0f;
-            s_gc[4 * BN + i] = ok ? __ldg(p.genec + GC_LGT * G + g) : 0.0f;
-            s_gc[5 * BN + i] = ok ? __ldg(p.bm + g) : 0.0f;
+            s_gc[0 * BN + i] = ok ? __ldg(p.genec + GC_CPL * G + g) : 0.0f;   // constants of nb_forward_v3
+            s_gc[1 * BN + i] = ok ? __ldg(p.genec + GC_CSL * G + g) : 0.0f;
+            s_gc[2 * BN + i] = ok ? __ldg(p.bm + g) : 0.0f;
+            s_gc[3 * BN + i] = ok ? __ldg(p.genec + GC_THETA * G + g) : 1.0f;
+            s_gc[4 * BN + i] = ok ? __ldg(p.genec + GC_THE * G + g) : 1.0f;
+            s_gc[5 * BN + i] = ok ? __ldg(p.genec + GC_K0 * G + g) : 0.0f;
         }
         const int e = warp - 2;
         const int q = warp & 3;          // TMEM lane quarter this warp may access
@@ -148,22 +156,22 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
         const int m = m0 + rloc;
         const bool mok = m < p.B;
         const int mm = mok ? m : 0;
-        const float Rp = __ldg(p.rowc + (long)mm * 4 + 0), Rs = __ldg(p.rowc + (long)mm * 4 + 1);
+        const float Rpl = NB_LOG2E * __ldg(p.rowc + (long)mm * 4 + 0), Rsl = NB_LOG2E * __ldg(p.rowc + (long)mm * 4 + 1);
         const long xrow = (p.rows ? (long)__ldg(p.rows + mm) : (long)mm) * p.ldx;
         // coalesced row gather of the tile's counts into registers (overlaps the MMA phase): warp e takes rows e, e + 8, ...;
         // lane l takes genes 2l, 2l + 1
-        uint32_t cw[BM / EPI_WARPS];
+        uint32_t cw[BM / EPI_WARPS];  // with GATHER_ROWS > 1 only the first BM / EPI_WARPS / GATHER_ROWS entries are used
         if (SRC == SPV_SRC_U16_LOG1P) {
             const unsigned short* X16 = reinterpret_cast<const unsigned short*>(p.X);
-            long xr[BM / EPI_WARPS];
+            long xr[BM / EPI_WARPS / GATHER_ROWS];
 #pragma unroll
-            for (int i = 0; i < BM / EPI_WARPS; ++i) {
-                const int gm = m0 + e + EPI_WARPS * i;
+            for (int i = 0; i < BM / EPI_WARPS / GATHER_ROWS; ++i) {
+                const int gm = m0 + cnt_row(e, lane, i);
                 xr[i] = gm < p.B ? (p.rows ? (long)__ldg(p.rows + gm) : (long)gm) * p.ldx : -1;
             }
-            const int g = n0 + 2 * lane;
+            const int g = n0 + 2 * (lane % (BN / 2));
 #pragma unroll
-            for (int i = 0; i < BM / EPI_WARPS; ++i) {
+            for (int i = 0; i < BM / EPI_WARPS / GATHER_ROWS; ++i) {
                 cw[i] = 0u;
                 if (xr[i] >= 0) {
                     const unsigned short* src = X16 + xr[i] + g;
@@ -180,15 +188,15 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
         tc::fence_after_sync();
         if (SRC == SPV_SRC_U16_LOG1P) {
 #pragma unroll
-            for (int i = 0; i < BM / EPI_WARPS; ++i) s_cnt[(e + EPI_WARPS * i) * CNT_PITCH_W + lane] = cw[i];
+            for (int i = 0; i < BM / EPI_WARPS / GATHER_ROWS; ++i) s_cnt[cnt_row(e, lane, i) * CNT_PITCH_W + lane % (BN / 2)] = cw[i];
         }
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");  // constants + counts staged (epilogue warps only)
         float sll = 0.0f, sep = 0.0f, ses = 0.0f;
         const bool vec_pi = p.pi && ((G & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.pi) & 15) == 0);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-            const int c0 = half * 32 + j4;
+        for (int j4 = 0; j4 < WCOLS; j4 += 4) {
+            const int c0 = half * WCOLS + j4;
             uint32_t rpi[4], rlp[4], rls[4];
             tc::tmem_ld4(lane_addr + (uint32_t)c0, rpi);
             tc::tmem_ld4(lane_addr + (uint32_t)(BN + c0), rlp);
@@ -201,18 +209,25 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
                 const int gl = c0 + jj, g = n0 + gl;
                 pv[jj] = 0.0f;
                 if (g < p.G) {
-                    const float lp = __uint_as_float(rlp[jj]) + s_gc[0 * BN + gl];
-                    const float ls = __uint_as_float(rls[jj]) + s_gc[1 * BN + gl];
-                    const float piv = __uint_as_float(rpi[jj]) + s_gc[5 * BN + gl];
+                    NbGene ge;
+                    ge.cpl = s_gc[0 * BN + gl]; ge.csl = s_gc[1 * BN + gl]; ge.bm = s_gc[2 * BN + gl];
+                    ge.th = s_gc[3 * BN + gl]; ge.thE = s_gc[4 * BN + gl]; ge.K = s_gc[5 * BN + gl];
+                    const float piv = __uint_as_float(rpi[jj]) + ge.bm;
                     float2 tl;
                     if (SRC == SPV_SRC_U16_LOG1P) {
                         uint32_t w = s_cnt[rloc * CNT_PITCH_W + (gl >> 1)];
-                        tl = nb_count_terms((gl & 1) ? (w >> 16) : (w & 0xffffu), s_lut);
+                        const uint32_t c = (gl & 1) ? (w >> 16) : (w & 0xffffu);
+                        tl = c < 256u ? s_lut[c] : nb_count_terms_exact(c);
                     } else {
                         tl.x = load_src<SRC>(p.X, xrow + g);
                         tl.y = lgamma_pos_fast(tl.x + 1.0f);
                     }
-                    NbOut o = nb_forward_fast2(tl.x, tl.y, lp, ls, piv, s_gc[2 * BN + gl], s_gc[3 * BN + gl], s_gc[4 * BN + gl], Rp, Rs);
+                    bool rare = false;
+                    NbOut o = nb_forward_v3<false>(tl.x, tl.y, __uint_as_float(rlp[jj]), __uint_as_float(rls[jj]), __uint_as_float(rpi[jj]),
+                                                   ge, Rpl, Rsl, rare);
+                    if (rare)
+                        o = nb_forward_v3<true>(tl.x, tl.y, __uint_as_float(rlp[jj]), __uint_as_float(rls[jj]), __uint_as_float(rpi[jj]), ge,
+                                                Rpl, Rsl, rare);
                     sll += o.ll; sep += o.ep; ses += o.es;
                     pv[jj] = piv;
                 }
@@ -277,6 +292,22 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
     if (store_pi && !ptrs[10]) return SPV_ERR_ARG;
     const int K = HD + P + S;
     CUtensorMap ma, mb, mz;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (ptc::eligible(B, G, K, ptc::sm_count())) {  // persistent kernel: one CTA per SM over 128 x 16 units
+        int rc = spv_make_tensor_map_bf16(&ma, amix_bf16, (unsigned long long)K, (unsigned long long)B, (unsigned long long)ld_amixb, 64, ptc::BM);
+        if (rc != SPV_OK) return rc;
+        rc = spv_make_tensor_map_bf16(&mb, wm_bf16, (unsigned long long)K, (unsigned long long)G, (unsigned long long)ld_wmb, 64, ptc::BN);
+        if (rc != SPV_OK) return rc;
+        rc = spv_make_tensor_map_bf16(&mz, wz_bf16, (unsigned long long)K, (unsigned long long)(2 * Gp), (unsigned long long)ld_w, 64, ptc::BN);
+        if (rc != SPV_OK) return rc;
+        ptc::FwdParams q;
+        q.X = ptrs[0]; q.ldx = ldx; q.rows = (const int*)ptrs[1]; q.bm = (const float*)ptrs[5]; q.genec = (const float*)ptrs[6];
+        q.rowc = (const float*)ptrs[9]; q.pi = store_pi ? (float*)ptrs[10] : nullptr; q.part = (float*)ptrs[11];
+        q.trace = nullptr;
+        q.B = B; q.G = G; q.num_kb = (K + BK - 1) / BK; q.kb_z = HD / BK; q.Gp = Gp;
+        q.nG = (G + ptc::BN - 1) / ptc::BN; q.units = ((B + ptc::BM - 1) / ptc::BM) * q.nG;
+        return ptc::fwd_launch(src, ma, mb, mz, q, st);
+    }
     int rc = spv_make_tensor_map_bf16(&ma, amix_bf16, (unsigned long long)K, (unsigned long long)B, (unsigned long long)ld_amixb, 64, BM);
     if (rc != SPV_OK) return rc;
     rc = spv_make_tensor_map_bf16(&mb, wm_bf16, (unsigned long long)K, (unsigned long long)G, (unsigned long long)ld_wmb, 64, BN);
@@ -288,7 +319,6 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
     p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
     p.rowc = (const float*)ptrs[9]; p.pi = store_pi ? (float*)ptrs[10] : nullptr; p.part_nb = (float*)ptrs[11];
     p.B = B; p.G = G; p.K = K; p.kb_z = HD / BK;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(nb_tc_fwd_kernel<SPV_SRC_U16_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
@@ -304,9 +334,17 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
     return SPV_OK;
 }
 
-// rec[b] = - sum over the 2 * ceil(G/64) per-tile partials of spv_dec_nb_fwd_tc; also the softmax-backward row sums rowc[:, 2:4]
-extern "C" int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, float* rowc, float* rec, void* stream) {
-    if (!part_nb || !rowc || !rec || G <= 0 || B <= 0) return SPV_ERR_ARG;
+// floats spv_dec_nb_fwd_tc needs in part_nb (either kernel variant)
+extern "C" long long spv_dec_nb_part_floats(int B, int G) {
+    if (B <= 0 || G <= 0) return 0;
+    const long long tiled = 2ll * ((G + BN - 1) / BN) * B * 3;
+    return tiled > ptc::part_floats() ? tiled : ptc::part_floats();
+}
+
+// rec[b] = - sum over the row partials of spv_dec_nb_fwd_tc (same B, G, HD); also the softmax-backward row sums rowc[:, 2:4]
+extern "C" int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, int HD, float* rowc, float* rec, void* stream) {
+    if (!part_nb || !rowc || !rec || G <= 0 || B <= 0 || HD < 0) return SPV_ERR_ARG;
+    if (ptc::eligible(B, G, HD + BK, ptc::sm_count())) return ptc::fwd_rowreduce(part_nb, G, B, rowc, rec, reinterpret_cast<cudaStream_t>(stream));
     rownb_tc_kernel<<<(B + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part_nb, 2 * ((G + BN - 1) / BN), B, rowc, rec);
     SPV_CHECK_LAUNCH();
     return SPV_OK;

@@ -13,10 +13,12 @@
 namespace {
 
 constexpr int BM = 128, BN = 64, BK = 64, STAGES = 2;
+constexpr int WCOLS = BN / 2;                 // gene columns per epilogue warp (two warps per TMEM lane quarter)
+constexpr int GATHER_ROWS = 64 / BN;          // rows of the count tile one warp gathers per load: 32 lanes cover BN / 2 words each
 constexpr int EPI_WARPS = 8, EPI_THREADS = 32 * EPI_WARPS;
 constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = BN == 64 ? 256 : 128;
 constexpr int CNT_PITCH_W = BN / 2 + 1;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 7 * BN * 4 + 4 * 4 * BN * 4 + 256 * 4 + 256;
 
@@ -33,6 +35,11 @@ struct NbTcBwdParams {
     int B, G, K, kb_z, Gp;
     float scale;
 };
+
+// row of the count tile that lane `lane` of epilogue warp e loads in its i-th gather: a warp covers GATHER_ROWS rows per load
+__device__ __forceinline__ int cnt_row(int e, int lane, int i) {
+    return (e + EPI_WARPS * i) * GATHER_ROWS + lane / (BN / 2);
+}
 
 template <int SRC>
 __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA,
@@ -128,14 +135,12 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
         for (int i = et; i < BN; i += EPI_THREADS) {
             int g = n0 + i;
             bool ok = g < p.G;
-            s_gc[0 * BN + i] = ok ? __ldg(p.genec + GC_CP * G + g) : 0.0f;
-            s_gc[1 * BN + i] = ok ? __ldg(p.genec + GC_CS * G + g) : 0.0f;
-            s_gc[2 * BN + i] = ok ? __ldg(p.genec + GC_THETA * G + g) : 1.0f;
-            s_gc[3 * BN + i] = ok ? __ldg(p.genec + GC_LTE * G + g) : 0.0f;
-            s_gc[4 * BN + i] = ok ? __ldg(p.genec + GC_DGT * G + g) : 0.0f;
-            s_gc[5 * BN + i] = ok ? __ldg(p.bm + g) : 0.0f;
-            const float th = s_gc[2 * BN + i];
-            s_gc[6 * BN + i] = th / (th + NB_EPS);
+            s_gc[0 * BN + i] = ok ? __ldg(p.genec + GC_CPL * G + g) : 0.0f;   // constants of nb_backward_v3
+            s_gc[1 * BN + i] = ok ? __ldg(p.genec + GC_CSL * G + g) : 0.0f;
+            s_gc[2 * BN + i] = ok ? __ldg(p.bm + g) : 0.0f;
+            s_gc[3 * BN + i] = ok ? __ldg(p.genec + GC_THETA * G + g) : 1.0f;
+            s_gc[4 * BN + i] = ok ? __ldg(p.genec + GC_THE * G + g) : 1.0f;
+            s_gc[5 * BN + i] = ok ? __ldg(p.genec + GC_K1 * G + g) : 0.0f;
         }
         const int e = warp - 2;
         const int q = warp & 3;
@@ -144,24 +149,24 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
         const int m = m0 + rloc;
         const bool mok = m < p.B;
         const int mm = mok ? m : 0;
-        const float Rp = __ldg(p.rowc + (long)mm * 4 + 0), Rs = __ldg(p.rowc + (long)mm * 4 + 1);
-        const float Dp = __ldg(p.rowc + (long)mm * 4 + 2), Ds = __ldg(p.rowc + (long)mm * 4 + 3);
+        const float Rpl = NB_LOG2E * __ldg(p.rowc + (long)mm * 4 + 0), Rsl = NB_LOG2E * __ldg(p.rowc + (long)mm * 4 + 1);
         const float inv_elib = fast_exp(-__ldg(p.lib + mm));
+        const float DpI = inv_elib * __ldg(p.rowc + (long)mm * 4 + 2), DsI = inv_elib * __ldg(p.rowc + (long)mm * 4 + 3);
         const long xrow = (p.rows ? (long)__ldg(p.rows + mm) : (long)mm) * p.ldx;
         // coalesced row gather of the tile's counts into registers (overlaps the MMA phase): warp e takes rows e, e + 8, ...;
         // lane l takes genes 2l, 2l + 1
-        uint32_t cw[BM / EPI_WARPS];
+        uint32_t cw[BM / EPI_WARPS];  // with GATHER_ROWS > 1 only the first BM / EPI_WARPS / GATHER_ROWS entries are used
         if (SRC == SPV_SRC_U16_LOG1P) {
             const unsigned short* X16 = reinterpret_cast<const unsigned short*>(p.X);
-            long xr[BM / EPI_WARPS];
+            long xr[BM / EPI_WARPS / GATHER_ROWS];
 #pragma unroll
-            for (int i = 0; i < BM / EPI_WARPS; ++i) {
-                const int gm = m0 + e + EPI_WARPS * i;
+            for (int i = 0; i < BM / EPI_WARPS / GATHER_ROWS; ++i) {
+                const int gm = m0 + cnt_row(e, lane, i);
                 xr[i] = gm < p.B ? (p.rows ? (long)__ldg(p.rows + gm) : (long)gm) * p.ldx : -1;
             }
-            const int g = n0 + 2 * lane;
+            const int g = n0 + 2 * (lane % (BN / 2));
 #pragma unroll
-            for (int i = 0; i < BM / EPI_WARPS; ++i) {
+            for (int i = 0; i < BM / EPI_WARPS / GATHER_ROWS; ++i) {
                 cw[i] = 0u;
                 if (xr[i] >= 0) {
                     const unsigned short* src = X16 + xr[i] + g;
@@ -178,14 +183,14 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
         tc::fence_after_sync();
         if (SRC == SPV_SRC_U16_LOG1P) {
 #pragma unroll
-            for (int i = 0; i < BM / EPI_WARPS; ++i) s_cnt[(e + EPI_WARPS * i) * CNT_PITCH_W + lane] = cw[i];
+            for (int i = 0; i < BM / EPI_WARPS / GATHER_ROWS; ++i) s_cnt[cnt_row(e, lane, i) * CNT_PITCH_W + lane % (BN / 2)] = cw[i];
         }
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
         const bool vec_b = ((p.ld_dpi & 3) == 0) && ((p.Gp & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dpi) & 7) == 0);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-            const int c0 = half * 32 + j4;
+        for (int j4 = 0; j4 < WCOLS; j4 += 4) {
+            const int c0 = half * WCOLS + j4;
             uint32_t rpi[4], rlp[4], rls[4];
             tc::tmem_ld4(lane_addr + (uint32_t)c0, rpi);
             tc::tmem_ld4(lane_addr + (uint32_t)(BN + c0), rlp);
@@ -197,9 +202,9 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
                 const int gl = c0 + jj, g = n0 + gl;
                 vyp[jj] = vys[jj] = vpi[jj] = vth[jj] = 0.0f;
                 if (mok && g < p.G) {
-                    const float lp = __uint_as_float(rlp[jj]) + s_gc[0 * BN + gl];
-                    const float ls = __uint_as_float(rls[jj]) + s_gc[1 * BN + gl];
-                    const float piv = __uint_as_float(rpi[jj]) + s_gc[5 * BN + gl];
+                    NbGene ge;
+                    ge.cpl = s_gc[0 * BN + gl]; ge.csl = s_gc[1 * BN + gl]; ge.bm = s_gc[2 * BN + gl];
+                    ge.th = s_gc[3 * BN + gl]; ge.thE = s_gc[4 * BN + gl]; ge.K = s_gc[5 * BN + gl];
                     float t;
                     if (SRC == SPV_SRC_U16_LOG1P) {
                         uint32_t w = s_cnt[rloc * CNT_PITCH_W + (gl >> 1)];
@@ -208,8 +213,12 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
                     } else {
                         t = load_src<SRC>(p.X, xrow + g);
                     }
-                    NbGrad o = nb_backward_fast2(t, lp, ls, piv, s_gc[2 * BN + gl], s_gc[3 * BN + gl], s_gc[4 * BN + gl],
-                                                 s_gc[6 * BN + gl], Rp, Rs, Dp, Ds, inv_elib, p.scale);
+                    bool rare = false;
+                    NbGrad o = nb_backward_v3<false>(t, __uint_as_float(rlp[jj]), __uint_as_float(rls[jj]), __uint_as_float(rpi[jj]), ge,
+                                                     Rpl, Rsl, DpI, DsI, p.scale, rare);
+                    if (rare)
+                        o = nb_backward_v3<true>(t, __uint_as_float(rlp[jj]), __uint_as_float(rls[jj]), __uint_as_float(rpi[jj]), ge, Rpl,
+                                                 Rsl, DpI, DsI, p.scale, rare);
                     vyp[jj] = o.dyp; vys[jj] = o.dys; vpi[jj] = o.dpi; vth[jj] = o.dth;
                 }
             }

@@ -178,7 +178,8 @@ class _GroupWS:
         self.wfold, self.genec = f(G, KZ), f(L.GENEC_ROWS, G)
         self.ah = f(B, HD)
         self.bn_h_mean, self.bn_h_istd = f(HD), f(HD)
-        self.part_stats, self.part_nb = f(self.nTG, B, 4), f(2 * self.nTG, B, 3)
+        self.part_stats = f(self.nTG, B, 4)
+        self.part_nb = f(max(2 * self.nTG * B * 3, int(L.load().spv_dec_nb_part_floats(B, G))))
         self.rowc = f(B, 4)
         self.pi = f(B, G)
         self.expert = f(B, 2 * S)  # cluster mode: plan-weighted expert statistics
@@ -465,7 +466,7 @@ class StepEngine:
                     if evs is not None:
                         evs[1].record()
                         evs = None
-                    L.check(lib.spv_dec_nb_rowreduce(L.ptr(w.part_nb), G, B, L.ptr(w.rowc), L.ptr(w.rec), st), "spv_dec_nb_rowreduce")
+                    L.check(lib.spv_dec_nb_rowreduce(L.ptr(w.part_nb), G, B, HD, L.ptr(w.rowc), L.ptr(w.rec), st), "spv_dec_nb_rowreduce")
                 else:  # unfused: tensor-core GEMM writes pi, the SIMT sweep consumes it
                     self._tc_gemm(L.ptr(w.amixb), L.ptr(w.Wmb), L.ptr(w.pi), B, G, KMIX, lda=w.KMp, ldb=w.KMp, ldc=G,
                                   bias=L.ptr(self.P(g, "bm")))
