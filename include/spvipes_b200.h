@@ -161,11 +161,12 @@ int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw
  * ticket != NULL (zeroed device int): the launch uses *step + 1 and its last CTA stores it back.
  * nseg (<= 8) staging segments, host arrays: the parameter block [seg_begin, seg_begin + seg_rows * seg_cols) viewed as
  * [seg_rows, seg_cols] is also written, updated, as bf16 into seg_dst (row pitch seg_ld): the tensor-core operand copies of
- * the large weights, so that the next step does not start with conversion kernels.  p, g, m, v 16-byte aligned. */
+ * the large weights, so that the next step does not start with conversion kernels.  p, g, m, v 16-byte aligned.
+ * max_blocks > 0 caps the grid (an update overlapped with other kernels should not occupy every SM). */
 int spv_adam_tick(int* step, void* stream);
 int spv_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
              float grad_scale, int* step, int* ticket, int nseg, const long long* seg_begin, const int* seg_rows,
-             const int* seg_cols, void* const* seg_dst, const long long* seg_ld, void* stream);
+             const int* seg_cols, void* const* seg_dst, const long long* seg_ld, int max_blocks, void* stream);
 
 #ifdef __cplusplus
 }

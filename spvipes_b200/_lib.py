@@ -51,7 +51,7 @@ _SIGS = {
     "spv_dec_nb_part_floats": [i, i],
     "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, p],
     "spv_adam_tick": [p, p],
-    "spv_adam": [p, p, p, p, ll, f, f, f, f, f, f, p, p, i, p, p, p, p, p, p],
+    "spv_adam": [p, p, p, p, ll, f, f, f, f, f, f, p, p, i, p, p, p, p, p, i, p],
 }
 
 _lib = None

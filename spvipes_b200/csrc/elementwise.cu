@@ -407,7 +407,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 // [seg_rows, seg_cols] is mirrored as bf16 into seg_dst with row pitch seg_ld.
 extern "C" int spv_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                         float wd, float grad_scale, int* step, int* ticket, int nseg, const long long* seg_begin,
-                        const int* seg_rows, const int* seg_cols, void* const* seg_dst, const long long* seg_ld, void* stream) {
+                        const int* seg_rows, const int* seg_cols, void* const* seg_dst, const long long* seg_ld, int max_blocks,
+                        void* stream) {
     if (!p || !g || !m || !v || !step || n <= 0 || nseg < 0 || nseg > ADAM_MAX_SEGS) return SPV_ERR_ARG;
     if (nseg > 0 && (!seg_begin || !seg_rows || !seg_cols || !seg_dst || !seg_ld)) return SPV_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -427,6 +428,7 @@ extern "C" int spv_adam(float* p, const float* g, float* m, float* v, long long 
         sg.inv_cols[s] = 1.0f / (float)seg_cols[s];
     }
     int blocks = (int)min((long long)148 * 8, (n / 4 + 255) / 256);
+    if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;  // a small grid leaves SMs to concurrently running kernels
     if (blocks < 1) blocks = 1;
     adam_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, b1, b2, eps, wd, grad_scale, step,
                                                                             ticket, sg);

@@ -189,7 +189,8 @@ class _GroupWS:
         self.splits_b = max(1, min(8, B // 64))         # reductions over the minibatch with a small output
         big = max(2 * H, KMIX)
         self.ws = f(max(32 * B * big, self.splits_b * G * KZ, 2 * self.splits_b * big * big, 1))
-        self.ws2 = f(max(2 * self.splits_b * big * big, 1))  # split-K scratch of the auxiliary (weight-gradient) stream
+        self.ws2 = f(max(2 * self.splits_b * big * big, 1))  # split-K scratch of the auxiliary (weight-gradient) streams
+        self.ws3 = f(max(2 * self.splits_b * big * big, 1))
         r8 = lambda x: (x + 7) // 8 * 8
         self.Gp, self.KMp = r8(G), r8(KMIX)
         if bf16:
@@ -262,6 +263,7 @@ class StepEngine:
         self._ctx = None
         self._side = None
         self._aux = None
+        self._aux_lanes = int(__import__("os").environ.get("SPV_AUX_LANES", "2"))  # A/B switch
         self._pending = {}
         self.parallel_groups = True
         r8 = lambda x: (x + 7) // 8 * 8
@@ -325,19 +327,19 @@ class StepEngine:
             cur.wait_event(ev)
 
     @contextlib.contextmanager
-    def _branch(self, g, tag):
-        """run the enclosed launches on group g's auxiliary stream, forked from the current stream; `_join(g, tag)` makes
-        the current stream wait for them.  Used for work that is off the critical path of the step (weight-gradient GEMMs,
-        bias column sums, operand staging that does not depend on the minibatch)."""
+    def _branch(self, g, tag, lane=0):
+        """run the enclosed launches on one of group g's two auxiliary streams (`lane`), forked from the current stream;
+        `_join(g, tag)` makes the current stream wait for them.  Used for work that is off the critical path of the step
+        (weight-gradient GEMMs, bias column sums, operand staging that does not depend on the minibatch)."""
         if not self.parallel_groups or self.device.type != "cuda":
             yield
             return
         if self._aux is None:
-            self._aux = [torch.cuda.Stream(device=self.device) for _ in (0, 1)]
+            self._aux = [[torch.cuda.Stream(device=self.device) for _ in (0, 1)] for _ in (0, 1)]
         cur = torch.cuda.current_stream(self.device)
         fork = torch.cuda.Event()
         fork.record(cur)
-        aux = self._aux[g]
+        aux = self._aux[g][lane if self._aux_lanes > 1 else 0]
         aux.wait_event(fork)
         with torch.cuda.stream(aux):
             yield
@@ -557,14 +559,24 @@ class StepEngine:
                                      L.ptr(self.step_dev), self._stream()), "spv_poe_fwd")
 
     # -------------------------------------------------------------------------------- backward
-    def backward(self, grad_scale: float = 1.0):
-        """gradients of loss * grad_scale w.r.t. every parameter, written into self.grads."""
+    def backward(self, grad_scale: float = 1.0, adam: Optional[dict] = None):
+        """gradients of loss * grad_scale w.r.t. every parameter, written into self.grads.
+        adam (single-GPU training only: keys lr, betas, eps, weight_decay): also apply the optimiser step, per parameter range
+        as soon as its gradients are complete: the decoder ranges (55 % of the parameters) update on an auxiliary stream
+        while the encoder backward, a chain of small latency-bound kernels that leaves HBM idle, is still running."""
         ctx = self._ctx
         if ctx is None or not ctx["training"]:
             raise RuntimeError("backward needs a preceding training-mode forward")
         d, st, lib = self.d, self._stream(), self.lib
         H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
         batches, ws, Bs, noise, srcs, aux = ctx["batches"], ctx["ws"], ctx["Bs"], ctx["noise"], ctx["srcs"], ctx["aux"]
+        if adam is not None:
+            if self.adam_m is None:
+                self.adam_m = torch.zeros_like(self.params.flat)
+                self.adam_v = torch.zeros_like(self.params.flat)
+            with self._branch(0, "tick", lane=1):  # the step count of this update, off the critical path
+                L.check(lib.spv_adam_tick(L.ptr(self.step_dev), self._stream()), "spv_adam_tick")
+            tick_events = self._pending.pop((0, "tick"), [])
         # ---------------- decoders
         for g in self._fork_groups():
             bt, w, st = batches[g], ws[g], self._stream()
@@ -622,6 +634,7 @@ class StepEngine:
             with self._branch(g, "wgrad"):
                 self._gemm(L.ptr(w.dah), zzp, L.ptr(self.Gd(g, "Wh")), HD, KZ, B, lda=HD, ldb=KMIX, ldc=KZ, ta=1,
                            splits=w.splits_b, ws=w.ws2)
+            with self._branch(g, "wgrad1", lane=1):
                 L.check(lib.spv_colsum(L.ptr(w.dah), HD, B, HD, L.ptr(self.Gd(g, "bh")), self._stream()), "spv_colsum")
             gb = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), Qp, Qs, w.genec, w.colsum, w.zmean, w.zcov,
                               self.Gd(g, "Wp"), self.Gd(g, "Ws"), self.Gd(g, "gp"), self.Gd(g, "bp"), self.Gd(g, "gs"),
@@ -662,8 +675,18 @@ class StepEngine:
                                    L.ptr(self.P(g, "ghd")), L.ptr(w.bn_hd_mean), L.ptr(w.bn_hd_istd), L.ptr(self.Gd(g, "ghd")),
                                    L.ptr(self.Gd(g, "bthd")), st), "spv_bn_bwd")
             drs = w.dr.data_ptr() + 4 * 2 * P
-            with self._branch(g, "wgrad"):
+            if adam is not None:  # every decoder gradient of this group is final: update that range now
+                self._join(g, "wgrad")
+                self._join(g, "wgrad1")
+                with self._branch(g, "adam", lane=1):
+                    for ev in tick_events:
+                        torch.cuda.current_stream(self.device).wait_event(ev)
+                    lo = self.params.offsets[g]["Wp"][0]
+                    hi = self.params.offsets[g + 1]["W1"][0] if g + 1 < len(self.d.genes) else self.params.numel
+                    self._adam_range(lo, hi, adam, max_blocks=int(__import__("os").environ.get("SPV_ADAM_BLOCKS", "296")))
+            with self._branch(g, "wgrad1", lane=1):
                 L.check(lib.spv_colsum(L.ptr(w.dr), NST, B, NST, L.ptr(self.Gd(g, "bhd")), self._stream()), "spv_colsum")
+            with self._branch(g, "wgrad"):
                 self._gemm(L.ptr(w.dr), L.ptr(w.h2), L.ptr(self.Gd(g, "Whp")), 2 * P, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1,
                            splits=w.splits_b, ws=w.ws2)
                 self._gemm(drs, w.h2.data_ptr() + 4 * H, L.ptr(self.Gd(g, "Whs")), 2 * S, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1,
@@ -674,9 +697,9 @@ class StepEngine:
             scale = 1.0 / (1.0 - self.dropout_rate) if self.dropout_rate > 0 else 1.0
             L.check(lib.spv_relu_bwd(L.ptr(w.dh2), 2 * H, L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, scale, st),
                     "spv_relu_bwd")
-            with self._branch(g, "wgrad"):
+            with self._branch(g, "wgrad1", lane=1):
                 self._gemm(L.ptr(w.dh2), L.ptr(w.h1), L.ptr(self.Gd(g, "W2")), H, H, B, lda=2 * H, ldb=2 * H, ldc=H, ta=1,
-                           batch=2, sA=H, sB=H, sC=H * H, splits=w.splits_b, ws=w.ws2)
+                           batch=2, sA=H, sB=H, sC=H * H, splits=w.splits_b, ws=w.ws3)
                 L.check(lib.spv_colsum(L.ptr(w.dh2), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b2")), self._stream()), "spv_colsum")
             self._gemm(L.ptr(w.dh2), L.ptr(self.P(g, "W2")), L.ptr(w.dh1), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, batch=2, sA=H,
                        sB=H * H, sC=H)
@@ -688,9 +711,13 @@ class StepEngine:
             else:
                 self._gemm(L.ptr(w.dh1), xptr, L.ptr(self.Gd(g, "W1")), 2 * H, G, B, lda=2 * H, ldb=ldx, ldc=G, ta=1, srcB=src,
                            rowsB=bt.rows)
-            with self._branch(g, "wgrad"):
+            with self._branch(g, "wgrad1", lane=1):
                 L.check(lib.spv_colsum(L.ptr(w.dh1), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b1")), self._stream()), "spv_colsum")
             self._join(g)
+            if adam is not None:  # encoder range of this group
+                for ev in tick_events:
+                    torch.cuda.current_stream(self.device).wait_event(ev)
+                self._adam_range(self.params.offsets[g]["W1"][0], self.params.offsets[g]["Wp"][0], adam)
 
     # -------------------------------------------------------------------------------- optimiser
     def adam_step(self, lr=1e-3, betas=(0.9, 0.999), eps=0.01, weight_decay=1e-6, grad_scale=1.0):
@@ -704,7 +731,19 @@ class StepEngine:
                                   L.ptr(self.step_dev), L.ptr(self.adam_ticket), len(segs),
                                   L.ll_array([s[0] for s in segs]), L.int_array([s[1] for s in segs]),
                                   L.int_array([s[2] for s in segs]), L.ptr_array([s[3] for s in segs]),
-                                  L.ll_array([s[4] for s in segs]), st), "spv_adam")
+                                  L.ll_array([s[4] for s in segs]), 0, st), "spv_adam")
+
+    def _adam_range(self, lo, hi, cfg, max_blocks=0):
+        """Adam on the flat parameter range [lo, hi); *step already holds this update's index (spv_adam_tick)"""
+        segs = [s for s in self._stage_segments() if lo <= s[0] < hi] if (self.bf16 and self.stage_in_adam) else []
+        betas = cfg.get("betas", (0.9, 0.999))
+        off = 4 * lo
+        L.check(self.lib.spv_adam(self.params.flat.data_ptr() + off, self.grads.data_ptr() + off, self.adam_m.data_ptr() + off,
+                                  self.adam_v.data_ptr() + off, hi - lo, cfg["lr"], betas[0], betas[1], cfg["eps"],
+                                  cfg["weight_decay"], cfg.get("grad_scale", 1.0), L.ptr(self.step_dev), None, len(segs),
+                                  L.ll_array([s[0] - lo for s in segs]), L.int_array([s[1] for s in segs]),
+                                  L.int_array([s[2] for s in segs]), L.ptr_array([s[3] for s in segs]),
+                                  L.ll_array([s[4] for s in segs]), max_blocks, self._stream()), "spv_adam")
 
     def _stage_segments(self):
         """(flat offset, rows, cols, bf16 destination, destination row pitch) of the weights the tensor-core path reads"""

@@ -14,6 +14,7 @@ Index semantics restated from the reference (bit-exact contract, SURVEY.md secti
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -85,6 +86,7 @@ class TrainLoop:
         self.n_epochs_kl_warmup = n_epochs_kl_warmup
         self.epoch = 0
         self.grad_sync = None  # optional callable(engine) run between backward and the optimiser step (data parallel)
+        self.early_adam = os.environ.get("SPV_EARLY_ADAM", "1") == "1"  # A/B switch for the per-range optimiser step
         # this loop owns the optimiser step: Adam also refreshes the bf16 tensor-core copies of the large weights
         # (largest staged block must stay below 2^24 elements, the range of the kernel's index arithmetic)
         if engine.bf16 and max(engine.d.genes) * max(engine.d.KMIX, 2 * engine.d.n_hidden) < (1 << 24):
@@ -98,9 +100,12 @@ class TrainLoop:
     def step(self, batches: Sequence[GroupBatch], noise: Optional[Noise] = None):
         e = self.engine
         e.forward(batches, training=True, noise=noise)
-        e.backward()
-        gs = self.grad_sync(e) if self.grad_sync is not None else 1.0
-        e.adam_step(lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=gs)
+        if self.grad_sync is None and self.early_adam:  # single GPU: the optimiser step is interleaved with the backward
+            e.backward(adam={"lr": self.lr, "eps": self.eps, "weight_decay": self.weight_decay})
+        else:
+            e.backward()
+            gs = self.grad_sync(e) if self.grad_sync is not None else 1.0
+            e.adam_step(lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=gs)
         return e.loss_terms()
 
     def capture(self, batches: Sequence[GroupBatch], noise: Optional[Noise] = None) -> "torch.cuda.CUDAGraph":
