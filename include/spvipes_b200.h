@@ -55,6 +55,8 @@ int spv_tc_gemm(int a_mn, int b_mn, const void* A, long long lda, const void* B,
                 int N, int K, const float* bias, int relu, int accumulate, int splits, float* ws, void* stream);
 /* bf16 staging of GEMM operands: dst[r, :C] = bf16(src[r, :C]), zero padded up to ld_dst */
 int spv_to_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, int R, int C, void* stream);
+/* column block: dst[r, :C] = bf16(src[r, :C]), zeros up to `width`; the other columns of dst (row pitch ld_dst) are untouched */
+int spv_to_bf16_block(const float* src, long long ld_src, void* dst, long long ld_dst, int R, int C, int width, void* stream);
 /* T[b, :G] = bf16(log1p(X[rows[b], :G])), zero padded to ld_dst (a multiple of 8)   module/spVIPESmodule.py:428-433;
  * lib (optional, [B]): library size log(sum_g log1p(x[b,g])) from the same pass   module/spVIPESmodule.py:433-435 */
 int spv_counts_to_bf16(int src, const void* X, long long ldx, const int* rows, void* dst, long long ld_dst, int B, int G,
@@ -133,6 +135,12 @@ int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld
 int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
                       const void* wstack_bf16, long long ld_w, int Gp, int B, int G, int HD, int P, int S, int store_pi,
                       void* stream);
+/* tensor-core version of phase 1 of spv_dec_nb_fwd (bf16 path): softmax normalisers rowc[b, 0:2] = lib[b] -
+ * logsumexp_g(y_p), (y_s) from the latent k-block of amix_bf16 against the folded weights in wstack_bf16 (spv_dec_fold);
+ * part_stats: scratch of 2 * ceil(G/64) * B * 4 floats.   nn/networks.py:318-320, module/spVIPESmodule.py:751-757 */
+int spv_dec_stats_tc(const void* amix_bf16, long long ld_amixb, const void* wstack_bf16, long long ld_w, int Gp,
+                     const float* genec, const float* lib, float* part_stats, float* rowc, int B, int G, int HD, int P, int S,
+                     void* stream);
 /* floats spv_dec_nb_fwd_tc needs in part_nb (ptrs[11]) for a [B, G] problem */
 long long spv_dec_nb_part_floats(int B, int G);
 /* rec[b] (ptrs[16] of the forward) and the softmax-backward row sums rowc[:, 2:4] from the row partials part_nb that

@@ -282,6 +282,13 @@ __global__ void rowstat_kernel(const float* __restrict__ part, int nTG, int B, c
     }
 }
 
+// launch helper shared with the tensor-core statistics kernel (nb_tc.cu)
+int spv_internal_rowstat(const float* part, int nparts, int B, const float* lib, float* rowc, cudaStream_t st) {
+    rowstat_kernel<<<(B + 7) / 8, 256, 0, st>>>(part, nparts, B, lib, rowc);
+    SPV_CHECK_LAUNCH();
+    return SPV_OK;
+}
+
 __global__ void rownb_kernel(const float* __restrict__ part, int nTG, int B, float* __restrict__ rowc, float* __restrict__ rec) {
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= B) return;

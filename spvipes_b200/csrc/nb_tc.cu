@@ -254,6 +254,114 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Softmax statistics of the two factor-regressor branches on the tensor cores: y = zz W'^T + c is one 64-wide k-block
+// (the latent columns of the bf16 operand) against the folded weights, so a 128 x 64 tile costs 8 MMAs; each epilogue thread
+// (= cell) reduces its 32 columns to (max, sum exp) per branch.  Replaces the fp32 SIMT pass (19.5 us per group at C2,
+// instruction bound); using the same bf16-rounded logits as the likelihood kernels also makes the normaliser consistent
+// with the rho they compute.  part_stats [2 * ceil(G/64), B, 4] = (max_p, sum_p, max_s, sum_s), natural units.
+// ---------------------------------------------------------------------------------------
+constexpr int ST_SMEM = A_BYTES + 2 * B_BYTES + 1024 + 2 * BN * 4 + 64;
+
+__global__ void __launch_bounds__(THREADS, 2) nb_tc_stats_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                 const __grid_constant__ CUtensorMap mapZ, const float* __restrict__ genec,
+                                                                 float* __restrict__ part_stats, int B, int G, int kb_z, int Gp) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = tc::smem_u32(smem_raw);
+    uint8_t* tiles = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint8_t* z_tiles = tiles + A_BYTES;
+    float* s_c = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);  // [2][BN]: cp log2e, cs log2e
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_c + 2 * BN);
+    uint64_t* tmem_full = full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&mapA);
+        tc::tma_prefetch_desc(&mapZ);
+        tc::mbar_init(full, 1);
+        tc::mbar_init(tmem_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_slot, 128);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            tc::mbar_expect_tx(full, A_BYTES + 2 * B_BYTES);
+            tc::tma_load_2d(&mapA, full, tiles, kb_z * BK, m0);
+            tc::tma_load_2d(&mapZ, full, z_tiles, kb_z * BK, n0);
+            tc::tma_load_2d(&mapZ, full, z_tiles + B_BYTES, kb_z * BK, Gp + n0);
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, false, false);
+            tc::mbar_wait(full, 0);
+            tc::fence_after_sync();
+            const uint32_t a_base = tc::smem_u32(tiles), zp_base = tc::smem_u32(z_tiles), zs_base = zp_base + B_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+                tc::umma_bf16(tmem_base, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zp_base + kk * 32, 16, 1024), idesc,
+                              kk > 0 ? 1u : 0u);
+                tc::umma_bf16(tmem_base + BN, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zs_base + kk * 32, 16, 1024), idesc,
+                              kk > 0 ? 1u : 0u);
+            }
+            tc::umma_commit(tmem_full);
+        }
+    } else {
+        const int et = threadIdx.x - 64;
+        const long Gl = G;
+        for (int i = et; i < 2 * BN; i += EPI_THREADS) {
+            const int k = i / BN, c = i - k * BN, g = n0 + c;
+            s_c[i] = g < G ? __ldg(genec + (k == 0 ? GC_CPL : GC_CSL) * Gl + g) : 0.0f;
+        }
+        const int e = warp - 2, q = warp & 3, half = e >> 2;
+        const int m = m0 + q * 32 + lane;
+        asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
+        tc::mbar_wait(tmem_full, 0);
+        tc::fence_after_sync();
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float yp[WCOLS], ys[WCOLS];  // this cell's 32 + 32 logits of the tile half, base-2 units
+        float Mp = -INFINITY, Ms = -INFINITY;
+#pragma unroll
+        for (int j4 = 0; j4 < WCOLS; j4 += 4) {
+            const int c0 = half * WCOLS + j4;
+            uint32_t rp4[4], rs4[4];
+            tc::tmem_ld4(lane_addr + (uint32_t)c0, rp4);
+            tc::tmem_ld4(lane_addr + (uint32_t)(BN + c0), rs4);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const bool ok = n0 + c0 + jj < G;
+                yp[j4 + jj] = ok ? fmaf(__uint_as_float(rp4[jj]), NB_LOG2E, s_c[c0 + jj]) : -INFINITY;
+                ys[j4 + jj] = ok ? fmaf(__uint_as_float(rs4[jj]), NB_LOG2E, s_c[BN + c0 + jj]) : -INFINITY;
+                Mp = fmaxf(Mp, yp[j4 + jj]);
+                Ms = fmaxf(Ms, ys[j4 + jj]);
+            }
+        }
+        float Sp = 0.0f, Ss = 0.0f;
+        if (Mp > -INFINITY) {  // at least one valid column in this half (the tile may end inside it)
+#pragma unroll
+            for (int j = 0; j < WCOLS; ++j) {
+                Sp += fast_ex2(yp[j] - Mp);
+                Ss += fast_ex2(ys[j] - Ms);
+            }
+        }
+        if (m < B) {
+            float4 o = make_float4(Mp * NB_LN2, Sp, Ms * NB_LN2, Ss);
+            *reinterpret_cast<float4*>(part_stats + ((long)(blockIdx.x * 2 + half) * B + m) * 4) = o;
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc(tmem_base, 128);
+    }
+}
+
 __global__ void rownb_tc_kernel(const float* __restrict__ part, int nPart, int B, float* __restrict__ rowc, float* __restrict__ rec) {
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -332,6 +440,35 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
     else return SPV_ERR_ARG;
     SPV_CHECK_LAUNCH();
     return SPV_OK;
+}
+
+int spv_internal_rowstat(const float* part, int nparts, int B, const float* lib, float* rowc, cudaStream_t st);
+
+// Softmax normalisers of the two branches on the tensor cores: rowc[b, 0:2] = lib[b] - logsumexp_g(y_p / y_s)   (phase 1 of
+// spv_dec_nb_fwd for the bf16 path).  part_stats needs 2 * ceil(G/64) * B * 4 floats.
+extern "C" int spv_dec_stats_tc(const void* amix_bf16, long long ld_amixb, const void* wstack_bf16, long long ld_w, int Gp,
+                                const float* genec, const float* lib, float* part_stats, float* rowc, int B, int G, int HD, int P,
+                                int S, void* stream) {
+    if (!amix_bf16 || !wstack_bf16 || !genec || !lib || !part_stats || !rowc || Gp < G || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0)
+        return SPV_ERR_ARG;
+    if ((HD % BK) != 0 || P + S > BK) return SPV_ERR_ARG;
+    const int K = HD + P + S;
+    const void* wz_bf16 = reinterpret_cast<const __nv_bfloat16*>(wstack_bf16) + (size_t)Gp * ld_w;
+    CUtensorMap ma, mz;
+    int rc = spv_make_tensor_map_bf16(&ma, amix_bf16, (unsigned long long)K, (unsigned long long)B, (unsigned long long)ld_amixb, 64, BM);
+    if (rc != SPV_OK) return rc;
+    rc = spv_make_tensor_map_bf16(&mz, wz_bf16, (unsigned long long)K, (unsigned long long)(2 * Gp), (unsigned long long)ld_w, 64, BN);
+    if (rc != SPV_OK) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(nb_tc_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM) != cudaSuccess) return SPV_ERR_LAUNCH;
+        configured = true;
+    }
+    dim3 grid((G + BN - 1) / BN, (B + BM - 1) / BM);
+    nb_tc_stats_kernel<<<grid, THREADS, ST_SMEM, st>>>(ma, mz, genec, part_stats, B, G, HD / BK, Gp);
+    SPV_CHECK_LAUNCH();
+    return spv_internal_rowstat(part_stats, 2 * (int)grid.x, B, lib, rowc, st);
 }
 
 // floats spv_dec_nb_fwd_tc needs in part_nb (either kernel variant)

@@ -305,6 +305,28 @@ extern "C" int spv_to_bf16(const float* src, long long ld_src, void* dst, long l
     return SPV_OK;
 }
 
+// column block: dst[r, c] = bf16(src[r, c]) for c < C, 0 for C <= c < width; columns beyond `width` of dst are left untouched
+__global__ void to_bf16_block_kernel(const float* __restrict__ src, long ld_src, __nv_bfloat16* __restrict__ dst, long ld_dst, int R,
+                                     int C, int width) {
+    long total = (long)R * width;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % width);
+        long r = i / width;
+        dst[r * ld_dst + c] = __float2bfloat16(c < C ? src[r * ld_src + c] : 0.0f);
+    }
+}
+
+extern "C" int spv_to_bf16_block(const float* src, long long ld_src, void* dst, long long ld_dst, int R, int C, int width,
+                                 void* stream) {
+    if (!src || !dst || R <= 0 || C <= 0 || width < C || ld_dst < width) return SPV_ERR_ARG;
+    long total = (long)R * width;
+    int blocks = (int)min((long)148 * 16, (total + 255) / 256);
+    to_bf16_block_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst),
+                                                                                     ld_dst, R, C, width);
+    SPV_CHECK_LAUNCH();
+    return SPV_OK;
+}
+
 // T[b, g] = bf16(log1p(X[rows[b], g]))   (the encoder's input, reference module/spVIPESmodule.py:428-433), zero padded to ld_dst,
 // and optionally library[b] = log(sum_g log1p(x[b, g]))  (reference :433-435) from the same pass over the row.
 // One CTA per cell.  uint16 counts: 8 genes per 16-byte load when the row is 16-byte aligned, log1p of counts < 256 from a

@@ -178,7 +178,7 @@ class _GroupWS:
         self.wfold, self.genec = f(G, KZ), f(L.GENEC_ROWS, G)
         self.ah = f(B, HD)
         self.bn_h_mean, self.bn_h_istd = f(HD), f(HD)
-        self.part_stats = f(self.nTG, B, 4)
+        self.part_stats = f(2 * self.nTG, B, 4)
         self.part_nb = f(max(2 * self.nTG * B * 3, int(L.load().spv_dec_nb_part_floats(B, G))))
         self.rowc = f(B, 4)
         self.pi = f(B, G)
@@ -445,8 +445,17 @@ class StepEngine:
                                 self.Bf(g, "rm_s"), self.Bf(g, "rv_s"), zzp, w.zsum, w.cov_part, w.wfold, w.genec, w.zmean,
                                 w.zcov])
             wz = w.Wstack.data_ptr() + 2 * w.Gp * w.KMp if self.fused_nb else None
+            if self.fused_nb:  # latent columns of the bf16 operand [hm | zz]: all the softmax statistics need
+                L.check(lib.spv_to_bf16_block(zzp, KMIX, w.amixb.data_ptr() + 2 * HD, w.KMp, B, KZ, w.KMp - HD, st),
+                        "spv_to_bf16_block")
             L.check(lib.spv_dec_fold(fold, KMIX, B, G, P, S, tr, DEC_BN_EPS, DEC_BN_MOM, wz, w.KMp if self.fused_nb else 0,
                                      w.Gp, HD, st), "spv_dec_fold")
+            if self.fused_nb:  # softmax normalisers on the tensor cores, next to the hidden layer of the mixing net
+                self._join(g, "lib")
+                with self._branch(g, "stats"):
+                    L.check(lib.spv_dec_stats_tc(L.ptr(w.amixb), w.KMp, L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.genec), L.ptr(w.lib),
+                                                 L.ptr(w.part_stats), L.ptr(w.rowc), B, G, HD, P, S, self._stream()),
+                            "spv_dec_stats_tc")
             self._gemm(zzp, L.ptr(self.P(g, "Wh")), L.ptr(w.ah), B, HD, KZ, lda=KMIX, ldb=KZ, ldc=HD, tb=1,
                        bias=L.ptr(self.P(g, "bh")))
             L.check(lib.spv_bn_fwd(L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, B, HD, L.ptr(self.P(g, "gh")), L.ptr(self.P(g, "bth")),
@@ -454,9 +463,14 @@ class StepEngine:
                                    L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), tr, 1, st), "spv_bn_fwd")
             dptrs = self._dec_ptrs(g, w, xptr, bt.rows, with_grad)
             self._join(g, "lib")
-            L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 1, st), "spv_dec_nb_fwd")
+            if not self.fused_nb:
+                L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 1, st), "spv_dec_nb_fwd")
             evs = next(self.nb_events) if self.nb_events is not None else None
-            if self.bf16:  # mixture logits on the tensor cores, consumed by the NB sweep
+            if self.fused_nb:  # hidden-layer columns of the bf16 operand (the latent columns are in place already)
+                L.check(lib.spv_to_bf16_block(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, HD, HD, st), "spv_to_bf16_block")
+                self._join(g, "wm")
+                self._join(g, "stats")
+            elif self.bf16:  # mixture logits on the tensor cores, consumed by the NB sweep
                 L.check(lib.spv_to_bf16(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX, st), "spv_to_bf16")
                 self._join(g, "wm")
             if evs is not None:
