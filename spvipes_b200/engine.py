@@ -353,6 +353,16 @@ class StepEngine:
             for ev in self._pending.pop(key):
                 cur.wait_event(ev)
 
+    def _hidden_mix(self, g, w, B, tr, zzp):
+        """hm = relu(BatchNorm(zz Wh^T + bh)) into the first HD columns of amix   (reference nn/networks.py:322-323)"""
+        d = self.d
+        self._gemm(zzp, L.ptr(self.P(g, "Wh")), L.ptr(w.ah), B, HD, d.KZ, lda=d.KMIX, ldb=d.KZ, ldc=HD, tb=1,
+                   bias=L.ptr(self.P(g, "bh")))
+        L.check(self.lib.spv_bn_fwd(L.ptr(w.ah), HD, L.ptr(w.amix), d.KMIX, B, HD, L.ptr(self.P(g, "gh")),
+                                    L.ptr(self.P(g, "bth")), DEC_BN_EPS, DEC_BN_MOM, L.ptr(self.Bf(g, "rm_h")),
+                                    L.ptr(self.Bf(g, "rv_h")), L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), tr, 1, self._stream()),
+                 "spv_bn_fwd")
+
     def workspace(self, B0, B1, with_grad=True):
         key = (B0, B1, with_grad)
         if key not in self._ws:
@@ -445,31 +455,31 @@ class StepEngine:
                                 self.Bf(g, "rm_s"), self.Bf(g, "rv_s"), zzp, w.zsum, w.cov_part, w.wfold, w.genec, w.zmean,
                                 w.zcov])
             wz = w.Wstack.data_ptr() + 2 * w.Gp * w.KMp if self.fused_nb else None
-            if self.fused_nb:  # latent columns of the bf16 operand [hm | zz]: all the softmax statistics need
+            if self.fused_nb:
+                # hidden layer of the mixing net (needs only zz) on the auxiliary stream, beside latent stats / fold / normalisers
+                with self._branch(g, "hm"):
+                    self._hidden_mix(g, w, B, tr, zzp)
+                    L.check(lib.spv_to_bf16_block(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, HD, HD, self._stream()),
+                            "spv_to_bf16_block")
+                # latent columns of the bf16 operand [hm | zz]: all the softmax statistics need
                 L.check(lib.spv_to_bf16_block(zzp, KMIX, w.amixb.data_ptr() + 2 * HD, w.KMp, B, KZ, w.KMp - HD, st),
                         "spv_to_bf16_block")
             L.check(lib.spv_dec_fold(fold, KMIX, B, G, P, S, tr, DEC_BN_EPS, DEC_BN_MOM, wz, w.KMp if self.fused_nb else 0,
                                      w.Gp, HD, st), "spv_dec_fold")
-            if self.fused_nb:  # softmax normalisers on the tensor cores, next to the hidden layer of the mixing net
+            if self.fused_nb:  # softmax normalisers on the tensor cores (main stream: latent stats -> fold -> normalisers)
                 self._join(g, "lib")
-                with self._branch(g, "stats"):
-                    L.check(lib.spv_dec_stats_tc(L.ptr(w.amixb), w.KMp, L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.genec), L.ptr(w.lib),
-                                                 L.ptr(w.part_stats), L.ptr(w.rowc), B, G, HD, P, S, self._stream()),
-                            "spv_dec_stats_tc")
-            self._gemm(zzp, L.ptr(self.P(g, "Wh")), L.ptr(w.ah), B, HD, KZ, lda=KMIX, ldb=KZ, ldc=HD, tb=1,
-                       bias=L.ptr(self.P(g, "bh")))
-            L.check(lib.spv_bn_fwd(L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, B, HD, L.ptr(self.P(g, "gh")), L.ptr(self.P(g, "bth")),
-                                   DEC_BN_EPS, DEC_BN_MOM, L.ptr(self.Bf(g, "rm_h")), L.ptr(self.Bf(g, "rv_h")),
-                                   L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), tr, 1, st), "spv_bn_fwd")
+                L.check(lib.spv_dec_stats_tc(L.ptr(w.amixb), w.KMp, L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.genec), L.ptr(w.lib),
+                                             L.ptr(w.part_stats), L.ptr(w.rowc), B, G, HD, P, S, st), "spv_dec_stats_tc")
+                self._join(g, "hm")
+            else:
+                self._hidden_mix(g, w, B, tr, zzp)
             dptrs = self._dec_ptrs(g, w, xptr, bt.rows, with_grad)
             self._join(g, "lib")
             if not self.fused_nb:
                 L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 1, st), "spv_dec_nb_fwd")
             evs = next(self.nb_events) if self.nb_events is not None else None
-            if self.fused_nb:  # hidden-layer columns of the bf16 operand (the latent columns are in place already)
-                L.check(lib.spv_to_bf16_block(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, HD, HD, st), "spv_to_bf16_block")
+            if self.fused_nb:
                 self._join(g, "wm")
-                self._join(g, "stats")
             elif self.bf16:  # mixture logits on the tensor cores, consumed by the NB sweep
                 L.check(lib.spv_to_bf16(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX, st), "spv_to_bf16")
                 self._join(g, "wm")
