@@ -353,6 +353,12 @@ class StepEngine:
             for ev in self._pending.pop(key):
                 cur.wait_event(ev)
 
+    def _gene_bwd(self, g, w, Qp, Qs, ldq, B, G):
+        gb = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), Qp, Qs, w.genec, w.colsum, w.zmean, w.zcov,
+                          self.Gd(g, "Wp"), self.Gd(g, "Ws"), self.Gd(g, "gp"), self.Gd(g, "bp"), self.Gd(g, "gs"),
+                          self.Gd(g, "bs"), self.Gd(g, "px_r"), self.Gd(g, "bm"), w.vpart, w.mpart])
+        L.check(self.lib.spv_dec_gene_bwd(gb, ldq, B, G, self.d.n_private, self.d.n_shared, self._stream()), "spv_dec_gene_bwd")
+
     def _hidden_mix(self, g, w, B, tr, zzp):
         """hm = relu(BatchNorm(zz Wh^T + bh)) into the first HD columns of amix   (reference nn/networks.py:322-323)"""
         d = self.d
@@ -390,6 +396,11 @@ class StepEngine:
         noise = noise or Noise()
         tr = 1 if training else 0
         srcs = []
+        if self.mode == "label":  # integer pairing needs only the labels: off the critical path, beside the encoders
+            if batches[0].labels is None or batches[1].labels is None:
+                raise ValueError("Labels are required when using label-based POE.")  # reference :401-402
+            with self._branch(0, "pair", lane=1):
+                self._pair_label(batches, ws, Bs)
         convert = self.bf16 and not (self.stage_in_adam and self._staged_version == self.params.flat._version)
         # ---------------- encoders (reference nn/networks.py:119-125, module :428-448)
         for g in self._fork_groups():
@@ -426,10 +437,12 @@ class StepEngine:
                     L.check(lib.spv_dropout(L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, self.dropout_rate, self.seed,
                                             8 + g, L.ptr(self.step_dev), st), "spv_dropout")
             bhd = self.P(g, "bhd")
-            self._gemm(L.ptr(w.h2), L.ptr(self.P(g, "Whp")), L.ptr(w.r), B, 2 * P, H, lda=2 * H, ldb=H, ldc=NST, tb=1,
-                       bias=L.ptr(bhd))
+            with self._branch(g, "headp"):  # the private and the shared heads are independent
+                self._gemm(L.ptr(w.h2), L.ptr(self.P(g, "Whp")), L.ptr(w.r), B, 2 * P, H, lda=2 * H, ldb=H, ldc=NST, tb=1,
+                           bias=L.ptr(bhd))
             self._gemm(w.h2.data_ptr() + 4 * H, L.ptr(self.P(g, "Whs")), w.r.data_ptr() + 4 * 2 * P, B, 2 * S, H, lda=2 * H,
                        ldb=H, ldc=NST, tb=1, bias=bhd.data_ptr() + 4 * 2 * P)
+            self._join(g, "headp")
             L.check(lib.spv_bn_fwd(L.ptr(w.r), NST, L.ptr(w.stats), NST, B, NST, L.ptr(self.P(g, "ghd")),
                                    L.ptr(self.P(g, "bthd")), ENC_BN_EPS, ENC_BN_MOM, L.ptr(self.Bf(g, "rm_hd")),
                                    L.ptr(self.Bf(g, "rv_hd")), L.ptr(w.bn_hd_mean), L.ptr(w.bn_hd_istd), tr, 0, st), "spv_bn_fwd")
@@ -516,10 +529,8 @@ class StepEngine:
     def _pairing(self, batches, ws, Bs):
         lib, st, d = self.lib, self._stream(), self.d
         aux = {}
-        if self.mode == "label":
-            if batches[0].labels is None or batches[1].labels is None:
-                raise ValueError("Labels are required when using label-based POE.")  # reference :401-402
-            self._pair_label(batches, ws, Bs)
+        if self.mode == "label":  # launched at the start of forward
+            self._join(0, "pair")
             return aux
         if self.plan is None:
             raise ValueError("a transport plan is required for the OT PoE modes")
@@ -616,13 +627,17 @@ class StepEngine:
                 with self._branch(g, "wgrad"):  # d Wm = dpi^T [hm | zz]
                     self._tc_gemm(L.ptr(w.D3), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=Gp3, ldb=w.KMp, ldc=KMIX,
                                   a_mn=1, b_mn=1)
-                # [Qp | .] = dyp^T zz, [. | Qs] = dys^T zz in one GEMM over the stacked rows (rows g and Gp + g)
-                self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, w.amixb.data_ptr() + 2 * HD, L.ptr(w.CQ), 2 * w.Gp, KZ, B, lda=Gp3,
-                              ldb=w.KMp, ldc=KZ, a_mn=1, b_mn=1)
+                Qp, Qs, ldq, dzraw = w.CQ.data_ptr(), w.CQ.data_ptr() + 4 * (w.Gp * KZ + P), KZ, None
+                # per-gene BatchNorm backward chain on the second auxiliary stream: it needs Q and the column sums, not
+                # d [hm | zz], so it runs beside the input-gradient GEMM and the hidden layer's backward
+                with self._branch(g, "gene", lane=1):
+                    # [Qp | .] = dyp^T zz, [. | Qs] = dys^T zz in one GEMM over the stacked rows (rows g and Gp + g)
+                    self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, w.amixb.data_ptr() + 2 * HD, L.ptr(w.CQ), 2 * w.Gp, KZ, B, lda=Gp3,
+                                  ldb=w.KMp, ldc=KZ, a_mn=1, b_mn=1)
+                    self._gene_bwd(g, w, Qp, Qs, ldq, B, G)
                 # d [hm | zz] = dpi Wm + dyp W'p + dys W's: one GEMM against the stacked weights
                 self._tc_gemm(L.ptr(w.D3), L.ptr(w.Wstack), L.ptr(w.damix), B, KMIX, Gp3, lda=Gp3, ldb=w.KMp, ldc=KMIX, b_mn=1,
                               splits=w.tc_splits_damix3, ws=w.ws)
-                Qp, Qs, ldq, dzraw = w.CQ.data_ptr(), w.CQ.data_ptr() + 4 * (w.Gp * KZ + P), KZ, None
             else:
                 L.check(lib.spv_dec_nb_bwd(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, KMIX, B, G, HD, P, S,
                                            -float(grad_scale) / B, L.ptr(w.colsum), L.ptr(w.dpib) if self.bf16 else None,
@@ -660,11 +675,10 @@ class StepEngine:
                            splits=w.splits_b, ws=w.ws2)
             with self._branch(g, "wgrad1", lane=1):
                 L.check(lib.spv_colsum(L.ptr(w.dah), HD, B, HD, L.ptr(self.Gd(g, "bh")), self._stream()), "spv_colsum")
-            gb = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), Qp, Qs, w.genec, w.colsum, w.zmean, w.zcov,
-                              self.Gd(g, "Wp"), self.Gd(g, "Ws"), self.Gd(g, "gp"), self.Gd(g, "bp"), self.Gd(g, "gs"),
-                              self.Gd(g, "bs"), self.Gd(g, "px_r"), self.Gd(g, "bm"), w.vpart, w.mpart])
-            L.check(lib.spv_dec_gene_bwd(gb, ldq, B, G, P, S, st), "spv_dec_gene_bwd")
+            if not self.fused_nb:
+                self._gene_bwd(g, w, Qp, Qs, ldq, B, G)
             self._join(g, "hid")
+            self._join(g, "gene")
             L.check(lib.spv_dec_dzz_combine(w.damix.data_ptr() + 4 * HD, KMIX, dzraw, L.ptr(w.vpart), L.ptr(w.mpart),
                                             w.nGB, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S, st), "spv_dec_dzz_combine")
         # ---------------- PoE
@@ -699,6 +713,8 @@ class StepEngine:
                                    L.ptr(self.P(g, "ghd")), L.ptr(w.bn_hd_mean), L.ptr(w.bn_hd_istd), L.ptr(self.Gd(g, "ghd")),
                                    L.ptr(self.Gd(g, "bthd")), st), "spv_bn_bwd")
             drs = w.dr.data_ptr() + 4 * 2 * P
+            with self._branch(g, "dh2p"):  # first on its auxiliary stream: this one is on the critical path
+                self._gemm(L.ptr(w.dr), L.ptr(self.P(g, "Whp")), L.ptr(w.dh2), B, H, 2 * P, lda=NST, ldb=H, ldc=2 * H)
             if adam is not None:  # every decoder gradient of this group is final: update that range now
                 self._join(g, "wgrad")
                 self._join(g, "wgrad1")
@@ -715,8 +731,8 @@ class StepEngine:
                            splits=w.splits_b, ws=w.ws2)
                 self._gemm(drs, w.h2.data_ptr() + 4 * H, L.ptr(self.Gd(g, "Whs")), 2 * S, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1,
                            splits=w.splits_b, ws=w.ws2)
-            self._gemm(L.ptr(w.dr), L.ptr(self.P(g, "Whp")), L.ptr(w.dh2), B, H, 2 * P, lda=NST, ldb=H, ldc=2 * H)
             self._gemm(drs, L.ptr(self.P(g, "Whs")), w.dh2.data_ptr() + 4 * H, B, H, 2 * S, lda=NST, ldb=H, ldc=2 * H)
+            self._join(g, "dh2p")
             mask = noise.drop[g] if noise.drop is not None else None
             scale = 1.0 / (1.0 - self.dropout_rate) if self.dropout_rate > 0 else 1.0
             L.check(lib.spv_relu_bwd(L.ptr(w.dh2), 2 * H, L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, scale, st),
