@@ -751,8 +751,8 @@ class StepEngine:
             else:
                 self._gemm(L.ptr(w.dh1), xptr, L.ptr(self.Gd(g, "W1")), 2 * H, G, B, lda=2 * H, ldb=ldx, ldc=G, ta=1, srcB=src,
                            rowsB=bt.rows)
-            with self._branch(g, "wgrad1", lane=1):
-                L.check(lib.spv_colsum(L.ptr(w.dh1), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b1")), self._stream()), "spv_colsum")
+            # last bias gradient on the main stream: queued behind the auxiliary lanes' weight-gradient GEMMs it would finish later
+            L.check(lib.spv_colsum(L.ptr(w.dh1), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b1")), st), "spv_colsum")
             self._join(g)
             if adam is not None:  # encoder range of this group
                 for ev in tick_events:
