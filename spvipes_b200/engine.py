@@ -775,7 +775,8 @@ class StepEngine:
 
     def _adam_range(self, lo, hi, cfg, max_blocks=0):
         """Adam on the flat parameter range [lo, hi); *step already holds this update's index (spv_adam_tick)"""
-        segs = [s for s in self._stage_segments() if lo <= s[0] < hi] if (self.bf16 and self.stage_in_adam) else []
+        segs = ([s for s in self._stage_segments() if s[0] < hi and lo < s[0] + s[1] * s[2]]  # any overlap with the range
+                if (self.bf16 and self.stage_in_adam) else [])
         betas = cfg.get("betas", (0.9, 0.999))
         off = 4 * lo
         L.check(self.lib.spv_adam(self.params.flat.data_ptr() + off, self.grads.data_ptr() + off, self.adam_m.data_ptr() + off,

@@ -61,3 +61,92 @@ def test_tc_gemm(a_mn, b_mn, M, N, K):
         torch.cuda.synchronize()
         err = float((C.double() - want).abs().max() / want.abs().max())
         assert err < 1e-4, (splits, err)
+
+
+@pytest.mark.parametrize("tb", [1, 0])
+@pytest.mark.parametrize("M,N,K,batch", [(512, 128, 128, 2), (512, 50, 128, 1), (512, 256, 35, 1), (300, 35, 256, 1), (77, 20, 9, 1)])
+def test_smallk_gemm(tb, M, N, K, batch):
+    """whole-K variant behind spv_gemm (K <= 256, no split, A not transposed): bias, ReLU, accumulate, batch, odd pitches"""
+    from spvipes_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    lda, ldc = K * batch + 3, N * batch + 1  # batches side by side in the columns, unaligned pitches (scalar staging path)
+    A = torch.randn(M, lda, generator=g, device="cuda")
+    Bm = torch.randn(batch, N, K, generator=g, device="cuda") if tb else torch.randn(batch, K, N, generator=g, device="cuda")
+    bias = torch.randn(batch, N, generator=g, device="cuda")
+    C0 = torch.randn(M, ldc, generator=g, device="cuda")
+    for relu, acc in ((1, 0), (0, 1)):
+        C = C0.clone()
+        L.check(lib.spv_gemm(0, 0, 0, tb, A.data_ptr(), lda, None, Bm.data_ptr(), Bm.stride(1), None, C.data_ptr(), ldc, M, N, K,
+                             batch, K, Bm.stride(0), N, bias.data_ptr(), N, relu, acc, 1, None, _stream()), "spv_gemm")
+        torch.cuda.synchronize()
+        for b in range(batch):
+            a = A[:, b * K:(b + 1) * K].double()
+            w = Bm[b].double()
+            want = a @ (w.t() if tb else w) + bias[b].double()
+            if relu:
+                want = torch.relu(want)
+            if acc:
+                want = want + C0[:, b * N:(b + 1) * N].double()
+            got = C[:, b * N:(b + 1) * N].double()
+            err = float((got - want).abs().max() / want.abs().max())
+            assert err < 1e-5, (relu, acc, b, err)
+        assert torch.equal(C[:, batch * N:], C0[:, batch * N:])  # padding column untouched
+
+
+def test_to_bf16_block():
+    from spvipes_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    src = torch.randn(100, 291, generator=g, device="cuda")
+    dst = torch.full((100, 296), 7.0, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.spv_to_bf16_block(src.data_ptr() + 4 * 256, 291, dst.data_ptr() + 2 * 256, 296, 100, 35, 40, _stream()), "to_bf16_block")
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:, 256:291], src[:, 256:291].bfloat16())
+    assert float(dst[:, 291:296].abs().max()) == 0.0
+    assert float((dst[:, :256] - 7.0).abs().max()) == 0.0
+
+
+def test_adam_ranges_and_staging():
+    """spv_adam on sub-ranges with bf16 staging == one launch over the whole vector == torch.optim.Adam semantics"""
+    from spvipes_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n, rows, cols, off = 4096 + 4 * 37, 31, 37, 1024
+    p0 = torch.randn(n, generator=g, device="cuda")
+    gr = torch.randn(n, generator=g, device="cuda")
+    m0 = torch.randn(n, generator=g, device="cuda") * 0.1
+    v0 = torch.rand(n, generator=g, device="cuda") * 0.1
+    lr, b1, b2, eps, wd, t = 1e-3, 0.9, 0.999, 0.01, 1e-6, 3
+    step = torch.full((1,), t, dtype=torch.int32, device="cuda")
+
+    def run(ranges):
+        p, m, v = p0.clone(), m0.clone(), v0.clone()
+        stage = torch.full((rows, 40), 5.0, device="cuda", dtype=torch.bfloat16)
+        for lo, hi in ranges:
+            segs = [(off - lo, rows, cols, stage, 40)] if (off < hi and lo < off + rows * cols) else []  # any overlap
+            L.check(lib.spv_adam(p.data_ptr() + 4 * lo, gr.data_ptr() + 4 * lo, m.data_ptr() + 4 * lo, v.data_ptr() + 4 * lo, hi - lo,
+                                 lr, b1, b2, eps, wd, 1.0, step.data_ptr(), None, len(segs), L.ll_array([s[0] for s in segs]),
+                                 L.int_array([s[1] for s in segs]), L.int_array([s[2] for s in segs]),
+                                 L.ptr_array([s[3] for s in segs]), L.ll_array([s[4] for s in segs]), 0, _stream()), "spv_adam")
+        torch.cuda.synchronize()
+        return p, m, v, stage
+
+    pa, ma, va, sa = run([(0, n)])
+    pb, mb, vb, sb = run([(0, 1000), (1000, 2048), (2048, n)])
+    assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb) and torch.equal(sa, sb)
+    assert torch.equal(sa[:, :cols], pa[off:off + rows * cols].view(rows, cols).bfloat16())
+    assert float((sa[:, cols:] - 5.0).abs().max()) == 0.0
+    gd = gr.double() + wd * p0.double()
+    m_ref = b1 * m0.double() + (1 - b1) * gd
+    v_ref = b2 * v0.double() + (1 - b2) * gd * gd
+    p_ref = p0.double() - lr / (1 - b1 ** t) * m_ref / (v_ref.sqrt() / (1 - b2 ** t) ** 0.5 + eps)
+    assert float((pa.double() - p_ref).abs().max()) < 1e-6
+    # ticket mode: uses *step + 1 and stores it
+    step2 = torch.full((1,), t - 1, dtype=torch.int32, device="cuda")
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    p, m, v = p0.clone(), m0.clone(), v0.clone()
+    L.check(lib.spv_adam(p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, b1, b2, eps, wd, 1.0, step2.data_ptr(),
+                         ticket.data_ptr(), 0, None, None, None, None, None, 0, _stream()), "spv_adam")
+    torch.cuda.synchronize()
+    assert int(step2) == t and int(ticket) == 0 and torch.equal(p, pa)

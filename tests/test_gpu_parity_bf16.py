@@ -105,3 +105,48 @@ def test_c1_shape_against_oracle(precision):
         assert cos > 0.999999 and rel < 1e-3, (cos, rel)
     else:
         assert cos > 0.995 and rel < 0.1, (cos, rel)
+
+
+def test_stats_tc_matches_simt_statistics():
+    """softmax normalisers from the tensor-core statistics kernel (bf16 logits) vs the fp32 SIMT phase on the same state"""
+    import torch
+    from spvipes_b200 import _lib as L
+    gd = Golden("label_tiny")
+    eng, batches, noise = engine_from_golden(gd, precision="bf16")
+    assert eng.fused_nb
+    ws = eng.forward(batches, training=True, noise=noise)
+    torch.cuda.synchronize()
+    d = eng.d
+    for g, w in enumerate(ws):
+        got = w.rowc[:, :2].clone()
+        bt = batches[g]
+        src, esz = eng._src_of(bt.X)
+        ptrs = eng._dec_ptrs(g, w, bt.X.data_ptr(), bt.rows, True)
+        L.check(eng.lib.spv_dec_nb_fwd(src, ptrs, bt.X.stride(0), d.KMIX, w.B, w.G, 256, d.n_private, d.n_shared, 1,
+                                       torch.cuda.current_stream().cuda_stream), "spv_dec_nb_fwd")
+        torch.cuda.synchronize()
+        want = w.rowc[:, :2]
+        assert float((got - want).abs().max()) < 2e-2, g
+
+
+def test_early_adam_is_the_same_update():
+    """optimiser step interleaved with the backward (per parameter range) == backward followed by one Adam launch"""
+    import torch
+    from spvipes_b200.trainer import TrainLoop
+    gd = Golden("label_tiny")
+    out = []
+    for early in (True, False):
+        eng, batches, noise = engine_from_golden(gd, precision="bf16")
+        loop = TrainLoop(eng)
+        loop.early_adam = early
+        loop.set_epoch(1)
+        for _ in range(3):
+            loop.step(batches, noise)
+        torch.cuda.synchronize()
+        out.append((eng.params.flat.clone(), eng.adam_m.clone(), eng.adam_v.clone(), int(eng.step_dev), eng.wb[0][0].clone(),
+                    eng.wb[0][1][:eng.d.genes[0]].clone()))
+    for a, b in zip(*out):
+        assert torch.equal(a, b) if torch.is_tensor(a) else a == b
+    off, shape = eng.params.offsets[0]["W1"]
+    W1 = out[0][0][off:off + shape[0] * shape[1]].view(shape)
+    assert torch.equal(out[0][4][:, :shape[1]], W1.bfloat16())  # the bf16 operand copy tracks the fp32 master
