@@ -211,6 +211,7 @@ class _GroupWS:
             tiles = ((B + 127) // 128) * ((KMIX + 127) // 128)
             self.tc_splits_damix = max(1, min(148 // tiles, (G + 63) // 64 // 2))
             self.tc_splits_damix3 = max(1, min(148 // tiles, (3 * self.Gp + 63) // 64 // 2))
+            self.tc_splits_dz = max(1, min(148 // ((B + 127) // 128), (2 * self.Gp + 63) // 64 // 2))
         if with_grad:
             self.dyp, self.dys, self.dpi = f(B, G), f(B, G), f(B, G)
             self.colpart, self.colsum = f(self.nTB, 4, G), f(4, G)
@@ -624,6 +625,11 @@ class StepEngine:
                                               L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.D3), B, G, HD, P, S,
                                               -float(grad_scale) / B, L.ptr(w.colsum), st), "spv_dec_nb_bwd_tc")
                 Gp3 = 3 * w.Gp
+                # d zz through the two softmax branches: [dyp | dys] against the folded weights' latent columns (K = 2 Gp,
+                # N = P + S).  Kept out of the mixture GEMM below: stacked into its K it would triple that GEMM's operand traffic.
+                with self._branch(g, "dzg"):
+                    self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, w.Wstack.data_ptr() + 2 * (w.Gp * w.KMp + HD), L.ptr(w.dzraw), B, KZ,
+                                  2 * w.Gp, lda=Gp3, ldb=w.KMp, ldc=KZ, b_mn=1, splits=w.tc_splits_dz, ws=w.ws2)
                 with self._branch(g, "wgrad"):  # d Wm = dpi^T [hm | zz]
                     self._tc_gemm(L.ptr(w.D3), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=Gp3, ldb=w.KMp, ldc=KMIX,
                                   a_mn=1, b_mn=1)
@@ -635,9 +641,9 @@ class StepEngine:
                     self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, w.amixb.data_ptr() + 2 * HD, L.ptr(w.CQ), 2 * w.Gp, KZ, B, lda=Gp3,
                                   ldb=w.KMp, ldc=KZ, a_mn=1, b_mn=1)
                     self._gene_bwd(g, w, Qp, Qs, ldq, B, G)
-                # d [hm | zz] = dpi Wm + dyp W'p + dys W's: one GEMM against the stacked weights
-                self._tc_gemm(L.ptr(w.D3), L.ptr(w.Wstack), L.ptr(w.damix), B, KMIX, Gp3, lda=Gp3, ldb=w.KMp, ldc=KMIX, b_mn=1,
-                              splits=w.tc_splits_damix3, ws=w.ws)
+                # d [hm | zz] (mixture part) = dpi Wm
+                self._tc_gemm(L.ptr(w.D3), L.ptr(w.Wstack), L.ptr(w.damix), B, KMIX, G, lda=Gp3, ldb=w.KMp, ldc=KMIX, b_mn=1,
+                              splits=w.tc_splits_damix, ws=w.ws)
             else:
                 L.check(lib.spv_dec_nb_bwd(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, KMIX, B, G, HD, P, S,
                                            -float(grad_scale) / B, L.ptr(w.colsum), L.ptr(w.dpib) if self.bf16 else None,
@@ -664,10 +670,10 @@ class StepEngine:
             L.check(lib.spv_bn_bwd(L.ptr(w.damix), KMIX, L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, L.ptr(w.dah), HD, B, HD,
                                    L.ptr(self.P(g, "gh")), L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), L.ptr(self.Gd(g, "gh")),
                                    L.ptr(self.Gd(g, "bth")), st), "spv_bn_bwd")
-            if dzraw is None:
+            if dzraw is None:  # fused path: dzraw already holds the softmax-branch part (branch "dzg", same auxiliary stream)
                 dzraw = L.ptr(w.dzraw)
                 with self._branch(g, "hid"):
-                    self._gemm(L.ptr(w.dah), L.ptr(self.P(g, "Wh")), dzraw, B, KZ, HD, lda=HD, ldb=KZ, ldc=KZ)
+                    self._gemm(L.ptr(w.dah), L.ptr(self.P(g, "Wh")), dzraw, B, KZ, HD, lda=HD, ldb=KZ, ldc=KZ, acc=1)
             else:
                 self._gemm(L.ptr(w.dah), L.ptr(self.P(g, "Wh")), dzraw, B, KZ, HD, lda=HD, ldb=KZ, ldc=KZ, acc=1)
             with self._branch(g, "wgrad"):
