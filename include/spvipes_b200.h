@@ -47,6 +47,19 @@ int spv_gemm(int srcA, int transA, int srcB, int transB, const void* A, long lon
              long long ldb, const int* rowsB, float* C, long long ldc, int M, int N, int K, int batch, long long sA,
              long long sB, long long sC, const float* bias, long long sBias, int relu, int accumulate, int splits, float* ws,
              void* stream);
+/* spv_gemm with fused epilogue stages, applied after bias / ReLU / accumulate to element (m, n') of the full output
+ * (n' = batch * sC + n): gate_y != NULL: multiply by (gate_y[m, n'] > 0 ? (gate_mask ? gate_mask[m, n'] : gate_scale) : 0)
+ * (ReLU [+ dropout] backward, nn/networks.py:119-125 reversed); drop_mask / drop_p > 0: dropout forward with an explicit
+ * multiplier matrix or the Philox keep mask of spv_dropout (seed, stream id, *drop_step, index m * drop_ld + n');
+ * c_bf16 != NULL: also store the result as bf16 (operand of the tensor-core weight-gradient GEMM).  The fused stages
+ * exist in the whole-K kernel only (fp32 operands, A not transposed, no row gather, K <= 256, splits == 1); -1 otherwise. */
+int spv_gemm_fused(int srcA, int transA, int srcB, int transB, const void* A, long long lda, const int* rowsA, const void* B,
+                   long long ldb, const int* rowsB, float* C, long long ldc, int M, int N, int K, int batch, long long sA,
+                   long long sB, long long sC, const float* bias, long long sBias, int relu, int accumulate, int splits,
+                   float* ws, const float* gate_y, long long ld_gate, const float* gate_mask, long long ld_mask,
+                   float gate_scale, float drop_p, const float* drop_mask, unsigned long long drop_seed,
+                   unsigned int drop_stream, const int* drop_step, long long drop_ld, void* c_bf16, long long ld_cbf16,
+                   void* stream);
 
 /* bf16 tensor-core GEMM (tcgen05.mma, TMEM accumulator, TMA-fed): C[M,N] (+)= act(A B^T + bias), fp32 output.
  * a_mn = 0: A stored [M][K], 1: A stored [K][M];  b_mn = 0: B stored [N][K], 1: B stored [K][N]; lda / ldb in bf16

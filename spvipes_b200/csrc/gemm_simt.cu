@@ -1,5 +1,6 @@
 // Generic fp32 SIMT GEMM (+ split-K reduce) behind spv_gemm.  Replaces the cuBLAS calls the
 // reference makes through nn.Linear / autograd (reference nn/networks.py:119-125, 314-325).
+#include <cuda_bf16.h>
 #include "gemm_simt.cuh"
 #include "../../include/spvipes_b200.h"
 
@@ -13,6 +14,19 @@ struct GemmParams {
     float* ws;
     long lda, ldb, ldc, sA, sB, sC, sBias;
     int M, N, K, batch, splits, kchunk, relu, accumulate;
+    // optional fused epilogue (whole-K kernel only; spv_gemm_fused), applied after bias / ReLU, (m, n') with n' = batch * sC + n:
+    const float* gate_y;     // multiply by (gate_y[m, n'] > 0 ? (gate_mask ? gate_mask[m, n'] : gate_scale) : 0): ReLU (+ dropout) backward
+    const float* gate_mask;
+    long ld_gate, ld_mask;
+    float gate_scale;
+    float drop_p;            // > 0 (or drop_mask): dropout forward with the Philox keep mask of spv_dropout (seed, stream id, *step,
+    const float* drop_mask;  //   element index m * drop_ld + n') or an explicit multiplier matrix
+    unsigned long long drop_seed;
+    unsigned int drop_stream;
+    const int* drop_step;
+    long drop_ld;
+    __nv_bfloat16* c_bf16;   // also store the result as bf16 at c_bf16[m * ld_cbf16 + n']
+    long ld_cbf16;
 };
 
 template <int SRC_A, bool TA, int SRC_B, bool TB>
@@ -208,7 +222,21 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_smallk_kernel(GemmParams p) {
         if (bias) v += __ldg(bias + n);
         if (p.relu) v = fmaxf(v, 0.0f);
         float* c = C + (size_t)m * p.ldc + n;
-        *c = p.accumulate ? (*c + v) : v;
+        if (p.accumulate) v += *c;
+        const long nn = (long)b * p.sC + n;  // column inside the full output matrix
+        if (p.gate_y) {
+            const float gm = p.gate_mask ? __ldg(p.gate_mask + (size_t)m * p.ld_mask + nn) : p.gate_scale;
+            v = __ldg(p.gate_y + (size_t)m * p.ld_gate + nn) > 0.0f ? v * gm : 0.0f;
+        }
+        if (p.drop_mask) {
+            v *= __ldg(p.drop_mask + (size_t)m * p.drop_ld + nn);
+        } else if (p.drop_p > 0.0f) {
+            const unsigned int stp = p.drop_step ? (unsigned int)*p.drop_step : 0u;
+            const float keep = 1.0f - p.drop_p;
+            v = philox_uniform(p.drop_seed, p.drop_stream, stp, (unsigned long long)((size_t)m * p.drop_ld + nn)) <= keep ? v * (1.0f / keep) : 0.0f;
+        }
+        *c = v;
+        if (p.c_bf16) p.c_bf16[(size_t)m * p.ld_cbf16 + nn] = __float2bfloat16(v);
     }
 }
 
@@ -246,10 +274,31 @@ extern "C" int spv_gemm(int srcA, int transA, int srcB, int transB, const void* 
                         const void* B, long long ldb, const int* rowsB, float* C, long long ldc, int M, int N, int K,
                         int batch, long long sA, long long sB, long long sC, const float* bias, long long sBias, int relu,
                         int accumulate, int splits, float* ws, void* stream) {
+    return spv_gemm_fused(srcA, transA, srcB, transB, A, lda, rowsA, B, ldb, rowsB, C, ldc, M, N, K, batch, sA, sB, sC, bias, sBias,
+                          relu, accumulate, splits, ws, nullptr, 0, nullptr, 0, 1.0f, 0.0f, nullptr, 0ull, 0u, nullptr, 0, nullptr, 0,
+                          stream);
+}
+
+// spv_gemm + fused epilogue stages (see GemmParams).  The fused stages need the whole-K kernel: fp32 operands, A not
+// transposed, no row gather, K <= 256, splits == 1; otherwise SPV_ERR_ARG when any of them is requested.
+extern "C" int spv_gemm_fused(int srcA, int transA, int srcB, int transB, const void* A, long long lda, const int* rowsA,
+                              const void* B, long long ldb, const int* rowsB, float* C, long long ldc, int M, int N, int K,
+                              int batch, long long sA, long long sB, long long sC, const float* bias, long long sBias, int relu,
+                              int accumulate, int splits, float* ws, const float* gate_y, long long ld_gate,
+                              const float* gate_mask, long long ld_mask, float gate_scale, float drop_p, const float* drop_mask,
+                              unsigned long long drop_seed, unsigned int drop_stream, const int* drop_step, long long drop_ld,
+                              void* c_bf16, long long ld_cbf16, void* stream) {
     if (M <= 0 || N <= 0 || K < 0 || batch <= 0 || !A || !B || !C) return SPV_ERR_ARG;
+    if (drop_p < 0.0f || drop_p >= 1.0f) return SPV_ERR_ARG;
     if (splits < 1) splits = 1;
     if (splits > 1 && !ws) return SPV_ERR_ARG;
     GemmParams p;
+    p.gate_y = gate_y; p.gate_mask = gate_mask; p.ld_gate = ld_gate; p.ld_mask = ld_mask; p.gate_scale = gate_scale;
+    p.drop_p = drop_p; p.drop_mask = drop_mask; p.drop_seed = drop_seed; p.drop_stream = drop_stream; p.drop_step = drop_step;
+    p.drop_ld = drop_ld; p.c_bf16 = reinterpret_cast<__nv_bfloat16*>(c_bf16); p.ld_cbf16 = ld_cbf16;
+    const bool fused = gate_y || drop_mask || drop_p > 0.0f || c_bf16;
+    const bool smallk_ok = srcA == SPV_SRC_F32 && srcB == SPV_SRC_F32 && !transA && !rowsA && !rowsB && splits == 1 && K > 0 && K <= SK_MAXK;
+    if (fused && !smallk_ok) return SPV_ERR_ARG;
     p.A = A; p.B = B; p.C = C; p.bias = bias; p.rowsA = rowsA; p.rowsB = rowsB; p.ws = ws;
     p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.sA = sA; p.sB = sB; p.sC = sC; p.sBias = sBias;
     p.M = M; p.N = N; p.K = K; p.batch = batch; p.relu = relu; p.accumulate = accumulate;

@@ -430,18 +430,27 @@ __global__ void __launch_bounds__(256) poe_bwd_scatter_kernel(PoeScatterParams p
         int d = lane + 32 * q;
         acc[q] = d < W ? s.g_own[(long)row * W + d] : 0.0f;
     }
-    for (int i0 = 0; i0 < s.B_oth; i0 += 32) {
-        int i = i0 + lane;
-        bool hit = i < s.B_oth && s.partner_oth && s.partner_oth[i] == row;
-        unsigned m = __ballot_sync(0xffffffffu, hit);
-        while (m) {
-            int b = __ffs(m) - 1;
-            m &= m - 1;
-            int ii = i0 + b;
+    // the other side's partner list is scanned 8 x 32 entries at a time: the eight loads are in flight together (one memory
+    // round trip per 256 entries instead of one per 32), then the ballots; contributions are added in index order
+    for (int c0 = 0; s.partner_oth && c0 < s.B_oth; c0 += 256) {
+        int pv[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                int d = lane + 32 * q;
-                if (d < W) acc[q] += s.contrib_oth[(long)ii * W + d];
+        for (int u = 0; u < 8; ++u) {
+            const int i = c0 + 32 * u + lane;
+            pv[u] = i < s.B_oth ? __ldg(s.partner_oth + i) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            unsigned m = __ballot_sync(0xffffffffu, pv[u] == row);
+            while (m) {
+                int b = __ffs(m) - 1;
+                m &= m - 1;
+                int ii = c0 + 32 * u + b;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int d = lane + 32 * q;
+                    if (d < W) acc[q] += s.contrib_oth[(long)ii * W + d];
+                }
             }
         }
     }

@@ -294,9 +294,22 @@ class StepEngine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _gemm(self, A, B, C, M, N, K, *, lda, ldb, ldc, ta=0, tb=0, srcA=L.SRC_F32, srcB=L.SRC_F32, rowsA=None, rowsB=None,
-              batch=1, sA=0, sB=0, sC=0, bias=None, sBias=0, relu=0, acc=0, splits=1, ws=None):
-        L.check(self.lib.spv_gemm(srcA, ta, srcB, tb, A, lda, L.ptr(rowsA), B, ldb, L.ptr(rowsB), C, ldc, M, N, K, batch,
-                                  sA, sB, sC, bias, sBias, relu, acc, splits, L.ptr(ws), self._stream()), "spv_gemm")
+              batch=1, sA=0, sB=0, sC=0, bias=None, sBias=0, relu=0, acc=0, splits=1, ws=None, gate=None, drop=None, c_bf16=None):
+        """gate = (y ptr, ld, mask ptr or None, ld, scale); drop = (p, mask ptr or None, stream id, ld); c_bf16 = (ptr, ld):
+        fused epilogue stages of spv_gemm_fused (whole-K kernel only: see self._can_fuse)"""
+        if gate is None and drop is None and c_bf16 is None:
+            L.check(self.lib.spv_gemm(srcA, ta, srcB, tb, A, lda, L.ptr(rowsA), B, ldb, L.ptr(rowsB), C, ldc, M, N, K, batch,
+                                      sA, sB, sC, bias, sBias, relu, acc, splits, L.ptr(ws), self._stream()), "spv_gemm")
+            return
+        gy, gld, gm, gmld, gs = gate if gate is not None else (None, 0, None, 0, 1.0)
+        dp, dm, dsid, dld = drop if drop is not None else (0.0, None, 0, 0)
+        cb, cbld = c_bf16 if c_bf16 is not None else (None, 0)
+        L.check(self.lib.spv_gemm_fused(srcA, ta, srcB, tb, A, lda, L.ptr(rowsA), B, ldb, L.ptr(rowsB), C, ldc, M, N, K, batch,
+                                        sA, sB, sC, bias, sBias, relu, acc, splits, L.ptr(ws), gy, gld, gm, gmld, gs, dp, dm,
+                                        self.seed, dsid, L.ptr(self.step_dev), dld, cb, cbld, self._stream()), "spv_gemm_fused")
+
+    def _can_fuse(self, K):
+        return K <= 256
 
     def _tc_gemm(self, A, B, C, M, N, K, *, lda, ldb, ldc, a_mn=0, b_mn=0, bias=None, relu=0, acc=0, splits=1, ws=None):
         L.check(self.lib.spv_tc_gemm(a_mn, b_mn, A, lda, B, ldb, C, ldc, M, N, K, bias, relu, acc, splits, L.ptr(ws),
@@ -430,13 +443,15 @@ class StepEngine:
                             "spv_library_size")
                 self._gemm(xptr, L.ptr(self.P(g, "W1")), L.ptr(w.h1), B, 2 * H, G, lda=ldx, ldb=G, ldc=2 * H, tb=1, srcA=src,
                            rowsA=bt.rows, bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.splits_fc1, ws=w.ws)
+            mask = noise.drop[g] if (training and noise.drop is not None) else None
+            dropping = training and (mask is not None or self.dropout_rate > 0)
+            fuse_drop = dropping and self._can_fuse(H)  # dropout in the fc2 epilogue (same keep mask as spv_dropout)
             self._gemm(L.ptr(w.h1), L.ptr(self.P(g, "W2")), L.ptr(w.h2), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, tb=1, batch=2,
-                       sA=H, sB=H * H, sC=H, bias=L.ptr(self.P(g, "b2")), sBias=H, relu=1)
-            if training:
-                mask = noise.drop[g] if noise.drop is not None else None
-                if mask is not None or self.dropout_rate > 0:
-                    L.check(lib.spv_dropout(L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, self.dropout_rate, self.seed,
-                                            8 + g, L.ptr(self.step_dev), st), "spv_dropout")
+                       sA=H, sB=H * H, sC=H, bias=L.ptr(self.P(g, "b2")), sBias=H, relu=1,
+                       drop=(0.0 if mask is not None else self.dropout_rate, L.ptr(mask), 8 + g, 2 * H) if fuse_drop else None)
+            if dropping and not fuse_drop:
+                L.check(lib.spv_dropout(L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, self.dropout_rate, self.seed,
+                                        8 + g, L.ptr(self.step_dev), st), "spv_dropout")
             bhd = self.P(g, "bhd")
             with self._branch(g, "headp"):  # the private and the shared heads are independent
                 self._gemm(L.ptr(w.h2), L.ptr(self.P(g, "Whp")), L.ptr(w.r), B, 2 * P, H, lda=2 * H, ldb=H, ldc=NST, tb=1,
@@ -719,8 +734,13 @@ class StepEngine:
                                    L.ptr(self.P(g, "ghd")), L.ptr(w.bn_hd_mean), L.ptr(w.bn_hd_istd), L.ptr(self.Gd(g, "ghd")),
                                    L.ptr(self.Gd(g, "bthd")), st), "spv_bn_bwd")
             drs = w.dr.data_ptr() + 4 * 2 * P
+            mask = noise.drop[g] if noise.drop is not None else None
+            scale = 1.0 / (1.0 - self.dropout_rate) if self.dropout_rate > 0 else 1.0
+            fuse2 = self._can_fuse(2 * S)  # ReLU + dropout backward in the epilogue of the two head input-gradient GEMMs
+            gate_p = (L.ptr(w.h2), 2 * H, L.ptr(mask), 2 * H, scale) if fuse2 else None
+            gate_s = (w.h2.data_ptr() + 4 * H, 2 * H, mask.data_ptr() + 4 * H if mask is not None else None, 2 * H, scale) if fuse2 else None
             with self._branch(g, "dh2p"):  # first on its auxiliary stream: this one is on the critical path
-                self._gemm(L.ptr(w.dr), L.ptr(self.P(g, "Whp")), L.ptr(w.dh2), B, H, 2 * P, lda=NST, ldb=H, ldc=2 * H)
+                self._gemm(L.ptr(w.dr), L.ptr(self.P(g, "Whp")), L.ptr(w.dh2), B, H, 2 * P, lda=NST, ldb=H, ldc=2 * H, gate=gate_p)
             if adam is not None:  # every decoder gradient of this group is final: update that range now
                 self._join(g, "wgrad")
                 self._join(g, "wgrad1")
@@ -737,21 +757,24 @@ class StepEngine:
                            splits=w.splits_b, ws=w.ws2)
                 self._gemm(drs, w.h2.data_ptr() + 4 * H, L.ptr(self.Gd(g, "Whs")), 2 * S, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1,
                            splits=w.splits_b, ws=w.ws2)
-            self._gemm(drs, L.ptr(self.P(g, "Whs")), w.dh2.data_ptr() + 4 * H, B, H, 2 * S, lda=NST, ldb=H, ldc=2 * H)
+            self._gemm(drs, L.ptr(self.P(g, "Whs")), w.dh2.data_ptr() + 4 * H, B, H, 2 * S, lda=NST, ldb=H, ldc=2 * H, gate=gate_s)
             self._join(g, "dh2p")
-            mask = noise.drop[g] if noise.drop is not None else None
-            scale = 1.0 / (1.0 - self.dropout_rate) if self.dropout_rate > 0 else 1.0
-            L.check(lib.spv_relu_bwd(L.ptr(w.dh2), 2 * H, L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, scale, st),
-                    "spv_relu_bwd")
+            if not fuse2:
+                L.check(lib.spv_relu_bwd(L.ptr(w.dh2), 2 * H, L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, scale, st),
+                        "spv_relu_bwd")
             with self._branch(g, "wgrad1", lane=1):
                 self._gemm(L.ptr(w.dh2), L.ptr(w.h1), L.ptr(self.Gd(g, "W2")), H, H, B, lda=2 * H, ldb=2 * H, ldc=H, ta=1,
                            batch=2, sA=H, sB=H, sC=H * H, splits=w.splits_b, ws=w.ws3)
                 L.check(lib.spv_colsum(L.ptr(w.dh2), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b2")), self._stream()), "spv_colsum")
+            fuse1 = self._can_fuse(H)  # ReLU backward and the bf16 operand copy in the epilogue of the fc2 input-gradient GEMM
             self._gemm(L.ptr(w.dh2), L.ptr(self.P(g, "W2")), L.ptr(w.dh1), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, batch=2, sA=H,
-                       sB=H * H, sC=H)
-            L.check(lib.spv_relu_bwd(L.ptr(w.dh1), 2 * H, L.ptr(w.h1), 2 * H, B, 2 * H, None, 0, 1.0, st), "spv_relu_bwd")
+                       sB=H * H, sC=H, gate=(L.ptr(w.h1), 2 * H, None, 0, 1.0) if fuse1 else None,
+                       c_bf16=(L.ptr(w.dh1b), 2 * H) if (fuse1 and self.bf16) else None)
+            if not fuse1:
+                L.check(lib.spv_relu_bwd(L.ptr(w.dh1), 2 * H, L.ptr(w.h1), 2 * H, B, 2 * H, None, 0, 1.0, st), "spv_relu_bwd")
             if self.bf16:
-                L.check(lib.spv_to_bf16(L.ptr(w.dh1), 2 * H, L.ptr(w.dh1b), 2 * H, B, 2 * H, st), "spv_to_bf16")
+                if not fuse1:
+                    L.check(lib.spv_to_bf16(L.ptr(w.dh1), 2 * H, L.ptr(w.dh1b), 2 * H, B, 2 * H, st), "spv_to_bf16")
                 self._tc_gemm(L.ptr(w.dh1b), L.ptr(w.Tb), L.ptr(self.Gd(g, "W1")), 2 * H, G, B, lda=2 * H, ldb=w.Gp, ldc=G,
                               a_mn=1, b_mn=1)
             else:
