@@ -1,5 +1,5 @@
 """Turn an `ncu --metrics gpu__time_duration.sum --csv` launch list of bench.py into a per-kernel table for ONE training
-step (markdown).  usage: python tools/summarize_launches.py gpurun_out/launches.csv [step_index] > profiles/xxx.md"""
+step (markdown).  usage: python tools/summarize_launches.py gpurun_out/launches.csv [step_index [marker_kernel]] > profiles/xxx.md"""
 import collections
 import csv
 import re
@@ -14,7 +14,8 @@ for r in rows:
         continue
     if hdr and len(r) == len(hdr):
         data.append(dict(zip(hdr, r)))
-start = [i for i, d in enumerate(data) if "library_kernel" in d["Kernel Name"]]
+marker = sys.argv[3] if len(sys.argv) > 3 else "counts_to_bf16_kernel"  # launched exactly twice per step (once per group)
+start = [i for i, d in enumerate(data) if marker in d["Kernel Name"]]
 i0, i1 = start[2 * step], start[2 * step + 2]
 agg = collections.OrderedDict()
 tot = 0.0

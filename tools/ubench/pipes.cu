@@ -25,6 +25,14 @@ __global__ void k(float* out, long long* cyc, float seed) {
             if (OP == 5) asm volatile("add.f32 %0, %0, %1;" : "+f"(v[i]) : "f"(c));
             if (OP == 6) asm volatile("fma.rn.f32 %0, %0, 0f3F800347, 0f3A83126F;" : "+f"(v[i]));
             if (OP == 7) asm volatile("max.f32 %0, %0, %1;" : "+f"(v[i]) : "f"(c));
+            if (OP == 8 && (i & 1) == 0) {  // packed: two floats per instruction (counted as one instruction per pair)
+                unsigned long long a, b2, c2;
+                asm volatile("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(v[i]), "f"(v[i + 1]));
+                asm volatile("mov.b64 %0, {%1, %1};" : "=l"(b2) : "f"(c));
+                asm volatile("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(seed));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a) : "l"(b2), "l"(c2));
+                asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(v[i]), "=f"(v[i + 1]) : "l"(a));
+            }
         }
     }
     long long t1 = clock64();
@@ -52,6 +60,6 @@ void run(const char* name) {
     printf("\n");
 }
 int main() {
-    run<0>("ex2"); run<1>("lg2"); run<2>("rcp"); run<3>("ffma 3reg"); run<4>("fmul"); run<5>("fadd"); run<6>("ffma imm"); run<7>("fmnmx");
+    run<0>("ex2"); run<1>("lg2"); run<2>("rcp"); run<3>("ffma 3reg"); run<4>("fmul"); run<5>("fadd"); run<6>("ffma imm"); run<7>("fmnmx"); run<8>("ffma2 x4");
     return 0;
 }
