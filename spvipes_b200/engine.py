@@ -47,6 +47,10 @@ class Dims:
         return 2 * self.n_shared + 2 * self.n_private
 
 
+PHASE_ENC, PHASE_DEC = 0, 1
+_ENCODER_BLOCKS = ("W1", "b1", "W2", "b2", "Whp", "Whs", "bhd", "ghd", "bthd")
+
+
 def _group_param_entries(g: int, G: int, d: Dims):
     """[(fused name, shape, [(state_dict name, row slice / index)])] in flat order for group g."""
     H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
@@ -101,19 +105,32 @@ def _group_buffer_entries(g: int, G: int, d: Dims):
 class FlatStore:
     """one flat fp32 tensor + named views (fused blocks per group, and reference state_dict names)"""
 
-    def __init__(self, entries_per_group, device):
-        self.offsets: List[Dict[str, Tuple[int, Tuple[int, ...]]]] = []
+    def __init__(self, entries_per_group, device, phase_of=None):
+        """phase_of(name) -> int: blocks are laid out phase by phase (all groups' phase-0 blocks, then phase 1, ...), so that
+        e.g. every encoder parameter and every decoder parameter form one contiguous range each (`self.ranges[phase]`,
+        per group `self.group_ranges[phase][g]`): the data-parallel step all-reduces a whole phase with one call."""
+        self.offsets: List[Dict[str, Tuple[int, Tuple[int, ...]]]] = [dict() for _ in entries_per_group]
         self.sd_index: "OrderedDict[str, Tuple[int, str, Optional[Tuple[int, int]]]]" = OrderedDict()
+        phases = sorted({(phase_of(n) if phase_of else 0) for entries in entries_per_group for n, _, _ in entries})
+        self.ranges: Dict[int, Tuple[int, int]] = {}
+        self.group_ranges: Dict[int, List[Tuple[int, int]]] = {}
         off = 0
-        for g, entries in enumerate(entries_per_group):
-            table = {}
+        for ph in phases:
+            lo_ph = off
+            self.group_ranges[ph] = []
+            for g, entries in enumerate(entries_per_group):
+                lo_g = off
+                for name, shape, subs in entries:
+                    if (phase_of(name) if phase_of else 0) != ph:
+                        continue
+                    self.offsets[g][name] = (off, shape)
+                    off += (int(math.prod(shape)) + 3) // 4 * 4  # keep every block 16-byte aligned
+                self.group_ranges[ph].append((lo_g, off))
+            self.ranges[ph] = (lo_ph, off)
+        for g, entries in enumerate(entries_per_group):  # state_dict key order: group by group, as the reference registers them
             for name, shape, subs in entries:
-                n = int(math.prod(shape))
-                table[name] = (off, shape)
                 for sd_name, sl in subs:
                     self.sd_index[sd_name] = (g, name, sl)
-                off += (n + 3) // 4 * 4  # keep every block 16-byte aligned
-            self.offsets.append(table)
         self.numel = off
         self.flat = torch.zeros(off, dtype=torch.float32, device=device)
 
@@ -248,7 +265,9 @@ class StepEngine:
         self.dropout_rate = float(dropout_rate)
         self.device = torch.device(device)
         self.seed = int(seed)
-        self.params = FlatStore([_group_param_entries(g, G, self.d) for g, G in enumerate(self.d.genes)], self.device)
+        # parameter layout: [encoders of group 0 | encoders of group 1 | decoders of group 0 | decoders of group 1]
+        self.params = FlatStore([_group_param_entries(g, G, self.d) for g, G in enumerate(self.d.genes)], self.device,
+                                phase_of=lambda n: PHASE_ENC if n in _ENCODER_BLOCKS else PHASE_DEC)
         self.buffers = FlatStore([_group_buffer_entries(g, G, self.d) for g, G in enumerate(self.d.genes)], self.device)
         for n in self.buffers.names():
             if n.endswith("running_var"):
@@ -610,24 +629,38 @@ class StepEngine:
                                      L.ptr(self.step_dev), self._stream()), "spv_poe_fwd")
 
     # -------------------------------------------------------------------------------- backward
-    def backward(self, grad_scale: float = 1.0, adam: Optional[dict] = None):
+    def backward(self, grad_scale: float = 1.0, adam: Optional[dict] = None, stage: str = "all"):
         """gradients of loss * grad_scale w.r.t. every parameter, written into self.grads.
         adam (single-GPU training only: keys lr, betas, eps, weight_decay): also apply the optimiser step, per parameter range
         as soon as its gradients are complete: the decoder ranges (55 % of the parameters) update on an auxiliary stream
-        while the encoder backward, a chain of small latency-bound kernels that leaves HBM idle, is still running."""
+        while the encoder backward, a chain of small latency-bound kernels that leaves HBM idle, is still running.
+        stage: "all", or "decoder" (decoders + PoE: every decoder-range gradient final) followed by "encoder" - the
+        data-parallel step all-reduces the decoder range while the encoder stage runs."""
         ctx = self._ctx
         if ctx is None or not ctx["training"]:
             raise RuntimeError("backward needs a preceding training-mode forward")
-        d, st, lib = self.d, self._stream(), self.lib
-        H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
-        batches, ws, Bs, noise, srcs, aux = ctx["batches"], ctx["ws"], ctx["Bs"], ctx["noise"], ctx["srcs"], ctx["aux"]
+        if stage not in ("all", "decoder", "encoder") or (adam is not None and stage != "all"):
+            raise ValueError("stage must be 'all', 'decoder' or 'encoder' (the interleaved optimiser step needs 'all')")
+        tick_events = []
         if adam is not None:
             if self.adam_m is None:
                 self.adam_m = torch.zeros_like(self.params.flat)
                 self.adam_v = torch.zeros_like(self.params.flat)
             with self._branch(0, "tick", lane=1):  # the step count of this update, off the critical path
-                L.check(lib.spv_adam_tick(L.ptr(self.step_dev), self._stream()), "spv_adam_tick")
+                L.check(self.lib.spv_adam_tick(L.ptr(self.step_dev), self._stream()), "spv_adam_tick")
             tick_events = self._pending.pop((0, "tick"), [])
+        if stage != "encoder":
+            self._backward_decoders(ctx, grad_scale)
+        if stage == "decoder":
+            for g in (0, 1):  # every auxiliary branch back on the calling stream (a graph capture may end here)
+                self._join(g)
+            return
+        self._backward_encoders(ctx, grad_scale, adam, tick_events)
+
+    def _backward_decoders(self, ctx, grad_scale):
+        d, st, lib = self.d, self._stream(), self.lib
+        H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
+        batches, ws, Bs, noise, srcs, aux = ctx["batches"], ctx["ws"], ctx["Bs"], ctx["noise"], ctx["srcs"], ctx["aux"]
         # ---------------- decoders
         for g in self._fork_groups():
             bt, w, st = batches[g], ws[g], self._stream()
@@ -725,6 +758,10 @@ class StepEngine:
                        lda=Bs[1], ldb=2 * S, ldc=NST, ta=1, acc=1)
             self._gemm(L.ptr(aux["P2"]), L.ptr(ws[1].dexpert), ws[1].dstats.data_ptr() + 4 * 2 * P, Bs[0], 2 * S, Bs[1],
                        lda=Bs[0], ldb=2 * S, ldc=NST, ta=1, acc=1)
+    def _backward_encoders(self, ctx, grad_scale, adam, tick_events):
+        d, st, lib = self.d, self._stream(), self.lib
+        H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
+        batches, ws, Bs, noise, srcs, aux = ctx["batches"], ctx["ws"], ctx["Bs"], ctx["noise"], ctx["srcs"], ctx["aux"]
         # ---------------- encoders
         for g in self._fork_groups():
             bt, w, st = batches[g], ws[g], self._stream()
@@ -747,8 +784,7 @@ class StepEngine:
                 with self._branch(g, "adam", lane=1):
                     for ev in tick_events:
                         torch.cuda.current_stream(self.device).wait_event(ev)
-                    lo = self.params.offsets[g]["Wp"][0]
-                    hi = self.params.offsets[g + 1]["W1"][0] if g + 1 < len(self.d.genes) else self.params.numel
+                    lo, hi = self.params.group_ranges[PHASE_DEC][g]
                     self._adam_range(lo, hi, adam, max_blocks=int(__import__("os").environ.get("SPV_ADAM_BLOCKS", "296")))
             with self._branch(g, "wgrad1", lane=1):
                 L.check(lib.spv_colsum(L.ptr(w.dr), NST, B, NST, L.ptr(self.Gd(g, "bhd")), self._stream()), "spv_colsum")
@@ -786,7 +822,7 @@ class StepEngine:
             if adam is not None:  # encoder range of this group
                 for ev in tick_events:
                     torch.cuda.current_stream(self.device).wait_event(ev)
-                self._adam_range(self.params.offsets[g]["W1"][0], self.params.offsets[g]["Wp"][0], adam)
+                self._adam_range(*self.params.group_ranges[PHASE_ENC][g], adam)
 
     # -------------------------------------------------------------------------------- optimiser
     def adam_step(self, lr=1e-3, betas=(0.9, 0.999), eps=0.01, weight_decay=1e-6, grad_scale=1.0):

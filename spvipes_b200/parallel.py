@@ -3,9 +3,9 @@
 argmax are per-minibatch quantities in the reference, so each rank runs the reference semantics on its own minibatch and
 only the parameter gradients are exchanged (NCCL all-reduce over NVLink 5 / NVSwitch; gloo in the CPU tests).
 
-The all-reduce is issued on the step's stream as a few large buckets in backward-completion order (decoder of group 1,
-decoder of group 0, encoders) so that NCCL pipelines them; inside the captured CUDA graph the buckets become graph nodes
-that overlap the tail of the backward kernels of the other group's stream.
+Two all-reduces per step, in backward-completion order: the decoder range of the flat gradient buffer as soon as the decoder
+and PoE backward are done (it then overlaps the encoder backward), the encoder range after it; Adam waits for both.
+The collectives stay outside CUDA-graph capture: the step is three captured graphs with the two eager all-reduces between.
 """
 from __future__ import annotations
 
@@ -30,20 +30,30 @@ def bucket_bounds(numel: int, n_buckets: int) -> List[Tuple[int, int]]:
 
 
 class GradSync:
-    """sum the flat gradient buffer over ranks in `n_buckets` chunks; returns the 1/world factor that the fused Adam kernel
-    folds into its gradient read (no separate scaling pass)."""
+    """sum the gradient buffer over ranks; returns the 1/world factor that the Adam kernel folds into its gradient read
+    (no separate scaling pass).  The flat layout is [all encoder blocks | all decoder blocks] (engine.FlatStore phases), so
+    each phase is ONE all-reduce: `start(engine, phase)` issues it asynchronously (the decoder range while the encoder
+    backward still runs), `finish()` makes the current stream wait for everything issued."""
 
     def __init__(self, engine, dist, n_buckets: int = 0):
         self.dist = dist
-        if n_buckets <= 0:  # one bucket up to 64 MiB of gradients (latency bound on NVSwitch), then 32 MiB buckets
-            n_buckets = max(1, (engine.grads.numel() * 4 + (64 << 20) - 1) // (64 << 20) * 2 - 1)
         self.world = dist.get_world_size()
-        self.buckets = [engine.grads[a:b] for a, b in reversed(bucket_bounds(engine.grads.numel(), n_buckets))]
+        self.phase_slices = {ph: engine.grads[lo:hi] for ph, (lo, hi) in engine.params.ranges.items()}
+        self._work = []
+
+    def start(self, engine, phase):
+        self._work.append(self.dist.all_reduce(self.phase_slices[phase], op=self.dist.ReduceOp.SUM, async_op=True))
+
+    def finish(self) -> float:
+        for w in self._work:
+            w.wait()
+        self._work = []
+        return 1.0 / self.world
 
     def __call__(self, engine) -> float:
-        for b in self.buckets:
-            self.dist.all_reduce(b, op=self.dist.ReduceOp.SUM)
-        return 1.0 / self.world
+        for ph in sorted(self.phase_slices, reverse=True):  # decoder range first: complete first in the backward
+            self.start(engine, ph)
+        return self.finish()
 
 
 def broadcast_params(engine, dist, src: int = 0):

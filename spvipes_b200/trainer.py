@@ -102,9 +102,16 @@ class TrainLoop:
         e.forward(batches, training=True, noise=noise)
         if self.grad_sync is None and self.early_adam:  # single GPU: the optimiser step is interleaved with the backward
             e.backward(adam={"lr": self.lr, "eps": self.eps, "weight_decay": self.weight_decay})
-        else:
+        elif self.grad_sync is None:
             e.backward()
-            gs = self.grad_sync(e) if self.grad_sync is not None else 1.0
+            e.adam_step(lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=1.0)
+        else:  # data parallel: the decoder range is all-reduced while the encoder backward runs
+            from .engine import PHASE_DEC, PHASE_ENC
+            e.backward(stage="decoder")
+            self.grad_sync.start(e, PHASE_DEC)
+            e.backward(stage="encoder")
+            self.grad_sync.start(e, PHASE_ENC)
+            gs = self.grad_sync.finish()
             e.adam_step(lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=gs)
         return e.loss_terms()
 
@@ -131,16 +138,18 @@ class TrainLoop:
             with torch.cuda.graph(graph):
                 self.step(batches, noise)
         else:
-            # data parallel: forward + backward and the optimiser are two graphs, the gradient all-reduce is issued eagerly
-            # on the stream between the two replays (collectives are kept out of graph capture)
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            # data parallel: forward + decoder/PoE backward, encoder backward and the optimiser are three graphs; the two
+            # gradient all-reduces are issued eagerly between the replays (collectives are kept out of graph capture)
+            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
                 e.forward(batches, training=True, noise=noise)
-                e.backward()
-            scale = 1.0 / self.grad_sync.world
+                e.backward(stage="decoder")
             with torch.cuda.graph(g2):
+                e.backward(stage="encoder")
+            scale = 1.0 / self.grad_sync.world
+            with torch.cuda.graph(g3):
                 e.adam_step(lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=scale)
-            graph = _SyncedGraphs(g1, g2, self.grad_sync, e)
+            graph = _SyncedGraphs(g1, g2, g3, self.grad_sync, e)
         torch.cuda.synchronize(e.device)
         e.params.flat.copy_(keep[0]); e.buffers.flat.copy_(keep[1]); e.step_dev.copy_(keep[2])
         if keep[3] is None:
@@ -152,14 +161,19 @@ class TrainLoop:
 
 
 class _SyncedGraphs:
-    """replay(): forward+backward graph -> eager gradient all-reduce -> Adam graph"""
+    """replay(): [forward + decoder/PoE backward] -> all-reduce(decoder range, async) -> [encoder backward] ->
+    all-reduce(encoder range) -> wait -> [Adam]"""
 
-    def __init__(self, g_fb, g_opt, grad_sync, engine):
-        self.g_fb, self.g_opt, self.grad_sync, self.engine = g_fb, g_opt, grad_sync, engine
+    def __init__(self, g_dec, g_enc, g_opt, grad_sync, engine):
+        self.g_dec, self.g_enc, self.g_opt, self.grad_sync, self.engine = g_dec, g_enc, g_opt, grad_sync, engine
 
     def replay(self):
-        self.g_fb.replay()
-        self.grad_sync(self.engine)
+        from .engine import PHASE_DEC, PHASE_ENC
+        self.g_dec.replay()
+        self.grad_sync.start(self.engine, PHASE_DEC)
+        self.g_enc.replay()
+        self.grad_sync.start(self.engine, PHASE_ENC)
+        self.grad_sync.finish()
         self.g_opt.replay()
 
 

@@ -16,6 +16,7 @@ class _FakeEngine:
         class _P:
             pass
         self.params, self.buffers = _P(), _P()
+        self.params.ranges = {0: (0, 400), 1: (400, n)}  # [encoder range | decoder range] of the flat layout
         self.params.flat = torch.full((8,), float(rank))
         self.buffers.flat = torch.full((4,), float(rank) + 0.5)
 
@@ -26,7 +27,13 @@ def _worker(rank, world, port, n, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from spvipes_b200.parallel import GradSync, broadcast_params, shard_rows
     eng = _FakeEngine(n, rank)
-    scale = GradSync(eng, dist, n_buckets=3)(eng)
+    sync = GradSync(eng, dist)
+    sync.start(eng, 1)  # the way the step uses it: decoder range first (asynchronously), then the encoder range
+    sync.start(eng, 0)
+    scale = sync.finish()
+    again = GradSync(eng, dist)(eng)  # one-shot form: sums once more
+    eng.grads /= 2.0  # two ranks: every entry was summed over identical (already reduced) buffers -> doubled
+    assert again == scale
     broadcast_params(eng, dist, src=0)
     rows = shard_rows(np.arange(1001), rank, world)
     if rank == 0:
