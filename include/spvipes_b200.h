@@ -61,6 +61,21 @@ int spv_gemm_fused(int srcA, int transA, int srcB, int transB, const void* A, lo
                    unsigned int drop_stream, const int* drop_step, long long drop_ld, void* c_bf16, long long ld_cbf16,
                    void* stream);
 
+/* Middle of the two encoders of a group in one launch per direction (nn/networks.py:119-125):
+ *   forward : h2 = dropout(relu(h1 W2^T + b2)) [B, 2H], r = h2 Whead^T + bhead [B, 2P + 2S]   (blocks: private | shared)
+ *   backward: dh2 = (dr Whead) * gate(h2, dropout), dh1 = (dh2 W2) * gate(h1); dh1_bf16 optional (operand of the dW1 GEMM)
+ * W2 [2H, H], Whp [2P, H], Whs [2S, H], bhd [2P + 2S].  Dropout: explicit multiplier matrix drop_mask or Philox
+ * (seed, stream id, *step, index m * 2H + column) as spv_dropout; backward multiplier drop_mask or drop_scale.
+ * Needs H <= 128, H % 4 == 0, 2P, 2S <= 128 (spv_enc_mid_supported), 16-byte aligned rows. */
+int spv_enc_mid_supported(int H, int P, int S);
+int spv_enc_mid_fwd(const float* h1, long long ld_h1, const float* W2, const float* b2, const float* Whp, const float* Whs,
+                    const float* bhd, float* h2, long long ld_h2, float* r, long long ld_r, const float* drop_mask,
+                    long long ld_mask, float drop_p, unsigned long long seed, unsigned int stream_id, const int* step, int B,
+                    int H, int P, int S, void* stream);
+int spv_enc_mid_bwd(const float* dr, long long ld_dr, const float* Whp, const float* Whs, const float* W2, const float* h2,
+                    long long ld_h2, const float* h1, long long ld_h1, const float* drop_mask, long long ld_mask,
+                    float drop_scale, float* dh2, long long ld_dh2, float* dh1, long long ld_dh1, void* dh1_bf16,
+                    long long ld_dh1b, int B, int H, int P, int S, void* stream);
 /* bf16 tensor-core GEMM (tcgen05.mma, TMEM accumulator, TMA-fed): C[M,N] (+)= act(A B^T + bias), fp32 output.
  * a_mn = 0: A stored [M][K], 1: A stored [K][M];  b_mn = 0: B stored [N][K], 1: B stored [K][N]; lda / ldb in bf16
  * elements, multiples of 8, bases 16-byte aligned.  Same call sites as spv_gemm, for the "bf16 tensor-core path". */

@@ -24,6 +24,9 @@ _SIGS = {
     "spv_launch_count": [],
     "spv_arch_check": [i],
     "spv_gemm": [i, i, i, i, p, ll, p, p, ll, p, p, ll, i, i, i, i, ll, ll, ll, p, ll, i, i, i, p, p],
+    "spv_enc_mid_supported": [i, i, i],
+    "spv_enc_mid_fwd": [p, ll, p, p, p, p, p, p, ll, p, ll, p, ll, f, u64, u32, p, i, i, i, i, p],
+    "spv_enc_mid_bwd": [p, ll, p, p, p, p, ll, p, ll, p, ll, f, p, ll, p, ll, p, ll, i, i, i, i, p],
     "spv_gemm_fused": [i, i, i, i, p, ll, p, p, ll, p, p, ll, i, i, i, i, ll, ll, ll, p, ll, i, i, i, p, p, ll, p, ll, f, f, p, u64, u32, p, ll, p, ll, p],
     "spv_tc_gemm": [i, i, p, ll, p, ll, p, ll, i, i, i, p, i, i, i, p, p],
     "spv_to_bf16": [p, ll, p, ll, i, i, p],

@@ -286,6 +286,11 @@ class StepEngine:
         self._aux_lanes = int(__import__("os").environ.get("SPV_AUX_LANES", "2"))  # A/B switch
         self._pending = {}
         self.parallel_groups = True
+        # fc2 + heads (and their backward) as one launch each (spv_enc_mid_*): opt-in.  Measured at C2 it is slower than the
+        # separate whole-K GEMMs (0.404 against 0.385 ms per step): 143 KB of shared memory per CTA means one 4-warp CTA per SM
+        # and no overlap of the two groups' launches (15 us alone, 21-30 us for the second group).
+        self.enc_mid = (self.device.type == "cuda" and bool(self.lib.spv_enc_mid_supported(self.d.n_hidden, self.d.n_private, self.d.n_shared))
+                        and __import__("os").environ.get("SPV_ENC_MID", "0") == "1")
         r8 = lambda x: (x + 7) // 8 * 8
         self.wb = None
         if self.bf16:
@@ -464,19 +469,26 @@ class StepEngine:
                            rowsA=bt.rows, bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.splits_fc1, ws=w.ws)
             mask = noise.drop[g] if (training and noise.drop is not None) else None
             dropping = training and (mask is not None or self.dropout_rate > 0)
-            fuse_drop = dropping and self._can_fuse(H)  # dropout in the fc2 epilogue (same keep mask as spv_dropout)
-            self._gemm(L.ptr(w.h1), L.ptr(self.P(g, "W2")), L.ptr(w.h2), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, tb=1, batch=2,
-                       sA=H, sB=H * H, sC=H, bias=L.ptr(self.P(g, "b2")), sBias=H, relu=1,
-                       drop=(0.0 if mask is not None else self.dropout_rate, L.ptr(mask), 8 + g, 2 * H) if fuse_drop else None)
-            if dropping and not fuse_drop:
-                L.check(lib.spv_dropout(L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, self.dropout_rate, self.seed,
-                                        8 + g, L.ptr(self.step_dev), st), "spv_dropout")
             bhd = self.P(g, "bhd")
-            with self._branch(g, "headp"):  # the private and the shared heads are independent
-                self._gemm(L.ptr(w.h2), L.ptr(self.P(g, "Whp")), L.ptr(w.r), B, 2 * P, H, lda=2 * H, ldb=H, ldc=NST, tb=1,
-                           bias=L.ptr(bhd))
-            self._gemm(w.h2.data_ptr() + 4 * H, L.ptr(self.P(g, "Whs")), w.r.data_ptr() + 4 * 2 * P, B, 2 * S, H, lda=2 * H,
-                       ldb=H, ldc=NST, tb=1, bias=bhd.data_ptr() + 4 * 2 * P)
+            if self.enc_mid:  # fc2 -> ReLU -> dropout -> mu / logvar heads of both encoders in one launch
+                L.check(lib.spv_enc_mid_fwd(L.ptr(w.h1), 2 * H, L.ptr(self.P(g, "W2")), L.ptr(self.P(g, "b2")),
+                                            L.ptr(self.P(g, "Whp")), L.ptr(self.P(g, "Whs")), L.ptr(bhd), L.ptr(w.h2), 2 * H,
+                                            L.ptr(w.r), NST, L.ptr(mask), 2 * H, self.dropout_rate if dropping else 0.0,
+                                            self.seed, 8 + g, L.ptr(self.step_dev), B, H, P, S, st), "spv_enc_mid_fwd")
+            else:
+                fuse_drop = dropping and self._can_fuse(H)  # dropout in the fc2 epilogue (same keep mask as spv_dropout)
+                self._gemm(L.ptr(w.h1), L.ptr(self.P(g, "W2")), L.ptr(w.h2), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, tb=1, batch=2,
+                           sA=H, sB=H * H, sC=H, bias=L.ptr(self.P(g, "b2")), sBias=H, relu=1,
+                           drop=(0.0 if mask is not None else self.dropout_rate, L.ptr(mask), 8 + g, 2 * H) if fuse_drop else None)
+                if dropping and not fuse_drop:
+                    L.check(lib.spv_dropout(L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, self.dropout_rate, self.seed,
+                                            8 + g, L.ptr(self.step_dev), st), "spv_dropout")
+                bhd = self.P(g, "bhd")
+                with self._branch(g, "headp"):  # the private and the shared heads are independent
+                    self._gemm(L.ptr(w.h2), L.ptr(self.P(g, "Whp")), L.ptr(w.r), B, 2 * P, H, lda=2 * H, ldb=H, ldc=NST, tb=1,
+                               bias=L.ptr(bhd))
+                self._gemm(w.h2.data_ptr() + 4 * H, L.ptr(self.P(g, "Whs")), w.r.data_ptr() + 4 * 2 * P, B, 2 * S, H, lda=2 * H,
+                           ldb=H, ldc=NST, tb=1, bias=bhd.data_ptr() + 4 * 2 * P)
             self._join(g, "headp")
             L.check(lib.spv_bn_fwd(L.ptr(w.r), NST, L.ptr(w.stats), NST, B, NST, L.ptr(self.P(g, "ghd")),
                                    L.ptr(self.P(g, "bthd")), ENC_BN_EPS, ENC_BN_MOM, L.ptr(self.Bf(g, "rm_hd")),
@@ -776,8 +788,15 @@ class StepEngine:
             fuse2 = self._can_fuse(2 * S)  # ReLU + dropout backward in the epilogue of the two head input-gradient GEMMs
             gate_p = (L.ptr(w.h2), 2 * H, L.ptr(mask), 2 * H, scale) if fuse2 else None
             gate_s = (w.h2.data_ptr() + 4 * H, 2 * H, mask.data_ptr() + 4 * H if mask is not None else None, 2 * H, scale) if fuse2 else None
-            with self._branch(g, "dh2p"):  # first on its auxiliary stream: this one is on the critical path
-                self._gemm(L.ptr(w.dr), L.ptr(self.P(g, "Whp")), L.ptr(w.dh2), B, H, 2 * P, lda=NST, ldb=H, ldc=2 * H, gate=gate_p)
+            if self.enc_mid:  # heads -> (ReLU, dropout) -> fc2 -> ReLU backward of both encoders in one launch: dh2, dh1 (+ bf16)
+                L.check(lib.spv_enc_mid_bwd(L.ptr(w.dr), NST, L.ptr(self.P(g, "Whp")), L.ptr(self.P(g, "Whs")),
+                                            L.ptr(self.P(g, "W2")), L.ptr(w.h2), 2 * H, L.ptr(w.h1), 2 * H, L.ptr(mask), 2 * H,
+                                            scale, L.ptr(w.dh2), 2 * H, L.ptr(w.dh1), 2 * H,
+                                            L.ptr(w.dh1b) if self.bf16 else None, 2 * H, B, H, P, S, st), "spv_enc_mid_bwd")
+            else:
+                with self._branch(g, "dh2p"):  # first on its auxiliary stream: this one is on the critical path
+                    self._gemm(L.ptr(w.dr), L.ptr(self.P(g, "Whp")), L.ptr(w.dh2), B, H, 2 * P, lda=NST, ldb=H, ldc=2 * H,
+                               gate=gate_p)
             if adam is not None:  # every decoder gradient of this group is final: update that range now
                 self._join(g, "wgrad")
                 self._join(g, "wgrad1")
@@ -793,19 +812,22 @@ class StepEngine:
                            splits=w.splits_b, ws=w.ws2)
                 self._gemm(drs, w.h2.data_ptr() + 4 * H, L.ptr(self.Gd(g, "Whs")), 2 * S, H, B, lda=NST, ldb=2 * H, ldc=H, ta=1,
                            splits=w.splits_b, ws=w.ws2)
-            self._gemm(drs, L.ptr(self.P(g, "Whs")), w.dh2.data_ptr() + 4 * H, B, H, 2 * S, lda=NST, ldb=H, ldc=2 * H, gate=gate_s)
-            self._join(g, "dh2p")
-            if not fuse2:
-                L.check(lib.spv_relu_bwd(L.ptr(w.dh2), 2 * H, L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, scale, st),
-                        "spv_relu_bwd")
+            if not self.enc_mid:
+                self._gemm(drs, L.ptr(self.P(g, "Whs")), w.dh2.data_ptr() + 4 * H, B, H, 2 * S, lda=NST, ldb=H, ldc=2 * H,
+                           gate=gate_s)
+                self._join(g, "dh2p")
+                if not fuse2:
+                    L.check(lib.spv_relu_bwd(L.ptr(w.dh2), 2 * H, L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, scale, st),
+                            "spv_relu_bwd")
             with self._branch(g, "wgrad1", lane=1):
                 self._gemm(L.ptr(w.dh2), L.ptr(w.h1), L.ptr(self.Gd(g, "W2")), H, H, B, lda=2 * H, ldb=2 * H, ldc=H, ta=1,
                            batch=2, sA=H, sB=H, sC=H * H, splits=w.splits_b, ws=w.ws3)
                 L.check(lib.spv_colsum(L.ptr(w.dh2), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b2")), self._stream()), "spv_colsum")
-            fuse1 = self._can_fuse(H)  # ReLU backward and the bf16 operand copy in the epilogue of the fc2 input-gradient GEMM
-            self._gemm(L.ptr(w.dh2), L.ptr(self.P(g, "W2")), L.ptr(w.dh1), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, batch=2, sA=H,
-                       sB=H * H, sC=H, gate=(L.ptr(w.h1), 2 * H, None, 0, 1.0) if fuse1 else None,
-                       c_bf16=(L.ptr(w.dh1b), 2 * H) if (fuse1 and self.bf16) else None)
+            fuse1 = self.enc_mid or self._can_fuse(H)  # ReLU backward + bf16 copy in the fc2 input-gradient GEMM's epilogue
+            if not self.enc_mid:
+                self._gemm(L.ptr(w.dh2), L.ptr(self.P(g, "W2")), L.ptr(w.dh1), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, batch=2,
+                           sA=H, sB=H * H, sC=H, gate=(L.ptr(w.h1), 2 * H, None, 0, 1.0) if fuse1 else None,
+                           c_bf16=(L.ptr(w.dh1b), 2 * H) if (fuse1 and self.bf16) else None)
             if not fuse1:
                 L.check(lib.spv_relu_bwd(L.ptr(w.dh1), 2 * H, L.ptr(w.h1), 2 * H, B, 2 * H, None, 0, 1.0, st), "spv_relu_bwd")
             if self.bf16:

@@ -150,3 +150,20 @@ def test_early_adam_is_the_same_update():
     off, shape = eng.params.offsets[0]["W1"]
     W1 = out[0][0][off:off + shape[0] * shape[1]].view(shape)
     assert torch.equal(out[0][4][:, :shape[1]], W1.bfloat16())  # the bf16 operand copy tracks the fp32 master
+
+
+def test_enc_mid_kernels_match_separate_launches():
+    """opt-in fused fc2 + heads kernels (spv_enc_mid_fwd / _bwd) against the default separate GEMM launches: same step"""
+    gd = Golden("label_tiny")
+    res = []
+    for fused in (False, True):
+        eng, batches, noise = engine_from_golden(gd, precision="bf16")
+        eng.enc_mid = fused and bool(eng.lib.spv_enc_mid_supported(eng.d.n_hidden, eng.d.n_private, eng.d.n_shared))
+        if fused and not eng.enc_mid:
+            pytest.skip("sizes not supported by the fused kernels")
+        ws = eng.forward(batches, training=True, noise=noise)
+        eng.backward()
+        torch.cuda.synchronize()
+        res.append((eng.loss_out.clone(), eng.grads.clone(), ws[0].r.clone(), ws[0].h2.clone(), ws[0].dh1.clone()))
+    for a, b in zip(*res):
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-7
