@@ -641,20 +641,21 @@ class StepEngine:
                                      L.ptr(self.step_dev), self._stream()), "spv_poe_fwd")
 
     # -------------------------------------------------------------------------------- backward
-    def backward(self, grad_scale: float = 1.0, adam: Optional[dict] = None, stage: str = "all"):
+    def backward(self, grad_scale: float = 1.0, adam: Optional[dict] = None, stage: str = "all", tick: bool = False):
         """gradients of loss * grad_scale w.r.t. every parameter, written into self.grads.
         adam (single-GPU training only: keys lr, betas, eps, weight_decay): also apply the optimiser step, per parameter range
         as soon as its gradients are complete: the decoder ranges (55 % of the parameters) update on an auxiliary stream
         while the encoder backward, a chain of small latency-bound kernels that leaves HBM idle, is still running.
         stage: "all", or "decoder" (decoders + PoE: every decoder-range gradient final) followed by "encoder" - the
-        data-parallel step all-reduces the decoder range while the encoder stage runs."""
+        data-parallel step all-reduces the decoder range while the encoder stage runs.  tick: advance the optimiser step
+        counter now (off the critical path), for callers that apply Adam per range afterwards (`adam_range_step`)."""
         ctx = self._ctx
         if ctx is None or not ctx["training"]:
             raise RuntimeError("backward needs a preceding training-mode forward")
         if stage not in ("all", "decoder", "encoder") or (adam is not None and stage != "all"):
             raise ValueError("stage must be 'all', 'decoder' or 'encoder' (the interleaved optimiser step needs 'all')")
         tick_events = []
-        if adam is not None:
+        if adam is not None or (tick and stage != "encoder"):
             if self.adam_m is None:
                 self.adam_m = torch.zeros_like(self.params.flat)
                 self.adam_v = torch.zeros_like(self.params.flat)
@@ -666,6 +667,8 @@ class StepEngine:
         if stage == "decoder":
             for g in (0, 1):  # every auxiliary branch back on the calling stream (a graph capture may end here)
                 self._join(g)
+            for ev in tick_events:
+                torch.cuda.current_stream(self.device).wait_event(ev)
             return
         self._backward_encoders(ctx, grad_scale, adam, tick_events)
 
@@ -859,6 +862,12 @@ class StepEngine:
                                   L.ll_array([s[0] for s in segs]), L.int_array([s[1] for s in segs]),
                                   L.int_array([s[2] for s in segs]), L.ptr_array([s[3] for s in segs]),
                                   L.ll_array([s[4] for s in segs]), 0, st), "spv_adam")
+
+    def adam_range_step(self, phase, lr=1e-3, betas=(0.9, 0.999), eps=0.01, weight_decay=1e-6, grad_scale=1.0):
+        """Adam on one phase of the flat layout (PHASE_ENC / PHASE_DEC); the step counter must have been advanced already
+        (backward(..., tick=True))"""
+        self._adam_range(*self.params.ranges[phase], {"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay,
+                                                      "grad_scale": grad_scale})
 
     def _adam_range(self, lo, hi, cfg, max_blocks=0):
         """Adam on the flat parameter range [lo, hi); *step already holds this update's index (spv_adam_tick)"""

@@ -107,12 +107,13 @@ class TrainLoop:
             e.adam_step(lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=1.0)
         else:  # data parallel: the decoder range is all-reduced while the encoder backward runs
             from .engine import PHASE_DEC, PHASE_ENC
-            e.backward(stage="decoder")
+            e.backward(stage="decoder", tick=True)
             self.grad_sync.start(e, PHASE_DEC)
             e.backward(stage="encoder")
             self.grad_sync.start(e, PHASE_ENC)
             gs = self.grad_sync.finish()
-            e.adam_step(lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=gs)
+            for ph in (PHASE_DEC, PHASE_ENC):
+                e.adam_range_step(ph, lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=gs)
         return e.loss_terms()
 
     def capture(self, batches: Sequence[GroupBatch], noise: Optional[Noise] = None) -> "torch.cuda.CUDAGraph":
@@ -138,18 +139,21 @@ class TrainLoop:
             with torch.cuda.graph(graph):
                 self.step(batches, noise)
         else:
-            # data parallel: forward + decoder/PoE backward, encoder backward and the optimiser are three graphs; the two
-            # gradient all-reduces are issued eagerly between the replays (collectives are kept out of graph capture)
-            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            # data parallel: forward + decoder/PoE backward, encoder backward and the two halves of the optimiser step are four
+            # graphs; the two gradient all-reduces are issued eagerly between the replays (collectives stay out of capture)
+            from .engine import PHASE_DEC, PHASE_ENC
+            g1, g2, g3, g4 = (torch.cuda.CUDAGraph() for _ in range(4))
+            scale = 1.0 / self.grad_sync.world
             with torch.cuda.graph(g1):
                 e.forward(batches, training=True, noise=noise)
-                e.backward(stage="decoder")
+                e.backward(stage="decoder", tick=True)
             with torch.cuda.graph(g2):
                 e.backward(stage="encoder")
-            scale = 1.0 / self.grad_sync.world
             with torch.cuda.graph(g3):
-                e.adam_step(lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=scale)
-            graph = _SyncedGraphs(g1, g2, g3, self.grad_sync, e)
+                e.adam_range_step(PHASE_DEC, lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=scale)
+            with torch.cuda.graph(g4):
+                e.adam_range_step(PHASE_ENC, lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=scale)
+            graph = _SyncedGraphs(g1, g2, g3, g4, self.grad_sync, e)
         torch.cuda.synchronize(e.device)
         e.params.flat.copy_(keep[0]); e.buffers.flat.copy_(keep[1]); e.step_dev.copy_(keep[2])
         if keep[3] is None:
@@ -161,20 +165,29 @@ class TrainLoop:
 
 
 class _SyncedGraphs:
-    """replay(): [forward + decoder/PoE backward] -> all-reduce(decoder range, async) -> [encoder backward] ->
-    all-reduce(encoder range) -> wait -> [Adam]"""
+    """replay(): [forward + decoder/PoE backward] -> all-reduce(decoder range, async) -> [encoder backward] on the main
+    stream while a side stream waits for that all-reduce and runs [Adam, decoder range] -> all-reduce(encoder range) ->
+    [Adam, encoder range]"""
 
-    def __init__(self, g_dec, g_enc, g_opt, grad_sync, engine):
-        self.g_dec, self.g_enc, self.g_opt, self.grad_sync, self.engine = g_dec, g_enc, g_opt, grad_sync, engine
+    def __init__(self, g_dec, g_enc, g_opt_dec, g_opt_enc, grad_sync, engine):
+        self.g_dec, self.g_enc, self.g_opt_dec, self.g_opt_enc = g_dec, g_enc, g_opt_dec, g_opt_enc
+        self.grad_sync, self.engine = grad_sync, engine
+        self.side = torch.cuda.Stream(device=engine.device)
 
     def replay(self):
         from .engine import PHASE_DEC, PHASE_ENC
+        main = torch.cuda.current_stream(self.engine.device)
         self.g_dec.replay()
         self.grad_sync.start(self.engine, PHASE_DEC)
+        with torch.cuda.stream(self.side):  # decoder half of the optimiser step beside the encoder backward
+            self.grad_sync.finish()
+            self.g_opt_dec.replay()
         self.g_enc.replay()
         self.grad_sync.start(self.engine, PHASE_ENC)
         self.grad_sync.finish()
-        self.g_opt.replay()
+        main.wait_stream(self.side)
+        self.g_opt_enc.replay()
+        self.side.wait_stream(main)  # the next replay's decoder-range Adam must not start before this step is done
 
 
 def init_params(engine: StepEngine, seed: int = 0):
