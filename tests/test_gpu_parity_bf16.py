@@ -153,11 +153,12 @@ def test_early_adam_is_the_same_update():
 
 
 def test_enc_mid_kernels_match_separate_launches():
-    """opt-in fused fc2 + heads kernels (spv_enc_mid_fwd / _bwd) against the default separate GEMM launches: same step"""
+    """opt-in fused fc2 + heads kernels (spv_enc_mid_fwd / _bwd) against the default separate GEMM launches: same step.
+    fp32 engine, so that rounding-order differences (~1e-7) are not amplified by bf16 operand rounding downstream."""
     gd = Golden("label_tiny")
     res = []
     for fused in (False, True):
-        eng, batches, noise = engine_from_golden(gd, precision="bf16")
+        eng, batches, noise = engine_from_golden(gd, precision="fp32")
         eng.enc_mid = fused and bool(eng.lib.spv_enc_mid_supported(eng.d.n_hidden, eng.d.n_private, eng.d.n_shared))
         if fused and not eng.enc_mid:
             pytest.skip("sizes not supported by the fused kernels")
@@ -166,4 +167,4 @@ def test_enc_mid_kernels_match_separate_launches():
         torch.cuda.synchronize()
         res.append((eng.loss_out.clone(), eng.grads.clone(), ws[0].r.clone(), ws[0].h2.clone(), ws[0].dh1.clone()))
     for a, b in zip(*res):
-        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-7
+        assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-7
