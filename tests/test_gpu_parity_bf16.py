@@ -168,3 +168,54 @@ def test_enc_mid_kernels_match_separate_launches():
         res.append((eng.loss_out.clone(), eng.grads.clone(), ws[0].r.clone(), ws[0].h2.clone(), ws[0].dh1.clone()))
     for a, b in zip(*res):
         assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-7
+
+
+@pytest.mark.parametrize("mode,precision", [("paired", "fp32"), ("cluster", "fp32"), ("paired", "bf16"), ("cluster", "bf16")])
+def test_ot_modes_hidden256_against_oracle(mode, precision):
+    """BASELINE.json configs[2] / [3] flavour at a size the oracle finishes in seconds: OT-paired and OT-cluster PoE with
+    n_hidden 256 (fc2 at the K = 256 limit of the whole-K GEMM), gene counts that are not multiples of the tile sizes,
+    different gene counts per group.  Indices bit-exact, loss terms within the north-star tolerances."""
+    from oracle import restatement as rs
+    from spvipes_b200 import synth
+    from spvipes_b200.engine import GroupBatch, Noise, StepEngine
+    from spvipes_b200.trainer import init_params
+
+    B, G0, G1, H, S, P, NL = 256, 1003, 1210, 256, 25, 10, 6
+    data = synth.make_counts((B, B), (G0, G1), NL, device="cuda", seed=77)
+    plan = synth.make_plan(B, B, data.labels[0], data.labels[1], NL, device="cuda", seed=7)
+    eng = StepEngine((G0, G1), H, S, P, 0.1, mode, "cuda", plan=plan, precision=precision)
+    sd0 = init_params(eng, 5)
+    eng.set_kl_weight(0.5)
+    gen = torch.Generator().manual_seed(13)
+    eps_p = [torch.randn(B, P, generator=gen) for _ in (0, 1)]
+    eps_q = [torch.randn(B, S, generator=gen) for _ in (0, 1)]
+    drop = [(torch.rand(B, 2 * H, generator=gen) < 0.9).float() / 0.9 for _ in (0, 1)]
+    noise = Noise([e.cuda() for e in eps_p], [e.cuda() for e in eps_q], [d.cuda() for d in drop])
+    idx = [torch.arange(B, dtype=torch.int32, device="cuda") for _ in (0, 1)]
+    labels = [data.labels[g] if mode == "cluster" else None for g in (0, 1)]
+    batches = [GroupBatch(X=data.X[g], labels=labels[g], idx=idx[g]) for g in (0, 1)]
+    ws = eng.forward(batches, training=True, noise=noise)
+    eng.backward()
+    torch.cuda.synchronize()
+    out = engine_outputs(eng, ws)
+    sd = {k: v.clone().requires_grad_("running" not in k) for k, v in sd0.items()}
+    dm = {(g, k): drop[g][:, i * H:(i + 1) * H] for g in (0, 1) for i, k in enumerate(("private", "shared"))}
+    want = rs.step(sd, [data.X[g].cpu().to(torch.float32) for g in (0, 1)], mode=mode, n_shared=S, n_private=P,
+                   eps_private=eps_p, eps_poe=eps_q, sub=plan.cpu(),
+                   labels=[data.labels[g].cpu().numpy() for g in (0, 1)] if mode == "cluster" else None, drop_masks=dm,
+                   kl_weight=0.5)
+    want["loss"].backward()
+    tol = 1e-4 if precision == "fp32" else 1e-2
+    assert relerr(out["loss"], want["loss"].detach()) < tol
+    for k in TERMS:
+        for g in (0, 1):
+            assert relerr(out[k][g], want[k][g].detach()) < tol, (k, g)
+    if mode == "paired":
+        for g in (0, 1):
+            assert np.array_equal(out["partners"][g], want["partners"][g])
+    grads = {k: sd[k].grad for k in rs.param_names(sd)}
+    cos, rel = _grad_cos({k: v.cpu() for k, v in eng.grad_dict().items()}, grads)
+    if precision == "fp32":
+        assert cos > 0.999999 and rel < 1e-3, (cos, rel)
+    else:
+        assert cos > 0.99 and rel < 0.15, (cos, rel)
