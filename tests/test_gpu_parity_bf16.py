@@ -219,3 +219,17 @@ def test_ot_modes_hidden256_against_oracle(mode, precision):
         assert cos > 0.999999 and rel < 1e-3, (cos, rel)
     else:
         assert cos > 0.99 and rel < 0.15, (cos, rel)
+
+
+def test_persistent_nb_kernel_opt_in():
+    """SPV_NB_PERSISTENT=1 selects the persistent forward kernel (nb_ptc.cu) when the library is first used, so the check runs
+    in a child process: the golden forward / backward cases and the C1-shaped oracle case with that kernel."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SPV_NB_PERSISTENT="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity_bf16.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "bf16_forward_matches_golden or bf16_backward_matches_golden or c1_shape_against_oracle"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
