@@ -1,4 +1,8 @@
-"""Per-unit timestamps of the persistent NB forward kernel (diagnostic): python tools/ptc_trace.py"""
+"""Per-unit timestamps of the persistent NB forward kernel (diagnostic).  Needs a library built with the trace code and the
+opt-in kernel selected:
+    SPV_NVCC_EXTRA="-DPTC_TRACE" python -m spvipes_b200.build --force
+    SPV_NVCC_EXTRA="-DPTC_TRACE" SPV_NB_PERSISTENT=1 python tools/ptc_trace.py
+(-DPTC_EXP=1|2|3 builds the timing experiments described in profiles/r1_nb_persistent_notes.md)."""
 import ctypes
 import os
 import sys
