@@ -2,7 +2,8 @@
 opt-in kernel selected:
     SPV_NVCC_EXTRA="-DPTC_TRACE" python -m spvipes_b200.build --force
     SPV_NVCC_EXTRA="-DPTC_TRACE" SPV_NB_PERSISTENT=1 python tools/ptc_trace.py
-(-DPTC_EXP=1|2|3 builds the timing experiments described in profiles/r1_nb_persistent_notes.md)."""
+(-DPTC_EXP=2 replaces every MUFU by an FFMA: one of the timing experiments of profiles/r1_nb_persistent_notes.md; the
+count-gather and no-math variants were one-off edits and are not in the tree)."""
 import ctypes
 import os
 import sys
