@@ -25,6 +25,7 @@ extern "C" int spv_debug_trace(long long* buf) {  // diagnostic hook (tools/ptc_
     g_trace = buf;
     return 0;
 }
+extern "C" long long* spv_debug_get_trace() { return g_trace; }
 __device__ __forceinline__ long long gtime() {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

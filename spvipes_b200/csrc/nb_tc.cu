@@ -19,9 +19,14 @@
 #include "decoder_common.cuh"
 #include "../../include/spvipes_b200.h"
 
+extern "C" long long* spv_debug_get_trace();  // nb_ptc.cu: the buffer set by spv_debug_trace, or null
+
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 64, STAGES = 2;
+#ifndef NB_STAGES
+#define NB_STAGES 2
+#endif
+constexpr int BM = 128, BN = 64, BK = 64, STAGES = NB_STAGES;
 constexpr int WCOLS = BN / 2;                 // gene columns per epilogue warp (two warps per TMEM lane quarter)
 constexpr int GATHER_ROWS = 64 / BN;          // rows of the count tile one warp gathers per load: 32 lanes cover BN / 2 words each
 constexpr int EPI_WARPS = 8, EPI_THREADS = 32 * EPI_WARPS;
@@ -42,6 +47,7 @@ struct NbTcParams {
     float* part_nb;                    // [nTG, B, 3]
     int B, G, K, kb_z;                 // kb_z: k-block holding the latent columns
     int Gp;                            // row offset of the shared block inside the folded-weight operand
+    long long* trace;                  // diagnostic (NB_TRACE builds): 6 globaltimer stamps per CTA
 };
 
 // row of the count tile that lane `lane` of epilogue warp e loads in its i-th gather: a warp covers GATHER_ROWS rows per load
@@ -70,6 +76,14 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
     const int num_kb = (p.K + BK - 1) / BK;
+#ifdef NB_TRACE
+    long long* tr = (p.trace && threadIdx.x == 64) ? p.trace + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    auto stamp = [&](int i) { if (tr) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[i] = t; } };
+    if (tr) { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); tr[7] = smid; }
+    stamp(0);
+#else
+    auto stamp = [&](int) {};
+#endif
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&mapA);
@@ -88,6 +102,7 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    stamp(1);  // barriers initialised, tensor memory allocated
 
     if (warp == 0) {
         if (tc::elect_one()) {
@@ -138,17 +153,8 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
         // ================= epilogue: 8 warps =================
         const int et = threadIdx.x - 64;  // 0..255
         const long G = p.G;
-        if (SRC == SPV_SRC_U16_LOG1P) nb_fill_count_lut(s_lut, et);  // EPI_THREADS == 256; overlaps the TMA / MMA phase
-        for (int i = et; i < BN; i += EPI_THREADS) {  // per-gene constants of the tile
-            int g = n0 + i;
-            bool ok = g < p.G;
-            s_gc[0 * BN + i] = ok ? __ldg(p.genec + GC_CPL * G + g) : 0.0f;   // constants of nb_forward_v3
-            s_gc[1 * BN + i] = ok ? __ldg(p.genec + GC_CSL * G + g) : 0.0f;
-            s_gc[2 * BN + i] = ok ? __ldg(p.bm + g) : 0.0f;
-            s_gc[3 * BN + i] = ok ? __ldg(p.genec + GC_THETA * G + g) : 1.0f;
-            s_gc[4 * BN + i] = ok ? __ldg(p.genec + GC_THE * G + g) : 1.0f;
-            s_gc[5 * BN + i] = ok ? __ldg(p.genec + GC_K0 * G + g) : 0.0f;
-        }
+        // Every global load of the prologue is issued before anything waits on one: the row indices first (the count gather
+        // depends on them), then the per-gene and per-row constants; the count LUT is computed while they are in flight.
         const int e = warp - 2;
         const int q = warp & 3;          // TMEM lane quarter this warp may access
         const int half = e >> 2;         // which 32 gene columns of the tile
@@ -156,25 +162,40 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
         const int m = m0 + rloc;
         const bool mok = m < p.B;
         const int mm = mok ? m : 0;
-        const float Rpl = NB_LOG2E * __ldg(p.rowc + (long)mm * 4 + 0), Rsl = NB_LOG2E * __ldg(p.rowc + (long)mm * 4 + 1);
-        const long xrow = (p.rows ? (long)__ldg(p.rows + mm) : (long)mm) * p.ldx;
+        constexpr int NGATHER = BM / EPI_WARPS / GATHER_ROWS;
+        int ridx[NGATHER];
+        if (SRC == SPV_SRC_U16_LOG1P) {
+#pragma unroll
+            for (int i = 0; i < NGATHER; ++i) {
+                const int gm = m0 + cnt_row(e, lane, i);
+                ridx[i] = gm < p.B ? (p.rows ? __ldg(p.rows + gm) : gm) : -1;
+            }
+        }
+        const int my_row = p.rows ? __ldg(p.rows + mm) : mm;
+        float Rpl = __ldg(p.rowc + (long)mm * 4 + 0), Rsl = __ldg(p.rowc + (long)mm * 4 + 1);
+        float gcv[6] = {0.0f, 0.0f, 0.0f, 1.0f, 1.0f, 0.0f};
+        static_assert(BN <= EPI_THREADS, "one thread per gene of the tile stages its constants");
+        if (et < BN && n0 + et < p.G) {
+            const int g = n0 + et;
+            gcv[0] = __ldg(p.genec + GC_CPL * G + g);  // constants of nb_forward_v3
+            gcv[1] = __ldg(p.genec + GC_CSL * G + g);
+            gcv[2] = __ldg(p.bm + g);
+            gcv[3] = __ldg(p.genec + GC_THETA * G + g);
+            gcv[4] = __ldg(p.genec + GC_THE * G + g);
+            gcv[5] = __ldg(p.genec + GC_K0 * G + g);
+        }
+        if (SRC == SPV_SRC_U16_LOG1P) nb_fill_count_lut(s_lut, et);  // EPI_THREADS == 256; overlaps the TMA / MMA phase
         // coalesced row gather of the tile's counts into registers (overlaps the MMA phase): warp e takes rows e, e + 8, ...;
         // lane l takes genes 2l, 2l + 1
-        uint32_t cw[BM / EPI_WARPS];  // with GATHER_ROWS > 1 only the first BM / EPI_WARPS / GATHER_ROWS entries are used
+        uint32_t cw[BM / EPI_WARPS];  // with GATHER_ROWS > 1 only the first NGATHER entries are used
         if (SRC == SPV_SRC_U16_LOG1P) {
             const unsigned short* X16 = reinterpret_cast<const unsigned short*>(p.X);
-            long xr[BM / EPI_WARPS / GATHER_ROWS];
-#pragma unroll
-            for (int i = 0; i < BM / EPI_WARPS / GATHER_ROWS; ++i) {
-                const int gm = m0 + cnt_row(e, lane, i);
-                xr[i] = gm < p.B ? (p.rows ? (long)__ldg(p.rows + gm) : (long)gm) * p.ldx : -1;
-            }
             const int g = n0 + 2 * (lane % (BN / 2));
 #pragma unroll
-            for (int i = 0; i < BM / EPI_WARPS / GATHER_ROWS; ++i) {
+            for (int i = 0; i < NGATHER; ++i) {
                 cw[i] = 0u;
-                if (xr[i] >= 0) {
-                    const unsigned short* src = X16 + xr[i] + g;
+                if (ridx[i] >= 0) {
+                    const unsigned short* src = X16 + (long)ridx[i] * p.ldx + g;
                     if (g + 1 < p.G && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
                         cw[i] = __ldg(reinterpret_cast<const uint32_t*>(src));
                     } else {
@@ -184,13 +205,22 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
                 }
             }
         }
+        if (et < BN) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) s_gc[j * BN + et] = gcv[j];
+        }
+        Rpl *= NB_LOG2E; Rsl *= NB_LOG2E;
+        const long xrow = (long)my_row * p.ldx;
+        stamp(2);  // count gather issued
         tc::mbar_wait(tmem_full, 0);  // accumulators complete; the operand stages are free from here on
         tc::fence_after_sync();
+        stamp(3);  // accumulators complete
         if (SRC == SPV_SRC_U16_LOG1P) {
 #pragma unroll
             for (int i = 0; i < BM / EPI_WARPS / GATHER_ROWS; ++i) s_cnt[cnt_row(e, lane, i) * CNT_PITCH_W + lane % (BN / 2)] = cw[i];
         }
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");  // constants + counts staged (epilogue warps only)
+        stamp(4);  // counts staged
         float sll = 0.0f, sep = 0.0f, ses = 0.0f;
         const bool vec_pi = p.pi && ((G & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.pi) & 15) == 0);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -245,6 +275,7 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
             float* o = p.part_nb + ((long)(blockIdx.x * 2 + half) * p.B + m) * 3;
             o[0] = sll; o[1] = sep; o[2] = ses;
         }
+        stamp(5);  // epilogue done
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -427,6 +458,7 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
     p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
     p.rowc = (const float*)ptrs[9]; p.pi = store_pi ? (float*)ptrs[10] : nullptr; p.part_nb = (float*)ptrs[11];
     p.B = B; p.G = G; p.K = K; p.kb_z = HD / BK;
+    p.trace = spv_debug_get_trace();
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(nb_tc_fwd_kernel<SPV_SRC_U16_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||

@@ -131,17 +131,8 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
         // ================= epilogue: 8 warps =================
         const int et = threadIdx.x - 64;
         const long G = p.G;
-        if (SRC == SPV_SRC_U16_LOG1P) s_lut[et] = et == 0 ? 0.0f : log1pf((float)et);  // EPI_THREADS == 256
-        for (int i = et; i < BN; i += EPI_THREADS) {
-            int g = n0 + i;
-            bool ok = g < p.G;
-            s_gc[0 * BN + i] = ok ? __ldg(p.genec + GC_CPL * G + g) : 0.0f;   // constants of nb_backward_v3
-            s_gc[1 * BN + i] = ok ? __ldg(p.genec + GC_CSL * G + g) : 0.0f;
-            s_gc[2 * BN + i] = ok ? __ldg(p.bm + g) : 0.0f;
-            s_gc[3 * BN + i] = ok ? __ldg(p.genec + GC_THETA * G + g) : 1.0f;
-            s_gc[4 * BN + i] = ok ? __ldg(p.genec + GC_THE * G + g) : 1.0f;
-            s_gc[5 * BN + i] = ok ? __ldg(p.genec + GC_K1 * G + g) : 0.0f;
-        }
+        // Every global load of the prologue is issued before anything waits on one (as in nb_tc_fwd_kernel): the row indices
+        // first, then the per-row and per-gene constants; the LUT is computed while they are in flight.
         const int e = warp - 2;
         const int q = warp & 3;
         const int half = e >> 2;
@@ -149,27 +140,41 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
         const int m = m0 + rloc;
         const bool mok = m < p.B;
         const int mm = mok ? m : 0;
-        const float Rpl = NB_LOG2E * __ldg(p.rowc + (long)mm * 4 + 0), Rsl = NB_LOG2E * __ldg(p.rowc + (long)mm * 4 + 1);
-        const float inv_elib = fast_exp(-__ldg(p.lib + mm));
-        const float DpI = inv_elib * __ldg(p.rowc + (long)mm * 4 + 2), DsI = inv_elib * __ldg(p.rowc + (long)mm * 4 + 3);
-        const long xrow = (p.rows ? (long)__ldg(p.rows + mm) : (long)mm) * p.ldx;
+        constexpr int NGATHER = BM / EPI_WARPS / GATHER_ROWS;
+        int ridx[NGATHER];
+        if (SRC == SPV_SRC_U16_LOG1P) {
+#pragma unroll
+            for (int i = 0; i < NGATHER; ++i) {
+                const int gm = m0 + cnt_row(e, lane, i);
+                ridx[i] = gm < p.B ? (p.rows ? __ldg(p.rows + gm) : gm) : -1;
+            }
+        }
+        const int my_row = p.rows ? __ldg(p.rows + mm) : mm;
+        const float4 rc = __ldg(reinterpret_cast<const float4*>(p.rowc) + mm);  // Rp, Rs, Dp, Ds
+        const float libm = __ldg(p.lib + mm);
+        float gcv[6] = {0.0f, 0.0f, 0.0f, 1.0f, 1.0f, 0.0f};
+        static_assert(BN <= EPI_THREADS, "one thread per gene of the tile stages its constants");
+        if (et < BN && n0 + et < p.G) {
+            const int g = n0 + et;
+            gcv[0] = __ldg(p.genec + GC_CPL * G + g);  // constants of nb_backward_v3
+            gcv[1] = __ldg(p.genec + GC_CSL * G + g);
+            gcv[2] = __ldg(p.bm + g);
+            gcv[3] = __ldg(p.genec + GC_THETA * G + g);
+            gcv[4] = __ldg(p.genec + GC_THE * G + g);
+            gcv[5] = __ldg(p.genec + GC_K1 * G + g);
+        }
+        if (SRC == SPV_SRC_U16_LOG1P) s_lut[et] = et == 0 ? 0.0f : log1pf((float)et);  // EPI_THREADS == 256
         // coalesced row gather of the tile's counts into registers (overlaps the MMA phase): warp e takes rows e, e + 8, ...;
         // lane l takes genes 2l, 2l + 1
-        uint32_t cw[BM / EPI_WARPS];  // with GATHER_ROWS > 1 only the first BM / EPI_WARPS / GATHER_ROWS entries are used
+        uint32_t cw[BM / EPI_WARPS];  // with GATHER_ROWS > 1 only the first NGATHER entries are used
         if (SRC == SPV_SRC_U16_LOG1P) {
             const unsigned short* X16 = reinterpret_cast<const unsigned short*>(p.X);
-            long xr[BM / EPI_WARPS / GATHER_ROWS];
-#pragma unroll
-            for (int i = 0; i < BM / EPI_WARPS / GATHER_ROWS; ++i) {
-                const int gm = m0 + cnt_row(e, lane, i);
-                xr[i] = gm < p.B ? (p.rows ? (long)__ldg(p.rows + gm) : (long)gm) * p.ldx : -1;
-            }
             const int g = n0 + 2 * (lane % (BN / 2));
 #pragma unroll
-            for (int i = 0; i < BM / EPI_WARPS / GATHER_ROWS; ++i) {
+            for (int i = 0; i < NGATHER; ++i) {
                 cw[i] = 0u;
-                if (xr[i] >= 0) {
-                    const unsigned short* src = X16 + xr[i] + g;
+                if (ridx[i] >= 0) {
+                    const unsigned short* src = X16 + (long)ridx[i] * p.ldx + g;
                     if (g + 1 < p.G && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
                         cw[i] = __ldg(reinterpret_cast<const uint32_t*>(src));
                     } else {
@@ -179,6 +184,14 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
                 }
             }
         }
+        if (et < BN) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) s_gc[j * BN + et] = gcv[j];
+        }
+        const float Rpl = NB_LOG2E * rc.x, Rsl = NB_LOG2E * rc.y;
+        const float inv_elib = fast_exp(-libm);
+        const float DpI = inv_elib * rc.z, DsI = inv_elib * rc.w;
+        const long xrow = (long)my_row * p.ldx;
         tc::mbar_wait(tmem_full, 0);  // accumulators complete; the operand stages are free from here on
         tc::fence_after_sync();
         if (SRC == SPV_SRC_U16_LOG1P) {
@@ -312,6 +325,7 @@ extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
     const int K = HD + P + S;
+    if (reinterpret_cast<uintptr_t>(ptrs[9]) & 15) return SPV_ERR_ARG;  // rowc rows are read as one float4
     const void* wz_bf16 = reinterpret_cast<const __nv_bfloat16*>(wstack_bf16) + (size_t)Gp * ld_w;
     CUtensorMap ma, mb, mz;
     int rc = spv_make_tensor_map_bf16(&ma, amix_bf16, (unsigned long long)K, (unsigned long long)B, (unsigned long long)ld_amixb, 64, BM);
