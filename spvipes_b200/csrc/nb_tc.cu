@@ -56,7 +56,7 @@ __device__ __forceinline__ int cnt_row(int e, int lane, int i) {
 }
 
 template <int SRC>
-__global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                const __grid_constant__ CUtensorMap mapB,
                                                                const __grid_constant__ CUtensorMap mapZ, NbTcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -70,17 +70,18 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
     uint64_t* empty = full + STAGES;
     uint64_t* z_full = empty + STAGES;
     uint64_t* tmem_full = z_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_ready = tmem_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_ready + 1);
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(tiles);  // aliases the operand stages once the MMAs are done
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
     const int num_kb = (p.K + BK - 1) / BK;
 #ifdef NB_TRACE
-    long long* tr = (p.trace && threadIdx.x == 64) ? p.trace + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    long long* tr = (p.trace && (threadIdx.x == 64 || threadIdx.x == 32)) ? p.trace + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
     auto stamp = [&](int i) { if (tr) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[i] = t; } };
-    if (tr) { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); tr[7] = smid; }
-    stamp(0);
+    if (tr && threadIdx.x == 64) { unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); tr[7] = smid; }
+    if (threadIdx.x == 64) stamp(0);
 #else
     auto stamp = [&](int) {};
 #endif
@@ -95,14 +96,15 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
         }
         tc::mbar_init(z_full, 1);
         tc::mbar_init(tmem_full, 1);
+        tc::mbar_init(tmem_ready, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
-    tc::fence_before_sync();
     __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-    stamp(1);  // barriers initialised, tensor memory allocated
+    // Tensor memory is allocated by the MMA warp only when it is about to issue: 3 x 64 accumulator columns round up to 256, so
+    // two CTAs own an SM's 512 columns, while registers and shared memory admit a third.  That third CTA runs its whole
+    // prologue (operand loads into both stages, count gather) while it waits in tcgen05.alloc for an owner to exit, which hides
+    // most of the ~5 us load phase behind the other CTAs' likelihood math (profiles/r1_nb_persistent_notes.md).
+    uint32_t tmem_base = 0;
 
     if (warp == 0) {
         if (tc::elect_one()) {
@@ -120,7 +122,14 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
             }
         }
     } else if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, TMEM_COLS);  // whole warp; blocks while two other CTAs own the SM's tensor memory
+        tc::fence_before_sync();
+        __syncwarp();
+        tc::fence_after_sync();
+        tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+        if (lane == 0) stamp(6);  // tensor memory granted
         if (tc::elect_one()) {
+            tc::mbar_arrive(tmem_ready);  // release: the epilogue warps read the slot after acquiring this barrier
             constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, false, false);
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
@@ -212,6 +221,8 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
         Rpl *= NB_LOG2E; Rsl *= NB_LOG2E;
         const long xrow = (long)my_row * p.ldx;
         stamp(2);  // count gather issued
+        tc::mbar_wait(tmem_ready, 0);
+        tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
         tc::mbar_wait(tmem_full, 0);  // accumulators complete; the operand stages are free from here on
         tc::fence_after_sync();
         stamp(3);  // accumulators complete
@@ -279,6 +290,7 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_fwd_kernel(const __grid_cons
     }
     tc::fence_before_sync();
     __syncthreads();
+    if (threadIdx.x == 64) stamp(1);  // every warp of the CTA done
     if (warp == 1) {
         tc::fence_after_sync();
         tc::tmem_dealloc(tmem_base, TMEM_COLS);

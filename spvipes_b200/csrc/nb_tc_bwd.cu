@@ -42,7 +42,7 @@ __device__ __forceinline__ int cnt_row(int e, int lane, int i) {
 }
 
 template <int SRC>
-__global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                const __grid_constant__ CUtensorMap mapB,
                                                                const __grid_constant__ CUtensorMap mapZ, NbTcBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
     uint64_t* empty = full + STAGES;
     uint64_t* z_full = empty + STAGES;
     uint64_t* tmem_full = z_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_ready = tmem_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_ready + 1);
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(tiles);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -74,13 +75,13 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
         }
         tc::mbar_init(z_full, 1);
         tc::mbar_init(tmem_full, 1);
+        tc::mbar_init(tmem_ready, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
-    tc::fence_before_sync();
     __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
+    // tensor memory is allocated by the MMA warp when it is about to issue, so that a third resident CTA runs its prologue
+    // while two others own the SM's 512 columns (see nb_tc_fwd_kernel)
+    uint32_t tmem_base = 0;
 
     if (warp == 0) {
         if (tc::elect_one()) {
@@ -98,7 +99,13 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
             }
         }
     } else if (warp == 1) {
+        tc::tmem_alloc(tmem_slot, TMEM_COLS);  // whole warp; blocks while two other CTAs own the SM's tensor memory
+        tc::fence_before_sync();
+        __syncwarp();
+        tc::fence_after_sync();
+        tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
         if (tc::elect_one()) {
+            tc::mbar_arrive(tmem_ready);  // release: the epilogue warps read the slot after acquiring this barrier
             constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, false, false);
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
@@ -192,6 +199,8 @@ __global__ void __launch_bounds__(THREADS, 2) nb_tc_bwd_kernel(const __grid_cons
         const float inv_elib = fast_exp(-libm);
         const float DpI = inv_elib * rc.z, DsI = inv_elib * rc.w;
         const long xrow = (long)my_row * p.ldx;
+        tc::mbar_wait(tmem_ready, 0);
+        tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
         tc::mbar_wait(tmem_full, 0);  // accumulators complete; the operand stages are free from here on
         tc::fence_after_sync();
         if (SRC == SPV_SRC_U16_LOG1P) {

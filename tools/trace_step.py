@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--out", default="gpurun_out/timeline.md")
     ap.add_argument("--replays", type=int, default=7)
+    ap.add_argument("--cells", type=int, default=None, help="cells per group held on the device (default: the workload's)")
     a = ap.parse_args()
     from spvipes_b200 import _lib as L
     from spvipes_b200 import synth
@@ -32,6 +33,7 @@ def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     mode, n_cells, genes, H, B, n_labels = bench.WORKLOADS[a.workload]
+    n_cells = a.cells or n_cells
     L.load()
     data = synth.make_counts((n_cells, n_cells), (genes, genes), n_labels, device=dev, seed=1234)
     eng = StepEngine((genes, genes), H, bench.S_DIM, bench.P_DIM, 0.1, mode, device=dev, seed=0, precision=a.precision)
