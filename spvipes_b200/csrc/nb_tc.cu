@@ -32,7 +32,9 @@ constexpr int GATHER_ROWS = 64 / BN;          // rows of the count tile one warp
 constexpr int EPI_WARPS = 8, EPI_THREADS = 32 * EPI_WARPS;
 constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TMEM_COLS = BN == 64 ? 256 : 128;           // 3 x 64 used
+constexpr int TMEM_COLS = BN == 64 ? 256 : 128;           // single allocation of the statistics kernel
+constexpr int ACC_COLS = BN, Z_COLS = 2 * BN;             // the likelihood kernels allocate in two steps (powers of two >= 32)
+static_assert(ACC_COLS == 32 || ACC_COLS == 64, "tensor-memory allocations are powers of two");
 constexpr int CNT_PITCH_W = BN / 2 + 1;  // uint16 count tile: 33 32-bit words per row, conflict-free for thread = row reads
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 6 * BN * 4 + 256 * 8 + 256;
 
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
     // two CTAs own an SM's 512 columns, while registers and shared memory admit a third.  That third CTA runs its whole
     // prologue (operand loads into both stages, count gather) while it waits in tcgen05.alloc for an owner to exit, which hides
     // most of the ~5 us load phase behind the other CTAs' likelihood math (profiles/r1_nb_persistent_notes.md).
-    uint32_t tmem_base = 0;
+    uint32_t tmem_base = 0, tmem_z = 0;  // mixture-logit accumulator [BN columns]; the two branch-logit accumulators [2 BN]
 
     if (warp == 0) {
         if (tc::elect_one()) {
@@ -122,15 +124,18 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
             }
         }
     } else if (warp == 1) {
-        tc::tmem_alloc(tmem_slot, TMEM_COLS);  // whole warp; blocks while two other CTAs own the SM's tensor memory
+        // Two-step allocation.  The BN columns of the mixture-logit accumulator are free whenever at most two other CTAs hold
+        // their full 3 x BN, so this CTA streams all its k-blocks through the stages and finishes that accumulator while it
+        // is still waiting for tensor memory; only the 8 MMAs of the two branch logits (one k-block against the resident
+        // folded-weight tiles) are left once the second allocation is granted.  One thread issues every MMA and commit.
+        tc::tmem_alloc_keep_permit(tmem_slot, ACC_COLS);
         tc::fence_before_sync();
         __syncwarp();
         tc::fence_after_sync();
         tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-        if (lane == 0) stamp(6);  // tensor memory granted
-        if (tc::elect_one()) {
-            tc::mbar_arrive(tmem_ready);  // release: the epilogue warps read the slot after acquiring this barrier
-            constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, false, false);
+        constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, false, false);
+        const int s_z = p.kb_z % STAGES;  // kb_z is the last k-block (checked by the host): its stage is kept for the branch MMAs
+        if (lane == 0) {
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
@@ -142,22 +147,32 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
                 for (int kk = 0; kk < BK / 16; ++kk)
                     tc::umma_bf16(tmem_base, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(b_base + kk * 32, 16, 1024),
                                   idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                if (i == p.kb_z) {  // the two softmax-branch logits: same A block against the folded weights
-                    tc::mbar_wait(z_full, 0);
-                    tc::fence_after_sync();
-                    const uint32_t zp_base = tc::smem_u32(z_tiles), zs_base = zp_base + B_BYTES;
+                if (i != p.kb_z) tc::umma_commit(&empty[s]);
+            }
+        }
+        __syncwarp();
+        tc::tmem_alloc(tmem_slot + 1, Z_COLS);  // whole warp; blocks while two other CTAs own their full sets
+        tc::fence_before_sync();
+        __syncwarp();
+        tc::fence_after_sync();
+        tmem_z = *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1);
+        if (lane == 0) {
+            stamp(6);  // tensor memory granted
+            tc::mbar_arrive(tmem_ready);  // release: the epilogue warps read the slots after acquiring this barrier
+            tc::mbar_wait(z_full, 0);
+            tc::fence_after_sync();
+            const uint32_t a_base = tc::smem_u32(tiles + s_z * STAGE_BYTES);
+            const uint32_t zp_base = tc::smem_u32(z_tiles), zs_base = zp_base + B_BYTES;
 #pragma unroll
-                    for (int kk = 0; kk < BK / 16; ++kk) {
-                        tc::umma_bf16(tmem_base + BN, tc::smem_desc(a_base + kk * 32, 16, 1024),
-                                      tc::smem_desc(zp_base + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
-                        tc::umma_bf16(tmem_base + 2 * BN, tc::smem_desc(a_base + kk * 32, 16, 1024),
-                                      tc::smem_desc(zs_base + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
-                    }
-                }
-                tc::umma_commit(&empty[s]);
+            for (int kk = 0; kk < BK / 16; ++kk) {  // the two softmax-branch logits: latent k-block against the folded weights
+                tc::umma_bf16(tmem_z, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zp_base + kk * 32, 16, 1024), idesc,
+                              kk > 0 ? 1u : 0u);
+                tc::umma_bf16(tmem_z + BN, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zs_base + kk * 32, 16, 1024),
+                              idesc, kk > 0 ? 1u : 0u);
             }
             tc::umma_commit(tmem_full);
         }
+        __syncwarp();
     } else {
         // ================= epilogue: 8 warps =================
         const int et = threadIdx.x - 64;  // 0..255
@@ -223,6 +238,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
         stamp(2);  // count gather issued
         tc::mbar_wait(tmem_ready, 0);
         tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+        tmem_z = *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1);
         tc::mbar_wait(tmem_full, 0);  // accumulators complete; the operand stages are free from here on
         tc::fence_after_sync();
         stamp(3);  // accumulators complete
@@ -234,14 +250,14 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
         stamp(4);  // counts staged
         float sll = 0.0f, sep = 0.0f, ses = 0.0f;
         const bool vec_pi = p.pi && ((G & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.pi) & 15) == 0);
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16), lane_z = tmem_z + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
         for (int j4 = 0; j4 < WCOLS; j4 += 4) {
             const int c0 = half * WCOLS + j4;
             uint32_t rpi[4], rlp[4], rls[4];
             tc::tmem_ld4(lane_addr + (uint32_t)c0, rpi);
-            tc::tmem_ld4(lane_addr + (uint32_t)(BN + c0), rlp);
-            tc::tmem_ld4(lane_addr + (uint32_t)(2 * BN + c0), rls);
+            tc::tmem_ld4(lane_z + (uint32_t)c0, rlp);
+            tc::tmem_ld4(lane_z + (uint32_t)(BN + c0), rls);
             tc::tmem_ld_wait();
             if (!mok) continue;
             float pv[4];
@@ -293,7 +309,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
     if (threadIdx.x == 64) stamp(1);  // every warp of the CTA done
     if (warp == 1) {
         tc::fence_after_sync();
-        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+        tc::tmem_dealloc(tmem_z, Z_COLS);
+        tc::tmem_dealloc(tmem_base, ACC_COLS);
     }
 }
 
@@ -470,6 +487,7 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
     p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
     p.rowc = (const float*)ptrs[9]; p.pi = store_pi ? (float*)ptrs[10] : nullptr; p.part_nb = (float*)ptrs[11];
     p.B = B; p.G = G; p.K = K; p.kb_z = HD / BK;
+    if (p.kb_z != (K + BK - 1) / BK - 1) return SPV_ERR_ARG;  // the latent columns must be the last k-block (P + S <= 64)
     p.trace = spv_debug_get_trace();
     static bool configured = false;
     if (!configured) {

@@ -18,7 +18,8 @@ constexpr int GATHER_ROWS = 64 / BN;          // rows of the count tile one warp
 constexpr int EPI_WARPS = 8, EPI_THREADS = 32 * EPI_WARPS;
 constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TMEM_COLS = BN == 64 ? 256 : 128;
+constexpr int ACC_COLS = BN, Z_COLS = 2 * BN;  // tensor memory is allocated in two steps (powers of two >= 32)
+static_assert(ACC_COLS == 32 || ACC_COLS == 64, "tensor-memory allocations are powers of two");
 constexpr int CNT_PITCH_W = BN / 2 + 1;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 7 * BN * 4 + 4 * 4 * BN * 4 + 256 * 4 + 256;
 
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
     __syncthreads();
     // tensor memory is allocated by the MMA warp when it is about to issue, so that a third resident CTA runs its prologue
     // while two others own the SM's 512 columns (see nb_tc_fwd_kernel)
-    uint32_t tmem_base = 0;
+    uint32_t tmem_base = 0, tmem_z = 0;  // mixture-logit accumulator [BN columns]; the two branch-logit accumulators [2 BN]
 
     if (warp == 0) {
         if (tc::elect_one()) {
@@ -99,14 +100,16 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
             }
         }
     } else if (warp == 1) {
-        tc::tmem_alloc(tmem_slot, TMEM_COLS);  // whole warp; blocks while two other CTAs own the SM's tensor memory
+        // two-step allocation as in nb_tc_fwd_kernel: the mixture-logit accumulator is completed while the CTA still waits
+        // for the 2 BN columns of the branch logits; one thread issues every MMA and commit
+        tc::tmem_alloc_keep_permit(tmem_slot, ACC_COLS);
         tc::fence_before_sync();
         __syncwarp();
         tc::fence_after_sync();
         tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-        if (tc::elect_one()) {
-            tc::mbar_arrive(tmem_ready);  // release: the epilogue warps read the slot after acquiring this barrier
-            constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, false, false);
+        constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, false, false);
+        const int s_z = p.kb_z % STAGES;  // kb_z is the last k-block (checked by the host): its stage is kept for the branch MMAs
+        if (lane == 0) {
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
@@ -118,22 +121,31 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
                 for (int kk = 0; kk < BK / 16; ++kk)
                     tc::umma_bf16(tmem_base, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(b_base + kk * 32, 16, 1024),
                                   idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                if (i == p.kb_z) {
-                    tc::mbar_wait(z_full, 0);
-                    tc::fence_after_sync();
-                    const uint32_t zp_base = tc::smem_u32(z_tiles), zs_base = zp_base + B_BYTES;
+                if (i != p.kb_z) tc::umma_commit(&empty[s]);
+            }
+        }
+        __syncwarp();
+        tc::tmem_alloc(tmem_slot + 1, Z_COLS);  // whole warp; blocks while two other CTAs own their full sets
+        tc::fence_before_sync();
+        __syncwarp();
+        tc::fence_after_sync();
+        tmem_z = *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1);
+        if (lane == 0) {
+            tc::mbar_arrive(tmem_ready);  // release: the epilogue warps read the slots after acquiring this barrier
+            tc::mbar_wait(z_full, 0);
+            tc::fence_after_sync();
+            const uint32_t a_base = tc::smem_u32(tiles + s_z * STAGE_BYTES);
+            const uint32_t zp_base = tc::smem_u32(z_tiles), zs_base = zp_base + B_BYTES;
 #pragma unroll
-                    for (int kk = 0; kk < BK / 16; ++kk) {
-                        tc::umma_bf16(tmem_base + BN, tc::smem_desc(a_base + kk * 32, 16, 1024),
-                                      tc::smem_desc(zp_base + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
-                        tc::umma_bf16(tmem_base + 2 * BN, tc::smem_desc(a_base + kk * 32, 16, 1024),
-                                      tc::smem_desc(zs_base + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
-                    }
-                }
-                tc::umma_commit(&empty[s]);
+            for (int kk = 0; kk < BK / 16; ++kk) {
+                tc::umma_bf16(tmem_z, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zp_base + kk * 32, 16, 1024), idesc,
+                              kk > 0 ? 1u : 0u);
+                tc::umma_bf16(tmem_z + BN, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zs_base + kk * 32, 16, 1024),
+                              idesc, kk > 0 ? 1u : 0u);
             }
             tc::umma_commit(tmem_full);
         }
+        __syncwarp();
     } else {
         // ================= epilogue: 8 warps =================
         const int et = threadIdx.x - 64;
@@ -201,6 +213,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
         const long xrow = (long)my_row * p.ldx;
         tc::mbar_wait(tmem_ready, 0);
         tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+        tmem_z = *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1);
         tc::mbar_wait(tmem_full, 0);  // accumulators complete; the operand stages are free from here on
         tc::fence_after_sync();
         if (SRC == SPV_SRC_U16_LOG1P) {
@@ -209,14 +222,14 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
         }
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
         const bool vec_b = ((p.ld_dpi & 3) == 0) && ((p.Gp & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dpi) & 7) == 0);
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16), lane_z = tmem_z + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
         for (int j4 = 0; j4 < WCOLS; j4 += 4) {
             const int c0 = half * WCOLS + j4;
             uint32_t rpi[4], rlp[4], rls[4];
             tc::tmem_ld4(lane_addr + (uint32_t)c0, rpi);
-            tc::tmem_ld4(lane_addr + (uint32_t)(BN + c0), rlp);
-            tc::tmem_ld4(lane_addr + (uint32_t)(2 * BN + c0), rls);
+            tc::tmem_ld4(lane_z + (uint32_t)c0, rlp);
+            tc::tmem_ld4(lane_z + (uint32_t)(BN + c0), rls);
             tc::tmem_ld_wait();
             float vyp[4], vys[4], vpi[4], vth[4];
 #pragma unroll
@@ -308,7 +321,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
     __syncthreads();
     if (warp == 1) {
         tc::fence_after_sync();
-        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+        tc::tmem_dealloc(tmem_z, Z_COLS);
+        tc::tmem_dealloc(tmem_base, ACC_COLS);
     }
 }
 
