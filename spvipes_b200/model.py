@@ -244,10 +244,16 @@ class spVIPES:
                                   normalized: bool = False, give_mean: bool = True, mc_samples: int = 5000,
                                   batch_size: Optional[int] = None, drop_last: Optional[bool] = None) -> dict:
         """reference model/spvipes.py:424-650: sequential minibatches, the shorter group cycled (zip(largest, cycle(other))),
-        module in eval mode; returns the SAMPLED log_z of the PoE / private posteriors (softmax-normalised Monte-Carlo mean of
-        the private posterior when normalized=True), truncated to the group sizes and re-ordered by within-group index."""
+        module in eval mode; returns the SAMPLED log_z of the PoE / private posteriors, truncated to the group sizes and
+        re-ordered by within-group index.
+
+        normalized=True cannot complete in the reference either: _process_batches appends nothing to the shared lists in that
+        branch (spvipes.py:542-544, 552) and _format_results then calls torch.cat on the empty lists (:634-635), which raises
+        RuntimeError; with give_mean=False it fails earlier on an unbound local (:556-563).  The same error type is raised here
+        instead of inventing a result the reference never produced."""
         if normalized:
-            raise NotImplementedError("normalized=True (Monte-Carlo softmax means) is not implemented yet")
+            raise RuntimeError("normalized=True: the reference collects no shared latents in this branch and fails in "
+                               "torch.cat on an empty list (model/spvipes.py:542-544, 634); use normalized=False")
         self._to_device()
         eng = self.module.engine
         batch_size = batch_size or 128

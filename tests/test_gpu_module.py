@@ -87,5 +87,7 @@ def test_model_api_train_and_latent():
     assert lat["shared"][0].shape == (n[0], 12) and lat["shared"][1].shape == (n[1], 12)
     assert lat["private"][0].shape == (n[0], 6) and lat["private_reordered"][1].shape == (n[1], 6)
     assert np.isfinite(lat["shared"][0]).all() and np.isfinite(lat["private"][1]).all()
+    with pytest.raises(RuntimeError):  # as the reference: torch.cat of the empty shared list (model/spvipes.py:542-544, 634)
+        model.get_latent_representation(gil, batch_size=256, normalized=True)
     load = model.get_loadings()
     assert load[(0, "shared")].shape == (G[0], 12) and load[(1, "private")].shape == (G[1], 6)
