@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
 // ---------------------------------------------------------------------------------------
 constexpr int ST_SMEM = A_BYTES + 2 * B_BYTES + 1024 + 2 * BN * 4 + 64;
 
-__global__ void __launch_bounds__(THREADS, 2) nb_tc_stats_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(THREADS, 3) nb_tc_stats_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                  const __grid_constant__ CUtensorMap mapZ, const float* __restrict__ genec,
                                                                  float* __restrict__ part_stats, int B, int G, int kb_z, int Gp) {
     extern __shared__ uint8_t smem_raw[];

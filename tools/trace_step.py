@@ -73,8 +73,8 @@ def main():
     for e in g:
         s = e["args"].get("stream", 0)
         sid = streams.setdefault(s, len(streams))
-        n = re.sub(r"\(.*", "", e["name"])
-        n = re.sub(r"^void ", "", n).replace("(anonymous namespace)::", "")
+        n = e["name"].replace("(anonymous namespace)::", "")
+        n = re.sub(r"^void ", "", re.sub(r"\(.*", "", n))
         st, du = e["ts"] - t0, e["dur"]
         if st > busy_end:
             idle += st - busy_end
