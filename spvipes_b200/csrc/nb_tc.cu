@@ -57,6 +57,9 @@ __device__ __forceinline__ int cnt_row(int e, int lane, int i) {
     return (e + EPI_WARPS * i) * GATHER_ROWS + lane / (BN / 2);
 }
 
+// CTAs of this kernel currently resident per SM (a scheduling hint only, see the allocation below; balanced by every CTA)
+__device__ int g_resident_fwd[256];
+
 template <int SRC>
 __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                const __grid_constant__ CUtensorMap mapB,
@@ -128,7 +131,16 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
         // their full 3 x BN, so this CTA streams all its k-blocks through the stages and finishes that accumulator while it
         // is still waiting for tensor memory; only the 8 MMAs of the two branch logits (one k-block against the resident
         // folded-weight tiles) are left once the second allocation is granted.  One thread issues every MMA and commit.
+        // A CTA that has allocated without giving up its permit keeps the SM from launching further CTAs (measured: the second
+        // and third CTA of an SM entered 5 and 9.5 us after the first), so the two-step path is only taken by a CTA that finds
+        // two others resident - the SM is full then anyway; the first two allocate everything at once.
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        int ahead = 0;
+        if (lane == 0) ahead = atomicAdd(&g_resident_fwd[smid & 255], 1);
+        const bool at_once = __shfl_sync(0xffffffffu, ahead, 0) < 2;
         tc::tmem_alloc_keep_permit(tmem_slot, ACC_COLS);
+        if (at_once) tc::tmem_alloc(tmem_slot + 1, Z_COLS);
         tc::fence_before_sync();
         __syncwarp();
         tc::fence_after_sync();
@@ -151,10 +163,12 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
             }
         }
         __syncwarp();
-        tc::tmem_alloc(tmem_slot + 1, Z_COLS);  // whole warp; blocks while two other CTAs own their full sets
-        tc::fence_before_sync();
-        __syncwarp();
-        tc::fence_after_sync();
+        if (!at_once) {
+            tc::tmem_alloc(tmem_slot + 1, Z_COLS);  // whole warp; blocks while two other CTAs own their full sets
+            tc::fence_before_sync();
+            __syncwarp();
+            tc::fence_after_sync();
+        }
         tmem_z = *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1);
         if (lane == 0) {
             stamp(6);  // tensor memory granted
@@ -311,6 +325,9 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
         tc::fence_after_sync();
         tc::tmem_dealloc(tmem_z, Z_COLS);
         tc::tmem_dealloc(tmem_base, ACC_COLS);
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (lane == 0) atomicSub(&g_resident_fwd[smid & 255], 1);
     }
 }
 
@@ -489,6 +506,12 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
     p.B = B; p.G = G; p.K = K; p.kb_z = HD / BK;
     if (p.kb_z != (K + BK - 1) / BK - 1) return SPV_ERR_ARG;  // the latent columns must be the last k-block (P + S <= 64)
     p.trace = spv_debug_get_trace();
+#ifdef NB_TRACE
+    {  // consecutive launches (the two groups of a step) stamp alternate halves of the buffer
+        static int n_launch = 0;
+        if (p.trace) p.trace += (long)(n_launch++ & 1) * 8 * ((G + BN - 1) / BN) * ((B + BM - 1) / BM);
+    }
+#endif
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(nb_tc_fwd_kernel<SPV_SRC_U16_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||

@@ -42,6 +42,9 @@ __device__ __forceinline__ int cnt_row(int e, int lane, int i) {
     return (e + EPI_WARPS * i) * GATHER_ROWS + lane / (BN / 2);
 }
 
+// CTAs of this kernel currently resident per SM (a scheduling hint only, see the allocation below; balanced by every CTA)
+__device__ int g_resident_bwd[256];
+
 template <int SRC>
 __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                const __grid_constant__ CUtensorMap mapB,
@@ -102,7 +105,16 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
     } else if (warp == 1) {
         // two-step allocation as in nb_tc_fwd_kernel: the mixture-logit accumulator is completed while the CTA still waits
         // for the 2 BN columns of the branch logits; one thread issues every MMA and commit
+        // A CTA that has allocated without giving up its permit keeps the SM from launching further CTAs (measured: the second
+        // and third CTA of an SM entered 5 and 9.5 us after the first), so the two-step path is only taken by a CTA that finds
+        // two others resident - the SM is full then anyway; the first two allocate everything at once.
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        int ahead = 0;
+        if (lane == 0) ahead = atomicAdd(&g_resident_bwd[smid & 255], 1);
+        const bool at_once = __shfl_sync(0xffffffffu, ahead, 0) < 2;
         tc::tmem_alloc_keep_permit(tmem_slot, ACC_COLS);
+        if (at_once) tc::tmem_alloc(tmem_slot + 1, Z_COLS);
         tc::fence_before_sync();
         __syncwarp();
         tc::fence_after_sync();
@@ -125,10 +137,12 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
             }
         }
         __syncwarp();
-        tc::tmem_alloc(tmem_slot + 1, Z_COLS);  // whole warp; blocks while two other CTAs own their full sets
-        tc::fence_before_sync();
-        __syncwarp();
-        tc::fence_after_sync();
+        if (!at_once) {
+            tc::tmem_alloc(tmem_slot + 1, Z_COLS);  // whole warp; blocks while two other CTAs own their full sets
+            tc::fence_before_sync();
+            __syncwarp();
+            tc::fence_after_sync();
+        }
         tmem_z = *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1);
         if (lane == 0) {
             tc::mbar_arrive(tmem_ready);  // release: the epilogue warps read the slots after acquiring this barrier
@@ -323,6 +337,9 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
         tc::fence_after_sync();
         tc::tmem_dealloc(tmem_z, Z_COLS);
         tc::tmem_dealloc(tmem_base, ACC_COLS);
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (lane == 0) atomicSub(&g_resident_bwd[smid & 255], 1);
     }
 }
 
