@@ -311,13 +311,13 @@ def run_ours(args):
     peak, peak_src = peaks()
     achieved = alg_bytes / (nb_ms * 1e-3) / 1e9
     # dram__bytes_read + write per launch from the committed ncu --set full capture of this workload (profiles/r1_nb_final_ncu.md)
-    traffic = 11.04e6 if (workload == "C2" and args.precision == "bf16") else None
+    traffic = 11.05e6 if (workload == "C2" and args.precision == "bf16") else None
     roofline = {"kernel": kname, "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": nb_ms,
-                "note": "instruction-issue bound, not HBM bound: ~126 instructions per (cell, gene) element at 1.5-1.9 issue cycles "
-                        "each (tools/ubench/pipes.cu, profiles/r1_nb_persistent_notes.md); the HBM fraction is reported as the "
-                        "contract asks"}
+                "note": "instruction-issue bound, not HBM bound: 132 warp instructions per 32 (cell, gene) elements, 16 of them MUFU "
+                        "at 8 issue cycles each (tools/ubench/pipes.cu, profiles/r1_nb_persistent_notes.md, "
+                        "profiles/r1_nb_final_ncu.md); the HBM fraction is reported as the contract asks"}
     # ---- the step's HBM-bound kernel for comparison: Adam over the whole flat parameter vector (28 bytes per parameter),
     #      timed alone with CUDA events (lr = 0: the parameters stay put, the traffic is the same)
     ad_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(8)]
