@@ -54,53 +54,6 @@ __device__ __forceinline__ float half_warp_max(float v) {
     return v;
 }
 
-// ---------------------------------------------------------------------------------------
-// Gather several small global arrays into ONE contiguous shared-memory block, with all global loads of a thread in flight
-// before its first store: one memory round trip per U * blockDim elements instead of one per array (or, in a
-// load-use-load chain, one per access).  The small per-gene / per-column kernels of the step are bound by exactly that
-// chain of dependent round trips (~0.5-1 us each on B200), not by bandwidth or arithmetic.
-// ---------------------------------------------------------------------------------------
-template <int NSEG>
-struct SegList {
-    const float* src[NSEG];
-    int len[NSEG];
-    int start[NSEG];
-    int total;
-    __device__ __forceinline__ void finalize() {
-        int s = 0;
-#pragma unroll
-        for (int i = 0; i < NSEG; ++i) {
-            if (len[i] < 0 || src[i] == nullptr) len[i] = 0;
-            start[i] = s;
-            s += len[i];
-        }
-        total = s;
-    }
-};
-
-template <int NSEG, int U>
-__device__ __forceinline__ void stage_segments(float* dst, const SegList<NSEG>& sl) {
-    for (int base = 0; base < sl.total; base += U * (int)blockDim.x) {
-        float v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int idx = base + u * (int)blockDim.x + (int)threadIdx.x;
-            const float* ptr = nullptr;
-#pragma unroll
-            for (int s = 0; s < NSEG; ++s) {
-                const int o = idx - sl.start[s];
-                if (o >= 0 && o < sl.len[s]) ptr = sl.src[s] + o;
-            }
-            v[u] = ptr ? __ldg(ptr) : 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int idx = base + u * (int)blockDim.x + (int)threadIdx.x;
-            if (idx < sl.total) dst[idx] = v[u];
-        }
-    }
-}
-
 // First round (U elements per thread) of copying a small global array to shared memory, split into load() and store() so
 // that the loads of several arrays are in flight before the first store; rest() copies what is beyond U * blockDim.
 template <int U>
