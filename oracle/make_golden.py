@@ -21,6 +21,9 @@ from oracle import ref_harness as rh  # noqa: E402
 from oracle import restatement as rs  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+# fixtures of SURVEY.md section 8(f) rows the CUDA path does not cover yet: kept out of tests/golden/, whose files the GPU
+# parity tests enumerate
+OUT_NEXT = os.path.join(os.path.dirname(HERE), "tests", "golden_next")
 
 CASES = {
     # name: (mode, B, (G0, G1), H, S, P, n_labels, dropout, N_per_group, training)
@@ -32,6 +35,13 @@ CASES = {
     "label_medium": ("label", 96, (300, 350), 64, 25, 10, 10, 0.1, 400, True),
     "label_eval": ("label", 24, (50, 60), 32, 25, 10, 4, 0.1, 40, False),
     "cluster_eval": ("cluster", 24, (50, 60), 32, 25, 10, 4, 0.1, 40, False),
+}
+
+
+# batch covariates (n_batch > 1): name -> (spec as in CASES, n_batch)
+CASES_NEXT = {
+    "label_batch3_tiny": (("label", 24, (50, 60), 32, 25, 10, 4, 0.1, 40, True), 3),
+    "paired_batch2_eval": (("paired", 24, (50, 60), 32, 25, 10, 4, 0.1, 40, False), 2),
 }
 
 
@@ -53,11 +63,16 @@ def synth(case_seed, mode, B, G, H, S, P, nl, drop, N):
     return x_own, idx, labels, plan, eps_p, eps_q, masks
 
 
-def make(name, spec, seed):
+def make(name, spec, seed, n_batch=0, out_dir=None):
     mode, B, G, H, S, P, nl, drop, N, training = spec
     x_own, idx, labels, plan, eps_p, eps_q, masks = synth(seed, mode, B, G, H, S, P, nl, drop, N)
     xfull = [torch.cat([x_own[0], torch.zeros(B, G[1])], 1), torch.cat([torch.zeros(B, G[0]), x_own[1]], 1)]
-    m = rh.build_reference(G, mode=mode, n_hidden=H, n_shared=S, n_private=P, dropout_rate=drop, plan=plan, n_labels=nl, seed=seed)
+    bcodes = None
+    if n_batch > 1:
+        gb = torch.Generator().manual_seed(seed + 5000)
+        bcodes = [torch.randint(0, n_batch, (B,), generator=gb).numpy().astype(np.int64) for _ in (0, 1)]
+    m = rh.build_reference(G, mode=mode, n_hidden=H, n_shared=S, n_private=P, dropout_rate=drop, plan=plan, n_labels=nl, seed=seed,
+                           n_batch=n_batch)
     g = torch.Generator().manual_seed(seed + 1000)
     with torch.no_grad():  # move BN affine / running stats off their defaults so that they matter
         for k, p in m.named_parameters():
@@ -71,16 +86,19 @@ def make(name, spec, seed):
     sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
     keep = 1.0 - drop
     dm = {k: v.float() / keep for k, v in masks.items()}
-    batch = rh.make_batch(xfull, idx, labels=labels if mode == "label" else None, clabels=labels if mode == "cluster" else None)
+    batch = rh.make_batch(xfull, idx, labels=labels if mode == "label" else None, clabels=labels if mode == "cluster" else None,
+                          batch=bcodes)
     kl_w = 0.37
     ref = rh.run_reference(m, batch, eps_private=eps_p, eps_poe=eps_q, drop_masks=dm if drop > 0 else None,
                            kl_weight=kl_w, training=training, backward=training)
     blob = {
         "meta_mode": np.array(mode), "meta_dims": np.array([B, G[0], G[1], H, S, P, nl, N], dtype=np.int64),
         "meta_dropout": np.array(drop), "meta_kl_weight": np.array(kl_w), "meta_training": np.array(training),
-        "plan": plan.numpy(),
+        "plan": plan.numpy(), "meta_n_batch": np.array(n_batch, dtype=np.int64),
     }
     for gi in (0, 1):
+        if bcodes is not None:
+            blob[f"batch{gi}"] = bcodes[gi]
         blob[f"x{gi}"] = x_own[gi].numpy().astype(np.uint16)
         blob[f"idx{gi}"] = idx[gi]
         blob[f"labels{gi}"] = labels[gi]
@@ -108,12 +126,16 @@ def make(name, spec, seed):
     for k, v in ref["state_after"].items():
         if "running" in k:
             blob["after/" + k] = v.numpy()
-    os.makedirs(OUT, exist_ok=True)
-    path = os.path.join(OUT, name + ".npz")
+    out_dir = out_dir or OUT
+    os.makedirs(out_dir, exist_ok=True)
+    path = os.path.join(out_dir, name + ".npz")
     np.savez_compressed(path, **blob)
     print(f"{name}: loss={float(ref['loss']):.6f}  {os.path.getsize(path) / 1024:.0f} KiB")
 
 
 if __name__ == "__main__":
-    for i, (name, spec) in enumerate(CASES.items()):
-        make(name, spec, 100 + i)
+    if "--next-only" not in sys.argv:
+        for i, (name, spec) in enumerate(CASES.items()):
+            make(name, spec, 100 + i)
+    for i, (name, (spec, nb)) in enumerate(CASES_NEXT.items()):
+        make(name, spec, 300 + i, n_batch=nb, out_dir=OUT_NEXT)

@@ -21,7 +21,7 @@ from torch.distributions import Normal
 from . import ref_loader
 
 
-def make_batch(x_full: Sequence[torch.Tensor], indices, labels=None, clabels=None):
+def make_batch(x_full: Sequence[torch.Tensor], indices, labels=None, clabels=None, batch=None):
     """tuple-of-dicts minibatch in the layout scvi 0.20's AnnTorchDataset yields (all f32,
     [B,1] code columns) — reference module/spVIPESmodule.py:381-405."""
     out = []
@@ -29,7 +29,7 @@ def make_batch(x_full: Sequence[torch.Tensor], indices, labels=None, clabels=Non
         B = x_full[g].shape[0]
         d = {
             "X": x_full[g].float(),
-            "batch": torch.zeros(B, 1),
+            "batch": torch.zeros(B, 1) if batch is None else torch.as_tensor(np.asarray(batch[g]).reshape(-1, 1), dtype=torch.float32),
             "groups": torch.full((B, 1), float(g)),
             "indices": torch.as_tensor(np.asarray(indices[g]).reshape(-1, 1), dtype=torch.float32),
         }
@@ -41,7 +41,7 @@ def make_batch(x_full: Sequence[torch.Tensor], indices, labels=None, clabels=Non
     return tuple(out)
 
 
-def build_reference(genes, *, mode, n_hidden, n_shared, n_private, dropout_rate, plan=None, n_labels=None, seed=0):
+def build_reference(genes, *, mode, n_hidden, n_shared, n_private, dropout_rate, plan=None, n_labels=None, seed=0, n_batch=0):
     cls, _ = ref_loader.load()
     G0, G1 = genes
     torch.manual_seed(seed)
@@ -55,7 +55,7 @@ def build_reference(genes, *, mode, n_hidden, n_shared, n_private, dropout_rate,
         pair_data=(mode == "paired"),
         use_labels=(mode == "label"),
         n_labels=n_labels,
-        n_batch=0,
+        n_batch=n_batch,
         n_hidden=n_hidden,
         n_dimensions_shared=n_shared,
         n_dimensions_private=n_private,

@@ -235,9 +235,24 @@ def poe_cluster(loc, lv, scale, sub, clabels):
 # ----------------------------------------------------------------------------------------
 # the step
 # ----------------------------------------------------------------------------------------
-def encoder(sd, prefix, xl, training, drop_mask, new_stats):
-    """reference Encoder.forward nn/networks.py:119-125 (no covariates: n_batch <= 1)."""
-    h = F.relu(F.linear(xl, sd[prefix + ".fc1.weight"], sd[prefix + ".fc1.bias"]))
+def one_hot_batch(batch_index, n_batch: int, dtype):
+    """reference nn/utils.py:9-13 (`one_hot`): [B] or [B, 1] batch codes -> [B, n_batch]; None when the covariate is not
+    injected (n_batch <= 1: nn/networks.py:60-62 and scvi FCLayers zero the category count)."""
+    if n_batch <= 1 or batch_index is None:
+        return None
+    idx = torch.as_tensor(np.asarray(batch_index) if not torch.is_tensor(batch_index) else batch_index).reshape(-1, 1).long()
+    oh = torch.zeros(idx.shape[0], n_batch, dtype=dtype)
+    oh.scatter_(1, idx, 1)
+    return oh
+
+
+def _with_cov(x, cov):
+    return x if cov is None else torch.cat((x, cov), dim=-1)
+
+
+def encoder(sd, prefix, xl, training, drop_mask, new_stats, cov=None):
+    """reference Encoder.forward nn/networks.py:110-125; `cov` = one-hot batch covariate appended to the fc1 input (:110-118)."""
+    h = F.relu(F.linear(_with_cov(xl, cov), sd[prefix + ".fc1.weight"], sd[prefix + ".fc1.bias"]))
     h = F.relu(F.linear(h, sd[prefix + ".fc2.weight"], sd[prefix + ".fc2.bias"]))
     if training and drop_mask is not None:
         h = h * drop_mask  # mask already holds 0 or 1/(1-p)
@@ -251,13 +266,14 @@ def encoder(sd, prefix, xl, training, drop_mask, new_stats):
     return loc, lv, torch.exp(0.5 * lv)
 
 
-def decoder(sd, g, z_private, z_shared, library, training, new_stats):
-    """reference LinearDecoderSPVIPE.forward nn/networks.py:314-325 + scvi FCLayers."""
+def decoder(sd, g, z_private, z_shared, library, training, new_stats, cov=None):
+    """reference LinearDecoderSPVIPE.forward nn/networks.py:314-325 + scvi FCLayers; `cov` = one-hot batch covariate that
+    FCLayers appends to the input of each of the four one-layer nets (n_cat_list at nn/networks.py:203, 217, 245, 256)."""
     p = f"decoder_{g}"
 
     def fc(name, x, bn, eps=DEC_BN_EPS, mom=DEC_BN_MOM):
         k = f"{p}.{name}.fc_layers.Layer 0"
-        y = F.linear(x, sd[k + ".0.weight"], sd.get(k + ".0.bias"))
+        y = F.linear(_with_cov(x, cov), sd[k + ".0.weight"], sd.get(k + ".0.bias"))
         if bn:
             y = batch_norm(y, sd[k + ".1.weight"], sd[k + ".1.bias"], sd[k + ".1.running_mean"], sd[k + ".1.running_var"],
                            training, eps, mom, new_stats, k + ".1")
@@ -274,13 +290,16 @@ def decoder(sd, g, z_private, z_shared, library, training, new_stats):
 def step(sd: Dict[str, torch.Tensor], x: Sequence[torch.Tensor], *, mode: str, n_shared: int, n_private: int,
          eps_private: Sequence[torch.Tensor], eps_poe: Sequence[torch.Tensor],
          labels: Optional[Sequence] = None, sub: Optional[torch.Tensor] = None,
-         drop_masks: Optional[Dict] = None, kl_weight: float = 1.0, training: bool = True):
+         drop_masks: Optional[Dict] = None, kl_weight: float = 1.0, training: bool = True,
+         batch_index: Optional[Sequence] = None, n_batch: int = 0):
     """One forward pass of inference -> generative -> loss for both groups.
 
     x[g]: [B_g, G_g] counts of group g's OWN genes (any float dtype; the reference slices
     them out of the combined var axis at module/spVIPESmodule.py:428-430).
     mode: "label" | "paired" | "cluster".  labels: per-group int arrays (cell-type labels in
     label mode, processed_transport_labels in cluster mode).  sub: [B0, B1] sub-plan.
+    batch_index / n_batch: per-group batch codes and the number of batches; with n_batch > 1 their one-hot is appended to
+    the encoders' fc1 input and to the input of the four decoder nets (module/spVIPESmodule.py:133, 440-446, 748-756).
     Returns a dict of every quantity the parity gates name.
     """
     S, P = n_shared, n_private
@@ -289,10 +308,11 @@ def step(sd: Dict[str, torch.Tensor], x: Sequence[torch.Tensor], *, mode: str, n
     xl = [torch.log(1 + xs) for xs in x]  # :432-433
     lib = [torch.log(t.sum(1)).unsqueeze(1) for t in xl]  # :435 (sum of the log1p'd values)
     priv, shared = [], []
+    cov = [one_hot_batch(batch_index[g] if batch_index is not None else None, n_batch, dt) for g in (0, 1)]
     for g in (0, 1):
         dm = drop_masks or {}
-        priv.append(encoder(sd, f"encoder_{g}_private", xl[g], training, dm.get((g, "private")), new_stats))
-        shared.append(encoder(sd, f"encoder_{g}_shared", xl[g], training, dm.get((g, "shared")), new_stats))
+        priv.append(encoder(sd, f"encoder_{g}_private", xl[g], training, dm.get((g, "private")), new_stats, cov[g]))
+        shared.append(encoder(sd, f"encoder_{g}_shared", xl[g], training, dm.get((g, "shared")), new_stats, cov[g]))
     s_loc = [shared[0][0], shared[1][0]]
     s_lv = [shared[0][1], shared[1][1]]
     s_sc = [shared[0][2], shared[1][2]]
@@ -316,7 +336,7 @@ def step(sd: Dict[str, torch.Tensor], x: Sequence[torch.Tensor], *, mode: str, n
         c = torch.cat((z_priv, z_poe), dim=-1)  # :733  [private | poe]
         z_private_arg = c[:, S:S + P]  # :753  (quirk Q1)
         z_shared_arg = c[:, :S]  # :754
-        rate_p, rate_s, mix = decoder(sd, g, z_private_arg, z_shared_arg, lib[g], training, new_stats)
+        rate_p, rate_s, mix = decoder(sd, g, z_private_arg, z_shared_arg, lib[g], training, new_stats, cov[g])
         theta = torch.exp(sd[f"px_r.{g}"])
         rec = -log_mixture_nb(xl[g], rate_p, rate_s, theta, mix).sum(-1)  # :820-824 (target = log1p counts, Q3)
         klp = kl_std_normal(p_loc, p_sc)

@@ -20,15 +20,25 @@ def golden_names(training=None):
     return [n for n in names if n.endswith("_eval") != training]
 
 
+# fixtures of functionality the CUDA path does not cover yet (batch covariates): oracle-only, not enumerated by the GPU tests
+GOLDEN_NEXT_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_next")
+
+
+def golden_next_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_NEXT_DIR, "*.npz")))
+
+
 class Golden:
-    def __init__(self, name):
-        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    def __init__(self, name, directory=GOLDEN_DIR):
+        z = np.load(os.path.join(directory, name + ".npz"))
         self.name = name
         self.mode = str(z["meta_mode"])
         self.B, self.G0, self.G1, self.H, self.S, self.P, self.n_labels, self.N = (int(v) for v in z["meta_dims"])
         self.dropout = float(z["meta_dropout"])
         self.kl_weight = float(z["meta_kl_weight"])
         self.training = bool(z["meta_training"])
+        self.n_batch = int(z["meta_n_batch"]) if "meta_n_batch" in z.files else 0
+        self.batch = [z[f"batch{g}"] for g in (0, 1)] if self.n_batch > 1 else None
         self.plan = torch.from_numpy(z["plan"])
         self.x = [torch.from_numpy(z[f"x{g}"].astype(np.int32)) for g in (0, 1)]
         self.idx = [z[f"idx{g}"] for g in (0, 1)]
@@ -67,7 +77,7 @@ def run_oracle(gd: Golden, dtype=torch.float32, backward=True):
     out = rs.step(sd, [t.to(dtype) for t in gd.x], mode=gd.mode, n_shared=gd.S, n_private=gd.P,
                   eps_private=[e.to(dtype) for e in gd.eps_private], eps_poe=[e.to(dtype) for e in gd.eps_poe],
                   labels=gd.labels, sub=gd.sub(dtype), drop_masks=gd.drop_masks(dtype), kl_weight=gd.kl_weight,
-                  training=gd.training)
+                  training=gd.training, batch_index=gd.batch, n_batch=gd.n_batch)
     grads = None
     if backward and gd.training:
         out["loss"].backward()

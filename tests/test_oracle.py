@@ -7,15 +7,21 @@ import torch
 
 from oracle import ref_loader
 from oracle import restatement as rs
-from tests.helpers import Golden, golden_names, grad_errors, relerr, run_oracle
+from tests.helpers import GOLDEN_NEXT_DIR, Golden, golden_names, golden_next_names, grad_errors, relerr, run_oracle
 
 TERMS = ("rec", "kl_private", "kl_poe", "library", "private_loc", "private_logvar", "private_log_z",
          "shared_loc", "shared_logvar", "poe_loc", "poe_logvar", "poe_scale", "poe_log_z")
 
 
-@pytest.mark.parametrize("name", golden_names())
+def test_golden_next_fixtures_present():
+    assert golden_next_names() == ["label_batch3_tiny", "paired_batch2_eval"]
+
+
+@pytest.mark.parametrize("name", golden_names() + ["next:" + n for n in golden_next_names()])
 def test_oracle_matches_golden(name):
-    gd = Golden(name)
+    """every committed fixture of the unmodified reference; the `next:` ones exercise batch covariates (n_batch > 1,
+    SURVEY.md 8f rank 3), which only the oracle implements so far"""
+    gd = Golden(name[5:], GOLDEN_NEXT_DIR) if name.startswith("next:") else Golden(name)
     out, grads, _ = run_oracle(gd)
     assert relerr(out["loss"], gd.out["loss"]) < 2e-6
     for k in TERMS:
@@ -69,21 +75,24 @@ def test_adam_matches_torch():
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
-@pytest.mark.parametrize("mode", ["label", "paired", "cluster"])
-def test_oracle_matches_live_reference(mode):
+@pytest.mark.parametrize("mode,n_batch", [("label", 0), ("paired", 0), ("cluster", 0), ("label", 4), ("cluster", 2), ("paired", 1)])
+def test_oracle_matches_live_reference(mode, n_batch):
     from oracle import make_golden as mg, ref_harness as rh
     B, G, H, S, P, nl, drop, N = 40, (80, 64), 32, 25, 10, 6, 0.15, 90
     x_own, idx, labels, plan, eps_p, eps_q, masks = mg.synth(777, mode, B, G, H, S, P, nl, drop, N)
     xfull = [torch.cat([x_own[0], torch.zeros(B, G[1])], 1), torch.cat([torch.zeros(B, G[0]), x_own[1]], 1)]
-    m = rh.build_reference(G, mode=mode, n_hidden=H, n_shared=S, n_private=P, dropout_rate=drop, plan=plan, n_labels=nl, seed=3)
+    bcodes = [np.random.RandomState(5 + g).randint(0, max(n_batch, 1), B) for g in (0, 1)] if n_batch else None
+    m = rh.build_reference(G, mode=mode, n_hidden=H, n_shared=S, n_private=P, dropout_rate=drop, plan=plan, n_labels=nl, seed=3,
+                           n_batch=n_batch)
     sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
     dm = {k: v.float() / (1 - drop) for k, v in masks.items()}
-    batch = rh.make_batch(xfull, idx, labels=labels if mode == "label" else None, clabels=labels if mode == "cluster" else None)
+    batch = rh.make_batch(xfull, idx, labels=labels if mode == "label" else None, clabels=labels if mode == "cluster" else None,
+                          batch=bcodes)
     ref = rh.run_reference(m, batch, eps_private=eps_p, eps_poe=eps_q, drop_masks=dm, kl_weight=0.5)
     sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd0.items()}
     sub = rs.sub_plan(plan, idx[0], idx[1]) if mode != "label" else None
     out = rs.step(sd, x_own, mode=mode, n_shared=S, n_private=P, eps_private=eps_p, eps_poe=eps_q, labels=labels,
-                  sub=sub, drop_masks=dm, kl_weight=0.5)
+                  sub=sub, drop_masks=dm, kl_weight=0.5, batch_index=bcodes, n_batch=n_batch)
     out["loss"].backward()
     assert relerr(out["loss"], ref["loss"]) < 2e-6
     for k in TERMS:
