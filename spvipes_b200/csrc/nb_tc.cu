@@ -5,11 +5,12 @@
 //                                      (W', c: BatchNorm folded into the factor regressors by spv_dec_fold)
 //   rec_b    = - sum_g log_mixture_nb(log1p(x[b, g]); exp(lib) softmax(lp), exp(lib) softmax(ls), theta, pi)
 //
-// All three contractions run on tcgen05.mma (bf16 operands via TMA, fp32 accumulators in TMEM: columns 0-63 pi, 64-127 lp,
-// 128-191 ls).  The latent columns of the A operand all sit in k-block HD/64, so lp and ls each cost one extra MMA group on
-// that block against a zero-padded [genes, 64] copy of the folded weights.
-// One 128 (cells) x 64 (genes) tile per CTA, two CTAs per SM.  warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer,
-// warps 2..9: epilogue (thread = cell row; two warps per TMEM lane quarter, 32 gene columns each).  Once the accumulators
+// All three contractions run on tcgen05.mma (bf16 operands via TMA, fp32 accumulators in TMEM: 64 columns for pi, 2 x 64 for
+// lp | ls, allocated separately).  The latent columns of the A operand all sit in the last k-block HD/64, so lp and ls each
+// cost one extra MMA group on that block against a zero-padded [genes, 64] copy of the folded weights.
+// One 128 (cells) x 64 (genes) tile per CTA, three CTAs resident per SM of which two own a full accumulator set (the third
+// streams its operands and completes pi while it waits: see the allocation in the MMA warp).  warp 0: TMA producer, warp 1:
+// TMEM allocator + MMA issuer, warps 2..9: epilogue (thread = cell row; two warps per TMEM lane quarter, 32 gene columns each).  Once the accumulators
 // are complete the operand stages are reused for the tile's raw counts (coalesced row gather, uint16); the accumulators
 // are streamed out of TMEM four columns at a time.  Nothing of size [B, G] is written unless store_pi is set.
 // Reference: nn/networks.py:314-325, module/spVIPESmodule.py:751-759, 817-824; scvi log_mixture_nb.
