@@ -176,7 +176,8 @@ long long spv_dec_nb_part_floats(int B, int G);
 int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, int HD, float* rowc, float* rec, void* stream);
 /* tensor-core backward sweep: recomputes the three logit tiles on tcgen05 and writes D3 = [dpi | dyp | dys] (bf16
  * [B, 3 Gp], operand of the gradient GEMMs) and colsum [4, G] (column sums of dyp, dys, dpi, d loss / d theta);
- * ptrs[15] = colpart workspace [ceil(B/128), 4, G].  scale = - grad_scale / B. */
+ * ptrs[15] = colpart workspace [ceil(B/128), 4, G].  scale = - grad_scale / B.  rowc (ptrs[9], [B, 4] floats) must be
+ * 16-byte aligned (SPV_ERR_ARG otherwise): a row is read as one float4. */
 int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
                       const void* wstack_bf16, long long ld_w, int Gp, void* d3_bf16, int B, int G, int HD, int P, int S,
                       float scale, float* colsum, void* stream);
