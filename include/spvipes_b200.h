@@ -51,15 +51,16 @@ int spv_gemm(int srcA, int transA, int srcB, int transB, const void* A, long lon
  * (n' = batch * sC + n): gate_y != NULL: multiply by (gate_y[m, n'] > 0 ? (gate_mask ? gate_mask[m, n'] : gate_scale) : 0)
  * (ReLU [+ dropout] backward, nn/networks.py:119-125 reversed); drop_mask / drop_p > 0: dropout forward with an explicit
  * multiplier matrix or the Philox keep mask of spv_dropout (seed, stream id, *drop_step, index m * drop_ld + n');
- * c_bf16 != NULL: also store the result as bf16 (operand of the tensor-core weight-gradient GEMM).  The fused stages
+ * c_bf16 != NULL: also store the result as bf16 (operand of the tensor-core weight-gradient GEMM), c_bf16_lo (optional): its
+ * bf16 residual bf16(v - hi) for the split-operand GEMM.  The fused stages
  * exist in the whole-K kernel only (fp32 operands, A not transposed, no row gather, K <= 256, splits == 1); -1 otherwise. */
 int spv_gemm_fused(int srcA, int transA, int srcB, int transB, const void* A, long long lda, const int* rowsA, const void* B,
                    long long ldb, const int* rowsB, float* C, long long ldc, int M, int N, int K, int batch, long long sA,
                    long long sB, long long sC, const float* bias, long long sBias, int relu, int accumulate, int splits,
                    float* ws, const float* gate_y, long long ld_gate, const float* gate_mask, long long ld_mask,
                    float gate_scale, float drop_p, const float* drop_mask, unsigned long long drop_seed,
-                   unsigned int drop_stream, const int* drop_step, long long drop_ld, void* c_bf16, long long ld_cbf16,
-                   void* stream);
+                   unsigned int drop_stream, const int* drop_step, long long drop_ld, void* c_bf16, void* c_bf16_lo,
+                   long long ld_cbf16, void* stream);
 
 /* Middle of the two encoders of a group in one launch per direction (nn/networks.py:119-125):
  *   forward : h2 = dropout(relu(h1 W2^T + b2)) [B, 2H], r = h2 Whead^T + bhead [B, 2P + 2S]   (blocks: private | shared)
@@ -81,14 +82,23 @@ int spv_enc_mid_bwd(const float* dr, long long ld_dr, const float* Whp, const fl
  * elements, multiples of 8, bases 16-byte aligned.  Same call sites as spv_gemm, for the "bf16 tensor-core path". */
 int spv_tc_gemm(int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb, float* C, long long ldc, int M,
                 int N, int K, const float* bias, int relu, int accumulate, int splits, float* ws, void* stream);
+/* the same with split-bf16 operands x ~ hi + lo (lo = bf16(x - hi), same layout and pitch as hi): hi.hi + hi.lo + lo.hi on
+ * tcgen05 into one TMEM accumulator, ~16 mantissa bits per operand.  The K = genes contractions of the encoder's first layer
+ * (nn/networks.py:119 forward and its weight gradient): north_star's 1e-3 gate on the latent statistics holds on this path. */
+int spv_tc_gemm_split(int a_mn, int b_mn, const void* A, const void* A_lo, long long lda, const void* B, const void* B_lo,
+                      long long ldb, float* C, long long ldc, int M, int N, int K, const float* bias, int relu, int accumulate,
+                      int splits, float* ws, void* stream);
 /* bf16 staging of GEMM operands: dst[r, :C] = bf16(src[r, :C]), zero padded up to ld_dst */
 int spv_to_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, int R, int C, void* stream);
+/* ... as a (hi, lo) pair for spv_tc_gemm_split */
+int spv_to_bf16_split(const float* src, long long ld_src, void* dst_hi, void* dst_lo, long long ld_dst, int R, int C, void* stream);
 /* column block: dst[r, :C] = bf16(src[r, :C]), zeros up to `width`; the other columns of dst (row pitch ld_dst) are untouched */
 int spv_to_bf16_block(const float* src, long long ld_src, void* dst, long long ld_dst, int R, int C, int width, void* stream);
 /* T[b, :G] = bf16(log1p(X[rows[b], :G])), zero padded to ld_dst (a multiple of 8)   module/spVIPESmodule.py:428-433;
+ * dst_lo (optional): the bf16 residual plane for spv_tc_gemm_split;
  * lib (optional, [B]): library size log(sum_g log1p(x[b,g])) from the same pass   module/spVIPESmodule.py:433-435 */
-int spv_counts_to_bf16(int src, const void* X, long long ldx, const int* rows, void* dst, long long ld_dst, int B, int G,
-                       float* lib, void* stream);
+int spv_counts_to_bf16(int src, const void* X, long long ldx, const int* rows, void* dst, void* dst_lo, long long ld_dst, int B,
+                       int G, float* lib, void* stream);
 
 /* lib[b] = log(sum_g log1p(x[b,g]))   module/spVIPESmodule.py:433-435 */
 int spv_library_size(int src, const void* X, long long ldx, const int* rows, int B, int G, float* lib, void* stream);
@@ -193,17 +203,21 @@ int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw
                         int nparts, const float* zz, long long ld_zz, const float* zmean, float* dzz, int B, int P, int S,
                         void* stream);
 
+/* *step += 1 on the stream: the optimiser's step count, and (a separate counter) the Philox stream position that the noise /
+ * dropout kernels read - the two must not share a counter, the backward regenerates its noise from the forward's value. */
 /* Adam with the scvi TrainingPlan defaults restated by the caller (training_mixin.py:93-111); *step is a device counter of
  * completed optimiser steps.  ticket == NULL: *step already holds this step's 1-based index (spv_adam_tick first);
  * ticket != NULL (zeroed device int): the launch uses *step + 1 and its last CTA stores it back.
  * nseg (<= 8) staging segments, host arrays: the parameter block [seg_begin, seg_begin + seg_rows * seg_cols) viewed as
  * [seg_rows, seg_cols] is also written, updated, as bf16 into seg_dst (row pitch seg_ld): the tensor-core operand copies of
- * the large weights, so that the next step does not start with conversion kernels.  p, g, m, v 16-byte aligned.
+ * the large weights, so that the next step does not start with conversion kernels; seg_dst_lo (optional array, entries may
+ * be NULL): the bf16 residual plane of a segment (split-operand GEMM), same pitch.  p, g, m, v 16-byte aligned.
  * max_blocks > 0 caps the grid (an update overlapped with other kernels should not occupy every SM). */
 int spv_adam_tick(int* step, void* stream);
 int spv_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
              float grad_scale, int* step, int* ticket, int nseg, const long long* seg_begin, const int* seg_rows,
-             const int* seg_cols, void* const* seg_dst, const long long* seg_ld, int max_blocks, void* stream);
+             const int* seg_cols, void* const* seg_dst, void* const* seg_dst_lo, const long long* seg_ld, int max_blocks,
+             void* stream);
 
 #ifdef __cplusplus
 }

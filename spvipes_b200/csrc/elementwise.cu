@@ -325,6 +325,7 @@ extern "C" int spv_adam_tick(int* step, void* stream) {
 struct AdamSegs {
     long long begin[ADAM_MAX_SEGS], end[ADAM_MAX_SEGS], ld[ADAM_MAX_SEGS];
     __nv_bfloat16* dst[ADAM_MAX_SEGS];
+    __nv_bfloat16* dst_lo[ADAM_MAX_SEGS];  // optional bf16 residual plane (split-operand GEMMs), same pitch
     int cols[ADAM_MAX_SEGS];
     float inv_cols[ADAM_MAX_SEGS];
     int n;
@@ -340,7 +341,9 @@ __device__ __forceinline__ void adam_stage(const AdamSegs& sg, long long idx, fl
             int c = j - r * cols;
             if (c < 0) { --r; c += cols; }
             else if (c >= cols) { ++r; c -= cols; }
-            sg.dst[s][(long long)r * sg.ld[s] + c] = __float2bfloat16(val);
+            const __nv_bfloat16 hi = __float2bfloat16(val);
+            sg.dst[s][(long long)r * sg.ld[s] + c] = hi;
+            if (sg.dst_lo[s]) sg.dst_lo[s][(long long)r * sg.ld[s] + c] = __float2bfloat16(val - __bfloat162float(hi));
             return;
         }
     }
@@ -407,8 +410,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 // [seg_rows, seg_cols] is mirrored as bf16 into seg_dst with row pitch seg_ld.
 extern "C" int spv_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                         float wd, float grad_scale, int* step, int* ticket, int nseg, const long long* seg_begin,
-                        const int* seg_rows, const int* seg_cols, void* const* seg_dst, const long long* seg_ld, int max_blocks,
-                        void* stream) {
+                        const int* seg_rows, const int* seg_cols, void* const* seg_dst, void* const* seg_dst_lo,
+                        const long long* seg_ld, int max_blocks, void* stream) {
     if (!p || !g || !m || !v || !step || n <= 0 || nseg < 0 || nseg > ADAM_MAX_SEGS) return SPV_ERR_ARG;
     if (nseg > 0 && (!seg_begin || !seg_rows || !seg_cols || !seg_dst || !seg_ld)) return SPV_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -424,6 +427,7 @@ extern "C" int spv_adam(float* p, const float* g, float* m, float* v, long long 
         sg.end[s] = seg_begin[s] + (long long)seg_rows[s] * seg_cols[s];
         sg.ld[s] = seg_ld[s];
         sg.dst[s] = reinterpret_cast<__nv_bfloat16*>(seg_dst[s]);
+        sg.dst_lo[s] = seg_dst_lo ? reinterpret_cast<__nv_bfloat16*>(seg_dst_lo[s]) : nullptr;
         sg.cols[s] = seg_cols[s];
         sg.inv_cols[s] = 1.0f / (float)seg_cols[s];
     }

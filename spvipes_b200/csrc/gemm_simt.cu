@@ -26,6 +26,7 @@ struct GemmParams {
     const int* drop_step;
     long drop_ld;
     __nv_bfloat16* c_bf16;   // also store the result as bf16 at c_bf16[m * ld_cbf16 + n']
+    __nv_bfloat16* c_bf16_lo;  // and (optional) its bf16 residual, same layout (split-operand tensor-core GEMM)
     long ld_cbf16;
 };
 
@@ -236,7 +237,11 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_smallk_kernel(GemmParams p) {
             v = philox_uniform(p.drop_seed, p.drop_stream, stp, (unsigned long long)((size_t)m * p.drop_ld + nn)) <= keep ? v * (1.0f / keep) : 0.0f;
         }
         *c = v;
-        if (p.c_bf16) p.c_bf16[(size_t)m * p.ld_cbf16 + nn] = __float2bfloat16(v);
+        if (p.c_bf16) {
+            const __nv_bfloat16 hi = __float2bfloat16(v);
+            p.c_bf16[(size_t)m * p.ld_cbf16 + nn] = hi;
+            if (p.c_bf16_lo) p.c_bf16_lo[(size_t)m * p.ld_cbf16 + nn] = __float2bfloat16(v - __bfloat162float(hi));
+        }
     }
 }
 
@@ -275,7 +280,7 @@ extern "C" int spv_gemm(int srcA, int transA, int srcB, int transB, const void* 
                         int batch, long long sA, long long sB, long long sC, const float* bias, long long sBias, int relu,
                         int accumulate, int splits, float* ws, void* stream) {
     return spv_gemm_fused(srcA, transA, srcB, transB, A, lda, rowsA, B, ldb, rowsB, C, ldc, M, N, K, batch, sA, sB, sC, bias, sBias,
-                          relu, accumulate, splits, ws, nullptr, 0, nullptr, 0, 1.0f, 0.0f, nullptr, 0ull, 0u, nullptr, 0, nullptr, 0,
+                          relu, accumulate, splits, ws, nullptr, 0, nullptr, 0, 1.0f, 0.0f, nullptr, 0ull, 0u, nullptr, 0, nullptr, nullptr, 0,
                           stream);
 }
 
@@ -287,7 +292,7 @@ extern "C" int spv_gemm_fused(int srcA, int transA, int srcB, int transB, const 
                               int accumulate, int splits, float* ws, const float* gate_y, long long ld_gate,
                               const float* gate_mask, long long ld_mask, float gate_scale, float drop_p, const float* drop_mask,
                               unsigned long long drop_seed, unsigned int drop_stream, const int* drop_step, long long drop_ld,
-                              void* c_bf16, long long ld_cbf16, void* stream) {
+                              void* c_bf16, void* c_bf16_lo, long long ld_cbf16, void* stream) {
     if (M <= 0 || N <= 0 || K < 0 || batch <= 0 || !A || !B || !C) return SPV_ERR_ARG;
     if (drop_p < 0.0f || drop_p >= 1.0f) return SPV_ERR_ARG;
     if (splits < 1) splits = 1;
@@ -296,6 +301,7 @@ extern "C" int spv_gemm_fused(int srcA, int transA, int srcB, int transB, const 
     p.gate_y = gate_y; p.gate_mask = gate_mask; p.ld_gate = ld_gate; p.ld_mask = ld_mask; p.gate_scale = gate_scale;
     p.drop_p = drop_p; p.drop_mask = drop_mask; p.drop_seed = drop_seed; p.drop_stream = drop_stream; p.drop_step = drop_step;
     p.drop_ld = drop_ld; p.c_bf16 = reinterpret_cast<__nv_bfloat16*>(c_bf16); p.ld_cbf16 = ld_cbf16;
+    p.c_bf16_lo = reinterpret_cast<__nv_bfloat16*>(c_bf16_lo);
     const bool fused = gate_y || drop_mask || drop_p > 0.0f || c_bf16;
     const bool smallk_ok = srcA == SPV_SRC_F32 && srcB == SPV_SRC_F32 && !transA && !rowsA && !rowsB && splits == 1 && K > 0 && K <= SK_MAXK;
     if (fused && !smallk_ok) return SPV_ERR_ARG;

@@ -13,7 +13,6 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int STAGES = 4;
 constexpr int THREADS = 192;
 
 struct TcParams {
@@ -24,19 +23,26 @@ struct TcParams {
     int M, N, K, relu, accumulate, splits, kb_per_split;
 };
 
-template <int BN>
+// SPLIT: both operands are given as a bf16 pair (hi, lo) with x ~ hi + lo (lo = bf16(x - hi)), and the product is
+// hi.hi + hi.lo + lo.hi accumulated into the same TMEM tile: ~16 mantissa bits per operand, fp32-grade results from
+// the bf16 tensor-core path (the dropped lo.lo term is 2^-18 relative).  A stage then holds four tiles.
+template <int BN, bool SPLIT>
 struct Smem {
+    static constexpr int STAGES = SPLIT ? 3 : 4;
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                             const __grid_constant__ CUtensorMap mapB, TcParams p) {
+                                                             const __grid_constant__ CUtensorMap mapB,
+                                                             const __grid_constant__ CUtensorMap mapAlo,
+                                                             const __grid_constant__ CUtensorMap mapBlo, TcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    using S = Smem<BN>;
+    using S = Smem<BN, SPLIT>;
+    constexpr int STAGES = S::STAGES;
     const uint32_t raw = tc::smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
     uint8_t* tiles = smem_raw + pad;  // 1024-byte aligned (SWIZZLE_128B atoms)
@@ -56,6 +62,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&mapA);
         tc::tma_prefetch_desc(&mapB);
+        if (SPLIT) {
+            tc::tma_prefetch_desc(&mapAlo);
+            tc::tma_prefetch_desc(&mapBlo);
+        }
         for (int s = 0; s < STAGES; ++s) {
             tc::mbar_init(&full[s], 1);
             tc::mbar_init(&empty[s], 1);
@@ -92,6 +102,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
 #pragma unroll
                     for (int h = 0; h < BN / 64; ++h) tc::tma_load_2d(&mapB, &full[s], b_dst + h * 8192, n0 + 64 * h, k0);
                 }
+                if (SPLIT) {  // the residual planes, same boxes
+                    uint8_t* al_dst = b_dst + S::B_BYTES;
+                    uint8_t* bl_dst = al_dst + S::A_BYTES;
+                    if (!A_MN) {
+                        tc::tma_load_2d(&mapAlo, &full[s], al_dst, k0, m0);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < BM / 64; ++h) tc::tma_load_2d(&mapAlo, &full[s], al_dst + h * 8192, m0 + 64 * h, k0);
+                    }
+                    if (!B_MN) {
+                        tc::tma_load_2d(&mapBlo, &full[s], bl_dst, k0, n0);
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < BN / 64; ++h) tc::tma_load_2d(&mapBlo, &full[s], bl_dst + h * 8192, n0 + 64 * h, k0);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -112,6 +138,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
                     const uint64_t da = A_MN ? tc::smem_desc(a_base + kk * 2048, 8192, 1024) : tc::smem_desc(a_base + kk * 32, 16, 1024);
                     const uint64_t db = B_MN ? tc::smem_desc(b_base + kk * 2048, 8192, 1024) : tc::smem_desc(b_base + kk * 32, 16, 1024);
                     tc::umma_bf16(tmem_base, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                    if (SPLIT) {
+                        const uint32_t al_base = b_base + S::B_BYTES, bl_base = al_base + S::A_BYTES;
+                        const uint64_t dal = A_MN ? tc::smem_desc(al_base + kk * 2048, 8192, 1024) : tc::smem_desc(al_base + kk * 32, 16, 1024);
+                        const uint64_t dbl = B_MN ? tc::smem_desc(bl_base + kk * 2048, 8192, 1024) : tc::smem_desc(bl_base + kk * 32, 16, 1024);
+                        tc::umma_bf16(tmem_base, da, dbl, idesc, 1u);
+                        tc::umma_bf16(tmem_base, dal, db, idesc, 1u);
+                    }
                 }
                 tc::umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
             }
@@ -207,17 +240,21 @@ EncodeFn get_encode() {
     return fn;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
-    using S = Smem<BN>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
+template <int BN, bool A_MN, bool B_MN, bool SPLIT>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mal, const CUtensorMap& mbl, const TcParams& p,
+           cudaStream_t st) {
+    using S = Smem<BN, SPLIT>;
+    // the attribute is per device: set it once per device this process drives
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        if (cudaFuncSetAttribute(tc_gemm_kernel<BN, A_MN, B_MN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
             return SPV_ERR_LAUNCH;
-        configured = true;
+        configured[dev & 63] = true;
     }
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
-    tc_gemm_kernel<BN, A_MN, B_MN><<<grid, THREADS, S::TOTAL, st>>>(ma, mb, p);
+    tc_gemm_kernel<BN, A_MN, B_MN, SPLIT><<<grid, THREADS, S::TOTAL, st>>>(ma, mb, mal, mbl, p);
     SPV_CHECK_LAUNCH();
     if (p.splits > 1) {
         long total = (long)p.M * p.N;
@@ -228,12 +265,60 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cuda
     return SPV_OK;
 }
 
-template <int BN>
-int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t st) {
-    if (!a_mn && !b_mn) return launch<BN, false, false>(ma, mb, p, st);
-    if (!a_mn && b_mn) return launch<BN, false, true>(ma, mb, p, st);
-    if (a_mn && !b_mn) return launch<BN, true, false>(ma, mb, p, st);
-    return launch<BN, true, true>(ma, mb, p, st);
+template <int BN, bool SPLIT>
+int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mal, const CUtensorMap& mbl,
+                   const TcParams& p, cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch<BN, false, false, SPLIT>(ma, mb, mal, mbl, p, st);
+    if (!a_mn && b_mn) return launch<BN, false, true, SPLIT>(ma, mb, mal, mbl, p, st);
+    if (a_mn && !b_mn) return launch<BN, true, false, SPLIT>(ma, mb, mal, mbl, p, st);
+    return launch<BN, true, true, SPLIT>(ma, mb, mal, mbl, p, st);
+}
+
+int tc_gemm_impl(int a_mn, int b_mn, const void* A, const void* A_lo, long long lda, const void* B, const void* B_lo, long long ldb,
+                 float* C, long long ldc, int M, int N, int K, const float* bias, int relu, int accumulate, int splits, float* ws,
+                 void* stream) {
+    if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return SPV_ERR_ARG;
+    const bool split_ops = A_lo != nullptr;
+    if (split_ops != (B_lo != nullptr)) return SPV_ERR_ARG;
+    if (splits < 1) splits = 1;
+    const int num_kb = (K + BK - 1) / BK;
+    if (splits > num_kb) splits = num_kb;
+    int kb_per = (num_kb + splits - 1) / splits;
+    splits = (num_kb + kb_per - 1) / kb_per;
+    if (splits > 1 && !ws) return SPV_ERR_ARG;
+    const int BN = N <= 64 ? 64 : 128;
+    CUtensorMap ma, mb, mal, mbl;
+    auto map_a = [&](CUtensorMap* m, const void* base) {
+        return !a_mn ? spv_make_tensor_map_bf16(m, base, (unsigned long long)K, (unsigned long long)M, (unsigned long long)lda, 64, BM)
+                     : spv_make_tensor_map_bf16(m, base, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, 64, 64);
+    };
+    auto map_b = [&](CUtensorMap* m, const void* base) {
+        return !b_mn ? spv_make_tensor_map_bf16(m, base, (unsigned long long)K, (unsigned long long)N, (unsigned long long)ldb, 64, BN)
+                     : spv_make_tensor_map_bf16(m, base, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldb, 64, 64);
+    };
+    int rc = map_a(&ma, A);
+    if (rc != SPV_OK) return rc;
+    rc = map_b(&mb, B);
+    if (rc != SPV_OK) return rc;
+    if (split_ops) {
+        rc = map_a(&mal, A_lo);
+        if (rc != SPV_OK) return rc;
+        rc = map_b(&mbl, B_lo);
+        if (rc != SPV_OK) return rc;
+    } else {
+        mal = ma;
+        mbl = mb;
+    }
+    TcParams p;
+    p.C = C; p.bias = bias; p.ws = ws; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu; p.accumulate = accumulate;
+    p.splits = splits; p.kb_per_split = kb_per;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (split_ops) {
+        if (BN == 64) return dispatch_major<64, true>(a_mn, b_mn, ma, mb, mal, mbl, p, st);
+        return dispatch_major<128, true>(a_mn, b_mn, ma, mb, mal, mbl, p, st);
+    }
+    if (BN == 64) return dispatch_major<64, false>(a_mn, b_mn, ma, mb, mal, mbl, p, st);
+    return dispatch_major<128, false>(a_mn, b_mn, ma, mb, mal, mbl, p, st);
 }
 
 }  // namespace
@@ -259,40 +344,41 @@ int spv_make_tensor_map_bf16(CUtensorMap* map, const void* base, unsigned long l
 extern "C" int spv_tc_gemm(int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb, float* C,
                            long long ldc, int M, int N, int K, const float* bias, int relu, int accumulate, int splits,
                            float* ws, void* stream) {
-    if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return SPV_ERR_ARG;
-    if (splits < 1) splits = 1;
-    const int num_kb = (K + BK - 1) / BK;
-    if (splits > num_kb) splits = num_kb;
-    int kb_per = (num_kb + splits - 1) / splits;
-    splits = (num_kb + kb_per - 1) / kb_per;
-    if (splits > 1 && !ws) return SPV_ERR_ARG;
-    const int BN = N <= 64 ? 64 : 128;
-    CUtensorMap ma, mb;
-    int rc;
-    if (!a_mn) rc = spv_make_tensor_map_bf16(&ma, A, (unsigned long long)K, (unsigned long long)M, (unsigned long long)lda, 64, BM);
-    else rc = spv_make_tensor_map_bf16(&ma, A, (unsigned long long)M, (unsigned long long)K, (unsigned long long)lda, 64, 64);
-    if (rc != SPV_OK) return rc;
-    if (!b_mn) rc = spv_make_tensor_map_bf16(&mb, B, (unsigned long long)K, (unsigned long long)N, (unsigned long long)ldb, 64, BN);
-    else rc = spv_make_tensor_map_bf16(&mb, B, (unsigned long long)N, (unsigned long long)K, (unsigned long long)ldb, 64, 64);
-    if (rc != SPV_OK) return rc;
-    TcParams p;
-    p.C = C; p.bias = bias; p.ws = ws; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu; p.accumulate = accumulate;
-    p.splits = splits; p.kb_per_split = kb_per;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (BN == 64) return dispatch_major<64>(a_mn, b_mn, ma, mb, p, st);
-    return dispatch_major<128>(a_mn, b_mn, ma, mb, p, st);
+    return tc_gemm_impl(a_mn, b_mn, A, nullptr, lda, B, nullptr, ldb, C, ldc, M, N, K, bias, relu, accumulate, splits, ws, stream);
+}
+
+// the same with split-bf16 operands: A ~ A + A_lo, B ~ B + B_lo (same layout and pitch as their hi planes); three MMAs per
+// k-step (hi.hi + hi.lo + lo.hi) into one accumulator.  Used for the K = genes contractions of the encoder's first layer
+// (forward and weight gradient), where bf16 operand rounding alone would miss the 1e-3 gate on the latent statistics.
+extern "C" int spv_tc_gemm_split(int a_mn, int b_mn, const void* A, const void* A_lo, long long lda, const void* B, const void* B_lo,
+                                 long long ldb, float* C, long long ldc, int M, int N, int K, const float* bias, int relu,
+                                 int accumulate, int splits, float* ws, void* stream) {
+    if (!A_lo || !B_lo) return SPV_ERR_ARG;
+    return tc_gemm_impl(a_mn, b_mn, A, A_lo, lda, B, B_lo, ldb, C, ldc, M, N, K, bias, relu, accumulate, splits, ws, stream);
 }
 
 // ---------------------------------------------------------------------------------------
 // bf16 operand staging for the tensor-core path
 // ---------------------------------------------------------------------------------------
-// dst[r, c] = bf16(src[r, c]) for c < C, 0 for C <= c < ld_dst  (ld_dst = C rounded up to a multiple of 8)
-__global__ void to_bf16_kernel(const float* __restrict__ src, long ld_src, __nv_bfloat16* __restrict__ dst, long ld_dst, int R, int C) {
+// split of an fp32 value into a bf16 pair: hi = bf16(x), lo = bf16(x - hi)  (x - hi is exact in fp32)
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16(x);
+    lo = __float2bfloat16(x - __bfloat162float(hi));
+}
+
+// dst[r, c] = bf16(src[r, c]) for c < C, 0 for C <= c < ld_dst  (ld_dst = C rounded up to a multiple of 8);
+// dst_lo (optional, same shape): the bf16 residual of the split-operand GEMM
+__global__ void to_bf16_kernel(const float* __restrict__ src, long ld_src, __nv_bfloat16* __restrict__ dst,
+                               __nv_bfloat16* __restrict__ dst_lo, long ld_dst, int R, int C) {
     long total = (long)R * ld_dst;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         int c = (int)(i % ld_dst);
         long r = i / ld_dst;
-        dst[i] = __float2bfloat16(c < C ? src[r * ld_src + c] : 0.0f);
+        const float x = c < C ? src[r * ld_src + c] : 0.0f;
+        __nv_bfloat16 hi, lo;
+        split_bf16(x, hi, lo);
+        dst[i] = hi;
+        if (dst_lo) dst_lo[i] = lo;
     }
 }
 
@@ -300,7 +386,19 @@ extern "C" int spv_to_bf16(const float* src, long long ld_src, void* dst, long l
     if (!src || !dst || R <= 0 || C <= 0 || ld_dst < C) return SPV_ERR_ARG;
     long total = (long)R * ld_dst;
     int blocks = (int)min((long)148 * 16, (total + 255) / 256);
-    to_bf16_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, R, C);
+    to_bf16_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), nullptr,
+                                                                               ld_dst, R, C);
+    SPV_CHECK_LAUNCH();
+    return SPV_OK;
+}
+
+extern "C" int spv_to_bf16_split(const float* src, long long ld_src, void* dst_hi, void* dst_lo, long long ld_dst, int R, int C,
+                                 void* stream) {
+    if (!src || !dst_hi || !dst_lo || R <= 0 || C <= 0 || ld_dst < C) return SPV_ERR_ARG;
+    long total = (long)R * ld_dst;
+    int blocks = (int)min((long)148 * 16, (total + 255) / 256);
+    to_bf16_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst_hi),
+                                                                               reinterpret_cast<__nv_bfloat16*>(dst_lo), ld_dst, R, C);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }
@@ -328,22 +426,32 @@ extern "C" int spv_to_bf16_block(const float* src, long long ld_src, void* dst, 
 }
 
 // T[b, g] = bf16(log1p(X[rows[b], g]))   (the encoder's input, reference module/spVIPESmodule.py:428-433), zero padded to ld_dst,
-// and optionally library[b] = log(sum_g log1p(x[b, g]))  (reference :433-435) from the same pass over the row.
+// optionally its bf16 residual T_lo (split-operand GEMM), and optionally library[b] = log(sum_g log1p(x[b, g]))
+// (reference :433-435) from the same pass over the row.
 // One CTA per cell.  uint16 counts: 8 genes per 16-byte load when the row is 16-byte aligned, log1p of counts < 256 from a
-// shared-memory table filled with the same log1pf (bit-identical to computing it in place).
+// shared-memory table filled with the same log1pf (bit-identical to computing it in place); the table also holds the packed
+// (hi | lo << 16) bf16 pair of each entry.
 #define ENC_IN_THREADS 256
+__device__ __forceinline__ unsigned int pack_split(float f) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(f, hi, lo);
+    return (unsigned int)__bfloat16_as_ushort(hi) | ((unsigned int)__bfloat16_as_ushort(lo) << 16);
+}
 template <int SRC>
 __global__ void __launch_bounds__(ENC_IN_THREADS) counts_to_bf16_kernel(const void* __restrict__ X, long ldx, const int* __restrict__ rows,
-                                                                        __nv_bfloat16* __restrict__ dst, long ld_dst, int B, int G,
-                                                                        float* __restrict__ lib) {
+                                                                        __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst_lo,
+                                                                        long ld_dst, int B, int G, float* __restrict__ lib) {
     __shared__ float lut[256];
+    __shared__ unsigned int lutp[256];
     __shared__ float red[ENC_IN_THREADS / 32];
     const int b = blockIdx.x;
     const long r = rows ? (long)rows[b] : (long)b;
     __nv_bfloat16* out = dst + (long)b * ld_dst;
+    __nv_bfloat16* out_lo = dst_lo ? dst_lo + (long)b * ld_dst : nullptr;
     float sum = 0.0f;
     if (SRC == SPV_SRC_U16_LOG1P) {
         lut[threadIdx.x] = threadIdx.x == 0 ? 0.0f : log1pf((float)threadIdx.x);
+        lutp[threadIdx.x] = pack_split(lut[threadIdx.x]);
         __syncthreads();
         const unsigned short* row = reinterpret_cast<const unsigned short*>(X) + r * ldx;
         const bool vec = (reinterpret_cast<uintptr_t>(row) & 15) == 0;  // dst rows are 16-byte aligned (ld_dst % 8 == 0)
@@ -351,19 +459,23 @@ __global__ void __launch_bounds__(ENC_IN_THREADS) counts_to_bf16_kernel(const vo
         for (int v = threadIdx.x; v < nvec; v += ENC_IN_THREADS) {
             uint4 raw = __ldg(reinterpret_cast<const uint4*>(row) + v);
             unsigned int w[4] = {raw.x, raw.y, raw.z, raw.w};
-            uint4 o;
+            uint4 o, ol;
             unsigned int* ow = &o.x;
+            unsigned int* olw = &ol.x;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 unsigned int c0 = w[j] & 0xffffu, c1 = w[j] >> 16;
-                float f0 = c0 < 256u ? lut[c0] : log1pf((float)c0);
-                float f1 = c1 < 256u ? lut[c1] : log1pf((float)c1);
+                float f0, f1;
+                unsigned int e0, e1;
+                if (c0 < 256u) { f0 = lut[c0]; e0 = lutp[c0]; } else { f0 = log1pf((float)c0); e0 = pack_split(f0); }
+                if (c1 < 256u) { f1 = lut[c1]; e1 = lutp[c1]; } else { f1 = log1pf((float)c1); e1 = pack_split(f1); }
                 sum += f0;
                 sum += f1;
-                __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-                ow[j] = *reinterpret_cast<unsigned int*>(&h);
+                ow[j] = __byte_perm(e0, e1, 0x5410);
+                olw[j] = __byte_perm(e0, e1, 0x7632);
             }
             *(reinterpret_cast<uint4*>(out) + v) = o;
+            if (out_lo) *(reinterpret_cast<uint4*>(out_lo) + v) = ol;
         }
         for (int g = nvec * 8 + threadIdx.x; g < ld_dst; g += ENC_IN_THREADS) {
             float f = 0.0f;
@@ -372,13 +484,19 @@ __global__ void __launch_bounds__(ENC_IN_THREADS) counts_to_bf16_kernel(const vo
                 f = c < 256u ? lut[c] : log1pf((float)c);
             }
             sum += f;
-            out[g] = __float2bfloat16(f);
+            __nv_bfloat16 hi, lo;
+            split_bf16(f, hi, lo);
+            out[g] = hi;
+            if (out_lo) out_lo[g] = lo;
         }
     } else {
         for (int g = threadIdx.x; g < ld_dst; g += ENC_IN_THREADS) {
             float f = g < G ? load_src<SRC>(X, r * ldx + g) : 0.0f;
             sum += f;
-            out[g] = __float2bfloat16(f);
+            __nv_bfloat16 hi, lo;
+            split_bf16(f, hi, lo);
+            out[g] = hi;
+            if (out_lo) out_lo[g] = lo;
         }
     }
     if (!lib) return;
@@ -393,13 +511,14 @@ __global__ void __launch_bounds__(ENC_IN_THREADS) counts_to_bf16_kernel(const vo
     }
 }
 
-extern "C" int spv_counts_to_bf16(int src, const void* X, long long ldx, const int* rows, void* dst, long long ld_dst, int B, int G,
-                                  float* lib, void* stream) {
+extern "C" int spv_counts_to_bf16(int src, const void* X, long long ldx, const int* rows, void* dst, void* dst_lo, long long ld_dst,
+                                  int B, int G, float* lib, void* stream) {
     if (!X || !dst || B <= 0 || G <= 0 || ld_dst < G || (ld_dst & 7)) return SPV_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
-    if (src == SPV_SRC_U16_LOG1P) counts_to_bf16_kernel<SPV_SRC_U16_LOG1P><<<B, ENC_IN_THREADS, 0, st>>>(X, ldx, rows, d, ld_dst, B, G, lib);
-    else if (src == SPV_SRC_F32_LOG1P) counts_to_bf16_kernel<SPV_SRC_F32_LOG1P><<<B, ENC_IN_THREADS, 0, st>>>(X, ldx, rows, d, ld_dst, B, G, lib);
+    __nv_bfloat16* dl = reinterpret_cast<__nv_bfloat16*>(dst_lo);
+    if (src == SPV_SRC_U16_LOG1P) counts_to_bf16_kernel<SPV_SRC_U16_LOG1P><<<B, ENC_IN_THREADS, 0, st>>>(X, ldx, rows, d, dl, ld_dst, B, G, lib);
+    else if (src == SPV_SRC_F32_LOG1P) counts_to_bf16_kernel<SPV_SRC_F32_LOG1P><<<B, ENC_IN_THREADS, 0, st>>>(X, ldx, rows, d, dl, ld_dst, B, G, lib);
     else return SPV_ERR_ARG;
     SPV_CHECK_LAUNCH();
     return SPV_OK;

@@ -213,13 +213,15 @@ class _GroupWS:
         if bf16:
             h = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
             self.Tb, self.amixb = h(B, self.Gp), h(B, self.KMp)
+            self.Tb_lo = h(B, self.Gp)  # bf16 residual of log1p(counts): the fc1 contractions run on split operands
             # bf16 weight operands are per engine (shared by every workspace): W1b [2H, Gp] and the stacked operand
             # Wstack [3 Gp, KMp]: rows [0, G) mixture weight, [Gp, Gp+G) / [2Gp, 2Gp+G) the folded private / shared
             # factor-regressor weights of the current minibatch in the latent columns (zero elsewhere)
-            self.W1b, self.Wstack = wb
+            self.W1b, self.Wstack, self.W1b_lo = wb
             self.Wmb = self.Wstack[:G]
             if with_grad:
                 self.D3, self.dh1b = h(B, 3 * self.Gp), h(B, 2 * H)  # D3 = [dpi | dyp | dys]
+                self.dh1b_lo = h(B, 2 * H)
                 self.dpib = self.D3  # unfused path: only the first Gp columns are used (row pitch 3 Gp)
                 self.CQ = f(2 * self.Gp, KZ)
             # split-K factors of the tensor-core GEMMs (128-wide tiles): fill the 148 SMs
@@ -275,7 +277,11 @@ class StepEngine:
         self.grads = torch.zeros_like(self.params.flat)
         self.adam_m: Optional[torch.Tensor] = None
         self.adam_v: Optional[torch.Tensor] = None
-        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)   # Adam's t: only the optimiser kernels write it
+        # counter of the Philox streams (reparameterisation noise, dropout masks): advanced once at the start of every
+        # forward and left alone until the matching backward has regenerated its noise from it
+        self.noise_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._noise_events = []
         self.kl_weight = torch.ones(1, dtype=torch.float32, device=self.device)
         self.loss_out = torch.zeros(8, dtype=torch.float32, device=self.device)
         self.plan = plan
@@ -295,7 +301,8 @@ class StepEngine:
         self.wb = None
         if self.bf16:
             self.wb = [(torch.zeros(2 * self.d.n_hidden, r8(G), dtype=torch.bfloat16, device=self.device),
-                        torch.zeros(3 * r8(G), r8(self.d.KMIX), dtype=torch.bfloat16, device=self.device)) for G in self.d.genes]
+                        torch.zeros(3 * r8(G), r8(self.d.KMIX), dtype=torch.bfloat16, device=self.device),
+                        torch.zeros(2 * self.d.n_hidden, r8(G), dtype=torch.bfloat16, device=self.device)) for G in self.d.genes]
         # bf16 copies of W1 / Wm: refreshed by conversion kernels at the start of every forward, or (stage_in_adam, set by
         # the owner of the optimiser step: TrainLoop) written by the Adam kernel itself; _staged_version detects parameter
         # writes made through torch (load_state_dict, .copy_, a torch optimiser) since the last staging
@@ -319,7 +326,7 @@ class StepEngine:
 
     def _gemm(self, A, B, C, M, N, K, *, lda, ldb, ldc, ta=0, tb=0, srcA=L.SRC_F32, srcB=L.SRC_F32, rowsA=None, rowsB=None,
               batch=1, sA=0, sB=0, sC=0, bias=None, sBias=0, relu=0, acc=0, splits=1, ws=None, gate=None, drop=None, c_bf16=None):
-        """gate = (y ptr, ld, mask ptr or None, ld, scale); drop = (p, mask ptr or None, stream id, ld); c_bf16 = (ptr, ld):
+        """gate = (y ptr, ld, mask ptr or None, ld, scale); drop = (p, mask ptr or None, stream id, ld); c_bf16 = (ptr, lo ptr or None, ld):
         fused epilogue stages of spv_gemm_fused (whole-K kernel only: see self._can_fuse)"""
         if gate is None and drop is None and c_bf16 is None:
             L.check(self.lib.spv_gemm(srcA, ta, srcB, tb, A, lda, L.ptr(rowsA), B, ldb, L.ptr(rowsB), C, ldc, M, N, K, batch,
@@ -327,10 +334,10 @@ class StepEngine:
             return
         gy, gld, gm, gmld, gs = gate if gate is not None else (None, 0, None, 0, 1.0)
         dp, dm, dsid, dld = drop if drop is not None else (0.0, None, 0, 0)
-        cb, cbld = c_bf16 if c_bf16 is not None else (None, 0)
+        cb, cblo, cbld = c_bf16 if c_bf16 is not None else (None, None, 0)
         L.check(self.lib.spv_gemm_fused(srcA, ta, srcB, tb, A, lda, L.ptr(rowsA), B, ldb, L.ptr(rowsB), C, ldc, M, N, K, batch,
                                         sA, sB, sC, bias, sBias, relu, acc, splits, L.ptr(ws), gy, gld, gm, gmld, gs, dp, dm,
-                                        self.seed, dsid, L.ptr(self.step_dev), dld, cb, cbld, self._stream()), "spv_gemm_fused")
+                                        self.seed, dsid, L.ptr(self.noise_dev), dld, cb, cblo, cbld, self._stream()), "spv_gemm_fused")
 
     def _can_fuse(self, K):
         return K <= 256
@@ -338,6 +345,11 @@ class StepEngine:
     def _tc_gemm(self, A, B, C, M, N, K, *, lda, ldb, ldc, a_mn=0, b_mn=0, bias=None, relu=0, acc=0, splits=1, ws=None):
         L.check(self.lib.spv_tc_gemm(a_mn, b_mn, A, lda, B, ldb, C, ldc, M, N, K, bias, relu, acc, splits, L.ptr(ws),
                                      self._stream()), "spv_tc_gemm")
+
+    def _tc_gemm_split(self, A, Alo, B, Blo, C, M, N, K, *, lda, ldb, ldc, a_mn=0, b_mn=0, bias=None, relu=0, acc=0, splits=1, ws=None):
+        """split-bf16 operands (hi + lo planes): three MMAs per k-step, fp32-grade products (spv_tc_gemm_split)"""
+        L.check(self.lib.spv_tc_gemm_split(a_mn, b_mn, A, Alo, lda, B, Blo, ldb, C, ldc, M, N, K, bias, relu, acc, splits,
+                                           L.ptr(ws), self._stream()), "spv_tc_gemm_split")
 
     def _fork_groups(self):
         """iterate over the two groups, issuing each group's launches on its own stream (forked from the current stream and
@@ -426,14 +438,34 @@ class StepEngine:
     def forward(self, batches: Sequence[GroupBatch], training: bool = True, noise: Optional[Noise] = None,
                 with_grad: Optional[bool] = None, decode: bool = True):
         """inference -> generative -> loss.  Returns the workspaces (device tensors) holding every output."""
+        with_grad = training if with_grad is None else with_grad
+        ctx = self._encode(batches, training, noise, with_grad, stage_wm=decode)
+        if not decode:
+            for g in (0, 1):
+                self._join(g)
+            return ctx["ws"]
+        return self._decode(ctx)
+
+    def decode(self):
+        """generative + loss on the latents of the preceding forward(decode=False) (same minibatch, same noise, BatchNorm
+        running statistics of the encoders not updated a second time): reference module/spVIPESmodule.py:720-771, 809-899"""
+        if self._ctx is None:
+            raise RuntimeError("decode() follows forward(..., decode=False)")
+        return self._decode(self._ctx)
+
+    def _encode(self, batches, training, noise, with_grad, stage_wm=True):
         d, st, lib = self.d, self._stream(), self.lib
         H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
-        with_grad = training if with_grad is None else with_grad
         Bs = [b.batch_size() for b in batches]
         ws = self.workspace(Bs[0], Bs[1], with_grad)
         noise = noise or Noise()
         tr = 1 if training else 0
         srcs = []
+        decode = stage_wm
+        # new Philox counter value for this pass (off the critical path; the first consumers wait for it below)
+        with self._branch(0, "ntick", lane=1):
+            L.check(lib.spv_adam_tick(L.ptr(self.noise_dev), self._stream()), "spv_adam_tick")
+        self._noise_events = self._pending.pop((0, "ntick"), [])
         if self.mode == "label":  # integer pairing needs only the labels: off the critical path, beside the encoders
             if batches[0].labels is None or batches[1].labels is None:
                 raise ValueError("Labels are required when using label-based POE.")  # reference :401-402
@@ -450,17 +482,18 @@ class StepEngine:
             srcs.append((src, xptr, ldx))
             if convert:  # bf16 copies of the two big weights do not depend on the minibatch: off the critical path
                 with self._branch(g, "w1"):
-                    L.check(lib.spv_to_bf16(L.ptr(self.P(g, "W1")), G, L.ptr(w.W1b), w.Gp, 2 * H, G, self._stream()), "spv_to_bf16")
+                    L.check(lib.spv_to_bf16_split(L.ptr(self.P(g, "W1")), G, L.ptr(w.W1b), L.ptr(w.W1b_lo), w.Gp, 2 * H, G,
+                                                  self._stream()), "spv_to_bf16_split")
                 if decode or self.stage_in_adam:
                     with self._branch(g, "wm"):
                         L.check(lib.spv_to_bf16(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX, self._stream()),
                                 "spv_to_bf16")
             if self.bf16:  # encoder input and library size from one pass over the gathered rows
-                L.check(lib.spv_counts_to_bf16(src, xptr, ldx, L.ptr(bt.rows), L.ptr(w.Tb), w.Gp, B, G, L.ptr(w.lib), st),
-                        "spv_counts_to_bf16")
+                L.check(lib.spv_counts_to_bf16(src, xptr, ldx, L.ptr(bt.rows), L.ptr(w.Tb), L.ptr(w.Tb_lo), w.Gp, B, G,
+                                               L.ptr(w.lib), st), "spv_counts_to_bf16")
                 self._join(g, "w1")
-                self._tc_gemm(L.ptr(w.Tb), L.ptr(w.W1b), L.ptr(w.h1), B, 2 * H, G, lda=w.Gp, ldb=w.Gp, ldc=2 * H,
-                              bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.tc_splits_fc1, ws=w.ws)
+                self._tc_gemm_split(L.ptr(w.Tb), L.ptr(w.Tb_lo), L.ptr(w.W1b), L.ptr(w.W1b_lo), L.ptr(w.h1), B, 2 * H, G, lda=w.Gp,
+                                    ldb=w.Gp, ldc=2 * H, bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.tc_splits_fc1, ws=w.ws)
             else:
                 with self._branch(g, "lib"):
                     L.check(lib.spv_library_size(src, xptr, ldx, L.ptr(bt.rows), B, G, L.ptr(w.lib), self._stream()),
@@ -469,12 +502,14 @@ class StepEngine:
                            rowsA=bt.rows, bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.splits_fc1, ws=w.ws)
             mask = noise.drop[g] if (training and noise.drop is not None) else None
             dropping = training and (mask is not None or self.dropout_rate > 0)
+            for ev in self._noise_events:
+                torch.cuda.current_stream(self.device).wait_event(ev)
             bhd = self.P(g, "bhd")
             if self.enc_mid:  # fc2 -> ReLU -> dropout -> mu / logvar heads of both encoders in one launch
                 L.check(lib.spv_enc_mid_fwd(L.ptr(w.h1), 2 * H, L.ptr(self.P(g, "W2")), L.ptr(self.P(g, "b2")),
                                             L.ptr(self.P(g, "Whp")), L.ptr(self.P(g, "Whs")), L.ptr(bhd), L.ptr(w.h2), 2 * H,
                                             L.ptr(w.r), NST, L.ptr(mask), 2 * H, self.dropout_rate if dropping else 0.0,
-                                            self.seed, 8 + g, L.ptr(self.step_dev), B, H, P, S, st), "spv_enc_mid_fwd")
+                                            self.seed, 8 + g, L.ptr(self.noise_dev), B, H, P, S, st), "spv_enc_mid_fwd")
             else:
                 fuse_drop = dropping and self._can_fuse(H)  # dropout in the fc2 epilogue (same keep mask as spv_dropout)
                 self._gemm(L.ptr(w.h1), L.ptr(self.P(g, "W2")), L.ptr(w.h2), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, tb=1, batch=2,
@@ -482,7 +517,7 @@ class StepEngine:
                            drop=(0.0 if mask is not None else self.dropout_rate, L.ptr(mask), 8 + g, 2 * H) if fuse_drop else None)
                 if dropping and not fuse_drop:
                     L.check(lib.spv_dropout(L.ptr(w.h2), 2 * H, B, 2 * H, L.ptr(mask), 2 * H, self.dropout_rate, self.seed,
-                                            8 + g, L.ptr(self.step_dev), st), "spv_dropout")
+                                            8 + g, L.ptr(self.noise_dev), st), "spv_dropout")
                 bhd = self.P(g, "bhd")
                 with self._branch(g, "headp"):  # the private and the shared heads are independent
                     self._gemm(L.ptr(w.h2), L.ptr(self.P(g, "Whp")), L.ptr(w.r), B, 2 * P, H, lda=2 * H, ldb=H, ldc=NST, tb=1,
@@ -498,17 +533,23 @@ class StepEngine:
         # ---------------- pairing (integer work) and PoE (reference :484-718)
         aux = self._pairing(batches, ws, Bs)
         self._poe_fwd(ws, Bs, noise, aux)
-        ctx = {"batches": batches, "ws": ws, "Bs": Bs, "noise": noise, "srcs": srcs, "aux": aux, "training": training}
+        ctx = {"batches": batches, "ws": ws, "Bs": Bs, "noise": noise, "srcs": srcs, "aux": aux, "training": training,
+               "with_grad": with_grad, "wm_staged": (not convert) or decode or self.stage_in_adam}
         self._ctx = ctx
-        if not decode:
-            for g in (0, 1):
-                self._join(g)
-            return ws
+        return ctx
+
+    def _decode(self, ctx):
+        d, st, lib = self.d, self._stream(), self.lib
+        H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
+        batches, ws, Bs, srcs, training, with_grad = ctx["batches"], ctx["ws"], ctx["Bs"], ctx["srcs"], ctx["training"], ctx["with_grad"]
+        tr = 1 if training else 0
         # ---------------- decoders + NB likelihood (reference nn/networks.py:314-325, module :751-759, :817-824)
         for g in self._fork_groups():
             bt, w, st = batches[g], ws[g], self._stream()
             G, B = d.genes[g], Bs[g]
             src, xptr, ldx = srcs[g]
+            if self.bf16 and not ctx["wm_staged"]:  # decode() after an encoder-only pass: the mixture weight's bf16 copy
+                L.check(lib.spv_to_bf16(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX, st), "spv_to_bf16")
             zzp = w.amix.data_ptr() + 4 * HD
             fold = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), self.P(g, "gp"), self.P(g, "bp"), self.P(g, "gs"),
                                 self.P(g, "bs"), self.P(g, "px_r"), self.Bf(g, "rm_p"), self.Bf(g, "rv_p"),
@@ -638,7 +679,7 @@ class StepEngine:
             lds = L.ll_array([o[2], t[2], NST, KMIX])
             arrs.append((ptrs, lds))
         L.check(self.lib.spv_poe_fwd(self.mode_id, S, P, Bs[0], Bs[1], arrs[0][0], arrs[0][1], arrs[1][0], arrs[1][1], self.seed,
-                                     L.ptr(self.step_dev), self._stream()), "spv_poe_fwd")
+                                     L.ptr(self.noise_dev), self._stream()), "spv_poe_fwd")
 
     # -------------------------------------------------------------------------------- backward
     def backward(self, grad_scale: float = 1.0, adam: Optional[dict] = None, stage: str = "all", tick: bool = False):
@@ -765,7 +806,7 @@ class StepEngine:
             lds = L.ll_array([o[2], t[2], NST, KZ, NST, ld_out])
             arrs.append((ptrs, lds))
         L.check(lib.spv_poe_bwd(self.mode_id, S, P, Bs[0], Bs[1], arrs[0][0], arrs[0][1], arrs[1][0], arrs[1][1], self.seed,
-                                L.ptr(self.step_dev), L.ptr(self.kl_weight), float(grad_scale) / Bs[0], self._stream()),
+                                L.ptr(self.noise_dev), L.ptr(self.kl_weight), float(grad_scale) / Bs[0], self._stream()),
                 "spv_poe_bwd")
         if self.mode == "cluster":
             # d stats_0[:, shared] += P1^T d expertA ;  d stats_1[:, shared] += P2^T d expertB   (quirk Q5)
@@ -830,14 +871,15 @@ class StepEngine:
             if not self.enc_mid:
                 self._gemm(L.ptr(w.dh2), L.ptr(self.P(g, "W2")), L.ptr(w.dh1), B, H, H, lda=2 * H, ldb=H, ldc=2 * H, batch=2,
                            sA=H, sB=H * H, sC=H, gate=(L.ptr(w.h1), 2 * H, None, 0, 1.0) if fuse1 else None,
-                           c_bf16=(L.ptr(w.dh1b), 2 * H) if (fuse1 and self.bf16) else None)
+                           c_bf16=(L.ptr(w.dh1b), L.ptr(w.dh1b_lo), 2 * H) if (fuse1 and self.bf16) else None)
             if not fuse1:
                 L.check(lib.spv_relu_bwd(L.ptr(w.dh1), 2 * H, L.ptr(w.h1), 2 * H, B, 2 * H, None, 0, 1.0, st), "spv_relu_bwd")
             if self.bf16:
-                if not fuse1:
-                    L.check(lib.spv_to_bf16(L.ptr(w.dh1), 2 * H, L.ptr(w.dh1b), 2 * H, B, 2 * H, st), "spv_to_bf16")
-                self._tc_gemm(L.ptr(w.dh1b), L.ptr(w.Tb), L.ptr(self.Gd(g, "W1")), 2 * H, G, B, lda=2 * H, ldb=w.Gp, ldc=G,
-                              a_mn=1, b_mn=1)
+                if not fuse1 or self.enc_mid:
+                    L.check(lib.spv_to_bf16_split(L.ptr(w.dh1), 2 * H, L.ptr(w.dh1b), L.ptr(w.dh1b_lo), 2 * H, B, 2 * H, st),
+                            "spv_to_bf16_split")
+                self._tc_gemm_split(L.ptr(w.dh1b), L.ptr(w.dh1b_lo), L.ptr(w.Tb), L.ptr(w.Tb_lo), L.ptr(self.Gd(g, "W1")), 2 * H, G, B,
+                                    lda=2 * H, ldb=w.Gp, ldc=G, a_mn=1, b_mn=1)
             else:
                 self._gemm(L.ptr(w.dh1), xptr, L.ptr(self.Gd(g, "W1")), 2 * H, G, B, lda=2 * H, ldb=ldx, ldc=G, ta=1, srcB=src,
                            rowsB=bt.rows)
@@ -861,7 +903,7 @@ class StepEngine:
                                   L.ptr(self.step_dev), L.ptr(self.adam_ticket), len(segs),
                                   L.ll_array([s[0] for s in segs]), L.int_array([s[1] for s in segs]),
                                   L.int_array([s[2] for s in segs]), L.ptr_array([s[3] for s in segs]),
-                                  L.ll_array([s[4] for s in segs]), 0, st), "spv_adam")
+                                  L.ptr_array([s[5] for s in segs]), L.ll_array([s[4] for s in segs]), 0, st), "spv_adam")
 
     def adam_range_step(self, phase, lr=1e-3, betas=(0.9, 0.999), eps=0.01, weight_decay=1e-6, grad_scale=1.0):
         """Adam on one phase of the flat layout (PHASE_ENC / PHASE_DEC); the step counter must have been advanced already
@@ -880,24 +922,30 @@ class StepEngine:
                                   cfg["weight_decay"], cfg.get("grad_scale", 1.0), L.ptr(self.step_dev), None, len(segs),
                                   L.ll_array([s[0] - lo for s in segs]), L.int_array([s[1] for s in segs]),
                                   L.int_array([s[2] for s in segs]), L.ptr_array([s[3] for s in segs]),
-                                  L.ll_array([s[4] for s in segs]), max_blocks, self._stream()), "spv_adam")
+                                  L.ptr_array([s[5] for s in segs]), L.ll_array([s[4] for s in segs]), max_blocks,
+                                  self._stream()), "spv_adam")
 
     def _stage_segments(self):
-        """(flat offset, rows, cols, bf16 destination, destination row pitch) of the weights the tensor-core path reads"""
+        """(flat offset, rows, cols, bf16 destination, destination row pitch, residual plane or None) of the weights the
+        tensor-core path reads"""
         out = []
         for g, G in enumerate(self.d.genes):
-            W1b, Wstack = self.wb[g]
-            out.append((self.params.offsets[g]["W1"][0], 2 * self.d.n_hidden, G, W1b, W1b.stride(0)))
-            out.append((self.params.offsets[g]["Wm"][0], G, self.d.KMIX, Wstack, Wstack.stride(0)))
+            W1b, Wstack, W1b_lo = self.wb[g]
+            out.append((self.params.offsets[g]["W1"][0], 2 * self.d.n_hidden, G, W1b, W1b.stride(0), W1b_lo))
+            out.append((self.params.offsets[g]["Wm"][0], G, self.d.KMIX, Wstack, Wstack.stride(0), None))
         return out
 
     def stage_weights(self):
         """refresh the bf16 operand copies of W1 / Wm from the fp32 parameters (bf16 mode; a no-op otherwise)"""
         if not self.bf16:
             return
-        for off, rows, cols, dst, ld in self._stage_segments():
+        for off, rows, cols, dst, ld, dst_lo in self._stage_segments():
             src = self.params.flat[off:off + rows * cols]
-            L.check(self.lib.spv_to_bf16(L.ptr(src), cols, L.ptr(dst), ld, rows, cols, self._stream()), "spv_to_bf16")
+            if dst_lo is None:
+                L.check(self.lib.spv_to_bf16(L.ptr(src), cols, L.ptr(dst), ld, rows, cols, self._stream()), "spv_to_bf16")
+            else:
+                L.check(self.lib.spv_to_bf16_split(L.ptr(src), cols, L.ptr(dst), L.ptr(dst_lo), ld, rows, cols, self._stream()),
+                        "spv_to_bf16_split")
         self._staged_version = self.params.flat._version
 
     # -------------------------------------------------------------------------------- state

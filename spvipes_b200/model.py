@@ -274,7 +274,6 @@ class spVIPES:
                 r = rows[g].long()
                 lab = d["labels"][r].contiguous() if d["labels"] is not None else None
                 batches.append(GroupBatch(X=d["X"], rows=rows[g], labels=lab, idx=d["idx"][r].contiguous(), B=len(st[g])))
-            eng.step_dev.add_(1)
             ws = eng.forward(batches, training=False, with_grad=False, decode=False)
             for g in (0, 1):
                 res["shared"][g].append(ws[g].zpoe.cpu().clone())

@@ -196,7 +196,7 @@ class spVIPESmodule(nn.Module):
             G = int(vi.shape[0])
             if X.shape[1] == G:      # already this group's own genes
                 col0 = 0
-            elif vi[-1] - vi[0] + 1 == G:  # contiguous block of the combined var axis: zero-copy column offset
+            elif np.array_equal(vi, np.arange(vi[0], vi[0] + G)):  # contiguous, ascending block of the combined var axis: zero-copy column offset
                 col0 = int(vi[0])
             else:                    # arbitrary gene subset: gather once (data movement only)
                 X, col0 = X.index_select(1, torch.as_tensor(vi, device=dev)).contiguous(), 0
@@ -245,7 +245,7 @@ class spVIPESmodule(nn.Module):
             raise ValueError("the only supported number of groups is 2, make sure you passed only 2 groups to `prepare_adatas`")
         if self._last_batches is None:
             raise RuntimeError("generative() follows inference() on the same minibatch")
-        ws = self.engine.forward(self._last_batches, training=self.training, noise=self._noise, with_grad=False)
+        ws = self.engine.decode()  # decoders + likelihood on the latents inference() left in the workspace (its arguments are views of it)
         self._last_ws = ws
         return self._generative_dict(ws)
 
@@ -276,7 +276,6 @@ class spVIPESmodule(nn.Module):
         batches = self._batches(inp["x"], inp["global_indices"], inp.get("labels"), inp.get("processed_labels"))
         kl_weight = float((loss_kwargs or {}).get("kl_weight", 1.0))
         self.engine.set_kl_weight(kl_weight)
-        self.engine.step_dev.add_(1)  # advances the Philox noise / dropout streams
         self._last_batches = batches
         if self.training and torch.is_grad_enabled():
             loss = _StepFunction.apply(self, batches, True, *[self._torch_params[n] for n in self._param_names])

@@ -56,6 +56,11 @@ class GradSync:
         return self.finish()
 
 
+def make_grad_sync(engine, dist):
+    """the gradient synchroniser bench.py / the NCCL test use for this process group"""
+    return GradSync(engine, dist)
+
+
 def broadcast_params(engine, dist, src: int = 0):
     """identical initial weights / running statistics on every rank"""
     dist.broadcast(engine.params.flat, src=src)

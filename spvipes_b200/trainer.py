@@ -124,7 +124,7 @@ class TrainLoop:
         Engine state (parameters, Adam moments, BatchNorm running statistics, step counter) is restored after the
         warm-up launches that precede the capture, so capturing does not advance training."""
         e = self.engine
-        keep = [e.params.flat.clone(), e.buffers.flat.clone(), e.step_dev.clone(),
+        keep = [e.params.flat.clone(), e.buffers.flat.clone(), (e.step_dev.clone(), e.noise_dev.clone()),
                 None if e.adam_m is None else e.adam_m.clone(), None if e.adam_v is None else e.adam_v.clone()]
         cur = torch.cuda.current_stream(e.device)
         side = torch.cuda.Stream(device=e.device)
@@ -155,7 +155,7 @@ class TrainLoop:
                 e.adam_range_step(PHASE_ENC, lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=scale)
             graph = _SyncedGraphs(g1, g2, g3, g4, self.grad_sync, e)
         torch.cuda.synchronize(e.device)
-        e.params.flat.copy_(keep[0]); e.buffers.flat.copy_(keep[1]); e.step_dev.copy_(keep[2])
+        e.params.flat.copy_(keep[0]); e.buffers.flat.copy_(keep[1]); e.step_dev.copy_(keep[2][0]); e.noise_dev.copy_(keep[2][1])
         if keep[3] is None:
             e.adam_m.zero_(); e.adam_v.zero_()
         else:

@@ -1,31 +1,24 @@
-"""-m gpu: the bf16 tensor-core path (tcgen05 GEMMs for encoder fc1 and the decoder mixture layer, fused NB-likelihood
-epilogue) against the golden vectors from the unmodified reference and against the oracle at a BASELINE shape.
+"""-m gpu: the tensor-core path (tcgen05 GEMMs: encoder fc1 on split-bf16 operands, decoder mixture / branch logits in bf16,
+fused NB-likelihood epilogue) against the golden vectors from the unmodified reference and against the oracle.
 
 Tolerances (BASELINE.json north_star, "bf16 tensor-core path"): indices bit-exact; per-batch ELBO and each of the
-2 reconstruction + 4 KL terms <= 1e-2 relative.  Latent statistics pass through a bf16-input GEMM (relative rounding 2^-9
-per operand), so they are checked at 2e-2 here; the 1e-3 latent gate belongs to the fp32 mode (test_gpu_parity.py).
-
-Gradients: with bf16 GEMM inputs a few ReLU / dropout gates of units whose pre-activation is ~0 flip relative to the fp32
-reference; on the 24-row golden minibatches one flipped unit moves a weight-gradient row by several percent, so the tiny
-fixtures are checked on the direction and norm of the full gradient (cosine >= 0.98, relative L2 <= 0.2) and the
-512-row case on cosine >= 0.995, relative L2 <= 0.1."""
+2 reconstruction + 4 KL terms <= 1e-2 relative; latent means / log-variances / scales <= 1e-3 (the encoders' K = genes
+contraction runs as hi.hi + hi.lo + lo.hi on bf16 pairs, so the latents are fp32-grade in this mode too).
+Gradients: per parameter, max |error| / max |gradient| <= GRAD_TOL (the decoder-side gradient GEMMs read bf16 operands:
+dpi / dy rounded to 2^-9 relative, averaged over the minibatch rows).  The exact BASELINE minibatch shapes are in
+tests/test_gpu_shapes.py."""
 import numpy as np
 import pytest
 import torch
 
-from tests.helpers import Golden, golden_names, relerr
+from tests.helpers import Golden, golden_names, grad_errors, relerr
 from tests.gpu_helpers import engine_from_golden, engine_outputs
 
 pytestmark = pytest.mark.gpu
 
 TERMS = ("rec", "kl_private", "kl_poe")
 LATENTS = ("private_loc", "private_logvar", "shared_loc", "shared_logvar", "poe_loc", "poe_logvar", "poe_scale")
-
-
-def _grad_cos(got, want):
-    g = torch.cat([got[k].double().reshape(-1) for k in want])
-    w = torch.cat([want[k].double().reshape(-1) for k in want])
-    return float(torch.dot(g, w) / (g.norm() * w.norm())), float((g - w).norm() / w.norm())
+GRAD_TOL = 2e-3
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -43,7 +36,7 @@ def test_bf16_forward_matches_golden(name):
         assert relerr(out["library"][g].reshape(-1), gd.out[f"library{g}"].reshape(-1)) < 1e-5  # library stays fp32
     for k in LATENTS:
         for g in (0, 1):
-            assert relerr(out[k][g], gd.out[f"{k}{g}"]) < 2e-2, (k, g)
+            assert relerr(out[k][g], gd.out[f"{k}{g}"]) < 1e-3, (k, g, relerr(out[k][g], gd.out[f"{k}{g}"]))
     if gd.mode in ("label", "paired"):
         for g in (0, 1):
             assert np.array_equal(out["partners"][g], gd.out[f"partner{g}"]), g
@@ -57,8 +50,8 @@ def test_bf16_backward_matches_golden(name):
     eng.backward()
     torch.cuda.synchronize()
     got = {k: v.cpu() for k, v in eng.grad_dict().items()}
-    cos, rel = _grad_cos(got, gd.grads)
-    assert cos > 0.98 and rel < 0.2, (cos, rel)
+    worst, where = grad_errors(got, gd.grads)
+    assert worst < GRAD_TOL, (worst, where)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -99,12 +92,12 @@ def test_c1_shape_against_oracle(precision):
             assert relerr(out[k][g], want[k][g].detach()) < tol, (k, g)
     for g in (0, 1):
         assert np.array_equal(out["partners"][g], want["partners"][g])
+    for k in LATENTS:
+        for g in (0, 1):
+            assert relerr(out[k][g], want[k][g].detach()) < 1e-3, (k, g)
     grads = {k: sd[k].grad for k in rs.param_names(sd)}
-    cos, rel = _grad_cos({k: v.cpu() for k, v in eng.grad_dict().items()}, grads)
-    if precision == "fp32":
-        assert cos > 0.999999 and rel < 1e-3, (cos, rel)
-    else:
-        assert cos > 0.995 and rel < 0.1, (cos, rel)
+    worst, where = grad_errors({k: v.cpu() for k, v in eng.grad_dict().items()}, grads)
+    assert worst < GRAD_TOL, (worst, where)
 
 
 def test_stats_tc_matches_simt_statistics():
@@ -150,6 +143,44 @@ def test_early_adam_is_the_same_update():
     off, shape = eng.params.offsets[0]["W1"]
     W1 = out[0][0][off:off + shape[0] * shape[1]].view(shape)
     assert torch.equal(out[0][4][:, :shape[1]], W1.bfloat16())  # the bf16 operand copy tracks the fp32 master
+    lo = eng.wb[0][2][:, :shape[1]]                               # and its residual plane: hi + lo ~ W1 to 2^-17
+    assert torch.equal(lo, (W1 - W1.bfloat16().float()).bfloat16())
+
+
+def test_philox_noise_is_the_same_in_forward_and_backward():
+    """TrainLoop.step with in-kernel Philox noise (noise=None): the backward must regenerate the eps of ITS forward.  The
+    optimiser's step counter advances on an auxiliary stream during the backward; the Philox streams read their own counter.
+    Recover eps from the forward's outputs, replay the step on a second engine with that eps given explicitly, compare the
+    gradients."""
+    from spvipes_b200.engine import Noise
+    from spvipes_b200.trainer import TrainLoop
+    for name in ("label_tiny", "paired_tiny"):
+        gd = Golden(name)
+        engA, batches, _ = engine_from_golden(gd, precision="fp32")
+        engA.dropout_rate = 0.0
+        p0, b0 = engA.params.flat.clone(), engA.buffers.flat.clone()
+        loop = TrainLoop(engA)
+        loop.set_epoch(200)
+        for _ in range(3):  # several steps: the counters move apart
+            p0.copy_(engA.params.flat); b0.copy_(engA.buffers.flat)
+            loop.step(batches)
+        torch.cuda.synchronize()
+        ws = engA._ctx["ws"]
+        P_ = gd.P
+        eps_p = [((w.zpriv - w.stats[:, :P_]) / torch.exp(0.5 * w.stats[:, P_:2 * P_])).clone() for w in ws]
+        sc = [w.poe_scale if gd.mode == "label" else w.poe_scale.clamp(min=1e-6) for w in ws]
+        eps_q = [((w.zpoe - w.poe_loc) / s).clone() for w, s in zip(ws, sc)]
+        gA = engA.grads.clone()
+        engB, batchesB, _ = engine_from_golden(gd, precision="fp32")
+        engB.dropout_rate = 0.0
+        engB.params.flat.copy_(p0); engB.buffers.flat.copy_(b0)
+        engB.set_kl_weight(0.5)
+        engB.forward(batchesB, training=True, noise=Noise(eps_p, eps_q, None))
+        engB.backward()
+        torch.cuda.synchronize()
+        err = float((gA - engB.grads).abs().max() / engB.grads.abs().max())
+        assert err < 1e-4, (name, err)
+        assert int(engA.step_dev) == 3 and int(engA.noise_dev) == 3
 
 
 def test_enc_mid_kernels_match_separate_launches():
@@ -213,12 +244,12 @@ def test_ot_modes_hidden256_against_oracle(mode, precision):
     if mode == "paired":
         for g in (0, 1):
             assert np.array_equal(out["partners"][g], want["partners"][g])
+    for k in LATENTS:
+        for g in (0, 1):
+            assert relerr(out[k][g], want[k][g].detach()) < 1e-3, (k, g)
     grads = {k: sd[k].grad for k in rs.param_names(sd)}
-    cos, rel = _grad_cos({k: v.cpu() for k, v in eng.grad_dict().items()}, grads)
-    if precision == "fp32":
-        assert cos > 0.999999 and rel < 1e-3, (cos, rel)
-    else:
-        assert cos > 0.99 and rel < 0.15, (cos, rel)
+    worst, where = grad_errors({k: v.cpu() for k, v in eng.grad_dict().items()}, grads)
+    assert worst < GRAD_TOL, (worst, where)
 
 
 def test_persistent_nb_kernel_opt_in():
