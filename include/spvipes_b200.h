@@ -152,11 +152,15 @@ int spv_loss(const float* rec0, const float* rec1, const float* klp0, const floa
  * zmean, zcov.  training != 0: zsum / zmean / zcov [P+S], [P+S], [P+S, P+S] are OUTPUTS (column sums, mean and biased
  * covariance of the latent minibatch zz [B, P+S], one cluster launch).   nn/networks.py:314-320, scvi FCLayers;
  * module/spVIPESmodule.py:758 */
-#define SPV_DEC_GENEC_ROWS 17
+#define SPV_DEC_GENEC_ROWS 19
 /* wz_bf16 (optional): rows [Gp, 3 Gp) of the stacked bf16 tensor-core operand [3 Gp, ld_wz] (rows [0, G): mixture weight,
- * [Gp, Gp + G): folded private weights in the latent columns HD .., [2 Gp, 2 Gp + G): folded shared weights) */
+ * [Gp, Gp + G): folded private weights in the latent columns HD .., [2 Gp, 2 Gp + G): folded shared weights) - the B operand
+ * of the input-gradient GEMM of the two branches.
+ * wz_f16 / zc_f16 (optional, both or none): fp16 operands of the branch-logit MMAs of the tensor-core sweeps: wz_f16
+ * [2 Gp, 64] folded weights (private rows, columns [0, P); shared rows from Gp, columns [P, P + S)), zc_f16 [B, 64] the
+ * CENTRED latents zz - mean(zz) (eval mode: zz); genec rows GC_CPLC / GC_CSLC hold the matching shifts. */
 int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, int S, int training, float eps, float momentum,
-                 void* wz_bf16, long long ld_wz, int Gp, int HD, void* stream);
+                 void* wz_bf16, long long ld_wz, int Gp, int HD, void* wz_f16, void* zc_f16, void* stream);
 /* fused decoder + NB-mixture likelihood sweeps.  ptrs (SPV_DEC_NPTR): X, rows, amix, wfold, wm, bm, genec, lib, part_stats,
  * rowc, pi, part_nb, dyp, dys, dpi, colpart, rec.   nn/networks.py:314-325; module/spVIPESmodule.py:759, 817-824 */
 #define SPV_DEC_NPTR 17
@@ -167,18 +171,18 @@ int spv_dec_nb_fwd(int src, const void* const* ptrs, long long ldx, long long ld
 int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P, int S,
                    float scale, float* colsum, void* dpi_bf16, long long ld_dpi_bf16, void* stream);
 /* tensor-core version of phase 2 of spv_dec_nb_fwd: the mixture GEMM and the two softmax-branch logit GEMMs on tcgen05
- * (bf16 operands via TMA, fp32 accumulators in TMEM) with the NB-mixture log-likelihood fused into the TMEM epilogue.
- * amix_bf16 [B, ld_amixb] = [hm | zz]; wstack_bf16 [3 Gp, ld_w] = mixture weight + folded branch weights (spv_dec_fold).
- * part_nb (ptrs[11]) needs spv_dec_nb_part_floats(B, G) floats.  store_pi: also write the mixture logits to ptrs[10] (fp32). */
+ * (operands via TMA, fp32 accumulators in TMEM) with the NB-mixture log-likelihood fused into the TMEM epilogue.
+ * amix_bf16 [B, ld_amixb] = [hm | zz]; wstack_bf16 [>= G, ld_w]: the mixture weight; zc_f16 [B, 64], wz_f16 [2 Gp, 64]: the
+ * fp16 branch operands written by spv_dec_fold.  part_nb (ptrs[11]) needs spv_dec_nb_part_floats(B, G) floats.
+ * store_pi: also write the mixture logits to ptrs[10] (fp32). */
 int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
-                      const void* wstack_bf16, long long ld_w, int Gp, int B, int G, int HD, int P, int S, int store_pi,
-                      void* stream);
-/* tensor-core version of phase 1 of spv_dec_nb_fwd (bf16 path): softmax normalisers rowc[b, 0:2] = lib[b] -
- * logsumexp_g(y_p), (y_s) from the latent k-block of amix_bf16 against the folded weights in wstack_bf16 (spv_dec_fold);
- * part_stats: scratch of 2 * ceil(G/64) * B * 4 floats.   nn/networks.py:318-320, module/spVIPESmodule.py:751-757 */
-int spv_dec_stats_tc(const void* amix_bf16, long long ld_amixb, const void* wstack_bf16, long long ld_w, int Gp,
-                     const float* genec, const float* lib, float* part_stats, float* rowc, int B, int G, int HD, int P, int S,
-                     void* stream);
+                      const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16, int B, int G,
+                      int HD, int P, int S, int store_pi, void* stream);
+/* tensor-core version of phase 1 of spv_dec_nb_fwd: softmax normalisers rowc[b, 0:2] = lib[b] - logsumexp_g(y_p), (y_s)
+ * from the fp16 branch operands (spv_dec_fold); part_stats: scratch of 2 * ceil(G/64) * B * 4 floats.
+ * nn/networks.py:318-320, module/spVIPESmodule.py:751-757 */
+int spv_dec_stats_tc(const void* zc_f16, const void* wz_f16, int Gp, const float* genec, const float* lib, float* part_stats,
+                     float* rowc, int B, int G, int P, int S, void* stream);
 /* floats spv_dec_nb_fwd_tc needs in part_nb (ptrs[11]) for a [B, G] problem */
 long long spv_dec_nb_part_floats(int B, int G);
 /* rec[b] (ptrs[16] of the forward) and the softmax-backward row sums rowc[:, 2:4] from the row partials part_nb that
@@ -189,8 +193,8 @@ int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, int HD, float* rowc
  * ptrs[15] = colpart workspace [ceil(B/128), 4, G].  scale = - grad_scale / B.  rowc (ptrs[9], [B, 4] floats) must be
  * 16-byte aligned (SPV_ERR_ARG otherwise): a row is read as one float4. */
 int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
-                      const void* wstack_bf16, long long ld_w, int Gp, void* d3_bf16, int B, int G, int HD, int P, int S,
-                      float scale, float* colsum, void* stream);
+                      const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16, void* d3_bf16,
+                      int B, int G, int HD, int P, int S, float scale, float* colsum, void* stream);
 /* ptrs (18): Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm,
  * vpart [parts, P+S], mpart [parts, (P+S)^2] with parts = spv_dec_gene_bwd_parts(G)
  * (backward of nn/networks.py:314-320 through the folded BatchNorm) */

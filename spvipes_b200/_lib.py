@@ -14,7 +14,7 @@ SRC_F32, SRC_U16_LOG1P, SRC_F32_LOG1P = 0, 1, 2
 POE_LABEL, POE_PAIRED, POE_CLUSTER = 0, 1, 2
 PARTNER_PAD, PARTNER_ABSENT = -1, -2
 POE_MODES = {"label": POE_LABEL, "paired": POE_PAIRED, "cluster": POE_CLUSTER}
-GENEC_ROWS = 17
+GENEC_ROWS = 19
 
 p, i, ll, f, u64, u32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong, C.c_uint
 
@@ -46,16 +46,16 @@ _SIGS = {
     "spv_poe_fwd": [i, i, i, i, i, p, p, p, p, u64, p, p],
     "spv_poe_bwd": [i, i, i, i, i, p, p, p, p, u64, p, p, f, p],
     "spv_loss": [p, p, p, p, p, p, i, p, p, p],
-    "spv_dec_fold": [p, ll, i, i, i, i, i, f, f, p, ll, i, i, p],
+    "spv_dec_fold": [p, ll, i, i, i, i, i, f, f, p, ll, i, i, p, p, p],
     "spv_dec_nb_fwd": [i, p, ll, ll, i, i, i, i, i, i, p],
     "spv_dec_nb_bwd": [i, p, ll, ll, i, i, i, i, i, f, p, p, ll, p],
-    "spv_dec_nb_fwd_tc": [i, p, ll, p, ll, p, ll, i, i, i, i, i, i, i, p],
+    "spv_dec_nb_fwd_tc": [i, p, ll, p, ll, p, ll, i, p, p, i, i, i, i, i, i, p],
     "spv_dec_nb_rowreduce": [p, i, i, i, p, p, p],
-    "spv_dec_nb_bwd_tc": [i, p, ll, p, ll, p, ll, i, p, i, i, i, i, i, f, p, p],
+    "spv_dec_nb_bwd_tc": [i, p, ll, p, ll, p, ll, i, p, p, p, i, i, i, i, i, f, p, p],
     "spv_dec_gene_bwd": [p, ll, i, i, i, i, p],
     "spv_dec_gene_bwd_parts": [i],
     "spv_dec_nb_part_floats": [i, i],
-    "spv_dec_stats_tc": [p, ll, p, ll, i, p, p, p, p, i, i, i, i, i, p],
+    "spv_dec_stats_tc": [p, p, i, p, p, p, p, i, i, i, i, p],
     "spv_to_bf16_block": [p, ll, p, ll, i, i, i, p],
     "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, p],
     "spv_adam_tick": [p, p],

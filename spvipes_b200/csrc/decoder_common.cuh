@@ -19,5 +19,9 @@ enum {
     GC_THE,      // theta + eps
     GC_K0,       // theta log(theta + eps) - lgamma(theta) + 0.5 log(2 pi)          (forward)
     GC_K1,       // log(theta + eps) + theta / (theta + eps) - digamma(theta)       (backward)
+    // shifts of the CENTRED form y = W' (z - m) + c' used by the tensor-core kernels (m = batch mean of z when training, so
+    // c' = beta exactly; m = 0 in eval mode), times log2(e)
+    GC_CPLC,
+    GC_CSLC,
     GC_N
 };

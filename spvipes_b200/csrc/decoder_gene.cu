@@ -7,6 +7,7 @@
 // Work split: one warp per gene (lanes over the latent dimension), 64 genes per CTA.
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "decoder_common.cuh"
 #include "../../include/spvipes_b200.h"
@@ -141,6 +142,14 @@ struct FoldP {
     __nv_bfloat16* wfold_bf16;
     long ld_wz;
     int Gp, HD;
+    // optional fp16 operands of the branch-logit MMAs (forward / statistics / backward sweeps): wz_f16 [2 Gp, 64] = folded
+    // private weights in columns [0, P) of rows [0, G), folded shared weights in columns [P, P + S) of rows [Gp, Gp + G);
+    // zc_f16 [B, 64] = zz - m (m = batch mean when training, else 0) in columns [0, P + S).  Centring makes the shift exactly
+    // beta and keeps the operand rounding (2^-12) from acting on the common part of the latents.
+    __half* wz_f16;
+    __half* zc_f16;
+    const float* zz;
+    long ld_zz;
     int G, P, S, B, training;
     float eps, momentum;
 };
@@ -233,6 +242,7 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
             sA[br * 32 + gl] = a;
             p.genec[(br == 0 ? GC_CP : GC_CS) * G + g] = beta - mean * a;
             p.genec[(br == 0 ? GC_CPL : GC_CSL) * G + g] = (beta - mean * a) * 1.4426950408889634f;
+            p.genec[(br == 0 ? GC_CPLC : GC_CSLC) * G + g] = (p.training ? beta : beta - mean * a) * 1.4426950408889634f;
             p.genec[(br == 0 ? GC_AP : GC_AS) * G + g] = a;
             p.genec[(br == 0 ? GC_ISTD_P : GC_ISTD_S) * G + g] = invstd;
             p.genec[(br == 0 ? GC_MEAN_P : GC_MEAN_S) * G + g] = mean;
@@ -262,12 +272,20 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
         const int g = g0 + gl;
         p.wfold[(long)g * KZ + k] = wf;
         if (p.wfold_bf16) p.wfold_bf16[((long)(pr ? 0 : 1) * p.Gp + g) * p.ld_wz + p.HD + k] = __float2bfloat16(wf);
+        if (p.wz_f16) p.wz_f16[((long)(pr ? 0 : 1) * p.Gp + g) * 64 + k] = __float2half_rn(wf);
+    }
+    if (p.zc_f16) {  // centred latents: the CTAs share the rows
+        for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < (long)p.B * KZ; i += (long)gridDim.x * 256) {
+            const int b = (int)(i / KZ), k = (int)(i - (long)b * KZ);
+            const float m = p.training ? smean[k] : 0.0f;
+            p.zc_f16[(long)b * 64 + k] = __float2half_rn(__ldg(p.zz + (long)b * p.ld_zz + k) - m);
+        }
     }
 }
 
 // ptrs: Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, (unused), wfold, genec, zmean, zcov
 extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, int S, int training, float eps,
-                            float momentum, void* wz_bf16, long long ld_wz, int Gp, int HD, void* stream) {
+                            float momentum, void* wz_bf16, long long ld_wz, int Gp, int HD, void* wz_f16, void* zc_f16, void* stream) {
     if (!ptrs || B <= 0 || G <= 0 || P <= 0 || S <= 0 || P + S > 96) return SPV_ERR_ARG;
     for (int i = 0; i < 18; ++i)
         if (!ptrs[i]) return SPV_ERR_ARG;
@@ -289,6 +307,9 @@ extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int
     p.zmean = (const float*)ptrs[16]; p.zcov = (const float*)ptrs[17];
     p.wfold_bf16 = reinterpret_cast<__nv_bfloat16*>(wz_bf16);
     p.ld_wz = ld_wz; p.Gp = Gp; p.HD = HD;
+    if ((wz_f16 != nullptr) != (zc_f16 != nullptr) || (wz_f16 && KZ > 64)) return SPV_ERR_ARG;
+    p.wz_f16 = reinterpret_cast<__half*>(wz_f16); p.zc_f16 = reinterpret_cast<__half*>(zc_f16);
+    p.zz = zz; p.ld_zz = ld_zz;
     p.G = G; p.P = P; p.S = S; p.B = B; p.training = training; p.eps = eps; p.momentum = momentum;
     size_t sm2 = (size_t)(KZ + KZ * KZ + FOLD_GENES_PER_CTA * (2 * KZ + 11)) * sizeof(float);
     if (sm2 > 48 * 1024) cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);

@@ -5,9 +5,12 @@
 //                                      (W', c: BatchNorm folded into the factor regressors by spv_dec_fold)
 //   rec_b    = - sum_g log_mixture_nb(log1p(x[b, g]); exp(lib) softmax(lp), exp(lib) softmax(ls), theta, pi)
 //
-// All three contractions run on tcgen05.mma (bf16 operands via TMA, fp32 accumulators in TMEM: 64 columns for pi, 2 x 64 for
-// lp | ls, allocated separately).  The latent columns of the A operand all sit in the last k-block HD/64, so lp and ls each
-// cost one extra MMA group on that block against a zero-padded [genes, 64] copy of the folded weights.
+// All three contractions run on tcgen05.mma (operands via TMA, fp32 accumulators in TMEM: 64 columns for pi, 2 x 64 for
+// lp | ls, allocated separately).  pi: bf16 [hm | zz] against the bf16 mixture weight.  lp, ls: ONE extra 64-wide k-block of
+// fp16 operands - the centred latents zz - mean(zz) against the folded weights (spv_dec_fold writes both) - streamed through
+// the same shared-memory ring after the mixture k-blocks.  The softmax branches are where operand rounding hurts (it acts
+// coherently on every cell of a gene and feeds sums that cancel over the minibatch: tools/diag_grad_noise.py), hence fp16
+// (2^-12) and the centring (the shift of the centred form is exactly beta).
 // One 128 (cells) x 64 (genes) tile per CTA, three CTAs resident per SM of which two own a full accumulator set (the third
 // streams its operands and completes pi while it waits: see the allocation in the MMA warp).  warp 0: TMA producer, warp 1:
 // TMEM allocator + MMA issuer, warps 2..9: epilogue (thread = cell row; two warps per TMEM lane quarter, 32 gene columns each).  Once the accumulators
@@ -15,12 +18,14 @@
 // are streamed out of TMEM four columns at a time.  Nothing of size [B, G] is written unless store_pi is set.
 // Reference: nn/networks.py:314-325, module/spVIPESmodule.py:751-759, 817-824; scvi log_mixture_nb.
 #include "tc_common.cuh"
-#include "nb_ptc.cuh"
 #include "nb_math.cuh"
 #include "decoder_common.cuh"
 #include "../../include/spvipes_b200.h"
 
-extern "C" long long* spv_debug_get_trace();  // nb_ptc.cu: the buffer set by spv_debug_trace, or null
+// diagnostic hook (NB_TRACE builds, tools/nb_tile_trace*.py): per-CTA %globaltimer stamps go to this device buffer
+static long long* g_trace_buf = nullptr;
+extern "C" void spv_debug_trace(long long* buf) { g_trace_buf = buf; }
+extern "C" long long* spv_debug_get_trace() { return g_trace_buf; }
 
 namespace {
 
@@ -48,7 +53,7 @@ struct NbTcParams {
     const float* rowc;                 // [B, 4]: Rp, Rs
     float* pi;                         // [B, G] or null
     float* part_nb;                    // [nTG, B, 3]
-    int B, G, K, kb_z;                 // kb_z: k-block holding the latent columns
+    int B, G, K;
     int Gp;                            // row offset of the shared block inside the folded-weight operand
     long long* trace;                  // diagnostic (NB_TRACE builds): 6 globaltimer stamps per CTA
 };
@@ -64,7 +69,8 @@ __device__ int g_resident_fwd[256];
 template <int SRC>
 __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                const __grid_constant__ CUtensorMap mapB,
-                                                               const __grid_constant__ CUtensorMap mapZ, NbTcParams p) {
+                                                               const __grid_constant__ CUtensorMap mapZ,
+                                                               const __grid_constant__ CUtensorMap mapZc, NbTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = tc::smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
@@ -96,6 +102,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
         tc::tma_prefetch_desc(&mapA);
         tc::tma_prefetch_desc(&mapB);
         tc::tma_prefetch_desc(&mapZ);
+        tc::tma_prefetch_desc(&mapZc);
         for (int s = 0; s < STAGES; ++s) {
             tc::mbar_init(&full[s], 1);
             tc::mbar_init(&empty[s], 1);
@@ -115,8 +122,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
     if (warp == 0) {
         if (tc::elect_one()) {
             tc::mbar_expect_tx(z_full, 2 * B_BYTES);
-            tc::tma_load_2d(&mapZ, z_full, z_tiles, p.kb_z * BK, n0);                   // folded private weights (rows 0..G)
-            tc::tma_load_2d(&mapZ, z_full, z_tiles + B_BYTES, p.kb_z * BK, p.Gp + n0);  // folded shared weights (rows Gp..)
+            tc::tma_load_2d(&mapZ, z_full, z_tiles, 0, n0);                   // folded private weights (rows 0..G), fp16
+            tc::tma_load_2d(&mapZ, z_full, z_tiles + B_BYTES, 0, p.Gp + n0);  // folded shared weights (rows Gp..)
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
@@ -125,6 +132,13 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
                 tc::mbar_expect_tx(&full[s], STAGE_BYTES);
                 tc::tma_load_2d(&mapA, &full[s], a_dst, i * BK, m0);
                 tc::tma_load_2d(&mapB, &full[s], a_dst + A_BYTES, i * BK, n0);
+            }
+            {  // the branch k-block: centred latents (fp16), A tile only, next slot of the ring
+                const int s = num_kb % STAGES;
+                const uint32_t ph = (num_kb / STAGES) & 1;
+                tc::mbar_wait(&empty[s], ph ^ 1);
+                tc::mbar_expect_tx(&full[s], A_BYTES);
+                tc::tma_load_2d(&mapZc, &full[s], tiles + s * STAGE_BYTES, 0, m0);
             }
         }
     } else if (warp == 1) {
@@ -147,7 +161,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
         tc::fence_after_sync();
         tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
         constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, false, false);
-        const int s_z = p.kb_z % STAGES;  // kb_z is the last k-block (checked by the host): its stage is kept for the branch MMAs
+        constexpr uint32_t idesc_z = tc::idesc_f16(BM, BN);
+        const int s_z = num_kb % STAGES;  // ring slot of the branch k-block (the centred latents)
         if (lane == 0) {
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
@@ -160,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
                 for (int kk = 0; kk < BK / 16; ++kk)
                     tc::umma_bf16(tmem_base, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(b_base + kk * 32, 16, 1024),
                                   idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                if (i != p.kb_z) tc::umma_commit(&empty[s]);
+                tc::umma_commit(&empty[s]);
             }
         }
         __syncwarp();
@@ -175,15 +190,16 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
             stamp(6);  // tensor memory granted
             tc::mbar_arrive(tmem_ready);  // release: the epilogue warps read the slots after acquiring this barrier
             tc::mbar_wait(z_full, 0);
+            tc::mbar_wait(&full[s_z], (num_kb / STAGES) & 1);
             tc::fence_after_sync();
             const uint32_t a_base = tc::smem_u32(tiles + s_z * STAGE_BYTES);
             const uint32_t zp_base = tc::smem_u32(z_tiles), zs_base = zp_base + B_BYTES;
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) {  // the two softmax-branch logits: latent k-block against the folded weights
-                tc::umma_bf16(tmem_z, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zp_base + kk * 32, 16, 1024), idesc,
+            for (int kk = 0; kk < BK / 16; ++kk) {  // the two softmax-branch logits: centred latents against the folded weights (fp16)
+                tc::umma_bf16(tmem_z, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zp_base + kk * 32, 16, 1024), idesc_z,
                               kk > 0 ? 1u : 0u);
                 tc::umma_bf16(tmem_z + BN, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zs_base + kk * 32, 16, 1024),
-                              idesc, kk > 0 ? 1u : 0u);
+                              idesc_z, kk > 0 ? 1u : 0u);
             }
             tc::umma_commit(tmem_full);
         }
@@ -216,8 +232,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
         static_assert(BN <= EPI_THREADS, "one thread per gene of the tile stages its constants");
         if (et < BN && n0 + et < p.G) {
             const int g = n0 + et;
-            gcv[0] = __ldg(p.genec + GC_CPL * G + g);  // constants of nb_forward_v3
-            gcv[1] = __ldg(p.genec + GC_CSL * G + g);
+            gcv[0] = __ldg(p.genec + GC_CPLC * G + g);  // constants of nb_forward_v3 (shifts of the centred form)
+            gcv[1] = __ldg(p.genec + GC_CSLC * G + g);
             gcv[2] = __ldg(p.bm + g);
             gcv[3] = __ldg(p.genec + GC_THETA * G + g);
             gcv[4] = __ldg(p.genec + GC_THE * G + g);
@@ -343,7 +359,7 @@ constexpr int ST_SMEM = A_BYTES + 2 * B_BYTES + 1024 + 2 * BN * 4 + 64;
 
 __global__ void __launch_bounds__(THREADS, 3) nb_tc_stats_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                  const __grid_constant__ CUtensorMap mapZ, const float* __restrict__ genec,
-                                                                 float* __restrict__ part_stats, int B, int G, int kb_z, int Gp) {
+                                                                 float* __restrict__ part_stats, int B, int G, int Gp) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = tc::smem_u32(smem_raw);
     uint8_t* tiles = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -369,13 +385,13 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_stats_kernel(const __grid_co
     if (warp == 0) {
         if (tc::elect_one()) {
             tc::mbar_expect_tx(full, A_BYTES + 2 * B_BYTES);
-            tc::tma_load_2d(&mapA, full, tiles, kb_z * BK, m0);
-            tc::tma_load_2d(&mapZ, full, z_tiles, kb_z * BK, n0);
-            tc::tma_load_2d(&mapZ, full, z_tiles + B_BYTES, kb_z * BK, Gp + n0);
+            tc::tma_load_2d(&mapA, full, tiles, 0, m0);   // centred latents, fp16 [B, 64]
+            tc::tma_load_2d(&mapZ, full, z_tiles, 0, n0);  // folded weights, fp16 [2 Gp, 64]
+            tc::tma_load_2d(&mapZ, full, z_tiles + B_BYTES, 0, Gp + n0);
         }
     } else if (warp == 1) {
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, false, false);
+            constexpr uint32_t idesc = tc::idesc_f16(BM, BN);
             tc::mbar_wait(full, 0);
             tc::fence_after_sync();
             const uint32_t a_base = tc::smem_u32(tiles), zp_base = tc::smem_u32(z_tiles), zs_base = zp_base + B_BYTES;
@@ -393,7 +409,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_stats_kernel(const __grid_co
         const long Gl = G;
         for (int i = et; i < 2 * BN; i += EPI_THREADS) {
             const int k = i / BN, c = i - k * BN, g = n0 + c;
-            s_c[i] = g < G ? __ldg(genec + (k == 0 ? GC_CPL : GC_CSL) * Gl + g) : 0.0f;
+            s_c[i] = g < G ? __ldg(genec + (k == 0 ? GC_CPLC : GC_CSLC) * Gl + g) : 0.0f;
         }
         const int e = warp - 2, q = warp & 3, half = e >> 2;
         const int m = m0 + q * 32 + lane;
@@ -459,53 +475,48 @@ __global__ void rownb_tc_kernel(const float* __restrict__ part, int nPart, int B
 
 }  // namespace
 
+// per-device one-time kernel attribute (the attribute is per device; a process may drive several)
+template <typename K>
+static int set_smem_once(K kernel, int bytes, bool (&done)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done[dev & 63]) return SPV_OK;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return SPV_ERR_LAUNCH;
+    done[dev & 63] = true;
+    return SPV_OK;
+}
+
 // ptrs: the SPV_DEC_NPTR list of spv_dec_nb_fwd (X, rows, amix [unused], wfold [unused], wm [unused], bm, genec, lib,
 // part_stats, rowc, pi, part_nb [>= 2 * ceil(G/64) * B * 3 floats], ..., rec).  rowc[:, 0:2] must hold the softmax
-// normalisers (phase 1 of spv_dec_nb_fwd).  bf16 operands: amix_bf16 [B, ld_amixb] = [hm | zz]; wstack_bf16 [3 * Gp, ld_w]:
-// rows [0, G) the mixture weight, rows [Gp, Gp + G) / [2 Gp, 2 Gp + G) the folded private / shared factor-regressor weights
-// placed in the latent columns (written by spv_dec_fold), zero elsewhere.  Gp = G rounded up to a multiple of 8.
+// normalisers (spv_dec_stats_tc).  Operands: amix_bf16 [B, ld_amixb] = [hm | zz]; wstack_bf16 [>= G, ld_w]: rows [0, G) the
+// mixture weight (bf16); zc_f16 [B, 64] centred latents and wz_f16 [2 Gp, 64] folded branch weights (fp16, spv_dec_fold).
+// Gp = G rounded up to a multiple of 8.
 extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
-                                 const void* wstack_bf16, long long ld_w, int Gp, int B, int G, int HD, int P, int S,
-                                 int store_pi, void* stream) {
-    if (!ptrs || !amix_bf16 || !wstack_bf16 || Gp < G || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
-    const void* wm_bf16 = wstack_bf16;
-    const long long ld_wmb = ld_w;
-    const void* wz_bf16 = reinterpret_cast<const __nv_bfloat16*>(wstack_bf16) + (size_t)Gp * ld_w;
-    if ((HD % BK) != 0 || P + S > BK) return SPV_ERR_ARG;  // the latent columns must sit in one k-block
+                                 const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16, int B,
+                                 int G, int HD, int P, int S, int store_pi, void* stream) {
+    if (!ptrs || !amix_bf16 || !wstack_bf16 || !zc_f16 || !wz_f16 || Gp < G || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0)
+        return SPV_ERR_ARG;
+    if (P + S > BK) return SPV_ERR_ARG;  // the latent columns must fit the branch k-block
     const int need[] = {0, 5, 6, 9, 11, 16};
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
     if (store_pi && !ptrs[10]) return SPV_ERR_ARG;
     const int K = HD + P + S;
-    CUtensorMap ma, mb, mz;
+    CUtensorMap ma, mb, mz, mzc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (ptc::eligible(B, G, K, ptc::sm_count())) {  // persistent kernel: one CTA per SM over 128 x 16 units
-        int rc = spv_make_tensor_map_bf16(&ma, amix_bf16, (unsigned long long)K, (unsigned long long)B, (unsigned long long)ld_amixb, 64, ptc::BM);
-        if (rc != SPV_OK) return rc;
-        rc = spv_make_tensor_map_bf16(&mb, wm_bf16, (unsigned long long)K, (unsigned long long)G, (unsigned long long)ld_wmb, 64, ptc::BN);
-        if (rc != SPV_OK) return rc;
-        rc = spv_make_tensor_map_bf16(&mz, wz_bf16, (unsigned long long)K, (unsigned long long)(2 * Gp), (unsigned long long)ld_w, 64, ptc::BN);
-        if (rc != SPV_OK) return rc;
-        ptc::FwdParams q;
-        q.X = ptrs[0]; q.ldx = ldx; q.rows = (const int*)ptrs[1]; q.bm = (const float*)ptrs[5]; q.genec = (const float*)ptrs[6];
-        q.rowc = (const float*)ptrs[9]; q.pi = store_pi ? (float*)ptrs[10] : nullptr; q.part = (float*)ptrs[11];
-        q.trace = nullptr;
-        q.B = B; q.G = G; q.num_kb = (K + BK - 1) / BK; q.kb_z = HD / BK; q.Gp = Gp;
-        q.nG = (G + ptc::BN - 1) / ptc::BN; q.units = ((B + ptc::BM - 1) / ptc::BM) * q.nG;
-        return ptc::fwd_launch(src, ma, mb, mz, q, st);
-    }
     int rc = spv_make_tensor_map_bf16(&ma, amix_bf16, (unsigned long long)K, (unsigned long long)B, (unsigned long long)ld_amixb, 64, BM);
     if (rc != SPV_OK) return rc;
-    rc = spv_make_tensor_map_bf16(&mb, wm_bf16, (unsigned long long)K, (unsigned long long)G, (unsigned long long)ld_wmb, 64, BN);
+    rc = spv_make_tensor_map_bf16(&mb, wstack_bf16, (unsigned long long)K, (unsigned long long)G, (unsigned long long)ld_w, 64, BN);
     if (rc != SPV_OK) return rc;
-    rc = spv_make_tensor_map_bf16(&mz, wz_bf16, (unsigned long long)K, (unsigned long long)(2 * Gp), (unsigned long long)ld_w, 64, BN);
+    rc = spv_make_tensor_map_bf16(&mz, wz_f16, 64ull, (unsigned long long)(2 * Gp), 64ull, 64, BN);  // 16-bit elements: same map type
+    if (rc != SPV_OK) return rc;
+    rc = spv_make_tensor_map_bf16(&mzc, zc_f16, 64ull, (unsigned long long)B, 64ull, 64, BM);
     if (rc != SPV_OK) return rc;
     NbTcParams p;
     p.Gp = Gp;
     p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
     p.rowc = (const float*)ptrs[9]; p.pi = store_pi ? (float*)ptrs[10] : nullptr; p.part_nb = (float*)ptrs[11];
-    p.B = B; p.G = G; p.K = K; p.kb_z = HD / BK;
-    if (p.kb_z != (K + BK - 1) / BK - 1) return SPV_ERR_ARG;  // the latent columns must be the last k-block (P + S <= 64)
+    p.B = B; p.G = G; p.K = K;
     p.trace = spv_debug_get_trace();
 #ifdef NB_TRACE
     {  // consecutive launches (the two groups of a step) stamp alternate halves of the buffer
@@ -513,16 +524,13 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
         if (p.trace) p.trace += (long)(n_launch++ & 1) * 8 * ((G + BN - 1) / BN) * ((B + BM - 1) / BM);
     }
 #endif
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(nb_tc_fwd_kernel<SPV_SRC_U16_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(nb_tc_fwd_kernel<SPV_SRC_F32_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
-            return SPV_ERR_LAUNCH;
-        configured = true;
-    }
+    static bool done_u16[64] = {}, done_f32[64] = {};
+    if (set_smem_once(nb_tc_fwd_kernel<SPV_SRC_U16_LOG1P>, SMEM_BYTES, done_u16) != SPV_OK ||
+        set_smem_once(nb_tc_fwd_kernel<SPV_SRC_F32_LOG1P>, SMEM_BYTES, done_f32) != SPV_OK)
+        return SPV_ERR_LAUNCH;
     dim3 grid((G + BN - 1) / BN, (B + BM - 1) / BM);
-    if (src == SPV_SRC_U16_LOG1P) nb_tc_fwd_kernel<SPV_SRC_U16_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, p);
-    else if (src == SPV_SRC_F32_LOG1P) nb_tc_fwd_kernel<SPV_SRC_F32_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, p);
+    if (src == SPV_SRC_U16_LOG1P) nb_tc_fwd_kernel<SPV_SRC_U16_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, mzc, p);
+    else if (src == SPV_SRC_F32_LOG1P) nb_tc_fwd_kernel<SPV_SRC_F32_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, mzc, p);
     else return SPV_ERR_ARG;
     SPV_CHECK_LAUNCH();
     return SPV_OK;
@@ -531,43 +539,36 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
 int spv_internal_rowstat(const float* part, int nparts, int B, const float* lib, float* rowc, cudaStream_t st);
 
 // Softmax normalisers of the two branches on the tensor cores: rowc[b, 0:2] = lib[b] - logsumexp_g(y_p / y_s)   (phase 1 of
-// spv_dec_nb_fwd for the bf16 path).  part_stats needs 2 * ceil(G/64) * B * 4 floats.
-extern "C" int spv_dec_stats_tc(const void* amix_bf16, long long ld_amixb, const void* wstack_bf16, long long ld_w, int Gp,
-                                const float* genec, const float* lib, float* part_stats, float* rowc, int B, int G, int HD, int P,
-                                int S, void* stream) {
-    if (!amix_bf16 || !wstack_bf16 || !genec || !lib || !part_stats || !rowc || Gp < G || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0)
+// spv_dec_nb_fwd for the tensor-core path), from the fp16 operands spv_dec_fold wrote: zc_f16 [B, 64] centred latents, wz_f16
+// [2 Gp, 64] folded weights.  part_stats needs 2 * ceil(G/64) * B * 4 floats.
+extern "C" int spv_dec_stats_tc(const void* zc_f16, const void* wz_f16, int Gp, const float* genec, const float* lib,
+                                float* part_stats, float* rowc, int B, int G, int P, int S, void* stream) {
+    if (!zc_f16 || !wz_f16 || !genec || !lib || !part_stats || !rowc || Gp < G || B <= 0 || G <= 0 || P <= 0 || S <= 0)
         return SPV_ERR_ARG;
-    if ((HD % BK) != 0 || P + S > BK) return SPV_ERR_ARG;
-    const int K = HD + P + S;
-    const void* wz_bf16 = reinterpret_cast<const __nv_bfloat16*>(wstack_bf16) + (size_t)Gp * ld_w;
+    if (P + S > BK) return SPV_ERR_ARG;
     CUtensorMap ma, mz;
-    int rc = spv_make_tensor_map_bf16(&ma, amix_bf16, (unsigned long long)K, (unsigned long long)B, (unsigned long long)ld_amixb, 64, BM);
+    int rc = spv_make_tensor_map_bf16(&ma, zc_f16, 64ull, (unsigned long long)B, 64ull, 64, BM);
     if (rc != SPV_OK) return rc;
-    rc = spv_make_tensor_map_bf16(&mz, wz_bf16, (unsigned long long)K, (unsigned long long)(2 * Gp), (unsigned long long)ld_w, 64, BN);
+    rc = spv_make_tensor_map_bf16(&mz, wz_f16, 64ull, (unsigned long long)(2 * Gp), 64ull, 64, BN);
     if (rc != SPV_OK) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(nb_tc_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM) != cudaSuccess) return SPV_ERR_LAUNCH;
-        configured = true;
-    }
+    static bool done[64] = {};
+    if (set_smem_once(nb_tc_stats_kernel, ST_SMEM, done) != SPV_OK) return SPV_ERR_LAUNCH;
     dim3 grid((G + BN - 1) / BN, (B + BM - 1) / BM);
-    nb_tc_stats_kernel<<<grid, THREADS, ST_SMEM, st>>>(ma, mz, genec, part_stats, B, G, HD / BK, Gp);
+    nb_tc_stats_kernel<<<grid, THREADS, ST_SMEM, st>>>(ma, mz, genec, part_stats, B, G, Gp);
     SPV_CHECK_LAUNCH();
     return spv_internal_rowstat(part_stats, 2 * (int)grid.x, B, lib, rowc, st);
 }
 
-// floats spv_dec_nb_fwd_tc needs in part_nb (either kernel variant)
+// floats spv_dec_nb_fwd_tc needs in part_nb
 extern "C" long long spv_dec_nb_part_floats(int B, int G) {
     if (B <= 0 || G <= 0) return 0;
-    const long long tiled = 2ll * ((G + BN - 1) / BN) * B * 3;
-    return tiled > ptc::part_floats() ? tiled : ptc::part_floats();
+    return 2ll * ((G + BN - 1) / BN) * B * 3;
 }
 
 // rec[b] = - sum over the row partials of spv_dec_nb_fwd_tc (same B, G, HD); also the softmax-backward row sums rowc[:, 2:4]
 extern "C" int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, int HD, float* rowc, float* rec, void* stream) {
     if (!part_nb || !rowc || !rec || G <= 0 || B <= 0 || HD < 0) return SPV_ERR_ARG;
-    if (ptc::eligible(B, G, HD + BK, ptc::sm_count())) return ptc::fwd_rowreduce(part_nb, G, B, rowc, rec, reinterpret_cast<cudaStream_t>(stream));
     rownb_tc_kernel<<<(B + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part_nb, 2 * ((G + BN - 1) / BN), B, rowc, rec);
     SPV_CHECK_LAUNCH();
     return SPV_OK;

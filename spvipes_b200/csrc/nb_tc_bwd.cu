@@ -33,7 +33,7 @@ struct NbTcBwdParams {
     const float* lib;    // [B]
     __nv_bfloat16* dpi; long ld_dpi;   // D3 [B, 3 * Gp] = [dpi | dyp | dys]
     float* colpart;                    // [nTB, 4, G]
-    int B, G, K, kb_z, Gp;
+    int B, G, K, Gp;
     float scale;
 };
 
@@ -48,7 +48,8 @@ __device__ int g_resident_bwd[256];
 template <int SRC>
 __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                const __grid_constant__ CUtensorMap mapB,
-                                                               const __grid_constant__ CUtensorMap mapZ, NbTcBwdParams p) {
+                                                               const __grid_constant__ CUtensorMap mapZ,
+                                                               const __grid_constant__ CUtensorMap mapZc, NbTcBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = tc::smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
         tc::tma_prefetch_desc(&mapA);
         tc::tma_prefetch_desc(&mapB);
         tc::tma_prefetch_desc(&mapZ);
+        tc::tma_prefetch_desc(&mapZc);
         for (int s = 0; s < STAGES; ++s) {
             tc::mbar_init(&full[s], 1);
             tc::mbar_init(&empty[s], 1);
@@ -90,8 +92,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
     if (warp == 0) {
         if (tc::elect_one()) {
             tc::mbar_expect_tx(z_full, 2 * B_BYTES);
-            tc::tma_load_2d(&mapZ, z_full, z_tiles, p.kb_z * BK, n0);
-            tc::tma_load_2d(&mapZ, z_full, z_tiles + B_BYTES, p.kb_z * BK, p.Gp + n0);
+            tc::tma_load_2d(&mapZ, z_full, z_tiles, 0, n0);  // folded branch weights, fp16 [2 Gp, 64]
+            tc::tma_load_2d(&mapZ, z_full, z_tiles + B_BYTES, 0, p.Gp + n0);
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
@@ -100,6 +102,13 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
                 tc::mbar_expect_tx(&full[s], STAGE_BYTES);
                 tc::tma_load_2d(&mapA, &full[s], a_dst, i * BK, m0);
                 tc::tma_load_2d(&mapB, &full[s], a_dst + A_BYTES, i * BK, n0);
+            }
+            {  // the branch k-block: centred latents (fp16), A tile only, next slot of the ring
+                const int s = num_kb % STAGES;
+                const uint32_t ph = (num_kb / STAGES) & 1;
+                tc::mbar_wait(&empty[s], ph ^ 1);
+                tc::mbar_expect_tx(&full[s], A_BYTES);
+                tc::tma_load_2d(&mapZc, &full[s], tiles + s * STAGE_BYTES, 0, m0);
             }
         }
     } else if (warp == 1) {
@@ -120,7 +129,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
         tc::fence_after_sync();
         tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
         constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, false, false);
-        const int s_z = p.kb_z % STAGES;  // kb_z is the last k-block (checked by the host): its stage is kept for the branch MMAs
+        constexpr uint32_t idesc_z = tc::idesc_f16(BM, BN);
+        const int s_z = num_kb % STAGES;  // ring slot of the branch k-block (the centred latents)
         if (lane == 0) {
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
@@ -133,7 +143,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
                 for (int kk = 0; kk < BK / 16; ++kk)
                     tc::umma_bf16(tmem_base, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(b_base + kk * 32, 16, 1024),
                                   idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                if (i != p.kb_z) tc::umma_commit(&empty[s]);
+                tc::umma_commit(&empty[s]);
             }
         }
         __syncwarp();
@@ -147,15 +157,16 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
         if (lane == 0) {
             tc::mbar_arrive(tmem_ready);  // release: the epilogue warps read the slots after acquiring this barrier
             tc::mbar_wait(z_full, 0);
+            tc::mbar_wait(&full[s_z], (num_kb / STAGES) & 1);
             tc::fence_after_sync();
             const uint32_t a_base = tc::smem_u32(tiles + s_z * STAGE_BYTES);
             const uint32_t zp_base = tc::smem_u32(z_tiles), zs_base = zp_base + B_BYTES;
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
-                tc::umma_bf16(tmem_z, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zp_base + kk * 32, 16, 1024), idesc,
+                tc::umma_bf16(tmem_z, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zp_base + kk * 32, 16, 1024), idesc_z,
                               kk > 0 ? 1u : 0u);
                 tc::umma_bf16(tmem_z + BN, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zs_base + kk * 32, 16, 1024),
-                              idesc, kk > 0 ? 1u : 0u);
+                              idesc_z, kk > 0 ? 1u : 0u);
             }
             tc::umma_commit(tmem_full);
         }
@@ -189,8 +200,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
         static_assert(BN <= EPI_THREADS, "one thread per gene of the tile stages its constants");
         if (et < BN && n0 + et < p.G) {
             const int g = n0 + et;
-            gcv[0] = __ldg(p.genec + GC_CPL * G + g);  // constants of nb_backward_v3
-            gcv[1] = __ldg(p.genec + GC_CSL * G + g);
+            gcv[0] = __ldg(p.genec + GC_CPLC * G + g);  // constants of nb_backward_v3 (shifts of the centred form)
+            gcv[1] = __ldg(p.genec + GC_CSLC * G + g);
             gcv[2] = __ldg(p.bm + g);
             gcv[3] = __ldg(p.genec + GC_THETA * G + g);
             gcv[4] = __ldg(p.genec + GC_THE * G + g);
@@ -355,41 +366,45 @@ __global__ void colpart_reduce_tc_kernel(const float* __restrict__ colpart, int 
 
 // ptrs: the SPV_DEC_NPTR list (X, rows, -, -, -, bm, genec, lib, -, rowc, -, -, -, -, -, colpart [ceil(B/128), 4, G], -).
 // d3_bf16 [B, 3 * Gp] receives [d loss / d pi | d loss / d y_private | d loss / d y_shared] (bf16, the A operand of the
-// gradient GEMMs).  wstack_bf16 [3 * Gp, ld_w]: see spv_dec_nb_fwd_tc.  colsum [4, G] = column sums of dyp, dys, dpi, dtheta.
+// gradient GEMMs).  Operands as spv_dec_nb_fwd_tc.  colsum [4, G] = column sums of dyp, dys, dpi, dtheta.
 extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
-                                 const void* wstack_bf16, long long ld_w, int Gp, void* d3_bf16, int B, int G, int HD, int P,
-                                 int S, float scale, float* colsum, void* stream) {
-    if (!ptrs || !amix_bf16 || !wstack_bf16 || !d3_bf16 || !colsum || Gp < G || B <= 0 || G <= 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
-    if ((HD % BK) != 0 || P + S > BK) return SPV_ERR_ARG;
+                                 const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16,
+                                 void* d3_bf16, int B, int G, int HD, int P, int S, float scale, float* colsum, void* stream) {
+    if (!ptrs || !amix_bf16 || !wstack_bf16 || !zc_f16 || !wz_f16 || !d3_bf16 || !colsum || Gp < G || B <= 0 || G <= 0 || P <= 0 || S <= 0)
+        return SPV_ERR_ARG;
+    if (P + S > BK) return SPV_ERR_ARG;
     const int need[] = {0, 5, 6, 7, 9, 15};
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
     const int K = HD + P + S;
     if (reinterpret_cast<uintptr_t>(ptrs[9]) & 15) return SPV_ERR_ARG;  // rowc rows are read as one float4
-    const void* wz_bf16 = reinterpret_cast<const __nv_bfloat16*>(wstack_bf16) + (size_t)Gp * ld_w;
-    CUtensorMap ma, mb, mz;
+    CUtensorMap ma, mb, mz, mzc;
     int rc = spv_make_tensor_map_bf16(&ma, amix_bf16, (unsigned long long)K, (unsigned long long)B, (unsigned long long)ld_amixb, 64, BM);
     if (rc != SPV_OK) return rc;
     rc = spv_make_tensor_map_bf16(&mb, wstack_bf16, (unsigned long long)K, (unsigned long long)G, (unsigned long long)ld_w, 64, BN);
     if (rc != SPV_OK) return rc;
-    rc = spv_make_tensor_map_bf16(&mz, wz_bf16, (unsigned long long)K, (unsigned long long)(2 * Gp), (unsigned long long)ld_w, 64, BN);
+    rc = spv_make_tensor_map_bf16(&mz, wz_f16, 64ull, (unsigned long long)(2 * Gp), 64ull, 64, BN);
+    if (rc != SPV_OK) return rc;
+    rc = spv_make_tensor_map_bf16(&mzc, zc_f16, 64ull, (unsigned long long)B, 64ull, 64, BM);
     if (rc != SPV_OK) return rc;
     NbTcBwdParams p;
     p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
     p.lib = (const float*)ptrs[7]; p.rowc = (const float*)ptrs[9];
     p.colpart = (float*)ptrs[15]; p.dpi = reinterpret_cast<__nv_bfloat16*>(d3_bf16); p.ld_dpi = 3L * Gp;
-    p.B = B; p.G = G; p.K = K; p.kb_z = HD / BK; p.Gp = Gp; p.scale = scale;
+    p.B = B; p.G = G; p.K = K; p.Gp = Gp; p.scale = scale;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
         if (cudaFuncSetAttribute(nb_tc_bwd_kernel<SPV_SRC_U16_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(nb_tc_bwd_kernel<SPV_SRC_F32_LOG1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
             return SPV_ERR_LAUNCH;
-        configured = true;
+        configured[dev & 63] = true;
     }
     dim3 grid((G + BN - 1) / BN, (B + BM - 1) / BM);
-    if (src == SPV_SRC_U16_LOG1P) nb_tc_bwd_kernel<SPV_SRC_U16_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, p);
-    else if (src == SPV_SRC_F32_LOG1P) nb_tc_bwd_kernel<SPV_SRC_F32_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, p);
+    if (src == SPV_SRC_U16_LOG1P) nb_tc_bwd_kernel<SPV_SRC_U16_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, mzc, p);
+    else if (src == SPV_SRC_F32_LOG1P) nb_tc_bwd_kernel<SPV_SRC_F32_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, mzc, p);
     else return SPV_ERR_ARG;
     SPV_CHECK_LAUNCH();
     colpart_reduce_tc_kernel<<<(4 * G + 255) / 256, 256, 0, st>>>(p.colpart, (int)grid.y, G, colsum);

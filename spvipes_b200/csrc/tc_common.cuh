@@ -130,6 +130,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn_major,
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// instruction descriptor for kind::f16, F16 x F16 -> F32 (K-major operands)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 }  // namespace tc
 
 // host: bf16 2-D tensor map with 128-byte swizzle; dims / box in elements, inner dimension first

@@ -214,6 +214,9 @@ class _GroupWS:
             h = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
             self.Tb, self.amixb = h(B, self.Gp), h(B, self.KMp)
             self.Tb_lo = h(B, self.Gp)  # bf16 residual of log1p(counts): the fc1 contractions run on split operands
+            # fp16 operands of the branch-logit MMAs (spv_dec_fold writes them): centred latents and folded weights
+            self.zcb = torch.zeros(B, 64, dtype=torch.float16, device=dev)
+            self.wzf = torch.zeros(2 * self.Gp, 64, dtype=torch.float16, device=dev)
             # bf16 weight operands are per engine (shared by every workspace): W1b [2H, Gp] and the stacked operand
             # Wstack [3 Gp, KMp]: rows [0, G) mixture weight, [Gp, Gp+G) / [2Gp, 2Gp+G) the folded private / shared
             # factor-regressor weights of the current minibatch in the latent columns (zero elsewhere)
@@ -557,20 +560,18 @@ class StepEngine:
                                 w.zcov])
             wz = w.Wstack.data_ptr() + 2 * w.Gp * w.KMp if self.fused_nb else None
             if self.fused_nb:
-                # hidden layer of the mixing net (needs only zz) on the auxiliary stream, beside latent stats / fold / normalisers
+                # hidden layer of the mixing net (needs only zz) on the auxiliary stream, beside latent stats / fold / normalisers;
+                # the bf16 operand [hm | zz] of the mixture GEMM in one conversion pass after it
                 with self._branch(g, "hm"):
                     self._hidden_mix(g, w, B, tr, zzp)
-                    L.check(lib.spv_to_bf16_block(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, HD, HD, self._stream()),
-                            "spv_to_bf16_block")
-                # latent columns of the bf16 operand [hm | zz]: all the softmax statistics need
-                L.check(lib.spv_to_bf16_block(zzp, KMIX, w.amixb.data_ptr() + 2 * HD, w.KMp, B, KZ, w.KMp - HD, st),
-                        "spv_to_bf16_block")
+                    L.check(lib.spv_to_bf16(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX, self._stream()), "spv_to_bf16")
             L.check(lib.spv_dec_fold(fold, KMIX, B, G, P, S, tr, DEC_BN_EPS, DEC_BN_MOM, wz, w.KMp if self.fused_nb else 0,
-                                     w.Gp, HD, st), "spv_dec_fold")
+                                     w.Gp, HD, L.ptr(w.wzf) if self.fused_nb else None, L.ptr(w.zcb) if self.fused_nb else None, st),
+                    "spv_dec_fold")
             if self.fused_nb:  # softmax normalisers on the tensor cores (main stream: latent stats -> fold -> normalisers)
                 self._join(g, "lib")
-                L.check(lib.spv_dec_stats_tc(L.ptr(w.amixb), w.KMp, L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.genec), L.ptr(w.lib),
-                                             L.ptr(w.part_stats), L.ptr(w.rowc), B, G, HD, P, S, st), "spv_dec_stats_tc")
+                L.check(lib.spv_dec_stats_tc(L.ptr(w.zcb), L.ptr(w.wzf), w.Gp, L.ptr(w.genec), L.ptr(w.lib),
+                                             L.ptr(w.part_stats), L.ptr(w.rowc), B, G, P, S, st), "spv_dec_stats_tc")
                 self._join(g, "hm")
             else:
                 self._hidden_mix(g, w, B, tr, zzp)
@@ -588,8 +589,8 @@ class StepEngine:
                 evs[0].record()
             if self.bf16:
                 if self.fused_nb:
-                    L.check(lib.spv_dec_nb_fwd_tc(src, dptrs, ldx, L.ptr(w.amixb), w.KMp, L.ptr(w.Wstack), w.KMp, w.Gp, B, G,
-                                                  HD, P, S, 0, st), "spv_dec_nb_fwd_tc")  # backward recomputes pi
+                    L.check(lib.spv_dec_nb_fwd_tc(src, dptrs, ldx, L.ptr(w.amixb), w.KMp, L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.zcb),
+                                                  L.ptr(w.wzf), B, G, HD, P, S, 0, st), "spv_dec_nb_fwd_tc")  # backward recomputes pi
                     if evs is not None:
                         evs[1].record()
                         evs = None
@@ -726,7 +727,7 @@ class StepEngine:
             if self.fused_nb:
                 # logits recomputed on the tensor cores, gradients in the TMEM epilogue -> D3 = [dpi | dyp | dys] (bf16)
                 L.check(lib.spv_dec_nb_bwd_tc(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, L.ptr(w.amixb), w.KMp,
-                                              L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.D3), B, G, HD, P, S,
+                                              L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.zcb), L.ptr(w.wzf), L.ptr(w.D3), B, G, HD, P, S,
                                               -float(grad_scale) / B, L.ptr(w.colsum), st), "spv_dec_nb_bwd_tc")
                 Gp3 = 3 * w.Gp
                 # d zz through the two softmax branches: [dyp | dys] against the folded weights' latent columns (K = 2 Gp,

@@ -63,6 +63,41 @@ def test_tc_gemm(a_mn, b_mn, M, N, K):
         assert err < 1e-4, (splits, err)
 
 
+@pytest.mark.parametrize("a_mn,b_mn,M,N,K", [(0, 0, 512, 256, 5000), (1, 1, 256, 5000, 512), (0, 0, 100, 40, 333)])
+def test_tc_gemm_split_is_fp32_grade(a_mn, b_mn, M, N, K):
+    """spv_tc_gemm_split (hi.hi + hi.lo + lo.hi on bf16 pairs) against float64 on fp32 operands: ~2^-16 per operand, where the
+    plain bf16 GEMM of the same operands is at 2^-9.  Shapes of the encoder fc1 forward / weight gradient at C2."""
+    from spvipes_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    r8 = lambda x: (x + 7) // 8 * 8
+    Af = torch.rand(M, K, generator=g, device="cuda") * 3          # like log1p(counts): non-negative, no cancellation help
+    Bf = (torch.rand(N, K, generator=g, device="cuda") * 2 - 1) * 0.02
+    def planes(X, mn):
+        Xs = X.t().contiguous() if mn else X
+        hi = torch.zeros(Xs.shape[0], r8(Xs.shape[1]), device="cuda", dtype=torch.bfloat16)
+        lo = torch.zeros_like(hi)
+        L.check(lib.spv_to_bf16_split(Xs.data_ptr(), Xs.stride(0), hi.data_ptr(), lo.data_ptr(), hi.stride(0), Xs.shape[0], Xs.shape[1],
+                                      _stream()), "spv_to_bf16_split")
+        return hi, lo
+    Ah, Al = planes(Af, a_mn)
+    Bh, Bl = planes(Bf, b_mn)
+    want = Af.double() @ Bf.double().t()
+    ws = torch.empty(8 * M * N, device="cuda")
+    for splits in (1, 4):
+        C = torch.full((M, N), float("nan"), device="cuda")
+        L.check(lib.spv_tc_gemm_split(a_mn, b_mn, Ah.data_ptr(), Al.data_ptr(), Ah.stride(0), Bh.data_ptr(), Bl.data_ptr(), Bh.stride(0),
+                                      C.data_ptr(), N, M, N, K, None, 0, 0, splits, ws.data_ptr(), _stream()), "spv_tc_gemm_split")
+        torch.cuda.synchronize()
+        err = float((C.double() - want).abs().max() / want.abs().max())
+        assert err < 2e-5, (splits, err)
+    C1 = torch.empty(M, N, device="cuda")
+    L.check(lib.spv_tc_gemm(a_mn, b_mn, Ah.data_ptr(), Ah.stride(0), Bh.data_ptr(), Bh.stride(0), C1.data_ptr(), N, M, N, K, None, 0, 0, 1,
+                            None, _stream()), "spv_tc_gemm")
+    torch.cuda.synchronize()
+    assert float((C1.double() - want).abs().max() / want.abs().max()) > 10 * err  # the plain bf16 product is far coarser
+
+
 @pytest.mark.parametrize("tb", [1, 0])
 @pytest.mark.parametrize("M,N,K,batch", [(512, 128, 128, 2), (512, 50, 128, 1), (512, 256, 35, 1), (300, 35, 256, 1), (77, 20, 9, 1)])
 def test_smallk_gemm(tb, M, N, K, batch):
@@ -123,19 +158,24 @@ def test_adam_ranges_and_staging():
     def run(ranges):
         p, m, v = p0.clone(), m0.clone(), v0.clone()
         stage = torch.full((rows, 40), 5.0, device="cuda", dtype=torch.bfloat16)
+        stage_lo = torch.full((rows, 40), 5.0, device="cuda", dtype=torch.bfloat16)
         for lo, hi in ranges:
-            segs = [(off - lo, rows, cols, stage, 40)] if (off < hi and lo < off + rows * cols) else []  # any overlap
+            segs = [(off - lo, rows, cols, stage, 40, stage_lo)] if (off < hi and lo < off + rows * cols) else []  # any overlap
             L.check(lib.spv_adam(p.data_ptr() + 4 * lo, gr.data_ptr() + 4 * lo, m.data_ptr() + 4 * lo, v.data_ptr() + 4 * lo, hi - lo,
                                  lr, b1, b2, eps, wd, 1.0, step.data_ptr(), None, len(segs), L.ll_array([s[0] for s in segs]),
                                  L.int_array([s[1] for s in segs]), L.int_array([s[2] for s in segs]),
-                                 L.ptr_array([s[3] for s in segs]), L.ll_array([s[4] for s in segs]), 0, _stream()), "spv_adam")
+                                 L.ptr_array([s[3] for s in segs]), L.ptr_array([s[5] for s in segs]),
+                                 L.ll_array([s[4] for s in segs]), 0, _stream()), "spv_adam")
         torch.cuda.synchronize()
-        return p, m, v, stage
+        return p, m, v, torch.stack([stage, stage_lo])
 
-    pa, ma, va, sa = run([(0, n)])
-    pb, mb, vb, sb = run([(0, 1000), (1000, 2048), (2048, n)])
-    assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb) and torch.equal(sa, sb)
-    assert torch.equal(sa[:, :cols], pa[off:off + rows * cols].view(rows, cols).bfloat16())
+    pa, ma, va, sa2 = run([(0, n)])
+    pb, mb, vb, sb2 = run([(0, 1000), (1000, 2048), (2048, n)])
+    assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb) and torch.equal(sa2, sb2)
+    sa, sa_lo = sa2[0], sa2[1]
+    blk = pa[off:off + rows * cols].view(rows, cols)
+    assert torch.equal(sa[:, :cols], blk.bfloat16())
+    assert torch.equal(sa_lo[:, :cols], (blk - blk.bfloat16().float()).bfloat16())  # residual plane of the split-operand GEMM
     assert float((sa[:, cols:] - 5.0).abs().max()) == 0.0
     gd = gr.double() + wd * p0.double()
     m_ref = b1 * m0.double() + (1 - b1) * gd
@@ -147,6 +187,6 @@ def test_adam_ranges_and_staging():
     ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
     p, m, v = p0.clone(), m0.clone(), v0.clone()
     L.check(lib.spv_adam(p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, b1, b2, eps, wd, 1.0, step2.data_ptr(),
-                         ticket.data_ptr(), 0, None, None, None, None, None, 0, _stream()), "spv_adam")
+                         ticket.data_ptr(), 0, None, None, None, None, None, None, 0, _stream()), "spv_adam")
     torch.cuda.synchronize()
     assert int(step2) == t and int(ticket) == 0 and torch.equal(p, pa)

@@ -250,17 +250,3 @@ def test_ot_modes_hidden256_against_oracle(mode, precision):
     grads = {k: sd[k].grad for k in rs.param_names(sd)}
     worst, where = grad_errors({k: v.cpu() for k, v in eng.grad_dict().items()}, grads)
     assert worst < GRAD_TOL, (worst, where)
-
-
-def test_persistent_nb_kernel_opt_in():
-    """SPV_NB_PERSISTENT=1 selects the persistent forward kernel (nb_ptc.cu) when the library is first used, so the check runs
-    in a child process: the golden forward / backward cases and the C1-shaped oracle case with that kernel."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SPV_NB_PERSISTENT="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity_bf16.py"), "-q", "-x", "-m", "gpu",
-                        "-k", "bf16_forward_matches_golden or bf16_backward_matches_golden or c1_shape_against_oracle"],
-                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
