@@ -82,6 +82,11 @@ int spv_enc_mid_bwd(const float* dr, long long ld_dr, const float* Whp, const fl
  * elements, multiples of 8, bases 16-byte aligned.  Same call sites as spv_gemm, for the "bf16 tensor-core path". */
 int spv_tc_gemm(int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb, float* C, long long ldc, int M,
                 int N, int K, const float* bias, int relu, int accumulate, int splits, float* ws, void* stream);
+/* general form of spv_tc_gemm: fmt 0 = bf16 operands, 3 = fp16 operands (mixed formats trap on sm_100: SPV_ERR_ARG);
+ * C (+)= act(alpha * A B^T + bias) */
+int spv_tc_gemm_ex(int fmt, float alpha, int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb, float* C,
+                   long long ldc, int M, int N, int K, const float* bias, int relu, int accumulate, int splits, float* ws,
+                   void* stream);
 /* the same with split-bf16 operands x ~ hi + lo (lo = bf16(x - hi), same layout and pitch as hi): hi.hi + hi.lo + lo.hi on
  * tcgen05 into one TMEM accumulator, ~16 mantissa bits per operand.  The K = genes contractions of the encoder's first layer
  * (nn/networks.py:119 forward and its weight gradient): north_star's 1e-3 gate on the latent statistics holds on this path. */
@@ -90,6 +95,8 @@ int spv_tc_gemm_split(int a_mn, int b_mn, const void* A, const void* A_lo, long 
                       int splits, float* ws, void* stream);
 /* bf16 staging of GEMM operands: dst[r, :C] = bf16(src[r, :C]), zero padded up to ld_dst */
 int spv_to_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, int R, int C, void* stream);
+/* fp16 staging (decoder operands of the fused tensor-core path) */
+int spv_to_f16(const float* src, long long ld_src, void* dst, long long ld_dst, int R, int C, void* stream);
 /* ... as a (hi, lo) pair for spv_tc_gemm_split */
 int spv_to_bf16_split(const float* src, long long ld_src, void* dst_hi, void* dst_lo, long long ld_dst, int R, int C, void* stream);
 /* column block: dst[r, :C] = bf16(src[r, :C]), zeros up to `width`; the other columns of dst (row pitch ld_dst) are untouched */
@@ -155,7 +162,8 @@ int spv_loss(const float* rec0, const float* rec1, const float* klp0, const floa
 #define SPV_DEC_GENEC_ROWS 19
 /* wz_bf16 (optional): rows [Gp, 3 Gp) of the stacked bf16 tensor-core operand [3 Gp, ld_wz] (rows [0, G): mixture weight,
  * [Gp, Gp + G): folded private weights in the latent columns HD .., [2 Gp, 2 Gp + G): folded shared weights) - the B operand
- * of the input-gradient GEMM of the two branches.
+ * of the input-gradient GEMM of the two branches; written as FP16 when wz_f16 / zc_f16 are given (the fused tensor-core
+ * decoder runs on fp16 operands throughout), else as bf16.
  * wz_f16 / zc_f16 (optional, both or none): fp16 operands of the branch-logit MMAs of the tensor-core sweeps: wz_f16
  * [2 Gp, 64] folded weights (private rows, columns [0, P); shared rows from Gp, columns [P, P + S)), zc_f16 [B, 64] the
  * CENTRED latents zz - mean(zz) (eval mode: zz); genec rows GC_CPLC / GC_CSLC hold the matching shifts. */
@@ -172,8 +180,9 @@ int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld
                    float scale, float* colsum, void* dpi_bf16, long long ld_dpi_bf16, void* stream);
 /* tensor-core version of phase 2 of spv_dec_nb_fwd: the mixture GEMM and the two softmax-branch logit GEMMs on tcgen05
  * (operands via TMA, fp32 accumulators in TMEM) with the NB-mixture log-likelihood fused into the TMEM epilogue.
- * amix_bf16 [B, ld_amixb] = [hm | zz]; wstack_bf16 [>= G, ld_w]: the mixture weight; zc_f16 [B, 64], wz_f16 [2 Gp, 64]: the
- * fp16 branch operands written by spv_dec_fold.  part_nb (ptrs[11]) needs spv_dec_nb_part_floats(B, G) floats.
+ * amix_bf16 [B, ld_amixb] = [hm | zz] and wstack_bf16 [>= G, ld_w] (the mixture weight) hold FP16 values (spv_to_f16 /
+ * spv_adam staging; the parameter names predate the switch); zc_f16 [B, 64], wz_f16 [2 Gp, 64]: the fp16 branch operands
+ * written by spv_dec_fold.  part_nb (ptrs[11]) needs spv_dec_nb_part_floats(B, G) floats.
  * store_pi: also write the mixture logits to ptrs[10] (fp32). */
 int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
                       const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16, int B, int G,
@@ -188,8 +197,9 @@ long long spv_dec_nb_part_floats(int B, int G);
 /* rec[b] (ptrs[16] of the forward) and the softmax-backward row sums rowc[:, 2:4] from the row partials part_nb that
  * spv_dec_nb_fwd_tc wrote for the same B, G, HD */
 int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, int HD, float* rowc, float* rec, void* stream);
-/* tensor-core backward sweep: recomputes the three logit tiles on tcgen05 and writes D3 = [dpi | dyp | dys] (bf16
- * [B, 3 Gp], operand of the gradient GEMMs) and colsum [4, G] (column sums of dyp, dys, dpi, d loss / d theta);
+/* tensor-core backward sweep: recomputes the three logit tiles on tcgen05 and writes D3 = [dpi | dyp | dys] / |scale| (FP16
+ * [B, 3 Gp], operand of the gradient GEMMs, which apply |scale| as spv_tc_gemm_ex's alpha) and colsum [4, G] (column sums
+ * of dyp, dys, dpi, d loss / d theta, true scale);
  * ptrs[15] = colpart workspace [ceil(B/128), 4, G].  scale = - grad_scale / B.  rowc (ptrs[9], [B, 4] floats) must be
  * 16-byte aligned (SPV_ERR_ARG otherwise): a row is read as one float4. */
 int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
@@ -202,10 +212,12 @@ int spv_dec_gene_bwd_parts(int G);
 int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, int G, int P, int S, void* stream);
 /* d zz = dmix (latent columns of d [hm | zz]) + dzraw (optional further addends [B, P+S]: softmax-branch and hidden-layer
  * input gradients when they are not in dmix) - BatchNorm coupling terms, the latter summed from the `nparts` per-CTA
- * partials (vpart [nparts, P+S], mpart [nparts, (P+S)^2]) that spv_dec_gene_bwd writes (its last two ptrs) */
+ * partials (vpart [nparts, P+S], mpart [nparts, (P+S)^2]) that spv_dec_gene_bwd writes (its last two ptrs).
+ * centre_raw != 0 (tensor-core path): the mean-coupling term is taken as the column mean of dzraw itself instead of vpart, so
+ * that the coherent operand-rounding error of the GEMM that produced dzraw cancels instead of surviving as a column mean. */
 int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* vpart, const float* mpart,
                         int nparts, const float* zz, long long ld_zz, const float* zmean, float* dzz, int B, int P, int S,
-                        void* stream);
+                        int centre_raw, void* stream);
 
 /* *step += 1 on the stream: the optimiser's step count, and (a separate counter) the Philox stream position that the noise /
  * dropout kernels read - the two must not share a counter, the backward regenerates its noise from the forward's value. */
@@ -215,13 +227,14 @@ int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw
  * nseg (<= 8) staging segments, host arrays: the parameter block [seg_begin, seg_begin + seg_rows * seg_cols) viewed as
  * [seg_rows, seg_cols] is also written, updated, as bf16 into seg_dst (row pitch seg_ld): the tensor-core operand copies of
  * the large weights, so that the next step does not start with conversion kernels; seg_dst_lo (optional array, entries may
- * be NULL): the bf16 residual plane of a segment (split-operand GEMM), same pitch.  p, g, m, v 16-byte aligned.
+ * be NULL): the bf16 residual plane of a segment (split-operand GEMM), same pitch; seg_f16 (optional array): non-zero = the
+ * segment's destination holds fp16 values (decoder operands).  p, g, m, v 16-byte aligned.
  * max_blocks > 0 caps the grid (an update overlapped with other kernels should not occupy every SM). */
 int spv_adam_tick(int* step, void* stream);
 int spv_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float wd,
              float grad_scale, int* step, int* ticket, int nseg, const long long* seg_begin, const int* seg_rows,
-             const int* seg_cols, void* const* seg_dst, void* const* seg_dst_lo, const long long* seg_ld, int max_blocks,
-             void* stream);
+             const int* seg_cols, void* const* seg_dst, void* const* seg_dst_lo, const int* seg_f16, const long long* seg_ld,
+             int max_blocks, void* stream);
 
 #ifdef __cplusplus
 }

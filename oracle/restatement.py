@@ -250,10 +250,22 @@ def _with_cov(x, cov):
     return x if cov is None else torch.cat((x, cov), dim=-1)
 
 
-def encoder(sd, prefix, xl, training, drop_mask, new_stats, cov=None):
+def _relu(pre, key, gates, probe):
+    """ReLU, with two test hooks: `probe` (dict) records the pre-activation under `key`; `gates` (dict) may hold a boolean
+    mask for `key` that REPLACES the sign test (y = pre * gate).  A unit whose pre-activation is zero to within the rounding
+    of the forward pass has an ill-defined gate: a checker comparing gradients fixes those units' gates to the decision the
+    implementation under test took (tests/helpers.py: gate_consistent), every other unit keeps its own sign test."""
+    if probe is not None:
+        probe[key] = pre.detach()
+    if gates is not None and key in gates:
+        return pre * gates[key].to(pre.dtype)
+    return F.relu(pre)
+
+
+def encoder(sd, prefix, xl, training, drop_mask, new_stats, cov=None, gates=None, probe=None):
     """reference Encoder.forward nn/networks.py:110-125; `cov` = one-hot batch covariate appended to the fc1 input (:110-118)."""
-    h = F.relu(F.linear(_with_cov(xl, cov), sd[prefix + ".fc1.weight"], sd[prefix + ".fc1.bias"]))
-    h = F.relu(F.linear(h, sd[prefix + ".fc2.weight"], sd[prefix + ".fc2.bias"]))
+    h = _relu(F.linear(_with_cov(xl, cov), sd[prefix + ".fc1.weight"], sd[prefix + ".fc1.bias"]), prefix + ".fc1", gates, probe)
+    h = _relu(F.linear(h, sd[prefix + ".fc2.weight"], sd[prefix + ".fc2.bias"]), prefix + ".fc2", gates, probe)
     if training and drop_mask is not None:
         h = h * drop_mask  # mask already holds 0 or 1/(1-p)
     outs = []
@@ -266,7 +278,7 @@ def encoder(sd, prefix, xl, training, drop_mask, new_stats, cov=None):
     return loc, lv, torch.exp(0.5 * lv)
 
 
-def decoder(sd, g, z_private, z_shared, library, training, new_stats, cov=None):
+def decoder(sd, g, z_private, z_shared, library, training, new_stats, cov=None, gates=None, probe=None):
     """reference LinearDecoderSPVIPE.forward nn/networks.py:314-325 + scvi FCLayers; `cov` = one-hot batch covariate that
     FCLayers appends to the input of each of the four one-layer nets (n_cat_list at nn/networks.py:203, 217, 245, 256)."""
     p = f"decoder_{g}"
@@ -282,7 +294,7 @@ def decoder(sd, g, z_private, z_shared, library, training, new_stats, cov=None):
     rate_p = torch.exp(library) * torch.softmax(fc("factor_regressor_private", z_private, True), dim=-1)
     rate_s = torch.exp(library) * torch.softmax(fc("factor_regressor_shared", z_shared, True), dim=-1)
     zz = torch.cat([z_private, z_shared], dim=1)
-    hm = F.relu(fc("sigmoid_decoder", zz, True))
+    hm = _relu(fc("sigmoid_decoder", zz, True), f"{p}.sigmoid_decoder", gates, probe)
     mix = fc("mixture", torch.cat([hm, zz], dim=-1), False)
     return rate_p, rate_s, mix
 
@@ -291,7 +303,7 @@ def step(sd: Dict[str, torch.Tensor], x: Sequence[torch.Tensor], *, mode: str, n
          eps_private: Sequence[torch.Tensor], eps_poe: Sequence[torch.Tensor],
          labels: Optional[Sequence] = None, sub: Optional[torch.Tensor] = None,
          drop_masks: Optional[Dict] = None, kl_weight: float = 1.0, training: bool = True,
-         batch_index: Optional[Sequence] = None, n_batch: int = 0):
+         batch_index: Optional[Sequence] = None, n_batch: int = 0, gates: Optional[Dict] = None, probe: Optional[Dict] = None):
     """One forward pass of inference -> generative -> loss for both groups.
 
     x[g]: [B_g, G_g] counts of group g's OWN genes (any float dtype; the reference slices
@@ -300,6 +312,7 @@ def step(sd: Dict[str, torch.Tensor], x: Sequence[torch.Tensor], *, mode: str, n
     label mode, processed_transport_labels in cluster mode).  sub: [B0, B1] sub-plan.
     batch_index / n_batch: per-group batch codes and the number of batches; with n_batch > 1 their one-hot is appended to
     the encoders' fc1 input and to the input of the four decoder nets (module/spVIPESmodule.py:133, 440-446, 748-756).
+    gates / probe: test hooks of the ReLU gates, see _relu (None: plain ReLU everywhere, nothing recorded).
     Returns a dict of every quantity the parity gates name.
     """
     S, P = n_shared, n_private
@@ -311,8 +324,8 @@ def step(sd: Dict[str, torch.Tensor], x: Sequence[torch.Tensor], *, mode: str, n
     cov = [one_hot_batch(batch_index[g] if batch_index is not None else None, n_batch, dt) for g in (0, 1)]
     for g in (0, 1):
         dm = drop_masks or {}
-        priv.append(encoder(sd, f"encoder_{g}_private", xl[g], training, dm.get((g, "private")), new_stats, cov[g]))
-        shared.append(encoder(sd, f"encoder_{g}_shared", xl[g], training, dm.get((g, "shared")), new_stats, cov[g]))
+        priv.append(encoder(sd, f"encoder_{g}_private", xl[g], training, dm.get((g, "private")), new_stats, cov[g], gates, probe))
+        shared.append(encoder(sd, f"encoder_{g}_shared", xl[g], training, dm.get((g, "shared")), new_stats, cov[g], gates, probe))
     s_loc = [shared[0][0], shared[1][0]]
     s_lv = [shared[0][1], shared[1][1]]
     s_sc = [shared[0][2], shared[1][2]]
@@ -336,7 +349,7 @@ def step(sd: Dict[str, torch.Tensor], x: Sequence[torch.Tensor], *, mode: str, n
         c = torch.cat((z_priv, z_poe), dim=-1)  # :733  [private | poe]
         z_private_arg = c[:, S:S + P]  # :753  (quirk Q1)
         z_shared_arg = c[:, :S]  # :754
-        rate_p, rate_s, mix = decoder(sd, g, z_private_arg, z_shared_arg, lib[g], training, new_stats, cov[g])
+        rate_p, rate_s, mix = decoder(sd, g, z_private_arg, z_shared_arg, lib[g], training, new_stats, cov[g], gates, probe)
         theta = torch.exp(sd[f"px_r.{g}"])
         rec = -log_mixture_nb(xl[g], rate_p, rate_s, theta, mix).sum(-1)  # :820-824 (target = log1p counts, Q3)
         klp = kl_std_normal(p_loc, p_sc)

@@ -29,8 +29,10 @@ _SIGS = {
     "spv_enc_mid_bwd": [p, ll, p, p, p, p, ll, p, ll, p, ll, f, p, ll, p, ll, p, ll, i, i, i, i, p],
     "spv_gemm_fused": [i, i, i, i, p, ll, p, p, ll, p, p, ll, i, i, i, i, ll, ll, ll, p, ll, i, i, i, p, p, ll, p, ll, f, f, p, u64, u32, p, ll, p, p, ll, p],
     "spv_tc_gemm": [i, i, p, ll, p, ll, p, ll, i, i, i, p, i, i, i, p, p],
+    "spv_tc_gemm_ex": [i, f, i, i, p, ll, p, ll, p, ll, i, i, i, p, i, i, i, p, p],
     "spv_tc_gemm_split": [i, i, p, p, ll, p, p, ll, p, ll, i, i, i, p, i, i, i, p, p],
     "spv_to_bf16": [p, ll, p, ll, i, i, p],
+    "spv_to_f16": [p, ll, p, ll, i, i, p],
     "spv_to_bf16_split": [p, ll, p, p, ll, i, i, p],
     "spv_counts_to_bf16": [i, p, ll, p, p, p, ll, i, i, p, p],
     "spv_library_size": [i, p, ll, p, i, i, p, p],
@@ -57,9 +59,9 @@ _SIGS = {
     "spv_dec_nb_part_floats": [i, i],
     "spv_dec_stats_tc": [p, p, i, p, p, p, p, i, i, i, i, p],
     "spv_to_bf16_block": [p, ll, p, ll, i, i, i, p],
-    "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, p],
+    "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, i, p],
     "spv_adam_tick": [p, p],
-    "spv_adam": [p, p, p, p, ll, f, f, f, f, f, f, p, p, i, p, p, p, p, p, p, i, p],
+    "spv_adam": [p, p, p, p, ll, f, f, f, f, f, f, p, p, i, p, p, p, p, p, p, p, i, p],
 }
 
 _lib = None

@@ -142,6 +142,7 @@ struct FoldP {
     __nv_bfloat16* wfold_bf16;
     long ld_wz;
     int Gp, HD;
+    int stack_f16;  // the stacked operand holds fp16 (the fused tensor-core decoder) instead of bf16 values
     // optional fp16 operands of the branch-logit MMAs (forward / statistics / backward sweeps): wz_f16 [2 Gp, 64] = folded
     // private weights in columns [0, P) of rows [0, G), folded shared weights in columns [P, P + S) of rows [Gp, Gp + G);
     // zc_f16 [B, 64] = zz - m (m = batch mean when training, else 0) in columns [0, P + S).  Centring makes the shift exactly
@@ -271,7 +272,11 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
         const float wf = sA[(pr ? 0 : 32) + gl] * (pr ? sWp[gl * p.P + k] : sWs[gl * p.S + (k - p.P)]);
         const int g = g0 + gl;
         p.wfold[(long)g * KZ + k] = wf;
-        if (p.wfold_bf16) p.wfold_bf16[((long)(pr ? 0 : 1) * p.Gp + g) * p.ld_wz + p.HD + k] = __float2bfloat16(wf);
+        if (p.wfold_bf16) {
+            const long at = ((long)(pr ? 0 : 1) * p.Gp + g) * p.ld_wz + p.HD + k;
+            if (p.stack_f16) reinterpret_cast<__half*>(p.wfold_bf16)[at] = __float2half_rn(wf);
+            else p.wfold_bf16[at] = __float2bfloat16(wf);
+        }
         if (p.wz_f16) p.wz_f16[((long)(pr ? 0 : 1) * p.Gp + g) * 64 + k] = __float2half_rn(wf);
     }
     if (p.zc_f16) {  // centred latents: the CTAs share the rows
@@ -310,6 +315,7 @@ extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int
     if ((wz_f16 != nullptr) != (zc_f16 != nullptr) || (wz_f16 && KZ > 64)) return SPV_ERR_ARG;
     p.wz_f16 = reinterpret_cast<__half*>(wz_f16); p.zc_f16 = reinterpret_cast<__half*>(zc_f16);
     p.zz = zz; p.ld_zz = ld_zz;
+    p.stack_f16 = wz_f16 != nullptr;  // fp16 branch operands requested: the whole decoder runs on fp16 operands
     p.G = G; p.P = P; p.S = S; p.B = B; p.training = training; p.eps = eps; p.momentum = momentum;
     size_t sm2 = (size_t)(KZ + KZ * KZ + FOLD_GENES_PER_CTA * (2 * KZ + 11)) * sizeof(float);
     if (sm2 > 48 * 1024) cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
@@ -515,9 +521,10 @@ __global__ void __launch_bounds__(DZC_THREADS) dzz_combine_kernel(const float* _
                                                                   const float* __restrict__ mpart, int nparts,
                                                                   const float* __restrict__ zz, long ld_zz,
                                                                   const float* __restrict__ zmean, float* __restrict__ dzz, int B,
-                                                                  int P, int S) {
+                                                                  int P, int S, int centre_raw) {
     __shared__ float red[8][100];
     __shared__ float srow[100];  // [0, n): M[c, lo + .],  [n]: v1[c]
+    __shared__ float cred[8];
     const int KZ = P + S;
     const int c = blockIdx.x;
     const int lo = c < P ? 0 : P, n = c < P ? P : S;
@@ -541,6 +548,24 @@ __global__ void __launch_bounds__(DZC_THREADS) dzz_combine_kernel(const float* _
         srow[threadIdx.x] = s;
     }
     __syncthreads();
+    if (centre_raw) {
+        // v1 is the column mean of the uncorrected input gradient sum_g a dy W (BatchNorm backward: the corrected one sums to
+        // zero over the minibatch).  dzraw came out of a reduced-precision GEMM while vpart is exact fp32, so subtracting the
+        // exact v1 would leave the GEMM's coherent rounding error as a spurious column mean; the mean of dzraw itself cancels
+        // exactly (its other addend, the hidden layer's BatchNorm backward, has zero column mean as well).
+        float s = 0.0f;
+        for (int t = threadIdx.x; t < B; t += DZC_THREADS) s += dzraw[(long)t * KZ + c];
+        s = warp_sum(s);
+        if (lane == 0) cred[q] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tot += cred[i];
+            srow[n] = tot / (float)B;
+        }
+        __syncthreads();
+    }
     const int b = blockIdx.y * DZC_THREADS + threadIdx.x;
     if (b >= B) return;
     const float* zrow = zz + (long)b * ld_zz + lo;
@@ -551,12 +576,13 @@ __global__ void __launch_bounds__(DZC_THREADS) dzz_combine_kernel(const float* _
 
 extern "C" int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* vpart, const float* mpart,
                                    int nparts, const float* zz, long long ld_zz, const float* zmean, float* dzz, int B, int P,
-                                   int S, void* stream) {
+                                   int S, int centre_raw, void* stream) {
     if (!dmix || !vpart || !mpart || !zz || !zmean || !dzz || B <= 0 || P <= 0 || S <= 0 || nparts <= 0 || P > 96 || S > 96)
         return SPV_ERR_ARG;
+    if (centre_raw && !dzraw) return SPV_ERR_ARG;
     dim3 grid(P + S, (B + DZC_THREADS - 1) / DZC_THREADS);
     dzz_combine_kernel<<<grid, DZC_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dmix, ld_dmix, dzraw, vpart, mpart, nparts,
-                                                                                         zz, ld_zz, zmean, dzz, B, P, S);
+                                                                                         zz, ld_zz, zmean, dzz, B, P, S, centre_raw);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

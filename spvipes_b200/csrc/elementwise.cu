@@ -3,6 +3,7 @@
 // ReLU/dropout backward, Adam.  Reference: nn/networks.py:119-125 (Encoder.forward),
 // module/spVIPESmodule.py:435 (library), scvi FCLayers BatchNorm1d(momentum=0.01, eps=0.001).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "../../include/spvipes_b200.h"
 
@@ -327,6 +328,7 @@ struct AdamSegs {
     __nv_bfloat16* dst[ADAM_MAX_SEGS];
     __nv_bfloat16* dst_lo[ADAM_MAX_SEGS];  // optional bf16 residual plane (split-operand GEMMs), same pitch
     int cols[ADAM_MAX_SEGS];
+    int f16[ADAM_MAX_SEGS];                // destination holds fp16 instead of bf16 values (no residual plane then)
     float inv_cols[ADAM_MAX_SEGS];
     int n;
 };
@@ -341,6 +343,10 @@ __device__ __forceinline__ void adam_stage(const AdamSegs& sg, long long idx, fl
             int c = j - r * cols;
             if (c < 0) { --r; c += cols; }
             else if (c >= cols) { ++r; c -= cols; }
+            if (sg.f16[s]) {
+                reinterpret_cast<__half*>(sg.dst[s])[(long long)r * sg.ld[s] + c] = __float2half_rn(val);
+                return;
+            }
             const __nv_bfloat16 hi = __float2bfloat16(val);
             sg.dst[s][(long long)r * sg.ld[s] + c] = hi;
             if (sg.dst_lo[s]) sg.dst_lo[s][(long long)r * sg.ld[s] + c] = __float2bfloat16(val - __bfloat162float(hi));
@@ -411,7 +417,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 extern "C" int spv_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                         float wd, float grad_scale, int* step, int* ticket, int nseg, const long long* seg_begin,
                         const int* seg_rows, const int* seg_cols, void* const* seg_dst, void* const* seg_dst_lo,
-                        const long long* seg_ld, int max_blocks, void* stream) {
+                        const int* seg_f16, const long long* seg_ld, int max_blocks, void* stream) {
     if (!p || !g || !m || !v || !step || n <= 0 || nseg < 0 || nseg > ADAM_MAX_SEGS) return SPV_ERR_ARG;
     if (nseg > 0 && (!seg_begin || !seg_rows || !seg_cols || !seg_dst || !seg_ld)) return SPV_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
@@ -428,6 +434,7 @@ extern "C" int spv_adam(float* p, const float* g, float* m, float* v, long long 
         sg.ld[s] = seg_ld[s];
         sg.dst[s] = reinterpret_cast<__nv_bfloat16*>(seg_dst[s]);
         sg.dst_lo[s] = seg_dst_lo ? reinterpret_cast<__nv_bfloat16*>(seg_dst_lo[s]) : nullptr;
+        sg.f16[s] = seg_f16 ? seg_f16[s] : 0;
         sg.cols[s] = seg_cols[s];
         sg.inv_cols[s] = 1.0f / (float)seg_cols[s];
     }

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
         __syncwarp();
         tc::fence_after_sync();
         tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-        constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, false, false);
+        constexpr uint32_t idesc = tc::idesc_f16(BM, BN);  // every operand of the fused decoder is fp16
         constexpr uint32_t idesc_z = tc::idesc_f16(BM, BN);
         const int s_z = num_kb % STAGES;  // ring slot of the branch k-block (the centred latents)
         if (lane == 0) {

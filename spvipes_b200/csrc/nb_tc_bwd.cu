@@ -5,6 +5,7 @@
 //   dyp, dys [B, G] f32 (gradients w.r.t. the two folded BatchNorm outputs = softmax logits),
 //   colpart [nTB, 4, G]: per-128-row-tile column sums of dyp, dys, dpi and d loss / d theta.
 // Reference: autograd of nn/networks.py:314-325 + scvi log_mixture_nb (module/spVIPESmodule.py:823-824).
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 #include "nb_math.cuh"
 #include "decoder_common.cuh"
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
         __syncwarp();
         tc::fence_after_sync();
         tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-        constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, false, false);
+        constexpr uint32_t idesc = tc::idesc_f16(BM, BN);  // every operand of the fused decoder is fp16
         constexpr uint32_t idesc_z = tc::idesc_f16(BM, BN);
         const int s_z = num_kb % STAGES;  // ring slot of the branch k-block (the centred latents)
         if (lane == 0) {
@@ -291,12 +292,13 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
                 for (int blk = 0; blk < 3; ++blk) {
                     __nv_bfloat16* dst = d3 + (long)blk * p.Gp;
                     const float* v = vals[blk];
+                    __half* dsth = reinterpret_cast<__half*>(dst);
                     if (vec_b && g + 3 < p.G) {
-                        __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+                        __half2 lo = __floats2half2_rn(v[0], v[1]), hi = __floats2half2_rn(v[2], v[3]);
                         *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
                     } else {
                         for (int jj = 0; jj < 4; ++jj)
-                            if (g + jj < p.G) dst[jj] = __float2bfloat16(v[jj]);
+                            if (g + jj < p.G) dsth[jj] = __float2half_rn(v[jj]);
                     }
                 }
             }
@@ -354,19 +356,20 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
     }
 }
 
-__global__ void colpart_reduce_tc_kernel(const float* __restrict__ colpart, int nTB, int G, float* __restrict__ colsum) {
+__global__ void colpart_reduce_tc_kernel(const float* __restrict__ colpart, int nTB, int G, float* __restrict__ colsum, float mult) {
     long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i >= 4L * G) return;
     float s = 0.0f;
     for (int t = 0; t < nTB; ++t) s += colpart[(long)t * 4 * G + i];
-    colsum[i] = s;
+    colsum[i] = s * mult;
 }
 
 }  // namespace
 
 // ptrs: the SPV_DEC_NPTR list (X, rows, -, -, -, bm, genec, lib, -, rowc, -, -, -, -, -, colpart [ceil(B/128), 4, G], -).
-// d3_bf16 [B, 3 * Gp] receives [d loss / d pi | d loss / d y_private | d loss / d y_shared] (bf16, the A operand of the
-// gradient GEMMs).  Operands as spv_dec_nb_fwd_tc.  colsum [4, G] = column sums of dyp, dys, dpi, dtheta.
+// d3_bf16 [B, 3 * Gp] receives [d loss / d pi | d loss / d y_private | d loss / d y_shared] / |scale| as FP16 (the A operand
+// of the gradient GEMMs, which multiply by |scale|: spv_tc_gemm_ex fmt 3).  Operands as spv_dec_nb_fwd_tc.  colsum [4, G] =
+// column sums of dyp, dys, dpi, dtheta (true scale).
 extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
                                  const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16,
                                  void* d3_bf16, int B, int G, int HD, int P, int S, float scale, float* colsum, void* stream) {
@@ -391,7 +394,10 @@ extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx
     p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
     p.lib = (const float*)ptrs[7]; p.rowc = (const float*)ptrs[9];
     p.colpart = (float*)ptrs[15]; p.dpi = reinterpret_cast<__nv_bfloat16*>(d3_bf16); p.ld_dpi = 3L * Gp;
-    p.B = B; p.G = G; p.K = K; p.Gp = Gp; p.scale = scale;
+    // The sweep works in natural units (sign only): D3 holds d / |scale| in fp16 - |d pi| <= 1, |d y| bounded by log1p(count)
+    // + theta, all well inside fp16's normal range whatever the minibatch size - and the consumers apply |scale|: the
+    // column sums below, the gradient GEMMs through spv_tc_gemm_ex's alpha.
+    p.B = B; p.G = G; p.K = K; p.Gp = Gp; p.scale = scale < 0.0f ? -1.0f : 1.0f;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     static bool configured[64] = {};
     int dev = 0;
@@ -407,7 +413,7 @@ extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx
     else if (src == SPV_SRC_F32_LOG1P) nb_tc_bwd_kernel<SPV_SRC_F32_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, mzc, p);
     else return SPV_ERR_ARG;
     SPV_CHECK_LAUNCH();
-    colpart_reduce_tc_kernel<<<(4 * G + 255) / 256, 256, 0, st>>>(p.colpart, (int)grid.y, G, colsum);
+    colpart_reduce_tc_kernel<<<(4 * G + 255) / 256, 256, 0, st>>>(p.colpart, (int)grid.y, G, colsum, fabsf(scale));
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

@@ -130,6 +130,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn_major,
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// general form: per-operand format (0 = F16, 1 = BF16) and major-ness
+__host__ __device__ constexpr uint32_t idesc_16(int M, int N, bool a_mn_major, bool b_mn_major, bool a_bf16, bool b_bf16) {
+    return (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) | ((a_mn_major ? 1u : 0u) << 15) |
+           ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // instruction descriptor for kind::f16, F16 x F16 -> F32 (K-major operands)
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -6,6 +6,7 @@
 // (dW = dY^T X, dX = dY W) run without materialising transposes.
 // This is the "bf16 tensor-core path" of BASELINE.json's north_star (parity gate 1e-2); the fp32 SIMT path of
 // gemm_simt.cu is the 1e-4 mode.  Replaces the cuBLAS GEMMs behind nn.Linear in reference nn/networks.py:119, 323-325.
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 #include "../../include/spvipes_b200.h"
 
@@ -21,6 +22,8 @@ struct TcParams {
     float* ws;
     long ldc;
     int M, N, K, relu, accumulate, splits, kb_per_split;
+    uint32_t idesc;  // instruction descriptor (operand formats are a run-time choice: bf16 or fp16 per operand)
+    float alpha;     // C = alpha * (A B^T) + bias
 };
 
 // SPLIT: both operands are given as a bf16 pair (hi, lo) with x ~ hi + lo (lo = bf16(x - hi)), and the product is
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (tc::elect_one()) {
-            constexpr uint32_t idesc = tc::idesc_bf16(BM, BN, A_MN, B_MN);
+            const uint32_t idesc = p.idesc;
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const __grid_consta
             if (n_ok) {
 #pragma unroll 8
                 for (int rr = 0; rr < rows; ++rr) {
-                    float v = stage[rr * 33 + lane] + bv;
+                    float v = fmaf(stage[rr * 33 + lane], p.splits == 1 ? p.alpha : 1.0f, bv);
                     if (p.relu && p.splits == 1) v = fmaxf(v, 0.0f);
                     if (acc) v += dst[(size_t)rr * ld];
                     dst[(size_t)rr * ld] = v;
@@ -219,6 +222,7 @@ __global__ void tc_splitk_reduce_kernel(TcParams p) {
         long m = i / p.N;
         float v = 0.0f;
         for (int s = 0; s < p.splits; ++s) v += p.ws[(size_t)s * total + i];
+        v *= p.alpha;
         if (p.bias) v += p.bias[n];
         if (p.relu) v = fmaxf(v, 0.0f);
         float* c = p.C + m * p.ldc + n;
@@ -276,7 +280,7 @@ int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap&
 
 int tc_gemm_impl(int a_mn, int b_mn, const void* A, const void* A_lo, long long lda, const void* B, const void* B_lo, long long ldb,
                  float* C, long long ldc, int M, int N, int K, const float* bias, int relu, int accumulate, int splits, float* ws,
-                 void* stream) {
+                 void* stream, int fmt = 0, float alpha = 1.0f) {
     if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return SPV_ERR_ARG;
     const bool split_ops = A_lo != nullptr;
     if (split_ops != (B_lo != nullptr)) return SPV_ERR_ARG;
@@ -312,6 +316,8 @@ int tc_gemm_impl(int a_mn, int b_mn, const void* A, const void* A_lo, long long 
     TcParams p;
     p.C = C; p.bias = bias; p.ws = ws; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu; p.accumulate = accumulate;
     p.splits = splits; p.kb_per_split = kb_per;
+    p.idesc = tc::idesc_16(BM, BN, a_mn != 0, b_mn != 0, !(fmt & 1), !(fmt & 2));
+    p.alpha = alpha;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (split_ops) {
         if (BN == 64) return dispatch_major<64, true>(a_mn, b_mn, ma, mb, mal, mbl, p, st);
@@ -345,6 +351,14 @@ extern "C" int spv_tc_gemm(int a_mn, int b_mn, const void* A, long long lda, con
                            long long ldc, int M, int N, int K, const float* bias, int relu, int accumulate, int splits,
                            float* ws, void* stream) {
     return tc_gemm_impl(a_mn, b_mn, A, nullptr, lda, B, nullptr, ldb, C, ldc, M, N, K, bias, relu, accumulate, splits, ws, stream);
+}
+
+// general form: fmt 0 = both operands bf16, 3 = both fp16; C = alpha * A B^T (+ bias ...)
+extern "C" int spv_tc_gemm_ex(int fmt, float alpha, int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb,
+                              float* C, long long ldc, int M, int N, int K, const float* bias, int relu, int accumulate, int splits,
+                              float* ws, void* stream) {
+    if (fmt != 0 && fmt != 3) return SPV_ERR_ARG;  // tcgen05 kind::f16 traps on mixed bf16 / fp16 operands (measured on B200)
+    return tc_gemm_impl(a_mn, b_mn, A, nullptr, lda, B, nullptr, ldb, C, ldc, M, N, K, bias, relu, accumulate, splits, ws, stream, fmt, alpha);
 }
 
 // the same with split-bf16 operands: A ~ A + A_lo, B ~ B + B_lo (same layout and pitch as their hi planes); three MMAs per
@@ -388,6 +402,25 @@ extern "C" int spv_to_bf16(const float* src, long long ld_src, void* dst, long l
     int blocks = (int)min((long)148 * 16, (total + 255) / 256);
     to_bf16_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), nullptr,
                                                                                ld_dst, R, C);
+    SPV_CHECK_LAUNCH();
+    return SPV_OK;
+}
+
+__global__ void to_f16_kernel(const float* __restrict__ src, long ld_src, __half* __restrict__ dst, long ld_dst, int R, int C) {
+    long total = (long)R * ld_dst;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % ld_dst);
+        long r = i / ld_dst;
+        dst[i] = __float2half_rn(c < C ? src[r * ld_src + c] : 0.0f);
+    }
+}
+
+// fp16 staging (decoder operands of the tensor-core path): dst[r, :C] = half(src[r, :C]), zero padded up to ld_dst
+extern "C" int spv_to_f16(const float* src, long long ld_src, void* dst, long long ld_dst, int R, int C, void* stream) {
+    if (!src || !dst || R <= 0 || C <= 0 || ld_dst < C) return SPV_ERR_ARG;
+    long total = (long)R * ld_dst;
+    int blocks = (int)min((long)148 * 16, (total + 255) / 256);
+    to_f16_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, ld_src, reinterpret_cast<__half*>(dst), ld_dst, R, C);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

@@ -175,7 +175,7 @@ class Noise:
 
 
 class _GroupWS:
-    def __init__(self, B, G, d: Dims, dev, with_grad: bool, bf16: bool = False, wb=None):
+    def __init__(self, B, G, d: Dims, dev, with_grad: bool, bf16: bool = False, wb=None, dec_dtype=torch.bfloat16):
         H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         self.B, self.G = B, G
@@ -212,7 +212,8 @@ class _GroupWS:
         self.Gp, self.KMp = r8(G), r8(KMIX)
         if bf16:
             h = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
-            self.Tb, self.amixb = h(B, self.Gp), h(B, self.KMp)
+            hd = lambda *s: torch.zeros(*s, dtype=dec_dtype, device=dev)  # decoder operands: fp16 on the fused path
+            self.Tb, self.amixb = h(B, self.Gp), hd(B, self.KMp)
             self.Tb_lo = h(B, self.Gp)  # bf16 residual of log1p(counts): the fc1 contractions run on split operands
             # fp16 operands of the branch-logit MMAs (spv_dec_fold writes them): centred latents and folded weights
             self.zcb = torch.zeros(B, 64, dtype=torch.float16, device=dev)
@@ -223,7 +224,7 @@ class _GroupWS:
             self.W1b, self.Wstack, self.W1b_lo = wb
             self.Wmb = self.Wstack[:G]
             if with_grad:
-                self.D3, self.dh1b = h(B, 3 * self.Gp), h(B, 2 * H)  # D3 = [dpi | dyp | dys]
+                self.D3, self.dh1b = hd(B, 3 * self.Gp), h(B, 2 * H)  # D3 = [dpi | dyp | dys]
                 self.dh1b_lo = h(B, 2 * H)
                 self.dpib = self.D3  # unfused path: only the first Gp columns are used (row pitch 3 Gp)
                 self.CQ = f(2 * self.Gp, KZ)
@@ -261,6 +262,10 @@ class StepEngine:
         self.bf16 = precision == "bf16"
         # fused tcgen05 decoder-GEMMs + NB-likelihood kernel (bf16 mode); the latent columns must fit one 64-wide k-block
         self.fused_nb = self.bf16 and int(n_shared) + int(n_private) <= 64
+        # operands of the decoder GEMMs: fp16 on the fused path (2^-12 rounding, three bits more than bf16; every operand's range
+        # is bounded: activations after BatchNorm, weights, gradients stored in natural units), bf16 on the unfused fallback
+        self.dec_dtype = torch.float16 if self.fused_nb else torch.bfloat16
+        self.dec_fmt = 3 if self.fused_nb else 0
         self.lib = L.load()
         self.d = Dims(tuple(int(x) for x in genes), int(n_hidden), int(n_shared), int(n_private))
         if self.d.n_private > self.d.n_shared:
@@ -304,7 +309,7 @@ class StepEngine:
         self.wb = None
         if self.bf16:
             self.wb = [(torch.zeros(2 * self.d.n_hidden, r8(G), dtype=torch.bfloat16, device=self.device),
-                        torch.zeros(3 * r8(G), r8(self.d.KMIX), dtype=torch.bfloat16, device=self.device),
+                        torch.zeros(3 * r8(G), r8(self.d.KMIX), dtype=self.dec_dtype, device=self.device),
                         torch.zeros(2 * self.d.n_hidden, r8(G), dtype=torch.bfloat16, device=self.device)) for G in self.d.genes]
         # bf16 copies of W1 / Wm: refreshed by conversion kernels at the start of every forward, or (stage_in_adam, set by
         # the owner of the optimiser step: TrainLoop) written by the Adam kernel itself; _staged_version detects parameter
@@ -345,9 +350,15 @@ class StepEngine:
     def _can_fuse(self, K):
         return K <= 256
 
-    def _tc_gemm(self, A, B, C, M, N, K, *, lda, ldb, ldc, a_mn=0, b_mn=0, bias=None, relu=0, acc=0, splits=1, ws=None):
-        L.check(self.lib.spv_tc_gemm(a_mn, b_mn, A, lda, B, ldb, C, ldc, M, N, K, bias, relu, acc, splits, L.ptr(ws),
-                                     self._stream()), "spv_tc_gemm")
+    def _tc_gemm(self, A, B, C, M, N, K, *, lda, ldb, ldc, a_mn=0, b_mn=0, bias=None, relu=0, acc=0, splits=1, ws=None, fmt=0,
+                 alpha=1.0):
+        L.check(self.lib.spv_tc_gemm_ex(fmt, alpha, a_mn, b_mn, A, lda, B, ldb, C, ldc, M, N, K, bias, relu, acc, splits, L.ptr(ws),
+                                        self._stream()), "spv_tc_gemm_ex")
+
+    def _to_dec(self, src, ld_src, dst, ld_dst, R, C):
+        """fp32 -> the decoder's 16-bit operand format"""
+        fn, name = (self.lib.spv_to_f16, "spv_to_f16") if self.fused_nb else (self.lib.spv_to_bf16, "spv_to_bf16")
+        L.check(fn(src, ld_src, dst, ld_dst, R, C, self._stream()), name)
 
     def _tc_gemm_split(self, A, Alo, B, Blo, C, M, N, K, *, lda, ldb, ldc, a_mn=0, b_mn=0, bias=None, relu=0, acc=0, splits=1, ws=None):
         """split-bf16 operands (hi + lo planes): three MMAs per k-step, fp32-grade products (spv_tc_gemm_split)"""
@@ -425,8 +436,8 @@ class StepEngine:
     def workspace(self, B0, B1, with_grad=True):
         key = (B0, B1, with_grad)
         if key not in self._ws:
-            self._ws[key] = [_GroupWS(B, G, self.d, self.device, with_grad, self.bf16, self.wb[g] if self.bf16 else None)
-                             for g, (B, G) in enumerate(zip((B0, B1), self.d.genes))]
+            self._ws[key] = [_GroupWS(B, G, self.d, self.device, with_grad, self.bf16, self.wb[g] if self.bf16 else None,
+                                      self.dec_dtype) for g, (B, G) in enumerate(zip((B0, B1), self.d.genes))]
         return self._ws[key]
 
     @staticmethod
@@ -489,8 +500,7 @@ class StepEngine:
                                                   self._stream()), "spv_to_bf16_split")
                 if decode or self.stage_in_adam:
                     with self._branch(g, "wm"):
-                        L.check(lib.spv_to_bf16(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX, self._stream()),
-                                "spv_to_bf16")
+                        self._to_dec(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX)
             if self.bf16:  # encoder input and library size from one pass over the gathered rows
                 L.check(lib.spv_counts_to_bf16(src, xptr, ldx, L.ptr(bt.rows), L.ptr(w.Tb), L.ptr(w.Tb_lo), w.Gp, B, G,
                                                L.ptr(w.lib), st), "spv_counts_to_bf16")
@@ -552,7 +562,7 @@ class StepEngine:
             G, B = d.genes[g], Bs[g]
             src, xptr, ldx = srcs[g]
             if self.bf16 and not ctx["wm_staged"]:  # decode() after an encoder-only pass: the mixture weight's bf16 copy
-                L.check(lib.spv_to_bf16(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX, st), "spv_to_bf16")
+                self._to_dec(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX)
             zzp = w.amix.data_ptr() + 4 * HD
             fold = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), self.P(g, "gp"), self.P(g, "bp"), self.P(g, "gs"),
                                 self.P(g, "bs"), self.P(g, "px_r"), self.Bf(g, "rm_p"), self.Bf(g, "rv_p"),
@@ -564,7 +574,7 @@ class StepEngine:
                 # the bf16 operand [hm | zz] of the mixture GEMM in one conversion pass after it
                 with self._branch(g, "hm"):
                     self._hidden_mix(g, w, B, tr, zzp)
-                    L.check(lib.spv_to_bf16(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX, self._stream()), "spv_to_bf16")
+                    self._to_dec(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX)
             L.check(lib.spv_dec_fold(fold, KMIX, B, G, P, S, tr, DEC_BN_EPS, DEC_BN_MOM, wz, w.KMp if self.fused_nb else 0,
                                      w.Gp, HD, L.ptr(w.wzf) if self.fused_nb else None, L.ptr(w.zcb) if self.fused_nb else None, st),
                     "spv_dec_fold")
@@ -583,7 +593,7 @@ class StepEngine:
             if self.fused_nb:
                 self._join(g, "wm")
             elif self.bf16:  # mixture logits on the tensor cores, consumed by the NB sweep
-                L.check(lib.spv_to_bf16(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX, st), "spv_to_bf16")
+                self._to_dec(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX)
                 self._join(g, "wm")
             if evs is not None:
                 evs[0].record()
@@ -732,23 +742,24 @@ class StepEngine:
                 Gp3 = 3 * w.Gp
                 # d zz through the two softmax branches: [dyp | dys] against the folded weights' latent columns (K = 2 Gp,
                 # N = P + S).  Kept out of the mixture GEMM below: stacked into its K it would triple that GEMM's operand traffic.
+                f3, al = self.dec_fmt, float(grad_scale) / B  # D3 is stored in natural units: the GEMMs apply |scale|
                 with self._branch(g, "dzg"):
                     self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, w.Wstack.data_ptr() + 2 * (w.Gp * w.KMp + HD), L.ptr(w.dzraw), B, KZ,
-                                  2 * w.Gp, lda=Gp3, ldb=w.KMp, ldc=KZ, b_mn=1, splits=w.tc_splits_dz, ws=w.ws2)
+                                  2 * w.Gp, lda=Gp3, ldb=w.KMp, ldc=KZ, b_mn=1, splits=w.tc_splits_dz, ws=w.ws2, fmt=f3, alpha=al)
                 with self._branch(g, "wgrad"):  # d Wm = dpi^T [hm | zz]
                     self._tc_gemm(L.ptr(w.D3), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=Gp3, ldb=w.KMp, ldc=KMIX,
-                                  a_mn=1, b_mn=1)
+                                  a_mn=1, b_mn=1, fmt=f3, alpha=al)
                 Qp, Qs, ldq, dzraw = w.CQ.data_ptr(), w.CQ.data_ptr() + 4 * (w.Gp * KZ + P), KZ, None
                 # per-gene BatchNorm backward chain on the second auxiliary stream: it needs Q and the column sums, not
                 # d [hm | zz], so it runs beside the input-gradient GEMM and the hidden layer's backward
                 with self._branch(g, "gene", lane=1):
                     # [Qp | .] = dyp^T zz, [. | Qs] = dys^T zz in one GEMM over the stacked rows (rows g and Gp + g)
                     self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, w.amixb.data_ptr() + 2 * HD, L.ptr(w.CQ), 2 * w.Gp, KZ, B, lda=Gp3,
-                                  ldb=w.KMp, ldc=KZ, a_mn=1, b_mn=1)
+                                  ldb=w.KMp, ldc=KZ, a_mn=1, b_mn=1, fmt=f3, alpha=al)
                     self._gene_bwd(g, w, Qp, Qs, ldq, B, G)
                 # d [hm | zz] (mixture part) = dpi Wm
                 self._tc_gemm(L.ptr(w.D3), L.ptr(w.Wstack), L.ptr(w.damix), B, KMIX, G, lda=Gp3, ldb=w.KMp, ldc=KMIX, b_mn=1,
-                              splits=w.tc_splits_damix, ws=w.ws)
+                              splits=w.tc_splits_damix, ws=w.ws, fmt=f3, alpha=al)
             else:
                 L.check(lib.spv_dec_nb_bwd(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, KMIX, B, G, HD, P, S,
                                            -float(grad_scale) / B, L.ptr(w.colsum), L.ptr(w.dpib) if self.bf16 else None,
@@ -791,7 +802,8 @@ class StepEngine:
             self._join(g, "hid")
             self._join(g, "gene")
             L.check(lib.spv_dec_dzz_combine(w.damix.data_ptr() + 4 * HD, KMIX, dzraw, L.ptr(w.vpart), L.ptr(w.mpart),
-                                            w.nGB, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S, st), "spv_dec_dzz_combine")
+                                            w.nGB, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S, 1 if self.fused_nb else 0, st),
+                    "spv_dec_dzz_combine")
         # ---------------- PoE
         own = self._poe_sides(ws)
         arrs = []
@@ -904,7 +916,8 @@ class StepEngine:
                                   L.ptr(self.step_dev), L.ptr(self.adam_ticket), len(segs),
                                   L.ll_array([s[0] for s in segs]), L.int_array([s[1] for s in segs]),
                                   L.int_array([s[2] for s in segs]), L.ptr_array([s[3] for s in segs]),
-                                  L.ptr_array([s[5] for s in segs]), L.ll_array([s[4] for s in segs]), 0, st), "spv_adam")
+                                  L.ptr_array([s[5] for s in segs]), L.int_array([s[6] for s in segs]),
+                                  L.ll_array([s[4] for s in segs]), 0, st), "spv_adam")
 
     def adam_range_step(self, phase, lr=1e-3, betas=(0.9, 0.999), eps=0.01, weight_decay=1e-6, grad_scale=1.0):
         """Adam on one phase of the flat layout (PHASE_ENC / PHASE_DEC); the step counter must have been advanced already
@@ -923,27 +936,27 @@ class StepEngine:
                                   cfg["weight_decay"], cfg.get("grad_scale", 1.0), L.ptr(self.step_dev), None, len(segs),
                                   L.ll_array([s[0] - lo for s in segs]), L.int_array([s[1] for s in segs]),
                                   L.int_array([s[2] for s in segs]), L.ptr_array([s[3] for s in segs]),
-                                  L.ptr_array([s[5] for s in segs]), L.ll_array([s[4] for s in segs]), max_blocks,
-                                  self._stream()), "spv_adam")
+                                  L.ptr_array([s[5] for s in segs]), L.int_array([s[6] for s in segs]),
+                                  L.ll_array([s[4] for s in segs]), max_blocks, self._stream()), "spv_adam")
 
     def _stage_segments(self):
-        """(flat offset, rows, cols, bf16 destination, destination row pitch, residual plane or None) of the weights the
-        tensor-core path reads"""
+        """(flat offset, rows, cols, 16-bit destination, destination row pitch, residual plane or None, destination is fp16) of the
+        weights the tensor-core path reads"""
         out = []
         for g, G in enumerate(self.d.genes):
             W1b, Wstack, W1b_lo = self.wb[g]
-            out.append((self.params.offsets[g]["W1"][0], 2 * self.d.n_hidden, G, W1b, W1b.stride(0), W1b_lo))
-            out.append((self.params.offsets[g]["Wm"][0], G, self.d.KMIX, Wstack, Wstack.stride(0), None))
+            out.append((self.params.offsets[g]["W1"][0], 2 * self.d.n_hidden, G, W1b, W1b.stride(0), W1b_lo, 0))
+            out.append((self.params.offsets[g]["Wm"][0], G, self.d.KMIX, Wstack, Wstack.stride(0), None, 1 if self.fused_nb else 0))
         return out
 
     def stage_weights(self):
         """refresh the bf16 operand copies of W1 / Wm from the fp32 parameters (bf16 mode; a no-op otherwise)"""
         if not self.bf16:
             return
-        for off, rows, cols, dst, ld, dst_lo in self._stage_segments():
+        for off, rows, cols, dst, ld, dst_lo, f16 in self._stage_segments():
             src = self.params.flat[off:off + rows * cols]
             if dst_lo is None:
-                L.check(self.lib.spv_to_bf16(L.ptr(src), cols, L.ptr(dst), ld, rows, cols, self._stream()), "spv_to_bf16")
+                self._to_dec(L.ptr(src), cols, L.ptr(dst), ld, rows, cols)
             else:
                 L.check(self.lib.spv_to_bf16_split(L.ptr(src), cols, L.ptr(dst), L.ptr(dst_lo), ld, rows, cols, self._stream()),
                         "spv_to_bf16_split")

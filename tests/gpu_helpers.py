@@ -43,3 +43,15 @@ def engine_outputs(eng, ws):
         out["kl_private"].append(w.klp.cpu()); out["kl_poe"].append(w.klq.cpu())
         out["partners"].append(w.partner.cpu().numpy().astype(np.int64))
     return out
+
+
+def gate_consistent_grads(eng, ws, probe, grads, rerun, drop_masks=None):
+    """oracle gradients to compare the engine's with.  `grads` / `probe` come from the oracle's plain pass; if the engine took the
+    other decision on ReLU units whose pre-activation is zero to within tests.helpers.GATE_AMBIGUITY (and only on those:
+    asserted), `rerun(gates)` evaluates the oracle again with those units' gates fixed to the engine's and returns its
+    gradients.  Returns (grads, number of switched units)."""
+    from tests.helpers import engine_gates, gate_consistent
+    gates, switched = gate_consistent(probe, engine_gates(eng, ws, eng.d.n_hidden), drop_masks)
+    if switched == 0:
+        return grads, 0
+    return rerun(gates), switched

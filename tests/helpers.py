@@ -66,7 +66,7 @@ class Golden:
         return rs.sub_plan(self.plan, self.idx[0], self.idx[1]).to(dtype)
 
 
-def run_oracle(gd: Golden, dtype=torch.float32, backward=True):
+def run_oracle(gd: Golden, dtype=torch.float32, backward=True, gates=None, probe=None):
     sd = {}
     for k, v in gd.sd.items():
         if v.is_floating_point():
@@ -77,7 +77,7 @@ def run_oracle(gd: Golden, dtype=torch.float32, backward=True):
     out = rs.step(sd, [t.to(dtype) for t in gd.x], mode=gd.mode, n_shared=gd.S, n_private=gd.P,
                   eps_private=[e.to(dtype) for e in gd.eps_private], eps_poe=[e.to(dtype) for e in gd.eps_poe],
                   labels=gd.labels, sub=gd.sub(dtype), drop_masks=gd.drop_masks(dtype), kl_weight=gd.kl_weight,
-                  training=gd.training, batch_index=gd.batch, n_batch=gd.n_batch)
+                  training=gd.training, batch_index=gd.batch, n_batch=gd.n_batch, gates=gates, probe=probe)
     grads = None
     if backward and gd.training:
         out["loss"].backward()
@@ -104,3 +104,40 @@ def grad_errors(got, want):
         if d / denom > worst:
             worst, where = d / denom, k
     return worst, where
+
+
+GATE_AMBIGUITY = 1e-4  # relative to the layer's largest pre-activation: below the 1e-3 forward gate on the latents
+
+
+def engine_gates(eng, ws, n_hidden):
+    """the ReLU gate decisions the CUDA path took, keyed like oracle.restatement._relu: encoders' fc1 / fc2 and the decoder's
+    hidden layer.  h2 is stored after dropout, so only units the mask kept are informative (the others carry no gradient)."""
+    H = n_hidden
+    out = {}
+    for g, w in enumerate(ws):
+        for i, enc in enumerate(("private", "shared")):
+            out[f"encoder_{g}_{enc}.fc1"] = (w.h1[:, i * H:(i + 1) * H] > 0).cpu()
+            out[f"encoder_{g}_{enc}.fc2"] = (w.h2[:, i * H:(i + 1) * H] != 0).cpu()
+        out[f"decoder_{g}.sigmoid_decoder"] = (w.amix[:, :256] > 0).cpu()
+    return out
+
+
+def gate_consistent(probe, eng_gates, drop_masks=None):
+    """gates for a second oracle pass: the oracle's own sign test everywhere, except on units whose pre-activation is zero to
+    within GATE_AMBIGUITY (relative), where the implementation's decision is taken.  Asserts that the two sides disagree ONLY
+    on such units, and returns (gates, number of units that were switched)."""
+    gates, switched = {}, 0
+    for key, pre in probe.items():
+        own = pre > 0
+        theirs = eng_gates[key]
+        if key.endswith(".fc2") and drop_masks is not None:  # dropped units: h2 == 0 whatever the gate was
+            g, enc = int(key.split("_")[1]), key.split("_")[2].split(".")[0]
+            kept = drop_masks[(g, enc)] > 0
+            theirs = torch.where(kept, theirs, own)
+        diff = own != theirs
+        if bool(diff.any()):
+            worst = float(pre[diff].abs().max() / pre.abs().max())
+            assert worst < GATE_AMBIGUITY, (key, int(diff.sum()), worst)
+            switched += int(diff.sum())
+        gates[key] = torch.where(diff, theirs, own)
+    return gates, switched

@@ -63,6 +63,30 @@ def test_tc_gemm(a_mn, b_mn, M, N, K):
         assert err < 1e-4, (splits, err)
 
 
+@pytest.mark.parametrize("fmt", [0, 3])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 1), (0, 1)])
+def test_tc_gemm_operand_formats(fmt, a_mn, b_mn):
+    """spv_tc_gemm_ex: bf16 or fp16 operands (both the same: a mixed pair is an illegal instruction on sm_100), alpha scaling"""
+    from spvipes_b200 import _lib as L
+    lib = L.load()
+    M, N, K = 304, 200, 520  # MN-major operands: the leading dimension must be a multiple of 8 elements (TMA pitch)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    ta, tb = (torch.float16 if fmt & 1 else torch.bfloat16), (torch.float16 if fmt & 2 else torch.bfloat16)
+    A = torch.randn((K, M) if a_mn else (M, K), generator=g, device="cuda").to(ta).contiguous()
+    B = torch.randn((K, N) if b_mn else (N, K), generator=g, device="cuda").to(tb).contiguous()
+    want = 0.5 * ((A.t() if a_mn else A).double() @ (B if b_mn else B.t()).double())
+    ws = torch.empty(4 * M * N, device="cuda")
+    assert lib.spv_tc_gemm_ex(1, 1.0, a_mn, b_mn, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), ws.data_ptr(), N, M, N, K, None, 0,
+                              0, 1, None, _stream()) == -1
+    for splits in (1, 3):
+        C = torch.full((M, N), float("nan"), device="cuda")
+        L.check(lib.spv_tc_gemm_ex(fmt, 0.5, a_mn, b_mn, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), C.data_ptr(), N, M, N, K,
+                                   None, 0, 0, splits, ws.data_ptr(), _stream()), "spv_tc_gemm_ex")
+        torch.cuda.synchronize()
+        err = float((C.double() - want).abs().max() / want.abs().max())
+        assert err < 1e-4, (fmt, splits, err)
+
+
 @pytest.mark.parametrize("a_mn,b_mn,M,N,K", [(0, 0, 512, 256, 5000), (1, 1, 256, 5000, 512), (0, 0, 100, 40, 333)])
 def test_tc_gemm_split_is_fp32_grade(a_mn, b_mn, M, N, K):
     """spv_tc_gemm_split (hi.hi + hi.lo + lo.hi on bf16 pairs) against float64 on fp32 operands: ~2^-16 per operand, where the
@@ -90,7 +114,7 @@ def test_tc_gemm_split_is_fp32_grade(a_mn, b_mn, M, N, K):
                                       C.data_ptr(), N, M, N, K, None, 0, 0, splits, ws.data_ptr(), _stream()), "spv_tc_gemm_split")
         torch.cuda.synchronize()
         err = float((C.double() - want).abs().max() / want.abs().max())
-        assert err < 2e-5, (splits, err)
+        assert err < 5e-5, (splits, err)
     C1 = torch.empty(M, N, device="cuda")
     L.check(lib.spv_tc_gemm(a_mn, b_mn, Ah.data_ptr(), Ah.stride(0), Bh.data_ptr(), Bh.stride(0), C1.data_ptr(), N, M, N, K, None, 0, 0, 1,
                             None, _stream()), "spv_tc_gemm")
@@ -164,7 +188,7 @@ def test_adam_ranges_and_staging():
             L.check(lib.spv_adam(p.data_ptr() + 4 * lo, gr.data_ptr() + 4 * lo, m.data_ptr() + 4 * lo, v.data_ptr() + 4 * lo, hi - lo,
                                  lr, b1, b2, eps, wd, 1.0, step.data_ptr(), None, len(segs), L.ll_array([s[0] for s in segs]),
                                  L.int_array([s[1] for s in segs]), L.int_array([s[2] for s in segs]),
-                                 L.ptr_array([s[3] for s in segs]), L.ptr_array([s[5] for s in segs]),
+                                 L.ptr_array([s[3] for s in segs]), L.ptr_array([s[5] for s in segs]), L.int_array([0 for _ in segs]),
                                  L.ll_array([s[4] for s in segs]), 0, _stream()), "spv_adam")
         torch.cuda.synchronize()
         return p, m, v, torch.stack([stage, stage_lo])
@@ -187,6 +211,6 @@ def test_adam_ranges_and_staging():
     ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
     p, m, v = p0.clone(), m0.clone(), v0.clone()
     L.check(lib.spv_adam(p.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, b1, b2, eps, wd, 1.0, step2.data_ptr(),
-                         ticket.data_ptr(), 0, None, None, None, None, None, None, 0, _stream()), "spv_adam")
+                         ticket.data_ptr(), 0, None, None, None, None, None, None, None, 0, _stream()), "spv_adam")
     torch.cuda.synchronize()
     assert int(step2) == t and int(ticket) == 0 and torch.equal(p, pa)

@@ -11,8 +11,8 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import Golden, golden_names, grad_errors, relerr
-from tests.gpu_helpers import engine_from_golden, engine_outputs
+from tests.helpers import Golden, golden_names, grad_errors, relerr, run_oracle
+from tests.gpu_helpers import engine_from_golden, engine_outputs, gate_consistent_grads
 
 pytestmark = pytest.mark.gpu
 
@@ -46,12 +46,15 @@ def test_bf16_forward_matches_golden(name):
 def test_bf16_backward_matches_golden(name):
     gd = Golden(name)
     eng, batches, noise = engine_from_golden(gd, precision="bf16")
-    eng.forward(batches, training=True, noise=noise)
+    ws = eng.forward(batches, training=True, noise=noise)
     eng.backward()
     torch.cuda.synchronize()
     got = {k: v.cpu() for k, v in eng.grad_dict().items()}
-    worst, where = grad_errors(got, gd.grads)
-    assert worst < GRAD_TOL, (worst, where)
+    probe = {}
+    run_oracle(gd, backward=False, probe=probe)
+    want, switched = gate_consistent_grads(eng, ws, probe, gd.grads, lambda gates: run_oracle(gd, gates=gates)[1], gd.drop_masks())
+    worst, where = grad_errors(got, want)
+    assert worst < GRAD_TOL, (worst, where, switched)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -79,12 +82,18 @@ def test_c1_shape_against_oracle(precision):
     torch.cuda.synchronize()
     out = engine_outputs(eng, ws)
     # oracle
-    sd = {k: v.clone().requires_grad_("running" not in k) for k, v in sd0.items()}
     dm = {(g, k): drop[g][:, i * H:(i + 1) * H] for g in (0, 1) for i, k in enumerate(("private", "shared"))}
-    want = rs.step(sd, [data.X[g].cpu().to(torch.float32) for g in (0, 1)], mode="label", n_shared=S, n_private=P,
-                   eps_private=eps_p, eps_poe=eps_q, labels=[data.labels[g].cpu().numpy() for g in (0, 1)], drop_masks=dm,
-                   kl_weight=0.25)
-    want["loss"].backward()
+
+    def oracle(gates=None, probe=None):
+        sd = {k: v.clone().requires_grad_("running" not in k) for k, v in sd0.items()}
+        o = rs.step(sd, [data.X[g].cpu().to(torch.float32) for g in (0, 1)], mode="label", n_shared=S, n_private=P,
+                    eps_private=eps_p, eps_poe=eps_q, labels=[data.labels[g].cpu().numpy() for g in (0, 1)], drop_masks=dm,
+                    kl_weight=0.25, gates=gates, probe=probe)
+        o["loss"].backward()
+        return o, {k: sd[k].grad for k in rs.param_names(sd)}
+
+    probe = {}
+    want, grads = oracle(probe=probe)
     tol = 1e-4 if precision == "fp32" else 1e-2
     assert relerr(out["loss"], want["loss"].detach()) < tol
     for k in TERMS:
@@ -95,9 +104,9 @@ def test_c1_shape_against_oracle(precision):
     for k in LATENTS:
         for g in (0, 1):
             assert relerr(out[k][g], want[k][g].detach()) < 1e-3, (k, g)
-    grads = {k: sd[k].grad for k in rs.param_names(sd)}
+    grads, switched = gate_consistent_grads(eng, ws, probe, grads, lambda gates: oracle(gates=gates)[1], dm)
     worst, where = grad_errors({k: v.cpu() for k, v in eng.grad_dict().items()}, grads)
-    assert worst < GRAD_TOL, (worst, where)
+    assert worst < (2e-3 if precision == "fp32" else GRAD_TOL), (worst, where, switched)
 
 
 def test_stats_tc_matches_simt_statistics():
@@ -229,13 +238,19 @@ def test_ot_modes_hidden256_against_oracle(mode, precision):
     eng.backward()
     torch.cuda.synchronize()
     out = engine_outputs(eng, ws)
-    sd = {k: v.clone().requires_grad_("running" not in k) for k, v in sd0.items()}
     dm = {(g, k): drop[g][:, i * H:(i + 1) * H] for g in (0, 1) for i, k in enumerate(("private", "shared"))}
-    want = rs.step(sd, [data.X[g].cpu().to(torch.float32) for g in (0, 1)], mode=mode, n_shared=S, n_private=P,
-                   eps_private=eps_p, eps_poe=eps_q, sub=plan.cpu(),
-                   labels=[data.labels[g].cpu().numpy() for g in (0, 1)] if mode == "cluster" else None, drop_masks=dm,
-                   kl_weight=0.5)
-    want["loss"].backward()
+
+    def oracle(gates=None, probe=None):
+        sd = {k: v.clone().requires_grad_("running" not in k) for k, v in sd0.items()}
+        o = rs.step(sd, [data.X[g].cpu().to(torch.float32) for g in (0, 1)], mode=mode, n_shared=S, n_private=P,
+                    eps_private=eps_p, eps_poe=eps_q, sub=plan.cpu(),
+                    labels=[data.labels[g].cpu().numpy() for g in (0, 1)] if mode == "cluster" else None, drop_masks=dm,
+                    kl_weight=0.5, gates=gates, probe=probe)
+        o["loss"].backward()
+        return o, {k: sd[k].grad for k in rs.param_names(sd)}
+
+    probe = {}
+    want, grads = oracle(probe=probe)
     tol = 1e-4 if precision == "fp32" else 1e-2
     assert relerr(out["loss"], want["loss"].detach()) < tol
     for k in TERMS:
@@ -247,6 +262,6 @@ def test_ot_modes_hidden256_against_oracle(mode, precision):
     for k in LATENTS:
         for g in (0, 1):
             assert relerr(out[k][g], want[k][g].detach()) < 1e-3, (k, g)
-    grads = {k: sd[k].grad for k in rs.param_names(sd)}
+    grads, switched = gate_consistent_grads(eng, ws, probe, grads, lambda gates: oracle(gates=gates)[1], dm)
     worst, where = grad_errors({k: v.cpu() for k, v in eng.grad_dict().items()}, grads)
-    assert worst < GRAD_TOL, (worst, where)
+    assert worst < (2e-3 if precision == "fp32" else GRAD_TOL), (worst, where, switched)

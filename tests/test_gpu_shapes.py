@@ -9,7 +9,8 @@ The CPU oracle (oracle/restatement.py, pinned to the unmodified reference in tes
 these sizes; it is evaluated once per config and checked against both modes.  Gates (BASELINE.json north_star): pairing
 indices bit-exact; loss and each of the 2 rec + 4 KL terms <= 1e-4 (fp32 mode) / <= 1e-2 (tensor-core mode); latent means,
 log-variances and scales <= 1e-3 in BOTH modes (the tensor-core mode runs the K = genes contraction on split-bf16 operands);
-gradients per parameter (max |error| / max |gradient|) <= 2e-3 (fp32) / <= GRAD_TOL_TC (tensor-core mode).
+gradients per parameter (max |error| / max |gradient|) <= 2e-3 (fp32) / <= GRAD_TOL_TC (tensor-core mode), with the gates of
+ReLU units whose pre-activation is zero to within rounding taken from the implementation (asserted to be only those).
 The minibatch is gathered with scattered row indices from a 4x larger device-resident count matrix, as the training loop does."""
 import functools
 
@@ -18,7 +19,7 @@ import pytest
 import torch
 
 from tests.helpers import grad_errors, relerr
-from tests.gpu_helpers import engine_outputs
+from tests.gpu_helpers import engine_outputs, gate_consistent_grads
 
 pytestmark = pytest.mark.gpu
 
@@ -62,20 +63,24 @@ def _case(cfg):
     eng = StepEngine((G, G), H, S, P, 0.1, mode, "cuda", plan=plan, precision="fp32")
     sd0 = init_params(eng, 3)
     del eng
-    sd = {k: v.clone().requires_grad_("running" not in k) for k, v in sd0.items()}
     dm = {(g, k): drop[g][:, i * H:(i + 1) * H] for g in (0, 1) for i, k in enumerate(("private", "shared"))}
     x = [data.X[g].cpu().to(torch.int32)[rows[g].long()].to(torch.float32) for g in (0, 1)]
     labels = [data.labels[g].cpu()[rows[g].long()].numpy() for g in (0, 1)]
     sub = None
     if plan is not None:
         sub = plan[rows[0].long().cuda()][:, rows[1].long().cuda()].cpu()
-    want = rs.step(sd, x, mode=mode, n_shared=S, n_private=P, eps_private=eps_p, eps_poe=eps_q, sub=sub,
-                   labels=labels if mode in ("label", "cluster") else None, drop_masks=dm, kl_weight=0.25)
-    want["loss"].backward()
-    grads = {k: sd[k].grad.detach() for k in rs.param_names(sd)}
+    def oracle(gates=None, probe=None):
+        sd = {k: v.clone().requires_grad_("running" not in k) for k, v in sd0.items()}
+        out = rs.step(sd, x, mode=mode, n_shared=S, n_private=P, eps_private=eps_p, eps_poe=eps_q, sub=sub,
+                      labels=labels if mode in ("label", "cluster") else None, drop_masks=dm, kl_weight=0.25, gates=gates, probe=probe)
+        out["loss"].backward()
+        return out, {k: sd[k].grad.detach() for k in rs.param_names(sd)}
+
+    probe = {}
+    want, grads = oracle(probe=probe)
     want = {k: ([t.detach() if torch.is_tensor(t) else t for t in v] if isinstance(v, (list, tuple)) else (v.detach() if torch.is_tensor(v) else v))
             for k, v in want.items() if k != "new_stats"}
-    return (data, rows, eps_p, eps_q, drop, plan), sd0, want, grads
+    return (data, rows, eps_p, eps_q, drop, plan), sd0, want, grads, probe, dm, (lambda gates: oracle(gates=gates)[1])
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -83,7 +88,7 @@ def _case(cfg):
 def test_config_shape_against_oracle(cfg, precision):
     from spvipes_b200.engine import GroupBatch, Noise, StepEngine
     mode, B, G, H, NL = CONFIGS[cfg]
-    (data, rows, eps_p, eps_q, drop, plan), sd0, want, grads = _case(cfg)
+    (data, rows, eps_p, eps_q, drop, plan), sd0, want, grads, probe, dm, rerun = _case(cfg)
     eng = StepEngine((G, G), H, S, P, 0.1, mode, "cuda", plan=plan, precision=precision)
     eng.load_state_dict(sd0)
     eng.set_kl_weight(0.25)
@@ -112,5 +117,8 @@ def test_config_shape_against_oracle(cfg, precision):
     if mode in ("label", "paired"):
         for g in (0, 1):
             assert np.array_equal(out["partners"][g], want["partners"][g]), g
+    # ReLU units whose pre-activation is ~0 (|pre| < 1e-4 of the layer's largest) have no well-defined gate: on those, and only
+    # those (asserted), the oracle's gradient is evaluated with the engine's decision (tests/helpers.py: gate_consistent)
+    grads, switched = gate_consistent_grads(eng, ws, probe, grads, rerun, dm)
     worst, where = grad_errors({k: v.cpu() for k, v in eng.grad_dict().items()}, grads)
-    assert worst < (2e-3 if precision == "fp32" else GRAD_TOL_TC), (worst, where)
+    assert worst < (2e-3 if precision == "fp32" else GRAD_TOL_TC), (worst, where, switched)
