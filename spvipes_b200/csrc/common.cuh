@@ -146,5 +146,10 @@ __device__ __forceinline__ float digammaf_pos(float x) {
     return r + logf(x) - 0.5f * ix - s;
 }
 
+// fp32 -> fp16 operand with saturation: a value beyond fp16's range (an exploding latent of an outlier cell: the model does not
+// clamp its log-variances) stays finite, as it does in the fp32 / bf16 formats, instead of turning the step into NaN
+#include <cuda_fp16.h>
+__device__ __forceinline__ __half to_half_sat(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f)); }
+
 // torch F.softplus(x) (beta 1, threshold 20)
 __device__ __forceinline__ float softplusf(float x) { return x > 20.0f ? x : log1pf(expf(x)); }

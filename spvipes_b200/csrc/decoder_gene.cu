@@ -274,16 +274,16 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
         p.wfold[(long)g * KZ + k] = wf;
         if (p.wfold_bf16) {
             const long at = ((long)(pr ? 0 : 1) * p.Gp + g) * p.ld_wz + p.HD + k;
-            if (p.stack_f16) reinterpret_cast<__half*>(p.wfold_bf16)[at] = __float2half_rn(wf);
+            if (p.stack_f16) reinterpret_cast<__half*>(p.wfold_bf16)[at] = to_half_sat(wf);
             else p.wfold_bf16[at] = __float2bfloat16(wf);
         }
-        if (p.wz_f16) p.wz_f16[((long)(pr ? 0 : 1) * p.Gp + g) * 64 + k] = __float2half_rn(wf);
+        if (p.wz_f16) p.wz_f16[((long)(pr ? 0 : 1) * p.Gp + g) * 64 + k] = to_half_sat(wf);
     }
     if (p.zc_f16) {  // centred latents: the CTAs share the rows
         for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < (long)p.B * KZ; i += (long)gridDim.x * 256) {
             const int b = (int)(i / KZ), k = (int)(i - (long)b * KZ);
             const float m = p.training ? smean[k] : 0.0f;
-            p.zc_f16[(long)b * 64 + k] = __float2half_rn(__ldg(p.zz + (long)b * p.ld_zz + k) - m);
+            p.zc_f16[(long)b * 64 + k] = to_half_sat(__ldg(p.zz + (long)b * p.ld_zz + k) - m);
         }
     }
 }

@@ -344,7 +344,7 @@ __device__ __forceinline__ void adam_stage(const AdamSegs& sg, long long idx, fl
             if (c < 0) { --r; c += cols; }
             else if (c >= cols) { ++r; c -= cols; }
             if (sg.f16[s]) {
-                reinterpret_cast<__half*>(sg.dst[s])[(long long)r * sg.ld[s] + c] = __float2half_rn(val);
+                reinterpret_cast<__half*>(sg.dst[s])[(long long)r * sg.ld[s] + c] = to_half_sat(val);
                 return;
             }
             const __nv_bfloat16 hi = __float2bfloat16(val);

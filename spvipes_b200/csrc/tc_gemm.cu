@@ -411,7 +411,7 @@ __global__ void to_f16_kernel(const float* __restrict__ src, long ld_src, __half
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         int c = (int)(i % ld_dst);
         long r = i / ld_dst;
-        dst[i] = __float2half_rn(c < C ? src[r * ld_src + c] : 0.0f);
+        dst[i] = to_half_sat(c < C ? src[r * ld_src + c] : 0.0f);
     }
 }
 

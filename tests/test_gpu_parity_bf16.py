@@ -265,3 +265,19 @@ def test_ot_modes_hidden256_against_oracle(mode, precision):
     grads, switched = gate_consistent_grads(eng, ws, probe, grads, lambda gates: oracle(gates=gates)[1], dm)
     worst, where = grad_errors({k: v.cpu() for k, v in eng.grad_dict().items()}, grads)
     assert worst < (2e-3 if precision == "fp32" else GRAD_TOL), (worst, where, switched)
+
+
+def test_exploding_latent_stays_finite():
+    """the model does not clamp its log-variances, so an outlier cell can sample a latent far beyond fp16's range (seen in
+    C5-shaped training: KL spikes of 1e8).  The fp16 decoder operands saturate instead of overflowing: every loss term and
+    gradient stays finite, as in the fp32 mode."""
+    gd = Golden("label_tiny")
+    for precision in ("fp32", "bf16"):
+        eng, batches, noise = engine_from_golden(gd, precision=precision)
+        eng.state_dict()["encoder_0_private.lvar_encoder.1.bias"].fill_(26.0)  # scale = e^13 ~ 4e5: |z| beyond 65504
+        ws = eng.forward(batches, training=True, noise=noise)
+        eng.backward()
+        torch.cuda.synchronize()
+        assert float(ws[0].zpriv.abs().max()) > 65504.0
+        assert bool(torch.isfinite(eng.loss_out[:7]).all()), (precision, eng.loss_out)
+        assert bool(torch.isfinite(eng.grads).all()), precision
