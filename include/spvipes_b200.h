@@ -40,6 +40,11 @@ long long spv_launch_count(void);
 /* 0 if device `dev` is sm_100 (B200), SPV_ERR_ARCH otherwise, SPV_ERR_LAUNCH if no CUDA device. Host-side query. */
 int spv_arch_check(int dev);
 
+/* host -> device copy (cudaMemcpy2DAsync; asynchronous when the host matrix is pinned) of `rows` rows of `width` bytes from a
+ * host matrix with row pitch `spitch` into a device buffer with row pitch `dpitch`: one group's own gene columns out of the
+ * scvi minibatch matrix X [B, G0 + G1] (module/spVIPESmodule.py:428-430).  src is a HOST pointer. */
+int spv_copy2d_h2d(void* dst, long long dpitch, const void* src, long long spitch, long long width, long long rows, void* stream);
+
 /* C[b] (+)= act(op(A[b]) op(B[b]) + bias[b]) in fp32, batched over `batch` (element strides sA/sB/sC/sBias), optional
  * split-K (`ws` holds batch*splits*M*N floats).  transA: A stored [K][M]; transB: B stored [N][K] (y = x W^T).
  * Replaces nn.Linear forward/backward GEMMs: nn/networks.py:119-125 (Encoder), :314-325 (decoder, scvi FCLayers). */
@@ -133,6 +138,9 @@ int spv_pair_label(const int* la, const int* lb, const int* rows_a, const int* r
                    void* stream);
 /* sub = T[idx0][:, idx1]   :474-482 ;  row/col argmax (ties -> first)   :526-527 */
 int spv_plan_gather(const float* T, long long ldT, const int* idx0, const int* idx1, int B0, int B1, float* sub, void* stream);
+/* ... from a plan stored as bf16 (halves the residency of a large plan; cluster mode) */
+int spv_plan_gather_bf16(const void* T, long long ldT, const int* idx0, const int* idx1, int B0, int B1, float* sub, void* stream);
+/* NaN entries compare greater than any number and the first one wins, as torch.argmax */
 int spv_plan_argmax(const float* sub, int B0, int B1, int* row_arg, int* col_arg, void* stream);
 /* masked row-normalised sub-plans of the cluster mode   :207-219 */
 int spv_plan_cluster_norm(const float* sub, int B0, int B1, const int* l0, const int* l1, float* P1, float* P2, void* stream);

@@ -371,6 +371,43 @@ def param_names(sd) -> List[str]:
     return [k for k in sd if not (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"))]
 
 
+def default_state_dict(genes, n_hidden=128, n_shared=25, n_private=10, seed=0, decoder_hidden=256):
+    """reference default initialisation as a plain state_dict (names of module/spVIPESmodule.py:118-120, 172-175): nn.Linear ->
+    U(+-1/sqrt(fan_in)) for weight and bias, BatchNorm weight 1 / bias 0 / running stats 0 / 1, px_r ~ N(0, 1) (:115-117).
+    For the CPU baseline of bench.py: the oracle then needs nothing from the product package."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def linear(name, n_out, n_in, bias=True):
+        b = 1.0 / math.sqrt(n_in)
+        sd[name + ".weight"] = (torch.rand(n_out, n_in, generator=gen) * 2 - 1) * b
+        if bias:
+            sd[name + ".bias"] = (torch.rand(n_out, generator=gen) * 2 - 1) * b
+
+    def bn(name, n):
+        sd[name + ".weight"], sd[name + ".bias"] = torch.ones(n), torch.zeros(n)
+        sd[name + ".running_mean"], sd[name + ".running_var"] = torch.zeros(n), torch.ones(n)
+
+    kz = n_shared + n_private
+    for g, G in enumerate(genes):
+        for enc, n_out in ((f"encoder_{g}_private", n_private), (f"encoder_{g}_shared", n_shared)):
+            linear(enc + ".fc1", n_hidden, G)
+            linear(enc + ".fc2", n_hidden, n_hidden)
+            for head in ("mu_encoder", "lvar_encoder"):
+                linear(f"{enc}.{head}.0", n_out, n_hidden)
+                bn(f"{enc}.{head}.1", n_out)
+        fl = "fc_layers.Layer 0"
+        for name, n_out, n_in, bias, has_bn in ((f"decoder_{g}.factor_regressor_private", G, n_private, False, True),
+                                                (f"decoder_{g}.factor_regressor_shared", G, n_shared, False, True),
+                                                (f"decoder_{g}.sigmoid_decoder", decoder_hidden, kz, True, True),
+                                                (f"decoder_{g}.mixture", G, decoder_hidden + kz, True, False)):
+            linear(f"{name}.{fl}.0", n_out, n_in, bias)
+            if has_bn:
+                bn(f"{name}.{fl}.1", n_out)
+        sd[f"px_r.{g}"] = torch.randn(G, generator=gen)
+    return sd
+
+
 def adam_step(p, g, m, v, t, lr=1e-3, b1=0.9, b2=0.999, eps=0.01, wd=1e-6):
     """torch.optim.Adam (L2 weight decay folded into the gradient), single tensor, step t>=1."""
     g = g + wd * p

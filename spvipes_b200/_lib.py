@@ -23,6 +23,7 @@ _SIGS = {
     "spv_abi_version": [],
     "spv_launch_count": [],
     "spv_arch_check": [i],
+    "spv_copy2d_h2d": [p, ll, p, ll, ll, ll, p],
     "spv_gemm": [i, i, i, i, p, ll, p, p, ll, p, p, ll, i, i, i, i, ll, ll, ll, p, ll, i, i, i, p, p],
     "spv_enc_mid_supported": [i, i, i],
     "spv_enc_mid_fwd": [p, ll, p, p, p, p, p, p, ll, p, ll, p, ll, f, u64, u32, p, i, i, i, i, p],
@@ -43,6 +44,7 @@ _SIGS = {
     "spv_colsum": [p, ll, i, i, p, p],
     "spv_pair_label": [p, p, p, p, i, i, p, p, p],
     "spv_plan_gather": [p, ll, p, p, i, i, p, p],
+    "spv_plan_gather_bf16": [p, ll, p, p, i, i, p, p],
     "spv_plan_argmax": [p, i, i, p, p, p],
     "spv_plan_cluster_norm": [p, i, i, p, p, p, p, p],
     "spv_poe_fwd": [i, i, i, i, i, p, p, p, p, u64, p, p],

@@ -3,6 +3,7 @@
 // plus its backward.  Reference: module/spVIPESmodule.py:583-718 (_label_based_poe), :282-379
 // (_poe2), :511-581 (_paired_poe, _product_of_experts), :474-482 (_get_batch_transport_plans),
 // :184-280 (_cluster_based_poe), :841-868 (KL terms).
+#include <cuda_bf16.h>
 #include "common.cuh"
 #include "../../include/spvipes_b200.h"
 
@@ -72,6 +73,24 @@ __global__ void plan_gather_kernel(const float* __restrict__ T, long ldT, const 
     for (int j = threadIdx.x; j < B1; j += blockDim.x) sub[(long)i * B1 + j] = __ldg(row + idx1[j]);
 }
 
+// the same from a plan stored as bf16 (a 200k x 200k plan is 160 GB in fp32, 80 GB in bf16: the cluster mode, which only
+// uses row-normalised weights of the sub-plan, tolerates the 2^-9 rounding; the paired mode's bit-exact argmax keeps fp32)
+__global__ void plan_gather_bf16_kernel(const __nv_bfloat16* __restrict__ T, long ldT, const int* __restrict__ idx0,
+                                        const int* __restrict__ idx1, int B0, int B1, float* __restrict__ sub) {
+    int i = blockIdx.x;
+    const __nv_bfloat16* row = T + (long)idx0[i] * ldT;
+    for (int j = threadIdx.x; j < B1; j += blockDim.x) sub[(long)i * B1 + j] = __bfloat162float(row[idx1[j]]);
+}
+
+extern "C" int spv_plan_gather_bf16(const void* T, long long ldT, const int* idx0, const int* idx1, int B0, int B1, float* sub,
+                                    void* stream) {
+    if (!T || !idx0 || !idx1 || !sub || B0 <= 0 || B1 <= 0) return SPV_ERR_ARG;
+    plan_gather_bf16_kernel<<<B0, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(T), ldT, idx0,
+                                                                                    idx1, B0, B1, sub);
+    SPV_CHECK_LAUNCH();
+    return SPV_OK;
+}
+
 extern "C" int spv_plan_gather(const float* T, long long ldT, const int* idx0, const int* idx1, int B0, int B1, float* sub,
                                void* stream) {
     if (!T || !idx0 || !idx1 || !sub || B0 <= 0 || B1 <= 0) return SPV_ERR_ARG;
@@ -79,6 +98,9 @@ extern "C" int spv_plan_gather(const float* T, long long ldT, const int* idx0, c
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }
+
+// strict "greater" of torch.argmax: NaN compares greater than every number, and the FIRST NaN wins
+__device__ __forceinline__ bool arg_gt(float a, float b) { return a > b || (isnan(a) && !isnan(b)); }
 
 __global__ void plan_argmax_kernel(const float* __restrict__ sub, int B0, int B1, int* __restrict__ row_arg,
                                    int* __restrict__ col_arg) {
@@ -91,13 +113,13 @@ __global__ void plan_argmax_kernel(const float* __restrict__ sub, int B0, int B1
         if (lane < B1) { best = sub[(long)i * B1 + lane]; bj = lane; }
         for (int j = lane + 32; j < B1; j += 32) {
             float v = sub[(long)i * B1 + j];
-            if (v > best) { best = v; bj = j; }
+            if (arg_gt(v, best)) { best = v; bj = j; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             float ov = __shfl_xor_sync(0xffffffffu, best, o);
             int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-            if (ov > best || (ov == best && oj < bj)) { best = ov; bj = oj; }
+            if (arg_gt(ov, best) || ((ov == best || (isnan(ov) && isnan(best))) && oj < bj)) { best = ov; bj = oj; }
         }
         if (lane == 0) row_arg[i] = bj;
     } else {  // one thread per column
@@ -107,7 +129,7 @@ __global__ void plan_argmax_kernel(const float* __restrict__ sub, int B0, int B1
         int bi = 0;
         for (int i = 1; i < B0; ++i) {
             float v = sub[(long)i * B1 + j];
-            if (v > best) { best = v; bi = i; }
+            if (arg_gt(v, best)) { best = v; bi = i; }
         }
         col_arg[j] = bi;
     }

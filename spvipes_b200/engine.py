@@ -318,6 +318,7 @@ class StepEngine:
         self._staged_version = -1
         self.adam_ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.nb_events = None  # bench hook: iterator of (start, end) CUDA events bracketing the NB-loglik sweep
+        self.nb_bwd_events = None  # ... and its backward sweep
 
     # -------------------------------------------------------------------------------- helpers
     def P(self, g, name):
@@ -641,8 +642,9 @@ class StepEngine:
                              "P1": torch.empty(Bs[0], Bs[1], dtype=torch.float32, device=self.device),
                              "P2": torch.empty(Bs[1], Bs[0], dtype=torch.float32, device=self.device)}
         aux = self._ws[key]
-        L.check(lib.spv_plan_gather(L.ptr(self.plan), self.plan.stride(0), L.ptr(batches[0].idx), L.ptr(batches[1].idx),
-                                    Bs[0], Bs[1], L.ptr(aux["sub"]), st), "spv_plan_gather")
+        gather = lib.spv_plan_gather_bf16 if self.plan.dtype == torch.bfloat16 else lib.spv_plan_gather
+        L.check(gather(L.ptr(self.plan), self.plan.stride(0), L.ptr(batches[0].idx), L.ptr(batches[1].idx),
+                       Bs[0], Bs[1], L.ptr(aux["sub"]), st), "spv_plan_gather")
         if self.mode == "paired":
             L.check(lib.spv_plan_argmax(L.ptr(aux["sub"]), Bs[0], Bs[1], L.ptr(ws[0].partner), L.ptr(ws[1].partner), st),
                     "spv_plan_argmax")
@@ -736,9 +738,14 @@ class StepEngine:
             zzp = w.amix.data_ptr() + 4 * HD
             if self.fused_nb:
                 # logits recomputed on the tensor cores, gradients in the TMEM epilogue -> D3 = [dpi | dyp | dys] (bf16)
+                evs = next(self.nb_bwd_events) if self.nb_bwd_events is not None else None
+                if evs is not None:
+                    evs[0].record()
                 L.check(lib.spv_dec_nb_bwd_tc(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, L.ptr(w.amixb), w.KMp,
                                               L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.zcb), L.ptr(w.wzf), L.ptr(w.D3), B, G, HD, P, S,
                                               -float(grad_scale) / B, L.ptr(w.colsum), st), "spv_dec_nb_bwd_tc")
+                if evs is not None:
+                    evs[1].record()
                 Gp3 = 3 * w.Gp
                 # d zz through the two softmax branches: [dyp | dys] against the folded weights' latent columns (K = 2 Gp,
                 # N = P + S).  Kept out of the mixture GEMM below: stacked into its K it would triple that GEMM's operand traffic.

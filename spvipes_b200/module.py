@@ -71,6 +71,153 @@ class _NBMixtureHandle:
         raise NotImplementedError("the per-gene log-probabilities are never materialised; use neg_log_prob_sum")
 
 
+class _LazyDict(OrderedDict):
+    """ordered dict whose values may be zero-argument callables, evaluated on first access.  The reference's callers unpack
+    the stats dicts positionally (model/spvipes.py:539-551), so key order is the contract; scvi's TrainingPlan never reads
+    them, so building Normal / softmax objects per training step would be wasted launches."""
+
+    def _force(self, k):
+        v = OrderedDict.__getitem__(self, k)
+        if callable(v) and not isinstance(v, (torch.Tensor, torch.distributions.Distribution)):
+            v = v()
+            OrderedDict.__setitem__(self, k, v)
+        return v
+
+    def __getitem__(self, k):
+        return self._force(k)
+
+    def get(self, k, default=None):
+        return self._force(k) if k in self else default
+
+    def values(self):
+        return [self._force(k) for k in self.keys()]
+
+    def items(self):
+        return [(k, self._force(k)) for k in self.keys()]
+
+
+class _CapturedStep:
+    """the plugin call `module(batch, loss_kwargs)` -> `loss.backward()` for one minibatch signature, as two CUDA graphs
+    (forward; backward) over static input buffers.  Two buffer sets alternate, so the host -> device copy of step s + 1 (copy
+    stream) overlaps the kernels of step s; of the scvi minibatch matrix X [B, G0 + G1] only the group's own gene columns are
+    moved (one strided cudaMemcpy2DAsync per group)."""
+
+    def __init__(self, module, sig):
+        self.module, self.sig = module, sig
+        eng = module.engine
+        dev = eng.device
+        self.B = sig["B"]
+        self.bufs = []
+        for _ in (0, 1):
+            X = [torch.zeros(self.B, G, dtype=dt, device=dev) for G, dt in zip(eng.d.genes, sig["x_dtypes"])]
+            lab = [torch.zeros(self.B, dtype=torch.int32, device=dev) for _ in (0, 1)] if sig["labels"] else [None, None]
+            idx = [torch.zeros(self.B, dtype=torch.int32, device=dev) for _ in (0, 1)]
+            tmp = [[torch.zeros(self.B, dtype=torch.float32, device=dev) for _ in (0, 1)] for _ in (0, 1)]  # [labels | idx][group]
+            batches = [GroupBatch(X=X[g], labels=lab[g], idx=idx[g], B=self.B) for g in (0, 1)]
+            self.bufs.append({"X": X, "lab": lab, "idx": idx, "tmp": tmp, "batches": batches, "fwd": None, "bwd": None,
+                              "ready": torch.cuda.Event(), "free": torch.cuda.Event()})
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.turn = 0
+        self.warm = False
+        main = torch.cuda.current_stream(dev)
+        for b in self.bufs:
+            b["free"].record(main)
+
+    def stage(self, x, global_indices, labels):
+        """copy this call's minibatch into the next buffer set (asynchronous for pinned host tensors / device tensors)"""
+        from . import _lib as L
+        m, eng = self.module, self.module.engine
+        b = self.bufs[self.turn]
+        lib = eng.lib
+        cs = self.copy_stream
+        cs.wait_event(b["free"])  # the previous step that used this buffer set has finished reading it
+        with torch.cuda.stream(cs):
+            for g in (0, 1):
+                X = x[g]
+                G = eng.d.genes[g]
+                col0 = m._col0[g] if X.shape[1] != G else 0
+                if col0 is None:  # scattered gene subset: gather (data movement only)
+                    b["X"][g].copy_(X.to(eng.device, non_blocking=True).index_select(1, m._var_idx_dev[g]), non_blocking=True)
+                elif X.device.type == "cpu":
+                    esz = X.element_size()
+                    L.check(lib.spv_copy2d_h2d(b["X"][g].data_ptr(), G * esz, X.data_ptr() + col0 * esz, X.stride(0) * esz, G * esz,
+                                               self.B, cs.cuda_stream), "spv_copy2d_h2d")
+                else:
+                    b["X"][g].copy_(X[:, col0:col0 + G], non_blocking=True)
+                for which, src, dst in ((0, labels[g] if labels is not None else None, b["lab"][g]), (1, global_indices[g], b["idx"][g])):
+                    if src is None or dst is None:
+                        continue
+                    t = b["tmp"][which][g]
+                    t.copy_(src.reshape(-1), non_blocking=True)   # float codes as scvi delivers them
+                    dst.copy_(t)                                   # -> int32 on the device
+            b["ready"].record(cs)
+        return b
+
+    def forward(self, b):
+        eng = self.module.engine
+        main = torch.cuda.current_stream(eng.device)
+        main.wait_event(b["ready"])
+        if not self.warm:  # first use: lazily configured kernels, workspaces (not capturable)
+            eng.forward(b["batches"], training=True, noise=None)
+            self.warm = True
+        elif b["fwd"] is None:
+            side = torch.cuda.Stream(device=eng.device)
+            side.wait_stream(main)
+            torch.cuda.synchronize(eng.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                eng.forward(b["batches"], training=True, noise=None)
+            b["fwd"] = g
+            g.replay()
+        else:
+            if eng.bf16 and eng.stage_in_adam and eng._staged_version != eng.params.flat._version:
+                eng.stage_weights()  # the parameters were written through torch since the 16-bit operand copies were made
+            b["fwd"].replay()
+        return eng._ctx["ws"] if eng._ctx is not None else eng.workspace(self.B, self.B, True)
+
+    def backward(self, b):
+        eng = self.module.engine
+        if b["fwd"] is None:  # the eager first step
+            eng._ctx["batches"] = b["batches"]
+            eng.backward(grad_scale=1.0)
+        elif b["bwd"] is None:
+            torch.cuda.synchronize(eng.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                eng.backward(grad_scale=1.0)
+            b["bwd"] = g
+            g.replay()
+        else:
+            b["bwd"].replay()
+        b["free"].record(torch.cuda.current_stream(eng.device))
+
+
+class _GraphStepFunction(torch.autograd.Function):
+    """autograd node of the captured plugin step: forward = one graph replay, backward = one graph replay.  Its only autograd
+    input is a scalar anchor leaf: the backward kernels write every parameter gradient into the engine's flat gradient buffer and
+    `.grad` of each nn.Parameter is (re)bound to its view of that buffer - 66 AccumulateGrad nodes, gradient copies and scaling
+    launches per step would cost more host time than the whole step takes on the GPU (tools/profile_plugin.py).  Consequence:
+    gradients do not accumulate over several backward calls (each backward overwrites), as documented in INTEGRATION.md."""
+
+    @staticmethod
+    def forward(ctx, module, plan, buf, anchor):
+        ws = plan.forward(buf)
+        ctx.module, ctx.plan, ctx.buf = module, plan, buf
+        module._last_ws = ws
+        return module.engine.loss_out[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        module, eng = ctx.module, ctx.module.engine
+        ctx.plan.backward(ctx.buf)
+        if module.scale_grads_by_upstream:
+            eng.grads.mul_(grad_loss)  # one launch over the flat buffer (d total / d loss; 1.0 for a plain loss.backward())
+        for p, gv in module._param_grad_pairs:
+            if p.grad is None:
+                p.grad = gv
+        return None, None, None, None
+
+
 class _StepFunction(torch.autograd.Function):
     """loss = fused CUDA forward; backward = hand-written CUDA backward, gradients for every parameter"""
 
@@ -125,7 +272,12 @@ class spVIPESmodule(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("spvipes_b200.spVIPESmodule needs a CUDA (sm_100a) device: there is no CPU fallback")
         genes = tuple(int(v) for v in groups_lengths.values())
-        plan = transport_plan.to(dev, torch.float32).contiguous() if (transport_plan is not None and not use_labels) else None
+        plan = None
+        if transport_plan is not None and not use_labels:
+            # resident on the device in fp32 (paired mode: the argmax over the sub-plan is a bit-exact contract); a plan handed
+            # over as bf16 is kept as bf16 (cluster mode at sizes where fp32 does not fit: 200k x 200k = 160 GB)
+            keep = transport_plan.dtype == torch.bfloat16 and not pair_data
+            plan = transport_plan.to(dev, torch.bfloat16 if keep else torch.float32).contiguous()
         self.engine = StepEngine(genes, n_hidden, n_dimensions_shared, n_dimensions_private, dropout_rate, mode, dev,
                                  seed=int(torch.initial_seed() % (2 ** 62)), plan=plan, precision=precision)
         # parameters / buffers are VIEWS of the engine's flat stores under the reference's names
@@ -141,6 +293,22 @@ class spVIPESmodule(nn.Module):
                 self._register(name[:-len("running_mean")] + "num_batches_tracked",
                                torch.zeros((), dtype=torch.long, device=dev), is_param=False)
         self._init_like_reference()
+        self._grad_views = {n: self.engine.params.view(n, self.engine.grads) for n in self._param_names}
+        self._param_grad_pairs = [(self._torch_params[n], self._grad_views[n]) for n in self._param_names]
+        self._anchor = torch.zeros((), device=dev, requires_grad=True)  # the captured step's only autograd input
+        # loss.backward() hands the node d total / d loss = 1; callers that scale the loss before backward() (gradient
+        # accumulation, loss scaling) set this so that the flat gradient buffer is multiplied by the upstream gradient
+        self.scale_grads_by_upstream = False
+        # where a group's genes sit in the combined var axis of the scvi minibatch matrix: a column offset when they form a
+        # contiguous ascending block (what prepare_adatas produces), else None (gathered)
+        self._col0, self._var_idx_dev = [], []
+        for g in (0, 1):
+            vi = np.asarray(groups_var_indices[g])
+            contiguous = vi.size > 0 and np.array_equal(vi, np.arange(vi[0], vi[0] + vi.size))
+            self._col0.append(int(vi[0]) if contiguous else None)
+            self._var_idx_dev.append(None if contiguous else torch.as_tensor(vi, device=dev))
+        self._plans: Dict[tuple, _CapturedStep] = {}
+        self.capture_steps = True  # training-mode forward(): replay captured CUDA graphs per minibatch signature
         self._noise = None      # tests may set a Noise(...) with explicit eps / dropout multipliers
         self._last_ws = None
         self._last_batches = None
@@ -212,22 +380,25 @@ class spVIPESmodule(nn.Module):
         return out
 
     def _stats_dicts(self, ws):
+        """the reference's output dicts (key order = the contract, model/spvipes.py:539-551); derived entries (scales, softmax,
+        Normal objects) are built on access"""
         P, S = self.n_dimensions_private, self.n_dimensions_shared
         private_stats, shared_stats, poe_stats, library = {}, {}, {}, {}
         for g, w in enumerate(ws):
             st = w.stats
             loc, lv = st[:, :P], st[:, P:2 * P]
-            sc = torch.exp(0.5 * lv)
-            private_stats[g] = OrderedDict(logtheta_loc=loc, logtheta_logvar=lv, logtheta_scale=sc, log_z=w.zpriv,
-                                           theta=torch.softmax(w.zpriv, -1), qz=Normal(loc, sc))
             sloc, slv = st[:, 2 * P:2 * P + S], st[:, 2 * P + S:]
-            ssc = torch.exp(0.5 * slv)
-            shared_stats[g] = OrderedDict(logtheta_loc=sloc, logtheta_logvar=slv, logtheta_scale=ssc, log_z=None, theta=None,
-                                          qz=Normal(sloc, ssc))
-            qsc = w.poe_scale if self.use_labels else w.poe_scale.clamp(min=1e-6)
-            poe_stats[g] = OrderedDict(logtheta_loc=w.poe_loc, logtheta_logvar=w.poe_lv, logtheta_scale=w.poe_scale,
-                                       logtheta_qz=Normal(w.poe_loc, qsc), logtheta_log_z=w.zpoe,
-                                       logtheta_theta=torch.softmax(w.zpoe, -1))
+            clamp = not self.use_labels
+            private_stats[g] = _LazyDict(logtheta_loc=loc, logtheta_logvar=lv,
+                                         logtheta_scale=lambda lv=lv: torch.exp(0.5 * lv), log_z=w.zpriv,
+                                         theta=lambda w=w: torch.softmax(w.zpriv, -1),
+                                         qz=lambda loc=loc, lv=lv: Normal(loc, torch.exp(0.5 * lv)))
+            shared_stats[g] = _LazyDict(logtheta_loc=sloc, logtheta_logvar=slv,
+                                        logtheta_scale=lambda slv=slv: torch.exp(0.5 * slv), log_z=None, theta=None,
+                                        qz=lambda sloc=sloc, slv=slv: Normal(sloc, torch.exp(0.5 * slv)))
+            poe_stats[g] = _LazyDict(logtheta_loc=w.poe_loc, logtheta_logvar=w.poe_lv, logtheta_scale=w.poe_scale,
+                                     logtheta_qz=lambda w=w, clamp=clamp: Normal(w.poe_loc, w.poe_scale.clamp(min=1e-6) if clamp else w.poe_scale),
+                                     logtheta_log_z=w.zpoe, logtheta_theta=lambda w=w: torch.softmax(w.zpoe, -1))
             library[g] = w.lib.unsqueeze(1)
         return {"private_stats": private_stats, "shared_stats": shared_stats, "poe_stats": poe_stats, "library": library}
 
@@ -273,9 +444,22 @@ class spVIPESmodule(nn.Module):
                 generative_kwargs=None, loss_kwargs=None, compute_loss=True):
         """scvi BaseModuleClass.forward: inference -> generative -> loss, here as ONE fused CUDA step"""
         inp = self._get_inference_input(tensors)
-        batches = self._batches(inp["x"], inp["global_indices"], inp.get("labels"), inp.get("processed_labels"))
         kl_weight = float((loss_kwargs or {}).get("kl_weight", 1.0))
         self.engine.set_kl_weight(kl_weight)
+        plan = self._plan_for(inp) if (self.training and torch.is_grad_enabled() and self.capture_steps and self._noise is None) else None
+        if plan is not None:  # captured step: stage the inputs, replay the forward graph; loss.backward() replays the backward graph
+            labels = inp.get("labels") if self.use_labels else inp.get("processed_labels")
+            buf = plan.stage(inp["x"], inp["global_indices"], labels)
+            plan.turn ^= 1
+            self._last_batches = buf["batches"]
+            loss = _GraphStepFunction.apply(self, plan, buf, self._anchor)
+            ws = self._last_ws
+            inference_outputs = self._stats_dicts(ws)
+            generative_outputs = self._generative_dict(ws)
+            if not compute_loss:
+                return inference_outputs, generative_outputs
+            return inference_outputs, generative_outputs, self._loss_output(loss, ws)
+        batches = self._batches(inp["x"], inp["global_indices"], inp.get("labels"), inp.get("processed_labels"))
         self._last_batches = batches
         if self.training and torch.is_grad_enabled():
             loss = _StepFunction.apply(self, batches, True, *[self._torch_params[n] for n in self._param_names])
@@ -290,6 +474,21 @@ class spVIPESmodule(nn.Module):
         if not compute_loss:
             return inference_outputs, generative_outputs
         return inference_outputs, generative_outputs, self._loss_output(loss, ws)
+
+    def _plan_for(self, inp):
+        """captured-step plan for this minibatch signature, or None when the step has to run eagerly (unequal group sizes,
+        unsupported dtypes)"""
+        x = inp["x"]
+        B0, B1 = int(x[0].shape[0]), int(x[1].shape[0])
+        if B0 != B1 or any(x[g].dtype not in (torch.float32, torch.uint16) for g in (0, 1)):
+            return None
+        has_labels = self.use_labels or (self.use_transport_plan and not self.pair_data)
+        key = (B0, x[0].dtype, x[1].dtype, int(x[0].shape[1]), int(x[1].shape[1]), has_labels)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = _CapturedStep(self, {"B": B0, "x_dtypes": (x[0].dtype, x[1].dtype), "labels": has_labels})
+            self._plans[key] = plan
+        return plan
 
     @torch.inference_mode()
     def get_loadings(self, dataset: int, type_latent: str) -> np.ndarray:

@@ -45,14 +45,15 @@ def make_counts(n_cells: Tuple[int, int], genes: Tuple[int, int], n_labels: int 
 
 
 def make_plan(n0: int, n1: int, labels0: torch.Tensor, labels1: torch.Tensor, n_labels: int, device="cuda", seed: int = 7,
-              tau: float = 4.0) -> torch.Tensor:
-    """dense OT-like plan T[i, j] = exp(-|u_i - v_j|^2 / tau) from 8-dim label-centred Gaussian embeddings"""
+              tau: float = 4.0, dtype=torch.float32) -> torch.Tensor:
+    """dense OT-like plan T[i, j] = exp(-|u_i - v_j|^2 / tau) from 8-dim label-centred Gaussian embeddings; dtype bfloat16
+    halves its residency (200k x 200k: 80 GB instead of 160 GB)"""
     gen = torch.Generator(device=device).manual_seed(seed)
     centres = 3.0 * torch.randn(n_labels, 8, generator=gen, device=device)
     u = centres[labels0.long()] + torch.randn(n0, 8, generator=gen, device=device)
     v = centres[labels1.long()] + torch.randn(n1, 8, generator=gen, device=device)
-    T = torch.empty(n0, n1, dtype=torch.float32, device=device)
+    T = torch.empty(n0, n1, dtype=dtype, device=device)
     for r0 in range(0, n0, 4096):
         r1 = min(n0, r0 + 4096)
-        T[r0:r1] = torch.exp(-torch.cdist(u[r0:r1], v) ** 2 / tau)
+        T[r0:r1] = torch.exp(-torch.cdist(u[r0:r1], v) ** 2 / tau).to(dtype)
     return T

@@ -91,3 +91,77 @@ def test_model_api_train_and_latent():
         model.get_latent_representation(gil, batch_size=256, normalized=True)
     load = model.get_loadings()
     assert load[(0, "shared")].shape == (G[0], 12) and load[(1, "private")].shape == (G[1], 6)
+
+
+@pytest.mark.parametrize("mode,precision", [("label", "bf16"), ("paired", "fp32")])
+def test_plugin_call_captured_equals_eager(mode, precision):
+    """`module(batch, loss_kwargs)` -> `loss.backward()` -> torch Adam, driven like scvi's TrainingPlan with pinned host
+    minibatches in scvi's layout (X float32 [B, G0 + G1], [B, 1] float code columns): the captured fast path (two CUDA graphs
+    per buffer set, strided column copy, lazily built output dicts) leaves the same parameters as the eager path."""
+    from spvipes_b200 import synth
+    from spvipes_b200.module import spVIPESmodule
+    B, G0, G1, H, NL, STEPS = 128, 300, 260, 64, 5, 7
+    data = synth.make_counts((4 * B, 4 * B), (G0, G1), NL, device="cuda", seed=9)
+    plan = synth.make_plan(4 * B, 4 * B, data.labels[0], data.labels[1], NL, device="cuda").cpu() if mode == "paired" else None
+    gen = torch.Generator().manual_seed(3)
+    steps = []
+    for s in range(STEPS):
+        batch = []
+        for g in (0, 1):
+            r = torch.randperm(4 * B, generator=gen)[:B]
+            X = torch.zeros(B, G0 + G1)
+            X[:, (0 if g == 0 else G0):(G0 if g == 0 else G0 + G1)] = data.X[g].cpu().to(torch.int32)[r].float()
+            d = {"X": X.pin_memory(), "batch": torch.zeros(B, 1), "groups": torch.full((B, 1), float(g)),
+                 "indices": r.float().reshape(-1, 1).pin_memory()}
+            if mode == "label":
+                d["labels"] = data.labels[g].cpu()[r].float().reshape(-1, 1).pin_memory()
+            batch.append(d)
+        steps.append(tuple(batch))
+    res = []
+    for captured in (False, True):
+        torch.manual_seed(1234)
+        m = spVIPESmodule(groups_lengths={0: G0, 1: G1}, groups_obs_names=[None, None], groups_var_names={0: None, 1: None},
+                          groups_obs_indices=[None, None], groups_var_indices=[np.arange(G0), np.arange(G0, G0 + G1)],
+                          transport_plan=plan, pair_data=mode == "paired", use_labels=mode == "label", n_labels=NL, n_hidden=H,
+                          dropout_rate=0.1, precision=precision)
+        m.capture_steps = captured
+        m.train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, eps=0.01, weight_decay=1e-6)
+        losses = []
+        for s in range(STEPS):
+            opt.zero_grad()
+            inf, gen_out, lo = m(steps[s], loss_kwargs={"kl_weight": 0.1 * s})
+            lo.loss.backward()
+            opt.step()
+            losses.append(float(lo.loss))
+        torch.cuda.synchronize()
+        assert list(inf["private_stats"][0].keys()) == ["logtheta_loc", "logtheta_logvar", "logtheta_scale", "log_z", "theta", "qz"]
+        assert tuple(inf["poe_stats"][1]["logtheta_theta"].shape) == (B, 25)  # lazily built entries materialise on access
+        res.append((m.engine.params.flat.clone(), m.engine.buffers.flat.clone(), losses))
+    assert all(np.isfinite(res[1][2]))
+    assert float((res[0][0] - res[1][0]).abs().max()) <= 1e-6 * float(res[0][0].abs().max()), "parameters differ"
+    assert float((res[0][1] - res[1][1]).abs().max()) <= 1e-5 * float(res[0][1].abs().max()), "running statistics differ"
+    assert max(abs(a - b) for a, b in zip(res[0][2], res[1][2])) <= 1e-5 * abs(res[0][2][0])
+
+
+def test_flat_adam_equals_torch_adam():
+    """spvipes_b200.optim.FlatAdam (one fused launch over the flat buffers, refreshes the 16-bit operand copies) walks the same
+    trajectory as torch.optim.Adam with scvi's TrainingPlan hyper-parameters, driven through the plugin call"""
+    from spvipes_b200.optim import FlatAdam
+    gd = Golden("label_medium")
+    res = []
+    for flat in (False, True):
+        torch.manual_seed(7)
+        m, batch = _module_from_golden(gd)
+        m._noise = None
+        m.engine.dropout_rate = 0.0
+        m.train()
+        opt = FlatAdam(m) if flat else torch.optim.Adam(m.parameters(), lr=1e-3, eps=0.01, weight_decay=1e-6)
+        for s in range(6):
+            opt.zero_grad()
+            _, _, lo = m(batch, loss_kwargs={"kl_weight": 0.3})
+            lo.loss.backward()
+            opt.step()
+        torch.cuda.synchronize()
+        res.append(m.engine.params.flat.clone())
+    assert float((res[0] - res[1]).abs().max()) <= 2e-6 * float(res[0].abs().max())
