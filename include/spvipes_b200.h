@@ -221,11 +221,12 @@ int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, int G, int P
 /* d zz = dmix (latent columns of d [hm | zz]) + dzraw (optional further addends [B, P+S]: softmax-branch and hidden-layer
  * input gradients when they are not in dmix) - BatchNorm coupling terms, the latter summed from the `nparts` per-CTA
  * partials (vpart [nparts, P+S], mpart [nparts, (P+S)^2]) that spv_dec_gene_bwd writes (its last two ptrs).
- * centre_raw != 0 (tensor-core path): the mean-coupling term is taken as the column mean of dzraw itself instead of vpart, so
- * that the coherent operand-rounding error of the GEMM that produced dzraw cancels instead of surviving as a column mean. */
+ * raw_colsum != NULL (tensor-core path; [P+S] column sums of dzraw, spv_colsum): the mean-coupling term is taken as the column
+ * mean of dzraw itself instead of vpart, so that the coherent operand-rounding error of the GEMM that produced dzraw cancels
+ * instead of surviving as a column mean. */
 int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* vpart, const float* mpart,
                         int nparts, const float* zz, long long ld_zz, const float* zmean, float* dzz, int B, int P, int S,
-                        int centre_raw, void* stream);
+                        const float* raw_colsum, void* stream);
 
 /* *step += 1 on the stream: the optimiser's step count, and (a separate counter) the Philox stream position that the noise /
  * dropout kernels read - the two must not share a counter, the backward regenerates its noise from the forward's value. */

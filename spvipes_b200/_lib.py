@@ -61,7 +61,7 @@ _SIGS = {
     "spv_dec_nb_part_floats": [i, i],
     "spv_dec_stats_tc": [p, p, i, p, p, p, p, i, i, i, i, p],
     "spv_to_bf16_block": [p, ll, p, ll, i, i, i, p],
-    "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, i, p],
+    "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, p, p],
     "spv_adam_tick": [p, p],
     "spv_adam": [p, p, p, p, ll, f, f, f, f, f, f, p, p, i, p, p, p, p, p, p, p, i, p],
 }

@@ -282,9 +282,55 @@ __global__ void rowstat_kernel(const float* __restrict__ part, int nTG, int B, c
     }
 }
 
+// Many gene tiles (20k genes: 626 partials per row): one CTA per 32 rows, lanes over the rows so that every load of a warp is
+// one contiguous 512-byte run of the [tile][row] layout, the 8 warps split the tiles and merge their running (max, sum) pairs
+// through shared memory in warp order (deterministic).  The warp-per-row form above reads 16 useful bytes per 32-byte sector.
+__global__ void __launch_bounds__(256) rowstat_wide_kernel(const float* __restrict__ part, int nTG, int B, const float* __restrict__ lib,
+                                                           float* __restrict__ rowc) {
+    __shared__ float4 red[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + lane;
+    const bool ok = b < B;
+    float Mp = -INFINITY, Ms = -INFINITY, Sp = 0.0f, Ss = 0.0f;
+    const float4* src = reinterpret_cast<const float4*>(part) + (ok ? b : 0);
+    constexpr int U = 8;
+    for (int t0 = w; t0 < nTG; t0 += 8 * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t0 + 8 * u;
+            v[u] = (ok && t < nTG) ? __ldg(src + (long)t * B) : make_float4(-INFINITY, 0.0f, -INFINITY, 0.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {  // online merge of (max, sum exp) pairs
+            const float np = fmaxf(Mp, v[u].x), ns = fmaxf(Ms, v[u].z);
+            if (np > -INFINITY) Sp = Sp * __expf(Mp - np) + v[u].y * __expf(v[u].x - np);
+            if (ns > -INFINITY) Ss = Ss * __expf(Ms - ns) + v[u].w * __expf(v[u].z - ns);
+            Mp = np; Ms = ns;
+        }
+    }
+    red[w][lane] = make_float4(Mp, Sp, Ms, Ss);
+    __syncthreads();
+    if (w == 0 && ok) {
+        float4 a = red[0][lane];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) {
+            const float4 c = red[i][lane];
+            const float np = fmaxf(a.x, c.x), ns = fmaxf(a.z, c.z);
+            if (np > -INFINITY) a.y = a.y * __expf(a.x - np) + c.y * __expf(c.x - np);
+            if (ns > -INFINITY) a.w = a.w * __expf(a.z - ns) + c.w * __expf(c.z - ns);
+            a.x = np; a.z = ns;
+        }
+        const float l = __ldg(lib + b);
+        rowc[(long)b * 4 + 0] = l - (a.x + logf(a.y));
+        rowc[(long)b * 4 + 1] = l - (a.z + logf(a.w));
+    }
+}
+
 // launch helper shared with the tensor-core statistics kernel (nb_tc.cu)
 int spv_internal_rowstat(const float* part, int nparts, int B, const float* lib, float* rowc, cudaStream_t st) {
-    rowstat_kernel<<<(B + 7) / 8, 256, 0, st>>>(part, nparts, B, lib, rowc);
+    if (nparts > 128) rowstat_wide_kernel<<<(B + 31) / 32, 256, 0, st>>>(part, nparts, B, lib, rowc);
+    else rowstat_kernel<<<(B + 7) / 8, 256, 0, st>>>(part, nparts, B, lib, rowc);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

@@ -521,10 +521,9 @@ __global__ void __launch_bounds__(DZC_THREADS) dzz_combine_kernel(const float* _
                                                                   const float* __restrict__ mpart, int nparts,
                                                                   const float* __restrict__ zz, long ld_zz,
                                                                   const float* __restrict__ zmean, float* __restrict__ dzz, int B,
-                                                                  int P, int S, int centre_raw) {
+                                                                  int P, int S, const float* __restrict__ raw_colsum) {
     __shared__ float red[8][100];
     __shared__ float srow[100];  // [0, n): M[c, lo + .],  [n]: v1[c]
-    __shared__ float cred[8];
     const int KZ = P + S;
     const int c = blockIdx.x;
     const int lo = c < P ? 0 : P, n = c < P ? P : S;
@@ -548,22 +547,12 @@ __global__ void __launch_bounds__(DZC_THREADS) dzz_combine_kernel(const float* _
         srow[threadIdx.x] = s;
     }
     __syncthreads();
-    if (centre_raw) {
+    if (raw_colsum) {
         // v1 is the column mean of the uncorrected input gradient sum_g a dy W (BatchNorm backward: the corrected one sums to
         // zero over the minibatch).  dzraw came out of a reduced-precision GEMM while vpart is exact fp32, so subtracting the
         // exact v1 would leave the GEMM's coherent rounding error as a spurious column mean; the mean of dzraw itself cancels
         // exactly (its other addend, the hidden layer's BatchNorm backward, has zero column mean as well).
-        float s = 0.0f;
-        for (int t = threadIdx.x; t < B; t += DZC_THREADS) s += dzraw[(long)t * KZ + c];
-        s = warp_sum(s);
-        if (lane == 0) cred[q] = s;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float tot = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) tot += cred[i];
-            srow[n] = tot / (float)B;
-        }
+        if (threadIdx.x == 0) srow[n] = __ldg(raw_colsum + c) / (float)B;
         __syncthreads();
     }
     const int b = blockIdx.y * DZC_THREADS + threadIdx.x;
@@ -576,13 +565,13 @@ __global__ void __launch_bounds__(DZC_THREADS) dzz_combine_kernel(const float* _
 
 extern "C" int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* vpart, const float* mpart,
                                    int nparts, const float* zz, long long ld_zz, const float* zmean, float* dzz, int B, int P,
-                                   int S, int centre_raw, void* stream) {
+                                   int S, const float* raw_colsum, void* stream) {
     if (!dmix || !vpart || !mpart || !zz || !zmean || !dzz || B <= 0 || P <= 0 || S <= 0 || nparts <= 0 || P > 96 || S > 96)
         return SPV_ERR_ARG;
-    if (centre_raw && !dzraw) return SPV_ERR_ARG;
+    if (raw_colsum && !dzraw) return SPV_ERR_ARG;
     dim3 grid(P + S, (B + DZC_THREADS - 1) / DZC_THREADS);
     dzz_combine_kernel<<<grid, DZC_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dmix, ld_dmix, dzraw, vpart, mpart, nparts,
-                                                                                         zz, ld_zz, zmean, dzz, B, P, S, centre_raw);
+                                                                                         zz, ld_zz, zmean, dzz, B, P, S, raw_colsum);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

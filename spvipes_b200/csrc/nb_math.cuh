@@ -63,42 +63,51 @@ __device__ __forceinline__ void nb_fill_count_lut(float2* lut, int i) {
 
 struct NbGene { float cpl, csl, bm, th, thE, K; };
 
+// v4 (r2): the same algebra with 11 (forward) / 10 (backward) SFU operations per element instead of 16 / 15.  At the C5 shape
+// the forward sweep ran at 61 % of the SFU pipe's peak (bench.py roofline.other), so SFU operations are what to cut:
+//   * independent reciprocals share one rcp:  1/d1, 1/d2, 1/y from rcp(d1 d2 y);  1/o1, 1/o2 from rcp(o1 o2)  (2 extra FMULs per
+//     shared factor; the products stay far inside fp32's range: d <= rho + theta, y = t + theta + 4, o <= 2)
+//   * log2(rho + eps) = x (the logit, rho = 2^x) and rho / (rho + eps) = 1 unless rho < 1e-6, where the EXACT variant runs
+//     (the first-order eps / rho term of v3 cost two reciprocals; it only matters for elements with a positive count under an
+//     expected count below 1e-4, whose probability is of the order of that expected count).
 template <bool EXACT>
 __device__ __forceinline__ NbOut nb_forward_v3(float t, float lgt1, float accp, float accs, float accpi, const NbGene& g, float Rpl,
                                                float Rsl, bool& rare) {
     const float xp = fmaf(accp, NB_LOG2E, g.cpl + Rpl), xs = fmaf(accs, NB_LOG2E, g.csl + Rsl);
     const float pi = accpi + g.bm;
     const float rp = fast_ex2(xp), rs = fast_ex2(xs);
-    const float ap = rp + NB_EPS, as = rs + NB_EPS;
     const float d1 = rp + g.thE, d2 = rs + g.thE;
-    const float iap = fast_rcp(ap), ias = fast_rcp(as), id1 = fast_rcp(d1), id2 = fast_rcp(d2);
-    const float L1 = fast_lg2(d1), L2 = fast_lg2(d2);
-    float Lap, Las;  // log2(rho + eps): from the logit (rho = 2^x) unless rho < ~1e-6
-    if (EXACT) {
-        Lap = fast_lg2(ap); Las = fast_lg2(as);
-    } else {
-        const float wp = NB_EPS * iap, ws = NB_EPS * ias;
-        rare = rare || fmaxf(wp, ws) > 0.01f;
-        Lap = fmaf(wp, NB_LOG2E, xp); Las = fmaf(ws, NB_LOG2E, xs);
-    }
     // lgamma(x), x = t + th: shift by 4, P = x (x+1) (x+2) (x+3) = q (q + 2) with q = x (x + 3); Stirling at y = x + 4
     const float x = t + g.th;
     const float q = x * (x + 3.0f), P = q * (q + 2.0f), y = x + 4.0f;
-    const float iy = fast_rcp(y), iy2 = iy * iy;
+    const float d12 = d1 * d2;
+    const float r3 = fast_rcp(d12 * y);
+    const float id1 = r3 * (d2 * y), id2 = r3 * (d1 * y), iy = r3 * d12, iy2 = iy * iy;
+    const float L1 = fast_lg2(d1), L2 = fast_lg2(d2);
+    float Lap, Las, fp, fs;  // log2(rho + eps) and rho / (rho + eps)
+    if (EXACT) {
+        const float ap = rp + NB_EPS, as = rs + NB_EPS;
+        Lap = fast_lg2(ap); Las = fast_lg2(as);
+        fp = rp * fast_rcp(ap); fs = rs * fast_rcp(as);
+    } else {
+        rare = rare || fminf(rp, rs) < 1e-6f;
+        Lap = xp; Las = xs; fp = 1.0f; fs = 1.0f;
+    }
     const float lgv = fmaf(fmaf(y - 0.5f, fast_lg2(y), -fast_lg2(P)), NB_LN2, fmaf(iy, fmaf(iy2, -0.0027777778f, 0.083333333f), -y));
     // a = K0 + lgv - lgt1 - ln2 m1,  b = K0 + lgv - lgt1 - ln2 m2 - pi,  m = x log2(th + rho + eps) - t log2(rho + eps)
     const float m1 = fmaf(-t, Lap, x * L1), m2 = fmaf(-t, Las, x * L2);
     const float df = fmaf(m2 - m1, NB_LN2, pi);  // a - b
     const float e = fast_ex2(-NB_LOG2E * fabsf(df)), epi = fast_ex2(-NB_LOG2E * fabsf(pi));
     const float o1 = 1.0f + e, o2 = 1.0f + epi;
-    const float i1 = fast_rcp(o1), i2 = fast_rcp(o2);
+    const float r2 = fast_rcp(o1 * o2);
+    const float i1 = r2 * o2, i2 = r2 * o1;
     NbOut o;
     // logsumexp(a, b) - softplus(-pi) = a + max(0, -df) - max(-pi, 0) + log((1 + e) / (1 + epi))
     o.ll = (g.K + lgv - lgt1) + fmaf(m1, -NB_LN2, fmaxf(-df, 0.0f)) - fmaxf(-pi, 0.0f) + NB_LN2 * fast_lg2(o1 * i2);
     const float wmin = e * i1;
     const float wa = df >= 0.0f ? 1.0f - wmin : wmin, wb = 1.0f - wa;
-    o.ep = wa * fmaf(t, iap, -x * id1) * rp;
-    o.es = wb * fmaf(t, ias, -x * id2) * rs;
+    o.ep = wa * fmaf(t, fp, -(x * id1) * rp);
+    o.es = wb * fmaf(t, fs, -(x * id2) * rs);
     return o;
 }
 
@@ -108,33 +117,35 @@ __device__ __forceinline__ NbGrad nb_backward_v3(float t, float accp, float accs
     const float xp = fmaf(accp, NB_LOG2E, g.cpl + Rpl), xs = fmaf(accs, NB_LOG2E, g.csl + Rsl);
     const float pi = accpi + g.bm;
     const float rp = fast_ex2(xp), rs = fast_ex2(xs);
-    const float ap = rp + NB_EPS, as = rs + NB_EPS;
     const float d1 = rp + g.thE, d2 = rs + g.thE;
-    const float iap = fast_rcp(ap), ias = fast_rcp(as), id1 = fast_rcp(d1), id2 = fast_rcp(d2);
-    const float L1 = fast_lg2(d1), L2 = fast_lg2(d2);
-    float Lap, Las;
-    if (EXACT) {
-        Lap = fast_lg2(ap); Las = fast_lg2(as);
-    } else {
-        const float wp = NB_EPS * iap, ws = NB_EPS * ias;
-        rare = rare || fmaxf(wp, ws) > 0.01f;
-        Lap = fmaf(wp, NB_LOG2E, xp); Las = fmaf(ws, NB_LOG2E, xs);
-    }
     const float x = t + g.th;
-    const float m1 = fmaf(-t, Lap, x * L1), m2 = fmaf(-t, Las, x * L2);
-    const float df = fmaf(m2 - m1, NB_LN2, pi);
     // digamma(x): psi(x) = psi(x + 4) - P'(x) / P(x), P = q (q + 2), q = x (x + 3), P' = (2 q + 2)(2 x + 3); series at y = x + 4
     const float q = x * (x + 3.0f), P = q * (q + 2.0f), y = x + 4.0f;
+    const float ra = fast_rcp(d1 * d2), rb = fast_rcp(y * P);
+    const float id1 = ra * d2, id2 = ra * d1, iy = rb * P, iP = rb * y, iy2 = iy * iy;
+    const float L1 = fast_lg2(d1), L2 = fast_lg2(d2);
+    float Lap, Las, fp, fs;
+    if (EXACT) {
+        const float ap = rp + NB_EPS, as = rs + NB_EPS;
+        Lap = fast_lg2(ap); Las = fast_lg2(as);
+        fp = rp * fast_rcp(ap); fs = rs * fast_rcp(as);
+    } else {
+        rare = rare || fminf(rp, rs) < 1e-6f;
+        Lap = xp; Las = xs; fp = 1.0f; fs = 1.0f;
+    }
+    const float m1 = fmaf(-t, Lap, x * L1), m2 = fmaf(-t, Las, x * L2);
+    const float df = fmaf(m2 - m1, NB_LN2, pi);
     const float num = fmaf(q, 2.0f, 2.0f) * fmaf(x, 2.0f, 3.0f);
-    const float iy = fast_rcp(y), iP = fast_rcp(P), iy2 = iy * iy;
     const float ser = iy2 * fmaf(iy2, fmaf(iy2, 0.003968254f, -0.0083333333f), 0.083333333f);
     const float psi = fmaf(fast_lg2(y), NB_LN2, fmaf(-0.5f, iy, -ser)) - num * iP;
     const float e = fast_ex2(-NB_LOG2E * fabsf(df)), epi = fast_ex2(-NB_LOG2E * fabsf(pi));
-    const float i1 = fast_rcp(1.0f + e), i2 = fast_rcp(1.0f + epi);
+    const float o1 = 1.0f + e, o2 = 1.0f + epi;
+    const float r2 = fast_rcp(o1 * o2);
+    const float i1 = r2 * o2, i2 = r2 * o1;
     const float wmin = e * i1;
     const float wa = df >= 0.0f ? 1.0f - wmin : wmin, wb = 1.0f - wa;
     const float q1 = x * id1, q2 = x * id2;
-    const float ep = wa * fmaf(t, iap, -q1) * rp, es = wb * fmaf(t, ias, -q2) * rs;
+    const float ep = wa * fmaf(t, fp, -q1 * rp), es = wb * fmaf(t, fs, -q2 * rs);
     const float sneg = (pi >= 0.0f ? epi : 1.0f) * i2;  // sigmoid(-pi)
     NbGrad o;
     o.dyp = scale * fmaf(-rp, DpI, ep);

@@ -42,7 +42,7 @@ constexpr int TMEM_COLS = BN == 64 ? 256 : 128;           // single allocation o
 constexpr int ACC_COLS = BN, Z_COLS = 2 * BN;             // the likelihood kernels allocate in two steps (powers of two >= 32)
 static_assert(ACC_COLS == 32 || ACC_COLS == 64, "tensor-memory allocations are powers of two");
 constexpr int CNT_PITCH_W = BN / 2 + 1;  // uint16 count tile: 33 32-bit words per row, conflict-free for thread = row reads
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 6 * BN * 4 + 256 * 8 + 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 8 * BN * 4 + 256 * 8 + 256;
 
 static_assert(BM * CNT_PITCH_W * 4 <= STAGES * STAGE_BYTES, "count tile must fit in the operand stages");
 
@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
     uint8_t* tiles = smem_raw + pad;
     uint8_t* z_tiles = tiles + STAGES * STAGE_BYTES;                    // folded private | shared weights, [BN][64] bf16 each
-    float* s_gc = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);      // [6][BN]: cp, cs, theta, lte, lgt, bm
-    float2* s_lut = reinterpret_cast<float2*>(s_gc + 6 * BN);         // [256]: (log1p(c), lgamma(log1p(c) + 1)) per raw count
+    float* s_gc = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);      // [BN][8] gene-major: cpl, csl, bm, theta | theta + eps, K0, -, -  (two 128-bit loads per element)
+    float2* s_lut = reinterpret_cast<float2*>(s_gc + 8 * BN);         // [256]: (log1p(c), lgamma(log1p(c) + 1)) per raw count
     uint64_t* full = reinterpret_cast<uint64_t*>(s_lut + 256);
     uint64_t* empty = full + STAGES;
     uint64_t* z_full = empty + STAGES;
@@ -261,8 +261,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
             }
         }
         if (et < BN) {
-#pragma unroll
-            for (int j = 0; j < 6; ++j) s_gc[j * BN + et] = gcv[j];
+            *reinterpret_cast<float4*>(s_gc + et * 8) = make_float4(gcv[0], gcv[1], gcv[2], gcv[3]);
+            *reinterpret_cast<float4*>(s_gc + et * 8 + 4) = make_float4(gcv[4], gcv[5], 0.0f, 0.0f);
         }
         Rpl *= NB_LOG2E; Rsl *= NB_LOG2E;
         const long xrow = (long)my_row * p.ldx;
@@ -298,8 +298,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
                 pv[jj] = 0.0f;
                 if (g < p.G) {
                     NbGene ge;
-                    ge.cpl = s_gc[0 * BN + gl]; ge.csl = s_gc[1 * BN + gl]; ge.bm = s_gc[2 * BN + gl];
-                    ge.th = s_gc[3 * BN + gl]; ge.thE = s_gc[4 * BN + gl]; ge.K = s_gc[5 * BN + gl];
+                    const float4 ga = *reinterpret_cast<const float4*>(s_gc + gl * 8), gb = *reinterpret_cast<const float4*>(s_gc + gl * 8 + 4);
+                    ge.cpl = ga.x; ge.csl = ga.y; ge.bm = ga.z; ge.th = ga.w; ge.thE = gb.x; ge.K = gb.y;
                     const float piv = __uint_as_float(rpi[jj]) + ge.bm;
                     float2 tl;
                     if (SRC == SPV_SRC_U16_LOG1P) {
@@ -473,6 +473,41 @@ __global__ void rownb_tc_kernel(const float* __restrict__ part, int nPart, int B
     }
 }
 
+// wide variant for many gene tiles: one CTA per 32 rows, lanes over rows (each warp load is one contiguous 384-byte run of the
+// [tile][row][3] layout), 8 warps split the tiles, fixed-order merge through shared memory
+__global__ void __launch_bounds__(256) rownb_tc_wide_kernel(const float* __restrict__ part, int nPart, int B, float* __restrict__ rowc,
+                                                            float* __restrict__ rec) {
+    __shared__ float red[8][3][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + lane;
+    const bool ok = b < B;
+    float ll = 0.0f, dp = 0.0f, ds = 0.0f;
+    const float* src = part + (long)(ok ? b : 0) * 3;
+    constexpr int U = 8;
+    for (int t0 = w; t0 < nPart; t0 += 8 * U) {
+        float v[U][3];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t0 + 8 * u;
+            const bool in = ok && t < nPart;
+            const float* o = src + (long)t * B * 3;
+            v[u][0] = in ? __ldg(o) : 0.0f; v[u][1] = in ? __ldg(o + 1) : 0.0f; v[u][2] = in ? __ldg(o + 2) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { ll += v[u][0]; dp += v[u][1]; ds += v[u][2]; }
+    }
+    red[w][0][lane] = ll; red[w][1][lane] = dp; red[w][2][lane] = ds;
+    __syncthreads();
+    if (w == 0 && ok) {
+        float a = 0.0f, c = 0.0f, d = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a += red[i][0][lane]; c += red[i][1][lane]; d += red[i][2][lane]; }
+        rec[b] = -a;
+        rowc[(long)b * 4 + 2] = c;
+        rowc[(long)b * 4 + 3] = d;
+    }
+}
+
 }  // namespace
 
 // per-device one-time kernel attribute (the attribute is per device; a process may drive several)
@@ -569,7 +604,9 @@ extern "C" long long spv_dec_nb_part_floats(int B, int G) {
 // rec[b] = - sum over the row partials of spv_dec_nb_fwd_tc (same B, G, HD); also the softmax-backward row sums rowc[:, 2:4]
 extern "C" int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, int HD, float* rowc, float* rec, void* stream) {
     if (!part_nb || !rowc || !rec || G <= 0 || B <= 0 || HD < 0) return SPV_ERR_ARG;
-    rownb_tc_kernel<<<(B + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part_nb, 2 * ((G + BN - 1) / BN), B, rowc, rec);
+    const int nPart = 2 * ((G + BN - 1) / BN);
+    if (nPart > 128) rownb_tc_wide_kernel<<<(B + 31) / 32, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part_nb, nPart, B, rowc, rec);
+    else rownb_tc_kernel<<<(B + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(part_nb, nPart, B, rowc, rec);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

@@ -22,7 +22,7 @@ constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTE
 constexpr int ACC_COLS = BN, Z_COLS = 2 * BN;  // tensor memory is allocated in two steps (powers of two >= 32)
 static_assert(ACC_COLS == 32 || ACC_COLS == 64, "tensor-memory allocations are powers of two");
 constexpr int CNT_PITCH_W = BN / 2 + 1;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 7 * BN * 4 + 4 * 4 * BN * 4 + 256 * 4 + 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 8 * BN * 4 + 4 * 4 * BN * 4 + 256 * 4 + 256;
 
 static_assert(BM * CNT_PITCH_W * 4 <= STAGES * STAGE_BYTES, "count tile must fit in the operand stages");
 
@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
     uint8_t* tiles = smem_raw + pad;
     uint8_t* z_tiles = tiles + STAGES * STAGE_BYTES;
-    float* s_gc = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);  // [7][BN]: cp, cs, theta, lte, dgt, bm, theta / (theta + eps)
-    float* s_col = s_gc + 7 * BN;                                    // [4 quantities][4 quarters][BN]
+    float* s_gc = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);  // [BN][8] gene-major: cpl, csl, bm, theta | theta + eps, K1, -, -
+    float* s_col = s_gc + 8 * BN;                                    // [4 quantities][4 quarters][BN]
     float* s_lut = s_col + 16 * BN;                                  // [256]: log1p(c) per raw count
     uint64_t* full = reinterpret_cast<uint64_t*>(s_lut + 256);
     uint64_t* empty = full + STAGES;
@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
             }
         }
         if (et < BN) {
-#pragma unroll
-            for (int j = 0; j < 6; ++j) s_gc[j * BN + et] = gcv[j];
+            *reinterpret_cast<float4*>(s_gc + et * 8) = make_float4(gcv[0], gcv[1], gcv[2], gcv[3]);
+            *reinterpret_cast<float4*>(s_gc + et * 8 + 4) = make_float4(gcv[4], gcv[5], 0.0f, 0.0f);
         }
         const float Rpl = NB_LOG2E * rc.x, Rsl = NB_LOG2E * rc.y;
         const float inv_elib = fast_exp(-libm);
@@ -264,8 +264,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
                 vyp[jj] = vys[jj] = vpi[jj] = vth[jj] = 0.0f;
                 if (mok && g < p.G) {
                     NbGene ge;
-                    ge.cpl = s_gc[0 * BN + gl]; ge.csl = s_gc[1 * BN + gl]; ge.bm = s_gc[2 * BN + gl];
-                    ge.th = s_gc[3 * BN + gl]; ge.thE = s_gc[4 * BN + gl]; ge.K = s_gc[5 * BN + gl];
+                    const float4 ga = *reinterpret_cast<const float4*>(s_gc + gl * 8), gb = *reinterpret_cast<const float4*>(s_gc + gl * 8 + 4);
+                    ge.cpl = ga.x; ge.csl = ga.y; ge.bm = ga.z; ge.th = ga.w; ge.thE = gb.x; ge.K = gb.y;
                     float t;
                     if (SRC == SPV_SRC_U16_LOG1P) {
                         uint32_t w = s_cnt[rloc * CNT_PITCH_W + (gl >> 1)];

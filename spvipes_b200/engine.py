@@ -240,6 +240,7 @@ class _GroupWS:
             self.colpart, self.colsum = f(self.nTB, 4, G), f(4, G)
             self.Qp, self.Qs = f(G, P), f(G, S)
             self.damix, self.dzraw, self.dzz = f(B, KMIX), f(B, KZ), f(B, KZ)
+            self.dzraw_sum = f(KZ)
             self.nGB = L.load().spv_dec_gene_bwd_parts(G)
             self.vpart, self.mpart = f(self.nGB, KZ), f(self.nGB, KZ * KZ)  # per-CTA partials of spv_dec_gene_bwd
             self.dah = f(B, HD)
@@ -807,10 +808,12 @@ class StepEngine:
             if not self.fused_nb:
                 self._gene_bwd(g, w, Qp, Qs, ldq, B, G)
             self._join(g, "hid")
+            if self.fused_nb:  # column sums of the branch / hidden-layer input gradient (the consistent mean-coupling term)
+                L.check(lib.spv_colsum(dzraw, KZ, B, KZ, L.ptr(w.dzraw_sum), st), "spv_colsum")
             self._join(g, "gene")
             L.check(lib.spv_dec_dzz_combine(w.damix.data_ptr() + 4 * HD, KMIX, dzraw, L.ptr(w.vpart), L.ptr(w.mpart),
-                                            w.nGB, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S, 1 if self.fused_nb else 0, st),
-                    "spv_dec_dzz_combine")
+                                            w.nGB, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S,
+                                            L.ptr(w.dzraw_sum) if self.fused_nb else None, st), "spv_dec_dzz_combine")
         # ---------------- PoE
         own = self._poe_sides(ws)
         arrs = []

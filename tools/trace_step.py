@@ -32,7 +32,7 @@ def main():
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    mode, n_cells, genes, H, B, n_labels = bench.WORKLOADS[a.workload]
+    mode, n_cells, genes, H, B, n_labels, _plan_dtype = bench.WORKLOADS[a.workload]
     n_cells = a.cells or n_cells
     L.load()
     data = synth.make_counts((n_cells, n_cells), (genes, genes), n_labels, device=dev, seed=1234)
