@@ -242,7 +242,7 @@ class spVIPES:
     @torch.no_grad()
     def get_latent_representation(self, group_indices_list: Sequence[Sequence[int]], adata=None, indices=None,
                                   normalized: bool = False, give_mean: bool = True, mc_samples: int = 5000,
-                                  batch_size: Optional[int] = None, drop_last: Optional[bool] = None) -> dict:
+                                  batch_size: Optional[int] = None, drop_last: Optional[bool] = None, _noise_fn=None) -> dict:
         """reference model/spvipes.py:424-650: sequential minibatches, the shorter group cycled (zip(largest, cycle(other))),
         module in eval mode; returns the SAMPLED log_z of the PoE / private posteriors, truncated to the group sizes and
         re-ordered by within-group index.
@@ -250,35 +250,59 @@ class spVIPES:
         normalized=True cannot complete in the reference either: _process_batches appends nothing to the shared lists in that
         branch (spvipes.py:542-544, 552) and _format_results then calls torch.cat on the empty lists (:634-635), which raises
         RuntimeError; with give_mean=False it fails earlier on an unbound local (:556-563).  The same error type is raised here
-        instead of inventing a result the reference never produced."""
+        instead of inventing a result the reference never produced.
+
+        _noise_fn (tests): callable(batch number, B0, B1) -> engine.Noise with the eps of that minibatch; None = in-kernel Philox."""
         if normalized:
             raise RuntimeError("normalized=True: the reference collects no shared latents in this branch and fails in "
                                "torch.cat on an empty list (model/spvipes.py:542-544, 634); use normalized=False")
         self._to_device()
         eng = self.module.engine
-        batch_size = batch_size or 128
+        batch_size = batch_size or 128  # scvi.settings.batch_size
         n = [len(g) for g in group_indices_list]
         self.module.eval()
-        chunks = [[np.asarray(gi)[k:k + batch_size] for k in range(0, len(gi), batch_size)] for gi in group_indices_list]
-        largest = int(np.argmax([len(c) for c in chunks]))
-        its = [iter(c) if g == largest else cycle(c) for g, c in enumerate(chunks)]
+        # reference :478-515: drop_last defaults to False in every mode; the paired OT mode (no labels) then goes through the
+        # cycling path, every other mode through one ConcatDataLoader over the two index lists
+        drop_last = False if drop_last is None else bool(drop_last)
+        use_cycling = eng.mode == "paired" and not drop_last
         res = {"shared": [[], []], "private": [[], []], "idx": [[], []]}
-        for st in zip(*its):
-            if len(st[0]) != len(st[1]) and eng.mode != "label":
-                m = min(len(st[0]), len(st[1]))  # the OT modes need equally sized minibatches (reference :521-523)
-                st = [s[:m] for s in st]
-            rows = [torch.from_numpy(self._local_rows(g, st[g]).astype(np.int32)).to(eng.device) for g in (0, 1)]
-            batches = []
-            for g in (0, 1):
-                d = self._device_data[g]
-                r = rows[g].long()
-                lab = d["labels"][r].contiguous() if d["labels"] is not None else None
-                batches.append(GroupBatch(X=d["X"], rows=rows[g], labels=lab, idx=d["idx"][r].contiguous(), B=len(st[g])))
-            ws = eng.forward(batches, training=False, with_grad=False, decode=False)
-            for g in (0, 1):
-                res["shared"][g].append(ws[g].zpoe.cpu().clone())
-                res["private"][g].append(ws[g].zpriv.cpu().clone())
-                res["idx"][g].append(batches[g].idx.cpu().clone())
+        counter = [0]
+
+        def process(index_lists):
+            """reference _process_batches (:537-576) over ConcatDataLoader(shuffle=False): sequential chunks per group, the
+            loader with the most batches drives and the other one is cycled (dataloaders/_concat_dataloader.py:101-110)"""
+            chunks = [[np.asarray(gi)[k:k + batch_size] for k in range(0, len(gi), batch_size)] for gi in index_lists]
+            if drop_last:
+                chunks = [[c for c in ch if len(c) == batch_size] for ch in chunks]
+            largest = int(np.argmax([len(c) for c in chunks]))
+            its = [iter(c) if g == largest else cycle(c) for g, c in enumerate(chunks)]
+            for st in zip(*its):
+                rows = [torch.from_numpy(self._local_rows(g, st[g]).astype(np.int32)).to(eng.device) for g in (0, 1)]
+                batches = []
+                for g in (0, 1):
+                    d = self._device_data[g]
+                    r = rows[g].long()
+                    lab = d["labels"][r].contiguous() if d["labels"] is not None else None
+                    batches.append(GroupBatch(X=d["X"], rows=rows[g], labels=lab, idx=d["idx"][r].contiguous(), B=len(st[g])))
+                noise = _noise_fn(counter[0], len(st[0]), len(st[1])) if _noise_fn is not None else None
+                counter[0] += 1
+                ws = eng.forward(batches, training=False, noise=noise, with_grad=False, decode=False)
+                for g in (0, 1):
+                    res["shared"][g].append(ws[g].zpoe.cpu().clone())
+                    res["private"][g].append(ws[g].zpriv.cpu().clone())
+                    res["idx"][g].append(batches[g].idx.cpu().clone())
+
+        if use_cycling:
+            # reference _process_all_cells_with_cycling (:578-626): chunks of min(n) cells, the indices of BOTH groups taken
+            # modulo their group's length, each chunk through its own loader
+            lo, hi = min(n), max(n)
+            if lo == 0:
+                raise ValueError("One of the groups is empty")
+            for start in range(0, hi, lo):
+                process([[group_indices_list[g][(start + i) % n[g]] for i in range(lo)] for g in (0, 1)])
+        else:
+            process(group_indices_list)
+        # reference _format_results (:628-650): truncate to the group sizes; group 2 re-ordered by its within-group index
         shared = {g: torch.cat(res["shared"][g]).numpy()[:n[g]] for g in (0, 1)}
         private = {g: torch.cat(res["private"][g]).numpy()[:n[g]] for g in (0, 1)}
         idx2 = torch.cat(res["idx"][1]).numpy().flatten()[:n[1]]

@@ -165,3 +165,46 @@ def test_flat_adam_equals_torch_adam():
         torch.cuda.synchronize()
         res.append(m.engine.params.flat.clone())
     assert float((res[0] - res[1]).abs().max()) <= 2e-6 * float(res[0].abs().max())
+
+
+@pytest.mark.parametrize("name", ["latent_label_ragged", "latent_paired_cycling", "latent_cluster_equal"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_get_latent_representation_matches_reference(name, precision):
+    """model-level latent extraction (reference model/spvipes.py:424-650) against fixtures produced by the UNMODIFIED reference
+    module driven through the reference's batching (oracle/make_golden_latent.py): sequential minibatches with the shorter loader
+    cycled, ragged last batches, the paired mode's cycling over chunks of min(n) cells, truncation and the argsort of group 2,
+    same injected noise per minibatch.  Values <= 1e-3 (north_star's latent gate), eval mode (running statistics)."""
+    import os
+    from spvipes_b200.engine import Noise
+    from spvipes_b200.model import GroupedData, prepare_adatas, spVIPES
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_latent", name + ".npz"))
+    mode = str(z["meta_mode"])
+    n0, n1, G0, G1, H, S, P, nl, bs = (int(v) for v in z["meta_dims"])
+    ads = {}
+    for gi, key in enumerate(("a_first", "b_second")):
+        obs = pd.DataFrame({"cell_type": [f"t{int(v)}" for v in z[f"labels{gi}"]]})
+        if mode == "cluster":
+            obs["processed_transport_labels"] = z[f"labels{gi}"]
+        ads[key] = GroupedData(X=z[f"x{gi}"].astype(np.float32), obs=obs, var_names=[f"g{j}" for j in range((G0, G1)[gi])])
+    adata = prepare_adatas(ads)
+    if mode != "label":
+        adata.uns["transport_plan"] = z["plan"]
+    spVIPES.setup_anndata(adata, groups_key="groups", label_key="cell_type" if mode == "label" else None,
+                          transport_plan_key="transport_plan" if mode != "label" else None, match_clusters=mode == "cluster")
+    model = spVIPES(adata, n_hidden=H, n_dimensions_shared=S, n_dimensions_private=P, dropout_rate=0.1, precision=precision)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    model.module.load_state_dict(sd, strict=True)
+
+    def noise(k, B0, B1):  # the generator of oracle/make_golden_latent.batch_noise
+        g = torch.Generator().manual_seed(1000 + k)
+        ep = [torch.randn(B, P, generator=g) for B in (B0, B1)]
+        eq = [torch.randn(B, S, generator=g) for B in (B0, B1)]
+        return Noise([e.cuda() for e in ep], [e.cuda() for e in eq], None)
+
+    gil = [list(ix) for ix in adata.uns["groups_obs_indices"]]
+    lat = model.get_latent_representation(gil, batch_size=bs, _noise_fn=noise)
+    for key, got in (("shared0", lat["shared"][0]), ("shared1", lat["shared"][1]), ("private0", lat["private"][0]),
+                     ("private1", lat["private"][1]), ("shared1_reordered", lat["shared_reordered"][1]),
+                     ("private1_reordered", lat["private_reordered"][1])):
+        assert got.shape == z[key].shape, key
+        assert relerr(got, z[key]) < 1e-3, (key, relerr(got, z[key]))
