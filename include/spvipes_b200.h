@@ -47,6 +47,7 @@ int spv_copy2d_h2d(void* dst, long long dpitch, const void* src, long long spitc
 
 /* C[b] (+)= act(op(A[b]) op(B[b]) + bias[b]) in fp32, batched over `batch` (element strides sA/sB/sC/sBias), optional
  * split-K (`ws` holds batch*splits*M*N floats).  transA: A stored [K][M]; transB: B stored [N][K] (y = x W^T).
+ * accumulate: 0 = overwrite, 1 = add the result to C, 2 = C holds a PRE-activation addend (C <- act(A B + C + bias)).
  * Replaces nn.Linear forward/backward GEMMs: nn/networks.py:119-125 (Encoder), :314-325 (decoder, scvi FCLayers). */
 int spv_gemm(int srcA, int transA, int srcB, int transB, const void* A, long long lda, const int* rowsA, const void* B,
              long long ldb, const int* rowsB, float* C, long long ldc, int M, int N, int K, int batch, long long sA,
@@ -109,8 +110,21 @@ int spv_to_bf16_block(const float* src, long long ld_src, void* dst, long long l
 /* T[b, :G] = bf16(log1p(X[rows[b], :G])), zero padded to ld_dst (a multiple of 8)   module/spVIPESmodule.py:428-433;
  * dst_lo (optional): the bf16 residual plane for spv_tc_gemm_split;
  * lib (optional, [B]): library size log(sum_g log1p(x[b,g])) from the same pass   module/spVIPESmodule.py:433-435 */
+/* cov (optional, [B] batch codes) / n_cov: columns G .. G + n_cov of dst receive the one-hot batch code (batch covariates
+ * appended to the encoders' input, nn/networks.py:110-118); they do not enter the library size */
 int spv_counts_to_bf16(int src, const void* X, long long ldx, const int* rows, void* dst, void* dst_lo, long long ld_dst, int B,
-                       int G, float* lib, void* stream);
+                       int G, float* lib, const int* cov, int n_cov, void* stream);
+
+/* batch covariates (n_batch > 1; nn/utils.py:9-13, scvi FCLayers inject_covariates).  spv_one_hot: out[b, 0:nb] = one_hot(code[b]).
+ * spv_cov_expand: zzb[b] = [zz[b, 0:P] | oh | zz[b, P:P+S] | oh] (the inputs of the two factor regressors, whose weights are
+ * [G, P + nb] and [G, S + nb]) and oh_tail[b, 0:nb] = oh (optional: the covariate columns behind [hm | zz] in the mixing net's
+ * input).  spv_cov_compact: the reverse selection for gradients (covariate columns dropped), plus an optional addend
+ * add[b, 0 : P + S] (the mixture layer's input gradient, which has the plain [zz] layout). */
+int spv_one_hot(const int* code, float* out, long long ld, int B, int nb, void* stream);
+int spv_cov_expand(const float* zz, long long ld_zz, const int* code, float* zzb, long long ld_zzb, float* oh_tail, long long ld_oh,
+                   int B, int P, int S, int nb, void* stream);
+int spv_cov_compact(const float* dzzb, long long ld_in, float* dzz, long long ld_out, int B, int P, int S, int nb, const float* add,
+                    long long ld_add, void* stream);
 
 /* lib[b] = log(sum_g log1p(x[b,g]))   module/spVIPESmodule.py:433-435 */
 int spv_library_size(int src, const void* X, long long ldx, const int* rows, int B, int G, float* lib, void* stream);
@@ -182,10 +196,14 @@ int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, 
 #define SPV_DEC_NPTR 17
 /* phases: bit 0 = gene-axis softmax normaliser sweep, bit 1 = mixture GEMM + NB log-likelihood sweep (3 = both),
  * bit 2 = the mixture logits are already in `pi` (written by spv_tc_gemm), skip the in-kernel fp32 GEMM */
+/* zzb (optional, [B, P + S] with row pitch ld_zzb): the inputs of the two factor regressors when they are not the latent columns
+ * of amix (batch covariates: P and S then include the covariate columns, spv_cov_expand); kmix (0 = HD + P + S): width of the
+ * mixing net's input amix / of a row of wm. */
 int spv_dec_nb_fwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P, int S,
-                   int phases, void* stream);
+                   int phases, const float* zzb, long long ld_zzb, int kmix, void* stream);
 int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P, int S,
-                   float scale, float* colsum, void* dpi_bf16, long long ld_dpi_bf16, void* stream);
+                   float scale, float* colsum, void* dpi_bf16, long long ld_dpi_bf16, const float* zzb, long long ld_zzb, int kmix,
+                   void* stream);
 /* tensor-core version of phase 2 of spv_dec_nb_fwd: the mixture GEMM and the two softmax-branch logit GEMMs on tcgen05
  * (operands via TMA, fp32 accumulators in TMEM) with the NB-mixture log-likelihood fused into the TMEM epilogue.
  * amix_bf16 [B, ld_amixb] = [hm | zz] and wstack_bf16 [>= G, ld_w] (the mixture weight) hold FP16 values (spv_to_f16 /
@@ -194,7 +212,7 @@ int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld
  * store_pi: also write the mixture logits to ptrs[10] (fp32). */
 int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
                       const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16, int B, int G,
-                      int HD, int P, int S, int store_pi, void* stream);
+                      int HD, int P, int S, int store_pi, int kmix, void* stream);
 /* tensor-core version of phase 1 of spv_dec_nb_fwd: softmax normalisers rowc[b, 0:2] = lib[b] - logsumexp_g(y_p), (y_s)
  * from the fp16 branch operands (spv_dec_fold); part_stats: scratch of 2 * ceil(G/64) * B * 4 floats.
  * nn/networks.py:318-320, module/spVIPESmodule.py:751-757 */
@@ -212,13 +230,13 @@ int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, int HD, float* rowc
  * 16-byte aligned (SPV_ERR_ARG otherwise): a row is read as one float4. */
 int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
                       const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16, void* d3_bf16,
-                      int B, int G, int HD, int P, int S, float scale, float* colsum, void* stream);
+                      int B, int G, int HD, int P, int S, float scale, float* colsum, int kmix, void* stream);
 /* ptrs (18): Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm,
  * vpart [parts, P+S], mpart [parts, (P+S)^2] with parts = spv_dec_gene_bwd_parts(G)
  * (backward of nn/networks.py:314-320 through the folded BatchNorm) */
 int spv_dec_gene_bwd_parts(int G);
 int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, int G, int P, int S, void* stream);
-/* d zz = dmix (latent columns of d [hm | zz]) + dzraw (optional further addends [B, P+S]: softmax-branch and hidden-layer
+/* d zz = dmix (latent columns of d [hm | zz]; NULL = none) + dzraw (optional further addends [B, P+S]: softmax-branch and hidden-layer
  * input gradients when they are not in dmix) - BatchNorm coupling terms, the latter summed from the `nparts` per-CTA
  * partials (vpart [nparts, P+S], mpart [nparts, (P+S)^2]) that spv_dec_gene_bwd writes (its last two ptrs).
  * raw_colsum != NULL (tensor-core path; [P+S] column sums of dzraw, spv_colsum): the mean-coupling term is taken as the column

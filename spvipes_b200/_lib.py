@@ -35,7 +35,10 @@ _SIGS = {
     "spv_to_bf16": [p, ll, p, ll, i, i, p],
     "spv_to_f16": [p, ll, p, ll, i, i, p],
     "spv_to_bf16_split": [p, ll, p, p, ll, i, i, p],
-    "spv_counts_to_bf16": [i, p, ll, p, p, p, ll, i, i, p, p],
+    "spv_counts_to_bf16": [i, p, ll, p, p, p, ll, i, i, p, p, i, p],
+    "spv_one_hot": [p, p, ll, i, i, p],
+    "spv_cov_expand": [p, ll, p, p, ll, p, ll, i, i, i, i, p],
+    "spv_cov_compact": [p, ll, p, ll, i, i, i, i, p, ll, p],
     "spv_library_size": [i, p, ll, p, i, i, p, p],
     "spv_dropout": [p, ll, i, i, p, ll, f, u64, u32, p, p],
     "spv_relu_bwd": [p, ll, p, ll, i, i, p, ll, f, p],
@@ -51,11 +54,11 @@ _SIGS = {
     "spv_poe_bwd": [i, i, i, i, i, p, p, p, p, u64, p, p, f, p],
     "spv_loss": [p, p, p, p, p, p, i, p, p, p],
     "spv_dec_fold": [p, ll, i, i, i, i, i, f, f, p, ll, i, i, p, p, p],
-    "spv_dec_nb_fwd": [i, p, ll, ll, i, i, i, i, i, i, p],
-    "spv_dec_nb_bwd": [i, p, ll, ll, i, i, i, i, i, f, p, p, ll, p],
-    "spv_dec_nb_fwd_tc": [i, p, ll, p, ll, p, ll, i, p, p, i, i, i, i, i, i, p],
+    "spv_dec_nb_fwd": [i, p, ll, ll, i, i, i, i, i, i, p, ll, i, p],
+    "spv_dec_nb_bwd": [i, p, ll, ll, i, i, i, i, i, f, p, p, ll, p, ll, i, p],
+    "spv_dec_nb_fwd_tc": [i, p, ll, p, ll, p, ll, i, p, p, i, i, i, i, i, i, i, p],
     "spv_dec_nb_rowreduce": [p, i, i, i, p, p, p],
-    "spv_dec_nb_bwd_tc": [i, p, ll, p, ll, p, ll, i, p, p, p, i, i, i, i, i, f, p, p],
+    "spv_dec_nb_bwd_tc": [i, p, ll, p, ll, p, ll, i, p, p, p, i, i, i, i, i, f, p, i, p],
     "spv_dec_gene_bwd": [p, ll, i, i, i, i, p],
     "spv_dec_gene_bwd_parts": [i],
     "spv_dec_nb_part_floats": [i, i],

@@ -91,6 +91,8 @@ struct DecP {
     float* dyp; float* dys; float* dpi;                  // [B, G]
     float* colpart;                                      // [nTB, 4, G]
     int B, G, HD, P, S;
+    const float* zz; long ld_zz;                         // [B, P + S] inputs of the two factor regressors (default: amix + HD)
+    int kmix;                                            // width of the mixing net's input (default HD + P + S)
     float scale;
     int pi_ready;                                        // PASS_NB: pi already holds the mixture logits (tensor-core GEMM)
     __nv_bfloat16* dpi_bf16; long ld_dpi_bf16;           // PASS_BWD: write d pi as bf16 (operand of the tensor-core GEMMs)
@@ -104,16 +106,16 @@ __global__ void __launch_bounds__(GT_THREADS) dec_tile_kernel(DecP p) {
     __shared__ float red[16][GT_BN + 1];
     const int n0 = blockIdx.x * GT_BN, m0 = blockIdx.y * GT_BM;
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    const int KMIX = p.HD + p.P + p.S, KZ = p.P + p.S;
+    const int KMIX = p.kmix, KZ = p.P + p.S;
     const int G = p.G, B = p.B;
     float lp[4][4], ls[4][4], pi[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) lp[i][j] = ls[i][j] = pi[i][j] = 0.0f;
-    const float* azz = p.amix + p.HD;
-    tile_mainloop<SPV_SRC_F32, false, SPV_SRC_F32, true>(lp, azz, p.ld_amix, nullptr, p.wfold, KZ, nullptr, B, G, 0, p.P, m0, n0, sm);
-    tile_mainloop<SPV_SRC_F32, false, SPV_SRC_F32, true>(ls, azz + p.P, p.ld_amix, nullptr, p.wfold + p.P, KZ, nullptr, B, G, 0, p.S, m0, n0, sm);
+    const float* azz = p.zz;
+    tile_mainloop<SPV_SRC_F32, false, SPV_SRC_F32, true>(lp, azz, p.ld_zz, nullptr, p.wfold, KZ, nullptr, B, G, 0, p.P, m0, n0, sm);
+    tile_mainloop<SPV_SRC_F32, false, SPV_SRC_F32, true>(ls, azz + p.P, p.ld_zz, nullptr, p.wfold + p.P, KZ, nullptr, B, G, 0, p.S, m0, n0, sm);
     if (PASS == PASS_NB && !p.pi_ready)
         tile_mainloop<SPV_SRC_F32, false, SPV_SRC_F32, true>(pi, p.amix, p.ld_amix, nullptr, p.wm, KMIX, nullptr, B, G, 0, KMIX, m0, n0, sm);
 
@@ -353,25 +355,28 @@ __global__ void rownb_kernel(const float* __restrict__ part, int nTG, int B, flo
 }
 
 static void fill_decp(DecP& p, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P, int S,
-                      float scale) {
+                      float scale, const float* zzb, long long ld_zzb, int kmix) {
     p.X = ptrs[0]; p.rows = (const int*)ptrs[1]; p.amix = (const float*)ptrs[2]; p.wfold = (const float*)ptrs[3];
     p.wm = (const float*)ptrs[4]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6]; p.lib = (const float*)ptrs[7];
     p.part_stats = (float*)ptrs[8]; p.rowc = (float*)ptrs[9]; p.pi = (float*)ptrs[10]; p.part_nb = (float*)ptrs[11];
     p.dyp = (float*)ptrs[12]; p.dys = (float*)ptrs[13]; p.dpi = (float*)ptrs[14]; p.colpart = (float*)ptrs[15];
     p.ldx = ldx; p.ld_amix = ld_amix; p.B = B; p.G = G; p.HD = HD; p.P = P; p.S = S; p.scale = scale;
     p.pi_ready = 0; p.dpi_bf16 = nullptr; p.ld_dpi_bf16 = 0;
+    p.zz = zzb ? zzb : p.amix + HD;
+    p.ld_zz = zzb ? ld_zzb : ld_amix;
+    p.kmix = kmix > 0 ? kmix : HD + P + S;
 }
 
 // ptrs (SPV_DEC_NPTR = 17): X, rows, amix, wfold, wm, bm, genec, lib, part_stats, rowc, pi, part_nb, dyp, dys, dpi,
 // colpart, rec.   Forward: rec[b], rowc and pi are produced.
 extern "C" int spv_dec_nb_fwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P,
-                              int S, int phases, void* stream) {
+                              int S, int phases, const float* zzb, long long ld_zzb, int kmix, void* stream) {
     if (!ptrs || (phases & 3) == 0 || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
     const int need[] = {0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 16};
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
     DecP p;
-    fill_decp(p, ptrs, ldx, ld_amix, B, G, HD, P, S, 0.0f);
+    fill_decp(p, ptrs, ldx, ld_amix, B, G, HD, P, S, 0.0f, zzb, ld_zzb, kmix);
     p.pi_ready = (phases & 4) ? 1 : 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     dim3 grid((G + GT_BN - 1) / GT_BN, (B + GT_BM - 1) / GT_BM);
@@ -405,14 +410,15 @@ __global__ void colpart_reduce_kernel(const float* __restrict__ colpart, int nTB
 // Backward sweep: writes dyp, dys, dpi [B, G] (gradients w.r.t. the two BatchNorm outputs and the mixture logits)
 // and colsum [4, G] = column sums of dyp, dys, dpi and d loss / d theta.   scale = -grad_scale / B.
 extern "C" int spv_dec_nb_bwd(int src, const void* const* ptrs, long long ldx, long long ld_amix, int B, int G, int HD, int P,
-                              int S, float scale, float* colsum, void* dpi_bf16, long long ld_dpi_bf16, void* stream) {
+                              int S, float scale, float* colsum, void* dpi_bf16, long long ld_dpi_bf16, const float* zzb,
+                              long long ld_zzb, int kmix, void* stream) {
     if (!ptrs || !colsum || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0) return SPV_ERR_ARG;
     const int need[] = {0, 2, 3, 6, 7, 9, 10, 12, 13, 15};
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
     if (!ptrs[14] && !dpi_bf16) return SPV_ERR_ARG;
     DecP p;
-    fill_decp(p, ptrs, ldx, ld_amix, B, G, HD, P, S, scale);
+    fill_decp(p, ptrs, ldx, ld_amix, B, G, HD, P, S, scale, zzb, ld_zzb, kmix);
     p.dpi_bf16 = reinterpret_cast<__nv_bfloat16*>(dpi_bf16);
     p.ld_dpi_bf16 = ld_dpi_bf16;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -560,13 +560,13 @@ __global__ void __launch_bounds__(DZC_THREADS) dzz_combine_kernel(const float* _
     const float* zrow = zz + (long)b * ld_zz + lo;
     float corr = 0.0f;
     for (int l = 0; l < n; ++l) corr = fmaf(srow[l], zrow[l] - zmean[lo + l], corr);
-    dzz[(long)b * KZ + c] = dmix[(long)b * ld_dmix + c] + (dzraw ? dzraw[(long)b * KZ + c] : 0.0f) - srow[n] - corr;
+    dzz[(long)b * KZ + c] = (dmix ? dmix[(long)b * ld_dmix + c] : 0.0f) + (dzraw ? dzraw[(long)b * KZ + c] : 0.0f) - srow[n] - corr;
 }
 
 extern "C" int spv_dec_dzz_combine(const float* dmix, long long ld_dmix, const float* dzraw, const float* vpart, const float* mpart,
                                    int nparts, const float* zz, long long ld_zz, const float* zmean, float* dzz, int B, int P,
                                    int S, const float* raw_colsum, void* stream) {
-    if (!dmix || !vpart || !mpart || !zz || !zmean || !dzz || B <= 0 || P <= 0 || S <= 0 || nparts <= 0 || P > 96 || S > 96)
+    if (!vpart || !mpart || !zz || !zmean || !dzz || B <= 0 || P <= 0 || S <= 0 || nparts <= 0 || P > 96 || S > 96)
         return SPV_ERR_ARG;
     if (raw_colsum && !dzraw) return SPV_ERR_ARG;
     dim3 grid(P + S, (B + DZC_THREADS - 1) / DZC_THREADS);

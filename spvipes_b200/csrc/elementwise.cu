@@ -446,3 +446,72 @@ extern "C" int spv_adam(float* p, const float* g, float* m, float* v, long long 
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// batch covariates (n_batch > 1): the one-hot batch code is appended to the input of the encoders' first layer and of the four
+// decoder nets (reference nn/utils.py:9-13, nn/networks.py:110-118, scvi FCLayers inject_covariates).
+// ---------------------------------------------------------------------------------------
+__global__ void one_hot_kernel(const int* __restrict__ code, float* __restrict__ out, long ld, int B, int nb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * nb) return;
+    const int b = i / nb, k = i - b * nb;
+    out[(long)b * ld + k] = code[b] == k ? 1.0f : 0.0f;
+}
+
+// out[b, 0:nb] = one_hot(code[b])
+extern "C" int spv_one_hot(const int* code, float* out, long long ld, int B, int nb, void* stream) {
+    if (!code || !out || B <= 0 || nb <= 0 || ld < nb) return SPV_ERR_ARG;
+    one_hot_kernel<<<(B * nb + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(code, out, ld, B, nb);
+    SPV_CHECK_LAUNCH();
+    return SPV_OK;
+}
+
+// zzb[b] = [zz[b, 0:P] | oh | zz[b, P:P+S] | oh]: the inputs of the two factor regressors side by side, each with its covariate
+// columns (their weights are [G, P + nb] and [G, S + nb]); oh_tail[b, 0:nb] = oh (the covariate columns behind [hm | zz] in the
+// mixing net's input)
+__global__ void cov_expand_kernel(const float* __restrict__ zz, long ld_zz, const int* __restrict__ code, float* __restrict__ zzb,
+                                  long ld_zzb, float* __restrict__ oh_tail, long ld_oh, int B, int P, int S, int nb) {
+    const int W = P + S + 2 * nb;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * W) return;
+    const int b = i / W, c = i - b * W;
+    float v;
+    if (c < P) v = zz[(long)b * ld_zz + c];
+    else if (c < P + nb) v = code[b] == c - P ? 1.0f : 0.0f;
+    else if (c < P + nb + S) v = zz[(long)b * ld_zz + c - nb];
+    else {
+        v = code[b] == c - (P + nb + S) ? 1.0f : 0.0f;
+        if (oh_tail) oh_tail[(long)b * ld_oh + c - (P + nb + S)] = v;
+    }
+    zzb[(long)b * ld_zzb + c] = v;
+}
+
+extern "C" int spv_cov_expand(const float* zz, long long ld_zz, const int* code, float* zzb, long long ld_zzb, float* oh_tail,
+                              long long ld_oh, int B, int P, int S, int nb, void* stream) {
+    if (!zz || !code || !zzb || B <= 0 || P <= 0 || S <= 0 || nb <= 0) return SPV_ERR_ARG;
+    const int total = B * (P + S + 2 * nb);
+    cov_expand_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(zz, ld_zz, code, zzb, ld_zzb, oh_tail, ld_oh,
+                                                                                              B, P, S, nb);
+    SPV_CHECK_LAUNCH();
+    return SPV_OK;
+}
+
+// the reverse for gradients: dzz[b] = [dzzb[b, 0:P] | dzzb[b, P+nb : P+nb+S]] (the covariate columns carry no gradient)
+__global__ void cov_compact_kernel(const float* __restrict__ dzzb, long ld_in, float* __restrict__ dzz, long ld_out, int B, int P, int S,
+                                   int nb, const float* __restrict__ add, long ld_add) {
+    const int W = P + S;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * W) return;
+    const int b = i / W, c = i - b * W;
+    dzz[(long)b * ld_out + c] = dzzb[(long)b * ld_in + (c < P ? c : c + nb)] + (add ? add[(long)b * ld_add + c] : 0.0f);
+}
+
+extern "C" int spv_cov_compact(const float* dzzb, long long ld_in, float* dzz, long long ld_out, int B, int P, int S, int nb,
+                               const float* add, long long ld_add, void* stream) {
+    if (!dzzb || !dzz || B <= 0 || P <= 0 || S <= 0 || nb <= 0) return SPV_ERR_ARG;
+    const int total = B * (P + S);
+    cov_compact_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dzzb, ld_in, dzz, ld_out, B, P, S, nb,
+                                                                                               add, ld_add);
+    SPV_CHECK_LAUNCH();
+    return SPV_OK;
+}

@@ -72,10 +72,11 @@ __global__ void __launch_bounds__(GT_THREADS) gemm_kernel(GemmParams p) {
             int n = n0 + tx * 4 + j;
             if (n >= p.N) continue;
             float v = acc[i][j];
+            float* c = C + (size_t)m * p.ldc + n;
+            if (p.accumulate == 2) v += *c;  // pre-activation addend already in C (covariate term of the first encoder layer)
             if (bias) v += bias[n];
             if (p.relu) v = fmaxf(v, 0.0f);
-            float* c = C + (size_t)m * p.ldc + n;
-            *c = p.accumulate ? (*c + v) : v;
+            *c = p.accumulate == 1 ? (*c + v) : v;
         }
     }
 }
@@ -89,10 +90,11 @@ __global__ void splitk_reduce_kernel(GemmParams p) {
         int b = (int)(r / p.M);
         float v = 0.0f;
         for (int s = 0; s < p.splits; ++s) v += p.ws[((size_t)(b * p.splits + s) * p.M + m) * p.N + n];  // fixed order: deterministic
+        float* c = p.C + (size_t)b * p.sC + (size_t)m * p.ldc + n;
+        if (p.accumulate == 2) v += *c;
         if (p.bias) v += p.bias[(size_t)b * p.sBias + n];
         if (p.relu) v = fmaxf(v, 0.0f);
-        float* c = p.C + (size_t)b * p.sC + (size_t)m * p.ldc + n;
-        *c = p.accumulate ? (*c + v) : v;
+        *c = p.accumulate == 1 ? (*c + v) : v;
     }
 }
 
@@ -220,10 +222,11 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_smallk_kernel(GemmParams p) {
         const int n = n0 + (TB ? tx + 16 * j : tx * 4 + j);
         if (n >= p.N) continue;
         float v = acc[j];
+        float* c = C + (size_t)m * p.ldc + n;
+        if (p.accumulate == 2) v += *c;
         if (bias) v += __ldg(bias + n);
         if (p.relu) v = fmaxf(v, 0.0f);
-        float* c = C + (size_t)m * p.ldc + n;
-        if (p.accumulate) v += *c;
+        if (p.accumulate == 1) v += *c;
         const long nn = (long)b * p.sC + n;  // column inside the full output matrix
         if (p.gate_y) {
             const float gm = p.gate_mask ? __ldg(p.gate_mask + (size_t)m * p.ld_mask + nn) : p.gate_scale;

@@ -528,7 +528,7 @@ static int set_smem_once(K kernel, int bytes, bool (&done)[64]) {
 // Gp = G rounded up to a multiple of 8.
 extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
                                  const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16, int B,
-                                 int G, int HD, int P, int S, int store_pi, void* stream) {
+                                 int G, int HD, int P, int S, int store_pi, int kmix, void* stream) {
     if (!ptrs || !amix_bf16 || !wstack_bf16 || !zc_f16 || !wz_f16 || Gp < G || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0)
         return SPV_ERR_ARG;
     if (P + S > BK) return SPV_ERR_ARG;  // the latent columns must fit the branch k-block
@@ -536,7 +536,7 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
     if (store_pi && !ptrs[10]) return SPV_ERR_ARG;
-    const int K = HD + P + S;
+    const int K = kmix > 0 ? kmix : HD + P + S;  // width of the mixing net's input ([hm | zz | covariates])
     CUtensorMap ma, mb, mz, mzc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc = spv_make_tensor_map_bf16(&ma, amix_bf16, (unsigned long long)K, (unsigned long long)B, (unsigned long long)ld_amixb, 64, BM);

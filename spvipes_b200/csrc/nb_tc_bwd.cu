@@ -372,14 +372,14 @@ __global__ void colpart_reduce_tc_kernel(const float* __restrict__ colpart, int 
 // column sums of dyp, dys, dpi, dtheta (true scale).
 extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
                                  const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16,
-                                 void* d3_bf16, int B, int G, int HD, int P, int S, float scale, float* colsum, void* stream) {
+                                 void* d3_bf16, int B, int G, int HD, int P, int S, float scale, float* colsum, int kmix, void* stream) {
     if (!ptrs || !amix_bf16 || !wstack_bf16 || !zc_f16 || !wz_f16 || !d3_bf16 || !colsum || Gp < G || B <= 0 || G <= 0 || P <= 0 || S <= 0)
         return SPV_ERR_ARG;
     if (P + S > BK) return SPV_ERR_ARG;
     const int need[] = {0, 5, 6, 7, 9, 15};
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
-    const int K = HD + P + S;
+    const int K = kmix > 0 ? kmix : HD + P + S;  // width of the mixing net's input ([hm | zz | covariates])
     if (reinterpret_cast<uintptr_t>(ptrs[9]) & 15) return SPV_ERR_ARG;  // rowc rows are read as one float4
     CUtensorMap ma, mb, mz, mzc;
     int rc = spv_make_tensor_map_bf16(&ma, amix_bf16, (unsigned long long)K, (unsigned long long)B, (unsigned long long)ld_amixb, 64, BM);

@@ -473,7 +473,8 @@ __device__ __forceinline__ unsigned int pack_split(float f) {
 template <int SRC>
 __global__ void __launch_bounds__(ENC_IN_THREADS) counts_to_bf16_kernel(const void* __restrict__ X, long ldx, const int* __restrict__ rows,
                                                                         __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst_lo,
-                                                                        long ld_dst, int B, int G, float* __restrict__ lib) {
+                                                                        long ld_dst, int B, int G, float* __restrict__ lib,
+                                                                        const int* __restrict__ cov, int n_cov) {
     __shared__ float lut[256];
     __shared__ unsigned int lutp[256];
     __shared__ float red[ENC_IN_THREADS / 32];
@@ -510,22 +511,31 @@ __global__ void __launch_bounds__(ENC_IN_THREADS) counts_to_bf16_kernel(const vo
             *(reinterpret_cast<uint4*>(out) + v) = o;
             if (out_lo) *(reinterpret_cast<uint4*>(out_lo) + v) = ol;
         }
+        const int my_cov = cov ? __ldg(cov + b) : -1;  // columns G .. G + n_cov: one-hot batch code (not part of the library size)
         for (int g = nvec * 8 + threadIdx.x; g < ld_dst; g += ENC_IN_THREADS) {
             float f = 0.0f;
             if (g < G) {
                 unsigned int c = row[g];
                 f = c < 256u ? lut[c] : log1pf((float)c);
+                sum += f;
+            } else if (g - G < n_cov) {
+                f = (g - G == my_cov) ? 1.0f : 0.0f;
             }
-            sum += f;
             __nv_bfloat16 hi, lo;
             split_bf16(f, hi, lo);
             out[g] = hi;
             if (out_lo) out_lo[g] = lo;
         }
     } else {
+        const int my_cov = cov ? __ldg(cov + b) : -1;
         for (int g = threadIdx.x; g < ld_dst; g += ENC_IN_THREADS) {
-            float f = g < G ? load_src<SRC>(X, r * ldx + g) : 0.0f;
-            sum += f;
+            float f = 0.0f;
+            if (g < G) {
+                f = load_src<SRC>(X, r * ldx + g);
+                sum += f;
+            } else if (g - G < n_cov) {
+                f = (g - G == my_cov) ? 1.0f : 0.0f;
+            }
             __nv_bfloat16 hi, lo;
             split_bf16(f, hi, lo);
             out[g] = hi;
@@ -545,13 +555,14 @@ __global__ void __launch_bounds__(ENC_IN_THREADS) counts_to_bf16_kernel(const vo
 }
 
 extern "C" int spv_counts_to_bf16(int src, const void* X, long long ldx, const int* rows, void* dst, void* dst_lo, long long ld_dst,
-                                  int B, int G, float* lib, void* stream) {
-    if (!X || !dst || B <= 0 || G <= 0 || ld_dst < G || (ld_dst & 7)) return SPV_ERR_ARG;
+                                  int B, int G, float* lib, const int* cov, int n_cov, void* stream) {
+    if (!X || !dst || B <= 0 || G <= 0 || n_cov < 0 || ld_dst < G + n_cov || (ld_dst & 7) || (n_cov > 0 && !cov)) return SPV_ERR_ARG;
+    if (n_cov == 0) cov = nullptr;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
     __nv_bfloat16* dl = reinterpret_cast<__nv_bfloat16*>(dst_lo);
-    if (src == SPV_SRC_U16_LOG1P) counts_to_bf16_kernel<SPV_SRC_U16_LOG1P><<<B, ENC_IN_THREADS, 0, st>>>(X, ldx, rows, d, dl, ld_dst, B, G, lib);
-    else if (src == SPV_SRC_F32_LOG1P) counts_to_bf16_kernel<SPV_SRC_F32_LOG1P><<<B, ENC_IN_THREADS, 0, st>>>(X, ldx, rows, d, dl, ld_dst, B, G, lib);
+    if (src == SPV_SRC_U16_LOG1P) counts_to_bf16_kernel<SPV_SRC_U16_LOG1P><<<B, ENC_IN_THREADS, 0, st>>>(X, ldx, rows, d, dl, ld_dst, B, G, lib, cov, n_cov);
+    else if (src == SPV_SRC_F32_LOG1P) counts_to_bf16_kernel<SPV_SRC_F32_LOG1P><<<B, ENC_IN_THREADS, 0, st>>>(X, ldx, rows, d, dl, ld_dst, B, G, lib, cov, n_cov);
     else return SPV_ERR_ARG;
     SPV_CHECK_LAUNCH();
     return SPV_OK;

@@ -33,14 +33,32 @@ class Dims:
     n_hidden: int = 128
     n_shared: int = 25
     n_private: int = 10
+    n_batch: int = 0   # batch covariate: its one-hot code (n_batch columns) is appended to the input of the encoders' first layer
+                       # and of the four decoder nets when n_batch > 1 (reference nn/networks.py:60-68, scvi FCLayers)
 
     @property
-    def KZ(self):
+    def nb(self):
+        return self.n_batch if self.n_batch > 1 else 0
+
+    @property
+    def KZ(self):   # latent columns [z_private_arg | z_shared_arg]
         return self.n_shared + self.n_private
 
     @property
-    def KMIX(self):
-        return HD + self.KZ
+    def KMIX(self):  # input width of the mixture layer and row width of amix = [hm | zz | covariates]
+        return HD + self.KZ + self.nb
+
+    @property
+    def Pb(self):   # input width of the private factor regressor
+        return self.n_private + self.nb
+
+    @property
+    def Sb(self):
+        return self.n_shared + self.nb
+
+    @property
+    def KZb(self):  # [z_private_arg | covariates | z_shared_arg | covariates]: the two regressors' inputs side by side
+        return self.KZ + 2 * self.nb
 
     @property
     def NST(self):
@@ -56,8 +74,9 @@ def _group_param_entries(g: int, G: int, d: Dims):
     H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
     ep, es, dec = f"encoder_{g}_private", f"encoder_{g}_shared", f"decoder_{g}"
     fl = "fc_layers.Layer 0"
+    Gc = G + d.nb  # the covariate columns sit behind the genes / the latents in every first-layer weight
     return [
-        ("W1", (2 * H, G), [(f"{ep}.fc1.weight", (0, H)), (f"{es}.fc1.weight", (H, 2 * H))]),
+        ("W1", (2 * H, Gc), [(f"{ep}.fc1.weight", (0, H)), (f"{es}.fc1.weight", (H, 2 * H))]),
         ("b1", (2 * H,), [(f"{ep}.fc1.bias", (0, H)), (f"{es}.fc1.bias", (H, 2 * H))]),
         ("W2", (2 * H, H), [(f"{ep}.fc2.weight", (0, H)), (f"{es}.fc2.weight", (H, 2 * H))]),
         ("b2", (2 * H,), [(f"{ep}.fc2.bias", (0, H)), (f"{es}.fc2.bias", (H, 2 * H))]),
@@ -69,13 +88,13 @@ def _group_param_entries(g: int, G: int, d: Dims):
                          (f"{es}.mu_encoder.1.weight", (2 * P, 2 * P + S)), (f"{es}.lvar_encoder.1.weight", (2 * P + S, NST))]),
         ("bthd", (NST,), [(f"{ep}.mu_encoder.1.bias", (0, P)), (f"{ep}.lvar_encoder.1.bias", (P, 2 * P)),
                           (f"{es}.mu_encoder.1.bias", (2 * P, 2 * P + S)), (f"{es}.lvar_encoder.1.bias", (2 * P + S, NST))]),
-        ("Wp", (G, P), [(f"{dec}.factor_regressor_private.{fl}.0.weight", None)]),
+        ("Wp", (G, d.Pb), [(f"{dec}.factor_regressor_private.{fl}.0.weight", None)]),
         ("gp", (G,), [(f"{dec}.factor_regressor_private.{fl}.1.weight", None)]),
         ("bp", (G,), [(f"{dec}.factor_regressor_private.{fl}.1.bias", None)]),
-        ("Ws", (G, S), [(f"{dec}.factor_regressor_shared.{fl}.0.weight", None)]),
+        ("Ws", (G, d.Sb), [(f"{dec}.factor_regressor_shared.{fl}.0.weight", None)]),
         ("gs", (G,), [(f"{dec}.factor_regressor_shared.{fl}.1.weight", None)]),
         ("bs", (G,), [(f"{dec}.factor_regressor_shared.{fl}.1.bias", None)]),
-        ("Wh", (HD, KZ), [(f"{dec}.sigmoid_decoder.{fl}.0.weight", None)]),
+        ("Wh", (HD, KZ + d.nb), [(f"{dec}.sigmoid_decoder.{fl}.0.weight", None)]),
         ("bh", (HD,), [(f"{dec}.sigmoid_decoder.{fl}.0.bias", None)]),
         ("gh", (HD,), [(f"{dec}.sigmoid_decoder.{fl}.1.weight", None)]),
         ("bth", (HD,), [(f"{dec}.sigmoid_decoder.{fl}.1.bias", None)]),
@@ -159,6 +178,7 @@ class GroupBatch:
     idx: Optional[torch.Tensor] = None     # int32 [B] within-group indices into the transport plan
     B: Optional[int] = None
     labels_per_cell: bool = False          # labels (and idx) are indexed by X's row, i.e. gathered with `rows`
+    batch: Optional[torch.Tensor] = None   # int32 [B] batch codes of the minibatch (n_batch > 1 only)
 
     def batch_size(self):
         if self.B is not None:
@@ -188,11 +208,14 @@ class _GroupWS:
         self.poe_loc, self.poe_lv, self.poe_scale = f(B, S), f(B, S), f(B, S)
         self.klp, self.klq, self.rec = f(B), f(B), f(B)
         self.partner = torch.empty(B, dtype=torch.int32, device=dev)
-        self.amix = f(B, KMIX)
-        self.zsum, self.zmean, self.zcov = f(KZ), f(KZ), f(KZ, KZ)
+        nb, KZb = d.nb, d.KZb
+        self.amix = torch.zeros(B, KMIX, dtype=torch.float32, device=dev)
+        self.zzb = f(B, KZb) if nb else None      # [z_private_arg | oh | z_shared_arg | oh] (batch covariates)
+        self.oh = f(B, nb) if nb else None        # one-hot batch codes (fp32 path of the encoders' first layer)
+        self.zsum, self.zmean, self.zcov = f(KZb), f(KZb), f(KZb, KZb)
         # per-64-row partial second moments + one spare slot holding the "last CTA" ticket counter (must start at zero)
-        self.cov_part = torch.zeros(self.nTB + 1, KZ * KZ, dtype=torch.float32, device=dev)
-        self.wfold, self.genec = f(G, KZ), f(L.GENEC_ROWS, G)
+        self.cov_part = torch.zeros(self.nTB + 1, KZb * KZb, dtype=torch.float32, device=dev)
+        self.wfold, self.genec = f(G, KZb), f(L.GENEC_ROWS, G)
         self.ah = f(B, HD)
         self.bn_h_mean, self.bn_h_istd = f(HD), f(HD)
         self.part_stats = f(2 * self.nTG, B, 4)
@@ -205,16 +228,20 @@ class _GroupWS:
         self.splits_g = max(1, min(32, G // 256))       # reductions over the gene axis with a small output
         self.splits_b = max(1, min(8, B // 64))         # reductions over the minibatch with a small output
         big = max(2 * H, KMIX)
-        self.ws = f(max(32 * B * big, self.splits_b * G * KZ, 2 * self.splits_b * big * big, 1))
+        self.ws = f(max(32 * B * big, self.splits_b * G * KZb, 2 * self.splits_b * big * big, 1))
         self.ws2 = f(max(2 * self.splits_b * big * big, 1))  # split-K scratch of the auxiliary (weight-gradient) streams
         self.ws3 = f(max(2 * self.splits_b * big * big, 1))
         r8 = lambda x: (x + 7) // 8 * 8
-        self.Gp, self.KMp = r8(G), r8(KMIX)
+        # Gp: gene pitch of the decoder operands; Gpe: pitch of the encoder operands (genes + covariate columns);
+        # KMp: row pitch of the 16-bit [hm | zz | covariates] operand and of Wstack (whose folded-weight rows use columns
+        # HD .. HD + KZb)
+        self.Gp, self.Gpe, self.KMp = r8(G), r8(G + nb), r8(max(KMIX, HD + KZb))
         if bf16:
             h = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
             hd = lambda *s: torch.zeros(*s, dtype=dec_dtype, device=dev)  # decoder operands: fp16 on the fused path
-            self.Tb, self.amixb = h(B, self.Gp), hd(B, self.KMp)
-            self.Tb_lo = h(B, self.Gp)  # bf16 residual of log1p(counts): the fc1 contractions run on split operands
+            self.Tb, self.amixb = h(B, self.Gpe), hd(B, self.KMp)
+            self.Tb_lo = h(B, self.Gpe)  # bf16 residual of log1p(counts): the fc1 contractions run on split operands
+            self.zzb16 = hd(B, r8(KZb)) if nb else None  # 16-bit copy of zzb (operand of the Q = dy^T zz GEMM)
             # fp16 operands of the branch-logit MMAs (spv_dec_fold writes them): centred latents and folded weights
             self.zcb = torch.zeros(B, 64, dtype=torch.float16, device=dev)
             self.wzf = torch.zeros(2 * self.Gp, 64, dtype=torch.float16, device=dev)
@@ -227,7 +254,7 @@ class _GroupWS:
                 self.D3, self.dh1b = hd(B, 3 * self.Gp), h(B, 2 * H)  # D3 = [dpi | dyp | dys]
                 self.dh1b_lo = h(B, 2 * H)
                 self.dpib = self.D3  # unfused path: only the first Gp columns are used (row pitch 3 Gp)
-                self.CQ = f(2 * self.Gp, KZ)
+                self.CQ = f(2 * self.Gp, KZb)
             # split-K factors of the tensor-core GEMMs (128-wide tiles): fill the 148 SMs
             tiles = ((B + 127) // 128) * ((2 * H + 127) // 128)
             self.tc_splits_fc1 = max(1, min(148 // tiles, (G + 63) // 64 // 2))
@@ -238,11 +265,12 @@ class _GroupWS:
         if with_grad:
             self.dyp, self.dys, self.dpi = f(B, G), f(B, G), f(B, G)
             self.colpart, self.colsum = f(self.nTB, 4, G), f(4, G)
-            self.Qp, self.Qs = f(G, P), f(G, S)
-            self.damix, self.dzraw, self.dzz = f(B, KMIX), f(B, KZ), f(B, KZ)
-            self.dzraw_sum = f(KZ)
+            self.Qp, self.Qs = f(G, d.Pb), f(G, d.Sb)
+            self.damix, self.dzraw, self.dzz = f(B, KMIX), f(B, KZb), f(B, KZ)
+            self.dzzb = f(B, KZb) if nb else self.dzz
+            self.dzraw_sum = f(KZb)
             self.nGB = L.load().spv_dec_gene_bwd_parts(G)
-            self.vpart, self.mpart = f(self.nGB, KZ), f(self.nGB, KZ * KZ)  # per-CTA partials of spv_dec_gene_bwd
+            self.vpart, self.mpart = f(self.nGB, KZb), f(self.nGB, KZb * KZb)  # per-CTA partials of spv_dec_gene_bwd
             self.dah = f(B, HD)
             self.dstats, self.dr = f(B, NST), f(B, NST)
             self.g_own, self.g_contrib, self.dexpert = f(B, 2 * S), f(B, 2 * S), f(B, 2 * S)
@@ -253,7 +281,7 @@ class StepEngine:
     """fwd / bwd / Adam of the spVIPES step for two groups on one GPU."""
 
     def __init__(self, genes: Tuple[int, int], n_hidden=128, n_shared=25, n_private=10, dropout_rate=0.1, mode="label",
-                 device="cuda", seed: int = 0, plan: Optional[torch.Tensor] = None, precision: str = "fp32"):
+                 device="cuda", seed: int = 0, plan: Optional[torch.Tensor] = None, precision: str = "fp32", n_batch: int = 0):
         """precision: "fp32" = fp32 SIMT GEMMs everywhere (parity gate 1e-4); "bf16" = the large contractions (encoder fc1
         forward / weight gradient, decoder mixture GEMM forward / weight gradient / input gradient) run on the tcgen05
         tensor-core path with bf16 operands and fp32 accumulation (parity gate 1e-2, BASELINE.json north_star)."""
@@ -262,13 +290,14 @@ class StepEngine:
         self.precision = precision
         self.bf16 = precision == "bf16"
         # fused tcgen05 decoder-GEMMs + NB-likelihood kernel (bf16 mode); the latent columns must fit one 64-wide k-block
-        self.fused_nb = self.bf16 and int(n_shared) + int(n_private) <= 64
+        nb_cols = int(n_batch) if int(n_batch) > 1 else 0
+        self.fused_nb = self.bf16 and int(n_shared) + int(n_private) + 2 * nb_cols <= 64
         # operands of the decoder GEMMs: fp16 on the fused path (2^-12 rounding, three bits more than bf16; every operand's range
         # is bounded: activations after BatchNorm, weights, gradients stored in natural units), bf16 on the unfused fallback
         self.dec_dtype = torch.float16 if self.fused_nb else torch.bfloat16
         self.dec_fmt = 3 if self.fused_nb else 0
         self.lib = L.load()
-        self.d = Dims(tuple(int(x) for x in genes), int(n_hidden), int(n_shared), int(n_private))
+        self.d = Dims(tuple(int(x) for x in genes), int(n_hidden), int(n_shared), int(n_private), int(n_batch))
         if self.d.n_private > self.d.n_shared:
             raise ValueError("n_dimensions_private > n_dimensions_shared is not supported by the reference's latent slicing")
         self.mode = mode
@@ -309,9 +338,11 @@ class StepEngine:
         r8 = lambda x: (x + 7) // 8 * 8
         self.wb = None
         if self.bf16:
-            self.wb = [(torch.zeros(2 * self.d.n_hidden, r8(G), dtype=torch.bfloat16, device=self.device),
-                        torch.zeros(3 * r8(G), r8(self.d.KMIX), dtype=self.dec_dtype, device=self.device),
-                        torch.zeros(2 * self.d.n_hidden, r8(G), dtype=torch.bfloat16, device=self.device)) for G in self.d.genes]
+            kmp = r8(max(self.d.KMIX, HD + self.d.KZb))
+            self.wb = [(torch.zeros(2 * self.d.n_hidden, r8(G + self.d.nb), dtype=torch.bfloat16, device=self.device),
+                        torch.zeros(3 * r8(G), kmp, dtype=self.dec_dtype, device=self.device),
+                        torch.zeros(2 * self.d.n_hidden, r8(G + self.d.nb), dtype=torch.bfloat16, device=self.device))
+                       for G in self.d.genes]
         # bf16 copies of W1 / Wm: refreshed by conversion kernels at the start of every forward, or (stage_in_adam, set by
         # the owner of the optimiser step: TrainLoop) written by the Adam kernel itself; _staged_version detects parameter
         # writes made through torch (load_state_dict, .copy_, a torch optimiser) since the last staging
@@ -423,12 +454,13 @@ class StepEngine:
         gb = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), Qp, Qs, w.genec, w.colsum, w.zmean, w.zcov,
                           self.Gd(g, "Wp"), self.Gd(g, "Ws"), self.Gd(g, "gp"), self.Gd(g, "bp"), self.Gd(g, "gs"),
                           self.Gd(g, "bs"), self.Gd(g, "px_r"), self.Gd(g, "bm"), w.vpart, w.mpart])
-        L.check(self.lib.spv_dec_gene_bwd(gb, ldq, B, G, self.d.n_private, self.d.n_shared, self._stream()), "spv_dec_gene_bwd")
+        L.check(self.lib.spv_dec_gene_bwd(gb, ldq, B, G, self.d.Pb, self.d.Sb, self._stream()), "spv_dec_gene_bwd")
 
     def _hidden_mix(self, g, w, B, tr, zzp):
         """hm = relu(BatchNorm(zz Wh^T + bh)) into the first HD columns of amix   (reference nn/networks.py:322-323)"""
         d = self.d
-        self._gemm(zzp, L.ptr(self.P(g, "Wh")), L.ptr(w.ah), B, HD, d.KZ, lda=d.KMIX, ldb=d.KZ, ldc=HD, tb=1,
+        # input [zz | covariates]: the latent and covariate columns are contiguous in amix
+        self._gemm(zzp, L.ptr(self.P(g, "Wh")), L.ptr(w.ah), B, HD, d.KZ + d.nb, lda=d.KMIX, ldb=d.KZ + d.nb, ldc=HD, tb=1,
                    bias=L.ptr(self.P(g, "bh")))
         L.check(self.lib.spv_bn_fwd(L.ptr(w.ah), HD, L.ptr(w.amix), d.KMIX, B, HD, L.ptr(self.P(g, "gh")),
                                     L.ptr(self.P(g, "bth")), DEC_BN_EPS, DEC_BN_MOM, L.ptr(self.Bf(g, "rm_h")),
@@ -493,28 +525,39 @@ class StepEngine:
             bt, w, st = batches[g], ws[g], self._stream()
             G, B = d.genes[g], Bs[g]
             src, esz = self._src_of(bt.X)
+            if bt.X.dim() != 2 or bt.X.stride(1) != 1:
+                raise ValueError("the count matrix must be row-major (unit stride along the genes)")
             ldx = bt.X.stride(0)
             xptr = bt.X.data_ptr() + bt.col0 * esz
             srcs.append((src, xptr, ldx))
+            nb, Gc = d.nb, G + d.nb
+            if nb and bt.batch is None:
+                raise ValueError("batch codes are required when the model was built with n_batch > 1")
             if convert:  # bf16 copies of the two big weights do not depend on the minibatch: off the critical path
                 with self._branch(g, "w1"):
-                    L.check(lib.spv_to_bf16_split(L.ptr(self.P(g, "W1")), G, L.ptr(w.W1b), L.ptr(w.W1b_lo), w.Gp, 2 * H, G,
+                    L.check(lib.spv_to_bf16_split(L.ptr(self.P(g, "W1")), Gc, L.ptr(w.W1b), L.ptr(w.W1b_lo), w.Gpe, 2 * H, Gc,
                                                   self._stream()), "spv_to_bf16_split")
                 if decode or self.stage_in_adam:
                     with self._branch(g, "wm"):
                         self._to_dec(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX)
             if self.bf16:  # encoder input and library size from one pass over the gathered rows
-                L.check(lib.spv_counts_to_bf16(src, xptr, ldx, L.ptr(bt.rows), L.ptr(w.Tb), L.ptr(w.Tb_lo), w.Gp, B, G,
-                                               L.ptr(w.lib), st), "spv_counts_to_bf16")
+                # (with batch covariates: their one-hot columns behind the genes, so that fc1 stays one GEMM over K = G + nb)
+                L.check(lib.spv_counts_to_bf16(src, xptr, ldx, L.ptr(bt.rows), L.ptr(w.Tb), L.ptr(w.Tb_lo), w.Gpe, B, G,
+                                               L.ptr(w.lib), L.ptr(bt.batch) if nb else None, nb, st), "spv_counts_to_bf16")
                 self._join(g, "w1")
-                self._tc_gemm_split(L.ptr(w.Tb), L.ptr(w.Tb_lo), L.ptr(w.W1b), L.ptr(w.W1b_lo), L.ptr(w.h1), B, 2 * H, G, lda=w.Gp,
-                                    ldb=w.Gp, ldc=2 * H, bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.tc_splits_fc1, ws=w.ws)
+                self._tc_gemm_split(L.ptr(w.Tb), L.ptr(w.Tb_lo), L.ptr(w.W1b), L.ptr(w.W1b_lo), L.ptr(w.h1), B, 2 * H, Gc, lda=w.Gpe,
+                                    ldb=w.Gpe, ldc=2 * H, bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.tc_splits_fc1, ws=w.ws)
             else:
                 with self._branch(g, "lib"):
                     L.check(lib.spv_library_size(src, xptr, ldx, L.ptr(bt.rows), B, G, L.ptr(w.lib), self._stream()),
                             "spv_library_size")
-                self._gemm(xptr, L.ptr(self.P(g, "W1")), L.ptr(w.h1), B, 2 * H, G, lda=ldx, ldb=G, ldc=2 * H, tb=1, srcA=src,
-                           rowsA=bt.rows, bias=L.ptr(self.P(g, "b1")), relu=1, splits=w.splits_fc1, ws=w.ws)
+                if nb:  # covariate term + bias first (pre-activation), then the count GEMM adds to it and applies the ReLU
+                    L.check(lib.spv_one_hot(L.ptr(bt.batch), L.ptr(w.oh), nb, B, nb, st), "spv_one_hot")
+                    self._gemm(L.ptr(w.oh), self.P(g, "W1").data_ptr() + 4 * G, L.ptr(w.h1), B, 2 * H, nb, lda=nb, ldb=Gc, ldc=2 * H,
+                               tb=1, bias=L.ptr(self.P(g, "b1")))
+                self._gemm(xptr, L.ptr(self.P(g, "W1")), L.ptr(w.h1), B, 2 * H, G, lda=ldx, ldb=Gc, ldc=2 * H, tb=1, srcA=src,
+                           rowsA=bt.rows, bias=None if nb else L.ptr(self.P(g, "b1")), relu=1, acc=2 if nb else 0,
+                           splits=w.splits_fc1, ws=w.ws)
             mask = noise.drop[g] if (training and noise.drop is not None) else None
             dropping = training and (mask is not None or self.dropout_rate > 0)
             for ev in self._noise_events:
@@ -566,9 +609,18 @@ class StepEngine:
             if self.bf16 and not ctx["wm_staged"]:  # decode() after an encoder-only pass: the mixture weight's bf16 copy
                 self._to_dec(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX)
             zzp = w.amix.data_ptr() + 4 * HD
+            nb, Pb, Sb, KZb = d.nb, d.Pb, d.Sb, d.KZb
+            # zb / ld_zb: the two factor regressors' inputs side by side.  Without covariates these are the latent columns of
+            # amix; with them each regressor's input carries its own copy of the one-hot columns (spv_cov_expand, which also
+            # fills the covariate columns behind [hm | zz] in amix)
+            zb, ld_zb = zzp, KMIX
+            if nb:
+                L.check(lib.spv_cov_expand(zzp, KMIX, L.ptr(bt.batch), L.ptr(w.zzb), KZb, zzp + 4 * KZ, KMIX, B, P, S, nb, st),
+                        "spv_cov_expand")
+                zb, ld_zb = L.ptr(w.zzb), KZb
             fold = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), self.P(g, "gp"), self.P(g, "bp"), self.P(g, "gs"),
                                 self.P(g, "bs"), self.P(g, "px_r"), self.Bf(g, "rm_p"), self.Bf(g, "rv_p"),
-                                self.Bf(g, "rm_s"), self.Bf(g, "rv_s"), zzp, w.zsum, w.cov_part, w.wfold, w.genec, w.zmean,
+                                self.Bf(g, "rm_s"), self.Bf(g, "rv_s"), zb, w.zsum, w.cov_part, w.wfold, w.genec, w.zmean,
                                 w.zcov])
             wz = w.Wstack.data_ptr() + 2 * w.Gp * w.KMp if self.fused_nb else None
             if self.fused_nb:
@@ -577,20 +629,20 @@ class StepEngine:
                 with self._branch(g, "hm"):
                     self._hidden_mix(g, w, B, tr, zzp)
                     self._to_dec(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX)
-            L.check(lib.spv_dec_fold(fold, KMIX, B, G, P, S, tr, DEC_BN_EPS, DEC_BN_MOM, wz, w.KMp if self.fused_nb else 0,
+            L.check(lib.spv_dec_fold(fold, ld_zb, B, G, Pb, Sb, tr, DEC_BN_EPS, DEC_BN_MOM, wz, w.KMp if self.fused_nb else 0,
                                      w.Gp, HD, L.ptr(w.wzf) if self.fused_nb else None, L.ptr(w.zcb) if self.fused_nb else None, st),
                     "spv_dec_fold")
             if self.fused_nb:  # softmax normalisers on the tensor cores (main stream: latent stats -> fold -> normalisers)
                 self._join(g, "lib")
                 L.check(lib.spv_dec_stats_tc(L.ptr(w.zcb), L.ptr(w.wzf), w.Gp, L.ptr(w.genec), L.ptr(w.lib),
-                                             L.ptr(w.part_stats), L.ptr(w.rowc), B, G, P, S, st), "spv_dec_stats_tc")
+                                             L.ptr(w.part_stats), L.ptr(w.rowc), B, G, Pb, Sb, st), "spv_dec_stats_tc")
                 self._join(g, "hm")
             else:
                 self._hidden_mix(g, w, B, tr, zzp)
             dptrs = self._dec_ptrs(g, w, xptr, bt.rows, with_grad)
             self._join(g, "lib")
             if not self.fused_nb:
-                L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 1, st), "spv_dec_nb_fwd")
+                L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, Pb, Sb, 1, L.ptr(w.zzb) if nb else None, KZb, KMIX, st), "spv_dec_nb_fwd")
             evs = next(self.nb_events) if self.nb_events is not None else None
             if self.fused_nb:
                 self._join(g, "wm")
@@ -602,7 +654,7 @@ class StepEngine:
             if self.bf16:
                 if self.fused_nb:
                     L.check(lib.spv_dec_nb_fwd_tc(src, dptrs, ldx, L.ptr(w.amixb), w.KMp, L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.zcb),
-                                                  L.ptr(w.wzf), B, G, HD, P, S, 0, st), "spv_dec_nb_fwd_tc")  # backward recomputes pi
+                                                  L.ptr(w.wzf), B, G, HD, Pb, Sb, 0, KMIX, st), "spv_dec_nb_fwd_tc")  # backward recomputes pi
                     if evs is not None:
                         evs[1].record()
                         evs = None
@@ -610,9 +662,9 @@ class StepEngine:
                 else:  # unfused: tensor-core GEMM writes pi, the SIMT sweep consumes it
                     self._tc_gemm(L.ptr(w.amixb), L.ptr(w.Wmb), L.ptr(w.pi), B, G, KMIX, lda=w.KMp, ldb=w.KMp, ldc=G,
                                   bias=L.ptr(self.P(g, "bm")))
-                    L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 2 | 4, st), "spv_dec_nb_fwd")
+                    L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, Pb, Sb, 2 | 4, L.ptr(w.zzb) if nb else None, KZb, KMIX, st), "spv_dec_nb_fwd")
             else:
-                L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, P, S, 2, st), "spv_dec_nb_fwd")
+                L.check(lib.spv_dec_nb_fwd(src, dptrs, ldx, KMIX, B, G, HD, Pb, Sb, 2, L.ptr(w.zzb) if nb else None, KZb, KMIX, st), "spv_dec_nb_fwd")
             if evs is not None:
                 evs[1].record()
         if Bs[0] != Bs[1]:
@@ -737,14 +789,16 @@ class StepEngine:
             G, B = d.genes[g], Bs[g]
             src, xptr, ldx = srcs[g]
             zzp = w.amix.data_ptr() + 4 * HD
+            nb, Pb, Sb, KZb = d.nb, d.Pb, d.Sb, d.KZb
+            zb, ld_zb = (L.ptr(w.zzb), KZb) if nb else (zzp, KMIX)
             if self.fused_nb:
                 # logits recomputed on the tensor cores, gradients in the TMEM epilogue -> D3 = [dpi | dyp | dys] (bf16)
                 evs = next(self.nb_bwd_events) if self.nb_bwd_events is not None else None
                 if evs is not None:
                     evs[0].record()
                 L.check(lib.spv_dec_nb_bwd_tc(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, L.ptr(w.amixb), w.KMp,
-                                              L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.zcb), L.ptr(w.wzf), L.ptr(w.D3), B, G, HD, P, S,
-                                              -float(grad_scale) / B, L.ptr(w.colsum), st), "spv_dec_nb_bwd_tc")
+                                              L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.zcb), L.ptr(w.wzf), L.ptr(w.D3), B, G, HD, Pb, Sb,
+                                              -float(grad_scale) / B, L.ptr(w.colsum), KMIX, st), "spv_dec_nb_bwd_tc")
                 if evs is not None:
                     evs[1].record()
                 Gp3 = 3 * w.Gp
@@ -752,26 +806,30 @@ class StepEngine:
                 # N = P + S).  Kept out of the mixture GEMM below: stacked into its K it would triple that GEMM's operand traffic.
                 f3, al = self.dec_fmt, float(grad_scale) / B  # D3 is stored in natural units: the GEMMs apply |scale|
                 with self._branch(g, "dzg"):
-                    self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, w.Wstack.data_ptr() + 2 * (w.Gp * w.KMp + HD), L.ptr(w.dzraw), B, KZ,
-                                  2 * w.Gp, lda=Gp3, ldb=w.KMp, ldc=KZ, b_mn=1, splits=w.tc_splits_dz, ws=w.ws2, fmt=f3, alpha=al)
+                    self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, w.Wstack.data_ptr() + 2 * (w.Gp * w.KMp + HD), L.ptr(w.dzraw), B, KZb,
+                                  2 * w.Gp, lda=Gp3, ldb=w.KMp, ldc=KZb, b_mn=1, splits=w.tc_splits_dz, ws=w.ws2, fmt=f3, alpha=al)
                 with self._branch(g, "wgrad"):  # d Wm = dpi^T [hm | zz]
                     self._tc_gemm(L.ptr(w.D3), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=Gp3, ldb=w.KMp, ldc=KMIX,
                                   a_mn=1, b_mn=1, fmt=f3, alpha=al)
-                Qp, Qs, ldq, dzraw = w.CQ.data_ptr(), w.CQ.data_ptr() + 4 * (w.Gp * KZ + P), KZ, None
+                Qp, Qs, ldq, dzraw = w.CQ.data_ptr(), w.CQ.data_ptr() + 4 * (w.Gp * KZb + Pb), KZb, None
+                if nb:  # 16-bit copy of the regressors' inputs (without covariates they are the latent columns of amixb)
+                    self._to_dec(L.ptr(w.zzb), KZb, L.ptr(w.zzb16), w.zzb16.stride(0), B, KZb)
+                zb16, ld_zb16 = (L.ptr(w.zzb16), w.zzb16.stride(0)) if nb else (w.amixb.data_ptr() + 2 * HD, w.KMp)
                 # per-gene BatchNorm backward chain on the second auxiliary stream: it needs Q and the column sums, not
                 # d [hm | zz], so it runs beside the input-gradient GEMM and the hidden layer's backward
                 with self._branch(g, "gene", lane=1):
                     # [Qp | .] = dyp^T zz, [. | Qs] = dys^T zz in one GEMM over the stacked rows (rows g and Gp + g)
-                    self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, w.amixb.data_ptr() + 2 * HD, L.ptr(w.CQ), 2 * w.Gp, KZ, B, lda=Gp3,
-                                  ldb=w.KMp, ldc=KZ, a_mn=1, b_mn=1, fmt=f3, alpha=al)
+                    self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, zb16, L.ptr(w.CQ), 2 * w.Gp, KZb, B, lda=Gp3,
+                                  ldb=ld_zb16, ldc=KZb, a_mn=1, b_mn=1, fmt=f3, alpha=al)
                     self._gene_bwd(g, w, Qp, Qs, ldq, B, G)
                 # d [hm | zz] (mixture part) = dpi Wm
                 self._tc_gemm(L.ptr(w.D3), L.ptr(w.Wstack), L.ptr(w.damix), B, KMIX, G, lda=Gp3, ldb=w.KMp, ldc=KMIX, b_mn=1,
                               splits=w.tc_splits_damix, ws=w.ws, fmt=f3, alpha=al)
             else:
-                L.check(lib.spv_dec_nb_bwd(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, KMIX, B, G, HD, P, S,
+                L.check(lib.spv_dec_nb_bwd(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, KMIX, B, G, HD, Pb, Sb,
                                            -float(grad_scale) / B, L.ptr(w.colsum), L.ptr(w.dpib) if self.bf16 else None,
-                                           3 * w.Gp if self.bf16 else 0, st), "spv_dec_nb_bwd")
+                                           3 * w.Gp if self.bf16 else 0, L.ptr(w.zzb) if nb else None, KZb, KMIX, st),
+                        "spv_dec_nb_bwd")
                 # d Wm = dpi^T [hm | zz];   d [hm | zz] = dpi Wm
                 if self.bf16:
                     self._tc_gemm(L.ptr(w.dpib), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=3 * w.Gp, ldb=w.KMp,
@@ -783,10 +841,10 @@ class StepEngine:
                     self._gemm(L.ptr(w.dpi), L.ptr(self.P(g, "Wm")), L.ptr(w.damix), B, KMIX, G, lda=G, ldb=KMIX, ldc=KMIX,
                                splits=w.splits_g, ws=w.ws)
                 # Q = dy^T z ;  dz (softmax branches) = dy W'
-                self._gemm(L.ptr(w.dyp), zzp, L.ptr(w.Qp), G, P, B, lda=G, ldb=KMIX, ldc=P, ta=1, splits=w.splits_b, ws=w.ws)
-                self._gemm(L.ptr(w.dys), zzp + 4 * P, L.ptr(w.Qs), G, S, B, lda=G, ldb=KMIX, ldc=S, ta=1, splits=w.splits_b, ws=w.ws)
-                self._gemm(L.ptr(w.dyp), L.ptr(w.wfold), L.ptr(w.dzraw), B, P, G, lda=G, ldb=KZ, ldc=KZ, splits=w.splits_g, ws=w.ws)
-                self._gemm(L.ptr(w.dys), w.wfold.data_ptr() + 4 * P, w.dzraw.data_ptr() + 4 * P, B, S, G, lda=G, ldb=KZ, ldc=KZ,
+                self._gemm(L.ptr(w.dyp), zb, L.ptr(w.Qp), G, Pb, B, lda=G, ldb=ld_zb, ldc=Pb, ta=1, splits=w.splits_b, ws=w.ws)
+                self._gemm(L.ptr(w.dys), zb + 4 * Pb, L.ptr(w.Qs), G, Sb, B, lda=G, ldb=ld_zb, ldc=Sb, ta=1, splits=w.splits_b, ws=w.ws)
+                self._gemm(L.ptr(w.dyp), L.ptr(w.wfold), L.ptr(w.dzraw), B, Pb, G, lda=G, ldb=KZb, ldc=KZb, splits=w.splits_g, ws=w.ws)
+                self._gemm(L.ptr(w.dys), w.wfold.data_ptr() + 4 * Pb, w.dzraw.data_ptr() + 4 * Pb, B, Sb, G, lda=G, ldb=KZb, ldc=KZb,
                            splits=w.splits_g, ws=w.ws)
                 Qp, Qs, ldq, dzraw = L.ptr(w.Qp), L.ptr(w.Qs), 0, L.ptr(w.dzraw)
             # hidden layer of the mixing net: ReLU + BatchNorm backward (needs only d [hm | zz]); its Linear's input and
@@ -794,14 +852,23 @@ class StepEngine:
             L.check(lib.spv_bn_bwd(L.ptr(w.damix), KMIX, L.ptr(w.ah), HD, L.ptr(w.amix), KMIX, L.ptr(w.dah), HD, B, HD,
                                    L.ptr(self.P(g, "gh")), L.ptr(w.bn_h_mean), L.ptr(w.bn_h_istd), L.ptr(self.Gd(g, "gh")),
                                    L.ptr(self.Gd(g, "bth")), st), "spv_bn_bwd")
+            def hidden_input_grad(dst):
+                """dzraw += dah Wh (the latent columns; the covariate columns of Wh carry no input gradient)"""
+                wh, kh = self.P(g, "Wh").data_ptr(), KZ + nb
+                if not nb:
+                    self._gemm(L.ptr(w.dah), wh, dst, B, KZ, HD, lda=HD, ldb=kh, ldc=KZb, acc=1)
+                else:  # dzraw is laid out [z_private_arg | oh | z_shared_arg | oh], Wh's columns [z_private_arg | z_shared_arg | oh]
+                    self._gemm(L.ptr(w.dah), wh, dst, B, P, HD, lda=HD, ldb=kh, ldc=KZb, acc=1)
+                    self._gemm(L.ptr(w.dah), wh + 4 * P, dst + 4 * Pb, B, S, HD, lda=HD, ldb=kh, ldc=KZb, acc=1)
+
             if dzraw is None:  # fused path: dzraw already holds the softmax-branch part (branch "dzg", same auxiliary stream)
                 dzraw = L.ptr(w.dzraw)
                 with self._branch(g, "hid"):
-                    self._gemm(L.ptr(w.dah), L.ptr(self.P(g, "Wh")), dzraw, B, KZ, HD, lda=HD, ldb=KZ, ldc=KZ, acc=1)
+                    hidden_input_grad(dzraw)
             else:
-                self._gemm(L.ptr(w.dah), L.ptr(self.P(g, "Wh")), dzraw, B, KZ, HD, lda=HD, ldb=KZ, ldc=KZ, acc=1)
+                hidden_input_grad(dzraw)
             with self._branch(g, "wgrad"):
-                self._gemm(L.ptr(w.dah), zzp, L.ptr(self.Gd(g, "Wh")), HD, KZ, B, lda=HD, ldb=KMIX, ldc=KZ, ta=1,
+                self._gemm(L.ptr(w.dah), zzp, L.ptr(self.Gd(g, "Wh")), HD, KZ + nb, B, lda=HD, ldb=KMIX, ldc=KZ + nb, ta=1,
                            splits=w.splits_b, ws=w.ws2)
             with self._branch(g, "wgrad1", lane=1):
                 L.check(lib.spv_colsum(L.ptr(w.dah), HD, B, HD, L.ptr(self.Gd(g, "bh")), self._stream()), "spv_colsum")
@@ -809,11 +876,16 @@ class StepEngine:
                 self._gene_bwd(g, w, Qp, Qs, ldq, B, G)
             self._join(g, "hid")
             if self.fused_nb:  # column sums of the branch / hidden-layer input gradient (the consistent mean-coupling term)
-                L.check(lib.spv_colsum(dzraw, KZ, B, KZ, L.ptr(w.dzraw_sum), st), "spv_colsum")
+                L.check(lib.spv_colsum(dzraw, KZb, B, KZb, L.ptr(w.dzraw_sum), st), "spv_colsum")
             self._join(g, "gene")
-            L.check(lib.spv_dec_dzz_combine(w.damix.data_ptr() + 4 * HD, KMIX, dzraw, L.ptr(w.vpart), L.ptr(w.mpart),
-                                            w.nGB, zzp, KMIX, L.ptr(w.zmean), L.ptr(w.dzz), B, P, S,
+            # without covariates the mixture layer's input gradient (latent columns of damix) has the regressors' layout and is
+            # added here; with them it is added by the compaction below
+            L.check(lib.spv_dec_dzz_combine(None if nb else w.damix.data_ptr() + 4 * HD, KMIX, dzraw, L.ptr(w.vpart), L.ptr(w.mpart),
+                                            w.nGB, zb, ld_zb, L.ptr(w.zmean), L.ptr(w.dzzb), B, Pb, Sb,
                                             L.ptr(w.dzraw_sum) if self.fused_nb else None, st), "spv_dec_dzz_combine")
+            if nb:
+                L.check(lib.spv_cov_compact(L.ptr(w.dzzb), KZb, L.ptr(w.dzz), KZ, B, P, S, nb, w.damix.data_ptr() + 4 * HD, KMIX, st),
+                        "spv_cov_compact")
         # ---------------- PoE
         own = self._poe_sides(ws)
         arrs = []
@@ -901,11 +973,14 @@ class StepEngine:
                 if not fuse1 or self.enc_mid:
                     L.check(lib.spv_to_bf16_split(L.ptr(w.dh1), 2 * H, L.ptr(w.dh1b), L.ptr(w.dh1b_lo), 2 * H, B, 2 * H, st),
                             "spv_to_bf16_split")
-                self._tc_gemm_split(L.ptr(w.dh1b), L.ptr(w.dh1b_lo), L.ptr(w.Tb), L.ptr(w.Tb_lo), L.ptr(self.Gd(g, "W1")), 2 * H, G, B,
-                                    lda=2 * H, ldb=w.Gp, ldc=G, a_mn=1, b_mn=1)
+                self._tc_gemm_split(L.ptr(w.dh1b), L.ptr(w.dh1b_lo), L.ptr(w.Tb), L.ptr(w.Tb_lo), L.ptr(self.Gd(g, "W1")), 2 * H,
+                                    G + d.nb, B, lda=2 * H, ldb=w.Gpe, ldc=G + d.nb, a_mn=1, b_mn=1)
             else:
-                self._gemm(L.ptr(w.dh1), xptr, L.ptr(self.Gd(g, "W1")), 2 * H, G, B, lda=2 * H, ldb=ldx, ldc=G, ta=1, srcB=src,
+                self._gemm(L.ptr(w.dh1), xptr, L.ptr(self.Gd(g, "W1")), 2 * H, G, B, lda=2 * H, ldb=ldx, ldc=G + d.nb, ta=1, srcB=src,
                            rowsB=bt.rows)
+                if d.nb:  # covariate columns of the first layer's weight: dh1^T one_hot
+                    self._gemm(L.ptr(w.dh1), L.ptr(w.oh), self.Gd(g, "W1").data_ptr() + 4 * G, 2 * H, d.nb, B, lda=2 * H, ldb=d.nb,
+                               ldc=G + d.nb, ta=1)
             # last bias gradient on the main stream: queued behind the auxiliary lanes' weight-gradient GEMMs it would finish later
             L.check(lib.spv_colsum(L.ptr(w.dh1), 2 * H, B, 2 * H, L.ptr(self.Gd(g, "b1")), st), "spv_colsum")
             self._join(g)
@@ -955,7 +1030,7 @@ class StepEngine:
         out = []
         for g, G in enumerate(self.d.genes):
             W1b, Wstack, W1b_lo = self.wb[g]
-            out.append((self.params.offsets[g]["W1"][0], 2 * self.d.n_hidden, G, W1b, W1b.stride(0), W1b_lo, 0))
+            out.append((self.params.offsets[g]["W1"][0], 2 * self.d.n_hidden, G + self.d.nb, W1b, W1b.stride(0), W1b_lo, 0))
             out.append((self.params.offsets[g]["Wm"][0], G, self.d.KMIX, Wstack, Wstack.stride(0), None, 1 if self.fused_nb else 0))
         return out
 

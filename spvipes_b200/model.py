@@ -104,8 +104,8 @@ class spVIPES:
         if match_clusters and "processed_transport_labels" not in adata.obs.columns:
             raise ValueError("match_clusters=True needs adata.obs['processed_transport_labels'] (reference process_transport_plan "
                              "derives it with scanpy/leiden, which is outside this package)")
-        if batch_key is not None and adata.obs[batch_key].nunique() > 1:
-            raise NotImplementedError("batch covariates are not on the B200 hot path yet")
+        if batch_key is not None and batch_key not in adata.obs.columns:
+            raise KeyError(f"{batch_key} not in adata.obs")
         cls._setup[id(adata)] = {"groups_key": groups_key, "match_clusters": match_clusters, "transport_plan_key": transport_plan_key,
                                  "label_key": label_key, "batch_key": batch_key, "layer": layer}
 
@@ -130,10 +130,17 @@ class spVIPES:
             n_labels = len(cat.categories)
         elif not pair_data:
             self._label_codes = np.asarray(pd.Categorical(adata.obs["processed_transport_labels"]).codes, dtype=np.int32)
+        # batch covariate: categorical codes (scvi CategoricalObsField: sorted categories); n_batch = number of categories, the
+        # one-hot code is injected when n_batch > 1 (reference model/spvipes.py:230, 252; nn/networks.py:60-68)
+        batch_key = self.setup_args["batch_key"]
+        self._batch_codes, n_batch = None, 0
+        if batch_key is not None:
+            bcat = pd.Categorical(adata.obs[batch_key])
+            self._batch_codes, n_batch = np.asarray(bcat.codes, dtype=np.int32), len(bcat.categories)
         self.module = spVIPESmodule(groups_lengths=uns["groups_lengths"], groups_obs_names=uns["groups_obs_names"],
                                     groups_var_names=uns["groups_var_names"], groups_var_indices=uns["groups_var_indices"],
                                     groups_obs_indices=uns["groups_obs_indices"], transport_plan=transport_plan, pair_data=pair_data,
-                                    use_labels=use_labels, n_labels=n_labels, n_batch=0, n_hidden=n_hidden,
+                                    use_labels=use_labels, n_labels=n_labels, n_batch=n_batch, n_hidden=n_hidden,
                                     n_dimensions_shared=n_dimensions_shared, n_dimensions_private=n_dimensions_private,
                                     dropout_rate=dropout_rate, **model_kwargs)
         self.is_trained_ = False
@@ -153,12 +160,16 @@ class spVIPES:
             rows, cols = np.asarray(uns["groups_obs_indices"][g]), np.asarray(uns["groups_var_indices"][g])
             blk = _dense(X[rows][:, cols]) if not hasattr(X, "tocsr") else _dense(X.tocsr()[rows][:, cols])
             integral = np.all(blk == np.round(blk)) and blk.min() >= 0 and blk.max() <= 65535
-            t = torch.from_numpy(blk.astype(np.uint16)) if integral else torch.from_numpy(blk.astype(np.float32))
+            # (numpy's column selection hands back a Fortran-ordered block: make it row-major, the kernels read rows)
+            t = torch.from_numpy(np.ascontiguousarray(blk.astype(np.uint16 if integral else np.float32)))
             labels = None
             if self._label_codes is not None:
                 labels = torch.from_numpy(self._label_codes[rows].astype(np.int32)).to(dev)
             idx = torch.from_numpy(np.asarray(self.adata.obs["indices"])[rows].astype(np.int32)).to(dev)
-            data.append({"X": t.to(dev), "labels": labels, "idx": idx, "row0": int(rows[0]), "rows": rows})
+            batch = None
+            if self.module.engine.d.nb:
+                batch = torch.from_numpy(self._batch_codes[rows].astype(np.int32)).to(dev)
+            data.append({"X": t.to(dev), "labels": labels, "idx": idx, "row0": int(rows[0]), "rows": rows, "batch": batch})
         self._device_data = data
         return data
 
@@ -174,10 +185,13 @@ class spVIPES:
         dev = self.module.device
         data = self._to_device()
         bufs = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in (0, 1)]
+        # batch codes of the minibatch: a static buffer refreshed from the per-cell codes before every step
+        self._batch_bufs = [torch.zeros(B, dtype=torch.int32, device=dev) if data[g]["batch"] is not None else None for g in (0, 1)]
         batches = []
         for g in (0, 1):
             d = data[g]
-            batches.append(GroupBatch(X=d["X"], rows=bufs[g], labels=d["labels"], idx=d["idx"], labels_per_cell=True, B=B))
+            batches.append(GroupBatch(X=d["X"], rows=bufs[g], labels=d["labels"], idx=d["idx"], labels_per_cell=True, B=B,
+                                      batch=self._batch_bufs[g]))
         return bufs, batches
 
     # ------------------------------------------------------------------ training
@@ -199,6 +213,7 @@ class spVIPES:
             # the OT modes index the plan / cluster labels with per-minibatch arrays: gather them on the host per step
             use_cuda_graph = False
         loop = TrainLoop(eng, lr=lr, eps=eps, weight_decay=wd, n_epochs_kl_warmup=n_epochs_kl_warmup)
+        global_step = 0
         self.module.train()
         bufs, batches = self._static_batches(batch_size)
         graph = None
@@ -211,8 +226,13 @@ class spVIPES:
             dev_rows = [torch.stack([l[g] for l in local]).to(eng.device) for g in (0, 1)]
             tot = torch.zeros((), device=eng.device)
             for s in range(len(steps)):
+                if n_steps_kl_warmup:  # scvi TrainingPlan: the step-based warm-up takes precedence over the epoch-based one
+                    eng.set_kl_weight(min(1.0, global_step / n_steps_kl_warmup))
+                global_step += 1
                 for g in (0, 1):
                     bufs[g].copy_(dev_rows[g][s], non_blocking=True)
+                    if self._batch_bufs[g] is not None:
+                        self._batch_bufs[g].copy_(self._device_data[g]["batch"][dev_rows[g][s].long()])
                 if eng.mode != "label":
                     step_batches = self._ot_batches(bufs, batch_size)
                     loop.step(step_batches)
@@ -235,7 +255,7 @@ class spVIPES:
             d = data[g]
             r = bufs[g].long()
             lab = d["labels"][r].contiguous() if d["labels"] is not None else None
-            out.append(GroupBatch(X=d["X"], rows=bufs[g], labels=lab, idx=d["idx"][r].contiguous(), B=B))
+            out.append(GroupBatch(X=d["X"], rows=bufs[g], labels=lab, idx=d["idx"][r].contiguous(), B=B, batch=self._batch_bufs[g]))
         return out
 
     # ------------------------------------------------------------------ latent extraction
@@ -283,7 +303,8 @@ class spVIPES:
                     d = self._device_data[g]
                     r = rows[g].long()
                     lab = d["labels"][r].contiguous() if d["labels"] is not None else None
-                    batches.append(GroupBatch(X=d["X"], rows=rows[g], labels=lab, idx=d["idx"][r].contiguous(), B=len(st[g])))
+                    bc = d["batch"][r].contiguous() if d["batch"] is not None else None
+                    batches.append(GroupBatch(X=d["X"], rows=rows[g], labels=lab, idx=d["idx"][r].contiguous(), B=len(st[g]), batch=bc))
                 noise = _noise_fn(counter[0], len(st[0]), len(st[1])) if _noise_fn is not None else None
                 counter[0] += 1
                 ws = eng.forward(batches, training=False, noise=noise, with_grad=False, decode=False)

@@ -18,8 +18,7 @@ deposits `.grad` on the nn.Parameters, so scvi's TrainingPlan (or any torch opti
 fallback: constructing the module without a CUDA device / without the built library raises.
 
 Differences that are deliberate: reparameterisation noise and dropout masks come from an in-kernel Philox generator seeded
-from torch.initial_seed() (the reference consumes the global torch RNG, including draws it discards: quirk Q9); batch
-covariates (n_batch > 1) are not part of the hot path yet and raise NotImplementedError.
+from torch.initial_seed() (the reference consumes the global torch RNG, including draws it discards: quirk Q9).
 """
 from __future__ import annotations
 
@@ -250,8 +249,6 @@ class spVIPESmodule(nn.Module):
                  use_layer_norm: bool = False, log_variational_inference: bool = True, log_variational_generative: bool = True,
                  dispersion: str = "gene", device: Optional[str] = None, precision: str = "fp32"):
         super().__init__()
-        if n_batch > 1:
-            raise NotImplementedError("batch covariates (n_batch > 1) are not on the B200 hot path yet")
         if not (log_variational_inference and log_variational_generative) or use_layer_norm or not use_batch_norm:
             raise NotImplementedError("only the reference's default normalisation switches are implemented")
         if len(groups_lengths) != 2:
@@ -279,7 +276,7 @@ class spVIPESmodule(nn.Module):
             keep = transport_plan.dtype == torch.bfloat16 and not pair_data
             plan = transport_plan.to(dev, torch.bfloat16 if keep else torch.float32).contiguous()
         self.engine = StepEngine(genes, n_hidden, n_dimensions_shared, n_dimensions_private, dropout_rate, mode, dev,
-                                 seed=int(torch.initial_seed() % (2 ** 62)), plan=plan, precision=precision)
+                                 seed=int(torch.initial_seed() % (2 ** 62)), plan=plan, precision=precision, n_batch=n_batch)
         # parameters / buffers are VIEWS of the engine's flat stores under the reference's names
         self._param_names = self.engine.params.names()
         self._torch_params = OrderedDict()
@@ -355,9 +352,12 @@ class spVIPESmodule(nn.Module):
                 "poe_stats": inference_outputs["poe_stats"], "library": inference_outputs["library"],
                 "groups": [g["groups"] for g in tensors_by_group], "batch_index": [g[BATCH_KEY] for g in tensors_by_group]}
 
-    def _batches(self, x, global_indices, labels=None, processed_labels=None):
+    def _batches(self, x, global_indices, labels=None, processed_labels=None, batch_index=None):
         dev = self.engine.device
         out = []
+        nb = self.engine.d.nb
+        if nb and batch_index is None:
+            raise ValueError("batch_index is required: the module was built with n_batch > 1")
         for g in (0, 1):
             X = x[g].to(dev)
             vi = np.asarray(self.groups_var_indices[g])
@@ -376,7 +376,8 @@ class spVIPESmodule(nn.Module):
             elif processed_labels is not None:
                 lab = processed_labels[g].to(dev).flatten().to(torch.int32)
             idx = global_indices[g].to(dev).flatten().to(torch.int32) if global_indices is not None else None
-            out.append(GroupBatch(X=X.contiguous() if X.stride(1) != 1 else X, col0=col0, labels=lab, idx=idx, B=int(X.shape[0])))
+            bc = batch_index[g].to(dev).flatten().to(torch.int32) if nb else None
+            out.append(GroupBatch(X=X.contiguous() if X.stride(1) != 1 else X, col0=col0, labels=lab, idx=idx, B=int(X.shape[0]), batch=bc))
         return out
 
     def _stats_dicts(self, ws):
@@ -405,7 +406,7 @@ class spVIPESmodule(nn.Module):
     @torch.no_grad()
     def inference(self, x, batch_index, groups, global_indices, **kwargs):
         """encoders + PoE only (used by get_latent_representation, reference model/spvipes.py:537-538)"""
-        batches = self._batches(x, global_indices, kwargs.get("labels"), kwargs.get("processed_labels"))
+        batches = self._batches(x, global_indices, kwargs.get("labels"), kwargs.get("processed_labels"), batch_index)
         ws = self.engine.forward(batches, training=self.training, noise=self._noise, with_grad=False, decode=False)
         self._last_ws, self._last_batches = ws, batches
         return self._stats_dicts(ws)
@@ -459,7 +460,7 @@ class spVIPESmodule(nn.Module):
             if not compute_loss:
                 return inference_outputs, generative_outputs
             return inference_outputs, generative_outputs, self._loss_output(loss, ws)
-        batches = self._batches(inp["x"], inp["global_indices"], inp.get("labels"), inp.get("processed_labels"))
+        batches = self._batches(inp["x"], inp["global_indices"], inp.get("labels"), inp.get("processed_labels"), inp["batch_index"])
         self._last_batches = batches
         if self.training and torch.is_grad_enabled():
             loss = _StepFunction.apply(self, batches, True, *[self._torch_params[n] for n in self._param_names])
@@ -480,8 +481,8 @@ class spVIPESmodule(nn.Module):
         unsupported dtypes)"""
         x = inp["x"]
         B0, B1 = int(x[0].shape[0]), int(x[1].shape[0])
-        if B0 != B1 or any(x[g].dtype not in (torch.float32, torch.uint16) for g in (0, 1)):
-            return None
+        if B0 != B1 or any(x[g].dtype not in (torch.float32, torch.uint16) for g in (0, 1)) or self.engine.d.nb:
+            return None  # (batch covariates: the eager path stages the batch codes)
         has_labels = self.use_labels or (self.use_transport_plan and not self.pair_data)
         key = (B0, x[0].dtype, x[1].dtype, int(x[0].shape[1]), int(x[1].shape[1]), has_labels)
         plan = self._plans.get(key)
@@ -498,6 +499,8 @@ class spVIPESmodule(nn.Module):
         tag = "p" if type_latent == "private" else "s"
         e = self.engine
         w = e.P(dataset, "W" + tag)
+        if e.d.nb:
+            w = w[:, :-e.d.nb]  # the covariate columns are not loadings (reference :804-805)
         sigma = torch.sqrt(e.Bf(dataset, "rv_" + tag) + 1e-3)
         loadings = (e.P(dataset, "g" + tag) / sigma).unsqueeze(1) * w
         return loadings.detach().cpu().numpy()

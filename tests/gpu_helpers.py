@@ -7,7 +7,8 @@ def engine_from_golden(gd, device="cuda", precision="fp32"):
     from spvipes_b200.engine import GroupBatch, Noise, StepEngine
 
     plan = gd.plan.to(device) if gd.mode != "label" else None
-    eng = StepEngine((gd.G0, gd.G1), gd.H, gd.S, gd.P, gd.dropout, gd.mode, device, plan=plan, precision=precision)
+    eng = StepEngine((gd.G0, gd.G1), gd.H, gd.S, gd.P, gd.dropout, gd.mode, device, plan=plan, precision=precision,
+                     n_batch=gd.n_batch)
     eng.load_state_dict(gd.sd)
     eng.set_kl_weight(gd.kl_weight)
     batches = []
@@ -15,7 +16,8 @@ def engine_from_golden(gd, device="cuda", precision="fp32"):
         X = torch.from_numpy(gd.x[g].numpy().astype(np.uint16)).to(device)
         labels = torch.from_numpy(gd.labels[g].astype(np.int32)).to(device) if gd.mode in ("label", "cluster") else None
         idx = torch.from_numpy(gd.idx[g].astype(np.int32)).to(device)
-        batches.append(GroupBatch(X=X, labels=labels, idx=idx))
+        bc = torch.from_numpy(np.asarray(gd.batch[g]).reshape(-1).astype(np.int32)).to(device) if gd.n_batch > 1 else None
+        batches.append(GroupBatch(X=X, labels=labels, idx=idx, batch=bc))
     dm = gd.drop_masks()
     drop = None
     if dm is not None:

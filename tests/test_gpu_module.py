@@ -208,3 +208,31 @@ def test_get_latent_representation_matches_reference(name, precision):
                      ("private1_reordered", lat["private_reordered"][1])):
         assert got.shape == z[key].shape, key
         assert relerr(got, z[key]) < 1e-3, (key, relerr(got, z[key]))
+
+
+def test_model_api_with_batch_covariate_and_step_warmup():
+    """setup_anndata(batch_key=...) with two batches: the one-hot batch code reaches the kernels through train() and
+    get_latent_representation(); n_steps_kl_warmup drives the KL weight per step"""
+    from spvipes_b200 import synth
+    from spvipes_b200.model import GroupedData, prepare_adatas, spVIPES
+    n, G = (500, 420), (64, 72)
+    data = synth.make_counts(n, G, n_labels=3, device="cuda", seed=15)
+    ads = {}
+    rng = np.random.RandomState(0)
+    for gi, key in enumerate(("mouse", "human")):
+        obs = pd.DataFrame({"cell_type": [f"t{int(v)}" for v in data.labels[gi].cpu().numpy()], "lab": rng.choice(["b0", "b1"], n[gi])})
+        ads[key] = GroupedData(X=data.X[gi].cpu().numpy().astype(np.float32), obs=obs, var_names=[f"g{j}" for j in range(G[gi])])
+    adata = prepare_adatas(ads)
+    spVIPES.setup_anndata(adata, groups_key="groups", label_key="cell_type", batch_key="lab")
+    for precision in ("fp32", "bf16"):
+        model = spVIPES(adata, n_hidden=64, n_dimensions_shared=12, n_dimensions_private=6, dropout_rate=0.1, precision=precision)
+        assert model.module.engine.d.nb == 2
+        assert model.module.state_dict()["encoder_0_private.fc1.weight"].shape == (64, G[0] + 2)
+        gil = [list(ix) for ix in adata.uns["groups_obs_indices"]]
+        model.train(gil, max_epochs=8, batch_size=128, train_size=0.9, n_steps_kl_warmup=10)
+        h = model.history["train_loss_epoch"]
+        assert np.isfinite(h).all() and h[-1] < h[0], h
+        assert float(model.module.engine.kl_weight) == 1.0  # 10 warm-up steps are over
+        lat = model.get_latent_representation(gil, batch_size=200)
+        assert lat["shared"][1].shape == (n[1], 12) and np.isfinite(lat["private"][0]).all()
+        assert model.get_loadings()[(0, "private")].shape == (G[0], 6)

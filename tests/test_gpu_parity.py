@@ -87,3 +87,59 @@ def test_adam_step_matches_oracle():
         assert relerr(eng.params.flat, p) < 1e-5
         assert int(eng.step_dev.item()) == t
         p, m, v = eng.params.flat.clone(), eng.adam_m.clone(), eng.adam_v.clone()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["label_batch3_tiny", "paired_batch2_eval"])
+def test_batch_covariates_match_reference(name, precision):
+    """n_batch > 1: the one-hot batch code appended to the input of the encoders' first layer and of the four decoder nets
+    (reference nn/networks.py:60-68, 110-118; scvi FCLayers inject_covariates), against fixtures from the unmodified reference
+    (tests/golden_next/, oracle/make_golden.py) - forward gates of the mode, gradients per parameter <= 2e-3."""
+    from tests.helpers import GOLDEN_NEXT_DIR
+    from tests.gpu_helpers import gate_consistent_grads
+    gd = Golden(name, GOLDEN_NEXT_DIR)
+    assert gd.n_batch > 1
+    eng, batches, noise = engine_from_golden(gd, precision=precision)
+    ws = eng.forward(batches, training=gd.training, noise=noise)
+    if gd.training:
+        eng.backward()
+    torch.cuda.synchronize()
+    out = engine_outputs(eng, ws)
+    tol = 1e-4 if precision == "fp32" else 1e-2
+    assert relerr(out["loss"], gd.out["loss"]) < tol
+    for k in ("rec", "kl_private", "kl_poe"):
+        for g in (0, 1):
+            assert relerr(out[k][g].reshape(-1), gd.out[f"{k}{g}"].reshape(-1)) < tol, (k, g)
+    for k in LATENTS_1E3:
+        for g in (0, 1):
+            assert relerr(out[k][g], gd.out[f"{k}{g}"]) < 1e-3, (k, g)
+    if gd.training:
+        probe = {}
+        run_oracle(gd, backward=False, probe=probe)
+        want, switched = gate_consistent_grads(eng, ws, probe, gd.grads, lambda gates: run_oracle(gd, gates=gates)[1], gd.drop_masks())
+        worst, where = grad_errors({k: v.cpu() for k, v in eng.grad_dict().items()}, want)
+        assert worst < 2e-3, (worst, where, switched)
+        sd = eng.state_dict()
+        for k, v in gd.after.items():  # BatchNorm running statistics after the step
+            assert relerr(sd[k].cpu(), v) < (1e-4 if precision == "fp32" else 1e-3), k
+
+
+def test_get_loadings_strips_covariate_columns():
+    """reference module/spVIPESmodule.py:773-807: loadings = diag(gamma / sqrt(running_var + eps)) W, covariate columns dropped"""
+    import numpy as np
+    from tests.helpers import GOLDEN_NEXT_DIR
+    from spvipes_b200.module import spVIPESmodule
+    gd = Golden("label_batch3_tiny", GOLDEN_NEXT_DIR)
+    m = spVIPESmodule(groups_lengths={0: gd.G0, 1: gd.G1}, groups_obs_names=[None, None], groups_var_names={0: None, 1: None},
+                      groups_obs_indices=[None, None], groups_var_indices=[np.arange(gd.G0), np.arange(gd.G0, gd.G0 + gd.G1)],
+                      use_labels=True, n_labels=gd.n_labels, n_batch=gd.n_batch, n_hidden=gd.H, n_dimensions_shared=gd.S,
+                      n_dimensions_private=gd.P, dropout_rate=gd.dropout)
+    m.load_state_dict(gd.sd, strict=True)
+    for g, G in enumerate((gd.G0, gd.G1)):
+        for kind, dim in (("shared", gd.S), ("private", gd.P)):
+            k = f"decoder_{g}.factor_regressor_{kind}.fc_layers.Layer 0"
+            w, gamma, rv = gd.sd[k + ".0.weight"], gd.sd[k + ".1.weight"], gd.sd[k + ".1.running_var"]
+            want = ((gamma / torch.sqrt(rv + 1e-3)).unsqueeze(1) * w)[:, :-gd.n_batch].numpy()
+            got = m.get_loadings(g, kind)
+            assert got.shape == (G, dim)
+            assert np.allclose(got, want, rtol=1e-6, atol=1e-7)

@@ -124,7 +124,7 @@ def test_stats_tc_matches_simt_statistics():
         bt = batches[g]
         src, esz = eng._src_of(bt.X)
         ptrs = eng._dec_ptrs(g, w, bt.X.data_ptr(), bt.rows, True)
-        L.check(eng.lib.spv_dec_nb_fwd(src, ptrs, bt.X.stride(0), d.KMIX, w.B, w.G, 256, d.n_private, d.n_shared, 1,
+        L.check(eng.lib.spv_dec_nb_fwd(src, ptrs, bt.X.stride(0), d.KMIX, w.B, w.G, 256, d.n_private, d.n_shared, 1, None, 0, 0,
                                        torch.cuda.current_stream().cuda_stream), "spv_dec_nb_fwd")
         torch.cuda.synchronize()
         want = w.rowc[:, :2]
