@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspvipes_b200.so")
+LIB_PATH = os.environ.get("SPV_LIB") or os.path.join(_HERE, "libspvipes_b200.so")  # SPV_LIB: an A/B build of the same ABI
 
 SRC_F32, SRC_U16_LOG1P, SRC_F32_LOG1P = 0, 1, 2
 POE_LABEL, POE_PAIRED, POE_CLUSTER = 0, 1, 2
@@ -32,6 +32,8 @@ _SIGS = {
     "spv_tc_gemm": [i, i, p, ll, p, ll, p, ll, i, i, i, p, i, i, i, p, p],
     "spv_tc_gemm_ex": [i, f, i, i, p, ll, p, ll, p, ll, i, i, i, p, i, i, i, p, p],
     "spv_tc_gemm_split": [i, i, p, p, ll, p, p, ll, p, ll, i, i, i, p, i, i, i, p, p],
+    "spv_enc_fc1_fwd": [p, ll, p, p, p, ll, p, ll, i, i, i, p, i, i, i, p, p],
+    "spv_enc_fc1_dw": [p, ll, p, p, p, ll, p, ll, i, i, i, p],
     "spv_to_bf16": [p, ll, p, ll, i, i, p],
     "spv_to_f16": [p, ll, p, ll, i, i, p],
     "spv_to_bf16_split": [p, ll, p, p, ll, i, i, p],

@@ -25,10 +25,47 @@ __global__ void library_kernel(const void* __restrict__ X, long ldx, const int* 
     if (threadIdx.x == 0) lib[b] = logf(red[0] + red[1] + red[2] + red[3]);
 }
 
+// uint16 counts: 16-byte loads (8 genes) when the row is 16-byte aligned, log1p of counts < 256 from a shared-memory table filled
+// with the same log1pf (bit-identical to computing it in place), 256 threads per cell
+__global__ void __launch_bounds__(256) library_u16_kernel(const unsigned short* __restrict__ X, long ldx, const int* __restrict__ rows, int B,
+                                                          int G, float* __restrict__ lib) {
+    __shared__ float lut[256];
+    __shared__ float red[8];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    lut[threadIdx.x] = threadIdx.x == 0 ? 0.0f : log1pf((float)threadIdx.x);
+    const unsigned short* row = X + (rows ? (long)rows[b] : (long)b) * ldx;
+    __syncthreads();
+    const int nvec = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) ? G / 8 : 0;
+    float s = 0.0f;
+    for (int v = threadIdx.x; v < nvec; v += 256) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(row) + v);
+        const unsigned int wd[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned int c0 = wd[j] & 0xffffu, c1 = wd[j] >> 16;
+            s += c0 < 256u ? lut[c0] : log1pf((float)c0);
+            s += c1 < 256u ? lut[c1] : log1pf((float)c1);
+        }
+    }
+    for (int g = nvec * 8 + threadIdx.x; g < G; g += 256) {
+        const unsigned int c = row[g];
+        s += c < 256u ? lut[c] : log1pf((float)c);
+    }
+    s = warp_sum(s);
+    if (lane == 0) red[w] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i];
+        lib[b] = logf(t);
+    }
+}
+
 extern "C" int spv_library_size(int src, const void* X, long long ldx, const int* rows, int B, int G, float* lib, void* stream) {
     if (!X || !lib || B <= 0 || G <= 0) return SPV_ERR_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (src == SPV_SRC_U16_LOG1P) library_kernel<SPV_SRC_U16_LOG1P><<<B, 128, 0, st>>>(X, ldx, rows, B, G, lib);
+    if (src == SPV_SRC_U16_LOG1P) library_u16_kernel<<<B, 256, 0, st>>>(reinterpret_cast<const unsigned short*>(X), ldx, rows, B, G, lib);
     else if (src == SPV_SRC_F32_LOG1P) library_kernel<SPV_SRC_F32_LOG1P><<<B, 128, 0, st>>>(X, ldx, rows, B, G, lib);
     else return SPV_ERR_ARG;
     SPV_CHECK_LAUNCH();

@@ -239,8 +239,8 @@ class _GroupWS:
         if bf16:
             h = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
             hd = lambda *s: torch.zeros(*s, dtype=dec_dtype, device=dev)  # decoder operands: fp16 on the fused path
-            self.Tb, self.amixb = h(B, self.Gpe), hd(B, self.KMp)
-            self.Tb_lo = h(B, self.Gpe)  # bf16 residual of log1p(counts): the fc1 contractions run on split operands
+            self.amixb = hd(B, self.KMp)
+            self.Tb = self.Tb_lo = None  # log1p(counts) as a bf16 pair: only the unfused first layer needs it (need_tb)
             self.zzb16 = hd(B, r8(KZb)) if nb else None  # 16-bit copy of zzb (operand of the Q = dy^T zz GEMM)
             # fp16 operands of the branch-logit MMAs (spv_dec_fold writes them): centred latents and folded weights
             self.zcb = torch.zeros(B, 64, dtype=torch.float16, device=dev)
@@ -275,6 +275,15 @@ class _GroupWS:
             self.dstats, self.dr = f(B, NST), f(B, NST)
             self.g_own, self.g_contrib, self.dexpert = f(B, 2 * S), f(B, 2 * S), f(B, 2 * S)
             self.dh2, self.dh1 = f(B, 2 * H), f(B, 2 * H)
+
+
+def _need_tb(self, dev):
+    if self.Tb is None:
+        self.Tb = torch.zeros(self.B, self.Gpe, dtype=torch.bfloat16, device=dev)
+        self.Tb_lo = torch.zeros(self.B, self.Gpe, dtype=torch.bfloat16, device=dev)
+
+
+_GroupWS.need_tb = _need_tb
 
 
 class StepEngine:
@@ -349,6 +358,14 @@ class StepEngine:
         self.stage_in_adam = False
         self._staged_version = -1
         self.adam_ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # Encoder first layer with the count transform fused into the GEMM's operand path (spv_enc_fc1_fwd / _dw: producer warps
+        # gather the uint16 counts, look log1p up as a split-bf16 pair and write the A operand into tensor memory resp. the B
+        # operand into swizzled shared memory).  Correct and tested (tests/test_gpu_kernels.py), but OPT-IN (SPV_FUSED_FC1=1):
+        # measured at the C5 shape (tools/bench_fc1.py, profiles/r2_fc1_fusion.md) the fused forward takes 125 us and the fused
+        # weight gradient 183 us per group against 60 (staging pass, HBM bound) + 71 resp. 88 us for the TMA-fed split GEMMs:
+        # one scattered 16-byte access per lane makes every warp load 32 L1 wavefronts, and table look-ups, operand stores and
+        # the tensor core's operand reads share the shared-memory pipe.
+        self.fused_fc1 = __import__("os").environ.get("SPV_FUSED_FC1", "0") == "1"
         self.nb_events = None  # bench hook: iterator of (start, end) CUDA events bracketing the NB-loglik sweep
         self.nb_bwd_events = None  # ... and its backward sweep
 
@@ -540,8 +557,24 @@ class StepEngine:
                 if decode or self.stage_in_adam:
                     with self._branch(g, "wm"):
                         self._to_dec(L.ptr(self.P(g, "Wm")), KMIX, L.ptr(w.Wmb), w.KMp, G, KMIX)
-            if self.bf16:  # encoder input and library size from one pass over the gathered rows
+            fused1 = self.bf16 and self.fused_fc1 and src == L.SRC_U16_LOG1P
+            if fused1:
+                # first layer straight from the raw counts: the producer warps of the GEMM gather the rows, look log1p up as a
+                # split-bf16 pair and write the tensor-core operand tiles (spv_enc_fc1_fwd); the library size on the side
+                with self._branch(g, "lib"):
+                    L.check(lib.spv_library_size(src, xptr, ldx, L.ptr(bt.rows), B, G, L.ptr(w.lib), self._stream()),
+                            "spv_library_size")
+                if nb:  # covariate term + bias as a pre-activation addend
+                    L.check(lib.spv_one_hot(L.ptr(bt.batch), L.ptr(w.oh), nb, B, nb, st), "spv_one_hot")
+                    self._gemm(L.ptr(w.oh), self.P(g, "W1").data_ptr() + 4 * G, L.ptr(w.h1), B, 2 * H, nb, lda=nb, ldb=Gc, ldc=2 * H,
+                               tb=1, bias=L.ptr(self.P(g, "b1")))
+                self._join(g, "w1")
+                L.check(lib.spv_enc_fc1_fwd(xptr, ldx, L.ptr(bt.rows), L.ptr(w.W1b), L.ptr(w.W1b_lo), w.Gpe, L.ptr(w.h1), 2 * H, B,
+                                            2 * H, G, None if nb else L.ptr(self.P(g, "b1")), 1, 1 if nb else 0, w.tc_splits_fc1,
+                                            L.ptr(w.ws), st), "spv_enc_fc1_fwd")
+            elif self.bf16:  # encoder input and library size from one pass over the gathered rows
                 # (with batch covariates: their one-hot columns behind the genes, so that fc1 stays one GEMM over K = G + nb)
+                w.need_tb(self.device)
                 L.check(lib.spv_counts_to_bf16(src, xptr, ldx, L.ptr(bt.rows), L.ptr(w.Tb), L.ptr(w.Tb_lo), w.Gpe, B, G,
                                                L.ptr(w.lib), L.ptr(bt.batch) if nb else None, nb, st), "spv_counts_to_bf16")
                 self._join(g, "w1")
@@ -973,8 +1006,15 @@ class StepEngine:
                 if not fuse1 or self.enc_mid:
                     L.check(lib.spv_to_bf16_split(L.ptr(w.dh1), 2 * H, L.ptr(w.dh1b), L.ptr(w.dh1b_lo), 2 * H, B, 2 * H, st),
                             "spv_to_bf16_split")
-                self._tc_gemm_split(L.ptr(w.dh1b), L.ptr(w.dh1b_lo), L.ptr(w.Tb), L.ptr(w.Tb_lo), L.ptr(self.Gd(g, "W1")), 2 * H,
-                                    G + d.nb, B, lda=2 * H, ldb=w.Gpe, ldc=G + d.nb, a_mn=1, b_mn=1)
+                if self.fused_fc1 and src == L.SRC_U16_LOG1P:  # counts transformed in the GEMM's producer warps (as the forward)
+                    L.check(lib.spv_enc_fc1_dw(xptr, ldx, L.ptr(bt.rows), L.ptr(w.dh1b), L.ptr(w.dh1b_lo), 2 * H,
+                                               L.ptr(self.Gd(g, "W1")), G + d.nb, B, 2 * H, G, st), "spv_enc_fc1_dw")
+                    if d.nb:  # covariate columns of the first layer's weight: dh1^T one_hot
+                        self._gemm(L.ptr(w.dh1), L.ptr(w.oh), self.Gd(g, "W1").data_ptr() + 4 * G, 2 * H, d.nb, B, lda=2 * H,
+                                   ldb=d.nb, ldc=G + d.nb, ta=1)
+                else:
+                    self._tc_gemm_split(L.ptr(w.dh1b), L.ptr(w.dh1b_lo), L.ptr(w.Tb), L.ptr(w.Tb_lo), L.ptr(self.Gd(g, "W1")), 2 * H,
+                                        G + d.nb, B, lda=2 * H, ldb=w.Gpe, ldc=G + d.nb, a_mn=1, b_mn=1)
             else:
                 self._gemm(L.ptr(w.dh1), xptr, L.ptr(self.Gd(g, "W1")), 2 * H, G, B, lda=2 * H, ldb=ldx, ldc=G + d.nb, ta=1, srcB=src,
                            rowsB=bt.rows)
