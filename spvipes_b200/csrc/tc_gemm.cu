@@ -587,9 +587,6 @@ extern "C" int spv_counts_to_bf16(int src, const void* X, long long ldx, const i
 // (2 x 2 bytes per element written, read again by both GEMMs) is gone.  After the k-loop the producer warps turn into the
 // epilogue (TMEM -> registers -> global).
 // =======================================================================================================================
-#ifndef FC1_EXP
-#define FC1_EXP 0
-#endif
 namespace fc1 {
 
 constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
@@ -730,9 +727,6 @@ __global__ void __launch_bounds__(THREADS, 1) fc1_kernel(const __grid_constant__
         // lookup in the gradient kernel): the raw counts of the next PF k-blocks are kept in flight in registers.
         constexpr int PF = 4;
         uint4 buf[PF][4];
-#if FC1_EXP == 9
-        float dbg[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#endif
         auto issue = [&](int i, uint4 (&dst)[4]) {
             const int kb = kb_begin + i;
             const int cell = DW ? kb * BK + r : m0 + r;
@@ -768,24 +762,15 @@ __global__ void __launch_bounds__(THREADS, 1) fc1_kernel(const __grid_constant__
         };
 #pragma unroll
         for (int u = 0; u < PF; ++u)
-            if (u < num_kb) issue(u, buf[u]);  // (FC1_EXP 4 / 5: timing experiments without the refills)
+            if (u < num_kb) issue(u, buf[u]);
         for (int i0 = 0; i0 < num_kb; i0 += PF) {
 #pragma unroll
             for (int u = 0; u < PF; ++u) {
                 const int i = i0 + u;
                 if (i < num_kb) {
                     const int s = i % STAGES;
-#if FC1_EXP == 9
-                    long long c0_ = clock64();
-#endif
                     tc::mbar_wait(&empty[s], ((i / STAGES) & 1) ^ 1);
-#if FC1_EXP == 9
-                    long long c1_ = clock64();
-#endif
                     uint8_t* row_hi = prod_row + s * STAGE_BYTES;
-#if FC1_EXP == 4
-                    if (false)
-#endif
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const unsigned int w[4] = {buf[u][j].x, buf[u][j].y, buf[u][j].z, buf[u][j].w};
@@ -816,32 +801,13 @@ __global__ void __launch_bounds__(THREADS, 1) fc1_kernel(const __grid_constant__
                         *reinterpret_cast<uint4*>(row_hi + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                         *reinterpret_cast<uint4*>(row_hi + TILE + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
-#if FC1_EXP == 9
-                    long long c2_ = clock64();
-#endif
                     tc::fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
-#if FC1_EXP == 9
-                    long long c3_ = clock64();
-#endif
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&full_p[s]);
-#if FC1_EXP == 9
-                    long long c4_ = clock64();
-                    dbg[0] += (float)(c1_ - c0_); dbg[1] += (float)(c2_ - c1_); dbg[2] += (float)(c3_ - c2_); dbg[3] += (float)(c4_ - c3_);
-#endif
-#if FC1_EXP != 4 && FC1_EXP != 5
                     if (i + PF < num_kb) issue(i + PF, buf[u]);
-#endif
-#if FC1_EXP == 9
-                    dbg[4] += (float)(clock64() - c4_);
-#endif
                 }
             }
         }
-#if FC1_EXP == 9
-        if (t == 37 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && p.ws)
-            for (int k = 0; k < 5; ++k) p.ws[(size_t)8 * p.M * p.N - 8 + k] = dbg[k] / (float)max(num_kb, 1);
-#endif
         // ---- epilogue: warp (w & 3) owns TMEM lanes 32 (w & 3) .., the two warps of a quarter split the 128 columns
         if (num_kb > 0) {
             tc::mbar_wait(tmem_full, 0);

@@ -229,10 +229,12 @@ def test_model_api_with_batch_covariate_and_step_warmup():
         assert model.module.engine.d.nb == 2
         assert model.module.state_dict()["encoder_0_private.fc1.weight"].shape == (64, G[0] + 2)
         gil = [list(ix) for ix in adata.uns["groups_obs_indices"]]
-        model.train(gil, max_epochs=8, batch_size=128, train_size=0.9, n_steps_kl_warmup=10)
+        model.train(gil, max_epochs=8, batch_size=128, train_size=0.9, n_epochs_kl_warmup=None)  # constant KL weight 1
         h = model.history["train_loss_epoch"]
         assert np.isfinite(h).all() and h[-1] < h[0], h
-        assert float(model.module.engine.kl_weight) == 1.0  # 10 warm-up steps are over
+        model.train(gil, max_epochs=3, batch_size=128, train_size=0.9, n_steps_kl_warmup=10)
+        assert float(model.module.engine.kl_weight) == 1.0  # the 10 warm-up steps are over (the weight rose from 0 step by step)
+        assert np.isfinite(model.history["train_loss_epoch"]).all()
         lat = model.get_latent_representation(gil, batch_size=200)
         assert lat["shared"][1].shape == (n[1], 12) and np.isfinite(lat["private"][0]).all()
         assert model.get_loadings()[(0, "private")].shape == (G[0], 6)

@@ -27,5 +27,5 @@ for name, nrows in (("compact [B, G]", B), ("scattered over 100k rows", 100000),
         for _ in range(10):
             fn()
         e1.record(); torch.cuda.synchronize()
-        print(f"{name:28s} {label} {e0.elapsed_time(e1) / 10 * 1e3:8.1f} us", "  producer cycles per k-block [wait empty, convert+store, fence, arrive, refill]:", [round(float(v)) for v in ws[-8:-3]] if label == "fwd" else "")
+        print(f"{name:28s} {label} {e0.elapsed_time(e1) / 10 * 1e3:8.1f} us")
     del X
