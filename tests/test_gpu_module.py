@@ -232,8 +232,11 @@ def test_model_api_with_batch_covariate_and_step_warmup():
         model.train(gil, max_epochs=8, batch_size=128, train_size=0.9, n_epochs_kl_warmup=None)  # constant KL weight 1
         h = model.history["train_loss_epoch"]
         assert np.isfinite(h).all() and h[-1] < h[0], h
-        model.train(gil, max_epochs=3, batch_size=128, train_size=0.9, n_steps_kl_warmup=10)
-        assert float(model.module.engine.kl_weight) == 1.0  # the 10 warm-up steps are over (the weight rose from 0 step by step)
+        model.train(gil, max_epochs=2, batch_size=128, train_size=0.9, n_steps_kl_warmup=10)
+        # 3 steps per epoch (450 / 378 training rows, drop_last, the smaller group cycled): step k runs at weight k / 10
+        assert abs(float(model.module.engine.kl_weight) - 0.5) < 1e-6
+        model.train(gil, max_epochs=5, batch_size=128, train_size=0.9, n_steps_kl_warmup=10)
+        assert float(model.module.engine.kl_weight) == 1.0  # the 10 warm-up steps are over
         assert np.isfinite(model.history["train_loss_epoch"]).all()
         lat = model.get_latent_representation(gil, batch_size=200)
         assert lat["shared"][1].shape == (n[1], 12) and np.isfinite(lat["private"][0]).all()
