@@ -203,8 +203,9 @@ int spv_loss(const float* rec0, const float* rec1, const float* klp0, const floa
 int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int G, int P, int S, int training, float eps, float momentum,
                  void* wz_bf16, long long ld_wz, int Gp, int HD, void* wz_f16, void* zc_f16, void* stream);
 /* fused decoder + NB-mixture likelihood sweeps.  ptrs (SPV_DEC_NPTR): X, rows, amix, wfold, wm, bm, genec, lib, part_stats,
- * rowc, pi, part_nb, dyp, dys, dpi, colpart, rec.   nn/networks.py:314-325; module/spVIPESmodule.py:759, 817-824 */
-#define SPV_DEC_NPTR 17
+ * rowc, pi, part_nb, dyp, dys, dpi, colpart, rec, tgf, tgb (the last two: spv_dec_theta_tables, tensor-core sweeps only).
+ * nn/networks.py:314-325; module/spVIPESmodule.py:759, 817-824 */
+#define SPV_DEC_NPTR 19
 /* phases: bit 0 = gene-axis softmax normaliser sweep, bit 1 = mixture GEMM + NB log-likelihood sweep (3 = both),
  * bit 2 = the mixture logits are already in `pi` (written by spv_tc_gemm), skip the in-kernel fp32 GEMM */
 /* zzb (optional, [B, P + S] with row pitch ld_zzb): the inputs of the two factor regressors when they are not the latent columns
@@ -227,8 +228,13 @@ int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const voi
 /* tensor-core version of phase 1 of spv_dec_nb_fwd: softmax normalisers rowc[b, 0:2] = lib[b] - logsumexp_g(y_p), (y_s)
  * from the fp16 branch operands (spv_dec_fold); part_stats: scratch of 2 * ceil(G/64) * B * 4 floats.
  * nn/networks.py:318-320, module/spVIPESmodule.py:751-757 */
-int spv_dec_stats_tc(const void* zc_f16, const void* wz_f16, int Gp, const float* genec, const float* lib, float* part_stats,
+int spv_dec_stats_tc(void* zc_f16, const void* wz_f16, int Gp, const float* genec, const float* lib, float* part_stats,
                      float* rowc, int B, int G, int P, int S, void* stream);
+/* count tables of the tensor-core likelihood sweeps (csrc/decoder_common.cuh NB_TAB = 16 entries per gene, float2 each):
+ * tgf[g][c] = (log1p(c), lgamma(log1p(c) + theta_g) - lgamma(theta_g) - lgamma(log1p(c) + 1)), tgb[g][c] = (log1p(c),
+ * digamma(log1p(c) + theta_g) - digamma(theta_g)), theta = exp(px_r) (module/spVIPESmodule.py:758).  They depend on the
+ * parameter only; either pointer may be NULL.  16-byte aligned. */
+int spv_dec_theta_tables(const float* px_r, int G, void* tgf, void* tgb, void* stream);
 /* floats spv_dec_nb_fwd_tc needs in part_nb (ptrs[11]) for a [B, G] problem */
 long long spv_dec_nb_part_floats(int B, int G);
 /* rec[b] (ptrs[16] of the forward) and the softmax-backward row sums rowc[:, 2:4] from the row partials part_nb that

@@ -14,7 +14,7 @@ SRC_F32, SRC_U16_LOG1P, SRC_F32_LOG1P = 0, 1, 2
 POE_LABEL, POE_PAIRED, POE_CLUSTER = 0, 1, 2
 PARTNER_PAD, PARTNER_ABSENT = -1, -2
 POE_MODES = {"label": POE_LABEL, "paired": POE_PAIRED, "cluster": POE_CLUSTER}
-GENEC_ROWS = 19
+GENEC_ROWS = 21  # decoder_common.cuh GC_N
 
 p, i, ll, f, u64, u32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong, C.c_uint
 
@@ -65,6 +65,7 @@ _SIGS = {
     "spv_dec_gene_bwd_parts": [i],
     "spv_dec_nb_part_floats": [i, i],
     "spv_dec_stats_tc": [p, p, i, p, p, p, p, i, i, i, i, p],
+    "spv_dec_theta_tables": [p, i, p, p, p],
     "spv_to_bf16_block": [p, ll, p, ll, i, i, i, p],
     "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, p, p],
     "spv_adam_tick": [p, p],

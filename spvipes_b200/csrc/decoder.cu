@@ -8,6 +8,7 @@
 // form from mean(z) and Cov(z) (spv_dec_fold), the gene-axis softmax normaliser by a first tile sweep
 // (pass STATS), the likelihood and the row sums the backward needs by a second sweep (pass NB).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "gemm_simt.cuh"
 #include "../../include/spvipes_b200.h"
 
@@ -241,8 +242,19 @@ __global__ void __launch_bounds__(GT_THREADS) dec_tile_kernel(DecP p) {
 }
 
 // combine the per-gene-tile softmax partials: Rp = lib - logsumexp_g(y_p), Rs likewise
+// R columns of the tensor-core branch operand (decoder_common.cuh ZK_RP / ZK_RS): the row normalisers in base-2 units as
+// split-fp16 pairs, so that the likelihood kernels' accumulators are complete logits
+__device__ __forceinline__ void store_row_normalisers(__half* zc, int b, float rp, float rs) {
+    if (!zc) return;
+    const float vp = rp * 1.4426950408889634f, vs = rs * 1.4426950408889634f;
+    const __half ph = to_half_sat(vp), sh = to_half_sat(vs);
+    __half2* dst = reinterpret_cast<__half2*>(zc + (long)b * 64 + ZK_RP);
+    dst[0] = __halves2half2(ph, to_half_sat(vp - __half2float(ph)));
+    dst[1] = __halves2half2(sh, to_half_sat(vs - __half2float(sh)));
+}
+
 __global__ void rowstat_kernel(const float* __restrict__ part, int nTG, int B, const float* __restrict__ lib,
-                               float* __restrict__ rowc) {
+                               float* __restrict__ rowc, __half* __restrict__ zc) {
     // one warp per row, lanes over the gene tiles; the row's partials are read once (16-byte loads, all in flight) and the
     // library size is fetched up front: one memory round trip instead of three dependent ones
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -279,8 +291,10 @@ __global__ void rowstat_kernel(const float* __restrict__ part, int nTG, int B, c
     Sp = warp_sum(Sp);
     Ss = warp_sum(Ss);
     if (lane == 0) {
-        rowc[(long)b * 4 + 0] = l - (Mp + logf(Sp));
-        rowc[(long)b * 4 + 1] = l - (Ms + logf(Ss));
+        const float rp = l - (Mp + logf(Sp)), rs = l - (Ms + logf(Ss));
+        rowc[(long)b * 4 + 0] = rp;
+        rowc[(long)b * 4 + 1] = rs;
+        store_row_normalisers(zc, b, rp, rs);
     }
 }
 
@@ -288,7 +302,7 @@ __global__ void rowstat_kernel(const float* __restrict__ part, int nTG, int B, c
 // one contiguous 512-byte run of the [tile][row] layout, the 8 warps split the tiles and merge their running (max, sum) pairs
 // through shared memory in warp order (deterministic).  The warp-per-row form above reads 16 useful bytes per 32-byte sector.
 __global__ void __launch_bounds__(256) rowstat_wide_kernel(const float* __restrict__ part, int nTG, int B, const float* __restrict__ lib,
-                                                           float* __restrict__ rowc) {
+                                                           float* __restrict__ rowc, __half* __restrict__ zc) {
     __shared__ float4 red[8][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.x * 32 + lane;
@@ -324,15 +338,18 @@ __global__ void __launch_bounds__(256) rowstat_wide_kernel(const float* __restri
             a.x = np; a.z = ns;
         }
         const float l = __ldg(lib + b);
-        rowc[(long)b * 4 + 0] = l - (a.x + logf(a.y));
-        rowc[(long)b * 4 + 1] = l - (a.z + logf(a.w));
+        const float rp = l - (a.x + logf(a.y)), rs = l - (a.z + logf(a.w));
+        rowc[(long)b * 4 + 0] = rp;
+        rowc[(long)b * 4 + 1] = rs;
+        store_row_normalisers(zc, b, rp, rs);
     }
 }
 
 // launch helper shared with the tensor-core statistics kernel (nb_tc.cu)
-int spv_internal_rowstat(const float* part, int nparts, int B, const float* lib, float* rowc, cudaStream_t st) {
-    if (nparts > 128) rowstat_wide_kernel<<<(B + 31) / 32, 256, 0, st>>>(part, nparts, B, lib, rowc);
-    else rowstat_kernel<<<(B + 7) / 8, 256, 0, st>>>(part, nparts, B, lib, rowc);
+int spv_internal_rowstat(const float* part, int nparts, int B, const float* lib, float* rowc, void* zc_f16, cudaStream_t st) {
+    __half* zc = reinterpret_cast<__half*>(zc_f16);
+    if (nparts > 128) rowstat_wide_kernel<<<(B + 31) / 32, 256, 0, st>>>(part, nparts, B, lib, rowc, zc);
+    else rowstat_kernel<<<(B + 7) / 8, 256, 0, st>>>(part, nparts, B, lib, rowc, zc);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }
@@ -386,7 +403,7 @@ extern "C" int spv_dec_nb_fwd(int src, const void* const* ptrs, long long ldx, l
         if (src == SPV_SRC_U16_LOG1P) dec_tile_kernel<PASS_STATS, SPV_SRC_U16_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
         else dec_tile_kernel<PASS_STATS, SPV_SRC_F32_LOG1P><<<grid, GT_THREADS, 0, st>>>(p);
         SPV_CHECK_LAUNCH();
-        rowstat_kernel<<<(B + 7) / 8, 256, 0, st>>>(p.part_stats, nTG, B, p.lib, p.rowc);
+        rowstat_kernel<<<(B + 7) / 8, 256, 0, st>>>(p.part_stats, nTG, B, p.lib, p.rowc, nullptr);
         SPV_CHECK_LAUNCH();
     }
     if (phases & 2) {  // mixture GEMM + NB log-likelihood

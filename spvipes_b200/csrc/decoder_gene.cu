@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
     float* sWs = sWp + FOLD_GENES_PER_CTA * p.P;        // [32][S]
     float* svec = sWs + FOLD_GENES_PER_CTA * p.S;       // [9][32]
     float* sT = svec + 9 * FOLD_GENES_PER_CTA;          // [32][KZ]   T = W C (block diagonal)
-    float* sA = sT + FOLD_GENES_PER_CTA * KZ;           // [2][32]    folded scale a = gamma invstd
+    float* sA = sT + FOLD_GENES_PER_CTA * KZ;           // [2][32]    folded scale a = gamma invstd; [2][32] centred shift (base 2)
     {
         StageArr<5> c;
         StageArr<1> m;
@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
             const float invstd = 1.0f / sqrtf(var + p.eps);
             const float a = gamma * invstd;
             sA[br * 32 + gl] = a;
+            sA[64 + br * 32 + gl] = (p.training ? beta : beta - mean * a) * 1.4426950408889634f;
             p.genec[(br == 0 ? GC_CP : GC_CS) * G + g] = beta - mean * a;
             p.genec[(br == 0 ? GC_CPL : GC_CSL) * G + g] = (beta - mean * a) * 1.4426950408889634f;
             p.genec[(br == 0 ? GC_CPLC : GC_CSLC) * G + g] = (p.training ? beta : beta - mean * a) * 1.4426950408889634f;
@@ -262,6 +263,8 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
             p.genec[GC_THE * G + g] = th + NB_EPS;
             p.genec[GC_K0 * G + g] = fmaf(th, lte, 0.91893853f - lgt);
             p.genec[GC_K1 * G + g] = lte + th / (th + NB_EPS) - dgt;
+            p.genec[GC_KC * G + g] = th * lte;
+            p.genec[GC_K1C * G + g] = lte + th / (th + NB_EPS);
         }
     }
     __syncthreads();
@@ -277,15 +280,72 @@ __global__ void __launch_bounds__(256) fold_kernel(FoldP p) {
             if (p.stack_f16) reinterpret_cast<__half*>(p.wfold_bf16)[at] = to_half_sat(wf);
             else p.wfold_bf16[at] = __float2bfloat16(wf);
         }
-        if (p.wz_f16) p.wz_f16[((long)(pr ? 0 : 1) * p.Gp + g) * 64 + k] = to_half_sat(wf);
+        // branch operand of the likelihood kernels: base-2 units (decoder_common.cuh, ZK_*)
+        if (p.wz_f16) p.wz_f16[((long)(pr ? 0 : 1) * p.Gp + g) * 64 + k] = to_half_sat(wf * 1.4426950408889634f);
     }
-    if (p.zc_f16) {  // centred latents: the CTAs share the rows
-        for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < (long)p.B * KZ; i += (long)gridDim.x * 256) {
-            const int b = (int)(i / KZ), k = (int)(i - (long)b * KZ);
-            const float m = p.training ? smean[k] : 0.0f;
-            p.zc_f16[(long)b * 64 + k] = to_half_sat(__ldg(p.zz + (long)b * p.ld_zz + k) - m);
+    if (p.wz_f16) {  // the additive columns of the branch k-block: (shift hi, shift lo) against ones, ones against (R hi, R lo)
+        for (int i = threadIdx.x; i < 2 * ng * 6; i += 256) {
+            const int br = i / (ng * 6), r = i - br * ng * 6, gl = r / 6, c = r - gl * 6;
+            const float sh = sA[64 + br * 32 + gl];
+            const __half hi = to_half_sat(sh);
+            __half v;
+            if (c == 0) v = hi;
+            else if (c == 1) v = to_half_sat(sh - __half2float(hi));
+            else v = __float2half_rn(((c < 4) == (br == 0)) ? 1.0f : 0.0f);
+            p.wz_f16[((long)br * p.Gp + g0 + gl) * 64 + ZK_ONE + c] = v;
         }
     }
+    if (p.zc_f16) {  // centred latents: the CTAs share the rows; ones in the shift columns, zeros elsewhere (the R columns are
+                     // filled by the row-statistics kernel after the normaliser sweep, which must see them as zero)
+        for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < (long)p.B * 64; i += (long)gridDim.x * 256) {
+            const int b = (int)(i >> 6), k = (int)(i & 63);
+            float v = 0.0f;
+            if (k < KZ) v = __ldg(p.zz + (long)b * p.ld_zz + k) - (p.training ? smean[k] : 0.0f);
+            else if (k == ZK_ONE || k == ZK_ONE + 1) v = 1.0f;
+            p.zc_f16[i] = to_half_sat(v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Count tables of the tensor-core likelihood kernels (decoder_common.cuh, NB_TAB): they depend on the inverse dispersion only,
+// i.e. on a parameter, not on the minibatch, so they are computed beside the encoders, off the critical path.  Evaluated in
+// double: lgamma(t + theta) - lgamma(theta) cancels badly in fp32 once theta is large.
+// ---------------------------------------------------------------------------------------
+__device__ double digamma_d(double x) {
+    double r = 0.0;
+    while (x < 8.0) {
+        r -= 1.0 / x;
+        x += 1.0;
+    }
+    const double f = 1.0 / (x * x);
+    return r + log(x) - 0.5 / x - f * (1.0 / 12.0 - f * (1.0 / 120.0 - f * (1.0 / 252.0 - f * (1.0 / 240.0 - f * (1.0 / 132.0)))));
+}
+
+__global__ void __launch_bounds__(256) theta_tables_kernel(const float* __restrict__ px_r, int G, float2* __restrict__ tgf,
+                                                           float2* __restrict__ tgb) {
+    const int i = blockIdx.x * 256 + threadIdx.x;  // entry (gene, count): 16 consecutive threads share a gene
+    const int g = i / NB_TAB, c = i - g * NB_TAB;
+    if (g >= G) return;
+    const float thf = expf(__ldg(px_r + g));  // reference module/spVIPESmodule.py:758 (the same fp32 value as GC_THETA)
+    float2 f = make_float2(0.0f, 0.0f), b = make_float2(0.0f, 0.0f);
+    if (c > 0) {
+        const double th = (double)thf;
+        const float tf = log1pf((float)c);  // the fp32 value the reference's log1p produces
+        const double t = (double)tf;
+        f = make_float2(tf, (float)(lgamma(t + th) - lgamma(th) - lgamma(t + 1.0)));
+        b = make_float2(tf, (float)(digamma_d(t + th) - digamma_d(th)));
+    }
+    if (tgf) tgf[i] = f;
+    if (tgb) tgb[i] = b;
+}
+
+extern "C" int spv_dec_theta_tables(const float* px_r, int G, void* tgf, void* tgb, void* stream) {
+    if (!px_r || G <= 0 || (!tgf && !tgb)) return SPV_ERR_ARG;
+    theta_tables_kernel<<<(G * NB_TAB + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        px_r, G, reinterpret_cast<float2*>(tgf), reinterpret_cast<float2*>(tgb));
+    SPV_CHECK_LAUNCH();
+    return SPV_OK;
 }
 
 // ptrs: Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, (unused), wfold, genec, zmean, zcov
@@ -312,12 +372,12 @@ extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int
     p.zmean = (const float*)ptrs[16]; p.zcov = (const float*)ptrs[17];
     p.wfold_bf16 = reinterpret_cast<__nv_bfloat16*>(wz_bf16);
     p.ld_wz = ld_wz; p.Gp = Gp; p.HD = HD;
-    if ((wz_f16 != nullptr) != (zc_f16 != nullptr) || (wz_f16 && KZ > 64)) return SPV_ERR_ARG;
+    if ((wz_f16 != nullptr) != (zc_f16 != nullptr) || (wz_f16 && KZ > ZK_MAX_LATENT)) return SPV_ERR_ARG;
     p.wz_f16 = reinterpret_cast<__half*>(wz_f16); p.zc_f16 = reinterpret_cast<__half*>(zc_f16);
     p.zz = zz; p.ld_zz = ld_zz;
     p.stack_f16 = wz_f16 != nullptr;  // fp16 branch operands requested: the whole decoder runs on fp16 operands
     p.G = G; p.P = P; p.S = S; p.B = B; p.training = training; p.eps = eps; p.momentum = momentum;
-    size_t sm2 = (size_t)(KZ + KZ * KZ + FOLD_GENES_PER_CTA * (2 * KZ + 11)) * sizeof(float);
+    size_t sm2 = (size_t)(KZ + KZ * KZ + FOLD_GENES_PER_CTA * (2 * KZ + 13)) * sizeof(float);
     if (sm2 > 48 * 1024) cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
     fold_kernel<<<(G + FOLD_GENES_PER_CTA - 1) / FOLD_GENES_PER_CTA, 256, sm2, st>>>(p);
     SPV_CHECK_LAUNCH();

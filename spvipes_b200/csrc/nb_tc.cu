@@ -38,20 +38,19 @@ constexpr int GATHER_ROWS = 64 / BN;          // rows of the count tile one warp
 constexpr int EPI_WARPS = 8, EPI_THREADS = 32 * EPI_WARPS;
 constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TMEM_COLS = BN == 64 ? 256 : 128;           // single allocation of the statistics kernel
 constexpr int ACC_COLS = BN, Z_COLS = 2 * BN;             // the likelihood kernels allocate in two steps (powers of two >= 32)
 static_assert(ACC_COLS == 32 || ACC_COLS == 64, "tensor-memory allocations are powers of two");
-constexpr int CNT_PITCH_W = BN / 2 + 1;  // uint16 count tile: 33 32-bit words per row, conflict-free for thread = row reads
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 8 * BN * 4 + 256 * 8 + 256;
+constexpr int CNT_PITCH_W = BN / 2 + 2;  // count-code tile: 34 32-bit words per row - thread = row reads 64 bits (four codes) conflict-free
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + BN * 16 + BN * NB_TAB * 8 + 256;
 
 static_assert(BM * CNT_PITCH_W * 4 <= STAGES * STAGE_BYTES, "count tile must fit in the operand stages");
+static_assert(3 * (SMEM_BYTES + 1024) <= 228 * 1024, "three CTAs per SM");
 
 struct NbTcParams {
     const void* X; long ldx; const int* rows;
     const float* bm;                   // [G]
     const float* genec;                // [GC_N, G]
-    const float* rowc;                 // [B, 4]: Rp, Rs
-    float* pi;                         // [B, G] or null
+    const float2* tgf;                 // [G, NB_TAB] forward count table (spv_dec_theta_tables)
     float* part_nb;                    // [nTG, B, 3]
     int B, G, K;
     int Gp;                            // row offset of the shared block inside the folded-weight operand
@@ -66,6 +65,18 @@ __device__ __forceinline__ int cnt_row(int e, int lane, int i) {
 // CTAs of this kernel currently resident per SM (a scheduling hint only, see the allocation below; balanced by every CTA)
 __device__ int g_resident_fwd[256];
 
+// one element off the fast path (a count outside the table, a logit below the fast logarithm's range, an edge tile): out of line
+template <int SRC>
+__device__ __noinline__ NbOut nb_fwd_general(uint32_t code, float xp, float xs, float acc_pi, float4 gc, const uint8_t* tg_row,
+                                             const void* X, long xidx, const float* lgt) {
+    float2 tcn;
+    if (code == NB_CODE_SLOW) tcn = nb_count_terms_fwd_slow(nb_load_raw<SRC>(X, xidx), gc.x, __ldg(lgt));
+    else tcn = *reinterpret_cast<const float2*>(tg_row + code);
+    const float pi = acc_pi + gc.w;
+    if (tcn.x != 0.0f && fminf(xp, xs) < NB_X_RARE) return nb_forward_v5<true>(tcn.x, tcn.y, xp, xs, pi, gc.x, gc.y, gc.z);
+    return nb_forward_v5<false>(tcn.x, tcn.y, xp, xs, pi, gc.x, gc.y, gc.z);
+}
+
 template <int SRC>
 __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                const __grid_constant__ CUtensorMap mapB,
@@ -75,10 +86,10 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
     const uint32_t raw = tc::smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
     uint8_t* tiles = smem_raw + pad;
-    uint8_t* z_tiles = tiles + STAGES * STAGE_BYTES;                    // folded private | shared weights, [BN][64] bf16 each
-    float* s_gc = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);      // [BN][8] gene-major: cpl, csl, bm, theta | theta + eps, K0, -, -  (two 128-bit loads per element)
-    float2* s_lut = reinterpret_cast<float2*>(s_gc + 8 * BN);         // [256]: (log1p(c), lgamma(log1p(c) + 1)) per raw count
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_lut + 256);
+    uint8_t* z_tiles = tiles + STAGES * STAGE_BYTES;                    // folded private | shared weights, [BN][64] fp16 each
+    float4* s_gc = reinterpret_cast<float4*>(z_tiles + 2 * B_BYTES);    // [BN]: theta, theta + eps, theta log(theta + eps), bm
+    uint8_t* s_tg = reinterpret_cast<uint8_t*>(s_gc + BN);              // [BN][NB_TAB] float2: (log1p(c), count term) per gene
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_tg + BN * NB_TAB * 8);
     uint64_t* empty = full + STAGES;
     uint64_t* z_full = empty + STAGES;
     uint64_t* tmem_full = z_full + 1;
@@ -133,7 +144,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
                 tc::tma_load_2d(&mapA, &full[s], a_dst, i * BK, m0);
                 tc::tma_load_2d(&mapB, &full[s], a_dst + A_BYTES, i * BK, n0);
             }
-            {  // the branch k-block: centred latents (fp16), A tile only, next slot of the ring
+            {  // the branch k-block: centred latents + additive columns (fp16), A tile only, next slot of the ring
                 const int s = num_kb % STAGES;
                 const uint32_t ph = (num_kb / STAGES) & 1;
                 tc::mbar_wait(&empty[s], ph ^ 1);
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
             const uint32_t a_base = tc::smem_u32(tiles + s_z * STAGE_BYTES);
             const uint32_t zp_base = tc::smem_u32(z_tiles), zs_base = zp_base + B_BYTES;
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) {  // the two softmax-branch logits: centred latents against the folded weights (fp16)
+            for (int kk = 0; kk < BK / 16; ++kk) {  // the two branch logits, complete: latents, shift and row normaliser (fp16)
                 tc::umma_bf16(tmem_z, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zp_base + kk * 32, 16, 1024), idesc_z,
                               kk > 0 ? 1u : 0u);
                 tc::umma_bf16(tmem_z + BN, tc::smem_desc(a_base + kk * 32, 16, 1024), tc::smem_desc(zs_base + kk * 32, 16, 1024),
@@ -209,7 +220,7 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
         const int et = threadIdx.x - 64;  // 0..255
         const long G = p.G;
         // Every global load of the prologue is issued before anything waits on one: the row indices first (the count gather
-        // depends on them), then the per-gene and per-row constants; the count LUT is computed while they are in flight.
+        // depends on them), then the per-gene constants and the count table of the tile's genes.
         const int e = warp - 2;
         const int q = warp & 3;          // TMEM lane quarter this warp may access
         const int half = e >> 2;         // which 32 gene columns of the tile
@@ -219,52 +230,59 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
         const int mm = mok ? m : 0;
         constexpr int NGATHER = BM / EPI_WARPS / GATHER_ROWS;
         int ridx[NGATHER];
-        if (SRC == SPV_SRC_U16_LOG1P) {
 #pragma unroll
-            for (int i = 0; i < NGATHER; ++i) {
-                const int gm = m0 + cnt_row(e, lane, i);
-                ridx[i] = gm < p.B ? (p.rows ? __ldg(p.rows + gm) : gm) : -1;
-            }
+        for (int i = 0; i < NGATHER; ++i) {
+            const int gm = m0 + cnt_row(e, lane, i);
+            ridx[i] = gm < p.B ? (p.rows ? __ldg(p.rows + gm) : gm) : -1;
         }
         const int my_row = p.rows ? __ldg(p.rows + mm) : mm;
-        float Rpl = __ldg(p.rowc + (long)mm * 4 + 0), Rsl = __ldg(p.rowc + (long)mm * 4 + 1);
-        float gcv[6] = {0.0f, 0.0f, 0.0f, 1.0f, 1.0f, 0.0f};
+        float4 gcv = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
         static_assert(BN <= EPI_THREADS, "one thread per gene of the tile stages its constants");
         if (et < BN && n0 + et < p.G) {
             const int g = n0 + et;
-            gcv[0] = __ldg(p.genec + GC_CPLC * G + g);  // constants of nb_forward_v3 (shifts of the centred form)
-            gcv[1] = __ldg(p.genec + GC_CSLC * G + g);
-            gcv[2] = __ldg(p.bm + g);
-            gcv[3] = __ldg(p.genec + GC_THETA * G + g);
-            gcv[4] = __ldg(p.genec + GC_THE * G + g);
-            gcv[5] = __ldg(p.genec + GC_K0 * G + g);
+            gcv.x = __ldg(p.genec + GC_THETA * G + g);
+            gcv.y = __ldg(p.genec + GC_THE * G + g);
+            gcv.z = __ldg(p.genec + GC_KC * G + g);
+            gcv.w = __ldg(p.bm + g);
         }
-        if (SRC == SPV_SRC_U16_LOG1P) nb_fill_count_lut(s_lut, et);  // EPI_THREADS == 256; overlaps the TMA / MMA phase
-        // coalesced row gather of the tile's counts into registers (overlaps the MMA phase): warp e takes rows e, e + 8, ...;
-        // lane l takes genes 2l, 2l + 1
-        uint32_t cw[BM / EPI_WARPS];  // with GATHER_ROWS > 1 only the first NGATHER entries are used
-        if (SRC == SPV_SRC_U16_LOG1P) {
-            const unsigned short* X16 = reinterpret_cast<const unsigned short*>(p.X);
+        // the tile's slice of the count table: BN * NB_TAB * 8 bytes = 2 x 16 bytes per epilogue thread
+        static_assert(BN * NB_TAB * 8 == EPI_THREADS * 32, "two 16-byte table words per epilogue thread");
+        float4 tgv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int w16 = et + u * EPI_THREADS;          // 16-byte word of the slice: gene w16 / 8
+            const int g = n0 + (w16 >> 3);
+            tgv[u] = g < p.G ? __ldg(reinterpret_cast<const float4*>(p.tgf + (long)n0 * NB_TAB) + w16) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        // coalesced row gather of the tile's counts into registers as count codes (overlaps the MMA phase): warp e takes rows
+        // e, e + 8, ...; lane l takes genes 2l, 2l + 1
+        uint32_t cw[NGATHER];
+        {
             const int g = n0 + 2 * (lane % (BN / 2));
 #pragma unroll
-            for (int i = 0; i < NGATHER; ++i) {
-                cw[i] = 0u;
-                if (ridx[i] >= 0) {
-                    const unsigned short* src = X16 + (long)ridx[i] * p.ldx + g;
-                    if (g + 1 < p.G && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
-                        cw[i] = __ldg(reinterpret_cast<const uint32_t*>(src));
-                    } else {
-                        uint32_t c0 = g < p.G ? __ldg(src) : 0u, c1 = g + 1 < p.G ? __ldg(src + 1) : 0u;
-                        cw[i] = c0 | (c1 << 16);
+            for (int i = 0; i < NGATHER; ++i) cw[i] = 0u;
+            constexpr int BATCH = SRC == SPV_SRC_U16_LOG1P ? NGATHER : NGATHER / 2;  // every load of a batch in flight before any is used
+            if (nb_pair_vec_ok<SRC>(p.X, p.ldx, g, p.G)) {
+#pragma unroll
+                for (int i0 = 0; i0 < NGATHER; i0 += BATCH) {
+                    uint2 raw[BATCH];
+#pragma unroll
+                    for (int i = 0; i < BATCH; ++i) {
+                        raw[i] = make_uint2(0u, 0u);
+                        if (ridx[i0 + i] >= 0) raw[i] = nb_load_pair_vec<SRC>(p.X, (long)ridx[i0 + i] * p.ldx, g);
                     }
+#pragma unroll
+                    for (int i = 0; i < BATCH; ++i) cw[i0 + i] = nb_pair_codes<SRC>(raw[i]);
                 }
+            } else {  // odd pitch, unaligned base or the last gene of an odd-sized matrix: element loads
+#pragma unroll
+                for (int i = 0; i < NGATHER; ++i)
+                    if (ridx[i] >= 0) cw[i] = nb_pair_codes<SRC>(nb_load_pair<SRC>(p.X, (long)ridx[i] * p.ldx, g, p.G));
             }
         }
-        if (et < BN) {
-            *reinterpret_cast<float4*>(s_gc + et * 8) = make_float4(gcv[0], gcv[1], gcv[2], gcv[3]);
-            *reinterpret_cast<float4*>(s_gc + et * 8 + 4) = make_float4(gcv[4], gcv[5], 0.0f, 0.0f);
-        }
-        Rpl *= NB_LOG2E; Rsl *= NB_LOG2E;
+        if (et < BN) s_gc[et] = gcv;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) reinterpret_cast<float4*>(s_tg)[et + u * EPI_THREADS] = tgv[u];
         const long xrow = (long)my_row * p.ldx;
         stamp(2);  // count gather issued
         tc::mbar_wait(tmem_ready, 0);
@@ -273,15 +291,14 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
         tc::mbar_wait(tmem_full, 0);  // accumulators complete; the operand stages are free from here on
         tc::fence_after_sync();
         stamp(3);  // accumulators complete
-        if (SRC == SPV_SRC_U16_LOG1P) {
 #pragma unroll
-            for (int i = 0; i < BM / EPI_WARPS / GATHER_ROWS; ++i) s_cnt[cnt_row(e, lane, i) * CNT_PITCH_W + lane % (BN / 2)] = cw[i];
-        }
+        for (int i = 0; i < NGATHER; ++i) s_cnt[cnt_row(e, lane, i) * CNT_PITCH_W + lane % (BN / 2)] = cw[i];
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");  // constants + counts staged (epilogue warps only)
         stamp(4);  // counts staged
         float sll = 0.0f, sep = 0.0f, ses = 0.0f;
-        const bool vec_pi = p.pi && ((G & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.pi) & 15) == 0);
+        const bool full_tile = n0 + BN <= p.G && m0 + BM <= p.B;  // CTA-uniform
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16), lane_z = tmem_z + ((uint32_t)(q * 32) << 16);
+        const uint32_t* cnt_row_p = s_cnt + rloc * CNT_PITCH_W + half * (WCOLS / 2);
 #pragma unroll 1
         for (int j4 = 0; j4 < WCOLS; j4 += 4) {
             const int c0 = half * WCOLS + j4;
@@ -289,44 +306,37 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
             tc::tmem_ld4(lane_addr + (uint32_t)c0, rpi);
             tc::tmem_ld4(lane_z + (uint32_t)c0, rlp);
             tc::tmem_ld4(lane_z + (uint32_t)(BN + c0), rls);
+            const uint2 cc = *reinterpret_cast<const uint2*>(cnt_row_p + (j4 >> 1));  // four count codes
             tc::tmem_ld_wait();
-            if (!mok) continue;
-            float pv[4];
+            const uint32_t call = cc.x | cc.y;
+            // smallest branch logit of the four elements: log2(rho + eps) = log2(rho) needs rho >= 1e-6 wherever the count is positive
+            const float xm = fminf(fminf(fminf(__uint_as_float(rlp[0]), __uint_as_float(rls[0])), fminf(__uint_as_float(rlp[1]), __uint_as_float(rls[1]))),
+                                   fminf(fminf(__uint_as_float(rlp[2]), __uint_as_float(rls[2])), fminf(__uint_as_float(rlp[3]), __uint_as_float(rls[3]))));
+            const bool plain = full_tile && (call & 0x80008000u) == 0u && !(call != 0u && xm < NB_X_RARE);
+            if (plain) {  // every count tabulated, every column and row valid, the fast logarithm holds
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int gl = c0 + jj, g = n0 + gl;
-                pv[jj] = 0.0f;
-                if (g < p.G) {
-                    NbGene ge;
-                    const float4 ga = *reinterpret_cast<const float4*>(s_gc + gl * 8), gb = *reinterpret_cast<const float4*>(s_gc + gl * 8 + 4);
-                    ge.cpl = ga.x; ge.csl = ga.y; ge.bm = ga.z; ge.th = ga.w; ge.thE = gb.x; ge.K = gb.y;
-                    const float piv = __uint_as_float(rpi[jj]) + ge.bm;
-                    float2 tl;
-                    if (SRC == SPV_SRC_U16_LOG1P) {
-                        uint32_t w = s_cnt[rloc * CNT_PITCH_W + (gl >> 1)];
-                        const uint32_t c = (gl & 1) ? (w >> 16) : (w & 0xffffu);
-                        tl = c < 256u ? s_lut[c] : nb_count_terms_exact(c);
-                    } else {
-                        tl.x = load_src<SRC>(p.X, xrow + g);
-                        tl.y = lgamma_pos_fast(tl.x + 1.0f);
-                    }
-                    bool rare = false;
-                    NbOut o = nb_forward_v3<false>(tl.x, tl.y, __uint_as_float(rlp[jj]), __uint_as_float(rls[jj]), __uint_as_float(rpi[jj]),
-                                                   ge, Rpl, Rsl, rare);
-                    if (rare)
-                        o = nb_forward_v3<true>(tl.x, tl.y, __uint_as_float(rlp[jj]), __uint_as_float(rls[jj]), __uint_as_float(rpi[jj]), ge,
-                                                Rpl, Rsl, rare);
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int gl = c0 + jj;
+                    const uint32_t w = jj < 2 ? cc.x : cc.y;
+                    const uint32_t code = (jj & 1) ? (w >> 16) : (w & 0xffffu);
+                    const float2 tcn = *reinterpret_cast<const float2*>(s_tg + gl * (NB_TAB * 8) + code);
+                    const float4 gc = s_gc[gl];
+                    const NbOut o = nb_forward_v5<false>(tcn.x, tcn.y, __uint_as_float(rlp[jj]), __uint_as_float(rls[jj]),
+                                                         __uint_as_float(rpi[jj]) + gc.w, gc.x, gc.y, gc.z);
                     sll += o.ll; sep += o.ep; ses += o.es;
-                    pv[jj] = piv;
                 }
-            }
-            if (p.pi) {
-                const int g = n0 + c0;
-                float* dst = p.pi + (long)m * G + g;
-                if (vec_pi && g + 3 < p.G) *reinterpret_cast<float4*>(dst) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-                else
-                    for (int jj = 0; jj < 4; ++jj)
-                        if (g + jj < p.G) dst[jj] = pv[jj];
+            } else if (mok) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int gl = c0 + jj, g = n0 + gl;
+                    if (g < p.G) {
+                        const uint32_t w = jj < 2 ? cc.x : cc.y;
+                        const uint32_t code = (jj & 1) ? (w >> 16) : (w & 0xffffu);
+                        const NbOut o = nb_fwd_general<SRC>(code, __uint_as_float(rlp[jj]), __uint_as_float(rls[jj]), __uint_as_float(rpi[jj]),
+                                                            s_gc[gl], s_tg + gl * (NB_TAB * 8), p.X, xrow + g, p.genec + GC_LGT * G + g);
+                        sll += o.ll; sep += o.ep; ses += o.es;
+                    }
+                }
             }
         }
         if (mok) {
@@ -349,23 +359,22 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_fwd_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------
-// Softmax statistics of the two factor-regressor branches on the tensor cores: y = zz W'^T + c is one 64-wide k-block
-// (the latent columns of the bf16 operand) against the folded weights, so a 128 x 64 tile costs 8 MMAs; each epilogue thread
-// (= cell) reduces its 32 columns to (max, sum exp) per branch.  Replaces the fp32 SIMT pass (19.5 us per group at C2,
-// instruction bound); using the same bf16-rounded logits as the likelihood kernels also makes the normaliser consistent
-// with the rho they compute.  part_stats [2 * ceil(G/64), B, 4] = (max_p, sum_p, max_s, sum_s), natural units.
+// Softmax statistics of the two factor-regressor branches on the tensor cores: the base-2 logit y = zc . wz (latents against
+// the folded weights, the shift riding in the ones columns, the R columns still zero: decoder_common.cuh ZK_*) is one 64-wide
+// k-block, so a 128 x 64 tile costs 8 MMAs; each epilogue thread (= cell) reduces its 32 columns to (max, sum exp) per
+// branch.  Using the same fp16 operands as the likelihood kernels makes the normaliser consistent with the rho they compute.
+// part_stats [2 * ceil(G/64), B, 4] = (max_p, sum_p, max_s, sum_s), natural units.
 // ---------------------------------------------------------------------------------------
-constexpr int ST_SMEM = A_BYTES + 2 * B_BYTES + 1024 + 2 * BN * 4 + 64;
+constexpr int ST_SMEM = A_BYTES + 2 * B_BYTES + 1024 + 64;
 
 __global__ void __launch_bounds__(THREADS, 3) nb_tc_stats_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                 const __grid_constant__ CUtensorMap mapZ, const float* __restrict__ genec,
+                                                                 const __grid_constant__ CUtensorMap mapZ,
                                                                  float* __restrict__ part_stats, int B, int G, int Gp) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = tc::smem_u32(smem_raw);
     uint8_t* tiles = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
     uint8_t* z_tiles = tiles + A_BYTES;
-    float* s_c = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);  // [2][BN]: cp log2e, cs log2e
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_c + 2 * BN);
+    uint64_t* full = reinterpret_cast<uint64_t*>(z_tiles + 2 * B_BYTES);
     uint64_t* tmem_full = full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -405,15 +414,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_stats_kernel(const __grid_co
             tc::umma_commit(tmem_full);
         }
     } else {
-        const int et = threadIdx.x - 64;
-        const long Gl = G;
-        for (int i = et; i < 2 * BN; i += EPI_THREADS) {
-            const int k = i / BN, c = i - k * BN, g = n0 + c;
-            s_c[i] = g < G ? __ldg(genec + (k == 0 ? GC_CPLC : GC_CSLC) * Gl + g) : 0.0f;
-        }
         const int e = warp - 2, q = warp & 3, half = e >> 2;
         const int m = m0 + q * 32 + lane;
-        asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
         tc::mbar_wait(tmem_full, 0);
         tc::fence_after_sync();
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -429,8 +431,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_stats_kernel(const __grid_co
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const bool ok = n0 + c0 + jj < G;
-                yp[j4 + jj] = ok ? fmaf(__uint_as_float(rp4[jj]), NB_LOG2E, s_c[c0 + jj]) : -INFINITY;
-                ys[j4 + jj] = ok ? fmaf(__uint_as_float(rs4[jj]), NB_LOG2E, s_c[BN + c0 + jj]) : -INFINITY;
+                yp[j4 + jj] = ok ? __uint_as_float(rp4[jj]) : -INFINITY;
+                ys[j4 + jj] = ok ? __uint_as_float(rs4[jj]) : -INFINITY;
                 Mp = fmaxf(Mp, yp[j4 + jj]);
                 Ms = fmaxf(Ms, ys[j4 + jj]);
             }
@@ -521,21 +523,21 @@ static int set_smem_once(K kernel, int bytes, bool (&done)[64]) {
     return SPV_OK;
 }
 
-// ptrs: the SPV_DEC_NPTR list of spv_dec_nb_fwd (X, rows, amix [unused], wfold [unused], wm [unused], bm, genec, lib,
-// part_stats, rowc, pi, part_nb [>= 2 * ceil(G/64) * B * 3 floats], ..., rec).  rowc[:, 0:2] must hold the softmax
-// normalisers (spv_dec_stats_tc).  Operands: amix_bf16 [B, ld_amixb] = [hm | zz]; wstack_bf16 [>= G, ld_w]: rows [0, G) the
-// mixture weight (bf16); zc_f16 [B, 64] centred latents and wz_f16 [2 Gp, 64] folded branch weights (fp16, spv_dec_fold).
-// Gp = G rounded up to a multiple of 8.
+// ptrs: the SPV_DEC_NPTR list of spv_dec_nb_fwd (X, rows, -, -, -, bm, genec, -, -, -, -, part_nb [>= 2 * ceil(G/64) * B * 3
+// floats], ..., [17] = forward count table of spv_dec_theta_tables).  Operands (all fp16): amix_bf16 [B, ld_amixb] = [hm | zz];
+// wstack_bf16 [>= G, ld_w]: rows [0, G) the mixture weight; zc_f16 [B, 64] / wz_f16 [2 Gp, 64]: the branch k-block of
+// spv_dec_fold, completed by spv_dec_stats_tc (row normalisers).  Gp = G rounded up to a multiple of 8.
 extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
                                  const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16, int B,
                                  int G, int HD, int P, int S, int store_pi, int kmix, void* stream) {
     if (!ptrs || !amix_bf16 || !wstack_bf16 || !zc_f16 || !wz_f16 || Gp < G || B <= 0 || G <= 0 || HD < 0 || P <= 0 || S <= 0)
         return SPV_ERR_ARG;
-    if (P + S > BK) return SPV_ERR_ARG;  // the latent columns must fit the branch k-block
-    const int need[] = {0, 5, 6, 9, 11, 16};
+    if (P + S > ZK_MAX_LATENT) return SPV_ERR_ARG;  // the latent columns must fit the branch k-block below the additive columns
+    const int need[] = {0, 5, 6, 11, 17};
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
-    if (store_pi && !ptrs[10]) return SPV_ERR_ARG;
+    if (store_pi) return SPV_ERR_ARG;  // the sweep keeps the mixture logits in tensor memory (the backward recomputes them)
+    if (reinterpret_cast<uintptr_t>(ptrs[17]) & 15) return SPV_ERR_ARG;
     const int K = kmix > 0 ? kmix : HD + P + S;  // width of the mixing net's input ([hm | zz | covariates])
     CUtensorMap ma, mb, mz, mzc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -550,7 +552,7 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
     NbTcParams p;
     p.Gp = Gp;
     p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
-    p.rowc = (const float*)ptrs[9]; p.pi = store_pi ? (float*)ptrs[10] : nullptr; p.part_nb = (float*)ptrs[11];
+    p.tgf = (const float2*)ptrs[17]; p.part_nb = (float*)ptrs[11];
     p.B = B; p.G = G; p.K = K;
     p.trace = spv_debug_get_trace();
 #ifdef NB_TRACE
@@ -571,16 +573,17 @@ extern "C" int spv_dec_nb_fwd_tc(int src, const void* const* ptrs, long long ldx
     return SPV_OK;
 }
 
-int spv_internal_rowstat(const float* part, int nparts, int B, const float* lib, float* rowc, cudaStream_t st);
+int spv_internal_rowstat(const float* part, int nparts, int B, const float* lib, float* rowc, void* zc_f16, cudaStream_t st);
 
 // Softmax normalisers of the two branches on the tensor cores: rowc[b, 0:2] = lib[b] - logsumexp_g(y_p / y_s)   (phase 1 of
 // spv_dec_nb_fwd for the tensor-core path), from the fp16 operands spv_dec_fold wrote: zc_f16 [B, 64] centred latents, wz_f16
-// [2 Gp, 64] folded weights.  part_stats needs 2 * ceil(G/64) * B * 4 floats.
-extern "C" int spv_dec_stats_tc(const void* zc_f16, const void* wz_f16, int Gp, const float* genec, const float* lib,
+// [2 Gp, 64] folded weights.  Also writes the normalisers into the R columns of zc_f16 (decoder_common.cuh ZK_RP / ZK_RS), which
+// completes the branch operand for the likelihood sweeps.  part_stats needs 2 * ceil(G/64) * B * 4 floats.
+extern "C" int spv_dec_stats_tc(void* zc_f16, const void* wz_f16, int Gp, const float* genec, const float* lib,
                                 float* part_stats, float* rowc, int B, int G, int P, int S, void* stream) {
     if (!zc_f16 || !wz_f16 || !genec || !lib || !part_stats || !rowc || Gp < G || B <= 0 || G <= 0 || P <= 0 || S <= 0)
         return SPV_ERR_ARG;
-    if (P + S > BK) return SPV_ERR_ARG;
+    if (P + S > ZK_MAX_LATENT) return SPV_ERR_ARG;
     CUtensorMap ma, mz;
     int rc = spv_make_tensor_map_bf16(&ma, zc_f16, 64ull, (unsigned long long)B, 64ull, 64, BM);
     if (rc != SPV_OK) return rc;
@@ -590,9 +593,9 @@ extern "C" int spv_dec_stats_tc(const void* zc_f16, const void* wz_f16, int Gp, 
     static bool done[64] = {};
     if (set_smem_once(nb_tc_stats_kernel, ST_SMEM, done) != SPV_OK) return SPV_ERR_LAUNCH;
     dim3 grid((G + BN - 1) / BN, (B + BM - 1) / BM);
-    nb_tc_stats_kernel<<<grid, THREADS, ST_SMEM, st>>>(ma, mz, genec, part_stats, B, G, Gp);
+    nb_tc_stats_kernel<<<grid, THREADS, ST_SMEM, st>>>(ma, mz, part_stats, B, G, Gp);
     SPV_CHECK_LAUNCH();
-    return spv_internal_rowstat(part_stats, 2 * (int)grid.x, B, lib, rowc, st);
+    return spv_internal_rowstat(part_stats, 2 * (int)grid.x, B, lib, rowc, zc_f16, st);
 }
 
 // floats spv_dec_nb_fwd_tc needs in part_nb

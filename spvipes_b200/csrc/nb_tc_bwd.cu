@@ -22,7 +22,7 @@ constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTE
 constexpr int ACC_COLS = BN, Z_COLS = 2 * BN;  // tensor memory is allocated in two steps (powers of two >= 32)
 static_assert(ACC_COLS == 32 || ACC_COLS == 64, "tensor-memory allocations are powers of two");
 constexpr int CNT_PITCH_W = BN / 2 + 1;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + 8 * BN * 4 + 4 * 4 * BN * 4 + 256 * 4 + 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + BN * 16 + 4 * 4 * BN * 4 + BN * NB_TAB * 8 + 256;
 
 static_assert(BM * CNT_PITCH_W * 4 <= STAGES * STAGE_BYTES, "count tile must fit in the operand stages");
 
@@ -32,6 +32,7 @@ struct NbTcBwdParams {
     const float* genec;
     const float* rowc;   // [B, 4]: Rp, Rs, Dp, Ds
     const float* lib;    // [B]
+    const float2* tgb;   // [G, NB_TAB] backward count table (spv_dec_theta_tables)
     __nv_bfloat16* dpi; long ld_dpi;   // D3 [B, 3 * Gp] = [dpi | dyp | dys]
     float* colpart;                    // [nTB, 4, G]
     int B, G, K, Gp;
@@ -56,10 +57,10 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
     uint8_t* tiles = smem_raw + pad;
     uint8_t* z_tiles = tiles + STAGES * STAGE_BYTES;
-    float* s_gc = reinterpret_cast<float*>(z_tiles + 2 * B_BYTES);  // [BN][8] gene-major: cpl, csl, bm, theta | theta + eps, K1, -, -
-    float* s_col = s_gc + 8 * BN;                                    // [4 quantities][4 quarters][BN]
-    float* s_lut = s_col + 16 * BN;                                  // [256]: log1p(c) per raw count
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_lut + 256);
+    float4* s_gc = reinterpret_cast<float4*>(z_tiles + 2 * B_BYTES);  // [BN]: theta, theta + eps, K1c, bm
+    float* s_col = reinterpret_cast<float*>(s_gc + BN);                 // [4 quantities][4 quarters][BN]
+    uint8_t* s_tg = reinterpret_cast<uint8_t*>(s_col + 16 * BN);        // [BN][NB_TAB] float2: (log1p(c), digamma term) per gene
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_tg + BN * NB_TAB * 8);
     uint64_t* empty = full + STAGES;
     uint64_t* z_full = empty + STAGES;
     uint64_t* tmem_full = z_full + 1;
@@ -187,53 +188,58 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
         const int mm = mok ? m : 0;
         constexpr int NGATHER = BM / EPI_WARPS / GATHER_ROWS;
         int ridx[NGATHER];
-        if (SRC == SPV_SRC_U16_LOG1P) {
 #pragma unroll
-            for (int i = 0; i < NGATHER; ++i) {
-                const int gm = m0 + cnt_row(e, lane, i);
-                ridx[i] = gm < p.B ? (p.rows ? __ldg(p.rows + gm) : gm) : -1;
-            }
+        for (int i = 0; i < NGATHER; ++i) {
+            const int gm = m0 + cnt_row(e, lane, i);
+            ridx[i] = gm < p.B ? (p.rows ? __ldg(p.rows + gm) : gm) : -1;
         }
         const int my_row = p.rows ? __ldg(p.rows + mm) : mm;
         const float4 rc = __ldg(reinterpret_cast<const float4*>(p.rowc) + mm);  // Rp, Rs, Dp, Ds
         const float libm = __ldg(p.lib + mm);
-        float gcv[6] = {0.0f, 0.0f, 0.0f, 1.0f, 1.0f, 0.0f};
+        float4 gcv = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
         static_assert(BN <= EPI_THREADS, "one thread per gene of the tile stages its constants");
         if (et < BN && n0 + et < p.G) {
             const int g = n0 + et;
-            gcv[0] = __ldg(p.genec + GC_CPLC * G + g);  // constants of nb_backward_v3 (shifts of the centred form)
-            gcv[1] = __ldg(p.genec + GC_CSLC * G + g);
-            gcv[2] = __ldg(p.bm + g);
-            gcv[3] = __ldg(p.genec + GC_THETA * G + g);
-            gcv[4] = __ldg(p.genec + GC_THE * G + g);
-            gcv[5] = __ldg(p.genec + GC_K1 * G + g);
+            gcv.x = __ldg(p.genec + GC_THETA * G + g);
+            gcv.y = __ldg(p.genec + GC_THE * G + g);
+            gcv.z = __ldg(p.genec + GC_K1C * G + g);
+            gcv.w = __ldg(p.bm + g);
         }
-        if (SRC == SPV_SRC_U16_LOG1P) s_lut[et] = et == 0 ? 0.0f : log1pf((float)et);  // EPI_THREADS == 256
-        // coalesced row gather of the tile's counts into registers (overlaps the MMA phase): warp e takes rows e, e + 8, ...;
-        // lane l takes genes 2l, 2l + 1
-        uint32_t cw[BM / EPI_WARPS];  // with GATHER_ROWS > 1 only the first NGATHER entries are used
-        if (SRC == SPV_SRC_U16_LOG1P) {
-            const unsigned short* X16 = reinterpret_cast<const unsigned short*>(p.X);
+        float4 tgv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int w16 = et + u * EPI_THREADS;
+            const int g = n0 + (w16 >> 3);
+            tgv[u] = g < p.G ? __ldg(reinterpret_cast<const float4*>(p.tgb + (long)n0 * NB_TAB) + w16) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        // coalesced row gather of the tile's counts into registers as count codes (overlaps the MMA phase)
+        uint32_t cw[NGATHER];
+        {
             const int g = n0 + 2 * (lane % (BN / 2));
 #pragma unroll
-            for (int i = 0; i < NGATHER; ++i) {
-                cw[i] = 0u;
-                if (ridx[i] >= 0) {
-                    const unsigned short* src = X16 + (long)ridx[i] * p.ldx + g;
-                    if (g + 1 < p.G && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
-                        cw[i] = __ldg(reinterpret_cast<const uint32_t*>(src));
-                    } else {
-                        uint32_t c0 = g < p.G ? __ldg(src) : 0u, c1 = g + 1 < p.G ? __ldg(src + 1) : 0u;
-                        cw[i] = c0 | (c1 << 16);
+            for (int i = 0; i < NGATHER; ++i) cw[i] = 0u;
+            constexpr int BATCH = SRC == SPV_SRC_U16_LOG1P ? NGATHER : NGATHER / 2;  // every load of a batch in flight before any is used
+            if (nb_pair_vec_ok<SRC>(p.X, p.ldx, g, p.G)) {
+#pragma unroll
+                for (int i0 = 0; i0 < NGATHER; i0 += BATCH) {
+                    uint2 raw[BATCH];
+#pragma unroll
+                    for (int i = 0; i < BATCH; ++i) {
+                        raw[i] = make_uint2(0u, 0u);
+                        if (ridx[i0 + i] >= 0) raw[i] = nb_load_pair_vec<SRC>(p.X, (long)ridx[i0 + i] * p.ldx, g);
                     }
+#pragma unroll
+                    for (int i = 0; i < BATCH; ++i) cw[i0 + i] = nb_pair_codes<SRC>(raw[i]);
                 }
+            } else {  // odd pitch, unaligned base or the last gene of an odd-sized matrix: element loads
+#pragma unroll
+                for (int i = 0; i < NGATHER; ++i)
+                    if (ridx[i] >= 0) cw[i] = nb_pair_codes<SRC>(nb_load_pair<SRC>(p.X, (long)ridx[i] * p.ldx, g, p.G));
             }
         }
-        if (et < BN) {
-            *reinterpret_cast<float4*>(s_gc + et * 8) = make_float4(gcv[0], gcv[1], gcv[2], gcv[3]);
-            *reinterpret_cast<float4*>(s_gc + et * 8 + 4) = make_float4(gcv[4], gcv[5], 0.0f, 0.0f);
-        }
-        const float Rpl = NB_LOG2E * rc.x, Rsl = NB_LOG2E * rc.y;
+        if (et < BN) s_gc[et] = gcv;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) reinterpret_cast<float4*>(s_tg)[et + u * EPI_THREADS] = tgv[u];
         const float inv_elib = fast_exp(-libm);
         const float DpI = inv_elib * rc.z, DsI = inv_elib * rc.w;
         const long xrow = (long)my_row * p.ldx;
@@ -242,10 +248,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
         tmem_z = *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1);
         tc::mbar_wait(tmem_full, 0);  // accumulators complete; the operand stages are free from here on
         tc::fence_after_sync();
-        if (SRC == SPV_SRC_U16_LOG1P) {
 #pragma unroll
-            for (int i = 0; i < BM / EPI_WARPS / GATHER_ROWS; ++i) s_cnt[cnt_row(e, lane, i) * CNT_PITCH_W + lane % (BN / 2)] = cw[i];
-        }
+        for (int i = 0; i < NGATHER; ++i) s_cnt[cnt_row(e, lane, i) * CNT_PITCH_W + lane % (BN / 2)] = cw[i];
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
         const bool vec_b = ((p.ld_dpi & 3) == 0) && ((p.Gp & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dpi) & 7) == 0);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16), lane_z = tmem_z + ((uint32_t)(q * 32) << 16);
@@ -263,23 +267,16 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
                 const int gl = c0 + jj, g = n0 + gl;
                 vyp[jj] = vys[jj] = vpi[jj] = vth[jj] = 0.0f;
                 if (mok && g < p.G) {
-                    NbGene ge;
-                    const float4 ga = *reinterpret_cast<const float4*>(s_gc + gl * 8), gb = *reinterpret_cast<const float4*>(s_gc + gl * 8 + 4);
-                    ge.cpl = ga.x; ge.csl = ga.y; ge.bm = ga.z; ge.th = ga.w; ge.thE = gb.x; ge.K = gb.y;
-                    float t;
-                    if (SRC == SPV_SRC_U16_LOG1P) {
-                        uint32_t w = s_cnt[rloc * CNT_PITCH_W + (gl >> 1)];
-                        uint32_t c = (gl & 1) ? (w >> 16) : (w & 0xffffu);
-                        t = c < 256u ? s_lut[c] : fast_log(1.0f + (float)c);
-                    } else {
-                        t = load_src<SRC>(p.X, xrow + g);
-                    }
-                    bool rare = false;
-                    NbGrad o = nb_backward_v3<false>(t, __uint_as_float(rlp[jj]), __uint_as_float(rls[jj]), __uint_as_float(rpi[jj]), ge,
-                                                     Rpl, Rsl, DpI, DsI, p.scale, rare);
-                    if (rare)
-                        o = nb_backward_v3<true>(t, __uint_as_float(rlp[jj]), __uint_as_float(rls[jj]), __uint_as_float(rpi[jj]), ge, Rpl,
-                                                 Rsl, DpI, DsI, p.scale, rare);
+                    const float4 gc = s_gc[gl];
+                    const uint32_t w = s_cnt[rloc * CNT_PITCH_W + (gl >> 1)];
+                    const uint32_t code = (gl & 1) ? (w >> 16) : (w & 0xffffu);
+                    float2 tcn;
+                    if (code == NB_CODE_SLOW) tcn = nb_count_terms_bwd_slow(nb_load_raw<SRC>(p.X, xrow + g), gc.x, __ldg(p.genec + GC_DGT * G + g));
+                    else tcn = *reinterpret_cast<const float2*>(s_tg + gl * (NB_TAB * 8) + code);
+                    const float xp = __uint_as_float(rlp[jj]), xs = __uint_as_float(rls[jj]), pi = __uint_as_float(rpi[jj]) + gc.w;
+                    NbGrad o = nb_backward_v5<false>(tcn.x, tcn.y, xp, xs, pi, gc.x, gc.y, gc.z, DpI, DsI);
+                    if (tcn.x != 0.0f && fminf(xp, xs) < NB_X_RARE) o = nb_backward_v5<true>(tcn.x, tcn.y, xp, xs, pi, gc.x, gc.y, gc.z, DpI, DsI);
+                    o.dyp *= p.scale; o.dys *= p.scale; o.dpi *= p.scale; o.dth *= p.scale;
                     vyp[jj] = o.dyp; vys[jj] = o.dys; vpi[jj] = o.dpi; vth[jj] = o.dth;
                 }
             }
@@ -375,8 +372,8 @@ extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx
                                  void* d3_bf16, int B, int G, int HD, int P, int S, float scale, float* colsum, int kmix, void* stream) {
     if (!ptrs || !amix_bf16 || !wstack_bf16 || !zc_f16 || !wz_f16 || !d3_bf16 || !colsum || Gp < G || B <= 0 || G <= 0 || P <= 0 || S <= 0)
         return SPV_ERR_ARG;
-    if (P + S > BK) return SPV_ERR_ARG;
-    const int need[] = {0, 5, 6, 7, 9, 15};
+    if (P + S > ZK_MAX_LATENT) return SPV_ERR_ARG;
+    const int need[] = {0, 5, 6, 7, 9, 15, 18};
     for (int i : need)
         if (!ptrs[i]) return SPV_ERR_ARG;
     const int K = kmix > 0 ? kmix : HD + P + S;  // width of the mixing net's input ([hm | zz | covariates])
@@ -392,7 +389,7 @@ extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx
     if (rc != SPV_OK) return rc;
     NbTcBwdParams p;
     p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
-    p.lib = (const float*)ptrs[7]; p.rowc = (const float*)ptrs[9];
+    p.lib = (const float*)ptrs[7]; p.rowc = (const float*)ptrs[9]; p.tgb = (const float2*)ptrs[18];
     p.colpart = (float*)ptrs[15]; p.dpi = reinterpret_cast<__nv_bfloat16*>(d3_bf16); p.ld_dpi = 3L * Gp;
     // The sweep works in natural units (sign only): D3 holds d / |scale| in fp16 - |d pi| <= 1, |d y| bounded by log1p(count)
     // + theta, all well inside fp16's normal range whatever the minibatch size - and the consumers apply |scale|: the

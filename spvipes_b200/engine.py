@@ -245,6 +245,8 @@ class _GroupWS:
             # fp16 operands of the branch-logit MMAs (spv_dec_fold writes them): centred latents and folded weights
             self.zcb = torch.zeros(B, 64, dtype=torch.float16, device=dev)
             self.wzf = torch.zeros(2 * self.Gp, 64, dtype=torch.float16, device=dev)
+            # count tables of the likelihood sweeps (spv_dec_theta_tables): [G, 16] float2 each, forward / backward
+            self.tgf, self.tgb = f(G, 16, 2), (f(G, 16, 2) if with_grad else None)
             # bf16 weight operands are per engine (shared by every workspace): W1b [2H, Gp] and the stacked operand
             # Wstack [3 Gp, KMp]: rows [0, G) mixture weight, [Gp, Gp+G) / [2Gp, 2Gp+G) the folded private / shared
             # factor-regressor weights of the current minibatch in the latent columns (zero elsewhere)
@@ -657,6 +659,10 @@ class StepEngine:
                                 w.zcov])
             wz = w.Wstack.data_ptr() + 2 * w.Gp * w.KMp if self.fused_nb else None
             if self.fused_nb:
+                # count tables of the likelihood sweeps: a function of px_r only, on the second auxiliary stream
+                with self._branch(g, "tg", lane=1):
+                    L.check(lib.spv_dec_theta_tables(L.ptr(self.P(g, "px_r")), G, L.ptr(w.tgf), L.ptr(w.tgb) if with_grad else None,
+                                                     self._stream()), "spv_dec_theta_tables")
                 # hidden layer of the mixing net (needs only zz) on the auxiliary stream, beside latent stats / fold / normalisers;
                 # the bf16 operand [hm | zz] of the mixture GEMM in one conversion pass after it
                 with self._branch(g, "hm"):
@@ -679,6 +685,7 @@ class StepEngine:
             evs = next(self.nb_events) if self.nb_events is not None else None
             if self.fused_nb:
                 self._join(g, "wm")
+                self._join(g, "tg")
             elif self.bf16:  # mixture logits on the tensor cores, consumed by the NB sweep
                 self._to_dec(L.ptr(w.amix), KMIX, L.ptr(w.amixb), w.KMp, B, KMIX)
                 self._join(g, "wm")
@@ -710,7 +717,7 @@ class StepEngine:
         wg = with_grad
         return L.ptr_array([xptr, rows, w.amix, w.wfold, self.P(g, "Wm"), self.P(g, "bm"), w.genec, w.lib, w.part_stats,
                             w.rowc, w.pi, w.part_nb, w.dyp if wg else None, w.dys if wg else None, w.dpi if wg else None,
-                            w.colpart if wg else None, w.rec])
+                            w.colpart if wg else None, w.rec, getattr(w, "tgf", None), getattr(w, "tgb", None)])
 
     def _pairing(self, batches, ws, Bs):
         lib, st, d = self.lib, self._stream(), self.d

@@ -18,7 +18,7 @@ from spvipes_b200.trainer import TrainLoop, init_params  # noqa: E402
 
 dev = torch.device("cuda", 0)
 WL = os.environ.get("WL", "C2")
-mode, n_cells, genes, H, B, n_labels = bench.WORKLOADS[WL]
+mode, n_cells, genes, H, B, n_labels = bench.WORKLOADS[WL][:6]
 n_cells = min(n_cells, 60000)
 lib = L.load()
 clib = ctypes.CDLL(lib._name)
