@@ -244,10 +244,13 @@ class Bench:
                               plan=self.plan, precision=args.precision)
         init_params(self.eng, 0)
         self.loop = TrainLoop(self.eng)
+        self.sync_kind = None
         if world > 1:
             from spvipes_b200.parallel import broadcast_params, make_grad_sync
             broadcast_params(self.eng, dist, src=0)
             self.loop.grad_sync = make_grad_sync(self.eng, dist)
+            gs = self.loop.grad_sync
+            self.sync_kind = f"{type(gs).__name__}: {gs.kind}" + (f" (fallback: {gs.fallback_reason})" if getattr(gs, "fallback_reason", None) else "")
         self.loop.set_epoch(1)
         self.gen = torch.Generator(device=dev).manual_seed(5 + rank)
         B = self.B
@@ -335,7 +338,14 @@ class Bench:
                 self.loop.step(self.static)
 
         n0 = self.lib.spv_launch_count()
+        prof = bool(os.environ.get("SPV_PROFILE_RANGE"))  # `ncu --profile-from-start off`: skip data generation and capture
+        if prof:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
         blocks = self.timed_blocks(K, W, step)
+        if prof:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         ms = float(np.median(blocks))
         if use_graph:
             launches, per_step = self.per_step_launches * K * len(blocks), self.per_step_launches
@@ -373,7 +383,7 @@ class Bench:
         elems = B * G
         # SFU (MUFU) pipe: 16 lanes per SM and clock = 4 per sub-partition; ex2 / lg2 / rcp per (cell, gene) element in nb_math.cuh
         mufu_peak = 148 * 16 * sm_mhz * 1e6
-        MUFU_F, MUFU_B = 16, 17
+        MUFU_F, MUFU_B = 8, 8  # nb_math.cuh v5: ex2 x4, lg2 x3 (x2 backward), one shared rcp (+ the rare exact variant)
         if self.args.precision == "bf16":
             kf = "nb_tc_fwd_kernel (tcgen05 decoder GEMMs + fused NB-mixture log-likelihood epilogue, forward)"
             kb = "nb_tc_bwd_kernel (tcgen05 recompute of the logits + likelihood gradients -> D3, column sums)"
@@ -384,7 +394,7 @@ class Bench:
                 "traffic": measured_traffic(self.workload, "nb_tc_fwd_kernel"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_f, "avg_launch_ms": f_ms,
                 "note": "algorithmic bytes by SURVEY 8(d); the kernel is bound by the SFU / issue pipes, not by HBM: see `other` for the "
-                        "MUFU roofline (16 ex2/lg2/rcp per element) and profiles/ for the ncu counters",
+                        "MUFU roofline (8 ex2/lg2/rcp per element) and profiles/ for the ncu counters",
                 "other": [
                     {"kernel": kf, "bound": "mufu", "achieved": MUFU_F * elems / (f_ms * 1e-3) / 1e12, "peak": mufu_peak / 1e12, "unit": "T SFU op/s",
                      "frac": MUFU_F * elems / (f_ms * 1e-3) / mufu_peak, "sfu_ops_per_element": MUFU_F, "elements_per_launch": elems},
@@ -550,6 +560,9 @@ def run_ours(args):
         clk.start()
     res = bench.measure_value(K, W)
     clocks = clk.stop() if rank == 0 else None
+    if hasattr(bench.loop.grad_sync, "check"):
+        bench.loop.grad_sync.check()  # a handshake that timed out would have produced a number without the exchange
+    sync_kind = bench.sync_kind
     loss = float(bench.eng.loss_out[0].item())
     roofline = bench.measure_roofline(K)
     e2e = e2e_u16 = e2e_tl = e2e_torch = None
@@ -563,7 +576,7 @@ def run_ours(args):
             "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": ("f32 (tcgen05 GEMMs on split-bf16 / fp16 operands with f32 accumulation in TMEM; f32 elementwise, Adam)"
                       if args.precision == "bf16" else "f32"),
-            "data": "synthetic", "config": workload_config(workload, world), "clocks": clocks, "e2e": e2e,
+            "data": "synthetic", "config": dict(workload_config(workload, world), grad_sync=sync_kind), "clocks": clocks, "e2e": e2e,
             "e2e_uint16_input": e2e_u16, "e2e_trainloop": e2e_tl, "e2e_torch_adam": e2e_torch, "gpu_launches": res["gpu_launches"],
             "launches_per_step": res["launches_per_step"], "timing": {"blocks": len(res["blocks_ms"]), "steps_per_block": K,
                                                                         "block_ms": res["blocks_ms"], "reported": "median block"},

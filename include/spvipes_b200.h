@@ -240,14 +240,15 @@ long long spv_dec_nb_part_floats(int B, int G);
 /* rec[b] (ptrs[16] of the forward) and the softmax-backward row sums rowc[:, 2:4] from the row partials part_nb that
  * spv_dec_nb_fwd_tc wrote for the same B, G, HD */
 int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, int HD, float* rowc, float* rec, void* stream);
-/* tensor-core backward sweep: recomputes the three logit tiles on tcgen05 and writes D3 = [dpi | dyp | dys] / |scale| (FP16
- * [B, 3 Gp], operand of the gradient GEMMs, which apply |scale| as spv_tc_gemm_ex's alpha) and colsum [4, G] (column sums
- * of dyp, dys, dpi, d loss / d theta, true scale);
+/* tensor-core backward sweep: recomputes the three logit tiles on tcgen05 and writes D3T = [dpi ; dyp ; dys] / |scale| (FP16,
+ * GENE-major [3 Gp, ld_d3], ld_d3 >= B a multiple of 8: a warp's 32 cells are contiguous, so the stores coalesce; operand of
+ * the gradient GEMMs, which apply |scale| as spv_tc_gemm_ex's alpha) and colsum [4, G] (column sums of dyp, dys, dpi,
+ * d loss / d theta, true scale);
  * ptrs[15] = colpart workspace [ceil(B/128), 4, G].  scale = - grad_scale / B.  rowc (ptrs[9], [B, 4] floats) must be
  * 16-byte aligned (SPV_ERR_ARG otherwise): a row is read as one float4. */
 int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
-                      const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16, void* d3_bf16,
-                      int B, int G, int HD, int P, int S, float scale, float* colsum, int kmix, void* stream);
+                      const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16, void* d3_f16,
+                      long long ld_d3, int B, int G, int HD, int P, int S, float scale, float* colsum, int kmix, void* stream);
 /* ptrs (18): Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm,
  * vpart [parts, P+S], mpart [parts, (P+S)^2] with parts = spv_dec_gene_bwd_parts(G)
  * (backward of nn/networks.py:314-320 through the folded BatchNorm) */
@@ -279,6 +280,23 @@ int spv_adam(float* p, const float* g, float* m, float* v, long long n, float lr
              float grad_scale, int* step, int* ticket, int nseg, const long long* seg_begin, const int* seg_rows,
              const int* seg_cols, void* const* seg_dst, void* const* seg_dst_lo, const int* seg_f16, const long long* seg_ld,
              int max_blocks, void* stream);
+
+/* Data-parallel gradient all-reduce as ONE kernel per parameter range over NVLink 5 / NVSwitch, capturable inside the step's
+ * CUDA graph (the reference is single-device).  In-place sum over ranks of floats
+ * [offset, offset + n) of a gradient buffer that lives at the same offset of a symmetric allocation on every rank.
+ * peer_bufs / peer_flags: HOST arrays of `world` device addresses (each rank's buffer / flag buffer as mapped into this
+ * process; entry `rank` is the local one).  mc_buf: this rank's multicast (NVLS) address of the buffer - the switch then
+ * reduces (multimem.ld_reduce) and replicates (multimem.st) - or NULL: peer loads summed in rank order + peer stores.
+ * Rank r reduces slice r of the range and writes the sums into every rank's buffer, so all ranks end with bitwise
+ * identical values.  CTA b of every rank handshakes with CTA b of every peer before (peers' gradients complete) and after
+ * (all writes landed, all reads done) through release / acquire flags carrying an epoch; `state` = 12 ints on this device,
+ * zeroed once (per channel: epoch, ticket; state[8] = 1 + rank of a peer that did not answer within 20 s, 0 = healthy: the
+ * kernel then gives up instead of hanging the GPU); the flag buffer holds spv_xgpu_flag_ints() ints, zeroed on every rank before the
+ * first launch anywhere.  channel 0..3: launches that may overlap in time use different channels.  Every rank must launch
+ * the same (offset, n, channel, blocks) sequence per channel.  offset, n multiples of 4; buffers 16-byte aligned. */
+int spv_xgpu_allreduce(void* const* peer_bufs, void* const* peer_flags, void* mc_buf, long long offset, long long n, int rank,
+                       int world, int channel, int* state, int blocks, void* stream);
+int spv_xgpu_flag_ints(void);
 
 #ifdef __cplusplus
 }

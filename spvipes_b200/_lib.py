@@ -60,7 +60,7 @@ _SIGS = {
     "spv_dec_nb_bwd": [i, p, ll, ll, i, i, i, i, i, f, p, p, ll, p, ll, i, p],
     "spv_dec_nb_fwd_tc": [i, p, ll, p, ll, p, ll, i, p, p, i, i, i, i, i, i, i, p],
     "spv_dec_nb_rowreduce": [p, i, i, i, p, p, p],
-    "spv_dec_nb_bwd_tc": [i, p, ll, p, ll, p, ll, i, p, p, p, i, i, i, i, i, f, p, i, p],
+    "spv_dec_nb_bwd_tc": [i, p, ll, p, ll, p, ll, i, p, p, p, ll, i, i, i, i, i, f, p, i, p],
     "spv_dec_gene_bwd": [p, ll, i, i, i, i, p],
     "spv_dec_gene_bwd_parts": [i],
     "spv_dec_nb_part_floats": [i, i],
@@ -70,6 +70,8 @@ _SIGS = {
     "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, p, p],
     "spv_adam_tick": [p, p],
     "spv_adam": [p, p, p, p, ll, f, f, f, f, f, f, p, p, i, p, p, p, p, p, p, p, i, p],
+    "spv_xgpu_allreduce": [p, p, p, ll, ll, i, i, i, p, i, p],
+    "spv_xgpu_flag_ints": [],
 }
 
 _lib = None

@@ -1,8 +1,8 @@
 // Backward sweep of the fused decoder + NB-mixture likelihood on the tensor-core path.
 // Same tiling and pipeline as nb_tc.cu: the three logit tiles (pi, lp, ls) are RECOMPUTED on tcgen05 from the bf16 operands
 // (nothing [B, G]-sized was saved by the forward); the epilogue turns them into
-//   dpi [B, G] bf16  (operand of the weight / input gradient GEMMs of the mixture layer),
-//   dyp, dys [B, G] f32 (gradients w.r.t. the two folded BatchNorm outputs = softmax logits),
+//   D3T [3 Gp, B] fp16, gene-major: dpi (operand of the weight / input gradient GEMMs of the mixture layer), dyp, dys
+//   (gradients w.r.t. the two folded BatchNorm outputs = softmax logits),
 //   colpart [nTB, 4, G]: per-128-row-tile column sums of dyp, dys, dpi and d loss / d theta.
 // Reference: autograd of nn/networks.py:314-325 + scvi log_mixture_nb (module/spVIPESmodule.py:823-824).
 #include <cuda_fp16.h>
@@ -33,7 +33,7 @@ struct NbTcBwdParams {
     const float* rowc;   // [B, 4]: Rp, Rs, Dp, Ds
     const float* lib;    // [B]
     const float2* tgb;   // [G, NB_TAB] backward count table (spv_dec_theta_tables)
-    __nv_bfloat16* dpi; long ld_dpi;   // D3 [B, 3 * Gp] = [dpi | dyp | dys]
+    __nv_bfloat16* dpi; long ld_dpi;   // D3T [3 * Gp, ld_dpi >= B] = [dpi ; dyp ; dys], gene-major (fp16 values)
     float* colpart;                    // [nTB, 4, G]
     int B, G, K, Gp;
     float scale;
@@ -251,7 +251,8 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
 #pragma unroll
         for (int i = 0; i < NGATHER; ++i) s_cnt[cnt_row(e, lane, i) * CNT_PITCH_W + lane % (BN / 2)] = cw[i];
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
-        const bool vec_b = ((p.ld_dpi & 3) == 0) && ((p.Gp & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dpi) & 7) == 0);
+        __half* const d3t = reinterpret_cast<__half*>(p.dpi) + (long)n0 * p.ld_dpi + m;  // this cell's column, first gene of the tile
+        const long blk_stride = (long)p.Gp * p.ld_dpi;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16), lane_z = tmem_z + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
         for (int j4 = 0; j4 < WCOLS; j4 += 4) {
@@ -278,25 +279,12 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
                     if (tcn.x != 0.0f && fminf(xp, xs) < NB_X_RARE) o = nb_backward_v5<true>(tcn.x, tcn.y, xp, xs, pi, gc.x, gc.y, gc.z, DpI, DsI);
                     o.dyp *= p.scale; o.dys *= p.scale; o.dpi *= p.scale; o.dth *= p.scale;
                     vyp[jj] = o.dyp; vys[jj] = o.dys; vpi[jj] = o.dpi; vth[jj] = o.dth;
-                }
-            }
-            if (mok) {
-                const int g = n0 + c0;
-                // D3[b, :] = [dpi (Gp) | dyp (Gp) | dys (Gp)] in bf16: one operand for the three gradient GEMMs
-                __nv_bfloat16* d3 = p.dpi + (long)m * p.ld_dpi + g;
-                const float* vals[3] = {vpi, vyp, vys};
-#pragma unroll
-                for (int blk = 0; blk < 3; ++blk) {
-                    __nv_bfloat16* dst = d3 + (long)blk * p.Gp;
-                    const float* v = vals[blk];
-                    __half* dsth = reinterpret_cast<__half*>(dst);
-                    if (vec_b && g + 3 < p.G) {
-                        __half2 lo = __floats2half2_rn(v[0], v[1]), hi = __floats2half2_rn(v[2], v[3]);
-                        *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-                    } else {
-                        for (int jj = 0; jj < 4; ++jj)
-                            if (g + jj < p.G) dsth[jj] = __float2half_rn(v[jj]);
-                    }
+                    // D3T[gene, cell] (fp16): the 32 lanes of the warp are 32 consecutive cells, so each of the three stores
+                    // of a gene writes 64 contiguous bytes (the cell-major layout cost 32 partial sectors per store)
+                    __half* d = d3t + (long)gl * p.ld_dpi;
+                    d[0] = __float2half_rn(o.dpi);
+                    d[blk_stride] = __float2half_rn(o.dyp);
+                    d[2 * blk_stride] = __float2half_rn(o.dys);
                 }
             }
             // column sums over this warp's 32 rows (lanes): transpose-reduce of the 16 values (4 quantities x 4 columns).  Each
@@ -364,13 +352,16 @@ __global__ void colpart_reduce_tc_kernel(const float* __restrict__ colpart, int 
 }  // namespace
 
 // ptrs: the SPV_DEC_NPTR list (X, rows, -, -, -, bm, genec, lib, -, rowc, -, -, -, -, -, colpart [ceil(B/128), 4, G], -).
-// d3_bf16 [B, 3 * Gp] receives [d loss / d pi | d loss / d y_private | d loss / d y_shared] / |scale| as FP16 (the A operand
-// of the gradient GEMMs, which multiply by |scale|: spv_tc_gemm_ex fmt 3).  Operands as spv_dec_nb_fwd_tc.  colsum [4, G] =
+// d3_f16 [3 * Gp, ld_d3] (GENE-major, ld_d3 >= B a multiple of 8) receives d loss / d pi (rows 0 .. G), d loss / d y_private
+// (rows Gp ..), d loss / d y_shared (rows 2 Gp ..), each / |scale|, as FP16 (the A operand of the gradient GEMMs, which
+// multiply by |scale|: spv_tc_gemm_ex fmt 3); rows G .. Gp of each block and columns B .. ld_d3 are not written.  Operands as spv_dec_nb_fwd_tc.  colsum [4, G] =
 // column sums of dyp, dys, dpi, dtheta (true scale).
 extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
                                  const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16,
-                                 void* d3_bf16, int B, int G, int HD, int P, int S, float scale, float* colsum, int kmix, void* stream) {
-    if (!ptrs || !amix_bf16 || !wstack_bf16 || !zc_f16 || !wz_f16 || !d3_bf16 || !colsum || Gp < G || B <= 0 || G <= 0 || P <= 0 || S <= 0)
+                                 void* d3_f16, long long ld_d3, int B, int G, int HD, int P, int S, float scale, float* colsum, int kmix,
+                                 void* stream) {
+    if (!ptrs || !amix_bf16 || !wstack_bf16 || !zc_f16 || !wz_f16 || !d3_f16 || !colsum || Gp < G || B <= 0 || G <= 0 || P <= 0 || S <= 0 ||
+        ld_d3 < B)
         return SPV_ERR_ARG;
     if (P + S > ZK_MAX_LATENT) return SPV_ERR_ARG;
     const int need[] = {0, 5, 6, 7, 9, 15, 18};
@@ -390,7 +381,7 @@ extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx
     NbTcBwdParams p;
     p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
     p.lib = (const float*)ptrs[7]; p.rowc = (const float*)ptrs[9]; p.tgb = (const float2*)ptrs[18];
-    p.colpart = (float*)ptrs[15]; p.dpi = reinterpret_cast<__nv_bfloat16*>(d3_bf16); p.ld_dpi = 3L * Gp;
+    p.colpart = (float*)ptrs[15]; p.dpi = reinterpret_cast<__nv_bfloat16*>(d3_f16); p.ld_dpi = ld_d3;
     // The sweep works in natural units (sign only): D3 holds d / |scale| in fp16 - |d pi| <= 1, |d y| bounded by log1p(count)
     // + theta, all well inside fp16's normal range whatever the minibatch size - and the consumers apply |scale|: the
     // column sums below, the gradient GEMMs through spv_tc_gemm_ex's alpha.

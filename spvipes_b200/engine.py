@@ -253,9 +253,13 @@ class _GroupWS:
             self.W1b, self.Wstack, self.W1b_lo = wb
             self.Wmb = self.Wstack[:G]
             if with_grad:
-                self.D3, self.dh1b = hd(B, 3 * self.Gp), h(B, 2 * H)  # D3 = [dpi | dyp | dys]
+                # D3: the backward sweep's output = fp16 operand of the gradient GEMMs.  Fused path: GENE-major
+                # D3T [3 Gp, Bp] = [dpi ; dyp ; dys] (coalesced stores from the TMEM epilogue, thread = cell); unfused path: cell-major
+                # [B, 3 Gp], only the first Gp columns used
+                self.Bp = r8(B)
+                self.D3, self.dh1b = hd(3 * self.Gp * self.Bp).view(-1), h(B, 2 * H)
                 self.dh1b_lo = h(B, 2 * H)
-                self.dpib = self.D3  # unfused path: only the first Gp columns are used (row pitch 3 Gp)
+                self.dpib = self.D3.view(-1)[:B * 3 * self.Gp].view(B, 3 * self.Gp)
                 self.CQ = f(2 * self.Gp, KZb)
             # split-K factors of the tensor-core GEMMs (128-wide tiles): fill the 148 SMs
             tiles = ((B + 127) // 128) * ((2 * H + 127) // 128)
@@ -837,20 +841,20 @@ class StepEngine:
                 if evs is not None:
                     evs[0].record()
                 L.check(lib.spv_dec_nb_bwd_tc(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, L.ptr(w.amixb), w.KMp,
-                                              L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.zcb), L.ptr(w.wzf), L.ptr(w.D3), B, G, HD, Pb, Sb,
+                                              L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.zcb), L.ptr(w.wzf), L.ptr(w.D3), w.Bp, B, G, HD, Pb, Sb,
                                               -float(grad_scale) / B, L.ptr(w.colsum), KMIX, st), "spv_dec_nb_bwd_tc")
                 if evs is not None:
                     evs[1].record()
-                Gp3 = 3 * w.Gp
+                Bp, d3_branches = w.Bp, w.D3.data_ptr() + 2 * w.Gp * w.Bp  # D3T rows Gp .. 3 Gp: [dyp ; dys]
                 # d zz through the two softmax branches: [dyp | dys] against the folded weights' latent columns (K = 2 Gp,
                 # N = P + S).  Kept out of the mixture GEMM below: stacked into its K it would triple that GEMM's operand traffic.
                 f3, al = self.dec_fmt, float(grad_scale) / B  # D3 is stored in natural units: the GEMMs apply |scale|
                 with self._branch(g, "dzg"):
-                    self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, w.Wstack.data_ptr() + 2 * (w.Gp * w.KMp + HD), L.ptr(w.dzraw), B, KZb,
-                                  2 * w.Gp, lda=Gp3, ldb=w.KMp, ldc=KZb, b_mn=1, splits=w.tc_splits_dz, ws=w.ws2, fmt=f3, alpha=al)
+                    self._tc_gemm(d3_branches, w.Wstack.data_ptr() + 2 * (w.Gp * w.KMp + HD), L.ptr(w.dzraw), B, KZb,
+                                  2 * w.Gp, lda=Bp, ldb=w.KMp, ldc=KZb, a_mn=1, b_mn=1, splits=w.tc_splits_dz, ws=w.ws2, fmt=f3, alpha=al)
                 with self._branch(g, "wgrad"):  # d Wm = dpi^T [hm | zz]
-                    self._tc_gemm(L.ptr(w.D3), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=Gp3, ldb=w.KMp, ldc=KMIX,
-                                  a_mn=1, b_mn=1, fmt=f3, alpha=al)
+                    self._tc_gemm(L.ptr(w.D3), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=Bp, ldb=w.KMp, ldc=KMIX,
+                                  a_mn=0, b_mn=1, fmt=f3, alpha=al)
                 Qp, Qs, ldq, dzraw = w.CQ.data_ptr(), w.CQ.data_ptr() + 4 * (w.Gp * KZb + Pb), KZb, None
                 if nb:  # 16-bit copy of the regressors' inputs (without covariates they are the latent columns of amixb)
                     self._to_dec(L.ptr(w.zzb), KZb, L.ptr(w.zzb16), w.zzb16.stride(0), B, KZb)
@@ -859,11 +863,11 @@ class StepEngine:
                 # d [hm | zz], so it runs beside the input-gradient GEMM and the hidden layer's backward
                 with self._branch(g, "gene", lane=1):
                     # [Qp | .] = dyp^T zz, [. | Qs] = dys^T zz in one GEMM over the stacked rows (rows g and Gp + g)
-                    self._tc_gemm(w.D3.data_ptr() + 2 * w.Gp, zb16, L.ptr(w.CQ), 2 * w.Gp, KZb, B, lda=Gp3,
-                                  ldb=ld_zb16, ldc=KZb, a_mn=1, b_mn=1, fmt=f3, alpha=al)
+                    self._tc_gemm(d3_branches, zb16, L.ptr(w.CQ), 2 * w.Gp, KZb, B, lda=Bp,
+                                  ldb=ld_zb16, ldc=KZb, a_mn=0, b_mn=1, fmt=f3, alpha=al)
                     self._gene_bwd(g, w, Qp, Qs, ldq, B, G)
                 # d [hm | zz] (mixture part) = dpi Wm
-                self._tc_gemm(L.ptr(w.D3), L.ptr(w.Wstack), L.ptr(w.damix), B, KMIX, G, lda=Gp3, ldb=w.KMp, ldc=KMIX, b_mn=1,
+                self._tc_gemm(L.ptr(w.D3), L.ptr(w.Wstack), L.ptr(w.damix), B, KMIX, G, lda=Bp, ldb=w.KMp, ldc=KMIX, a_mn=1, b_mn=1,
                               splits=w.tc_splits_damix, ws=w.ws, fmt=f3, alpha=al)
             else:
                 L.check(lib.spv_dec_nb_bwd(src, self._dec_ptrs(g, w, xptr, bt.rows, True), ldx, KMIX, B, G, HD, Pb, Sb,

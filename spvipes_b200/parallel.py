@@ -5,11 +5,14 @@ only the parameter gradients are exchanged (NCCL all-reduce over NVLink 5 / NVSw
 
 Two all-reduces per step, in backward-completion order: the decoder range of the flat gradient buffer as soon as the decoder
 and PoE backward are done (it then overlaps the encoder backward), the encoder range after it; Adam waits for both.
-The collectives stay outside CUDA-graph capture: the step is three captured graphs with the two eager all-reduces between.
+Product path on NVLink boxes: `NvlinkGradSync` - the gradient buffer lives in symmetric memory and each range is summed by ONE
+hand-written kernel (csrc/xgpu.cu: multimem.ld_reduce / multimem.st through the NVSwitch, or peer loads / stores) that is
+captured INSIDE the step's CUDA graph: one graph launch per step, no host in the loop.  `GradSync` (torch.distributed
+all-reduce issued eagerly between four captured graphs) remains for gloo (CPU tests) and as the A/B baseline (SPV_DP_SYNC=nccl).
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -35,6 +38,9 @@ class GradSync:
     each phase is ONE all-reduce: `start(engine, phase)` issues it asynchronously (the decoder range while the encoder
     backward still runs), `finish()` makes the current stream wait for everything issued."""
 
+    in_graph = False
+    kind = "torch.distributed all-reduce (eager, between four graphs)"
+
     def __init__(self, engine, dist, n_buckets: int = 0):
         self.dist = dist
         self.world = dist.get_world_size()
@@ -56,8 +62,81 @@ class GradSync:
         return self.finish()
 
 
+class NvlinkGradSync:
+    """in-graph gradient all-reduce over NVLink (csrc/xgpu.cu).  Construction is collective: every rank allocates the flat
+    gradient buffer and a flag buffer in symmetric memory (torch.distributed._symmetric_memory: allocation + exchange of the
+    peer / multicast mappings only - the reduction itself is this library's kernel) and the engine adopts the buffer.
+    `allreduce(phase, channel)` enqueues the kernel for one phase of the flat layout on the current stream."""
+
+    in_graph = True
+
+    def __init__(self, engine, dist, multicast: Optional[bool] = None, blocks: int = 0):
+        import os
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib as L
+        self.dist, self.engine, self.lib = dist, engine, L.load()
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        group = dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass  # newer torch enables it implicitly
+        dev = engine.device
+        n = engine.params.numel
+        self.buf = symm.empty(n, dtype=torch.float32, device=dev)
+        self.flags = symm.empty(self.lib.spv_xgpu_flag_ints(), dtype=torch.int32, device=dev)
+        self.buf.zero_()
+        self.flags.zero_()
+        hb = symm.rendezvous(self.buf, group.group_name)
+        hf = symm.rendezvous(self.flags, group.group_name)
+        torch.cuda.synchronize(dev)
+        dist.barrier()  # every rank's flags are zero before anybody's first kernel signals
+        self._handles = (hb, hf)
+        self.peer_bufs = L.ptr_array([int(x) for x in hb.buffer_ptrs])
+        self.peer_flags = L.ptr_array([int(x) for x in hf.buffer_ptrs])
+        mc = int(getattr(hb, "multicast_ptr", 0) or 0)
+        if multicast is None:
+            multicast = os.environ.get("SPV_DP_MULTICAST", "1") == "1"
+        self.mc = mc if (multicast and mc) else None
+        self.kind = "nvlink-multimem" if self.mc else "nvlink-p2p"
+        self.blocks = blocks or int(os.environ.get("SPV_DP_BLOCKS", "0"))
+        self.state = torch.zeros(12, dtype=torch.int32, device=dev)
+        engine.grads = self.buf  # the backward kernels now write the symmetric buffer directly
+        self.ranges = dict(engine.params.ranges)
+
+    def allreduce(self, phase: int, channel: int):
+        from . import _lib as L
+        lo, hi = self.ranges[phase]
+        L.check(self.lib.spv_xgpu_allreduce(self.peer_bufs, self.peer_flags, self.mc, lo, hi - lo, self.rank, self.world, channel,
+                                            L.ptr(self.state), self.blocks, torch.cuda.current_stream(self.engine.device).cuda_stream),
+                "spv_xgpu_allreduce")
+
+    def check(self):
+        """raise if a handshake of any launch so far timed out (synchronises the device)"""
+        bad = int(self.state[8].item())
+        if bad:
+            raise RuntimeError(f"NVLink gradient all-reduce: rank {bad - 1} did not answer rank {self.rank} within the time limit")
+
+    def __call__(self, engine) -> float:
+        """all ranges, on the current stream (eager use: tests)"""
+        for ch, ph in enumerate(sorted(self.ranges, reverse=True)):
+            self.allreduce(ph, ch)
+        return 1.0 / self.world
+
+
 def make_grad_sync(engine, dist):
-    """the gradient synchroniser bench.py / the NCCL test use for this process group"""
+    """the gradient synchroniser bench.py / the NCCL tests use for this process group: the in-graph NVLink all-reduce on CUDA
+    with the NCCL backend, torch.distributed all-reduces otherwise (gloo) or when SPV_DP_SYNC=nccl asks for the baseline.
+    If symmetric memory cannot be set up on this box the NCCL path is used and the reason is kept in `.fallback_reason`."""
+    import os
+    want = os.environ.get("SPV_DP_SYNC", "nvlink")
+    if want == "nvlink" and engine.device.type == "cuda" and dist.get_backend() == "nccl":
+        try:
+            return NvlinkGradSync(engine, dist)
+        except Exception as e:  # no peer access / no symmetric-memory support: keep training, say why
+            gs = GradSync(engine, dist)
+            gs.fallback_reason = f"{type(e).__name__}: {e}"[:200]
+            return gs
     return GradSync(engine, dist)
 
 

@@ -86,6 +86,7 @@ class TrainLoop:
         self.n_epochs_kl_warmup = n_epochs_kl_warmup
         self.epoch = 0
         self.grad_sync = None  # optional callable(engine) run between backward and the optimiser step (data parallel)
+        self._dp_stream = None
         self.early_adam = os.environ.get("SPV_EARLY_ADAM", "1") == "1"  # A/B switch for the per-range optimiser step
         # this loop owns the optimiser step: Adam also refreshes the bf16 tensor-core copies of the large weights
         # (largest staged block must stay below 2^24 elements, the range of the kernel's index arithmetic)
@@ -105,6 +106,8 @@ class TrainLoop:
         elif self.grad_sync is None:
             e.backward()
             e.adam_step(lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=1.0)
+        elif getattr(self.grad_sync, "in_graph", False):
+            self._step_nvlink(e)
         else:  # data parallel: the decoder range is all-reduced while the encoder backward runs
             from .engine import PHASE_DEC, PHASE_ENC
             e.backward(stage="decoder", tick=True)
@@ -115,6 +118,30 @@ class TrainLoop:
             for ph in (PHASE_DEC, PHASE_ENC):
                 e.adam_range_step(ph, lr=self.lr, eps=self.eps, weight_decay=self.weight_decay, grad_scale=gs)
         return e.loss_terms()
+
+    def _step_nvlink(self, e):
+        """backward + gradient all-reduce + Adam of the data-parallel step, every launch on CUDA streams (capturable as one
+        graph): decoder / PoE backward -> on a side stream [all-reduce of the decoder range (csrc/xgpu.cu) -> Adam on it] beside
+        the encoder backward on the main stream -> all-reduce of the encoder range -> Adam on it.  Adam folds the 1 / world
+        factor.  The decoder all-reduce always precedes the encoder one in every rank's launch order (channels 0 and 1)."""
+        from .engine import PHASE_DEC, PHASE_ENC
+        gs, dev = self.grad_sync, e.device
+        kw = {"lr": self.lr, "eps": self.eps, "weight_decay": self.weight_decay, "grad_scale": 1.0 / gs.world}
+        e.backward(stage="decoder", tick=True)
+        main = torch.cuda.current_stream(dev)
+        if self._dp_stream is None:
+            self._dp_stream = torch.cuda.Stream(device=dev)
+        fork, done = torch.cuda.Event(), torch.cuda.Event()
+        fork.record(main)
+        self._dp_stream.wait_event(fork)
+        with torch.cuda.stream(self._dp_stream):
+            gs.allreduce(PHASE_DEC, 0)
+            e.adam_range_step(PHASE_DEC, **kw)
+            done.record(self._dp_stream)
+        e.backward(stage="encoder")
+        gs.allreduce(PHASE_ENC, 1)
+        e.adam_range_step(PHASE_ENC, **kw)
+        main.wait_event(done)
 
     def capture(self, batches: Sequence[GroupBatch], noise: Optional[Noise] = None) -> "torch.cuda.CUDAGraph":
         """record one step (every kernel launch of forward, backward, gradient sync and Adam) into a CUDA graph.
@@ -134,7 +161,8 @@ class TrainLoop:
                 self.step(batches, noise)
         cur.wait_stream(side)
         torch.cuda.synchronize(e.device)
-        if self.grad_sync is None:
+        if self.grad_sync is None or getattr(self.grad_sync, "in_graph", False):
+            # (data parallel over NVLink: the all-reduce kernels are part of the graph - every rank replays the same launch order)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self.step(batches, noise)

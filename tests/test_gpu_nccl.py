@@ -1,7 +1,10 @@
 """-m gpu, needs >= 2 GPUs (skipped on a 1-GPU box; run with `gpurun --gpus 2`): the data-parallel step exactly as bench.py
 times it at N > 1 - NCCL process group, one rank per GPU, the CAPTURED step (`TrainLoop.capture` with a gradient sync) replayed
 for several steps with in-kernel Philox noise, tensor-core mode.  Checks: every rank ends with bitwise-identical parameters and
-optimiser state, and they equal a single process that runs the two ranks' steps itself and averages their gradients by hand."""
+optimiser state, and they equal a single process that runs the two ranks' steps itself and averages their gradients by hand.
+Three gradient synchronisers: the in-graph NVLink all-reduce kernel (csrc/xgpu.cu) through the switch's multicast reduction,
+the same kernel on peer loads / stores, and torch.distributed all-reduces issued between four graphs (the r1 baseline).
+A second test drives the all-reduce kernel alone on ranges of awkward sizes."""
 import os
 import socket
 
@@ -32,8 +35,10 @@ def _rows_for(rank, step, dev):
     return [torch.randperm(4 * B, generator=gen)[:B].to(torch.int32).to(dev) for _ in (0, 1)]
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, sync):
     import torch.distributed as dist
+    os.environ["SPV_DP_SYNC"] = "nccl" if sync == "nccl" else "nvlink"
+    os.environ["SPV_DP_MULTICAST"] = "0" if sync == "nvlink-p2p" else "1"
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -54,19 +59,31 @@ def _worker(rank, world, port, out_dir):
             rows[g].copy_(r)
         graph.replay()
     torch.cuda.synchronize()
+    if hasattr(loop.grad_sync, "check"):
+        loop.grad_sync.check()
     torch.save({"params": eng.params.flat.cpu(), "m": eng.adam_m.cpu(), "v": eng.adam_v.cpu(), "step": int(eng.step_dev),
-                "loss": eng.loss_out.cpu(), "sync": type(loop.grad_sync).__name__}, os.path.join(out_dir, f"r{rank}.pt"))
+                "loss": eng.loss_out.cpu(), "sync": f"{type(loop.grad_sync).__name__} ({loop.grad_sync.kind})",
+                "fallback": getattr(loop.grad_sync, "fallback_reason", None)}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_nccl_captured_step_equals_manual_gradient_average(tmp_path):
+def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    return port
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("sync", ["nvlink", "nvlink-p2p", "nccl"])
+def test_nccl_captured_step_equals_manual_gradient_average(tmp_path, sync):
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), sync), nprocs=2, join=True)
     got = [torch.load(str(tmp_path / f"r{r}.pt")) for r in (0, 1)]
+    assert got[0]["fallback"] is None, got[0]["fallback"]  # the synchroniser asked for is the one that ran
+    if sync != "nccl":
+        assert "NvlinkGradSync" in got[0]["sync"] and ("multimem" in got[0]["sync"]) == (sync == "nvlink"), got[0]["sync"]
     for k in ("params", "m", "v"):
         assert torch.equal(got[0][k], got[1][k]), k  # bitwise across ranks
     assert got[0]["step"] == got[1]["step"] == STEPS
@@ -95,3 +112,55 @@ def test_nccl_captured_step_equals_manual_gradient_average(tmp_path):
     err = float((got[0]["params"] - want).abs().max()) / float(want.abs().max())
     print("sync:", got[0]["sync"], "max rel param diff vs manual average:", err)
     assert err <= 2e-6, err
+
+
+def _allreduce_worker(rank, world, port, out_dir, multicast):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from spvipes_b200.parallel import NvlinkGradSync
+
+    class _Store:  # the two attributes NvlinkGradSync reads from an engine
+        pass
+    eng = _Store()
+    eng.device = dev
+    eng.params = _Store()
+    # ranges of awkward sizes: one float4, fewer float4s than ranks x CTAs, a size that does not divide by the world size
+    eng.params.ranges = {0: (0, 4), 1: (4, 4 + 4 * 3), 2: (16, 16 + 4 * 100_003), 3: (16 + 4 * 100_003, 16 + 4 * 100_003 + 4 * 3_000_000)}
+    eng.params.numel = eng.params.ranges[3][1]
+    gs = NvlinkGradSync(eng, dist, multicast=multicast)
+    ok = True
+    for it in range(3):  # repeated launches on the same channels: the epochs advance
+        gen = torch.Generator(device=dev).manual_seed(100 * it + rank)
+        mine = torch.randn(eng.params.numel, generator=gen, device=dev)
+        theirs = [torch.randn(eng.params.numel, generator=torch.Generator(device=dev).manual_seed(100 * it + r), device=dev) for r in range(world)]
+        want = theirs[0].clone()
+        for r in range(1, world):
+            want += theirs[r]
+        eng.grads.copy_(mine)
+        torch.cuda.synchronize()
+        dist.barrier()
+        for ch, ph in enumerate(sorted(eng.params.ranges)):
+            gs.allreduce(ph, ch)
+        torch.cuda.synchronize()
+        gs.check()
+        ok = ok and bool(torch.equal(eng.grads, want)) if world == 2 else ok and bool(torch.allclose(eng.grads, want, rtol=1e-6, atol=1e-6))
+        dist.barrier()
+    torch.save({"ok": ok, "kind": gs.kind, "sum": eng.grads.double().sum().item()}, os.path.join(out_dir, f"a{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("multicast", [True, False])
+def test_xgpu_allreduce_kernel(tmp_path, multicast):
+    """spv_xgpu_allreduce alone: sums equal the plain sum (two ranks: one addition, so bit-exact), identical on both ranks"""
+    world = 2
+    mp.spawn(_allreduce_worker, args=(world, _free_port(), str(tmp_path), multicast), nprocs=world, join=True)
+    got = [torch.load(str(tmp_path / f"a{r}.pt")) for r in range(world)]
+    assert all(g["ok"] for g in got), got
+    assert got[0]["sum"] == got[1]["sum"]
+    assert ("multimem" in got[0]["kind"]) == multicast, got[0]["kind"]

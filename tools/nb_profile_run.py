@@ -1,5 +1,6 @@
 """small driver for ncu: a few eager training steps at a BASELINE minibatch shape (C5 by default) on a reduced resident matrix.
-    python tools/nb_profile_run.py [C5|C2] && ncu --set full --clock-control none --import-source on -k regex:nb_tc -s 4 -c 4 -o gpurun_out/prof python tools/nb_profile_run.py"""
+    python tools/nb_profile_run.py [C5|C2] && ncu --set full --clock-control none --import-source on --profile-from-start off \
+        -k regex:"nb_tc_(fwd|bwd)" -c 4 -o gpurun_out/prof python tools/nb_profile_run.py"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -19,6 +20,9 @@ loop = TrainLoop(eng)
 loop.set_epoch(1)
 gen = torch.Generator(device="cuda").manual_seed(5)
 for s in range(3):
+    if s == 2:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()  # ncu --profile-from-start off: the third step only
     rows = [torch.randperm(N, generator=gen, device="cuda")[:B].to(torch.int32) for _ in (0, 1)]
     loop.step([GroupBatch(X=data.X[g], rows=rows[g], labels=data.labels[g], labels_per_cell=True) for g in (0, 1)])
 torch.cuda.synchronize()
