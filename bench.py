@@ -290,13 +290,17 @@ class Bench:
             self.dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_blocks(self, K, W, step_fn):
-        """W warm-up steps, then R blocks of exactly K steps; returns the per-block ms (max over ranks each)"""
+    def timed_blocks(self, K, W, step_fn, profile=False):
+        """W warm-up steps, then R blocks of exactly K steps; returns the per-block ms (max over ranks each).
+        profile: cudaProfilerStart after the warm-up (`ncu --profile-from-start off` then sees only training steps, not the
+        data generation, the index draws or the graph capture)"""
         n_steps_hint = 64
         rows = self.draw_rows(n_steps_hint)
         for s in range(W):
             step_fn(rows, s % n_steps_hint)
         self.barrier()
+        if profile:
+            torch.cuda.profiler.start()
         # pilot block to size R: >= 5 blocks and ~1 s of timed steps in total, at most 60 blocks
         blocks, s = [], W
         R = 5
@@ -338,14 +342,7 @@ class Bench:
                 self.loop.step(self.static)
 
         n0 = self.lib.spv_launch_count()
-        prof = bool(os.environ.get("SPV_PROFILE_RANGE"))  # `ncu --profile-from-start off`: skip data generation and capture
-        if prof:
-            torch.cuda.synchronize()
-            torch.cuda.profiler.start()
-        blocks = self.timed_blocks(K, W, step)
-        if prof:
-            torch.cuda.synchronize()
-            torch.cuda.profiler.stop()
+        blocks = self.timed_blocks(K, W, step, profile=bool(os.environ.get("SPV_PROFILE_RANGE")))
         ms = float(np.median(blocks))
         if use_graph:
             launches, per_step = self.per_step_launches * K * len(blocks), self.per_step_launches

@@ -240,9 +240,9 @@ long long spv_dec_nb_part_floats(int B, int G);
 /* rec[b] (ptrs[16] of the forward) and the softmax-backward row sums rowc[:, 2:4] from the row partials part_nb that
  * spv_dec_nb_fwd_tc wrote for the same B, G, HD */
 int spv_dec_nb_rowreduce(const float* part_nb, int G, int B, int HD, float* rowc, float* rec, void* stream);
-/* tensor-core backward sweep: recomputes the three logit tiles on tcgen05 and writes D3T = [dpi ; dyp ; dys] / |scale| (FP16,
+/* tensor-core backward sweep: recomputes the three logit tiles on tcgen05 and writes D3T = [dpi ; dyp ; dys] / scale (FP16,
  * GENE-major [3 Gp, ld_d3], ld_d3 >= B a multiple of 8: a warp's 32 cells are contiguous, so the stores coalesce; operand of
- * the gradient GEMMs, which apply |scale| as spv_tc_gemm_ex's alpha) and colsum [4, G] (column sums of dyp, dys, dpi,
+ * the gradient GEMMs, which apply the signed scale as spv_tc_gemm_ex's alpha) and colsum [4, G] (column sums of dyp, dys, dpi,
  * d loss / d theta, true scale);
  * ptrs[15] = colpart workspace [ceil(B/128), 4, G].  scale = - grad_scale / B.  rowc (ptrs[9], [B, 4] floats) must be
  * 16-byte aligned (SPV_ERR_ARG otherwise): a row is read as one float4. */

@@ -21,7 +21,7 @@ constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int ACC_COLS = BN, Z_COLS = 2 * BN;  // tensor memory is allocated in two steps (powers of two >= 32)
 static_assert(ACC_COLS == 32 || ACC_COLS == 64, "tensor-memory allocations are powers of two");
-constexpr int CNT_PITCH_W = BN / 2 + 1;
+constexpr int CNT_PITCH_W = BN / 2 + 2;  // 34 words per row: thread = row reads 64 bits (four codes), aligned and conflict-free
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * B_BYTES + 1024 + BN * 16 + 4 * 4 * BN * 4 + BN * NB_TAB * 8 + 256;
 
 static_assert(BM * CNT_PITCH_W * 4 <= STAGES * STAGE_BYTES, "count tile must fit in the operand stages");
@@ -46,6 +46,28 @@ __device__ __forceinline__ int cnt_row(int e, int lane, int i) {
 
 // CTAs of this kernel currently resident per SM (a scheduling hint only, see the allocation below; balanced by every CTA)
 __device__ int g_resident_bwd[256];
+
+__device__ __forceinline__ unsigned long long mad_wide(uint32_t a, uint32_t b, unsigned long long c) {
+    unsigned long long d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ void st_half(unsigned long long addr, float v) {
+    const unsigned short h = __half_as_ushort(__float2half_rn(v));
+    asm volatile("st.global.u16 [%0], %1;" ::"l"(addr), "h"(h) : "memory");
+}
+
+// one element off the fast path (a count outside the table, a logit below the fast logarithm's range, an edge tile): out of line
+template <int SRC>
+__device__ __noinline__ NbGrad nb_bwd_general(uint32_t code, float xp, float xs, float acc_pi, float4 gc, const uint8_t* tg_row,
+                                              const void* X, long xidx, const float* dgt, float DpI, float DsI) {
+    float2 tcn;
+    if (code == NB_CODE_SLOW) tcn = nb_count_terms_bwd_slow(nb_load_raw<SRC>(X, xidx), gc.x, __ldg(dgt));
+    else tcn = *reinterpret_cast<const float2*>(tg_row + code);
+    const float pi = acc_pi + gc.w;
+    if (tcn.x != 0.0f && fminf(xp, xs) < NB_X_RARE) return nb_backward_v5<true>(tcn.x, tcn.y, xp, xs, pi, gc.x, gc.y, gc.z, DpI, DsI);
+    return nb_backward_v5<false>(tcn.x, tcn.y, xp, xs, pi, gc.x, gc.y, gc.z, DpI, DsI);
+}
 
 template <int SRC>
 __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA,
@@ -251,9 +273,14 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
 #pragma unroll
         for (int i = 0; i < NGATHER; ++i) s_cnt[cnt_row(e, lane, i) * CNT_PITCH_W + lane % (BN / 2)] = cw[i];
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
-        __half* const d3t = reinterpret_cast<__half*>(p.dpi) + (long)n0 * p.ld_dpi + m;  // this cell's column, first gene of the tile
-        const long blk_stride = (long)p.Gp * p.ld_dpi;
+        const uint32_t ldb = (uint32_t)p.ld_dpi * 2u;
+        // running store addresses: this cell's column in the three blocks of D3T, at the first gene of the current four
+        const unsigned long long blk_bytes = (unsigned long long)p.Gp * ldb;
+        unsigned long long d_pi = reinterpret_cast<unsigned long long>(p.dpi) + (unsigned long long)(n0 + half * WCOLS) * ldb + 2ull * (unsigned)m;
+        unsigned long long d_yp = d_pi + blk_bytes, d_ys = d_yp + blk_bytes;
+        const bool full_tile = n0 + BN <= p.G && m0 + BM <= p.B;  // CTA-uniform
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16), lane_z = tmem_z + ((uint32_t)(q * 32) << 16);
+        const uint32_t* cnt_row_p = s_cnt + rloc * CNT_PITCH_W + half * (WCOLS / 2);
 #pragma unroll 1
         for (int j4 = 0; j4 < WCOLS; j4 += 4) {
             const int c0 = half * WCOLS + j4;
@@ -261,32 +288,50 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_bwd_kernel(const __grid_cons
             tc::tmem_ld4(lane_addr + (uint32_t)c0, rpi);
             tc::tmem_ld4(lane_z + (uint32_t)c0, rlp);
             tc::tmem_ld4(lane_z + (uint32_t)(BN + c0), rls);
+            const uint2 cc = *reinterpret_cast<const uint2*>(cnt_row_p + (j4 >> 1));  // four count codes
             tc::tmem_ld_wait();
+            const uint32_t call = cc.x | cc.y;
+            const float xm = fminf(fminf(fminf(__uint_as_float(rlp[0]), __uint_as_float(rls[0])), fminf(__uint_as_float(rlp[1]), __uint_as_float(rls[1]))),
+                                   fminf(fminf(__uint_as_float(rlp[2]), __uint_as_float(rls[2])), fminf(__uint_as_float(rlp[3]), __uint_as_float(rls[3]))));
+            // every count tabulated, every column and row valid, the fast logarithm holds (as in nb_tc_fwd_kernel)
+            const bool plain = full_tile && (call & 0x80008000u) == 0u && !(call != 0u && xm < NB_X_RARE);
             float vyp[4], vys[4], vpi[4], vth[4];
+            // D3T[gene, cell] (fp16, gradients of the log-likelihood: the consumers apply the signed scale): the 32 lanes of the
+            // warp are 32 consecutive cells, so each of the three stores of a gene writes 64 contiguous bytes
+            if (plain) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int gl = c0 + jj, g = n0 + gl;
-                vyp[jj] = vys[jj] = vpi[jj] = vth[jj] = 0.0f;
-                if (mok && g < p.G) {
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int gl = c0 + jj;
+                    const uint32_t w = jj < 2 ? cc.x : cc.y;
+                    const uint32_t code = (jj & 1) ? (w >> 16) : (w & 0xffffu);
+                    const float2 tcn = *reinterpret_cast<const float2*>(s_tg + gl * (NB_TAB * 8) + code);
                     const float4 gc = s_gc[gl];
-                    const uint32_t w = s_cnt[rloc * CNT_PITCH_W + (gl >> 1)];
-                    const uint32_t code = (gl & 1) ? (w >> 16) : (w & 0xffffu);
-                    float2 tcn;
-                    if (code == NB_CODE_SLOW) tcn = nb_count_terms_bwd_slow(nb_load_raw<SRC>(p.X, xrow + g), gc.x, __ldg(p.genec + GC_DGT * G + g));
-                    else tcn = *reinterpret_cast<const float2*>(s_tg + gl * (NB_TAB * 8) + code);
-                    const float xp = __uint_as_float(rlp[jj]), xs = __uint_as_float(rls[jj]), pi = __uint_as_float(rpi[jj]) + gc.w;
-                    NbGrad o = nb_backward_v5<false>(tcn.x, tcn.y, xp, xs, pi, gc.x, gc.y, gc.z, DpI, DsI);
-                    if (tcn.x != 0.0f && fminf(xp, xs) < NB_X_RARE) o = nb_backward_v5<true>(tcn.x, tcn.y, xp, xs, pi, gc.x, gc.y, gc.z, DpI, DsI);
-                    o.dyp *= p.scale; o.dys *= p.scale; o.dpi *= p.scale; o.dth *= p.scale;
+                    const NbGrad o = nb_backward_v5<false>(tcn.x, tcn.y, __uint_as_float(rlp[jj]), __uint_as_float(rls[jj]),
+                                                           __uint_as_float(rpi[jj]) + gc.w, gc.x, gc.y, gc.z, DpI, DsI);
                     vyp[jj] = o.dyp; vys[jj] = o.dys; vpi[jj] = o.dpi; vth[jj] = o.dth;
-                    // D3T[gene, cell] (fp16): the 32 lanes of the warp are 32 consecutive cells, so each of the three stores
-                    // of a gene writes 64 contiguous bytes (the cell-major layout cost 32 partial sectors per store)
-                    __half* d = d3t + (long)gl * p.ld_dpi;
-                    d[0] = __float2half_rn(o.dpi);
-                    d[blk_stride] = __float2half_rn(o.dyp);
-                    d[2 * blk_stride] = __float2half_rn(o.dys);
+                    st_half(d_pi + jj * ldb, o.dpi);
+                    st_half(d_yp + jj * ldb, o.dyp);
+                    st_half(d_ys + jj * ldb, o.dys);
+                }
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int gl = c0 + jj;
+                    const uint32_t w = jj < 2 ? cc.x : cc.y;
+                    const uint32_t code = (jj & 1) ? (w >> 16) : (w & 0xffffu);
+                    vyp[jj] = vys[jj] = vpi[jj] = vth[jj] = 0.0f;
+                    if (mok && n0 + gl < p.G) {
+                        const NbGrad o = nb_bwd_general<SRC>(code, __uint_as_float(rlp[jj]), __uint_as_float(rls[jj]), __uint_as_float(rpi[jj]),
+                                                             s_gc[gl], s_tg + gl * (NB_TAB * 8), p.X, xrow + n0 + gl,
+                                                             p.genec + GC_DGT * G + n0 + gl, DpI, DsI);
+                        vyp[jj] = o.dyp; vys[jj] = o.dys; vpi[jj] = o.dpi; vth[jj] = o.dth;
+                        st_half(d_pi + jj * ldb, o.dpi);
+                        st_half(d_yp + jj * ldb, o.dyp);
+                        st_half(d_ys + jj * ldb, o.dys);
+                    }
                 }
             }
+            d_pi += 4ull * ldb; d_yp += 4ull * ldb; d_ys += 4ull * ldb;
             // column sums over this warp's 32 rows (lanes): transpose-reduce of the 16 values (4 quantities x 4 columns).  Each
             // butterfly step halves the values a lane carries, 15 shuffles in all instead of 16 x 5; lanes with bit 0 clear
             // end up with the total of value index (lane >> 1) and park it for the cross-quarter sum.
@@ -353,8 +398,8 @@ __global__ void colpart_reduce_tc_kernel(const float* __restrict__ colpart, int 
 
 // ptrs: the SPV_DEC_NPTR list (X, rows, -, -, -, bm, genec, lib, -, rowc, -, -, -, -, -, colpart [ceil(B/128), 4, G], -).
 // d3_f16 [3 * Gp, ld_d3] (GENE-major, ld_d3 >= B a multiple of 8) receives d loss / d pi (rows 0 .. G), d loss / d y_private
-// (rows Gp ..), d loss / d y_shared (rows 2 Gp ..), each / |scale|, as FP16 (the A operand of the gradient GEMMs, which
-// multiply by |scale|: spv_tc_gemm_ex fmt 3); rows G .. Gp of each block and columns B .. ld_d3 are not written.  Operands as spv_dec_nb_fwd_tc.  colsum [4, G] =
+// (rows Gp ..), d loss / d y_shared (rows 2 Gp ..), each / scale (i.e. the gradients of the log-likelihood), as FP16 (the A
+// operand of the gradient GEMMs, which multiply by the signed scale: spv_tc_gemm_ex fmt 3); rows G .. Gp of each block and columns B .. ld_d3 are not written.  Operands as spv_dec_nb_fwd_tc.  colsum [4, G] =
 // column sums of dyp, dys, dpi, dtheta (true scale).
 extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const void* amix_bf16, long long ld_amixb,
                                  const void* wstack_bf16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16,
@@ -382,10 +427,11 @@ extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx
     p.X = ptrs[0]; p.ldx = ldx; p.rows = (const int*)ptrs[1]; p.bm = (const float*)ptrs[5]; p.genec = (const float*)ptrs[6];
     p.lib = (const float*)ptrs[7]; p.rowc = (const float*)ptrs[9]; p.tgb = (const float2*)ptrs[18];
     p.colpart = (float*)ptrs[15]; p.dpi = reinterpret_cast<__nv_bfloat16*>(d3_f16); p.ld_dpi = ld_d3;
-    // The sweep works in natural units (sign only): D3 holds d / |scale| in fp16 - |d pi| <= 1, |d y| bounded by log1p(count)
-    // + theta, all well inside fp16's normal range whatever the minibatch size - and the consumers apply |scale|: the
-    // column sums below, the gradient GEMMs through spv_tc_gemm_ex's alpha.
-    p.B = B; p.G = G; p.K = K; p.Gp = Gp; p.scale = scale < 0.0f ? -1.0f : 1.0f;
+    // The sweep works in natural units: D3T holds the gradients of the LOG-LIKELIHOOD in fp16 - |d pi| <= 1, |d y| bounded by
+    // log1p(count) + theta, all well inside fp16's normal range whatever the minibatch size - and the consumers apply the
+    // signed scale: the column sums below, the gradient GEMMs through spv_tc_gemm_ex's alpha.
+    if ((long long)ld_d3 >= (1ll << 28)) return SPV_ERR_ARG;  // the row pitch in bytes is a 32-bit quantity inside the kernel
+    p.B = B; p.G = G; p.K = K; p.Gp = Gp; p.scale = scale;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     static bool configured[64] = {};
     int dev = 0;
@@ -401,7 +447,7 @@ extern "C" int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx
     else if (src == SPV_SRC_F32_LOG1P) nb_tc_bwd_kernel<SPV_SRC_F32_LOG1P><<<grid, THREADS, SMEM_BYTES, st>>>(ma, mb, mz, mzc, p);
     else return SPV_ERR_ARG;
     SPV_CHECK_LAUNCH();
-    colpart_reduce_tc_kernel<<<(4 * G + 255) / 256, 256, 0, st>>>(p.colpart, (int)grid.y, G, colsum, fabsf(scale));
+    colpart_reduce_tc_kernel<<<(4 * G + 255) / 256, 256, 0, st>>>(p.colpart, (int)grid.y, G, colsum, scale);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }

@@ -848,7 +848,7 @@ class StepEngine:
                 Bp, d3_branches = w.Bp, w.D3.data_ptr() + 2 * w.Gp * w.Bp  # D3T rows Gp .. 3 Gp: [dyp ; dys]
                 # d zz through the two softmax branches: [dyp | dys] against the folded weights' latent columns (K = 2 Gp,
                 # N = P + S).  Kept out of the mixture GEMM below: stacked into its K it would triple that GEMM's operand traffic.
-                f3, al = self.dec_fmt, float(grad_scale) / B  # D3 is stored in natural units: the GEMMs apply |scale|
+                f3, al = self.dec_fmt, -float(grad_scale) / B  # D3T holds d log-likelihood: the GEMMs apply the signed scale
                 with self._branch(g, "dzg"):
                     self._tc_gemm(d3_branches, w.Wstack.data_ptr() + 2 * (w.Gp * w.KMp + HD), L.ptr(w.dzraw), B, KZb,
                                   2 * w.Gp, lda=Bp, ldb=w.KMp, ldc=KZb, a_mn=1, b_mn=1, splits=w.tc_splits_dz, ws=w.ws2, fmt=f3, alpha=al)

@@ -76,7 +76,7 @@ def prepare_adatas(adatas: Dict[str, object], layers: Optional[Sequence[Optional
         obs_frames.append(obs)
         lengths[gi] = G
         groups_obs_names.append(list(getattr(a, "obs_names", range(n))))
-        groups_var_names[gi] = vn
+        groups_var_names[k] = vn  # keyed by group name, as the reference (data/prepare_adatas.py:111)
         groups_obs_indices.append(np.arange(row0, row0 + n))
         groups_var_indices.append(np.arange(col0, col0 + G))
         col0 += G
@@ -101,9 +101,14 @@ class spVIPES:
             raise KeyError(f"{groups_key} not in adata.obs")
         if transport_plan_key is not None and transport_plan_key not in adata.uns:
             raise ValueError(f"Transport plan not found in adata.uns['{transport_plan_key}']")
+        if match_clusters and transport_plan_key is not None and "processed_transport_labels" not in adata.obs.columns:
+            # reference :362-370: derive the shared cluster labels from the plan (transport.process_transport_plan; the
+            # clustering step is scanpy's Leiden when scanpy is installed, kNN + Louvain otherwise, or `cluster_fn=` in kwargs)
+            from .transport import process_transport_plan
+            labels = process_transport_plan(adata.uns[transport_plan_key], adata, groups_key, cluster_fn=kwargs.pop("cluster_fn", None))
+            adata.obs["processed_transport_labels"] = pd.Categorical(labels)
         if match_clusters and "processed_transport_labels" not in adata.obs.columns:
-            raise ValueError("match_clusters=True needs adata.obs['processed_transport_labels'] (reference process_transport_plan "
-                             "derives it with scanpy/leiden, which is outside this package)")
+            raise ValueError("match_clusters=True needs a transport plan (transport_plan_key) or adata.obs['processed_transport_labels']")
         if batch_key is not None and batch_key not in adata.obs.columns:
             raise KeyError(f"{batch_key} not in adata.obs")
         cls._setup[id(adata)] = {"groups_key": groups_key, "match_clusters": match_clusters, "transport_plan_key": transport_plan_key,
@@ -336,7 +341,7 @@ class spVIPES:
         """reference model/spvipes.py:652-677"""
         out = {}
         for g in (0, 1):
-            names = self.adata.uns["groups_var_names"][g]
+            names = list(self.adata.uns["groups_var_names"].values())[g]
             for kind, dim in (("shared", self.n_dimensions_shared), ("private", self.n_dimensions_private)):
                 w = self.module.get_loadings(g, kind)
                 out[(g, kind)] = pd.DataFrame(w, index=names, columns=[f"Z_{kind}_{i}" for i in range(w.shape[1])])

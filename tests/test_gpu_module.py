@@ -241,3 +241,29 @@ def test_model_api_with_batch_covariate_and_step_warmup():
         lat = model.get_latent_representation(gil, batch_size=200)
         assert lat["shared"][1].shape == (n[1], 12) and np.isfinite(lat["private"][0]).all()
         assert model.get_loadings()[(0, "private")].shape == (G[0], 6)
+
+
+def test_model_api_cluster_mode_derives_transport_labels():
+    """setup_anndata(match_clusters=True, transport_plan_key=...) without ready-made labels: process_transport_plan (reference
+    model/spvipes.py:26-162, :362-370) derives `processed_transport_labels` with the built-in clustering, and cluster-based PoE
+    trains on them"""
+    from spvipes_b200 import synth
+    from spvipes_b200.model import GroupedData, prepare_adatas, spVIPES
+
+    n, G = (300, 260), (64, 48)
+    data = synth.make_counts(n, G, n_labels=3, device="cuda", seed=9)
+    ads = {}
+    for gi, key in enumerate(("a", "b")):
+        ads[key] = GroupedData(X=data.X[gi].cpu().numpy().astype(np.float32), obs=pd.DataFrame({"dummy": np.zeros(n[gi])}),
+                               var_names=[f"g{j}" for j in range(G[gi])])
+    adata = prepare_adatas(ads)
+    plan = synth.make_plan(n[0], n[1], data.labels[0], data.labels[1], 3, device="cpu", seed=3)
+    adata.uns["transport_plan"] = plan.numpy()
+    spVIPES.setup_anndata(adata, groups_key="groups", transport_plan_key="transport_plan", match_clusters=True)
+    lab = adata.obs["processed_transport_labels"]
+    assert lab.notna().all() and 2 <= len(lab.cat.categories) <= 40 and set(adata.uns["optimal_resolutions"]) == {"a", "b"}
+    model = spVIPES(adata, n_hidden=32, n_dimensions_shared=8, n_dimensions_private=4, dropout_rate=0.1)
+    assert model.module.use_transport_plan and not model.module.pair_data
+    gil = [list(ix) for ix in adata.uns["groups_obs_indices"]]
+    model.train(gil, max_epochs=3, batch_size=64, train_size=0.9, n_epochs_kl_warmup=None)
+    assert np.isfinite(model.history["train_loss_epoch"]).all()
