@@ -354,54 +354,70 @@ class Bench:
 
     # ---- the likelihood kernels alone, timed with CUDA events on the launching stream (eager passes, second group off)
     def measure_roofline(self, K):
+        """the likelihood sweeps alone, each timed with CUDA events on the launching stream (eager passes, second group off):
+        the forward-only sweep (evaluation passes; the kernel SURVEY 8(d)'s byte formula describes) and what a TRAINING step
+        runs: one sweep that also emits the backward's operands (default), or forward + backward sweep (SPV_NB_SWEEPS=2)"""
         eng, B, G = self.eng, self.B, self.genes
         n = max(4, min(K, 20))
         rows = self.draw_rows(n)
-        fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * n)]
-        bwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2 * n)]
-        eng.nb_events, eng.nb_bwd_events = iter(fwd_ev), iter(bwd_ev)
+        mk = lambda k: [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        single = bool(getattr(eng, "single_sweep", False)) and self.args.precision == "bf16"
+        trn_ev, bwd_ev, fwd_ev = mk(2 * n), mk(2 * n), mk(2 * n)
         eng.parallel_groups = False  # each kernel is timed alone: no second group running beside it
+        eng.nb_events, eng.nb_bwd_events = iter(trn_ev), iter(bwd_ev)
         for s in range(n):
             self.set_rows(rows, s)
             eng.forward(self.static, training=True)
             eng.backward()
+        eng.nb_events, eng.nb_bwd_events = iter(fwd_ev), None
+        for s in range(n):  # forward-only sweep: evaluation passes (running statistics, no gradients)
+            self.set_rows(rows, s)
+            eng.forward(self.static, training=False)
         torch.cuda.synchronize()
         eng.nb_events = eng.nb_bwd_events = None
         eng.parallel_groups = True
-        f_ms = float(np.mean([a.elapsed_time(b) for a, b in fwd_ev[2:]]))
-        b_ms = float(np.mean([a.elapsed_time(b) for a, b in bwd_ev[2:]]))
+        ms = lambda ev: float(np.mean([a.elapsed_time(b) for a, b in ev[2:]]))
+        f_ms, t_ms = ms(fwd_ev), ms(trn_ev)
+        b_ms = None if single else ms(bwd_ev)
         peak, sm_mhz, peak_src = peaks()
         KZ = S_DIM + P_DIM
         # SURVEY.md section 8(d): bytes of the NB-loglik forward kernel alone = counts (u16) + decoder weights read once as
         # 16-bit operands + 6 per-gene constants + per-cell decoder inputs (latents, hidden layer, library) + per-cell output
         alg_f = B * G * 2 + G * (KZ + 291) * 2 + 6 * G * 4 + B * (KZ + HD + 1) * 4 + B * 4
-        # backward sweep: the same reads + D3 = [dpi | dyp | dys] written as 16-bit operands of the gradient GEMMs + 4 column sums
+        # training sweep: the same reads + the backward's operands it must emit, (ep, rp, es, rs, dpi) as 16-bit values, + 2 column sums
+        alg_t = alg_f + 5 * B * G * 2 + 2 * G * 4
+        # separate backward sweep: the forward's reads + D3 = [dpi ; dyp ; dys] (16-bit) + 4 column sums
         alg_b = alg_f + 3 * B * G * 2 + 4 * G * 4
         elems = B * G
         # SFU (MUFU) pipe: 16 lanes per SM and clock = 4 per sub-partition; ex2 / lg2 / rcp per (cell, gene) element in nb_math.cuh
         mufu_peak = 148 * 16 * sm_mhz * 1e6
-        MUFU_F, MUFU_B = 8, 8  # nb_math.cuh v5: ex2 x4, lg2 x3 (x2 backward), one shared rcp (+ the rare exact variant)
+        MUFU = 8  # nb_math.cuh v5: ex2 x4, lg2 x3 (x2 in the backward-only sweep), one shared rcp (+ the rare exact variant)
         if self.args.precision == "bf16":
-            kf = "nb_tc_fwd_kernel (tcgen05 decoder GEMMs + fused NB-mixture log-likelihood epilogue, forward)"
-            kb = "nb_tc_bwd_kernel (tcgen05 recompute of the logits + likelihood gradients -> D3, column sums)"
+            kf = "nb_tc_fwd_kernel (tcgen05 decoder GEMMs + fused NB-mixture log-likelihood epilogue; forward-only sweep of evaluation passes)"
+            kt = ("nb_tc_train_kernel (the training step's ONE sweep: the same + gradients w.r.t. the logits and theta, the backward GEMMs' "
+                  "16-bit operands and column sums)") if single else kf.replace("forward-only sweep of evaluation passes", "forward sweep of a training step")
+            kb = "nb_tc_bwd_kernel (tcgen05 recompute of the logits + likelihood gradients -> D3T, column sums)"
         else:
-            kf, kb = "dec_tile_kernel<PASS_NB> (fp32 SIMT decoder GEMM + NB log-likelihood)", "dec_tile_kernel<PASS_BWD>"
-        ach = alg_f / (f_ms * 1e-3) / 1e9
-        roof = {"kernel": kf, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": measured_traffic(self.workload, "nb_tc_fwd_kernel"), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_f, "avg_launch_ms": f_ms,
-                "note": "algorithmic bytes by SURVEY 8(d); the kernel is bound by the SFU / issue pipes, not by HBM: see `other` for the "
-                        "MUFU roofline (8 ex2/lg2/rcp per element) and profiles/ for the ncu counters",
-                "other": [
-                    {"kernel": kf, "bound": "mufu", "achieved": MUFU_F * elems / (f_ms * 1e-3) / 1e12, "peak": mufu_peak / 1e12, "unit": "T SFU op/s",
-                     "frac": MUFU_F * elems / (f_ms * 1e-3) / mufu_peak, "sfu_ops_per_element": MUFU_F, "elements_per_launch": elems},
-                    {"kernel": kb, "bound": "hbm", "achieved": alg_b / (b_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": alg_b / (b_ms * 1e-3) / 1e9 / peak, "traffic": measured_traffic(self.workload, "nb_tc_bwd_kernel"),
-                     "algorithmic_bytes_per_launch": alg_b, "avg_launch_ms": b_ms},
-                    {"kernel": kb, "bound": "mufu", "achieved": MUFU_B * elems / (b_ms * 1e-3) / 1e12, "peak": mufu_peak / 1e12, "unit": "T SFU op/s",
-                     "frac": MUFU_B * elems / (b_ms * 1e-3) / mufu_peak, "sfu_ops_per_element": MUFU_B, "elements_per_launch": elems}]}
+            kf = kt = "dec_tile_kernel<PASS_NB> (fp32 SIMT decoder GEMM + NB log-likelihood)"
+            kb = "dec_tile_kernel<PASS_BWD>"
+        hbm = lambda name, b, t, key: {"kernel": name, "bound": "hbm", "achieved": b / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": b / (t * 1e-3) / 1e9 / peak, "traffic": measured_traffic(self.workload, key),
+                                       "algorithmic_bytes_per_launch": b, "avg_launch_ms": t}
+        mufu = lambda name, t: {"kernel": name, "bound": "mufu", "achieved": MUFU * elems / (t * 1e-3) / 1e12, "peak": mufu_peak / 1e12,
+                                "unit": "T SFU op/s", "frac": MUFU * elems / (t * 1e-3) / mufu_peak, "sfu_ops_per_element": MUFU,
+                                "elements_per_launch": elems, "avg_launch_ms": t}
+        roof = hbm(kf, alg_f, f_ms, "nb_tc_fwd_kernel")
+        roof.update({"peak_source": peak_src,
+                     "note": "algorithmic bytes by SURVEY 8(d) (forward-only sweep); the sweeps are bound by the SFU / issue pipes, not by HBM: "
+                             "`other` carries the MUFU roofline (8 ex2/lg2/rcp per element) and the training step's sweep(s); ncu counters under profiles/",
+                     "other": [mufu(kf, f_ms)]})
+        if single:
+            roof["other"] += [hbm(kt, alg_t, t_ms, "nb_tc_train_kernel"), mufu(kt, t_ms)]
+        else:
+            roof["other"] += [hbm(kt, alg_f, t_ms, "nb_tc_fwd_kernel"), hbm(kb, alg_b, b_ms, "nb_tc_bwd_kernel"), mufu(kb, b_ms)]
+        roof["sweeps_per_training_step"] = 1 if single else 2
         # the step's HBM-bound kernel for comparison: Adam over the whole flat parameter vector (28 bytes per parameter + staging)
-        ad_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(8)]
+        ad_ev = mk(8)
         for a, b in ad_ev:
             a.record()
             eng.adam_step(lr=0.0, eps=0.01, weight_decay=0.0)

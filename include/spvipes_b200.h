@@ -233,8 +233,9 @@ int spv_dec_stats_tc(void* zc_f16, const void* wz_f16, int Gp, const float* gene
 /* count tables of the tensor-core likelihood sweeps (csrc/decoder_common.cuh NB_TAB = 16 entries per gene, float2 each):
  * tgf[g][c] = (log1p(c), lgamma(log1p(c) + theta_g) - lgamma(theta_g) - lgamma(log1p(c) + 1)), tgb[g][c] = (log1p(c),
  * digamma(log1p(c) + theta_g) - digamma(theta_g)), theta = exp(px_r) (module/spVIPESmodule.py:758).  They depend on the
- * parameter only; either pointer may be NULL.  16-byte aligned. */
-int spv_dec_theta_tables(const float* px_r, int G, void* tgf, void* tgb, void* stream);
+ * parameter only; any of the pointers may be NULL.  tb1 [G, 16] floats: the digamma terms alone (training sweep).  16-byte
+ * aligned. */
+int spv_dec_theta_tables(const float* px_r, int G, void* tgf, void* tgb, float* tb1, void* stream);
 /* floats spv_dec_nb_fwd_tc needs in part_nb (ptrs[11]) for a [B, G] problem */
 long long spv_dec_nb_part_floats(int B, int G);
 /* rec[b] (ptrs[16] of the forward) and the softmax-backward row sums rowc[:, 2:4] from the row partials part_nb that
@@ -253,7 +254,7 @@ int spv_dec_nb_bwd_tc(int src, const void* const* ptrs, long long ldx, const voi
  * vpart [parts, P+S], mpart [parts, (P+S)^2] with parts = spv_dec_gene_bwd_parts(G)
  * (backward of nn/networks.py:314-320 through the folded BatchNorm) */
 int spv_dec_gene_bwd_parts(int G);
-int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, int G, int P, int S, void* stream);
+int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, int G, int P, int S, int colsum_in_q, void* stream);
 /* d zz = dmix (latent columns of d [hm | zz]; NULL = none) + dzraw (optional further addends [B, P+S]: softmax-branch and hidden-layer
  * input gradients when they are not in dmix) - BatchNorm coupling terms, the latter summed from the `nparts` per-CTA
  * partials (vpart [nparts, P+S], mpart [nparts, (P+S)^2]) that spv_dec_gene_bwd writes (its last two ptrs).
@@ -280,6 +281,27 @@ int spv_adam(float* p, const float* g, float* m, float* v, long long n, float lr
              float grad_scale, int* step, int* ticket, int nseg, const long long* seg_begin, const int* seg_rows,
              const int* seg_cols, void* const* seg_dst, void* const* seg_dst_lo, const int* seg_f16, const long long* seg_ld,
              int max_blocks, void* stream);
+
+/* TRAINING sweep of the tensor-core decoder + likelihood (csrc/nb_tc_train.cu): spv_dec_nb_fwd_tc's outputs (row partials ->
+ * spv_dec_nb_rowreduce) plus everything the backward needs, so that a training step sweeps the [B, G] problem once:
+ *   e4t  [Gp, ld_e4 >= 4 B] fp16, gene-major, per cell (ep, rp', es, rs'): the branch gradients without the softmax coupling
+ *        and 4096 x the softmax values;  d ll / d y_p = ep - rp' Dp / 4096 (Dp = rowc[:, 2] once the row reduction has run)
+ *   dpit [Gp, ld_dpi >= B] fp16: d ll / d pi
+ *   ptrs[15] = colpart [ceil(B/128), 2, G]: per-row-tile column sums of d pi and d theta -> spv_dec_nb_train_colsum
+ * ptrs as spv_dec_nb_fwd_tc plus [7] = lib, [18] = tb1 (spv_dec_theta_tables).  The buffers must be zero-initialised once (rows
+ * >= G and cells >= B are never written); pitches multiples of 8.  Autograd of nn/networks.py:314-325 + scvi log_mixture_nb. */
+int spv_dec_nb_train_tc(int src, const void* const* ptrs, long long ldx, const void* amix_f16, long long ld_amixb,
+                        const void* wstack_f16, long long ld_w, int Gp, const void* zc_f16, const void* wz_f16, void* e4t,
+                        long long ld_e4, void* dpit, long long ld_dpi, int B, int G, int HD, int P, int S, int kmix, void* stream);
+/* colsum [2, G] = scale x column sums of (d ll / d pi, d ll / d theta) from colpart of spv_dec_nb_train_tc */
+int spv_dec_nb_train_colsum(const float* colpart, int B, int G, float scale, float* colsum, void* stream);
+/* zq [4 Bp, ldq] fp16, rows 4b .. 4b+3 = [zp 1 0 0], -Dp' [zp 1 0 0], [0 0 zs 1], -Ds' [0 0 zs 1] (zp / zs: the regressors' inputs
+ * zb[b, 0:Pb] / zb[b, Pb:Pb+Sb], D' = rowc[b, 2 or 3] / 4096): E4T . zq = [Qp | colsum dyp | Qs | colsum dys] with the softmax
+ * coupling applied */
+int spv_dec_zq4(const float* zb, long long ld_zb, const float* rowc, void* zq, long long ldq, int B, int Pb, int Sb, void* stream);
+/* out [B, Pb + Sb] = softmax-branch part of d zz from T [4 B, ld_t] = E4T^T [W'p | W's]: T[4b + k] - D' T[4b + k + 1] */
+int spv_dec_dz4_combine(const float* T, long long ld_t, const float* rowc, float* out, long long ld_out, int B, int Pb, int Sb,
+                        void* stream);
 
 /* Data-parallel gradient all-reduce as ONE kernel per parameter range over NVLink 5 / NVSwitch, capturable inside the step's
  * CUDA graph (the reference is single-device).  In-place sum over ranks of floats

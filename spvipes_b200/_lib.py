@@ -61,11 +61,15 @@ _SIGS = {
     "spv_dec_nb_fwd_tc": [i, p, ll, p, ll, p, ll, i, p, p, i, i, i, i, i, i, i, p],
     "spv_dec_nb_rowreduce": [p, i, i, i, p, p, p],
     "spv_dec_nb_bwd_tc": [i, p, ll, p, ll, p, ll, i, p, p, p, ll, i, i, i, i, i, f, p, i, p],
-    "spv_dec_gene_bwd": [p, ll, i, i, i, i, p],
+    "spv_dec_gene_bwd": [p, ll, i, i, i, i, i, p],
     "spv_dec_gene_bwd_parts": [i],
     "spv_dec_nb_part_floats": [i, i],
     "spv_dec_stats_tc": [p, p, i, p, p, p, p, i, i, i, i, p],
-    "spv_dec_theta_tables": [p, i, p, p, p],
+    "spv_dec_theta_tables": [p, i, p, p, p, p],
+    "spv_dec_nb_train_tc": [i, p, ll, p, ll, p, ll, i, p, p, p, ll, p, ll, i, i, i, i, i, i, p],
+    "spv_dec_nb_train_colsum": [p, i, i, f, p, p],
+    "spv_dec_zq4": [p, ll, p, p, ll, i, i, i, p],
+    "spv_dec_dz4_combine": [p, ll, p, p, ll, i, i, i, p],
     "spv_to_bf16_block": [p, ll, p, ll, i, i, i, p],
     "spv_dec_dzz_combine": [p, ll, p, p, p, i, p, ll, p, p, i, i, i, p, p],
     "spv_adam_tick": [p, p],

@@ -323,7 +323,7 @@ __device__ double digamma_d(double x) {
 }
 
 __global__ void __launch_bounds__(256) theta_tables_kernel(const float* __restrict__ px_r, int G, float2* __restrict__ tgf,
-                                                           float2* __restrict__ tgb) {
+                                                           float2* __restrict__ tgb, float* __restrict__ tb1) {
     const int i = blockIdx.x * 256 + threadIdx.x;  // entry (gene, count): 16 consecutive threads share a gene
     const int g = i / NB_TAB, c = i - g * NB_TAB;
     if (g >= G) return;
@@ -338,12 +338,13 @@ __global__ void __launch_bounds__(256) theta_tables_kernel(const float* __restri
     }
     if (tgf) tgf[i] = f;
     if (tgb) tgb[i] = b;
+    if (tb1) tb1[i] = b.y;
 }
 
-extern "C" int spv_dec_theta_tables(const float* px_r, int G, void* tgf, void* tgb, void* stream) {
-    if (!px_r || G <= 0 || (!tgf && !tgb)) return SPV_ERR_ARG;
+extern "C" int spv_dec_theta_tables(const float* px_r, int G, void* tgf, void* tgb, float* tb1, void* stream) {
+    if (!px_r || G <= 0 || (!tgf && !tgb && !tb1)) return SPV_ERR_ARG;
     theta_tables_kernel<<<(G * NB_TAB + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        px_r, G, reinterpret_cast<float2*>(tgf), reinterpret_cast<float2*>(tgb));
+        px_r, G, reinterpret_cast<float2*>(tgf), reinterpret_cast<float2*>(tgb), tb1);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
 }
@@ -396,6 +397,7 @@ extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int
 struct GeneBwdP {
     const float *Wp, *Ws, *Qp, *Qs, *zmean, *zcov;
     const float* vec[11];  // per-gene vectors: genec a_p, a_s, invstd_p, invstd_s, mean_p, mean_s, theta; colsum rows 0..3
+    long vstride[11];      // element stride of each (1; ldq for the two branch column sums when they ride behind Qp / Qs)
     float *dWp, *dWs, *dgp, *dbp, *dgs, *dbs, *dpx_r, *dbm, *vpart, *mpart;
     int G, P, S, B;
     long ldq;  // row pitch of Qp / Qs (0: packed, P resp. S)
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(GENE_BWD_THREADS) gene_bwd_kernel(GeneBwdP p) 
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int i = u * GENE_BWD_THREADS + (int)threadIdx.x, arr = i >> 5, gl = i & 31;
-            sc[u] = (arr < 11 && gl < ng) ? __ldg(p.vec[arr] + g0 + gl) : 0.0f;
+            sc[u] = (arr < 11 && gl < ng) ? __ldg(p.vec[arr] + (long)(g0 + gl) * p.vstride[arr]) : 0.0f;
         }
         c.store(scov, KZ * KZ);
         m.store(smean, KZ);
@@ -544,7 +546,9 @@ extern "C" int spv_dec_gene_bwd_parts(int G) { return G > 0 ? (G + GENES_PER_CTA
 
 // ptrs: Wp, Ws, Qp, Qs, genec, colsum, zmean, zcov, dWp, dWs, dgamma_p, dbeta_p, dgamma_s, dbeta_s, dpx_r, dbm,
 //       vpart [parts, KZ], mpart [parts, KZ*KZ]   with parts = spv_dec_gene_bwd_parts(G)
-extern "C" int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, int G, int P, int S, void* stream) {
+// colsum_in_q != 0 (needs ldq > 0): the column sums of dyp / dys are not rows 0 / 1 of colsum but the column right behind each Q
+// block, Qp[g * ldq + P] and Qs[g * ldq + S] (the ones column of the single-sweep Q GEMM, spv_dec_zq4)
+extern "C" int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, int G, int P, int S, int colsum_in_q, void* stream) {
     if (!ptrs || B <= 0 || G <= 0 || P <= 0 || S <= 0 || P + S > 96) return SPV_ERR_ARG;
     for (int i = 0; i < 18; ++i)
         if (!ptrs[i]) return SPV_ERR_ARG;
@@ -555,6 +559,12 @@ extern "C" int spv_dec_gene_bwd(const void* const* ptrs, long long ldq, int B, i
     const int gc_rows[7] = {GC_AP, GC_AS, GC_ISTD_P, GC_ISTD_S, GC_MEAN_P, GC_MEAN_S, GC_THETA};
     for (int i = 0; i < 7; ++i) p.vec[i] = genec + (long)gc_rows[i] * G;
     for (int i = 0; i < 4; ++i) p.vec[7 + i] = colsum + (long)i * G;
+    for (int i = 0; i < 11; ++i) p.vstride[i] = 1;
+    if (colsum_in_q) {
+        if (ldq <= 0) return SPV_ERR_ARG;
+        p.vec[7] = p.Qp + P; p.vec[8] = p.Qs + S;
+        p.vstride[7] = p.vstride[8] = ldq;
+    }
     p.zmean = (const float*)ptrs[6];
     p.zcov = (const float*)ptrs[7]; p.dWp = (float*)ptrs[8]; p.dWs = (float*)ptrs[9]; p.dgp = (float*)ptrs[10];
     p.dbp = (float*)ptrs[11]; p.dgs = (float*)ptrs[12]; p.dbs = (float*)ptrs[13]; p.dpx_r = (float*)ptrs[14];

@@ -10,6 +10,7 @@ torch is used for device memory and streams only; every arithmetic step is a lau
 from __future__ import annotations
 
 import contextlib
+import os
 import math
 from collections import OrderedDict
 from dataclasses import dataclass, field
@@ -195,7 +196,7 @@ class Noise:
 
 
 class _GroupWS:
-    def __init__(self, B, G, d: Dims, dev, with_grad: bool, bf16: bool = False, wb=None, dec_dtype=torch.bfloat16):
+    def __init__(self, B, G, d: Dims, dev, with_grad: bool, bf16: bool = False, wb=None, dec_dtype=torch.bfloat16, single_sweep=False):
         H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         self.B, self.G = B, G
@@ -246,7 +247,8 @@ class _GroupWS:
             self.zcb = torch.zeros(B, 64, dtype=torch.float16, device=dev)
             self.wzf = torch.zeros(2 * self.Gp, 64, dtype=torch.float16, device=dev)
             # count tables of the likelihood sweeps (spv_dec_theta_tables): [G, 16] float2 each, forward / backward
-            self.tgf, self.tgb = f(G, 16, 2), (f(G, 16, 2) if with_grad else None)
+            self.tgf, self.tgb = f(G, 16, 2), (f(G, 16, 2) if (with_grad and not single_sweep) else None)
+            self.tb1 = f(G, 16) if (with_grad and single_sweep) else None  # digamma terms alone (training sweep)
             # bf16 weight operands are per engine (shared by every workspace): W1b [2H, Gp] and the stacked operand
             # Wstack [3 Gp, KMp]: rows [0, G) mixture weight, [Gp, Gp+G) / [2Gp, 2Gp+G) the folded private / shared
             # factor-regressor weights of the current minibatch in the latent columns (zero elsewhere)
@@ -257,10 +259,22 @@ class _GroupWS:
                 # D3T [3 Gp, Bp] = [dpi ; dyp ; dys] (coalesced stores from the TMEM epilogue, thread = cell); unfused path: cell-major
                 # [B, 3 Gp], only the first Gp columns used
                 self.Bp = r8(B)
-                self.D3, self.dh1b = hd(3 * self.Gp * self.Bp).view(-1), h(B, 2 * H)
-                self.dh1b_lo = h(B, 2 * H)
-                self.dpib = self.D3.view(-1)[:B * 3 * self.Gp].view(B, 3 * self.Gp)
-                self.CQ = f(2 * self.Gp, KZb)
+                self.dh1b, self.dh1b_lo = h(B, 2 * H), h(B, 2 * H)
+                if single_sweep:
+                    # outputs of the training sweep (csrc/nb_tc_train.cu), gene-major fp16: E4T [Gp, 4 Bp] = (ep, rp', es, rs') per
+                    # cell, DPIT [Gp, Bp] = d ll / d pi; and the small operands / results of the single-sweep backward
+                    self.E4T, self.DPIT = hd(self.Gp * 4 * self.Bp), hd(self.Gp * self.Bp)
+                    self.ldq4 = r8(KZb + 2)
+                    self.ZQ4 = hd(4 * self.Bp, self.ldq4)
+                    self.CQ = f(self.Gp, KZb + 2)        # [Qp | colsum dyp | Qs | colsum dys]
+                    self.T4 = f(4 * self.Bp, KZb)
+                    self.Wcomb = hd(self.Gp, r8(KZb))    # [W'p | W's] (fp16 copy of wfold)
+                    self.tc_splits_dz4 = max(1, min(148 // ((4 * B + 127) // 128), (self.Gp + 63) // 64 // 2))
+                    self.D3 = None
+                else:
+                    self.D3 = hd(3 * self.Gp * self.Bp).view(-1)
+                    self.dpib = self.D3.view(-1)[:B * 3 * self.Gp].view(B, 3 * self.Gp)
+                    self.CQ = f(2 * self.Gp, KZb)
             # split-K factors of the tensor-core GEMMs (128-wide tiles): fill the 148 SMs
             tiles = ((B + 127) // 128) * ((2 * H + 127) // 128)
             self.tc_splits_fc1 = max(1, min(148 // tiles, (G + 63) // 64 // 2))
@@ -309,6 +323,9 @@ class StepEngine:
         self.fused_nb = self.bf16 and int(n_shared) + int(n_private) + 2 * nb_cols <= 64
         # operands of the decoder GEMMs: fp16 on the fused path (2^-12 rounding, three bits more than bf16; every operand's range
         # is bounded: activations after BatchNorm, weights, gradients stored in natural units), bf16 on the unfused fallback
+        # one sweep over [B, G] per training step: the forward sweep also emits what the backward needs (csrc/nb_tc_train.cu);
+        # SPV_NB_SWEEPS=2 keeps the separate backward sweep (csrc/nb_tc_bwd.cu) for A/B measurements
+        self.single_sweep = self.fused_nb and os.environ.get("SPV_NB_SWEEPS", "1") != "2"
         self.dec_dtype = torch.float16 if self.fused_nb else torch.bfloat16
         self.dec_fmt = 3 if self.fused_nb else 0
         self.lib = L.load()
@@ -473,11 +490,11 @@ class StepEngine:
             for ev in self._pending.pop(key):
                 cur.wait_event(ev)
 
-    def _gene_bwd(self, g, w, Qp, Qs, ldq, B, G):
+    def _gene_bwd(self, g, w, Qp, Qs, ldq, B, G, colsum_in_q=0):
         gb = L.ptr_array([self.P(g, "Wp"), self.P(g, "Ws"), Qp, Qs, w.genec, w.colsum, w.zmean, w.zcov,
                           self.Gd(g, "Wp"), self.Gd(g, "Ws"), self.Gd(g, "gp"), self.Gd(g, "bp"), self.Gd(g, "gs"),
                           self.Gd(g, "bs"), self.Gd(g, "px_r"), self.Gd(g, "bm"), w.vpart, w.mpart])
-        L.check(self.lib.spv_dec_gene_bwd(gb, ldq, B, G, self.d.Pb, self.d.Sb, self._stream()), "spv_dec_gene_bwd")
+        L.check(self.lib.spv_dec_gene_bwd(gb, ldq, B, G, self.d.Pb, self.d.Sb, colsum_in_q, self._stream()), "spv_dec_gene_bwd")
 
     def _hidden_mix(self, g, w, B, tr, zzp):
         """hm = relu(BatchNorm(zz Wh^T + bh)) into the first HD columns of amix   (reference nn/networks.py:322-323)"""
@@ -494,7 +511,7 @@ class StepEngine:
         key = (B0, B1, with_grad)
         if key not in self._ws:
             self._ws[key] = [_GroupWS(B, G, self.d, self.device, with_grad, self.bf16, self.wb[g] if self.bf16 else None,
-                                      self.dec_dtype) for g, (B, G) in enumerate(zip((B0, B1), self.d.genes))]
+                                      self.dec_dtype, self.single_sweep) for g, (B, G) in enumerate(zip((B0, B1), self.d.genes))]
         return self._ws[key]
 
     @staticmethod
@@ -665,7 +682,7 @@ class StepEngine:
             if self.fused_nb:
                 # count tables of the likelihood sweeps: a function of px_r only, on the second auxiliary stream
                 with self._branch(g, "tg", lane=1):
-                    L.check(lib.spv_dec_theta_tables(L.ptr(self.P(g, "px_r")), G, L.ptr(w.tgf), L.ptr(w.tgb) if with_grad else None,
+                    L.check(lib.spv_dec_theta_tables(L.ptr(self.P(g, "px_r")), G, L.ptr(w.tgf), L.ptr(w.tgb), L.ptr(w.tb1),
                                                      self._stream()), "spv_dec_theta_tables")
                 # hidden layer of the mixing net (needs only zz) on the auxiliary stream, beside latent stats / fold / normalisers;
                 # the bf16 operand [hm | zz] of the mixture GEMM in one conversion pass after it
@@ -697,8 +714,13 @@ class StepEngine:
                 evs[0].record()
             if self.bf16:
                 if self.fused_nb:
-                    L.check(lib.spv_dec_nb_fwd_tc(src, dptrs, ldx, L.ptr(w.amixb), w.KMp, L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.zcb),
-                                                  L.ptr(w.wzf), B, G, HD, Pb, Sb, 0, KMIX, st), "spv_dec_nb_fwd_tc")  # backward recomputes pi
+                    if self.single_sweep and training and with_grad:  # one sweep: likelihood + everything the backward needs
+                        L.check(lib.spv_dec_nb_train_tc(src, dptrs, ldx, L.ptr(w.amixb), w.KMp, L.ptr(w.Wstack), w.KMp, w.Gp,
+                                                        L.ptr(w.zcb), L.ptr(w.wzf), L.ptr(w.E4T), 4 * w.Bp, L.ptr(w.DPIT), w.Bp, B, G, HD,
+                                                        Pb, Sb, KMIX, st), "spv_dec_nb_train_tc")
+                    else:
+                        L.check(lib.spv_dec_nb_fwd_tc(src, dptrs, ldx, L.ptr(w.amixb), w.KMp, L.ptr(w.Wstack), w.KMp, w.Gp, L.ptr(w.zcb),
+                                                      L.ptr(w.wzf), B, G, HD, Pb, Sb, 0, KMIX, st), "spv_dec_nb_fwd_tc")  # backward recomputes pi
                     if evs is not None:
                         evs[1].record()
                         evs = None
@@ -721,7 +743,8 @@ class StepEngine:
         wg = with_grad
         return L.ptr_array([xptr, rows, w.amix, w.wfold, self.P(g, "Wm"), self.P(g, "bm"), w.genec, w.lib, w.part_stats,
                             w.rowc, w.pi, w.part_nb, w.dyp if wg else None, w.dys if wg else None, w.dpi if wg else None,
-                            w.colpart if wg else None, w.rec, getattr(w, "tgf", None), getattr(w, "tgb", None)])
+                            w.colpart if wg else None, w.rec, getattr(w, "tgf", None),
+                            getattr(w, "tb1", None) if self.single_sweep else getattr(w, "tgb", None)])
 
     def _pairing(self, batches, ws, Bs):
         lib, st, d = self.lib, self._stream(), self.d
@@ -835,7 +858,32 @@ class StepEngine:
             zzp = w.amix.data_ptr() + 4 * HD
             nb, Pb, Sb, KZb = d.nb, d.Pb, d.Sb, d.KZb
             zb, ld_zb = (L.ptr(w.zzb), KZb) if nb else (zzp, KMIX)
-            if self.fused_nb:
+            if self.fused_nb and self.single_sweep:
+                # the training sweep of the forward left E4T = (ep, rp', es, rs') and DPIT = d ll / d pi (fp16, gene-major): the
+                # backward of the likelihood is four GEMMs; the softmax coupling rides in their small operands (csrc/nb_tc_train.cu)
+                f3, al = self.dec_fmt, -float(grad_scale) / B
+                Bp, ldq = w.Bp, KZb + 2
+                L.check(lib.spv_dec_nb_train_colsum(L.ptr(w.colpart), B, G, al, w.colsum.data_ptr() + 4 * 2 * G, st), "spv_dec_nb_train_colsum")
+                with self._branch(g, "dzg"):  # d zz through the two softmax branches: T = E4T^T [W'p | W's], then the row combination
+                    self._to_dec(L.ptr(w.wfold), KZb, L.ptr(w.Wcomb), w.Wcomb.stride(0), G, KZb)
+                    self._tc_gemm(L.ptr(w.E4T), L.ptr(w.Wcomb), L.ptr(w.T4), 4 * B, KZb, w.Gp, lda=4 * Bp, ldb=w.Wcomb.stride(0), ldc=KZb,
+                                  a_mn=1, b_mn=1, splits=w.tc_splits_dz4, ws=w.ws2, fmt=f3, alpha=al)
+                    L.check(lib.spv_dec_dz4_combine(L.ptr(w.T4), KZb, L.ptr(w.rowc), L.ptr(w.dzraw), KZb, B, Pb, Sb, self._stream()),
+                            "spv_dec_dz4_combine")
+                with self._branch(g, "wgrad"):  # d Wm = dpi^T [hm | zz]
+                    self._tc_gemm(L.ptr(w.DPIT), L.ptr(w.amixb), L.ptr(self.Gd(g, "Wm")), G, KMIX, B, lda=Bp, ldb=w.KMp, ldc=KMIX,
+                                  a_mn=0, b_mn=1, fmt=f3, alpha=al)
+                with self._branch(g, "gene", lane=1):
+                    # [Qp | sum dyp | Qs | sum dys] = E4T . ZQ4 (K = 4 B: the coupling -D' [z 1] rides in ZQ4's odd rows)
+                    L.check(lib.spv_dec_zq4(zb, ld_zb, L.ptr(w.rowc), L.ptr(w.ZQ4), w.ldq4, B, Pb, Sb, self._stream()), "spv_dec_zq4")
+                    self._tc_gemm(L.ptr(w.E4T), L.ptr(w.ZQ4), L.ptr(w.CQ), G, ldq, 4 * B, lda=4 * Bp, ldb=w.ldq4, ldc=ldq,
+                                  a_mn=0, b_mn=1, fmt=f3, alpha=al)
+                    self._gene_bwd(g, w, w.CQ.data_ptr(), w.CQ.data_ptr() + 4 * (Pb + 1), ldq, B, G, colsum_in_q=1)
+                Qp, Qs, dzraw = None, None, None
+                # d [hm | zz] (mixture part) = dpi Wm
+                self._tc_gemm(L.ptr(w.DPIT), L.ptr(w.Wstack), L.ptr(w.damix), B, KMIX, G, lda=Bp, ldb=w.KMp, ldc=KMIX, a_mn=1, b_mn=1,
+                              splits=w.tc_splits_damix, ws=w.ws, fmt=f3, alpha=al)
+            elif self.fused_nb:
                 # logits recomputed on the tensor cores, gradients in the TMEM epilogue -> D3 = [dpi | dyp | dys] (bf16)
                 evs = next(self.nb_bwd_events) if self.nb_bwd_events is not None else None
                 if evs is not None:

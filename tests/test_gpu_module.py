@@ -257,7 +257,7 @@ def test_model_api_cluster_mode_derives_transport_labels():
         ads[key] = GroupedData(X=data.X[gi].cpu().numpy().astype(np.float32), obs=pd.DataFrame({"dummy": np.zeros(n[gi])}),
                                var_names=[f"g{j}" for j in range(G[gi])])
     adata = prepare_adatas(ads)
-    plan = synth.make_plan(n[0], n[1], data.labels[0], data.labels[1], 3, device="cpu", seed=3)
+    plan = synth.make_plan(n[0], n[1], data.labels[0].cpu(), data.labels[1].cpu(), 3, device="cpu", seed=3)
     adata.uns["transport_plan"] = plan.numpy()
     spVIPES.setup_anndata(adata, groups_key="groups", transport_plan_key="transport_plan", match_clusters=True)
     lab = adata.obs["processed_transport_labels"]

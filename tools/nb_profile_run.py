@@ -1,6 +1,6 @@
 """small driver for ncu: a few eager training steps at a BASELINE minibatch shape (C5 by default) on a reduced resident matrix.
     python tools/nb_profile_run.py [C5|C2] && ncu --set full --clock-control none --import-source on --profile-from-start off \
-        -k regex:"nb_tc_(fwd|bwd)" -c 4 -o gpurun_out/prof python tools/nb_profile_run.py"""
+        -k regex:"nb_tc_(fwd|bwd|train)" -c 4 -o gpurun_out/prof python tools/nb_profile_run.py"""
 import sys
 import torch
 sys.path.insert(0, ".")

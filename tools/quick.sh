@@ -9,6 +9,6 @@ import sys, json
 for l in open(sys.argv[1]):
     if l.startswith('{'):
         d = json.loads(l); r = d['roofline']
-        print(sys.argv[2], 'value', int(d['value']), 'ms', round(d['ms_per_step'], 4), 'nb fwd', round(r['avg_launch_ms'], 4), 'bwd', round(r['other'][1]['avg_launch_ms'], 4), 'loss', d.get('final_loss'))
+        print(sys.argv[2], 'value', int(d['value']), 'ms', round(d['ms_per_step'], 4), 'nb fwd-only', round(r['avg_launch_ms'], 4), 'other', [(o['kernel'][:14], o['bound'], round(o['avg_launch_ms'], 4)) for o in r['other']], 'loss', d.get('final_loss'))
 PY
 done
