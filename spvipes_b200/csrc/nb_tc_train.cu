@@ -290,11 +290,19 @@ __global__ void __launch_bounds__(THREADS, 3) nb_tc_train_kernel(const __grid_co
         for (int u = 0; u < 2; ++u) reinterpret_cast<float4*>(s_tg)[et + u * EPI_THREADS] = tgv[u];
         const float c_row = 4096.0f * fast_exp(-libm);  // rho -> 4096 x softmax value: fp16-safe whatever the library size
         const long xrow = (long)my_row * p.ldx;
-        tc::mbar_wait(tmem_ready, 0);
+        // One epilogue warp polls the two mbarriers; the other seven block in a named barrier, where they cost no issue slots (a
+        // CTA waiting for its tensor-memory grant spends most of its life here: eight polling warps took a quarter of the SM's
+        // issued instructions away from the two CTAs doing the math - profiles/r2_nb_ncu.md)
+        if (e == 0) {
+            tc::mbar_wait(tmem_ready, 0);
+            tc::mbar_wait(tmem_full, 0);  // accumulators complete; the operand stages are free from here on
+            tc::fence_after_sync();
+        }
+        tc::fence_before_sync();
+        asm volatile("bar.sync 2, %0;" ::"r"(EPI_THREADS) : "memory");
+        tc::fence_after_sync();
         tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
         tmem_z = *reinterpret_cast<volatile uint32_t*>(tmem_slot + 1);
-        tc::mbar_wait(tmem_full, 0);  // accumulators complete; the operand stages are free from here on
-        tc::fence_after_sync();
 #pragma unroll
         for (int i = 0; i < NGATHER; ++i) s_cnt[cnt_row(e, lane, i) * CNT_PITCH_W + lane % (BN / 2)] = cw[i];
         reinterpret_cast<float4*>(s_tb)[et] = tbv;

@@ -195,6 +195,22 @@ class Noise:
     drop: Optional[Sequence[torch.Tensor]] = None          # per group [B, 2H] multipliers (private | shared)
 
 
+def _pick_splits(tiles: int, num_kb: int, sms: int = 148, min_kb: int = 4, max_splits: int = 16) -> int:
+    """split-K factor of a GEMM whose output tiles do not fill the SMs evenly: the smallest factor (each split keeps >= min_kb
+    k-blocks) whose CTA count wastes the least of its last wave; 157 tiles on 148 SMs run two rounds unsplit, 942 CTAs run 6.4"""
+    best, best_eff = 1, 0.0
+    for sp in range(1, max_splits + 1):
+        if sp > 1 and num_kb // sp < min_kb:
+            break
+        ctas = tiles * sp
+        eff = ctas / (math.ceil(ctas / sms) * sms)
+        if eff >= 0.9:  # good enough: more splits only add partial-sum traffic
+            return sp
+        if eff > best_eff + 0.02:
+            best, best_eff = sp, eff
+    return best
+
+
 class _GroupWS:
     def __init__(self, B, G, d: Dims, dev, with_grad: bool, bf16: bool = False, wb=None, dec_dtype=torch.bfloat16, single_sweep=False):
         H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST
@@ -270,6 +286,11 @@ class _GroupWS:
                     self.T4 = f(4 * self.Bp, KZb)
                     self.Wcomb = hd(self.Gp, r8(KZb))    # [W'p | W's] (fp16 copy of wfold)
                     self.tc_splits_dz4 = max(1, min(148 // ((4 * B + 127) // 128), (self.Gp + 63) // 64 // 2))
+                    # unsplit by default: measured on B200 at C5, 157 CTAs that leave SMs to the kernels running beside this GEMM give
+                    # a faster STEP (1.85 ms) than 942 evenly filling ones (1.89 ms); _pick_splits stays for A/B (SPV_Q4_SPLITS=auto)
+                    q4 = os.environ.get("SPV_Q4_SPLITS", "1")
+                    self.tc_splits_q4 = _pick_splits((G + 127) // 128, (4 * B + 63) // 64) if q4 == "auto" else max(1, int(q4))
+                    self.ws_q4 = f(max(1, self.tc_splits_q4 * G * (KZb + 2))) if self.tc_splits_q4 > 1 else None
                     self.D3 = None
                 else:
                     self.D3 = hd(3 * self.Gp * self.Bp).view(-1)
@@ -877,7 +898,7 @@ class StepEngine:
                     # [Qp | sum dyp | Qs | sum dys] = E4T . ZQ4 (K = 4 B: the coupling -D' [z 1] rides in ZQ4's odd rows)
                     L.check(lib.spv_dec_zq4(zb, ld_zb, L.ptr(w.rowc), L.ptr(w.ZQ4), w.ldq4, B, Pb, Sb, self._stream()), "spv_dec_zq4")
                     self._tc_gemm(L.ptr(w.E4T), L.ptr(w.ZQ4), L.ptr(w.CQ), G, ldq, 4 * B, lda=4 * Bp, ldb=w.ldq4, ldc=ldq,
-                                  a_mn=0, b_mn=1, fmt=f3, alpha=al)
+                                  a_mn=0, b_mn=1, splits=w.tc_splits_q4, ws=w.ws_q4, fmt=f3, alpha=al)
                     self._gene_bwd(g, w, w.CQ.data_ptr(), w.CQ.data_ptr() + 4 * (Pb + 1), ldq, B, G, colsum_in_q=1)
                 Qp, Qs, dzraw = None, None, None
                 # d [hm | zz] (mixture part) = dpi Wm
