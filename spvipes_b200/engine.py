@@ -468,6 +468,8 @@ class StepEngine:
                 yield g
             return
         if self._side is None:
+            # (stream priorities were tried in r2 - main chains high, weight-gradient / optimiser lanes low: no effect on the replayed
+            # graph's step time at C5 or C2)
             self._side = [torch.cuda.Stream(device=self.device) for _ in (0, 1)]
         cur = torch.cuda.current_stream(self.device)
         fork = torch.cuda.Event()
