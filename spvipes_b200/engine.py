@@ -352,7 +352,10 @@ class StepEngine:
         self.lib = L.load()
         self.d = Dims(tuple(int(x) for x in genes), int(n_hidden), int(n_shared), int(n_private), int(n_batch))
         if self.d.n_private > self.d.n_shared:
-            raise ValueError("n_dimensions_private > n_dimensions_shared is not supported by the reference's latent slicing")
+            # the reference's slicing of [private | poe] (c[:, :S], c[:, S:S+P]) is defined for P > S as well; this implementation's
+            # zz column mapping covers P <= S (every BASELINE config and the reference's defaults, 10 / 25) - see INTEGRATION.md
+            raise NotImplementedError("n_dimensions_private > n_dimensions_shared is not implemented (the kernels' latent column "
+                                      "mapping covers n_dimensions_private <= n_dimensions_shared)")
         self.mode = mode
         self.mode_id = L.POE_MODES[mode]
         self.dropout_rate = float(dropout_rate)
