@@ -843,7 +843,8 @@ class StepEngine:
     # -------------------------------------------------------------------------------- backward
     def backward(self, grad_scale: float = 1.0, adam: Optional[dict] = None, stage: str = "all", tick: bool = False):
         """gradients of loss * grad_scale w.r.t. every parameter, written into self.grads.
-        adam (single-GPU training only: keys lr, betas, eps, weight_decay): also apply the optimiser step, per parameter range
+        adam (keys lr, betas, eps, weight_decay[, grad_scale]; data parallel: enc_only = True and sync = callable(g), which enqueues the
+        all-reduce of group g's encoder range on the current stream before its update): also apply the optimiser step, per parameter range
         as soon as its gradients are complete: the decoder ranges (55 % of the parameters) update on an auxiliary stream
         while the encoder backward, a chain of small latency-bound kernels that leaves HBM idle, is still running.
         stage: "all", or "decoder" (decoders + PoE: every decoder-range gradient final) followed by "encoder" - the
@@ -852,10 +853,12 @@ class StepEngine:
         ctx = self._ctx
         if ctx is None or not ctx["training"]:
             raise RuntimeError("backward needs a preceding training-mode forward")
-        if stage not in ("all", "decoder", "encoder") or (adam is not None and stage != "all"):
-            raise ValueError("stage must be 'all', 'decoder' or 'encoder' (the interleaved optimiser step needs 'all')")
+        if stage not in ("all", "decoder", "encoder") or (adam is not None and stage == "decoder") or \
+                (adam is not None and stage == "encoder" and not adam.get("enc_only")):
+            raise ValueError("stage must be 'all', 'decoder' or 'encoder' (the interleaved optimiser step needs 'all', or 'encoder' "
+                             "with adam['enc_only'])")
         tick_events = []
-        if adam is not None or (tick and stage != "encoder"):
+        if (adam is not None and not adam.get("enc_only")) or (tick and stage != "encoder"):  # (enc_only: the decoder stage ticked)
             if self.adam_m is None:
                 self.adam_m = torch.zeros_like(self.params.flat)
                 self.adam_v = torch.zeros_like(self.params.flat)
@@ -1054,7 +1057,7 @@ class StepEngine:
                 with self._branch(g, "dh2p"):  # first on its auxiliary stream: this one is on the critical path
                     self._gemm(L.ptr(w.dr), L.ptr(self.P(g, "Whp")), L.ptr(w.dh2), B, H, 2 * P, lda=NST, ldb=H, ldc=2 * H,
                                gate=gate_p)
-            if adam is not None:  # every decoder gradient of this group is final: update that range now
+            if adam is not None and not adam.get("enc_only"):  # every decoder gradient of this group is final: update that range now
                 self._join(g, "wgrad")
                 self._join(g, "wgrad1")
                 with self._branch(g, "adam", lane=1):
@@ -1112,6 +1115,8 @@ class StepEngine:
             if adam is not None:  # encoder range of this group
                 for ev in tick_events:
                     torch.cuda.current_stream(self.device).wait_event(ev)
+                if adam.get("sync") is not None:  # data parallel: sum this group's encoder gradients over the ranks first
+                    adam["sync"](g)
                 self._adam_range(*self.params.group_ranges[PHASE_ENC][g], adam)
 
     # -------------------------------------------------------------------------------- optimiser

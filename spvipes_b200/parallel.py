@@ -104,11 +104,15 @@ class NvlinkGradSync:
         engine.grads = self.buf  # the backward kernels now write the symmetric buffer directly
         self.ranges = dict(engine.params.ranges)
 
-    def allreduce(self, phase: int, channel: int):
+    def allreduce(self, phase: int, channel: int, blocks: int = 0):
+        self.allreduce_range(*self.ranges[phase], channel, blocks)
+
+    def allreduce_range(self, lo: int, hi: int, channel: int, blocks: int = 0):
+        """[lo, hi) of the flat gradient buffer (multiples of 4 floats: every block of the layout is 16-byte aligned).
+        blocks: CTAs of the exchange kernel (0: the synchroniser's default) - few when it runs beside compute it must not crowd out"""
         from . import _lib as L
-        lo, hi = self.ranges[phase]
         L.check(self.lib.spv_xgpu_allreduce(self.peer_bufs, self.peer_flags, self.mc, lo, hi - lo, self.rank, self.world, channel,
-                                            L.ptr(self.state), self.blocks, torch.cuda.current_stream(self.engine.device).cuda_stream),
+                                            L.ptr(self.state), blocks or self.blocks, torch.cuda.current_stream(self.engine.device).cuda_stream),
                 "spv_xgpu_allreduce")
 
     def check(self):

@@ -122,8 +122,10 @@ class TrainLoop:
     def _step_nvlink(self, e):
         """backward + gradient all-reduce + Adam of the data-parallel step, every launch on CUDA streams (capturable as one
         graph): decoder / PoE backward -> on a side stream [all-reduce of the decoder range (csrc/xgpu.cu) -> Adam on it] beside
-        the encoder backward on the main stream -> all-reduce of the encoder range -> Adam on it.  Adam folds the 1 / world
-        factor.  The decoder all-reduce always precedes the encoder one in every rank's launch order (channels 0 and 1)."""
+        the encoder backward -> per group, as soon as its encoder backward ends, [all-reduce of the group's encoder range -> Adam
+        on it] on the group's stream (the first group's exchange and update run beside the other group's first-layer weight
+        gradient).  Adam folds the 1 / world factor.  Channels: 0 decoder range, 1 / 2 the groups' encoder ranges; every rank
+        replays the same graph, so the launch order per channel is the same everywhere."""
         from .engine import PHASE_DEC, PHASE_ENC
         gs, dev = self.grad_sync, e.device
         kw = {"lr": self.lr, "eps": self.eps, "weight_decay": self.weight_decay, "grad_scale": 1.0 / gs.world}
@@ -135,12 +137,17 @@ class TrainLoop:
         fork.record(main)
         self._dp_stream.wait_event(fork)
         with torch.cuda.stream(self._dp_stream):
-            gs.allreduce(PHASE_DEC, 0)
+            gs.allreduce(PHASE_DEC, 0, blocks=int(os.environ.get("SPV_DP_BLOCKS_DEC", "8")))
             e.adam_range_step(PHASE_DEC, **kw)
             done.record(self._dp_stream)
-        e.backward(stage="encoder")
-        gs.allreduce(PHASE_ENC, 1)
-        e.adam_range_step(PHASE_ENC, **kw)
+        nb_enc = int(os.environ.get("SPV_DP_BLOCKS_ENC", "16"))
+        if os.environ.get("SPV_DP_ENC_SPLIT", "1") == "1":
+            enc = e.params.group_ranges[PHASE_ENC]
+            e.backward(stage="encoder", adam=dict(kw, enc_only=True, sync=lambda g: gs.allreduce_range(enc[g][0], enc[g][1], 1 + g, blocks=nb_enc)))
+        else:  # A/B: the whole encoder range in one exchange after both groups' backward
+            e.backward(stage="encoder")
+            gs.allreduce(PHASE_ENC, 1, blocks=nb_enc)
+            e.adam_range_step(PHASE_ENC, **kw)
         main.wait_event(done)
 
     def capture(self, batches: Sequence[GroupBatch], noise: Optional[Noise] = None) -> "torch.cuda.CUDAGraph":
