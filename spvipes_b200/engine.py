@@ -803,10 +803,13 @@ class StepEngine:
                                           L.ptr(aux["P1"]), L.ptr(aux["P2"]), st), "spv_plan_cluster_norm")
         S, P, NST = d.n_shared, d.n_private, d.NST
         # expert A = P1 @ stats_0[:, shared], expert B = P2 @ stats_1[:, shared]  (cross-indexing quirk Q5, :222, :228)
+        # (K = the other group's minibatch: split-K so that more than B / 64 CTAs share a 2048-deep reduction; nothing else uses
+        # the groups' split-K scratch at this point of the step)
+        sk = lambda K: max(1, min(8, K // 256))
         self._gemm(L.ptr(aux["P1"]), ws[0].stats.data_ptr() + 4 * 2 * P, L.ptr(ws[0].expert), Bs[0], 2 * S, Bs[1], lda=Bs[1],
-                   ldb=NST, ldc=2 * S)
+                   ldb=NST, ldc=2 * S, splits=sk(Bs[1]), ws=ws[0].ws)
         self._gemm(L.ptr(aux["P2"]), ws[1].stats.data_ptr() + 4 * 2 * P, L.ptr(ws[1].expert), Bs[1], 2 * S, Bs[0], lda=Bs[0],
-                   ldb=NST, ldc=2 * S)
+                   ldb=NST, ldc=2 * S, splits=sk(Bs[0]), ws=ws[1].ws)
         return aux
 
     def _pair_label(self, batches, ws, Bs):
@@ -1026,10 +1029,11 @@ class StepEngine:
                 "spv_poe_bwd")
         if self.mode == "cluster":
             # d stats_0[:, shared] += P1^T d expertA ;  d stats_1[:, shared] += P2^T d expertB   (quirk Q5)
+            sk = lambda K: max(1, min(8, K // 256))
             self._gemm(L.ptr(aux["P1"]), L.ptr(ws[0].dexpert), ws[0].dstats.data_ptr() + 4 * 2 * P, Bs[1], 2 * S, Bs[0],
-                       lda=Bs[1], ldb=2 * S, ldc=NST, ta=1, acc=1)
+                       lda=Bs[1], ldb=2 * S, ldc=NST, ta=1, acc=1, splits=sk(Bs[0]), ws=ws[0].ws)
             self._gemm(L.ptr(aux["P2"]), L.ptr(ws[1].dexpert), ws[1].dstats.data_ptr() + 4 * 2 * P, Bs[0], 2 * S, Bs[1],
-                       lda=Bs[0], ldb=2 * S, ldc=NST, ta=1, acc=1)
+                       lda=Bs[0], ldb=2 * S, ldc=NST, ta=1, acc=1, splits=sk(Bs[1]), ws=ws[1].ws)
     def _backward_encoders(self, ctx, grad_scale, adam, tick_events):
         d, st, lib = self.d, self._stream(), self.lib
         H, S, P, KZ, KMIX, NST = d.n_hidden, d.n_shared, d.n_private, d.KZ, d.KMIX, d.NST

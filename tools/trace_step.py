@@ -36,13 +36,20 @@ def main():
     n_cells = a.cells or n_cells
     L.load()
     data = synth.make_counts((n_cells, n_cells), (genes, genes), n_labels, device=dev, seed=1234)
-    eng = StepEngine((genes, genes), H, bench.S_DIM, bench.P_DIM, 0.1, mode, device=dev, seed=0, precision=a.precision)
+    plan = None
+    if mode != "label":  # OT modes: a plan over the cells held on the device, stored as the workload stores it
+        plan = synth.make_plan(n_cells, n_cells, data.labels[0], data.labels[1], n_labels, device=dev, seed=7, dtype=_plan_dtype)
+    eng = StepEngine((genes, genes), H, bench.S_DIM, bench.P_DIM, 0.1, mode, device=dev, seed=0, plan=plan, precision=a.precision)
     init_params(eng, 0)
     loop = TrainLoop(eng)
     loop.set_epoch(1)
     gen = torch.Generator(device=dev).manual_seed(5)
     rows_cur = [torch.randperm(n_cells, generator=gen, device=dev)[:B].to(torch.int32) for _ in (0, 1)]
-    batches = [GroupBatch(X=data.X[g], rows=rows_cur[g], labels=data.labels[g], labels_per_cell=True) for g in (0, 1)]
+    if mode == "label":
+        batches = [GroupBatch(X=data.X[g], rows=rows_cur[g], labels=data.labels[g], labels_per_cell=True) for g in (0, 1)]
+    else:
+        batches = [GroupBatch(X=data.X[g], rows=rows_cur[g], idx=rows_cur[g],
+                              labels=data.labels[g][rows_cur[g].long()].contiguous() if mode == "cluster" else None) for g in (0, 1)]
     graph = loop.capture(batches)
     for _ in range(20):
         graph.replay()
