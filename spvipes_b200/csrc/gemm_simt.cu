@@ -156,16 +156,21 @@ struct SkRound {
     }
 };
 
-template <bool TB>
+// RPT rows per thread: 8 x 64 tiles (RPT 1, the 512-row problems this kernel was written for) or 32 x 64 tiles (RPT 4, minibatches of
+// 1024+ rows: the weight tile is staged once per 32 rows instead of once per 8, and a thread's four rows share every weight
+// load - at 2048 rows and K = 256 the 8-row form moved 147 MB through L2 for 0.5 GFLOP).  The accumulation order per output element
+// is the same in both, so they agree bitwise.
+template <bool TB, int RPT>
 __global__ void __launch_bounds__(SK_THREADS) gemm_smallk_kernel(GemmParams p) {
+    constexpr int BM = SK_BM * RPT;
     extern __shared__ __align__(16) float sk_smem[];
     const int K4 = (p.K + 3) / 4, Kp = K4 * 4;
-    const int lda_s = Kp + 4;                   // A tile [SK_BM][Kp + 4]
+    const int lda_s = Kp + 4;                   // A tile [BM][Kp + 4]
     const int ldb_s = TB ? Kp + 4 : SK_BN + 4;  // B tile [SK_BN][Kp + 4] (TB) or [Kp][SK_BN + 4]
     float* As = sk_smem;
-    float* Bs = sk_smem + SK_BM * lda_s;
+    float* Bs = sk_smem + BM * lda_s;
     const int b = blockIdx.z;
-    const int m0 = blockIdx.y * SK_BM, n0 = blockIdx.x * SK_BN;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * SK_BN;
     const int nvalid = min(SK_BN, p.N - n0);
     const float* A = reinterpret_cast<const float*>(p.A) + (size_t)b * p.sA + (size_t)m0 * p.lda;
     const float* B = reinterpret_cast<const float*>(p.B) + (size_t)b * p.sB;
@@ -175,11 +180,11 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_smallk_kernel(GemmParams p) {
         const int b_rows = TB ? SK_BN : Kp, b_rows_valid = TB ? nvalid : p.K;
         const int b_cols4 = TB ? K4 : SK_BN / 4, b_cols_valid = TB ? p.K : nvalid;
         const int b_total = b_rows * b_cols4;
-        SkRound<SK_BM * SK_MAXK / 4 / SK_THREADS> ra;
+        SkRound<BM * SK_MAXK / 4 / SK_THREADS> ra;
         SkRound<SK_ROUND> rb;
-        ra.load(0, A, p.lda, SK_BM, min(SK_BM, p.M - m0), K4, p.K);
+        ra.load(0, A, p.lda, BM, min(BM, p.M - m0), K4, p.K);
         rb.load(0, Bsrc, p.ldb, b_rows, b_rows_valid, b_cols4, b_cols_valid);
-        ra.store(0, As, lda_s, SK_BM, K4);
+        ra.store(0, As, lda_s, BM, K4);
         rb.store(0, Bs, ldb_s, b_rows, b_cols4);
         for (int base = SK_ROUND * SK_THREADS; base < b_total; base += SK_ROUND * SK_THREADS) {
             rb.load(base, Bsrc, p.ldb, b_rows, b_rows_valid, b_cols4, b_cols_valid);
@@ -188,12 +193,12 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_smallk_kernel(GemmParams p) {
     }
     __syncthreads();
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;  // row ty; columns tx + 16 j (TB) or 4 tx + j
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* a0 = As + ty * lda_s;
+    float acc[RPT][4];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+    const float* a0 = As + ty * lda_s;  // rows ty + 8 r
 #pragma unroll 2
     for (int k = 0; k < Kp; k += 4) {
-        const float4 x0 = *reinterpret_cast<const float4*>(a0 + k);
-        const float xa[4] = {x0.x, x0.y, x0.z, x0.w};
         float wv[4][4];  // [kk][j]
         if (TB) {
 #pragma unroll
@@ -209,59 +214,75 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_smallk_kernel(GemmParams p) {
             }
         }
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
+        for (int r = 0; r < RPT; ++r) {
+            const float4 x0 = *reinterpret_cast<const float4*>(a0 + r * SK_BM * lda_s + k);
+            const float xa[4] = {x0.x, x0.y, x0.z, x0.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] = fmaf(xa[kk], wv[kk][j], acc[j]);
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[r][j] = fmaf(xa[kk], wv[kk][j], acc[r][j]);
+        }
     }
     float* C = p.C + (size_t)b * p.sC;
     const float* bias = p.bias ? p.bias + (size_t)b * p.sBias : nullptr;
-    const int m = m0 + ty;
-    if (m >= p.M) return;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int n = n0 + (TB ? tx + 16 * j : tx * 4 + j);
-        if (n >= p.N) continue;
-        float v = acc[j];
-        float* c = C + (size_t)m * p.ldc + n;
-        if (p.accumulate == 2) v += *c;
-        if (bias) v += __ldg(bias + n);
-        if (p.relu) v = fmaxf(v, 0.0f);
-        if (p.accumulate == 1) v += *c;
-        const long nn = (long)b * p.sC + n;  // column inside the full output matrix
-        if (p.gate_y) {
-            const float gm = p.gate_mask ? __ldg(p.gate_mask + (size_t)m * p.ld_mask + nn) : p.gate_scale;
-            v = __ldg(p.gate_y + (size_t)m * p.ld_gate + nn) > 0.0f ? v * gm : 0.0f;
-        }
-        if (p.drop_mask) {
-            v *= __ldg(p.drop_mask + (size_t)m * p.drop_ld + nn);
-        } else if (p.drop_p > 0.0f) {
-            const unsigned int stp = p.drop_step ? (unsigned int)*p.drop_step : 0u;
-            const float keep = 1.0f - p.drop_p;
-            v = philox_uniform(p.drop_seed, p.drop_stream, stp, (unsigned long long)((size_t)m * p.drop_ld + nn)) <= keep ? v * (1.0f / keep) : 0.0f;
-        }
-        *c = v;
-        if (p.c_bf16) {
-            const __nv_bfloat16 hi = __float2bfloat16(v);
-            p.c_bf16[(size_t)m * p.ld_cbf16 + nn] = hi;
-            if (p.c_bf16_lo) p.c_bf16_lo[(size_t)m * p.ld_cbf16 + nn] = __float2bfloat16(v - __bfloat162float(hi));
+    for (int r = 0; r < RPT; ++r) {
+        const int m = m0 + ty + SK_BM * r;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + (TB ? tx + 16 * j : tx * 4 + j);
+            if (n >= p.N) continue;
+            float v = acc[r][j];
+            float* c = C + (size_t)m * p.ldc + n;
+            if (p.accumulate == 2) v += *c;
+            if (bias) v += __ldg(bias + n);
+            if (p.relu) v = fmaxf(v, 0.0f);
+            if (p.accumulate == 1) v += *c;
+            const long nn = (long)b * p.sC + n;  // column inside the full output matrix
+            if (p.gate_y) {
+                const float gm = p.gate_mask ? __ldg(p.gate_mask + (size_t)m * p.ld_mask + nn) : p.gate_scale;
+                v = __ldg(p.gate_y + (size_t)m * p.ld_gate + nn) > 0.0f ? v * gm : 0.0f;
+            }
+            if (p.drop_mask) {
+                v *= __ldg(p.drop_mask + (size_t)m * p.drop_ld + nn);
+            } else if (p.drop_p > 0.0f) {
+                const unsigned int stp = p.drop_step ? (unsigned int)*p.drop_step : 0u;
+                const float keep = 1.0f - p.drop_p;
+                v = philox_uniform(p.drop_seed, p.drop_stream, stp, (unsigned long long)((size_t)m * p.drop_ld + nn)) <= keep ? v * (1.0f / keep) : 0.0f;
+            }
+            *c = v;
+            if (p.c_bf16) {
+                const __nv_bfloat16 hi = __float2bfloat16(v);
+                p.c_bf16[(size_t)m * p.ld_cbf16 + nn] = hi;
+                if (p.c_bf16_lo) p.c_bf16_lo[(size_t)m * p.ld_cbf16 + nn] = __float2bfloat16(v - __bfloat162float(hi));
+            }
         }
     }
 }
 
-template <bool TB>
-static int launch_smallk(const GemmParams& p, cudaStream_t st) {
+template <bool TB, int RPT>
+static int launch_smallk_rpt(const GemmParams& p, cudaStream_t st) {
+    constexpr int BM = SK_BM * RPT;
     const int Kp = (p.K + 3) / 4 * 4;
-    const size_t smem = sizeof(float) * ((size_t)SK_BM * (Kp + 4) + (TB ? (size_t)SK_BN * (Kp + 4) : (size_t)Kp * (SK_BN + 4)));
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        if (cudaFuncSetAttribute(gemm_smallk_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    const size_t smem = sizeof(float) * ((size_t)BM * (Kp + 4) + (TB ? (size_t)SK_BN * (Kp + 4) : (size_t)Kp * (SK_BN + 4)));
+    static size_t configured[64] = {};  // per device: the attribute belongs to the function ON a device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && smem > configured[dev & 63]) {
+        if (cudaFuncSetAttribute(gemm_smallk_kernel<TB, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return SPV_ERR_LAUNCH;
-        configured = smem;
+        configured[dev & 63] = smem;
     }
-    dim3 grid((p.N + SK_BN - 1) / SK_BN, (p.M + SK_BM - 1) / SK_BM, p.batch);
-    gemm_smallk_kernel<TB><<<grid, SK_THREADS, smem, st>>>(p);
+    dim3 grid((p.N + SK_BN - 1) / SK_BN, (p.M + BM - 1) / BM, p.batch);
+    gemm_smallk_kernel<TB, RPT><<<grid, SK_THREADS, smem, st>>>(p);
     SPV_CHECK_LAUNCH();
     return SPV_OK;
+}
+
+template <bool TB>
+static int launch_smallk(const GemmParams& p, cudaStream_t st) {
+    return p.M >= 1024 ? launch_smallk_rpt<TB, 4>(p, st) : launch_smallk_rpt<TB, 1>(p, st);
 }
 
 template <int SRC_A, bool TA, int SRC_B, bool TB>
