@@ -25,10 +25,12 @@
 // global-memory partials, no atomics, two cluster barriers instead of a second launch + "last CTA" pass.
 // ---------------------------------------------------------------------------------------
 #define ZS_CTAS 8
-#define ZS_ROWS 64
+// rows per shared-memory tile: template parameter ZS_ROWS = 64 / 128 / 256, the smallest that holds a CTA's slice (B / 8 rows) so
+// that the slice is read from global memory once and the passes run without tile loops (64-row tiles at B = 2048: 46 us)
 #define ZS_THREADS 256
 
 // rows [r0, r0 + nr) of zz into tile [ZS_ROWS][ldt] (zero rows beyond nr); all loads of a thread in flight before the stores
+template <int ZS_ROWS>
 __device__ __forceinline__ void zs_load_tile(float* tile, int ldt, const float* __restrict__ zz, long ld, int r0, int nr, int KZ) {
     const int total = ZS_ROWS * KZ;
     for (int base = 0; base < total; base += 12 * ZS_THREADS) {
@@ -48,6 +50,7 @@ __device__ __forceinline__ void zs_load_tile(float* tile, int ldt, const float* 
     }
 }
 
+template <int ZS_ROWS>
 __global__ void __cluster_dims__(ZS_CTAS, 1, 1) __launch_bounds__(ZS_THREADS)
     zstats_kernel(const float* __restrict__ zz, long ld, int B, int KZ, float* __restrict__ zsum_out,
                   float* __restrict__ zmean_out, float* __restrict__ zcov_out) {
@@ -72,7 +75,7 @@ __global__ void __cluster_dims__(ZS_CTAS, 1, 1) __launch_bounds__(ZS_THREADS)
     for (int r0 = r_begin; r0 < r_end || r0 == r_begin; r0 += ZS_ROWS) {
         const int nr = max(0, min(ZS_ROWS, r_end - r0));
         __syncthreads();
-        zs_load_tile(tile, ldt, zz, ld, r0, nr, KZ);
+        zs_load_tile<ZS_ROWS>(tile, ldt, zz, ld, r0, nr, KZ);
         __syncthreads();
         for (int k = lane; k < KZ; k += 32) {  // 8 row lanes per column, rows beyond nr are zero
             float s = 0.0f;
@@ -105,7 +108,7 @@ __global__ void __cluster_dims__(ZS_CTAS, 1, 1) __launch_bounds__(ZS_THREADS)
         const int nr = min(ZS_ROWS, r_end - r0);
         __syncthreads();
         if (!single) {
-            zs_load_tile(tile, ldt, zz, ld, r0, nr, KZ);
+            zs_load_tile<ZS_ROWS>(tile, ldt, zz, ld, r0, nr, KZ);
             __syncthreads();
         }
         for (int i = threadIdx.x; i < ZS_ROWS * KZ; i += ZS_THREADS) {
@@ -359,9 +362,20 @@ extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int
     const int KZ = P + S;
     const float* zz = (const float*)ptrs[11];
     if (training) {
-        size_t sm1 = (size_t)(ZS_ROWS * (KZ + 1) + 10 * KZ + KZ * KZ) * sizeof(float);
-        if (sm1 > 48 * 1024) cudaFuncSetAttribute(zstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
-        zstats_kernel<<<ZS_CTAS, ZS_THREADS, sm1, st>>>(zz, ld_zz, B, KZ, (float*)ptrs[12], (float*)ptrs[16], (float*)ptrs[17]);
+        const int chunk = (B + ZS_CTAS - 1) / ZS_CTAS;
+        const int zrows = chunk <= 64 ? 64 : (chunk <= 128 ? 128 : 256);
+        const size_t sm1 = (size_t)(zrows * (KZ + 1) + 10 * KZ + KZ * KZ) * sizeof(float);
+        float *zsum = (float*)ptrs[12], *zmean = (float*)ptrs[16], *zcov = (float*)ptrs[17];
+        if (zrows == 64) {
+            if (sm1 > 48 * 1024) cudaFuncSetAttribute(zstats_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+            zstats_kernel<64><<<ZS_CTAS, ZS_THREADS, sm1, st>>>(zz, ld_zz, B, KZ, zsum, zmean, zcov);
+        } else if (zrows == 128) {
+            if (sm1 > 48 * 1024) cudaFuncSetAttribute(zstats_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+            zstats_kernel<128><<<ZS_CTAS, ZS_THREADS, sm1, st>>>(zz, ld_zz, B, KZ, zsum, zmean, zcov);
+        } else {
+            if (sm1 > 48 * 1024) cudaFuncSetAttribute(zstats_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+            zstats_kernel<256><<<ZS_CTAS, ZS_THREADS, sm1, st>>>(zz, ld_zz, B, KZ, zsum, zmean, zcov);
+        }
         SPV_CHECK_LAUNCH();
     }
     FoldP p;
