@@ -188,7 +188,8 @@ int spv_loss(const float* rec0, const float* rec1, const float* klp0, const floa
              int B, const float* kl_weight, float* out, void* stream);
 
 /* decoder: closed-form per-gene BatchNorm fold + NB constants.
- * ptrs (18): Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, (unused), wfold, genec,
+ * ptrs (18): Wp, Ws, gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s, zz, zsum, scratch [ceil(B/64), (P+S) + (P+S)^2]
+ * (used when B > 512), wfold, genec,
  * zmean, zcov.  training != 0: zsum / zmean / zcov [P+S], [P+S], [P+S, P+S] are OUTPUTS (column sums, mean and biased
  * covariance of the latent minibatch zz [B, P+S], one cluster launch).   nn/networks.py:314-320, scvi FCLayers;
  * module/spVIPESmodule.py:758 */

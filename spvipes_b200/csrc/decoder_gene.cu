@@ -134,6 +134,86 @@ __global__ void __cluster_dims__(ZS_CTAS, 1, 1) __launch_bounds__(ZS_THREADS)
     cluster.sync();  // no CTA may exit while its shared memory is still being read by the others
 }
 
+// Larger minibatches (B > 512): the eight-CTA cluster above is bound by its own serial work (35-47 us at 2048 rows, on the critical
+// path before the decoders).  Instead: one CTA per 64 rows computes the tile's column sums and its second moments CENTRED ON THE
+// TILE'S OWN MEAN, and a merge kernel combines the tiles exactly (Chan et al.):
+//   Cov = [ sum_c M2_c + sum_c n_c (mean_c - mean)(mean_c - mean)^T ] / B.
+// Deterministic (fixed order), no atomics; part [tiles][KZ + KZ * KZ] is caller-provided scratch.
+__global__ void __launch_bounds__(ZS_THREADS) zstats_part_kernel(const float* __restrict__ zz, long ld, int B, int KZ, float* __restrict__ part) {
+    extern __shared__ float zs_sh[];
+    const int ldt = KZ + 1;
+    float* tile = zs_sh;               // [64][KZ + 1]
+    float* scratch = tile + 64 * ldt;  // [8][KZ]
+    float* lmean = scratch + 8 * KZ;   // [KZ]
+    const int r0 = blockIdx.x * 64, nr = min(64, B - r0);
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* out = part + (long)blockIdx.x * (KZ + KZ * KZ);
+    zs_load_tile<64>(tile, ldt, zz, ld, r0, nr, KZ);
+    __syncthreads();
+    for (int k = lane; k < KZ; k += 32) {  // 8 row lanes per column, rows beyond nr are zero
+        float s = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s += tile[(q + 8 * r) * ldt + k];
+        scratch[q * KZ + k] = s;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < KZ; k += ZS_THREADS) {
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += scratch[i * KZ + k];
+        out[k] = s;
+        lmean[k] = s / (float)nr;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * KZ; i += ZS_THREADS) {
+        const int r = i / KZ, k = i - r * KZ;
+        if (r < nr) tile[r * ldt + k] -= lmean[k];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < KZ * KZ; idx += ZS_THREADS) {
+        const int i = idx / KZ, j = idx - i * KZ;
+        float s = 0.0f;
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) s = fmaf(tile[r * ldt + i], tile[r * ldt + j], s);
+        out[KZ + idx] = s;
+    }
+}
+
+__global__ void __launch_bounds__(ZS_THREADS) zstats_merge_kernel(const float* __restrict__ part, int tiles, int B, int KZ,
+                                                                  float* __restrict__ zsum_out, float* __restrict__ zmean_out,
+                                                                  float* __restrict__ zcov_out) {
+    extern __shared__ float zm_sh[];
+    float* tot = zm_sh;      // [KZ] column sums of the whole minibatch
+    float* d = zm_sh + KZ;   // [tiles][KZ] tile mean - minibatch mean
+    const long pitch = KZ + (long)KZ * KZ;
+    const float invB = 1.0f / (float)B;
+    for (int k = threadIdx.x; k < KZ; k += ZS_THREADS) {
+        float s = 0.0f;
+        for (int c = 0; c < tiles; ++c) s += part[c * pitch + k];
+        tot[k] = s;
+        if (blockIdx.x == 0) {
+            zsum_out[k] = s;
+            zmean_out[k] = s * invB;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < tiles * KZ; i += ZS_THREADS) {
+        const int c = i / KZ, k = i - c * KZ;
+        const float n = (float)min(64, B - 64 * c);
+        d[i] = part[c * pitch + k] / n - tot[k] * invB;
+    }
+    __syncthreads();
+    const int idx = blockIdx.x * ZS_THREADS + threadIdx.x;
+    if (idx >= KZ * KZ) return;
+    const int i = idx / KZ, j = idx - i * KZ;
+    float s = 0.0f;
+    for (int c = 0; c < tiles; ++c) {
+        const float n = (float)min(64, B - 64 * c);
+        s += part[c * pitch + KZ + idx] + n * d[c * KZ + i] * d[c * KZ + j];
+    }
+    zcov_out[idx] = s * invB;
+}
+
 struct FoldP {
     const float *Wp, *Ws;
     const float* vec[9];  // per-gene vectors: gamma_p, beta_p, gamma_s, beta_s, px_r, rm_p, rv_p, rm_s, rv_s
@@ -364,19 +444,32 @@ extern "C" int spv_dec_fold(const void* const* ptrs, long long ld_zz, int B, int
     if (training) {
         const int chunk = (B + ZS_CTAS - 1) / ZS_CTAS;
         const int zrows = chunk <= 64 ? 64 : (chunk <= 128 ? 128 : 256);
-        const size_t sm1 = (size_t)(zrows * (KZ + 1) + 10 * KZ + KZ * KZ) * sizeof(float);
-        float *zsum = (float*)ptrs[12], *zmean = (float*)ptrs[16], *zcov = (float*)ptrs[17];
-        if (zrows == 64) {
-            if (sm1 > 48 * 1024) cudaFuncSetAttribute(zstats_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
-            zstats_kernel<64><<<ZS_CTAS, ZS_THREADS, sm1, st>>>(zz, ld_zz, B, KZ, zsum, zmean, zcov);
-        } else if (zrows == 128) {
-            if (sm1 > 48 * 1024) cudaFuncSetAttribute(zstats_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
-            zstats_kernel<128><<<ZS_CTAS, ZS_THREADS, sm1, st>>>(zz, ld_zz, B, KZ, zsum, zmean, zcov);
+        const int tiles = (B + 63) / 64;
+        const size_t sm_merge = (size_t)(KZ + tiles * KZ) * sizeof(float);
+        if (B > 512 && sm_merge <= 200 * 1024) {  // one CTA per 64 rows + an exact merge (scratch: ptrs[13])
+            float* part = (float*)ptrs[13];
+            const size_t sm_part = (size_t)(64 * (KZ + 1) + 9 * KZ) * sizeof(float);
+            zstats_part_kernel<<<tiles, ZS_THREADS, sm_part, st>>>(zz, ld_zz, B, KZ, part);
+            SPV_CHECK_LAUNCH();
+            if (sm_merge > 48 * 1024) cudaFuncSetAttribute(zstats_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_merge);
+            zstats_merge_kernel<<<(KZ * KZ + ZS_THREADS - 1) / ZS_THREADS, ZS_THREADS, sm_merge, st>>>(part, tiles, B, KZ, (float*)ptrs[12],
+                                                                                                   (float*)ptrs[16], (float*)ptrs[17]);
+            SPV_CHECK_LAUNCH();
         } else {
-            if (sm1 > 48 * 1024) cudaFuncSetAttribute(zstats_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
-            zstats_kernel<256><<<ZS_CTAS, ZS_THREADS, sm1, st>>>(zz, ld_zz, B, KZ, zsum, zmean, zcov);
+            const size_t sm1 = (size_t)(zrows * (KZ + 1) + 10 * KZ + KZ * KZ) * sizeof(float);
+            float *zsum = (float*)ptrs[12], *zmean = (float*)ptrs[16], *zcov = (float*)ptrs[17];
+            if (zrows == 64) {
+                if (sm1 > 48 * 1024) cudaFuncSetAttribute(zstats_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+                zstats_kernel<64><<<ZS_CTAS, ZS_THREADS, sm1, st>>>(zz, ld_zz, B, KZ, zsum, zmean, zcov);
+            } else if (zrows == 128) {
+                if (sm1 > 48 * 1024) cudaFuncSetAttribute(zstats_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+                zstats_kernel<128><<<ZS_CTAS, ZS_THREADS, sm1, st>>>(zz, ld_zz, B, KZ, zsum, zmean, zcov);
+            } else {
+                if (sm1 > 48 * 1024) cudaFuncSetAttribute(zstats_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+                zstats_kernel<256><<<ZS_CTAS, ZS_THREADS, sm1, st>>>(zz, ld_zz, B, KZ, zsum, zmean, zcov);
+            }
+            SPV_CHECK_LAUNCH();
         }
-        SPV_CHECK_LAUNCH();
     }
     FoldP p;
     p.Wp = (const float*)ptrs[0]; p.Ws = (const float*)ptrs[1];

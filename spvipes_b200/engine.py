@@ -230,8 +230,8 @@ class _GroupWS:
         self.zzb = f(B, KZb) if nb else None      # [z_private_arg | oh | z_shared_arg | oh] (batch covariates)
         self.oh = f(B, nb) if nb else None        # one-hot batch codes (fp32 path of the encoders' first layer)
         self.zsum, self.zmean, self.zcov = f(KZb), f(KZb), f(KZb, KZb)
-        # per-64-row partial second moments + one spare slot holding the "last CTA" ticket counter (must start at zero)
-        self.cov_part = torch.zeros(self.nTB + 1, KZb * KZb, dtype=torch.float32, device=dev)
+        # scratch of the latent statistics (spv_dec_fold, minibatches > 512 rows): per 64-row tile, column sums + centred second moments
+        self.cov_part = torch.zeros(self.nTB, KZb + KZb * KZb, dtype=torch.float32, device=dev)
         self.wfold, self.genec = f(G, KZb), f(L.GENEC_ROWS, G)
         self.ah = f(B, HD)
         self.bn_h_mean, self.bn_h_istd = f(HD), f(HD)
