@@ -253,10 +253,12 @@ extern "C" int spv_enc_mid_fwd(const float* h1, long long ld_h1, const float* W2
     p.r = r; p.ld_r = ld_r; p.drop_mask = drop_mask; p.ld_mask = ld_mask; p.drop_p = drop_mask ? 0.0f : drop_p; p.seed = seed;
     p.stream_id = stream_id; p.step = step; p.B = B; p.H = H; p.P2 = 2 * P; p.S2 = 2 * S;
     const size_t smem = em_smem(H);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[64] = {};  // per device: the attribute belongs to the function ON a device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
         if (cudaFuncSetAttribute(enc_mid_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SPV_ERR_LAUNCH;
-        configured = smem;
+        configured[dev & 63] = smem;
     }
     enc_mid_fwd_kernel<<<dim3((B + EM_ROWS - 1) / EM_ROWS, 2), EM_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     SPV_CHECK_LAUNCH();
@@ -278,10 +280,12 @@ extern "C" int spv_enc_mid_bwd(const float* dr, long long ld_dr, const float* Wh
     p.ld_dh1 = ld_dh1; p.dh1_bf16 = reinterpret_cast<__nv_bfloat16*>(dh1_bf16); p.ld_dh1b = ld_dh1b;
     p.B = B; p.H = H; p.P2 = 2 * P; p.S2 = 2 * S;
     const size_t smem = em_smem(H);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[64] = {};  // per device: the attribute belongs to the function ON a device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
         if (cudaFuncSetAttribute(enc_mid_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return SPV_ERR_LAUNCH;
-        configured = smem;
+        configured[dev & 63] = smem;
     }
     enc_mid_bwd_kernel<<<dim3((B + EM_ROWS - 1) / EM_ROWS, 2), EM_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     SPV_CHECK_LAUNCH();
